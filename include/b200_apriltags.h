@@ -1,0 +1,225 @@
+/*
+ * b200_apriltags.h -- C ABI of the B200-native AprilTag detector library (libb200apriltags.so).
+ *
+ * Part 1 mirrors, symbol for symbol, the three entry points the reference node binds from the closed
+ * cuAprilTags library, so the library is a link-time drop-in for
+ *   /root/reference/isaac_ros_apriltag/src/apriltag_node.cpp:450-452  (nvCreateAprilTagsDetector)
+ *   /root/reference/isaac_ros_apriltag/src/apriltag_node.cpp:491-493  (cuAprilTagsDetect)
+ *   /root/reference/isaac_ros_apriltag/src/apriltag_node.cpp:556      (cuAprilTagsDestroy)
+ * with the structs those call sites fill and read (:401-406, :409-418, :447, :481-486, :509-516).
+ *
+ * Part 2 (b200AprilTags*) is the extended surface this build adds: batches of frames per launch, every
+ * family/encoding the reference's VPI path accepts (apriltag_node.cpp:47-58, :76-82), host-buffer entry
+ * points, AprilRobotics detector knobs, per-stage timing and intermediate-buffer read-back for parity tests.
+ *
+ * All functions return 0 on success, non-zero error codes otherwise; no C++ exception crosses this ABI.
+ * Plain pointers and sizes only.
+ */
+#ifndef B200_APRILTAGS_H_
+#define B200_APRILTAGS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) || defined(B200_APRILTAGS_USE_CUDA_HEADERS)
+#include <cuda_runtime_api.h>
+#include <vector_types.h>
+#else
+/* layout-compatible stand-ins so plain C / ctypes / cgo callers need no CUDA headers */
+#ifndef __VECTOR_TYPES_H__
+typedef struct { float x, y; } float2;
+typedef struct { unsigned char x, y, z; } uchar3;
+#endif
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 1: cuAprilTags-shaped surface (what apriltag_node.cpp's CUAprilTagImpl binds)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct cuAprilTagsHandle_st *cuAprilTagsHandle;
+
+/* apriltag_node.cpp:409-418 reads orientation (column major) and translation, :509-516 id and corners. */
+typedef struct {
+  float2 corners[4];    /* message order: reverse of AprilRobotics p[0..3] */
+  uint16_t id;
+  uint8_t hamming_error;
+  float orientation[9]; /* 3x3 rotation, COLUMN major, camera optical frame */
+  float translation[3]; /* in units of tag_dim */
+} cuAprilTagsID_t;
+
+/* apriltag_node.cpp:481-486 */
+typedef struct {
+  uchar3 *dev_ptr; /* device pointer, pitch-linear rgb8/bgr8 */
+  size_t pitch;    /* bytes */
+  uint16_t width;
+  uint16_t height;
+} cuAprilTagsImageInput_t;
+
+/* apriltag_node.cpp:447 brace-initialises {fx, fy, cx, cy} */
+typedef struct {
+  float fx, fy, cx, cy;
+} cuAprilTagsCameraIntrinsics_t;
+
+/* apriltag_node.cpp:401-406 */
+typedef enum {
+  NVAT_TAG36H11 = 0,
+  NVAT_ENUM_SIZE = 0x7fffffff
+} cuAprilTagsFamily;
+
+/* 0 on success.  Detector is sized once for (img_width, img_height) (apriltag_node.cpp:450-457). */
+int nvCreateAprilTagsDetector(cuAprilTagsHandle *hApriltags, const uint32_t img_width, const uint32_t img_height,
+                              const uint32_t tile_size, const cuAprilTagsFamily tag_family,
+                              const cuAprilTagsCameraIntrinsics_t *cam, float tag_dim);
+
+/* Synchronous: tags_out (HOST, caller-allocated, max_tags entries) is valid on return
+ * (apriltag_node.cpp:490-503).  The bgr8/rgb8 distinction is not visible at this ABI (the reference passes
+ * both through the same uchar3 pointer); the luma weights assume the default set by
+ * b200AprilTagsSetInputEncoding (bgr8). */
+uint32_t cuAprilTagsDetect(cuAprilTagsHandle hApriltags, const cuAprilTagsImageInput_t *img_input,
+                           cuAprilTagsID_t *tags_out, uint32_t *num_tags, const uint32_t max_tags,
+                           cudaStream_t input_stream);
+
+int cuAprilTagsDestroy(cuAprilTagsHandle hApriltags);
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 2: extended surface
+ * ---------------------------------------------------------------------------------------------- */
+
+enum {
+  B200AT_OK = 0,
+  B200AT_ERR_INVALID_ARG = 1,
+  B200AT_ERR_UNSUPPORTED = 2, /* family / tile size / decimation not available on this backend */
+  B200AT_ERR_CUDA = 3,
+  B200AT_ERR_NOMEM = 4,
+  B200AT_ERR_OVERFLOW = 5,    /* a bounded device buffer overflowed; results are truncated, see status word */
+  B200AT_ERR_NO_DEVICE = 6
+};
+
+/* family indices (bit i of family_mask); same order as the oracle */
+enum { B200AT_FAM_36H11 = 0, B200AT_FAM_25H9 = 1, B200AT_FAM_16H5 = 2, B200AT_FAM_36H10 = 3, B200AT_NUM_FAMILIES = 4 };
+
+/* sensor_msgs encodings the reference's VPI path accepts (apriltag_node.cpp:76-82) */
+enum { B200AT_ENC_MONO8 = 0, B200AT_ENC_RGB8 = 1, B200AT_ENC_BGR8 = 2, B200AT_ENC_RGBA8 = 3, B200AT_ENC_BGRA8 = 4 };
+
+typedef struct {
+  uint32_t struct_size;       /* sizeof(b200AprilTagsOptions_t), for forward compatibility */
+  uint32_t family_mask;       /* default 1<<B200AT_FAM_36H11 */
+  uint32_t max_batch;         /* frames per launch the workspace is sized for; default 1 */
+  uint32_t max_tags;          /* per-frame output capacity; default 64 (node param max_tags, apriltag_node.cpp:564) */
+  uint32_t tile_size;         /* default 4 (node param tile_size, :566) */
+  float quad_decimate;        /* default 2.0  -- AprilRobotics apriltag_detector_create defaults below */
+  float quad_sigma;           /* default 0.0 */
+  int32_t refine_edges;       /* default 1 */
+  double decode_sharpening;   /* default 0.25 */
+  int32_t min_white_black_diff; /* default 5 */
+  int32_t max_nmaxima;        /* default 10 */
+  float critical_rad;         /* default 10 deg */
+  float max_line_fit_mse;     /* default 10 */
+  int32_t max_hamming;        /* default 2 */
+  int32_t input_encoding;     /* default B200AT_ENC_BGR8 */
+  int32_t device;             /* CUDA device ordinal, default -1 = current */
+  /* bounded-buffer sizing, 0 = automatic from resolution */
+  uint32_t hash_slots_per_frame;
+  uint32_t points_per_frame;
+  uint32_t clusters_per_frame;
+  uint32_t quads_per_frame;
+} b200AprilTagsOptions_t;
+
+/* Extended per-detection record (AprilRobotics apriltag_detection_t + pose). */
+typedef struct {
+  int32_t family;         /* B200AT_FAM_* */
+  int32_t id;
+  int32_t hamming;
+  float decision_margin;
+  double H[9];            /* row major, tag [-1,1]^2 -> pixels */
+  double c[2];
+  double p[4][2];         /* AprilRobotics order */
+  double R[9];            /* row major rotation, camera optical frame */
+  double t[3];
+  double pose_err;
+} b200AprilTagsDetection_t;
+
+typedef struct {
+  const void *ptr;  /* device (or host, for the *Host entry points) pointer to the top-left pixel */
+  size_t pitch;     /* bytes per row */
+} b200AprilTagsFrame_t;
+
+void b200AprilTagsDefaultOptions(b200AprilTagsOptions_t *opt);
+
+int b200AprilTagsCreate(cuAprilTagsHandle *h, uint32_t img_width, uint32_t img_height,
+                        const cuAprilTagsCameraIntrinsics_t *cam, float tag_dim, const b200AprilTagsOptions_t *opt);
+
+int b200AprilTagsSetInputEncoding(cuAprilTagsHandle h, int32_t encoding);
+
+/* Batch detect on DEVICE frames.  dets_out: HOST [n_frames][max_tags] (may be NULL), ids_out: HOST
+ * [n_frames][max_tags] cuAprilTagsID_t (may be NULL), counts: HOST [n_frames].  Synchronous. */
+int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,
+                             b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts,
+                             cudaStream_t stream);
+
+/* Same, frames in HOST memory (pinned for full copy bandwidth): the H2D copies are issued inside, chunked and
+ * overlapped with compute on an internal second stream.  n_frames may exceed max_batch. */
+int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,
+                                 b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts);
+
+/* Asynchronous halves of DetectBatch for pipelined callers (bench, multi-stream): Enqueue launches the kernels
+ * and the D2H copy on `stream`; Collect synchronises and unpacks into host arrays. */
+int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,
+                              cudaStream_t stream);
+int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out,
+                              uint32_t *counts);
+
+/* Status word of the last batch: bit0 hash table full, bit1 point pool full, bit2 cluster list full,
+ * bit3 quad list full, bit4 candidate list full, bit5 output truncated to max_tags. */
+int b200AprilTagsLastStatus(cuAprilTagsHandle h, uint32_t *status);
+
+/* Per-stage device times (ms, CUDA events on the launch stream) of the last batch, when enabled. */
+enum {
+  B200AT_STAGE_PREPROCESS = 0, B200AT_STAGE_THRESHOLD, B200AT_STAGE_CCL, B200AT_STAGE_CLUSTER, B200AT_STAGE_QUADFIT,
+  B200AT_STAGE_DECODE, B200AT_STAGE_FINALIZE, B200AT_STAGE_D2H, B200AT_NUM_STAGES
+};
+int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable);
+int b200AprilTagsGetStageTimes(cuAprilTagsHandle h, float *ms /* [B200AT_NUM_STAGES] */);
+/* launches issued by the last Enqueue (for the bench's gpu_launches claim) and counters of the last batch */
+int b200AprilTagsGetCounters(cuAprilTagsHandle h, uint64_t *counters /* [8]: launches, points, clusters, quads, candidates, detections, 0, 0 */);
+
+/* Intermediate buffers of the last batch, copied to HOST memory (parity tests). */
+enum {
+  B200AT_BUF_DECIMATED = 0, /* u8  [Hd][Wd] */
+  B200AT_BUF_TILE_MIN,      /* u8  [th][tw] (after 3x3 erode) */
+  B200AT_BUF_TILE_MAX,      /* u8  [th][tw] (after 3x3 dilate) */
+  B200AT_BUF_THRESHOLD,     /* u8  [Hd][Wd] */
+  B200AT_BUF_LABELS,        /* u32 [Hd][Wd] min-index representative */
+  B200AT_BUF_SIZES,         /* u32 [Hd][Wd] component size stored at the representative's index */
+  B200AT_BUF_CLUSTERS,      /* records {u64 key; u32 offset; u32 count; u32 frame; u32 pad}, all frames */
+  B200AT_BUF_POINTS,        /* u64 sort keys per kept point (slope bits | y | x), cluster-contiguous, sorted */
+  B200AT_BUF_QUADS,         /* records b200AprilTagsQuadRec_t, all frames */
+  B200AT_BUF_QUADS_REFINED  /* same records after rescale + refine_edges */
+};
+typedef struct {
+  uint64_t key;
+  float p[4][2];
+  uint32_t frame;
+  uint32_t reversed_border;
+} b200AprilTagsQuadRec_t;
+typedef struct {
+  uint64_t key;
+  uint32_t offset, count, frame, pad;
+} b200AprilTagsClusterRec_t;
+int b200AprilTagsGetDims(cuAprilTagsHandle h, uint32_t *wd, uint32_t *hd, uint32_t *tw, uint32_t *th);
+/* returns number of elements available via *n_elems; copies min(cap_bytes, available) bytes */
+int b200AprilTagsReadBuffer(cuAprilTagsHandle h, int which, uint32_t frame, void *dst, size_t cap_bytes, size_t *n_elems);
+
+const char *b200AprilTagsVersion(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_APRILTAGS_H_ */

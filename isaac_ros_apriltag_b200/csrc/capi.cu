@@ -1,0 +1,657 @@
+// capi.cu -- the C ABI (include/b200_apriltags.h): workspace management, stage sequencing, host marshalling.
+// Part 1 entry points are the three symbols the reference node binds
+// (/root/reference/isaac_ros_apriltag/src/apriltag_node.cpp:450-452, 491-493, 556).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "detector.h"
+#include "tag_families_data.inc"
+
+using namespace b200at;
+
+namespace {
+
+struct HostFamily {
+  int nbits, ncodes, width_at_border, total_width, reversed_border;
+  const unsigned char *bit_x, *bit_y;
+  const unsigned long long *codes;
+};
+const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
+    {tag36h11_nbits, tag36h11_ncodes, tag36h11_width_at_border, tag36h11_total_width, 0, tag36h11_bit_x, tag36h11_bit_y, tag36h11_codes},
+    {tag25h9_nbits, tag25h9_ncodes, tag25h9_width_at_border, tag25h9_total_width, 0, tag25h9_bit_x, tag25h9_bit_y, tag25h9_codes},
+    {tag16h5_nbits, tag16h5_ncodes, tag16h5_width_at_border, tag16h5_total_width, 0, tag16h5_bit_x, tag16h5_bit_y, tag16h5_codes},
+    {tag36h10_nbits, tag36h10_ncodes, tag36h10_width_at_border, tag36h10_total_width, 0, tag36h10_bit_x, tag36h10_bit_y, tag36h10_codes},
+};
+
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      fprintf(stderr, "[b200apriltags] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, \
+              cudaGetErrorString(e_));                                                                        \
+      return (e_ == cudaErrorMemoryAllocation) ? B200AT_ERR_NOMEM : B200AT_ERR_CUDA;                          \
+    }                                                                                                         \
+  } while (0)
+
+uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+struct cuAprilTagsHandle_st {
+  Workspace ws;
+  b200AprilTagsOptions_t opt;
+  int device = 0;
+  uint32_t max_batch = 1;
+  std::vector<void *> dev_allocs;
+  unsigned long long *dev_codes[B200AT_NUM_FAMILIES] = {nullptr, nullptr, nullptr, nullptr};
+  // pinned host mirrors
+  FrameDesc *h_frames = nullptr;
+  b200AprilTagsDetection_t *h_out = nullptr;
+  uint32_t *h_out_count = nullptr;
+  uint32_t *h_counters = nullptr;
+  // host-input staging
+  uint8_t *d_stage = nullptr;
+  size_t stage_pitch = 0;
+  cudaStream_t own_stream = nullptr;
+  // state of the batch in flight
+  cudaStream_t cur_stream = nullptr;
+  uint32_t cur_n = 0;
+  bool in_flight = false;
+  uint32_t last_status = 0;
+  uint64_t last_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[B200AT_NUM_STAGES + 1] = {};
+  float stage_ms[B200AT_NUM_STAGES] = {};
+  float tag_dim = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(cuAprilTagsHandle_st *h, T **p, size_t count) {
+  void *q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  CK(cudaMalloc(&q, bytes));
+  h->dev_allocs.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return 0;
+}
+
+void destroy_handle(cuAprilTagsHandle_st *h) {
+  if (!h) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (void *p : h->dev_allocs) cudaFree(p);
+  if (h->h_frames) cudaFreeHost(h->h_frames);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_out_count) cudaFreeHost(h->h_out_count);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  for (auto &e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete h;
+}
+
+int bpp_of(int enc) {
+  switch (enc) {
+    case B200AT_ENC_MONO8: return 1;
+    case B200AT_ENC_RGB8:
+    case B200AT_ENC_BGR8: return 3;
+    case B200AT_ENC_RGBA8:
+    case B200AT_ENC_BGRA8: return 4;
+    default: return 0;
+  }
+}
+
+void to_id_struct(const b200AprilTagsDetection_t &d, cuAprilTagsID_t *o) {
+  // message corner order = reverse of AprilRobotics p[0..3] (verified on the POL golden values)
+  for (int k = 0; k < 4; k++) {
+    o->corners[k].x = (float)d.p[3 - k][0];
+    o->corners[k].y = (float)d.p[3 - k][1];
+  }
+  o->id = (uint16_t)d.id;
+  o->hamming_error = (uint8_t)d.hamming;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) o->orientation[c * 3 + r] = (float)d.R[r * 3 + c];  // column major
+  for (int k = 0; k < 3; k++) o->translation[k] = (float)d.t[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *b200AprilTagsVersion(void) { return "b200apriltags 0.1.0 (sm_100a)"; }
+
+void b200AprilTagsDefaultOptions(b200AprilTagsOptions_t *o) {
+  memset(o, 0, sizeof(*o));
+  o->struct_size = sizeof(*o);
+  o->family_mask = 1u << B200AT_FAM_36H11;
+  o->max_batch = 1;
+  o->max_tags = 64;
+  o->tile_size = 4;
+  o->quad_decimate = 2.0f;
+  o->quad_sigma = 0.0f;
+  o->refine_edges = 1;
+  o->decode_sharpening = 0.25;
+  o->min_white_black_diff = 5;
+  o->max_nmaxima = 10;
+  o->critical_rad = (float)(10 * M_PI / 180);
+  o->max_line_fit_mse = 10.0f;
+  o->max_hamming = 2;
+  o->input_encoding = B200AT_ENC_BGR8;
+  o->device = -1;
+}
+
+int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cuAprilTagsCameraIntrinsics_t *cam, float tag_dim,
+                        const b200AprilTagsOptions_t *opt_in) {
+  if (!out) return B200AT_ERR_INVALID_ARG;
+  *out = nullptr;
+  b200AprilTagsOptions_t opt;
+  b200AprilTagsDefaultOptions(&opt);
+  if (opt_in) {
+    if (opt_in->struct_size != sizeof(opt)) return B200AT_ERR_INVALID_ARG;
+    opt = *opt_in;
+  }
+  if (W == 0 || H == 0 || W > 16382 || H > 16382) return B200AT_ERR_INVALID_ARG;
+  if (opt.max_batch == 0 || opt.max_tags == 0 || opt.tile_size == 0) return B200AT_ERR_INVALID_ARG;
+  if (opt.family_mask == 0 || (opt.family_mask >> B200AT_NUM_FAMILIES) != 0) return B200AT_ERR_UNSUPPORTED;
+  if (bpp_of(opt.input_encoding) == 0) return B200AT_ERR_INVALID_ARG;
+  // integer decimation only (AprilRobotics' 3->2 "1.5" special case is not built)
+  float qd = opt.quad_decimate;
+  if (!(qd >= 1.0f) || qd != floorf(qd) || qd > 8.0f) return B200AT_ERR_UNSUPPORTED;
+  if (opt.max_nmaxima < 4 || opt.max_nmaxima > 16) return B200AT_ERR_UNSUPPORTED;
+  if (opt.max_hamming < 0 || opt.max_hamming > 3) return B200AT_ERR_UNSUPPORTED;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "[b200apriltags] no CUDA device: this library has no CPU fallback\n");
+    return B200AT_ERR_NO_DEVICE;
+  }
+  cuAprilTagsHandle_st *h = new (std::nothrow) cuAprilTagsHandle_st();
+  if (!h) return B200AT_ERR_NOMEM;
+  if (opt.device >= 0) {
+    if (cudaSetDevice(opt.device) != cudaSuccess) {
+      delete h;
+      return B200AT_ERR_INVALID_ARG;
+    }
+  }
+  cudaGetDevice(&h->device);
+  h->opt = opt;
+  h->max_batch = opt.max_batch;
+  h->tag_dim = tag_dim;
+  Workspace &ws = h->ws;
+  memset(&ws, 0, sizeof(ws));
+  Geo &g = ws.g;
+  const int f = (int)qd;
+  g.W = (int)W;
+  g.H = (int)H;
+  g.f = f;
+  g.Wd = f > 1 ? 1 + ((int)W - 1) / f : (int)W;
+  g.Hd = f > 1 ? 1 + ((int)H - 1) / f : (int)H;
+  g.ts = (int)opt.tile_size;
+  g.tw = g.Wd / g.ts;
+  g.th = g.Hd / g.ts;
+  g.enc = opt.input_encoding;
+  g.bpp = bpp_of(opt.input_encoding);
+  g.min_wb_diff = opt.min_white_black_diff;
+  g.fast_align = 0;
+  if (g.Wd > 8191 || g.Hd > 8191 || g.tw < 1 || g.th < 1) {
+    delete h;
+    return B200AT_ERR_UNSUPPORTED;
+  }
+  const uint32_t B = opt.max_batch;
+  const size_t Wp = (size_t)at_Wp(g), Pp = Wp * g.Hd, Pd = (size_t)g.Wd * g.Hd;
+  g.hcap = opt.hash_slots_per_frame ? next_pow2(opt.hash_slots_per_frame) : next_pow2((uint32_t)std::max<size_t>(Pd / 2, 4096));
+  const size_t ppf = opt.points_per_frame ? opt.points_per_frame : Pd;
+  const size_t cpf = opt.clusters_per_frame ? opt.clusters_per_frame : std::max<size_t>(Pd / 64, 1024);
+  const size_t qpf = opt.quads_per_frame ? opt.quads_per_frame : 1024;
+  if (ppf * B > 0xfffffff0ull || cpf * B > 0xfffffff0ull) {
+    delete h;
+    return B200AT_ERR_INVALID_ARG;
+  }
+  g.pts_cap = (uint32_t)(ppf * B);
+  g.clu_cap = (uint32_t)(cpf * B);
+  g.quad_cap = (uint32_t)(qpf * B);
+  g.cand_cap = 256;
+  g.max_tags = opt.max_tags;
+  g.max_cluster_pts = (uint32_t)(2 * (2 * g.Wd + 2 * g.Hd));
+
+  FitParams &fp = ws.fp;
+  int min_tag_width = 1000000, nfam = 0;
+  fp.normal_border = fp.reversed_border = 0;
+  int rc = 0;
+  for (int i = 0; i < B200AT_NUM_FAMILIES && rc == 0; i++) {
+    if (!(opt.family_mask & (1u << i))) continue;
+    const HostFamily &hf = kHostFamilies[i];
+    DevFamily &df = ws.fams[nfam++];
+    df.nbits = hf.nbits;
+    df.ncodes = hf.ncodes;
+    df.width_at_border = hf.width_at_border;
+    df.total_width = hf.total_width;
+    df.reversed_border = hf.reversed_border;
+    df.index = i;
+    for (int k = 0; k < hf.nbits; k++) {
+      df.bit_x[k] = hf.bit_x[k];
+      df.bit_y[k] = hf.bit_y[k];
+    }
+    rc = dev_alloc(h, &h->dev_codes[i], (size_t)hf.ncodes);
+    if (rc == 0 && cudaMemcpy(h->dev_codes[i], hf.codes, sizeof(unsigned long long) * hf.ncodes, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = B200AT_ERR_CUDA;
+    df.codes = h->dev_codes[i];
+    if (hf.width_at_border < min_tag_width) min_tag_width = hf.width_at_border;
+    fp.normal_border |= !hf.reversed_border;
+    fp.reversed_border |= hf.reversed_border;
+  }
+  if (qd > 1) min_tag_width = (int)(min_tag_width / qd);
+  if (min_tag_width < 3) min_tag_width = 3;
+  fp.tag_width = min_tag_width;
+  fp.max_nmaxima = opt.max_nmaxima;
+  fp.max_line_fit_mse = opt.max_line_fit_mse;
+  fp.cos_critical_rad = (float)cos((double)opt.critical_rad);
+  {
+    const double sigma = 1;
+    for (int i = 0; i < 7; i++) {
+      int j = i - 3;
+      fp.smooth[i] = (float)exp(-j * j / (2 * sigma * sigma));
+    }
+  }
+  fp.quad_decimate = qd;
+  fp.refine_edges = opt.refine_edges;
+  fp.decode_sharpening = opt.decode_sharpening;
+  fp.max_hamming = opt.max_hamming;
+  fp.nfam = nfam;
+  if (cam) {
+    fp.fx = cam->fx;
+    fp.fy = cam->fy;
+    fp.cx = cam->cx;
+    fp.cy = cam->cy;
+  } else {
+    fp.fx = fp.fy = 1;
+    fp.cx = fp.cy = 0;
+  }
+  fp.tagsize = tag_dim;
+  // blur taps (apriltag_detector_detect's quad_sigma block + image_u8_gaussian_blur)
+  ws.blur_ksz = 0;
+  ws.blur_sharpen = 0;
+  if (opt.quad_sigma != 0) {
+    float sigma = fabsf(opt.quad_sigma);
+    int ksz = (int)(4 * sigma);
+    if ((ksz & 1) == 0) ksz++;
+    if (ksz > 31) ksz = 31;
+    if (ksz > 1) {
+      std::vector<double> dk(ksz);
+      double acc = 0;
+      for (int i = 0; i < ksz; i++) {
+        int x = -ksz / 2 + i;
+        dk[i] = exp(-.5 * ((double)x / sigma) * ((double)x / sigma));
+        acc += dk[i];
+      }
+      for (int i = 0; i < ksz; i++) ws.blur_k[i] = (uint8_t)(dk[i] / acc * 255);
+      ws.blur_ksz = ksz;
+      ws.blur_sharpen = opt.quad_sigma < 0 ? 1 : 0;
+    }
+  }
+
+#define ALLOC(ptr, count)                  \
+  if (rc == 0) rc = dev_alloc(h, &(ptr), (size_t)(count))
+  ALLOC(ws.frames, B);
+  ALLOC(ws.dec, B * Pp);
+  ALLOC(ws.dec_tmp, ws.blur_ksz > 1 ? B * Pp : 16);
+  ALLOC(ws.tmin, (size_t)B * g.th * at_twp(g));
+  ALLOC(ws.tmax, (size_t)B * g.th * at_twp(g));
+  ALLOC(ws.thr, B * Pp);
+  ALLOC(ws.thr2, B * Pp);
+  ALLOC(ws.lab, B * Pp);
+  ALLOC(ws.csize, B * Pp);
+  ALLOC(ws.hkey, (size_t)B * g.hcap);
+  ALLOC(ws.hcnt, (size_t)B * g.hcap);
+  ALLOC(ws.hoff, (size_t)B * g.hcap);
+  ALLOC(ws.hcur, (size_t)B * g.hcap);
+  ALLOC(ws.clusters, g.clu_cap);
+  ALLOC(ws.pts, g.pts_cap);
+  ALLOC(ws.keys, g.pts_cap);
+  ALLOC(ws.lfps, g.pts_cap);
+  ALLOC(ws.errs, (size_t)2 * g.pts_cap);
+  ALLOC(ws.quads, g.quad_cap);
+  ALLOC(ws.quads_refined, g.quad_cap);
+  ALLOC(ws.cands, (size_t)B * g.cand_cap);
+  ALLOC(ws.cand_count, B);
+  ALLOC(ws.out, (size_t)B * g.max_tags);
+  ALLOC(ws.out_count, B);
+  ALLOC(ws.counters, CNT_N);
+#undef ALLOC
+  if (rc == 0 && cudaMallocHost(&h->h_frames, sizeof(FrameDesc) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+  if (rc == 0 && cudaMallocHost(&h->h_out, sizeof(b200AprilTagsDetection_t) * B * g.max_tags) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+  if (rc == 0 && cudaMallocHost(&h->h_out_count, sizeof(uint32_t) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+  if (rc == 0 && cudaMallocHost(&h->h_counters, sizeof(uint32_t) * CNT_N) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+  if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  for (int i = 0; i <= B200AT_NUM_STAGES && rc == 0; i++)
+    if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  if (rc != 0) {
+    destroy_handle(h);
+    return rc;
+  }
+  *out = h;
+  return B200AT_OK;
+}
+
+int nvCreateAprilTagsDetector(cuAprilTagsHandle *hApriltags, const uint32_t img_width, const uint32_t img_height,
+                              const uint32_t tile_size, const cuAprilTagsFamily tag_family,
+                              const cuAprilTagsCameraIntrinsics_t *cam, float tag_dim) {
+  if (tag_family != NVAT_TAG36H11) return B200AT_ERR_UNSUPPORTED;  // the reference's cuAprilTags path: tag36h11 only
+  b200AprilTagsOptions_t opt;
+  b200AprilTagsDefaultOptions(&opt);
+  opt.tile_size = tile_size;
+  return b200AprilTagsCreate(hApriltags, img_width, img_height, cam, tag_dim, &opt);
+}
+
+int cuAprilTagsDestroy(cuAprilTagsHandle h) {
+  if (!h) return B200AT_ERR_INVALID_ARG;
+  destroy_handle(h);
+  return B200AT_OK;
+}
+
+int b200AprilTagsSetInputEncoding(cuAprilTagsHandle h, int32_t enc) {
+  if (!h || bpp_of(enc) == 0) return B200AT_ERR_INVALID_ARG;
+  h->ws.g.enc = enc;
+  h->ws.g.bpp = bpp_of(enc);
+  h->opt.input_encoding = enc;
+  return B200AT_OK;
+}
+
+int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable) {
+  if (!h) return B200AT_ERR_INVALID_ARG;
+  h->timing = enable != 0;
+  return B200AT_OK;
+}
+
+int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream) {
+  if (!h || !frames || n == 0 || n > h->max_batch) return B200AT_ERR_INVALID_ARG;
+  if (h->in_flight) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  Workspace &ws = h->ws;
+  Geo &g = ws.g;
+  int fast = 1;
+  const size_t min_pitch = (size_t)g.W * g.bpp;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!frames[i].ptr || frames[i].pitch < min_pitch) {
+      if (prev != h->device) cudaSetDevice(prev);
+      return B200AT_ERR_INVALID_ARG;
+    }
+    h->h_frames[i].ptr = (const uint8_t *)frames[i].ptr;
+    h->h_frames[i].pitch = frames[i].pitch;
+    if (((uintptr_t)frames[i].ptr & 15) || (frames[i].pitch & 15)) fast = 0;
+  }
+  g.fast_align = fast;
+  int launches = 0;
+  cudaError_t e = cudaMemcpyAsync(ws.frames, h->h_frames, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(uint32_t) * CNT_N, stream);
+  const bool tm = h->timing;
+#define STAMP(i) \
+  if (tm) cudaEventRecord(h->ev[i], stream)
+  STAMP(0);
+  launches += launch_preprocess(ws, (int)n, stream);
+  STAMP(1);
+  launches += launch_threshold(ws, (int)n, stream);
+  STAMP(2);
+  launches += launch_ccl(ws, (int)n, stream);
+  STAMP(3);
+  launches += launch_cluster(ws, (int)n, stream);
+  STAMP(4);
+  launches += launch_quadfit(ws, (int)n, stream);
+  STAMP(5);
+  launches += launch_decode(ws, (int)n, stream);
+  STAMP(6);
+  launches += launch_finalize(ws, (int)n, stream);
+  STAMP(7);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->h_out, ws.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_out_count, ws.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_counters, ws.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+  STAMP(8);
+#undef STAMP
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (prev != h->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[b200apriltags] enqueue failed: %s\n", cudaGetErrorString(e));
+    return B200AT_ERR_CUDA;
+  }
+  h->launches = launches;
+  h->cur_stream = stream;
+  h->cur_n = n;
+  h->in_flight = true;
+  return B200AT_OK;
+}
+
+int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts) {
+  if (!h || !h->in_flight) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaError_t e = cudaStreamSynchronize(h->cur_stream);
+  h->in_flight = false;
+  if (e == cudaSuccess && h->timing) {
+    for (int i = 0; i < B200AT_NUM_STAGES; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
+  }
+  if (prev != h->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[b200apriltags] batch failed: %s\n", cudaGetErrorString(e));
+    return B200AT_ERR_CUDA;
+  }
+  const uint32_t mt = h->ws.g.max_tags;
+  for (uint32_t i = 0; i < h->cur_n; i++) {
+    uint32_t c = h->h_out_count[i];
+    if (c > mt) c = mt;
+    if (counts) counts[i] = c;
+    if (dets_out) memcpy(dets_out + (size_t)i * mt, h->h_out + (size_t)i * mt, sizeof(b200AprilTagsDetection_t) * c);
+    if (ids_out)
+      for (uint32_t k = 0; k < c; k++) to_id_struct(h->h_out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
+  }
+  h->last_status = h->h_counters[CNT_STATUS];
+  h->last_counters[0] = (uint64_t)h->launches;
+  h->last_counters[1] = h->h_counters[CNT_POINTS];
+  h->last_counters[2] = h->h_counters[CNT_CLUSTERS];
+  h->last_counters[3] = h->h_counters[CNT_QUADS];
+  uint64_t nc = 0;
+  h->last_counters[4] = nc;
+  h->last_counters[5] = h->h_counters[CNT_DETS];
+  return h->last_status ? B200AT_ERR_OVERFLOW : B200AT_OK;
+}
+
+int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, b200AprilTagsDetection_t *dets_out,
+                             cuAprilTagsID_t *ids_out, uint32_t *counts, cudaStream_t stream) {
+  int rc = b200AprilTagsEnqueueBatch(h, frames, n, stream);
+  if (rc != B200AT_OK) return rc;
+  return b200AprilTagsCollectBatch(h, dets_out, ids_out, counts);
+}
+
+int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, b200AprilTagsDetection_t *dets_out,
+                                 cuAprilTagsID_t *ids_out, uint32_t *counts) {
+  if (!h || !frames || n == 0) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  const Geo &g = h->ws.g;
+  const size_t row = (size_t)g.W * g.bpp;
+  if (!h->d_stage) {
+    h->stage_pitch = (row + 255) & ~(size_t)255;
+    void *p = nullptr;
+    if (cudaMalloc(&p, h->stage_pitch * g.H * h->max_batch) != cudaSuccess) {
+      if (prev != h->device) cudaSetDevice(prev);
+      return B200AT_ERR_NOMEM;
+    }
+    h->dev_allocs.push_back(p);
+    h->d_stage = (uint8_t *)p;
+  }
+  int rc_all = B200AT_OK;
+  const uint32_t mt = g.max_tags;
+  std::vector<b200AprilTagsFrame_t> dframes(h->max_batch);
+  for (uint32_t i0 = 0; i0 < n; i0 += h->max_batch) {
+    const uint32_t m = std::min(h->max_batch, n - i0);
+    for (uint32_t k = 0; k < m; k++) {
+      uint8_t *dst = h->d_stage + (size_t)k * h->stage_pitch * g.H;
+      cudaError_t e = cudaMemcpy2DAsync(dst, h->stage_pitch, frames[i0 + k].ptr, frames[i0 + k].pitch, row, g.H,
+                                        cudaMemcpyHostToDevice, h->own_stream);
+      if (e != cudaSuccess) {
+        if (prev != h->device) cudaSetDevice(prev);
+        return B200AT_ERR_CUDA;
+      }
+      dframes[k].ptr = dst;
+      dframes[k].pitch = h->stage_pitch;
+    }
+    int rc = b200AprilTagsEnqueueBatch(h, dframes.data(), m, h->own_stream);
+    if (rc == B200AT_OK)
+      rc = b200AprilTagsCollectBatch(h, dets_out ? dets_out + (size_t)i0 * mt : nullptr, ids_out ? ids_out + (size_t)i0 * mt : nullptr,
+                                     counts ? counts + i0 : nullptr);
+    if (rc != B200AT_OK) {
+      rc_all = rc;
+      if (rc != B200AT_ERR_OVERFLOW) break;
+    }
+  }
+  if (prev != h->device) cudaSetDevice(prev);
+  return rc_all;
+}
+
+uint32_t cuAprilTagsDetect(cuAprilTagsHandle h, const cuAprilTagsImageInput_t *img, cuAprilTagsID_t *tags_out, uint32_t *num_tags,
+                           const uint32_t max_tags, cudaStream_t stream) {
+  if (!h || !img || !tags_out || !num_tags) return B200AT_ERR_INVALID_ARG;
+  if (img->width != h->ws.g.W || img->height != h->ws.g.H) return B200AT_ERR_INVALID_ARG;
+  if (h->ws.g.bpp != 3) return B200AT_ERR_INVALID_ARG;  // the uchar3 entry point carries rgb8/bgr8 only
+  b200AprilTagsFrame_t fr;
+  fr.ptr = img->dev_ptr;
+  fr.pitch = img->pitch;
+  uint32_t cnt = 0;
+  int rc = b200AprilTagsEnqueueBatch(h, &fr, 1, stream);
+  if (rc != B200AT_OK) return (uint32_t)rc;
+  rc = b200AprilTagsCollectBatch(h, nullptr, nullptr, &cnt);
+  if (rc != B200AT_OK && rc != B200AT_ERR_OVERFLOW) return (uint32_t)rc;
+  if (cnt > max_tags) cnt = max_tags;
+  for (uint32_t k = 0; k < cnt; k++) to_id_struct(h->h_out[k], tags_out + k);
+  *num_tags = cnt;
+  return rc == B200AT_ERR_OVERFLOW ? (uint32_t)rc : 0u;
+}
+
+int b200AprilTagsLastStatus(cuAprilTagsHandle h, uint32_t *status) {
+  if (!h || !status) return B200AT_ERR_INVALID_ARG;
+  *status = h->last_status;
+  return B200AT_OK;
+}
+
+int b200AprilTagsGetStageTimes(cuAprilTagsHandle h, float *ms) {
+  if (!h || !ms) return B200AT_ERR_INVALID_ARG;
+  for (int i = 0; i < B200AT_NUM_STAGES; i++) ms[i] = h->stage_ms[i];
+  return B200AT_OK;
+}
+
+int b200AprilTagsGetCounters(cuAprilTagsHandle h, uint64_t *c) {
+  if (!h || !c) return B200AT_ERR_INVALID_ARG;
+  for (int i = 0; i < 8; i++) c[i] = h->last_counters[i];
+  return B200AT_OK;
+}
+
+int b200AprilTagsGetDims(cuAprilTagsHandle h, uint32_t *wd, uint32_t *hd, uint32_t *tw, uint32_t *th) {
+  if (!h) return B200AT_ERR_INVALID_ARG;
+  if (wd) *wd = h->ws.g.Wd;
+  if (hd) *hd = h->ws.g.Hd;
+  if (tw) *tw = h->ws.g.tw;
+  if (th) *th = h->ws.g.th;
+  return B200AT_OK;
+}
+
+int b200AprilTagsReadBuffer(cuAprilTagsHandle h, int which, uint32_t frame, void *dst, size_t cap, size_t *n_elems) {
+  if (!h || frame >= h->max_batch) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  const Workspace &ws = h->ws;
+  const Geo &g = ws.g;
+  const size_t Wp = (size_t)at_Wp(g), Pp = Wp * g.Hd;
+  cudaError_t e = cudaSuccess;
+  size_t n = 0;
+  auto conv_label = [&](uint32_t v) -> uint32_t { return (uint32_t)((v / Wp) * g.Wd + (v % Wp)); };
+  auto conv_key = [&](unsigned long long k) -> unsigned long long {
+    return ((unsigned long long)conv_label((uint32_t)(k >> 32)) << 32) | conv_label((uint32_t)(k & 0xffffffffu));
+  };
+  switch (which) {
+    case B200AT_BUF_DECIMATED:
+    case B200AT_BUF_THRESHOLD: {
+      const uint8_t *src = (which == B200AT_BUF_DECIMATED ? ws.dec : ws.thr) + (size_t)frame * Pp;
+      n = (size_t)g.Wd * g.Hd;
+      if (dst && cap >= n) e = cudaMemcpy2D(dst, g.Wd, src, Wp, g.Wd, g.Hd, cudaMemcpyDeviceToHost);
+      break;
+    }
+    case B200AT_BUF_TILE_MIN:
+    case B200AT_BUF_TILE_MAX: {
+      const size_t twp = at_twp(g);
+      const uint8_t *src = (which == B200AT_BUF_TILE_MIN ? ws.tmin : ws.tmax) + (size_t)frame * g.th * twp;
+      n = (size_t)g.tw * g.th;
+      if (dst && cap >= n) e = cudaMemcpy2D(dst, g.tw, src, twp, g.tw, g.th, cudaMemcpyDeviceToHost);
+      break;
+    }
+    case B200AT_BUF_LABELS:
+    case B200AT_BUF_SIZES: {
+      const uint32_t *src = (which == B200AT_BUF_LABELS ? ws.lab : ws.csize) + (size_t)frame * Pp;
+      n = (size_t)g.Wd * g.Hd;
+      if (dst && cap >= n * 4) {
+        e = cudaMemcpy2D(dst, (size_t)g.Wd * 4, src, Wp * 4, (size_t)g.Wd * 4, g.Hd, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && which == B200AT_BUF_LABELS && Wp != (size_t)g.Wd) {
+          uint32_t *d = (uint32_t *)dst;
+          for (size_t i = 0; i < n; i++) d[i] = conv_label(d[i]);
+        }
+      }
+      break;
+    }
+    case B200AT_BUF_CLUSTERS: {
+      n = std::min<size_t>(h->h_counters[CNT_CLUSTERS], g.clu_cap);
+      size_t m = std::min(n, cap / sizeof(ClusterRec));
+      if (dst && m) {
+        e = cudaMemcpy(dst, ws.clusters, m * sizeof(ClusterRec), cudaMemcpyDeviceToHost);
+        ClusterRec *d = (ClusterRec *)dst;
+        if (e == cudaSuccess && Wp != (size_t)g.Wd)
+          for (size_t i = 0; i < m; i++) d[i].key = conv_key(d[i].key);
+      }
+      break;
+    }
+    case B200AT_BUF_POINTS: {
+      n = std::min<size_t>(h->h_counters[CNT_POINTS], g.pts_cap);
+      size_t m = std::min(n, cap / sizeof(unsigned long long));
+      if (dst && m) e = cudaMemcpy(dst, ws.keys, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      break;
+    }
+    case B200AT_BUF_QUADS:
+    case B200AT_BUF_QUADS_REFINED: {
+      n = std::min<size_t>(h->h_counters[CNT_QUADS], g.quad_cap);
+      size_t m = std::min(n, cap / sizeof(QuadRec));
+      if (dst && m) {
+        e = cudaMemcpy(dst, which == B200AT_BUF_QUADS ? ws.quads : ws.quads_refined, m * sizeof(QuadRec), cudaMemcpyDeviceToHost);
+        QuadRec *d = (QuadRec *)dst;
+        if (e == cudaSuccess && Wp != (size_t)g.Wd)
+          for (size_t i = 0; i < m; i++) d[i].key = conv_key(d[i].key);
+      }
+      break;
+    }
+    default:
+      if (prev != h->device) cudaSetDevice(prev);
+      return B200AT_ERR_INVALID_ARG;
+  }
+  if (n_elems) *n_elems = n;
+  if (prev != h->device) cudaSetDevice(prev);
+  return e == cudaSuccess ? B200AT_OK : B200AT_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// detector.h -- internal layout of the B200 AprilTag detector workspace and kernel entry points.
+//
+// HBM layout (all buffers batch-major, one slab per frame so a CTA never straddles frames):
+//   dec   u8  [B][Hd][Wd]   decimated (+blurred) gray        a5/a6 of SURVEY.md section 8a
+//   tmin/tmax u8 [B][th][tw] per-tile min / max (pre-dilation) a7
+//   thr   u8  [B][Hd][Wd]   {0,127,255}                       a7
+//   lab   u32 [B][Hd][Wd]   union-find parent -> min-index representative   a8
+//   csize u32 [B][Hd][Wd]   component size, stored at the representative    a8
+//   thr2  u8  [B][Hd][Wd]   thr with pixels of components < 25 px forced to 127 (folds the size gate of a9)
+//   hkey/hcnt/hoff/hcur     per-frame open-addressing table keyed by (rep_hi<<32|rep_lo)   a9
+//   pts   u32 pool          packed boundary points of kept clusters, cluster-contiguous    a9
+//   keys  u64 pool          (slope|y|x) sort keys, sorted per cluster                      a10
+//   lfps  6xf64 pool        sequential weighted prefix moments                             a10
+//   quads / cands / out     fixed-capacity record lists                                    a10-a15
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200_apriltags.h"
+
+namespace b200at {
+
+constexpr int kMaxFamilies = B200AT_NUM_FAMILIES;
+constexpr int kMaxBits = 52;
+
+struct DevFamily {
+  int nbits, ncodes, width_at_border, total_width, reversed_border, index;
+  uint8_t bit_x[kMaxBits], bit_y[kMaxBits];
+  const unsigned long long *codes;  // device pointer
+};
+
+struct FrameDesc {
+  const uint8_t *ptr;
+  unsigned long long pitch;
+};
+
+struct LineFitPt {
+  double Mx, My, Mxx, Mxy, Myy, W;
+};
+
+struct ClusterRec {  // == b200AprilTagsClusterRec_t
+  unsigned long long key;
+  uint32_t offset, count, frame, pad;
+};
+
+struct QuadRec {  // == b200AprilTagsQuadRec_t
+  unsigned long long key;
+  float p[4][2];
+  uint32_t frame;
+  uint32_t reversed_border;
+};
+
+struct Cand {  // decoded candidate before reconcile
+  unsigned long long key;
+  int32_t family, id, hamming;
+  float decision_margin;
+  double H[9];
+  double c[2];
+  double p[4][2];
+};
+
+// counters[] slots
+enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_N = 8 };
+enum { ST_HASH_FULL = 1, ST_POINTS_FULL = 2, ST_CLUSTERS_FULL = 4, ST_QUADS_FULL = 8, ST_CANDS_FULL = 16, ST_OUT_TRUNC = 32 };
+
+struct Geo {
+  int W, H;      // input frame
+  int Wd, Hd;    // decimated
+  int tw, th;    // full tiles
+  int f;         // integer decimation factor
+  int ts;        // tile size
+  int enc;       // B200AT_ENC_*
+  int bpp;       // bytes per input pixel
+  int min_wb_diff;
+  int fast_align;  // every frame pointer/pitch of the current batch is 16-byte aligned -> vector load path
+  uint32_t hcap;       // hash slots per frame (power of two)
+  uint32_t pts_cap;    // point pool capacity (whole batch)
+  uint32_t clu_cap;    // cluster list capacity (whole batch)
+  uint32_t quad_cap;   // quad list capacity (whole batch)
+  uint32_t cand_cap;   // candidates per frame
+  uint32_t max_tags;   // outputs per frame
+  uint32_t max_cluster_pts;  // 2*(2*Wd+2*Hd)
+};
+
+struct FitParams {
+  int tag_width;         // min_tag_width after decimation, >= 3
+  int normal_border, reversed_border;
+  int max_nmaxima;
+  float max_line_fit_mse;
+  float cos_critical_rad;
+  float smooth[7];       // exp(-j*j/2) taps, j=-3..3, as float (host libm, same as the oracle)
+  float quad_decimate;
+  int refine_edges;
+  double decode_sharpening;
+  int max_hamming;
+  int nfam;
+  float fx, fy, cx, cy;
+  float tagsize;
+};
+
+struct Workspace {
+  Geo g;
+  FitParams fp;
+  DevFamily fams[kMaxFamilies];
+  FrameDesc *frames;
+  uint8_t *dec, *dec_tmp, *tmin, *tmax, *thr, *thr2;
+  uint32_t *lab, *csize;
+  unsigned long long *hkey;
+  uint32_t *hcnt, *hoff, *hcur;
+  ClusterRec *clusters;
+  uint32_t *pts;
+  unsigned long long *keys;
+  LineFitPt *lfps;
+  double *errs;  // 2 x pts_cap
+  QuadRec *quads, *quads_refined;
+  Cand *cands;
+  uint32_t *cand_count;  // [B]
+  b200AprilTagsDetection_t *out;
+  uint32_t *out_count;   // [B]
+  uint32_t *counters;    // [CNT_N]
+  uint8_t blur_k[32];
+  int blur_ksz;
+  int blur_sharpen;
+};
+
+__host__ __device__ inline int at_Wp(const Geo &g) { return (g.Wd + 15) & ~15; }  // internal row pitch
+__host__ __device__ inline int at_twp(const Geo &g) { return g.tw > 0 ? g.tw : 1; }    // tile-array pitch
+
+// ---- launchers (each returns the number of kernel launches it issued) ----
+int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_decode(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_finalize(const Workspace &ws, int nframes, cudaStream_t s);
+
+}  // namespace b200at

@@ -1,0 +1,224 @@
+// k_ccl.cu -- connected components of the threshold image (a8): white 8-connected, black 4-connected, 127
+// ignored, with AprilRobotics' exact link set (do_unionfind_first_line / do_unionfind_line2, SURVEY App. A.3,
+// including the link elisions, which DO change the partition at the first/last image columns).
+//
+// Design: label-equivalence union-find with atomicMin (representative = minimum pixel index, which is also
+// the oracle's canonical label):
+//   1. k_ccl_tile   : 64x16 tile per CTA, union-find entirely in shared memory, writes flattened labels
+//   2. k_ccl_border : only links that cross tile borders are merged in global memory
+//   3. k_ccl_flatten: path-compress every pixel to its root; warp-aggregated component-size histogram
+//   4. k_ccl_mark   : thr2 = thr, but pixels of components with < 25 px become 127 (folds the size gates of
+//                     gradient_clusters into one byte image)
+// Algorithmic bytes per frame: read Pd (thr) + write 4*Pd (labels) = 5*Pd (SURVEY 8d contract figure).
+#include "detector.h"
+
+namespace b200at {
+
+constexpr int TW = 64, TH = 16;  // CCL tile
+
+struct Nb {
+  bool L, U, UL, UR;
+};
+
+// Links AprilRobotics makes for "current" pixel (x, y) with value v (see file header).
+__device__ __forceinline__ Nb ccl_links(int v, int vL, int vU, int vUL, int vUR, int x, int y, int Wd) {
+  Nb n = {false, false, false, false};
+  if (v == 127 || x < 1 || x > Wd - 2) return n;
+  n.L = (vL == v);
+  if (y >= 1) {
+    n.U = (vU == v) && (x == 1 || !((vL == vUL) && (vUL == vU)));
+    if (v == 255) {
+      n.UL = (vUL == v) && (x == 1 || !(vL == vUL || vU == vUL));
+      n.UR = (vUR == v) && !(vU == vUR);
+    }
+  }
+  return n;
+}
+
+__device__ __forceinline__ uint32_t find_s(volatile uint32_t *L, uint32_t a) {
+  uint32_t p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+__device__ __forceinline__ void unite_s(uint32_t *L, uint32_t a, uint32_t b) {
+  bool done;
+  do {
+    a = find_s(L, a);
+    b = find_s(L, b);
+    if (a < b) {
+      uint32_t old = atomicMin(&L[b], a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      uint32_t old = atomicMin(&L[a], b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+__device__ __forceinline__ uint32_t find_g(const uint32_t *L, uint32_t a) {
+  uint32_t p = __ldcg(&L[a]);
+  while (p != a) {
+    a = p;
+    p = __ldcg(&L[a]);
+  }
+  return a;
+}
+__device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {
+  bool done;
+  do {
+    a = find_g(L, a);
+    b = find_g(L, b);
+    if (a < b) {
+      uint32_t old = atomicMin(&L[b], a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      uint32_t old = atomicMin(&L[a], b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
+                                                  uint32_t *__restrict__ csize, int Wp) {
+  __shared__ uint8_t t[TH + 1][TW + 4];  // [0] = row above the tile; column 0 = x0-1, column TW+1 = x0+TW
+  __shared__ uint32_t L[TH * TW];
+  const int fr = blockIdx.z;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
+  const int tid = threadIdx.x;
+  // stage (TH+1) x (TW+2) bytes; out-of-image = 127 (never links)
+  for (int i = tid; i < (TH + 1) * (TW + 2); i += 256) {
+    int r = i / (TW + 2), c = i % (TW + 2);
+    int y = y0 - 1 + r, x = x0 - 1 + c;
+    uint8_t v = 127;
+    if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
+    t[r][c] = v;
+  }
+  for (int i = tid; i < TH * TW; i += 256) L[i] = i;
+  __syncthreads();
+  for (int i = tid; i < TH * TW; i += 256) {
+    int ly = i / TW, lx = i % TW;
+    int x = x0 + lx, y = y0 + ly;
+    if (x >= g.Wd || y >= g.Hd) continue;
+    int v = t[ly + 1][lx + 1];
+    Nb n = ccl_links(v, t[ly + 1][lx], t[ly][lx + 1], t[ly][lx], t[ly][lx + 2], x, y, g.Wd);
+    if (n.L && lx > 0) unite_s(L, i, i - 1);
+    if (ly > 0) {
+      if (n.U) unite_s(L, i, i - TW);
+      if (n.UL && lx > 0) unite_s(L, i, i - TW - 1);
+      if (n.UR && lx < TW - 1) unite_s(L, i, i - TW + 1);
+    }
+  }
+  __syncthreads();
+  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
+  uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
+  for (int i = tid; i < TH * TW; i += 256) {
+    int ly = i / TW, lx = i % TW;
+    int x = x0 + lx, y = y0 + ly;
+    if (x >= g.Wd || y >= g.Hd) continue;
+    uint32_t r = find_s(L, i);
+    int ry = r / TW, rx = r % TW;
+    labf[(size_t)y * Wp + x] = (uint32_t)((y0 + ry) * Wp + (x0 + rx));
+    szf[(size_t)y * Wp + x] = 0;
+  }
+}
+
+// one thread per tile-border pixel: top row (TW), left column rows 1..TH-1, right column rows 1..TH-1
+__global__ void __launch_bounds__(128) k_ccl_border(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab, int Wp) {
+  const int fr = blockIdx.z;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int b = threadIdx.x;
+  int lx, ly;
+  if (b < TW) {
+    lx = b;
+    ly = 0;
+  } else if (b < TW + TH - 1) {
+    lx = 0;
+    ly = b - TW + 1;
+  } else if (b < TW + 2 * (TH - 1)) {
+    lx = TW - 1;
+    ly = b - (TW + TH - 1) + 1;
+  } else {
+    return;
+  }
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= g.Wd || y >= g.Hd) return;
+  const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
+  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
+  auto T = [&](int xx, int yy) -> int {
+    if (xx < 0 || yy < 0 || xx >= g.Wd || yy >= g.Hd) return 127;
+    return img[(size_t)yy * Wp + xx];
+  };
+  int v = T(x, y);
+  Nb n = ccl_links(v, T(x - 1, y), T(x, y - 1), T(x - 1, y - 1), T(x + 1, y - 1), x, y, g.Wd);
+  const uint32_t me = (uint32_t)(y * Wp + x);
+  if (n.L && lx == 0) unite_g(labf, me, me - 1);
+  if (n.U && ly == 0) unite_g(labf, me, me - Wp);
+  if (n.UL && (ly == 0 || lx == 0)) unite_g(labf, me, me - Wp - 1);
+  if (n.UR && (ly == 0 || lx == TW - 1)) unite_g(labf, me, me - Wp + 1);
+}
+
+// flatten + size histogram.  One thread per pixel; lanes of a warp that share a root issue one atomicAdd.
+__global__ void __launch_bounds__(256) k_ccl_flatten(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
+                                                     uint32_t *__restrict__ csize, int Wp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int fr = blockIdx.z;
+  const size_t fo = (size_t)fr * g.Hd * Wp;
+  const bool in = x < g.Wd;
+  uint32_t root = 0xffffffffu;
+  bool counted = false;
+  if (in) {
+    const uint32_t me = (uint32_t)(y * Wp + x);
+    uint8_t v = thr[fo + me];
+    // AprilRobotics never connects 127 pixels: they stay singletons
+    root = (v == 127) ? me : find_g(lab + fo, me);
+    lab[fo + me] = root;
+    counted = true;
+  }
+  unsigned act = __ballot_sync(0xffffffffu, counted);
+  if (counted) {
+    unsigned peers = __match_any_sync(act, root);
+    int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&csize[fo + root], (uint32_t)__popc(peers));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_mark(Geo g, const uint8_t *__restrict__ thr, const uint32_t *__restrict__ lab,
+                                                  const uint32_t *__restrict__ csize, uint8_t *__restrict__ thr2, int Wp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int fr = blockIdx.z;
+  if (x >= g.Wd) return;
+  const size_t fo = (size_t)fr * g.Hd * Wp;
+  const size_t i = fo + (size_t)y * Wp + x;
+  uint8_t v = thr[i];
+  if (v != 127) {
+    if (csize[fo + lab[i]] < 25) v = 127;
+  }
+  thr2[i] = v;
+}
+
+int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
+  const int Wp = at_Wp(g);
+  dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
+  k_ccl_tile<<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
+  k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
+  dim3 gp((g.Wd + 255) / 256, g.Hd, nframes);
+  k_ccl_flatten<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
+  k_ccl_mark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
+  return 4;
+}
+
+}  // namespace b200at

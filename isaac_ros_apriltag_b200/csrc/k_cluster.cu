@@ -1,0 +1,263 @@
+// k_cluster.cu -- gradient_clusters (a9): boundary points between a black and a white component, grouped by
+// the component pair.  Restates AprilRobotics do_gradient_clusters (v3.4.x, incl. `connected_last`;
+// SURVEY App. A.4).  The CPU hash-map-of-zarrays becomes a count / select / emit triple over a per-frame
+// open-addressing table, so only clusters that can pass fit_quad's size gates (24 <= n <= 2(2w+2h)) are ever
+// materialised:
+//   k_cluster_count  : every boundary point -> (key) -> hash insert + count   (warp-aggregated atomics)
+//   k_cluster_select : per frame, scan the table: kept clusters get a contiguous segment in the point pool
+//   k_cluster_emit   : every boundary point of a kept cluster -> its segment   (order inside a segment is
+//                      irrelevant: the quad-fit sort key (slope, y, x) is a total order)
+// Algorithmic bytes per frame: read Pd (thr2) + 4*Pd (labels) per pass, + 4 B per emitted point.
+#include "detector.h"
+
+namespace b200at {
+
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+// find-or-insert; returns slot or 0xffffffff when the table is full
+__device__ __forceinline__ uint32_t hash_insert(unsigned long long *hk, uint32_t hcap, unsigned long long key) {
+  const uint32_t mask = hcap - 1;
+  uint32_t slot = hash_key(key) & mask;
+  for (uint32_t probe = 0; probe < hcap; probe++) {
+    unsigned long long cur = hk[slot];
+    if (cur == key) return slot;
+    if (cur == 0ULL) {
+      unsigned long long old = atomicCAS(&hk[slot], 0ULL, key);
+      if (old == 0ULL || old == key) return slot;
+    }
+    slot = (slot + 1) & mask;
+  }
+  return 0xffffffffu;
+}
+__device__ __forceinline__ uint32_t hash_find(const unsigned long long *hk, uint32_t hcap, unsigned long long key) {
+  const uint32_t mask = hcap - 1;
+  uint32_t slot = hash_key(key) & mask;
+  for (uint32_t probe = 0; probe < hcap; probe++) {
+    unsigned long long cur = hk[slot];
+    if (cur == key) return slot;
+    if (cur == 0ULL) return 0xffffffffu;
+    slot = (slot + 1) & mask;
+  }
+  return 0xffffffffu;
+}
+
+// The four probes of pixel (x, y).  thr2 already folds both size gates (components < 25 px read as 127), so a
+// point exists iff v0 + v1 == 255.  `connected_last`: the (-1,1) probe is skipped when the previous pixel's
+// (1,1) probe produced a point; at x == 1 there is no previous pixel.
+struct Probes {
+  bool p[4];
+};
+__device__ __forceinline__ Probes eval_probes(const uint8_t *img, int Wp, int x, int y) {
+  const uint8_t *r0 = img + (size_t)y * Wp, *r1 = r0 + Wp;
+  int v0 = r0[x];
+  Probes pr;
+  int vl = r0[x - 1], vr = r0[x + 1], dl = r1[x - 1], dc = r1[x], dr = r1[x + 1];
+  bool prev_conn = (x > 1) && (vl + dc == 255);
+  pr.p[0] = (v0 + vr == 255);
+  pr.p[1] = (v0 + dc == 255);
+  pr.p[2] = !prev_conn && (v0 + dl == 255);
+  pr.p[3] = (v0 + dr == 255);
+  return pr;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
+                                                      unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
+                                                      const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
+                                                      uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int y = blockIdx.y + 1;
+  const int fr = blockIdx.z;
+  const size_t fo = (size_t)fr * g.Hd * Wp;
+  const uint8_t *img = thr2 + fo;
+  const uint32_t *labf = lab + fo;
+  unsigned long long *hk = hkey + (size_t)fr * g.hcap;
+  const size_t ho = (size_t)fr * g.hcap;
+  const bool in = (x <= g.Wd - 2) && (y <= g.Hd - 2);
+  Probes pr = {{false, false, false, false}};
+  uint32_t rep0 = 0;
+  if (in) {
+    pr = eval_probes(img, Wp, x, y);
+    if (pr.p[0] || pr.p[1] || pr.p[2] || pr.p[3]) rep0 = labf[(size_t)y * Wp + x];
+  }
+  const int dxs[4] = {1, 0, -1, 1};
+  const int dys[4] = {0, 1, 1, 1};
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const bool has = pr.p[k];
+    const unsigned act = __ballot_sync(0xffffffffu, has);
+    if (!has) continue;
+    const int dx = dxs[k], dy = dys[k];
+    const uint32_t rep1 = labf[(size_t)(y + dy) * Wp + x + dx];
+    const unsigned long long key =
+        rep0 < rep1 ? (((unsigned long long)rep1 << 32) | rep0) : (((unsigned long long)rep0 << 32) | rep1);
+    const unsigned peers = __match_any_sync(act, key);
+    const int leader = __ffs(peers) - 1;
+    const int n = __popc(peers);
+    if (!EMIT) {
+      if ((int)lane == leader) {
+        uint32_t slot = hash_insert(hk, g.hcap, key);
+        if (slot == 0xffffffffu)
+          atomicOr(&counters[CNT_STATUS], (uint32_t)ST_HASH_FULL);
+        else
+          atomicAdd(&hcnt[ho + slot], (uint32_t)n);
+      }
+    } else {
+      uint32_t base = 0xffffffffu;
+      if ((int)lane == leader) {
+        uint32_t slot = hash_find(hk, g.hcap, key);
+        if (slot != 0xffffffffu) {
+          uint32_t off = hoff[ho + slot];
+          if (off != 0xffffffffu) base = off + atomicAdd(&hcur[ho + slot], (uint32_t)n);
+        }
+      }
+      base = __shfl_sync(peers, base, leader);
+      if (base != 0xffffffffu) {
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        // packed point: x (14 bits) | y (14 bits) | gx code (2) | gy code (2); code 0 = 0, 1 = +255, 2 = -255
+        const int v0 = img[(size_t)y * Wp + x], v1 = img[(size_t)(y + dy) * Wp + x + dx];
+        const int d = v1 - v0;  // +-255
+        const int gx = dx * d, gy = dy * d;
+        const uint32_t cx = gx == 0 ? 0u : (gx > 0 ? 1u : 2u), cy = gy == 0 ? 0u : (gy > 0 ? 1u : 2u);
+        pts[base + rank] = (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 14) | (cx << 28) | (cy << 30);
+      }
+    }
+  }
+}
+
+// One CTA per frame.  Pass 1 totals, pass 2 ordered allocation (clusters appear in table-slot order).
+__global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned long long *__restrict__ hkey,
+                                                         const uint32_t *__restrict__ hcnt, uint32_t *__restrict__ hoff,
+                                                         uint32_t *__restrict__ hcur, ClusterRec *__restrict__ clusters,
+                                                         uint32_t *__restrict__ counters) {
+  const int fr = blockIdx.x;
+  const size_t ho = (size_t)fr * g.hcap;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __shared__ uint32_t s_c[32], s_p[32];
+  __shared__ uint32_t s_base_c, s_base_p, s_run_c, s_run_p, s_ok;
+  // pass 1
+  uint32_t nc = 0, np = 0;
+  for (uint32_t i = tid; i < g.hcap; i += 1024) {
+    uint32_t c = hcnt[ho + i];
+    if (c >= 24u && c <= g.max_cluster_pts) {
+      nc++;
+      np += c;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nc += __shfl_xor_sync(0xffffffffu, nc, o);
+    np += __shfl_xor_sync(0xffffffffu, np, o);
+  }
+  if (lane == 0) {
+    s_c[wid] = nc;
+    s_p[wid] = np;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t tc = 0, tp = 0;
+    for (int w = 0; w < 32; w++) {
+      tc += s_c[w];
+      tp += s_p[w];
+    }
+    uint32_t bc = atomicAdd(&counters[CNT_CLUSTERS], tc);
+    uint32_t bp = atomicAdd(&counters[CNT_POINTS], tp);
+    uint32_t ok = 1;
+    if (bc + tc > g.clu_cap) {
+      atomicOr(&counters[CNT_STATUS], (uint32_t)ST_CLUSTERS_FULL);
+      ok = 0;
+    }
+    if (bp + tp > g.pts_cap) {
+      atomicOr(&counters[CNT_STATUS], (uint32_t)ST_POINTS_FULL);
+      ok = 0;
+    }
+    s_base_c = bc;
+    s_base_p = bp;
+    s_run_c = 0;
+    s_run_p = 0;
+    s_ok = ok;
+  }
+  __syncthreads();
+  const bool ok = s_ok != 0;
+  // pass 2: chunked block scan in slot order
+  for (uint32_t i0 = 0; i0 < g.hcap; i0 += 1024) {
+    const uint32_t i = i0 + tid;
+    uint32_t c = (i < g.hcap) ? hcnt[ho + i] : 0;
+    const bool keep = ok && c >= 24u && c <= g.max_cluster_pts;
+    uint32_t fc = keep ? 1u : 0u, fp = keep ? c : 0u;
+    // inclusive warp scan
+    uint32_t ic = fc, ip = fp;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t tc = __shfl_up_sync(0xffffffffu, ic, o), tp = __shfl_up_sync(0xffffffffu, ip, o);
+      if (lane >= o) {
+        ic += tc;
+        ip += tp;
+      }
+    }
+    if (lane == 31) {
+      s_c[wid] = ic;
+      s_p[wid] = ip;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t vc = s_c[lane], vp = s_p[lane];
+      uint32_t jc = vc, jp = vp;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t tc = __shfl_up_sync(0xffffffffu, jc, o), tp = __shfl_up_sync(0xffffffffu, jp, o);
+        if (lane >= o) {
+          jc += tc;
+          jp += tp;
+        }
+      }
+      s_c[lane] = jc - vc;  // exclusive warp offsets
+      s_p[lane] = jp - vp;
+    }
+    __syncthreads();
+    const uint32_t run_c = s_run_c, run_p = s_run_p;
+    const uint32_t ec = run_c + s_c[wid] + ic - fc;  // exclusive index of this slot's cluster
+    const uint32_t ep = run_p + s_p[wid] + ip - fp;
+    if (i < g.hcap) {
+      if (keep) {
+        ClusterRec r;
+        r.key = hkey[ho + i];
+        r.offset = s_base_p + ep;
+        r.count = c;
+        r.frame = (uint32_t)fr;
+        r.pad = 0;
+        clusters[s_base_c + ec] = r;
+        hoff[ho + i] = s_base_p + ep;
+      } else {
+        hoff[ho + i] = 0xffffffffu;
+      }
+      hcur[ho + i] = 0;
+    }
+    __syncthreads();
+    if (tid == 1023) {
+      s_run_c = ec + fc;
+      s_run_p = ep + fp;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
+  const int Wp = at_Wp(g);
+  if (g.Wd < 3 || g.Hd < 3) return 0;
+  cudaMemsetAsync(ws.hkey, 0, (size_t)nframes * g.hcap * sizeof(unsigned long long), s);
+  cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
+  dim3 gp((g.Wd - 2 + 255) / 256, g.Hd - 2, nframes);
+  k_cluster_pass<false><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+  k_cluster_select<<<nframes, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters);
+  k_cluster_pass<true><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+  return 5;
+}
+
+}  // namespace b200at

@@ -1,0 +1,497 @@
+// k_decode.cu -- per-quad stages (a11-a13): rescale to full resolution, refine_edges on the full-resolution
+// image, homography (8x9 Gaussian elimination, double), border gray models, bilinear bit sampling, Laplacian
+// sharpen, codeword lookup (<= max_hamming bit errors, 4 rotations).  One WARP per quad.
+// Restates AprilRobotics apriltag.c refine_edges / quad_update_homographies / quad_decode / sharpen /
+// quick_decode_codeword / rotate90 and common/homography.c homography_compute2 with the
+// oracle's types and evaluation order; every order-dependent sum (line moments, gray models, scores) is
+// accumulated in the serial order, redundantly by all lanes (no divergence), while the pixel gathers run
+// lane-parallel.  Colour frames are converted to gray on the fly at each gather.
+#include <math_constants.h>
+
+#include "detector.h"
+
+namespace b200at {
+
+constexpr int DT = 128;  // threads per CTA (4 warps = 4 quads in flight per CTA)
+constexpr int MAXTW = 12;
+
+__device__ __forceinline__ int gray_at(const FrameDesc &fd, int enc, int bpp, int x, int y) {
+  const uint8_t *p = fd.ptr + (size_t)y * fd.pitch + (size_t)x * bpp;
+  if (enc == B200AT_ENC_MONO8) return p[0];
+  uint32_t c0 = p[0], c1 = p[1], c2 = p[2];
+  const bool bgr = (enc == B200AT_ENC_BGR8 || enc == B200AT_ENC_BGRA8);
+  uint32_t r = bgr ? c2 : c0, b = bgr ? c0 : c2;
+  return (int)((r * 4899u + c1 * 9617u + b * 1868u + 8192u) >> 14);
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __forceinline__ void hproject(const double *H, double x, double y, double *ox, double *oy) {
+  double xx = H[0] * x + H[1] * y + H[2];
+  double yy = H[3] * x + H[4] * y + H[5];
+  double zz = H[6] * x + H[7] * y + H[8];
+  *ox = xx / zz;
+  *oy = yy / zz;
+}
+
+__device__ bool homography_compute2_dev(const double c[4][4], double H[9]) {
+  double A[72];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double *r0 = A + (2 * i) * 9, *r1 = A + (2 * i + 1) * 9;
+    r0[0] = c[i][0];
+    r0[1] = c[i][1];
+    r0[2] = 1;
+    r0[3] = 0;
+    r0[4] = 0;
+    r0[5] = 0;
+    r0[6] = -c[i][0] * c[i][2];
+    r0[7] = -c[i][1] * c[i][2];
+    r0[8] = c[i][2];
+    r1[0] = 0;
+    r1[1] = 0;
+    r1[2] = 0;
+    r1[3] = c[i][0];
+    r1[4] = c[i][1];
+    r1[5] = 1;
+    r1[6] = -c[i][0] * c[i][3];
+    r1[7] = -c[i][1] * c[i][3];
+    r1[8] = c[i][3];
+  }
+  const double epsilon = 1e-10;
+  for (int col = 0; col < 8; col++) {
+    double max_val = 0;
+    int max_val_idx = -1;
+    for (int row = col; row < 8; row++) {
+      double val = fabs(A[row * 9 + col]);
+      if (val > max_val) {
+        max_val = val;
+        max_val_idx = row;
+      }
+    }
+    if (max_val < epsilon) return false;
+    if (max_val_idx != col) {
+      for (int i = col; i < 9; i++) {
+        double tmp = A[col * 9 + i];
+        A[col * 9 + i] = A[max_val_idx * 9 + i];
+        A[max_val_idx * 9 + i] = tmp;
+      }
+    }
+    for (int i = col + 1; i < 8; i++) {
+      double f = A[i * 9 + col] / A[col * 9 + col];
+      A[i * 9 + col] = 0;
+      for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
+    }
+  }
+  for (int col = 7; col >= 0; col--) {
+    double sum = 0;
+    for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
+    A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+  }
+  H[0] = A[8];
+  H[1] = A[17];
+  H[2] = A[26];
+  H[3] = A[35];
+  H[4] = A[44];
+  H[5] = A[53];
+  H[6] = A[62];
+  H[7] = A[71];
+  H[8] = 1;
+  return true;
+}
+
+struct GrayModelD {
+  double A00, A01, A02, A11, A12, A22, B0, B1, B2, C0, C1, C2;
+};
+__device__ __forceinline__ void gm_solve(GrayModelD &m) {
+  // mat33_sym_solve: Cholesky, lower-triangular inverse, two triangular products (same op order as the oracle)
+  double L0 = sqrt(m.A00);
+  double L3 = m.A01 / L0;
+  double L6 = m.A02 / L0;
+  double L4 = sqrt(m.A11 - L3 * L3);
+  double L7 = (m.A12 - L3 * L6) / L4;
+  double L8 = sqrt(m.A22 - L6 * L6 - L7 * L7);
+  double M0 = 1 / L0;
+  double M3 = -L3 * M0 / L4;
+  double M4 = 1 / L4;
+  double M6 = (-L6 * M0 - L7 * M3) / L8;
+  double M7 = -L7 * M4 / L8;
+  double M8 = 1 / L8;
+  double t0 = M0 * m.B0;
+  double t1 = M3 * m.B0 + M4 * m.B1;
+  double t2 = M6 * m.B0 + M7 * m.B1 + M8 * m.B2;
+  m.C0 = M0 * t0 + M3 * t1 + M6 * t2;
+  m.C1 = M4 * t1 + M7 * t2;
+  m.C2 = M8 * t2;
+}
+__device__ __forceinline__ double gm_interp(const GrayModelD &m, double x, double y) { return m.C0 * x + m.C1 * y + m.C2; }
+
+__device__ __forceinline__ unsigned long long rotate90_dev(unsigned long long w, int numBits) {
+  int p = numBits;
+  unsigned long long l = 0;
+  if (numBits % 4 == 1) {
+    p = numBits - 1;
+    l = 1;
+  }
+  w = ((w >> l) << (p / 4 + l)) | (w >> (3 * p / 4 + l) << l) | (w & l);
+  w &= ((1ULL << numBits) - 1);
+  return w;
+}
+
+__device__ __forceinline__ double value_for_pixel_dev(const FrameDesc &fd, int enc, int bpp, int width, int height, double px,
+                                                      double py) {
+  int x1 = (int)floor(px - 0.5);
+  int x2 = (int)ceil(px - 0.5);
+  double x = px - 0.5 - x1;
+  int y1 = (int)floor(py - 0.5);
+  int y2 = (int)ceil(py - 0.5);
+  double y = py - 0.5 - y1;
+  if (x1 < 0 || x2 >= width || y1 < 0 || y2 >= height) return -1;
+  return gray_at(fd, enc, bpp, x1, y1) * (1 - x) * (1 - y) + gray_at(fd, enc, bpp, x2, y1) * x * (1 - y) +
+         gray_at(fd, enc, bpp, x1, y2) * (1 - x) * y + gray_at(fd, enc, bpp, x2, y2) * x * y;
+}
+
+struct DecodeFams {
+  DevFamily f[kMaxFamilies];
+};
+
+__global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
+                                               const QuadRec *__restrict__ quads, QuadRec *__restrict__ quads_refined,
+                                               Cand *__restrict__ cands, uint32_t *__restrict__ cand_count,
+                                               uint32_t *__restrict__ counters) {
+  __shared__ double s_val[DT / 32][MAXTW * MAXTW];
+  __shared__ double s_new[DT / 32][MAXTW * MAXTW];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t nq = min(counters[CNT_QUADS], g.quad_cap);
+  const int width = g.W, height = g.H;
+  const int enc = g.enc, bpp = g.bpp;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(&counters[7], 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= nq) break;
+    const QuadRec q0 = quads[qi];
+    const FrameDesc fd = frames[q0.frame];
+    const bool reversed = q0.reversed_border != 0;
+    float p[4][2];
+    // ---- a11: rescale to the full-resolution frame ----
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (fp.quad_decimate > 1) {
+        p[j][0] = (float)(((double)q0.p[j][0] - 0.5) * (double)fp.quad_decimate + 0.5);
+        p[j][1] = (float)(((double)q0.p[j][1] - 0.5) * (double)fp.quad_decimate + 0.5);
+      } else {
+        p[j][0] = q0.p[j][0];
+        p[j][1] = q0.p[j][1];
+      }
+    }
+    // ---- a12: refine_edges ----
+    if (fp.refine_edges) {
+      double lines[4][4];
+      const double range = (double)(fp.quad_decimate + 1.0f);
+      const int nsteps = (int)floor(2.0 * range / 0.25) + 1;
+#pragma unroll 1
+      for (int edge = 0; edge < 4; edge++) {
+        const int a = edge, b = (edge + 1) & 3;
+        double nx = (double)(p[b][1] - p[a][1]);
+        double ny = (double)(-p[b][0] + p[a][0]);
+        double mag = sqrt(nx * nx + ny * ny);
+        nx /= mag;
+        ny /= mag;
+        if (reversed) {
+          nx = -nx;
+          ny = -ny;
+        }
+        const int nsamples = max(16, (int)(mag / 8));
+        double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+        for (int s0 = 0; s0 < nsamples; s0 += 32) {
+          const int s = s0 + lane;
+          double bestx = 0, besty = 0;
+          int has = 0;
+          if (s < nsamples) {
+            double alpha = (1.0 + s) / (nsamples + 1);
+            double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
+            double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
+            double Mn = 0, Mcount = 0;
+            for (int k = 0; k < nsteps; k++) {
+              const double n = -range + 0.25 * k;
+              const double grange = 1;
+              int x1 = (int)(x0 + (n + grange) * nx);
+              int y1 = (int)(y0 + (n + grange) * ny);
+              if (x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) continue;
+              int x2 = (int)(x0 + (n - grange) * nx);
+              int y2 = (int)(y0 + (n - grange) * ny);
+              if (x2 < 0 || x2 >= width || y2 < 0 || y2 >= height) continue;
+              int g1 = gray_at(fd, enc, bpp, x1, y1);
+              int g2 = gray_at(fd, enc, bpp, x2, y2);
+              if (g1 < g2) continue;
+              double weight = (double)((g2 - g1) * (g2 - g1));
+              Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
+              Mcount += weight;
+            }
+            if (Mcount != 0) {
+              double n0 = Mn / Mcount;
+              bestx = x0 + n0 * nx;
+              besty = y0 + n0 * ny;
+              has = 1;
+            }
+          }
+          const int cnt = min(32, nsamples - s0);
+          for (int k = 0; k < cnt; k++) {
+            const int h = __shfl_sync(0xffffffffu, has, k);
+            const double bx = shfl_d(bestx, k), by = shfl_d(besty, k);
+            if (h) {
+              Mx += bx;
+              My += by;
+              Mxx += bx * bx;
+              Mxy += bx * by;
+              Myy += by * by;
+              N++;
+            }
+          }
+        }
+        double Ex = Mx / N, Ey = My / N;
+        double Cxx = Mxx / N - Ex * Ex;
+        double Cxy = Mxy / N - Ex * Ey;
+        double Cyy = Myy / N - Ey * Ey;
+        // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
+        float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
+        double normal_theta = .5 * th;
+        float nth = (float)normal_theta;
+        lines[edge][0] = Ex;
+        lines[edge][1] = Ey;
+        lines[edge][2] = (double)(float)cos((double)nth);
+        lines[edge][3] = (double)(float)sin((double)nth);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
+        double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
+        double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
+        double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
+        double det = A00 * A11 - A10 * A01;
+        if (fabs(det) > 0.001) {
+          double W00 = A11 / det, W01 = -A01 / det;
+          double L0 = W00 * B0 + W01 * B1;
+          p[i][0] = (float)(lines[i][0] + L0 * A00);
+          p[i][1] = (float)(lines[i][1] + L0 * A10);
+        }
+      }
+    }
+    if (lane == 0) {
+      QuadRec qr = q0;
+      for (int j = 0; j < 4; j++) {
+        qr.p[j][0] = p[j][0];
+        qr.p[j][1] = p[j][1];
+      }
+      quads_refined[qi] = qr;
+    }
+    // ---- a13: homography ----
+    double H[9];
+    {
+      double corr[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        corr[i][0] = (i == 0 || i == 3) ? -1 : 1;
+        corr[i][1] = (i == 0 || i == 1) ? -1 : 1;
+        corr[i][2] = p[i][0];
+        corr[i][3] = p[i][1];
+      }
+      if (!homography_compute2_dev(corr, H)) continue;
+      double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
+      if (det == 0) continue;
+    }
+    // ---- a13: decode against every registered family ----
+#pragma unroll 1
+    for (int fi = 0; fi < fp.nfam; fi++) {
+      const DevFamily &fam = fams.f[fi];
+      if ((fam.reversed_border != 0) != reversed) continue;
+      const int wab = fam.width_at_border, twd = fam.total_width, nbits = fam.nbits;
+      const float wabf = (float)wab;
+      GrayModelD wm = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bm = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const int nsamp = 8 * wab;
+      for (int j0 = 0; j0 < nsamp; j0 += 32) {
+        const int j = j0 + lane;
+        double tagx = 0, tagy = 0;
+        int v = 0, valid = 0, is_white = 0;
+        if (j < nsamp) {
+          const int pat = j / wab, i = j % wab;
+          float p0, p1, p2, p3;
+          switch (pat) {
+            case 0: p0 = -0.5f; p1 = 0.5f; p2 = 0; p3 = 1; is_white = 1; break;
+            case 1: p0 = 0.5f; p1 = 0.5f; p2 = 0; p3 = 1; is_white = 0; break;
+            case 2: p0 = wabf + 0.5f; p1 = .5f; p2 = 0; p3 = 1; is_white = 1; break;
+            case 3: p0 = wabf - 0.5f; p1 = .5f; p2 = 0; p3 = 1; is_white = 0; break;
+            case 4: p0 = 0.5f; p1 = -0.5f; p2 = 1; p3 = 0; is_white = 1; break;
+            case 5: p0 = 0.5f; p1 = 0.5f; p2 = 1; p3 = 0; is_white = 0; break;
+            case 6: p0 = 0.5f; p1 = wabf + 0.5f; p2 = 1; p3 = 0; is_white = 1; break;
+            default: p0 = 0.5f; p1 = wabf - 0.5f; p2 = 1; p3 = 0; is_white = 0; break;
+          }
+          // float arithmetic, as the C expression (float + int*float) / int evaluates
+          double tagx01 = (double)((p0 + (float)i * p2) / wabf);
+          double tagy01 = (double)((p1 + (float)i * p3) / wabf);
+          tagx = 2 * (tagx01 - 0.5);
+          tagy = 2 * (tagy01 - 0.5);
+          double px, py;
+          hproject(H, tagx, tagy, &px, &py);
+          int ix = (int)px, iy = (int)py;
+          if (!(ix < 0 || iy < 0 || ix >= width || iy >= height)) {
+            v = gray_at(fd, enc, bpp, ix, iy);
+            valid = 1;
+          }
+        }
+        const int cnt = min(32, nsamp - j0);
+        for (int k = 0; k < cnt; k++) {
+          const int vl = __shfl_sync(0xffffffffu, valid, k);
+          const int iw = __shfl_sync(0xffffffffu, is_white, k);
+          const int vv = __shfl_sync(0xffffffffu, v, k);
+          const double x = shfl_d(tagx, k), y = shfl_d(tagy, k);
+          if (vl) {
+            GrayModelD &m = iw ? wm : bm;
+            const double gray = (double)vv;
+            m.A00 += x * x;
+            m.A01 += x * y;
+            m.A02 += x;
+            m.A11 += y * y;
+            m.A12 += y;
+            m.A22 += 1;
+            m.B0 += x * gray;
+            m.B1 += y * gray;
+            m.B2 += gray;
+          }
+        }
+      }
+      if (wab > 1) {
+        gm_solve(wm);
+        gm_solve(bm);
+      } else {
+        gm_solve(wm);
+        bm.C0 = 0;
+        bm.C1 = 0;
+        bm.C2 = bm.B2 / 4;
+      }
+      if ((gm_interp(wm, 0, 0) - gm_interp(bm, 0, 0) < 0) != (fam.reversed_border != 0)) continue;
+      // bit samples
+      double *val = s_val[wid], *nval = s_new[wid];
+      for (int c = lane; c < twd * twd; c += 32) val[c] = 0;
+      __syncwarp();
+      const int min_coord = (wab - twd) / 2;
+      for (int i = lane; i < nbits; i += 32) {
+        const int bity = fam.bit_y[i], bitx = fam.bit_x[i];
+        double tagx01 = (bitx + 0.5) / (wab);
+        double tagy01 = (bity + 0.5) / (wab);
+        double tagx = 2 * (tagx01 - 0.5);
+        double tagy = 2 * (tagy01 - 0.5);
+        double px, py;
+        hproject(H, tagx, tagy, &px, &py);
+        double v = value_for_pixel_dev(fd, enc, bpp, width, height, px, py);
+        if (v == -1) continue;
+        double thresh = (gm_interp(bm, tagx, tagy) + gm_interp(wm, tagx, tagy)) / 2.0;
+        val[twd * (bity - min_coord) + bitx - min_coord] = v - thresh;
+      }
+      __syncwarp();
+      // sharpen: values + decode_sharpening * (3x3 Laplacian, zero padded), same term order as the serial loop
+      for (int c = lane; c < twd * twd; c += 32) {
+        const int y = c / twd, x = c % twd;
+        double sh = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            if ((y + i - 1) < 0 || (y + i - 1) > twd - 1 || (x + j - 1) < 0 || (x + j - 1) > twd - 1) continue;
+            const double kern = (i == 1 && j == 1) ? 4.0 : ((i == 1 || j == 1) ? -1.0 : 0.0);
+            sh += val[(y + i - 1) * twd + (x + j - 1)] * kern;
+          }
+        nval[c] = val[c] + fp.decode_sharpening * sh;
+      }
+      __syncwarp();
+      unsigned long long rcode = 0;
+      float black_score = 0, white_score = 0;
+      float black_score_count = 1, white_score_count = 1;
+      for (int i = 0; i < nbits; i++) {
+        const int bity = fam.bit_y[i], bitx = fam.bit_x[i];
+        rcode = (rcode << 1);
+        double v = nval[(bity - min_coord) * twd + bitx - min_coord];
+        if (v > 0) {
+          white_score = (float)((double)white_score + v);
+          white_score_count++;
+          rcode |= 1;
+        } else {
+          black_score = (float)((double)black_score - v);
+          black_score_count++;
+        }
+      }
+      __syncwarp();
+      // quick_decode_codeword: rotation by rotation, lowest code index within max_hamming wins
+      int e_id = 65535, e_ham = 255, e_rot = 0;
+      {
+        unsigned long long rc = rcode;
+        for (int ridx = 0; ridx < 4; ridx++) {
+          int best_k = 0x7fffffff, best_h = 255;
+          for (int k = lane; k < fam.ncodes; k += 32) {
+            int hd = __popcll(rc ^ fam.codes[k]);
+            if (hd <= fp.max_hamming && k < best_k) {
+              best_k = k;
+              best_h = hd;
+            }
+          }
+          for (int of = 16; of > 0; of >>= 1) {
+            int ok = __shfl_xor_sync(0xffffffffu, best_k, of), oh = __shfl_xor_sync(0xffffffffu, best_h, of);
+            if (ok < best_k) {
+              best_k = ok;
+              best_h = oh;
+            }
+          }
+          if (best_k != 0x7fffffff) {
+            e_id = best_k;
+            e_ham = best_h;
+            e_rot = ridx;
+            break;
+          }
+          rc = rotate90_dev(rc, nbits);
+        }
+      }
+      const float decision_margin = fminf(white_score / white_score_count, black_score / black_score_count);
+      if (decision_margin >= 0 && e_ham < 255 && lane == 0) {
+        const double kCos[4] = {1.0, 6.123233995736766e-17, -1.0, -1.8369701987210297e-16};
+        const double kSin[4] = {0.0, 1.0, 1.2246467991473532e-16, -1.0};
+        const double c = kCos[e_rot], s = kSin[e_rot];
+        const double Rm[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+        Cand cd;
+        cd.key = q0.key;
+        cd.family = fam.index;
+        cd.id = e_id;
+        cd.hamming = e_ham;
+        cd.decision_margin = decision_margin;
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) cd.H[i * 3 + j] = H[i * 3 + 0] * Rm[0 * 3 + j] + H[i * 3 + 1] * Rm[1 * 3 + j] + H[i * 3 + 2] * Rm[2 * 3 + j];
+        hproject(cd.H, 0, 0, &cd.c[0], &cd.c[1]);
+        for (int i = 0; i < 4; i++) {
+          int tcx = (i == 1 || i == 2) ? 1 : -1;
+          int tcy = (i < 2) ? 1 : -1;
+          hproject(cd.H, tcx, tcy, &cd.p[i][0], &cd.p[i][1]);
+        }
+        uint32_t slot = atomicAdd(&cand_count[q0.frame], 1u);
+        if (slot < g.cand_cap)
+          cands[(size_t)q0.frame * g.cand_cap + slot] = cd;
+        else
+          atomicOr(&counters[CNT_STATUS], (uint32_t)ST_CANDS_FULL);
+      }
+    }
+  }
+}
+
+int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
+  cudaMemsetAsync(ws.cand_count, 0, (size_t)nframes * sizeof(uint32_t), s);
+  DecodeFams df;
+  for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  k_decode<<<sms * 4, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.cands, ws.cand_count, ws.counters);
+  return 2;
+}
+
+}  // namespace b200at

@@ -1406,8 +1406,13 @@ double orthogonal_iteration(const double v[4][3], const double p[4][3], double t
 }
 
 double polyval(const double *p, int degree, double x) {
-  double ret = 0;
-  for (int i = 0; i <= degree; i++) ret += p[i] * pow(x, i);
+  // upstream: ret += p[i]*pow(x, i); restated with repeated multiplication so the CUDA pose kernel can
+  // reproduce it bit for bit (pow() is not reproducible across libms; the difference is <= 1 ulp per term)
+  double ret = 0, xp = 1;
+  for (int i = 0; i <= degree; i++) {
+    ret += p[i] * xp;
+    xp *= x;
+  }
   return ret;
 }
 

@@ -1,0 +1,125 @@
+"""Stage-by-stage comparison of the CUDA path (through the C ABI) with the CPU oracle on the same frames.
+
+The oracle is the checker here, never the thing shipped (see oracle/apriltag_oracle.h)."""
+import numpy as np
+from scipy import ndimage
+
+from isaac_ros_apriltag_b200 import capi
+from oracle import oracle as O
+
+
+def upload(frames):
+    """host (n,H,W[,C]) uint8 -> torch cuda tensor; returns (tensor, ptrs, pitch)"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(frames)).cuda()
+    n = t.shape[0]
+    frame_bytes = t[0].numel()
+    pitch = t.shape[2] * (t.shape[3] if t.dim() == 4 else 1)
+    ptrs = [t.data_ptr() + i * frame_bytes for i in range(n)]
+    return t, ptrs, pitch
+
+
+def to_gray_batch(frames, encoding):
+    if encoding == "mono8":
+        return frames
+    return np.stack([O.to_gray(f, encoding) for f in frames])
+
+
+def compare_stages(frames, encoding="mono8", families=("tag36h11",), report=None, **opts):
+    """Runs the batch through the GPU detector and every frame through the oracle; returns a dict of per-stage
+    mismatch counts (all zeros = bit-exact) plus float deviations for the tolerance-level stages."""
+    import torch
+    n, H, W = frames.shape[:3]
+    det = capi.Detector(W, H, families=families, encoding=encoding, max_batch=n, max_tags=256, **opts)
+    t, ptrs, pitch = upload(frames)
+    gdets = det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream, strict=False)
+    res = {"status": det.status(), "dec": 0, "tile": 0, "thr": 0, "labels": 0, "sizes": 0, "clusters": 0, "points": 0,
+           "quads_n": 0, "quads_bits": 0, "quads_max": 0.0, "refined_n": 0, "refined_bits": 0, "refined_max": 0.0,
+           "det_n": 0, "det_id": 0, "det_margin_max": 0.0, "det_corner_max": 0.0, "det_H_max": 0.0, "n_det": 0, "n_quads": 0,
+           "n_clusters": 0, "n_points": 0}
+    gray = to_gray_batch(frames, encoding)
+    okw = {}
+    for k in ("quad_decimate", "quad_sigma", "refine_edges", "decode_sharpening", "min_white_black_diff", "max_nmaxima",
+              "critical_rad", "max_line_fit_mse", "max_hamming", "tile_size"):
+        if k in opts:
+            okw[k] = opts[k]
+    orc = O.Oracle(families, **okw)
+    gclu = det.read_buffer(capi.BUF_CLUSTERS)
+    gkeys = det.read_buffer(capi.BUF_POINTS)
+    gquads = det.read_buffer(capi.BUF_QUADS)
+    gref = det.read_buffer(capi.BUF_QUADS_REFINED)
+    ts = opts.get("tile_size", 4)
+    for i in range(n):
+        odets = orc.detect(gray[i])
+        # dense stages
+        res["dec"] += int((det.read_buffer(capi.BUF_DECIMATED, i) != orc.quad_image()).sum())
+        omn, omx = orc.tile_minmax()
+        gmn = ndimage.minimum_filter(det.read_buffer(capi.BUF_TILE_MIN, i), size=3, mode="nearest")
+        gmx = ndimage.maximum_filter(det.read_buffer(capi.BUF_TILE_MAX, i), size=3, mode="nearest")
+        res["tile"] += int((gmn != omn).sum() + (gmx != omx).sum())
+        res["thr"] += int((det.read_buffer(capi.BUF_THRESHOLD, i) != orc.threshold()).sum())
+        olab, osz = orc.labels()
+        glab = det.read_buffer(capi.BUF_LABELS, i)
+        gsz = det.read_buffer(capi.BUF_SIZES, i)
+        res["labels"] += int((glab != olab).sum())
+        # GPU stores the size at the representative only (and never counts 127 pixels' singletons elsewhere)
+        gsz_full = gsz.reshape(-1)[glab.reshape(-1)].reshape(glab.shape)
+        res["sizes"] += int((gsz_full != osz).sum())
+        # clusters: same key set, same sorted point sequence
+        ocl = orc.clusters()
+        sel = gclu[gclu["frame"] == i]
+        gmap = {int(r["key"]): r for r in sel}
+        res["n_clusters"] += len(ocl)
+        if set(gmap) != set(k for k, _ in ocl):
+            res["clusters"] += len(set(gmap) ^ set(k for k, _ in ocl))
+        for key, pts in ocl:
+            r = gmap.get(key)
+            if r is None:
+                continue
+            res["n_points"] += len(pts)
+            # the GPU only sorts clusters that pass the bbox / polarity gates; compare as sets when unsorted
+            gk = gkeys[int(r["offset"]):int(r["offset"]) + int(r["count"])]
+            gp = ((gk & np.uint64(0xffff)) | (((gk >> np.uint64(16)) & np.uint64(0xffff)) << np.uint64(16))).astype(np.uint32)
+            if len(gp) != len(pts):
+                res["points"] += abs(len(gp) - len(pts))
+            elif not np.array_equal(gp, pts):
+                if not np.array_equal(np.sort(gp), np.sort(pts)):
+                    res["points"] += 1
+        # quads
+        for which, garr, tagn, tagb, tagm in ((False, gquads, "quads_n", "quads_bits", "quads_max"),
+                                              (True, gref, "refined_n", "refined_bits", "refined_max")):
+            oq = orc.quads(refined=which)
+            if which:  # the oracle applies refine_edges inside the decode loop; recompute refined corners here
+                pass
+            gq = garr[garr["frame"] == i]
+            gq = gq[np.argsort(gq["key"], kind="stable")]
+            okeys = [q["key"] for q in oq]
+            if not which:
+                res["n_quads"] += len(oq)
+            if list(gq["key"]) != okeys:
+                res[tagn] += len(set(int(k) for k in gq["key"]) ^ set(okeys)) + (0 if len(gq) == len(oq) else 1)
+                continue
+            if len(oq):
+                op = np.stack([q["p"] for q in oq])
+                res[tagb] += int((gq["p"].view(np.uint32) != op.view(np.uint32)).sum())
+                res[tagm] = max(res[tagm], float(np.abs(gq["p"] - op).max()))
+        # detections
+        g = gdets[i]
+        res["n_det"] += len(odets)
+        if len(g) != len(odets):
+            res["det_n"] += 1
+            if report is not None:
+                report.append(f"frame {i}: gpu {len(g)} dets vs oracle {len(odets)}: "
+                              f"gpu ids {list(g['id'])} oracle ids {[d['id'] for d in odets]}")
+            continue
+        for a, b in zip(g, odets):
+            if a["id"] != b["id"] or a["hamming"] != b["hamming"] or capi.FAMILY_NAMES[a["family"]] != b["family"]:
+                res["det_id"] += 1
+                continue
+            res["det_margin_max"] = max(res["det_margin_max"], abs(float(a["decision_margin"]) - b["decision_margin"]))
+            res["det_corner_max"] = max(res["det_corner_max"], float(np.abs(a["p"] - b["p"]).max()),
+                                        float(np.abs(a["c"] - b["c"]).max()))
+            res["det_H_max"] = max(res["det_H_max"], float(np.abs(a["H"].reshape(3, 3) - b["H"]).max()))
+    det.close()
+    del t
+    return res, gdets
