@@ -1,0 +1,307 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: 1080p tag36h11 frames/s on B200 (BASELINE.json metric), contract per the
+build instructions.
+
+One "step" = one pass of the full detection hot path (gray+decimate, threshold, union-find, gradient
+clusters, quad fit, refine+decode, reconcile, pose) over one batch of synthetic frames.
+  value    : whole-job frames/s with the batch already resident in HBM (CUDA events on the launch stream).
+  e2e      : same metric through the reference-facing C ABI with HOST (pinned) buffers
+             (b200AprilTagsDetectBatchHost): H2D of every frame and D2H of the results inside the timed region.
+  roofline : threshold kernel (the metric's named kernel): algorithmic bytes 2*Pd per frame / live event time.
+  cpu_baseline : the CPU oracle (port of AprilRobotics apriltag) timed on this box's host cores, rank 0, N=1.
+
+`--impl reference` times the CPU oracle port on the same workload (the reference's closed cuAprilTags / VPI
+libraries and the AprilRobotics sources are absent from this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames_per_sec_1080p_tag36h11"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(config, distinct, encoding):
+    from isaac_ros_apriltag_b200 import synth
+    frames, truths, K, tagsize, fams = synth.make_config_frames(config, distinct)
+    if encoding != "mono8":
+        ch = 3 if encoding in ("rgb8", "bgr8") else 4
+        col = np.repeat(frames[:, :, :, None], ch, axis=3)
+        if ch == 4:
+            col[..., 3] = 255
+        frames = np.ascontiguousarray(col)
+    return frames, truths, K, tagsize, fams
+
+
+def run_reference(args):
+    """CPU arm: the oracle port with all host threads, on the same workload, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    frames, _, _, _, fams = make_workload(args.config, args.distinct, args.encoding)
+    n_step = max(cores, 16)
+    n_step = min(n_step, 256)
+    idx = np.arange(n_step) % frames.shape[0]
+    sample = np.ascontiguousarray(frames[idx])
+    for _ in range(args.warmup):
+        O.detect_batch(sample[:max(cores, 1)], fams, nthreads=cores, encoding=args.encoding)
+    t0 = time.perf_counter()
+    ndet = 0
+    for _ in range(args.steps):
+        res, _times = O.detect_batch(sample, fams, nthreads=cores, encoding=args.encoding)
+        ndet += sum(len(r) for r in res)
+    dt = time.perf_counter() - t0
+    fps = n_step * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args), "frames_per_step": n_step, "detections_per_step": ndet // max(args.steps, 1)},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_step} frames/step x {args.steps} steps, frame-parallel, one detector per thread"},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(args):
+    desc = {"C2": "1920x1080 tag36h11, 10 tags/frame", "C1": "1280x720, 1 tag36h11", "C3": "3840x2160 tag36h11, 4 tags/frame",
+            "C4": "1280x720 dense grid 91 tag36h11", "C5": "1920x1080 6 tag36h11 + 4 tag25h9"}[args.config]
+    return f"{args.config}: {desc}, batch={args.batch}/GPU, {args.encoding}, {args.distinct} distinct seeded frames tiled"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--distinct", type=int, default=32)
+    ap.add_argument("--encoding", default="bgr8")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from isaac_ros_apriltag_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the detector has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frames, truths, K, tagsize, fams = make_workload(args.config, args.distinct, args.encoding)
+    H, W = frames.shape[1:3]
+    B = args.batch
+    # device-resident batch: `distinct` seeded frames tiled to the batch size (inputs >> L2: no flush needed)
+    dev_distinct = torch.from_numpy(frames).cuda()
+    reps = (B + args.distinct - 1) // args.distinct
+    dev_batch = dev_distinct.repeat((reps,) + (1,) * (dev_distinct.dim() - 1))[:B].contiguous()
+    frame_bytes = dev_batch[0].numel()
+    pitch = frame_bytes // H
+    ptrs = [dev_batch.data_ptr() + i * frame_bytes for i in range(B)]
+    det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=tagsize, families=fams,
+                        encoding=args.encoding, max_batch=B, max_tags=64, device=local_rank)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        dets = det.detect_device(ptrs, pitch, sh)
+    n_det = sum(len(d) for d in dets)
+    status = det.status()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    det.enable_timing(True)
+    stage_acc = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        det.detect_device(ptrs, pitch, sh)
+        for k, v in det.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        launches += det.counters()["launches"]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    det.enable_timing(False)
+    tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    counters = det.counters()
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.from_numpy(frames).pin_memory()
+        host_batch = host.repeat((reps,) + (1,) * (host.dim() - 1))[:B].contiguous().pin_memory()
+        hb = host_batch.numpy()
+        for _ in range(max(1, args.warmup - 1)):
+            det.detect_host(hb)
+        e2e_steps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = det.detect_host(hb)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        d2h = B * 64 * capi.DET_DTYPE.itemsize + B * 4 + 32
+        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * frame_bytes),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "timer": "host wall clock around the synchronous C-ABI call"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the threshold kernel (metric's named kernel) + per-stage table ----
+    peak, peak_kind = load_peaks()
+    wd, hd, tw, th = det.dims()
+    Pd = wd * hd
+    bpp = capi.BPP[args.encoding]
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    alg = {"preprocess": (bpp + 1) * Pd, "threshold": 2 * Pd, "ccl": 5 * Pd, "cluster": 2 * 5 * Pd}
+    stage_gbs = {k: (alg[k] * B / (stage_ms[k] / 1e3) / 1e9) if stage_ms.get(k, 0) > 0 else None for k in alg}
+    thr_gbs = stage_gbs["threshold"]
+    roofline = {"kernel": "k_threshold4", "bound": "hbm", "achieved": thr_gbs, "peak": peak, "unit": "GB/s",
+                "frac": (thr_gbs / peak) if thr_gbs else None, "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_launch": 2 * Pd * B, "launch_ms": stage_ms.get("threshold")}
+    dominant = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else None
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and args.gpus == 1:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        n_s = min(max(cores, 16), 256)
+        idx = np.arange(n_s) % frames.shape[0]
+        sample = np.ascontiguousarray(frames[idx])
+        O.detect_batch(sample[:cores], fams, nthreads=cores, encoding=args.encoding)
+        t0 = time.perf_counter()
+        reps_cpu = 0
+        while True:
+            res, times = O.detect_batch(sample, fams, nthreads=cores, encoding=args.encoding)
+            reps_cpu += 1
+            if time.perf_counter() - t0 > 8.0 or reps_cpu >= 20:
+                break
+        dtc = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        res1, times1 = O.detect_batch(sample[:4], fams, nthreads=1, encoding=args.encoding)
+        dt1 = time.perf_counter() - t1
+        cpu_baseline = {"value": n_s * reps_cpu / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_s} frames x {reps_cpu} passes, frame-parallel (one single-thread detector per core)",
+                        "single_thread_fps": 4 / dt1,
+                        "stage_share_single_thread": {k: round(v / max(times1["total"], 1e-9), 3) for k, v in times1.items() if k != "total"}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "inputs larger than L2 (batch %.0f MB)" % (B * frame_bytes / 1e6),
+                       "detections_per_batch": n_det, "status": status, "points_per_batch": int(counters["points"]),
+                       "clusters_per_batch": int(counters["clusters"]), "quads_per_batch": int(counters["quads"])},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "stages_ms_per_step": stage_ms, "stages_gbs": stage_gbs, "dominant_stage": dominant, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

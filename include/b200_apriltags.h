@@ -201,7 +201,8 @@ enum {
   B200AT_BUF_CLUSTERS,      /* records {u64 key; u32 offset; u32 count; u32 frame; u32 pad}, all frames */
   B200AT_BUF_POINTS,        /* u64 sort keys per kept point (slope bits | y | x), cluster-contiguous, sorted */
   B200AT_BUF_QUADS,         /* records b200AprilTagsQuadRec_t, all frames */
-  B200AT_BUF_QUADS_REFINED  /* same records after rescale + refine_edges */
+  B200AT_BUF_QUADS_REFINED, /* same records after rescale + refine_edges */
+  B200AT_BUF_POINTS_RAW     /* u32 packed points as emitted: x | y<<14 | gx code<<28 | gy code<<30, cluster-contiguous */
 };
 typedef struct {
   uint64_t key;

@@ -19,7 +19,7 @@ BPP = {"mono8": 1, "rgb8": 3, "bgr8": 3, "rgba8": 4, "bgra8": 4}
 ERRORS = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NOMEM", 5: "OVERFLOW", 6: "NO_DEVICE"}
 STAGES = ["preprocess", "threshold", "ccl", "cluster", "quadfit", "decode", "finalize", "d2h"]
 (BUF_DECIMATED, BUF_TILE_MIN, BUF_TILE_MAX, BUF_THRESHOLD, BUF_LABELS, BUF_SIZES, BUF_CLUSTERS, BUF_POINTS, BUF_QUADS,
- BUF_QUADS_REFINED) = range(10)
+ BUF_QUADS_REFINED, BUF_POINTS_RAW) = range(11)
 
 # every symbol include/b200_apriltags.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED_SYMBOLS = [
@@ -248,6 +248,8 @@ class Detector:
             out = np.empty(n.value, CLUSTER_DTYPE)
         elif which == BUF_POINTS:
             out = np.empty(n.value, np.uint64)
+        elif which == BUF_POINTS_RAW:
+            out = np.empty(n.value, np.uint32)
         else:
             out = np.empty(n.value, QUAD_DTYPE)
         if out.nbytes:

@@ -633,6 +633,12 @@ int b200AprilTagsReadBuffer(cuAprilTagsHandle h, int which, uint32_t frame, void
       if (dst && m) e = cudaMemcpy(dst, ws.keys, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       break;
     }
+    case B200AT_BUF_POINTS_RAW: {
+      n = std::min<size_t>(h->h_counters[CNT_POINTS], g.pts_cap);
+      size_t m = std::min(n, cap / sizeof(uint32_t));
+      if (dst && m) e = cudaMemcpy(dst, ws.pts, m * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+      break;
+    }
     case B200AT_BUF_QUADS:
     case B200AT_BUF_QUADS_REFINED: {
       n = std::min<size_t>(h->h_counters[CNT_QUADS], g.quad_cap);

@@ -1919,15 +1919,28 @@ void ato_to_gray(const uint8_t *src, int enc, int width, int height, int stride,
 
 int ato_detect_batch(const ato_params_t *p, const uint8_t *frames, int n, int width, int height, int nthreads,
                      ato_detection_t *out, int *counts, int max_out, ato_times_t *sum_times) {
+  return ato_detect_batch_enc(p, frames, 0, n, width, height, nthreads, out, counts, max_out, sum_times);
+}
+
+int ato_detect_batch_enc(const ato_params_t *p, const uint8_t *frames, int enc, int n, int width, int height, int nthreads,
+                         ato_detection_t *out, int *counts, int max_out, ato_times_t *sum_times) {
   if (nthreads < 1) nthreads = 1;
+  const int bpp = enc == 0 ? 1 : ((enc == 1 || enc == 2) ? 3 : 4);
   vector<std::thread> th;
   vector<ato_times_t> tsum(nthreads);
   for (int t = 0; t < nthreads; t++) memset(&tsum[t], 0, sizeof(ato_times_t));
   for (int t = 0; t < nthreads; t++) {
     th.emplace_back([=, &tsum]() {
       Detector *D = (Detector *)ato_create(p);
+      vector<uint8_t> graybuf;
+      if (enc != 0) graybuf.resize((size_t)width * height);
       for (int i = t; i < n; i += nthreads) {
-        counts[i] = detect(*D, frames + (size_t)i * width * height, width, height, width, out + (size_t)i * max_out, max_out);
+        const uint8_t *src = frames + (size_t)i * width * height * bpp;
+        if (enc != 0) {  // colour input: the conversion is part of the CPU path's per-frame work
+          ato_to_gray(src, enc, width, height, width * bpp, graybuf.data());
+          src = graybuf.data();
+        }
+        counts[i] = detect(*D, src, width, height, width, out + (size_t)i * max_out, max_out);
         const ato_times_t &x = D->times;
         ato_times_t &s = tsum[t];
         s.decimate += x.decimate;

@@ -103,6 +103,10 @@ void ato_to_gray(const uint8_t *src, int enc, int width, int height, int stride,
 int ato_detect_batch(const ato_params_t *p, const uint8_t *frames, int n, int width, int height, int nthreads,
                      ato_detection_t *out, int *counts, int max_out, ato_times_t *sum_times);
 
+/* same, frames in any of the five encodings (the colour->gray conversion is done per frame inside the workers) */
+int ato_detect_batch_enc(const ato_params_t *p, const uint8_t *frames, int enc, int n, int width, int height, int nthreads,
+                         ato_detection_t *out, int *counts, int max_out, ato_times_t *sum_times);
+
 /* upstream rotate90 / codebook access for known-answer tests */
 uint64_t ato_rotate90(uint64_t w, int nbits);
 int ato_family_info(int fam, int *nbits, int *ncodes, int *width_at_border, int *total_width);

@@ -81,6 +81,9 @@ def lib():
         L.ato_detect_batch.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(Detection), C.POINTER(C.c_int), C.c_int, C.POINTER(Times)]
         L.ato_detect_batch.restype = C.c_int
+        L.ato_detect_batch_enc.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(Detection), C.POINTER(C.c_int), C.c_int, C.POINTER(Times)]
+        L.ato_detect_batch_enc.restype = C.c_int
         L.ato_rotate90.argtypes = [C.c_uint64, C.c_int]
         L.ato_rotate90.restype = C.c_uint64
         L.ato_family_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4
@@ -214,14 +217,15 @@ class Oracle:
         return f(best), f(p1), f(p2)
 
 
-def detect_batch(frames, families=("tag36h11",), nthreads=1, max_out=256, **kw):
-    """frames: (n,h,w) uint8.  Returns (list of list of det dicts, summed stage times dict)."""
+def detect_batch(frames, families=("tag36h11",), nthreads=1, max_out=256, encoding="mono8", **kw):
+    """frames: (n,h,w[,c]) uint8.  Returns (list of list of det dicts, summed stage times dict)."""
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
-    n, h, w = frames.shape
+    n, h, w = frames.shape[:3]
     p = default_params(families, **kw)
     out = (Detection * (n * max_out))()
     counts = (C.c_int * n)()
     t = Times()
-    lib().ato_detect_batch(C.byref(p), frames.ctypes.data, n, w, h, nthreads, out, counts, max_out, C.byref(t))
+    lib().ato_detect_batch_enc(C.byref(p), frames.ctypes.data, ENCODINGS[encoding], n, w, h, nthreads, out, counts, max_out,
+                               C.byref(t))
     res = [[det_to_dict(out[i * max_out + k]) for k in range(counts[i])] for i in range(n)]
     return res, {nm: getattr(t, nm) for nm, _ in Times._fields_}

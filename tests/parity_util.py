@@ -46,6 +46,7 @@ def compare_stages(frames, encoding="mono8", families=("tag36h11",), report=None
     orc = O.Oracle(families, **okw)
     gclu = det.read_buffer(capi.BUF_CLUSTERS)
     gkeys = det.read_buffer(capi.BUF_POINTS)
+    graw = det.read_buffer(capi.BUF_POINTS_RAW)
     gquads = det.read_buffer(capi.BUF_QUADS)
     gref = det.read_buffer(capi.BUF_QUADS_REFINED)
     ts = opts.get("tile_size", 4)
@@ -77,14 +78,20 @@ def compare_stages(frames, encoding="mono8", families=("tag36h11",), report=None
             if r is None:
                 continue
             res["n_points"] += len(pts)
-            # the GPU only sorts clusters that pass the bbox / polarity gates; compare as sets when unsorted
-            gk = gkeys[int(r["offset"]):int(r["offset"]) + int(r["count"])]
+            lo, hi = int(r["offset"]), int(r["offset"]) + int(r["count"])
+            # (1) emitted point multiset == oracle's (emission order inside a cluster is free)
+            rw = graw[lo:hi]
+            rp = ((rw & np.uint32(0x3fff)) | (((rw >> np.uint32(14)) & np.uint32(0x3fff)) << np.uint32(16))).astype(np.uint32)
+            if len(rp) != len(pts) or not np.array_equal(np.sort(rp), np.sort(pts)):
+                res["points"] += 1
+                continue
+            # (2) clusters that reach the sort (bbox / polarity gates passed on both sides) have the same sequence
+            gk = gkeys[lo:hi]
             gp = ((gk & np.uint64(0xffff)) | (((gk >> np.uint64(16)) & np.uint64(0xffff)) << np.uint64(16))).astype(np.uint32)
-            if len(gp) != len(pts):
-                res["points"] += abs(len(gp) - len(pts))
-            elif not np.array_equal(gp, pts):
-                if not np.array_equal(np.sort(gp), np.sort(pts)):
-                    res["points"] += 1
+            if np.array_equal(np.sort(gp), np.sort(pts)):
+                res["n_sorted"] = res.get("n_sorted", 0) + 1
+                if not np.array_equal(gp, pts):
+                    res["order"] = res.get("order", 0) + 1
         # quads
         for which, garr, tagn, tagb, tagm in ((False, gquads, "quads_n", "quads_bits", "quads_max"),
                                               (True, gref, "refined_n", "refined_bits", "refined_max")):

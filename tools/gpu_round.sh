@@ -1,0 +1,7 @@
+#!/bin/bash
+# One GPU visit: gpu tests, smoke, bench, launch list.  Outputs under gpurun_out/.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
+timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
+tail -5 gpurun_out/bench.err
