@@ -57,10 +57,18 @@ struct cuAprilTagsHandle_st {
   b200AprilTagsDetection_t *h_out = nullptr;
   uint32_t *h_out_count = nullptr;
   uint32_t *h_counters = nullptr;
-  // host-input staging
+  // host-input path: double-buffered staging + copy stream, so H2D of sub-batch k+1 overlaps the kernels of sub-batch k
   uint8_t *d_stage = nullptr;
   size_t stage_pitch = 0;
-  cudaStream_t own_stream = nullptr;
+  uint32_t stage_sub = 0;  // frames per staging slot
+  cudaStream_t own_stream = nullptr;   // compute stream of the host path
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  FrameDesc *hp_frames = nullptr;
+  b200AprilTagsDetection_t *hp_out = nullptr;
+  uint32_t *hp_out_count = nullptr;
+  uint32_t *hp_counters = nullptr;
+  size_t hp_cap_frames = 0, hp_cap_subs = 0;
   // state of the batch in flight
   cudaStream_t cur_stream = nullptr;
   uint32_t cur_n = 0;
@@ -98,6 +106,20 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_out_count) cudaFreeHost(h->h_out_count);
   if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->hp_frames) cudaFreeHost(h->hp_frames);
+  if (h->hp_out) cudaFreeHost(h->hp_out);
+  if (h->hp_out_count) cudaFreeHost(h->hp_out_count);
+  if (h->hp_counters) cudaFreeHost(h->hp_counters);
+  for (int i = 0; i < 2; i++) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 2; i++) {
+    if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
+    if (h->ws.ev_join[i]) cudaEventDestroy(h->ws.ev_join[i]);
+  }
+  if (h->ws.ev_fork) cudaEventDestroy(h->ws.ev_fork);
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -172,7 +194,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   // integer decimation only (AprilRobotics' 3->2 "1.5" special case is not built)
   float qd = opt.quad_decimate;
   if (!(qd >= 1.0f) || qd != floorf(qd) || qd > 8.0f) return B200AT_ERR_UNSUPPORTED;
-  if (opt.max_nmaxima < 4 || opt.max_nmaxima > 16) return B200AT_ERR_UNSUPPORTED;
+  if (opt.max_nmaxima < 4 || opt.max_nmaxima > kMaxNMaxima) return B200AT_ERR_UNSUPPORTED;
   if (opt.max_hamming < 0 || opt.max_hamming > 3) return B200AT_ERR_UNSUPPORTED;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -331,6 +353,33 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.out, (size_t)B * g.max_tags);
   ALLOC(ws.out_count, B);
   ALLOC(ws.counters, CNT_N);
+  ALLOC(ws.bin_idx, (size_t)3 * g.clu_cap);
+  {
+    // combination tables: for every nm, all m0<m1<m2<m3<nm in lexicographic order (the serial loops' visiting order)
+    std::vector<unsigned char> tab;
+    for (int nm = 0; nm <= 17; nm++) {
+      ws.combo_off[nm] = (int)(tab.size() / 4);
+      if (nm < 4 || nm > kMaxNMaxima) continue;
+      for (int a = 0; a < nm - 3; a++)
+        for (int b = a + 1; b < nm - 2; b++)
+          for (int c = b + 1; c < nm - 1; c++)
+            for (int d = c + 1; d < nm; d++) {
+              tab.push_back((unsigned char)a);
+              tab.push_back((unsigned char)b);
+              tab.push_back((unsigned char)c);
+              tab.push_back((unsigned char)d);
+            }
+    }
+    unsigned char *dcomb = nullptr;
+    ALLOC(dcomb, tab.size());
+    if (rc == 0 && cudaMemcpy(dcomb, tab.data(), tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    ws.combos = dcomb;
+  }
+  for (int i = 0; i < 2 && rc == 0; i++) {
+    if (cudaStreamCreateWithFlags(&ws.aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    if (rc == 0 && cudaEventCreateWithFlags(&ws.ev_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  }
+  if (rc == 0 && cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
 #undef ALLOC
   if (rc == 0 && cudaMallocHost(&h->h_frames, sizeof(FrameDesc) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaMallocHost(&h->h_out, sizeof(b200AprilTagsDetection_t) * B * g.max_tags) != cudaSuccess) rc = B200AT_ERR_NOMEM;
@@ -377,30 +426,25 @@ int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable) {
   return B200AT_OK;
 }
 
-int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream) {
-  if (!h || !frames || n == 0 || n > h->max_batch) return B200AT_ERR_INVALID_ARG;
-  if (h->in_flight) return B200AT_ERR_INVALID_ARG;
-  int prev = -1;
-  cudaGetDevice(&prev);
-  if (prev != h->device) cudaSetDevice(h->device);
+// Launch every stage of one batch on `stream` and queue the D2H of its results.  `hf` is a pinned frame-table slice
+// that must stay untouched until the stream has consumed it; results land in the pinned arrays `out`, `cnt`, `ctr`.
+static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream, FrameDesc *hf,
+                        b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, bool timing, int *launches_out) {
   Workspace &ws = h->ws;
   Geo &g = ws.g;
   int fast = 1;
   const size_t min_pitch = (size_t)g.W * g.bpp;
   for (uint32_t i = 0; i < n; i++) {
-    if (!frames[i].ptr || frames[i].pitch < min_pitch) {
-      if (prev != h->device) cudaSetDevice(prev);
-      return B200AT_ERR_INVALID_ARG;
-    }
-    h->h_frames[i].ptr = (const uint8_t *)frames[i].ptr;
-    h->h_frames[i].pitch = frames[i].pitch;
+    if (!frames[i].ptr || frames[i].pitch < min_pitch) return B200AT_ERR_INVALID_ARG;
+    hf[i].ptr = (const uint8_t *)frames[i].ptr;
+    hf[i].pitch = frames[i].pitch;
     if (((uintptr_t)frames[i].ptr & 15) || (frames[i].pitch & 15)) fast = 0;
   }
   g.fast_align = fast;
   int launches = 0;
-  cudaError_t e = cudaMemcpyAsync(ws.frames, h->h_frames, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
+  cudaError_t e = cudaMemcpyAsync(ws.frames, hf, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(uint32_t) * CNT_N, stream);
-  const bool tm = h->timing;
+  const bool tm = timing;
 #define STAMP(i) \
   if (tm) cudaEventRecord(h->ev[i], stream)
   STAMP(0);
@@ -419,17 +463,30 @@ int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *f
   launches += launch_finalize(ws, (int)n, stream);
   STAMP(7);
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(h->h_out, ws.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_out_count, ws.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_counters, ws.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+    e = cudaMemcpyAsync(out, ws.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, ws.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, ws.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
   STAMP(8);
 #undef STAMP
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (prev != h->device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
     fprintf(stderr, "[b200apriltags] enqueue failed: %s\n", cudaGetErrorString(e));
     return B200AT_ERR_CUDA;
   }
+  if (launches_out) *launches_out = launches;
+  return B200AT_OK;
+}
+
+int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream) {
+  if (!h || !frames || n == 0 || n > h->max_batch) return B200AT_ERR_INVALID_ARG;
+  if (h->in_flight) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  int launches = 0;
+  int rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches);
+  if (prev != h->device) cudaSetDevice(prev);
+  if (rc != B200AT_OK) return rc;
   h->launches = launches;
   h->cur_stream = stream;
   h->cur_n = n;
@@ -481,49 +538,107 @@ int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *fr
 
 int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, b200AprilTagsDetection_t *dets_out,
                                  cuAprilTagsID_t *ids_out, uint32_t *counts) {
-  if (!h || !frames || n == 0) return B200AT_ERR_INVALID_ARG;
+  if (!h || !frames || n == 0 || h->in_flight) return B200AT_ERR_INVALID_ARG;
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
   const Geo &g = h->ws.g;
+  const uint32_t mt = g.max_tags;
   const size_t row = (size_t)g.W * g.bpp;
+  int rc = B200AT_OK;
+  auto fail = [&](int code) {
+    if (prev != h->device) cudaSetDevice(prev);
+    return code;
+  };
+  // sub-batch size: small enough that copy(k+1) overlaps compute(k) inside one call, large enough to fill the GPU
+  const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 3) / 4)));
   if (!h->d_stage) {
     h->stage_pitch = (row + 255) & ~(size_t)255;
+    h->stage_sub = S;
     void *p = nullptr;
-    if (cudaMalloc(&p, h->stage_pitch * g.H * h->max_batch) != cudaSuccess) {
-      if (prev != h->device) cudaSetDevice(prev);
-      return B200AT_ERR_NOMEM;
-    }
+    if (cudaMalloc(&p, h->stage_pitch * g.H * (size_t)S * 2) != cudaSuccess) return fail(B200AT_ERR_NOMEM);
     h->dev_allocs.push_back(p);
     h->d_stage = (uint8_t *)p;
-  }
-  int rc_all = B200AT_OK;
-  const uint32_t mt = g.max_tags;
-  std::vector<b200AprilTagsFrame_t> dframes(h->max_batch);
-  for (uint32_t i0 = 0; i0 < n; i0 += h->max_batch) {
-    const uint32_t m = std::min(h->max_batch, n - i0);
-    for (uint32_t k = 0; k < m; k++) {
-      uint8_t *dst = h->d_stage + (size_t)k * h->stage_pitch * g.H;
-      cudaError_t e = cudaMemcpy2DAsync(dst, h->stage_pitch, frames[i0 + k].ptr, frames[i0 + k].pitch, row, g.H,
-                                        cudaMemcpyHostToDevice, h->own_stream);
-      if (e != cudaSuccess) {
-        if (prev != h->device) cudaSetDevice(prev);
-        return B200AT_ERR_CUDA;
-      }
-      dframes[k].ptr = dst;
-      dframes[k].pitch = h->stage_pitch;
-    }
-    int rc = b200AprilTagsEnqueueBatch(h, dframes.data(), m, h->own_stream);
-    if (rc == B200AT_OK)
-      rc = b200AprilTagsCollectBatch(h, dets_out ? dets_out + (size_t)i0 * mt : nullptr, ids_out ? ids_out + (size_t)i0 * mt : nullptr,
-                                     counts ? counts + i0 : nullptr);
-    if (rc != B200AT_OK) {
-      rc_all = rc;
-      if (rc != B200AT_ERR_OVERFLOW) break;
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    for (int i = 0; i < 2; i++) {
+      if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+      if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
+  const uint32_t nsub = (n + S - 1) / S;
+  if (h->hp_cap_frames < n || h->hp_cap_subs < nsub) {
+    if (h->hp_frames) cudaFreeHost(h->hp_frames);
+    if (h->hp_out) cudaFreeHost(h->hp_out);
+    if (h->hp_out_count) cudaFreeHost(h->hp_out_count);
+    if (h->hp_counters) cudaFreeHost(h->hp_counters);
+    h->hp_frames = nullptr;
+    h->hp_out = nullptr;
+    h->hp_out_count = nullptr;
+    h->hp_counters = nullptr;
+    h->hp_cap_frames = h->hp_cap_subs = 0;
+    if (cudaMallocHost(&h->hp_frames, sizeof(FrameDesc) * n) != cudaSuccess || cudaMallocHost(&h->hp_out, sizeof(b200AprilTagsDetection_t) * (size_t)n * mt) != cudaSuccess ||
+        cudaMallocHost(&h->hp_out_count, sizeof(uint32_t) * n) != cudaSuccess || cudaMallocHost(&h->hp_counters, sizeof(uint32_t) * CNT_N * nsub) != cudaSuccess)
+      return fail(B200AT_ERR_NOMEM);
+    h->hp_cap_frames = n;
+    h->hp_cap_subs = nsub;
+  }
+  std::vector<b200AprilTagsFrame_t> dframes(S);
+  int launches = 0;
+  for (uint32_t k = 0; k < nsub && rc == B200AT_OK; k++) {
+    const uint32_t i0 = k * S, m = std::min(S, n - i0);
+    const int slot = (int)(k & 1);
+    uint8_t *slot_base = h->d_stage + (size_t)slot * S * h->stage_pitch * g.H;
+    cudaError_t e = cudaSuccess;
+    if (k >= 2) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
+    for (uint32_t j = 0; j < m && e == cudaSuccess; j++) {
+      if (!frames[i0 + j].ptr || frames[i0 + j].pitch < row) return fail(B200AT_ERR_INVALID_ARG);
+      uint8_t *dst = slot_base + (size_t)j * h->stage_pitch * g.H;
+      e = cudaMemcpy2DAsync(dst, h->stage_pitch, frames[i0 + j].ptr, frames[i0 + j].pitch, row, g.H, cudaMemcpyHostToDevice, h->copy_stream);
+      dframes[j].ptr = dst;
+      dframes[j].pitch = h->stage_pitch;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[slot], h->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->own_stream, h->ev_copied[slot], 0);
+    if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    int l = 0;
+    rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
+                      h->hp_counters + (size_t)k * CNT_N, false, &l);
+    launches += l;
+    if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], h->own_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  }
+  cudaError_t es = cudaStreamSynchronize(h->own_stream);
+  cudaStreamSynchronize(h->copy_stream);
   if (prev != h->device) cudaSetDevice(prev);
-  return rc_all;
+  if (rc != B200AT_OK) return rc;
+  if (es != cudaSuccess) {
+    fprintf(stderr, "[b200apriltags] batch failed: %s\n", cudaGetErrorString(es));
+    return B200AT_ERR_CUDA;
+  }
+  uint32_t status = 0;
+  uint64_t pts = 0, clu = 0, qd = 0, dt = 0;
+  for (uint32_t k = 0; k < nsub; k++) {
+    const uint32_t *c = h->hp_counters + (size_t)k * CNT_N;
+    status |= c[CNT_STATUS];
+    pts += c[CNT_POINTS];
+    clu += c[CNT_CLUSTERS];
+    qd += c[CNT_QUADS];
+    dt += c[CNT_DETS];
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t c = std::min(h->hp_out_count[i], mt);
+    if (counts) counts[i] = c;
+    if (dets_out) memcpy(dets_out + (size_t)i * mt, h->hp_out + (size_t)i * mt, sizeof(b200AprilTagsDetection_t) * c);
+    if (ids_out)
+      for (uint32_t k = 0; k < c; k++) to_id_struct(h->hp_out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
+  }
+  h->last_status = status;
+  h->launches = launches;
+  h->last_counters[0] = (uint64_t)launches;
+  h->last_counters[1] = pts;
+  h->last_counters[2] = clu;
+  h->last_counters[3] = qd;
+  h->last_counters[5] = dt;
+  return status ? B200AT_ERR_OVERFLOW : B200AT_OK;
 }
 
 uint32_t cuAprilTagsDetect(cuAprilTagsHandle h, const cuAprilTagsImageInput_t *img, cuAprilTagsID_t *tags_out, uint32_t *num_tags,

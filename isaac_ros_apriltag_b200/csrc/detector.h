@@ -22,6 +22,7 @@ namespace b200at {
 
 constexpr int kMaxFamilies = B200AT_NUM_FAMILIES;
 constexpr int kMaxBits = 52;
+constexpr int kMaxNMaxima = 12;  // upper bound of the max_nmaxima option (pair tables live in shared memory)
 
 struct DevFamily {
   int nbits, ncodes, width_at_border, total_width, reversed_border, index;
@@ -60,7 +61,8 @@ struct Cand {  // decoded candidate before reconcile
 };
 
 // counters[] slots
-enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_N = 8 };
+enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_WORK_DECODE = 7,
+       CNT_BIN0 = 8 /* ..10: clusters per size bin */, CNT_WORK0 = 11 /* ..13: quad-fit work queues */, CNT_N = 16 };
 enum { ST_HASH_FULL = 1, ST_POINTS_FULL = 2, ST_CLUSTERS_FULL = 4, ST_QUADS_FULL = 8, ST_CANDS_FULL = 16, ST_OUT_TRUNC = 32 };
 
 struct Geo {
@@ -118,6 +120,11 @@ struct Workspace {
   b200AprilTagsDetection_t *out;
   uint32_t *out_count;   // [B]
   uint32_t *counters;    // [CNT_N]
+  uint32_t *bin_idx;     // [3][clu_cap] cluster indices per size bin
+  const unsigned char *combos;  // per nm (4..kMaxNMaxima): all m0<m1<m2<m3 < nm in lexicographic order, uchar4 each
+  int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
+  cudaStream_t aux[2];   // side streams: the three quad-fit bins run concurrently
+  cudaEvent_t ev_fork, ev_join[2];
   uint8_t blur_k[32];
   int blur_ksz;
   int blur_sharpen;

@@ -35,12 +35,18 @@ __device__ __forceinline__ Nb ccl_links(int v, int vL, int vU, int vUL, int vUR,
   return n;
 }
 
+// find with compression of the start node.  Safe under concurrent atomicMin unions: unions only ever modify ROOT
+// entries, a non-root never becomes a root again, and every value written here is an ancestor of the start node.
 __device__ __forceinline__ uint32_t find_s(volatile uint32_t *L, uint32_t a) {
+  const uint32_t start = a;
   uint32_t p = L[a];
-  while (p != a) {
+  if (p == a) return a;
+  const uint32_t first = p;
+  do {
     a = p;
     p = L[a];
-  }
+  } while (p != a);
+  if (first != a) L[start] = a;
   return a;
 }
 __device__ __forceinline__ void unite_s(uint32_t *L, uint32_t a, uint32_t b) {
@@ -61,12 +67,16 @@ __device__ __forceinline__ void unite_s(uint32_t *L, uint32_t a, uint32_t b) {
     }
   } while (!done);
 }
-__device__ __forceinline__ uint32_t find_g(const uint32_t *L, uint32_t a) {
+__device__ __forceinline__ uint32_t find_g(uint32_t *L, uint32_t a) {
+  const uint32_t start = a;
   uint32_t p = __ldcg(&L[a]);
-  while (p != a) {
+  if (p == a) return a;
+  const uint32_t first = p;
+  do {
     a = p;
     p = __ldcg(&L[a]);
-  }
+  } while (p != a);
+  if (first != a) __stcg(&L[start], a);  // compression (see find_s)
   return a;
 }
 __device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams f
 
   for (;;) {
     uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(&counters[7], 1u);
+    if (lane == 0) qi = atomicAdd(&counters[CNT_WORK_DECODE], 1u);
     qi = __shfl_sync(0xffffffffu, qi, 0);
     if (qi >= nq) break;
     const QuadRec q0 = quads[qi];

@@ -1,31 +1,68 @@
-// k_quad.cu -- fit_quads (a10): one CTA per boundary-point cluster.
+// k_quad.cu -- fit_quads (a10).
 // Restates AprilRobotics fit_quad / ptsort / compute_lfps / quad_segment_maxima / fit_line
 // (apriltag_quad_thresh.c) with the SAME floating-point types and evaluation order as the
-// CPU oracle, so accept/reject decisions and the float corners are bit-identical (built with -fmad=false):
-//   * angle-proxy `slope` in float, sort key = (slope, y, x) as one u64 -> bitonic sort in shared memory
-//   * weighted prefix moments in double, accumulated SEQUENTIALLY (a parallel scan would change the roundings):
-//     the six moments run as six lanes of one warp, each walking the cluster once
-//   * line-fit error per point, 7-tap smoothing, local maxima, top-(max_nmaxima) selection, the C(n,4)
-//     corner search (pair table + parallel lexicographic arg-min), final four lines, corner intersections,
-//     area and angle gates.
-// Latency/atomic-bound stage (O(boundary points)); bytes are negligible next to the dense stages.
+// CPU oracle, so accept/reject decisions and the float corners are bit-identical (built with -fmad=false).
+//
+// One CTA per boundary-point cluster, clusters binned by size so the CTA shape fits the work:
+//   bin A  n <= 256   : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (16 KB)
+//   bin B  n <= 1024  : 128-thread CTA, everything in shared memory (64 KB)
+//   bin C  n  > 1024  : 256-thread CTA, sort keys in shared memory (64 KB), moments / errors in an L2-resident scratch
+// Per cluster: slope keys (float) -> bitonic sort of u64 (slope|y|x) keys in shared memory (steps with stride < 64
+// need only warp-level sync) -> line-fit terms -> SEQUENTIAL double prefix sums (a parallel scan would change the
+// roundings; the six moments run as six lanes reading shared memory) -> per-point window error -> 7-tap smoothing ->
+// local maxima -> top-(max_nmaxima) by rank counting -> pair table of line fits -> C(n,4) search over a precomputed
+// combination table with lexicographic arg-min -> corners, area and angle gates.
+// Latency-bound stage (O(boundary points)); HBM bytes are ~12 B per point (read packed point, write sorted key).
 #include <math_constants.h>
 
 #include "detector.h"
 
 namespace b200at {
 
-constexpr int QT = 128;            // threads per CTA
-constexpr int SORT_SMEM = 4096;    // keys sorted in shared memory up to this many points (32 KB)
-constexpr int MAXM = 16;           // max_nmaxima upper bound
+constexpr int MAXM = kMaxNMaxima;  // max_nmaxima upper bound
+constexpr int SCAN_CH = 512;   // staging chunk of the sequential scan when moments live in global memory
 
-__device__ __forceinline__ void fit_line_dev(const LineFitPt *__restrict__ lfps, int sz, int i0, int i1, double *lineparm,
-                                             double *err, double *mse) {
+struct LF6 {
+  double Mx, My, Mxx, Mxy, Myy, W;
+};
+
+// moments accessor: SoA in shared memory (stride = capacity + 1 doubles: the six scan lanes hit six different banks)
+// or AoS in global memory
+template <bool SMEM>
+struct LfAcc {
+  const double *m;        // smem SoA base
+  int stride;
+  const LineFitPt *g;     // global AoS base
+  __device__ __forceinline__ LF6 get(int i) const {
+    LF6 r;
+    if (SMEM) {
+      r.Mx = m[i];
+      r.My = m[stride + i];
+      r.Mxx = m[2 * stride + i];
+      r.Mxy = m[3 * stride + i];
+      r.Myy = m[4 * stride + i];
+      r.W = m[5 * stride + i];
+    } else {
+      const LineFitPt p = g[i];
+      r.Mx = p.Mx;
+      r.My = p.My;
+      r.Mxx = p.Mxx;
+      r.Mxy = p.Mxy;
+      r.Myy = p.Myy;
+      r.W = p.W;
+    }
+    return r;
+  }
+};
+
+template <bool SMEM>
+__device__ __forceinline__ void fit_line_dev(const LfAcc<SMEM> &lf, int sz, int i0, int i1, double *lineparm, double *err,
+                                             double *mse) {
   double Mx, My, Mxx, Myy, Mxy, W;
   int N;
   if (i0 < i1) {
     N = i1 - i0 + 1;
-    LineFitPt a = lfps[i1];
+    LF6 a = lf.get(i1);
     Mx = a.Mx;
     My = a.My;
     Mxx = a.Mxx;
@@ -33,7 +70,7 @@ __device__ __forceinline__ void fit_line_dev(const LineFitPt *__restrict__ lfps,
     Myy = a.Myy;
     W = a.W;
     if (i0 > 0) {
-      LineFitPt b = lfps[i0 - 1];
+      LF6 b = lf.get(i0 - 1);
       Mx -= b.Mx;
       My -= b.My;
       Mxx -= b.Mxx;
@@ -42,7 +79,7 @@ __device__ __forceinline__ void fit_line_dev(const LineFitPt *__restrict__ lfps,
       W -= b.W;
     }
   } else {
-    LineFitPt e = lfps[sz - 1], b = lfps[i0 - 1], a = lfps[i1];
+    LF6 e = lf.get(sz - 1), b = lf.get(i0 - 1), a = lf.get(i1);
     Mx = e.Mx - b.Mx;
     My = e.My - b.My;
     Mxx = e.Mxx - b.Mxx;
@@ -101,37 +138,57 @@ __device__ __forceinline__ uint32_t float_orderable(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// ascending bitonic network in the "mirror" formulation: every compare-exchange puts the smaller key at the
-// lower index, so the virtual +inf padding above n never has to be stored (works in shared or global memory).
-__device__ void sort_keys(unsigned long long *a, int n) {
-  int N = 1;
-  while (N < n) N <<= 1;
-  for (int k = 2; k <= N; k <<= 1) {
-    for (int i = threadIdx.x; i < N; i += QT) {
-      int l = i ^ (k - 1);
-      if (l > i && l < n) {
-        unsigned long long x = a[i], y = a[l];
-        if (x > y) {
-          a[i] = y;
-          a[l] = x;
-        }
-      }
-    }
+template <int THREADS>
+__device__ __forceinline__ void cta_sync() {
+  if (THREADS == 32)
+    __syncwarp();
+  else
     __syncthreads();
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < N; i += QT) {
-        int l = i ^ j;
-        if (l > i && l < n) {
-          unsigned long long x = a[i], y = a[l];
-          if (x > y) {
-            a[i] = y;
-            a[l] = x;
-          }
-        }
-      }
-      __syncthreads();
+}
+
+__device__ __forceinline__ void cas_keys(unsigned long long *a, int i, int l, int n) {
+  if (l < n) {
+    unsigned long long x = a[i], y = a[l];
+    if (x > y) {
+      a[i] = y;
+      a[l] = x;
     }
   }
+}
+
+// Ascending bitonic network, "mirror" formulation (every compare-exchange puts the smaller key at the lower index, so
+// the virtual +inf padding above n is never stored).  Work is organised by PAIRS: pair p of a step with stride j touches
+// elements inside one aligned 2j window, so for 2j <= 64 a warp that owns 32 consecutive pairs owns a closed 64-element
+// window and the step needs only __syncwarp(); only strides >= 64 use the block barrier.
+template <int THREADS>
+__device__ void sort_keys(unsigned long long *a, int n) {
+  int N = 64;
+  while (N < n) N <<= 1;
+  const int half = N >> 1;
+  const int tid = threadIdx.x;
+  for (int k = 2; k <= N; k <<= 1) {
+    // mirror step: element i (lower half of its k-block) with i ^ (k-1)
+    {
+      const int hk = k >> 1;
+      for (int p = tid; p < half; p += THREADS) {
+        int blk = p / hk, o = p - blk * hk;
+        int i = blk * k + o, l = blk * k + (k - 1 - o);
+        if (i < n) cas_keys(a, i, l, n);
+      }
+      if (k <= 64) __syncwarp(); else cta_sync<THREADS>();
+    }
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int p = tid; p < half; p += THREADS) {
+        int blk = p / j, o = p - blk * j;
+        int i = blk * 2 * j + o, l = i + j;
+        if (i < n) cas_keys(a, i, l, n);
+      }
+      if (2 * j <= 64) __syncwarp(); else cta_sync<THREADS>();
+    }
+    // stages >= 64 are followed by a stage whose first steps cross warp-owned windows: block-wide visibility
+    if (k >= 64) cta_sync<THREADS>();
+  }
+  cta_sync<THREADS>();
 }
 
 struct BBoxRed {
@@ -139,41 +196,56 @@ struct BBoxRed {
   long long s1;
 };
 
-__global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
-                                                const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys,
-                                                LineFitPt *__restrict__ lfps_pool, double *__restrict__ errs_pool,
-                                                const uint8_t *__restrict__ dec, QuadRec *__restrict__ quads,
-                                                uint32_t *__restrict__ counters, int Wp) {
-  extern __shared__ unsigned long long skeys[];
-  __shared__ BBoxRed s_red[QT / 32];
+// combination table for the current nm: all (m0<m1<m2<m3) < nm in lexicographic order, one byte each
+struct ComboTable {
+  const uchar4 *c;
+  int off[18];
+};
+
+template <int THREADS, int NCAP, bool ALL_SMEM>
+__global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
+                                                     const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
+                                                     unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
+                                                     double *__restrict__ errs_pool, const uint8_t *__restrict__ dec,
+                                                     QuadRec *__restrict__ quads, uint32_t *__restrict__ counters, ComboTable combos,
+                                                     int Wp) {
+  constexpr int NW = THREADS / 32;
+  constexpr int MSTRIDE = (ALL_SMEM ? NCAP : SCAN_CH) + 1;
+  extern __shared__ unsigned long long dsm[];
+  unsigned long long *skeys = dsm;                                  // [NCAP]  (later: errA)
+  double *s_errB = reinterpret_cast<double *>(dsm + NCAP);          // [NCAP]  (ALL_SMEM only)
+  double *s_M = reinterpret_cast<double *>(dsm + (ALL_SMEM ? 2 * NCAP : NCAP));  // [6][MSTRIDE]
+  __shared__ BBoxRed s_red[NW];
   __shared__ int s_cluster;
   __shared__ int s_fm[MAXM];
   __shared__ int s_nm;
-  __shared__ int s_scan[QT / 32];
+  __shared__ int s_scan[NW];
   __shared__ int s_run;
-  __shared__ double s_rv[QT / 32];
-  __shared__ int s_ri[QT / 32];
+  __shared__ double s_rv[NW];
+  __shared__ int s_ri[NW];
+  __shared__ unsigned int s_rr[NW];
   __shared__ double s_thresh;
+  __shared__ double s_carry[6];
   __shared__ double p_err[MAXM][MAXM], p_mse[MAXM][MAXM], p_nx[MAXM][MAXM], p_ny[MAXM][MAXM];
-  __shared__ unsigned long long s_rr[QT / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t ncl = min(counters[CNT_CLUSTERS], g.clu_cap);
+  const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_cluster = (int)atomicAdd(&counters[6], 1u);
-    __syncthreads();
-    const int c = s_cluster;
-    if ((uint32_t)c >= ncl) break;
-    const ClusterRec cr = clusters[c];
+    cta_sync<THREADS>();
+    if (tid == 0) s_cluster = (int)atomicAdd(&counters[CNT_WORK0 + bin], 1u);
+    cta_sync<THREADS>();
+    const int cw = s_cluster;
+    if ((uint32_t)cw >= nbin) break;
+    const ClusterRec cr = clusters[bin_idx[(size_t)bin * g.clu_cap + cw]];
     const int sz = (int)cr.count;
     const uint32_t o = cr.offset;
     const uint8_t *im = dec + (size_t)cr.frame * g.Hd * Wp;
+    const bool keys_in_smem = sz <= NCAP;  // bin C clusters larger than its capacity fall back to global memory
 
     // ---- Phase A: bounding box + integer sums for the border-polarity test ----
     BBoxRed r = {1 << 30, -1, 1 << 30, -1, 0, 0, 0};
-    for (int i = tid; i < sz; i += QT) {
+    for (int i = tid; i < sz; i += THREADS) {
       uint32_t p = pts[o + i];
       int x = p & 0x3fff, y = (p >> 14) & 0x3fff;
       int cxg = (p >> 28) & 3, cyg = (p >> 30) & 3;
@@ -195,18 +267,20 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
       r.sgy += __shfl_xor_sync(0xffffffffu, r.sgy, of);
       r.s1 += __shfl_xor_sync(0xffffffffu, r.s1, of);
     }
-    if (lane == 0) s_red[wid] = r;
-    __syncthreads();
-    r = s_red[0];
-    for (int w = 1; w < QT / 32; w++) {
-      BBoxRed q = s_red[w];
-      r.xmin = min(r.xmin, q.xmin);
-      r.xmax = max(r.xmax, q.xmax);
-      r.ymin = min(r.ymin, q.ymin);
-      r.ymax = max(r.ymax, q.ymax);
-      r.sgx += q.sgx;
-      r.sgy += q.sgy;
-      r.s1 += q.s1;
+    if (NW > 1) {
+      if (lane == 0) s_red[wid] = r;
+      __syncthreads();
+      r = s_red[0];
+      for (int w = 1; w < NW; w++) {
+        BBoxRed q = s_red[w];
+        r.xmin = min(r.xmin, q.xmin);
+        r.xmax = max(r.xmax, q.xmax);
+        r.ymin = min(r.ymin, q.ymin);
+        r.ymax = max(r.ymax, q.ymax);
+        r.sgx += q.sgx;
+        r.sgy += q.sgy;
+        r.s1 += q.s1;
+      }
     }
     if ((r.xmax - r.xmin) * (r.ymax - r.ymin) < fp.tag_width) continue;
     const float cx = (float)((r.xmin + r.xmax) * 0.5 + 0.05118);
@@ -218,9 +292,8 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
     if (!fp.normal_border && !reversed) continue;
 
     // ---- Phase C: sort keys (slope | y | x) ----
-    const bool in_smem = sz <= SORT_SMEM;
-    unsigned long long *ka = in_smem ? skeys : (keys + o);
-    for (int i = tid; i < sz; i += QT) {
+    unsigned long long *ka = keys_in_smem ? skeys : (keys + o);
+    for (int i = tid; i < sz; i += THREADS) {
       uint32_t p = pts[o + i];
       int x = p & 0x3fff, y = (p >> 14) & 0x3fff;
       float dx = (float)x - cx;
@@ -242,99 +315,136 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
       float slope = quadrant + dy / dx;
       ka[i] = ((unsigned long long)float_orderable(slope) << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
     }
-    __syncthreads();
-    sort_keys(ka, sz);
-    if (in_smem) {
-      for (int i = tid; i < sz; i += QT) keys[o + i] = skeys[i];
+    cta_sync<THREADS>();
+    sort_keys<THREADS>(ka, sz);
+    if (keys_in_smem) {
+      for (int i = tid; i < sz; i += THREADS) keys[o + i] = skeys[i];
     }
-    __syncthreads();
 
     // ---- Phase E: line-fit terms, then SEQUENTIAL prefix sums (six lanes, one per moment) ----
-    LineFitPt *lfps = lfps_pool + o;
-    for (int i = tid; i < sz; i += QT) {
-      unsigned long long k = ka[i];
-      int px = (int)(k & 0xffff), py = (int)((k >> 16) & 0xffff);
-      double x = px * .5 + 0.5;
-      double y = py * .5 + 0.5;
-      int ix = (int)x, iy = (int)y;
-      double W = 1;
-      if (ix > 0 && ix + 1 < g.Wd && iy > 0 && iy + 1 < g.Hd) {
-        int grad_x = (int)im[(size_t)iy * Wp + ix + 1] - (int)im[(size_t)iy * Wp + ix - 1];
-        int grad_y = (int)im[(size_t)(iy + 1) * Wp + ix] - (int)im[(size_t)(iy - 1) * Wp + ix];
-        W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+    LineFitPt *lfps_g = lfps_pool + o;
+    const int chunk = ALL_SMEM ? NCAP : SCAN_CH;
+    if (!ALL_SMEM && tid < 6) s_carry[tid] = 0.0;
+    for (int c0 = 0; c0 < sz; c0 += chunk) {
+      const int cn = min(chunk, sz - c0);
+      for (int ii = tid; ii < cn; ii += THREADS) {
+        const unsigned long long k = ka[c0 + ii];
+        const int px = (int)(k & 0xffff), py = (int)((k >> 16) & 0xffff);
+        const double x = px * .5 + 0.5;
+        const double y = py * .5 + 0.5;
+        const int ix = (int)x, iy = (int)y;
+        double W = 1;
+        if (ix > 0 && ix + 1 < g.Wd && iy > 0 && iy + 1 < g.Hd) {
+          int grad_x = (int)im[(size_t)iy * Wp + ix + 1] - (int)im[(size_t)iy * Wp + ix - 1];
+          int grad_y = (int)im[(size_t)(iy + 1) * Wp + ix] - (int)im[(size_t)(iy - 1) * Wp + ix];
+          W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+        }
+        const double fx = x, fy = y;
+        s_M[ii] = W * fx;
+        s_M[MSTRIDE + ii] = W * fy;
+        s_M[2 * MSTRIDE + ii] = W * fx * fx;
+        s_M[3 * MSTRIDE + ii] = W * fx * fy;
+        s_M[4 * MSTRIDE + ii] = W * fy * fy;
+        s_M[5 * MSTRIDE + ii] = W;
       }
-      double fx = x, fy = y;
-      LineFitPt t;
-      t.Mx = W * fx;
-      t.My = W * fy;
-      t.Mxx = W * fx * fx;
-      t.Mxy = W * fx * fy;
-      t.Myy = W * fy * fy;
-      t.W = W;
-      lfps[i] = t;
+      cta_sync<THREADS>();
+      if (tid < 6) {
+        double *base = s_M + tid * MSTRIDE;
+        double acc = ALL_SMEM ? 0.0 : s_carry[tid];
+        int i = 0;
+        for (; i + 8 <= cn; i += 8) {
+          double t0 = base[i], t1 = base[i + 1], t2 = base[i + 2], t3 = base[i + 3], t4 = base[i + 4], t5 = base[i + 5],
+                 t6 = base[i + 6], t7 = base[i + 7];
+          acc += t0;
+          base[i] = acc;
+          acc += t1;
+          base[i + 1] = acc;
+          acc += t2;
+          base[i + 2] = acc;
+          acc += t3;
+          base[i + 3] = acc;
+          acc += t4;
+          base[i + 4] = acc;
+          acc += t5;
+          base[i + 5] = acc;
+          acc += t6;
+          base[i + 6] = acc;
+          acc += t7;
+          base[i + 7] = acc;
+        }
+        for (; i < cn; i++) {
+          acc += base[i];
+          base[i] = acc;
+        }
+        if (!ALL_SMEM) s_carry[tid] = acc;
+      }
+      cta_sync<THREADS>();
+      if (!ALL_SMEM) {
+        for (int ii = tid; ii < cn; ii += THREADS) {
+          LineFitPt t;
+          t.Mx = s_M[ii];
+          t.My = s_M[MSTRIDE + ii];
+          t.Mxx = s_M[2 * MSTRIDE + ii];
+          t.Mxy = s_M[3 * MSTRIDE + ii];
+          t.Myy = s_M[4 * MSTRIDE + ii];
+          t.W = s_M[5 * MSTRIDE + ii];
+          lfps_g[c0 + ii] = t;
+        }
+        __syncthreads();
+      }
     }
-    __syncthreads();
-    if (tid < 6) {
-      double *base = reinterpret_cast<double *>(lfps) + tid;
-      double acc = 0;
-      int i = 0;
-      for (; i + 4 <= sz; i += 4) {
-        double t0 = base[(size_t)(i + 0) * 6], t1 = base[(size_t)(i + 1) * 6], t2 = base[(size_t)(i + 2) * 6],
-               t3 = base[(size_t)(i + 3) * 6];
-        acc += t0;
-        base[(size_t)(i + 0) * 6] = acc;
-        acc += t1;
-        base[(size_t)(i + 1) * 6] = acc;
-        acc += t2;
-        base[(size_t)(i + 2) * 6] = acc;
-        acc += t3;
-        base[(size_t)(i + 3) * 6] = acc;
-      }
-      for (; i < sz; i++) {
-        acc += base[(size_t)i * 6];
-        base[(size_t)i * 6] = acc;
-      }
-    }
-    __syncthreads();
+    LfAcc<ALL_SMEM> lf;
+    lf.m = s_M;
+    lf.stride = MSTRIDE;
+    lf.g = lfps_g;
 
     // ---- Phase F/G: per-point line-fit error over a +-ksz window, then 7-tap smoothing (circular) ----
     const int ksz = min(20, sz / 12);
     if (ksz < 2) continue;
-    double *errA = errs_pool + (size_t)2 * o, *errB = errA + sz;
-    for (int i = tid; i < sz; i += QT) {
+    // errA aliases the (now dead) key area when the keys are in shared memory
+    double *errA = keys_in_smem ? reinterpret_cast<double *>(skeys) : (errs_pool + (size_t)2 * o);
+    double *errB = ALL_SMEM ? s_errB : (errs_pool + (size_t)2 * o + sz);
+    for (int i = tid; i < sz; i += THREADS) {
       double e;
-      fit_line_dev(lfps, sz, (i + sz - ksz) % sz, (i + ksz) % sz, nullptr, &e, nullptr);
+      fit_line_dev(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, nullptr, &e, nullptr);
       errA[i] = e;
     }
-    __syncthreads();
-    for (int i = tid; i < sz; i += QT) {
+    cta_sync<THREADS>();
+    for (int i = tid; i < sz; i += THREADS) {
       double acc = 0;
 #pragma unroll
-      for (int k = 0; k < 7; k++) acc += errA[(i + k - 3 + sz) % sz] * fp.smooth[k];
+      for (int k = 0; k < 7; k++) {
+        int j = i + k - 3;
+        j = j < 0 ? j + sz : (j >= sz ? j - sz : j);
+        acc += errA[j] * fp.smooth[k];
+      }
       errB[i] = acc;
     }
-    __syncthreads();
+    cta_sync<THREADS>();
 
-    // ---- Phase H: local maxima, compacted in index order ----
-    double *merr = errA;                                                  // copy of maxima errs (top-k removal)
-    uint32_t *midx = reinterpret_cast<uint32_t *>(errA + (sz + 1) / 2);    // maxima indices
+    // ---- Phase H: local maxima, compacted in index order (errA area is dead again: reuse it) ----
+    double *merr = errA;                                                  // values of the maxima
+    uint32_t *midx = reinterpret_cast<uint32_t *>(errA + (sz + 1) / 2);    // their indices
     if (tid == 0) s_run = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < sz; i0 += QT) {
+    cta_sync<THREADS>();
+    for (int i0 = 0; i0 < sz; i0 += THREADS) {
       const int i = i0 + tid;
       bool is_max = false;
       double e = 0;
       if (i < sz) {
         e = errB[i];
-        is_max = e > errB[(i + 1) % sz] && e > errB[(i + sz - 1) % sz];
+        is_max = e > errB[i + 1 == sz ? 0 : i + 1] && e > errB[i == 0 ? sz - 1 : i - 1];
       }
-      unsigned bal = __ballot_sync(0xffffffffu, is_max);
-      if (lane == 0) s_scan[wid] = __popc(bal);
-      __syncthreads();
-      int woff = 0, tot = 0;
-      for (int w = 0; w < QT / 32; w++) {
-        if (w < wid) woff += s_scan[w];
-        tot += s_scan[w];
+      const unsigned bal = __ballot_sync(0xffffffffu, is_max);
+      int woff = 0, tot = __popc(bal);
+      if (NW > 1) {
+        if (lane == 0) s_scan[wid] = tot;
+        __syncthreads();
+        tot = 0;
+        for (int w = 0; w < NW; w++) {
+          if (w < wid) woff += s_scan[w];
+          tot += s_scan[w];
+        }
       }
       const int run = s_run;
       if (is_max) {
@@ -342,55 +452,69 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
         midx[pos] = (uint32_t)i;
         merr[pos] = e;
       }
-      __syncthreads();
+      cta_sync<THREADS>();
       if (tid == 0) s_run = run + tot;
-      __syncthreads();
+      cta_sync<THREADS>();
     }
     const int nmax_all = s_run;
     if (nmax_all < 4) continue;
 
-    // ---- Phase I: keep the max_nmaxima best maxima (threshold = (max_nmaxima+1)-th largest error) ----
+    // ---- Phase I: keep the max_nmaxima best maxima: threshold = value of descending rank max_nmaxima ----
     if (nmax_all > fp.max_nmaxima) {
-      for (int round = 0; round <= fp.max_nmaxima; round++) {
-        double bv = -CUDART_INF;
-        int bi = 0x7fffffff;
-        for (int i = tid; i < nmax_all; i += QT) {
-          double v = merr[i];
-          if (v > bv || (v == bv && i < bi)) {
-            bv = v;
-            bi = i;
+      if (nmax_all <= 1024) {
+        // rank by counting (unique ranks: ties broken by position), O(n^2 / THREADS)
+        for (int i = tid; i < nmax_all; i += THREADS) {
+          const double v = merr[i];
+          int rank = 0;
+          for (int j = 0; j < nmax_all; j++) {
+            const double u = merr[j];
+            rank += (u > v || (u == v && j < i)) ? 1 : 0;
           }
+          if (rank == fp.max_nmaxima) s_thresh = v;
         }
-        for (int of = 16; of > 0; of >>= 1) {
-          double ov = __shfl_xor_sync(0xffffffffu, bv, of);
-          int oi = __shfl_xor_sync(0xffffffffu, bi, of);
-          if (ov > bv || (ov == bv && oi < bi)) {
-            bv = ov;
-            bi = oi;
-          }
-        }
-        if (lane == 0) {
-          s_rv[wid] = bv;
-          s_ri[wid] = bi;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          for (int w = 1; w < QT / 32; w++) {
-            if (s_rv[w] > bv || (s_rv[w] == bv && s_ri[w] < bi)) {
-              bv = s_rv[w];
-              bi = s_ri[w];
+        cta_sync<THREADS>();
+      } else {
+        for (int round = 0; round <= fp.max_nmaxima; round++) {
+          double bv = -CUDART_INF;
+          int bi = 0x7fffffff;
+          for (int i = tid; i < nmax_all; i += THREADS) {
+            double v = merr[i];
+            if (v > bv || (v == bv && i < bi)) {
+              bv = v;
+              bi = i;
             }
           }
-          s_thresh = bv;
-          if (bi != 0x7fffffff) merr[bi] = -CUDART_INF;
+          for (int of = 16; of > 0; of >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, of);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, of);
+            if (ov > bv || (ov == bv && oi < bi)) {
+              bv = ov;
+              bi = oi;
+            }
+          }
+          if (lane == 0) {
+            s_rv[wid] = bv;
+            s_ri[wid] = bi;
+          }
+          cta_sync<THREADS>();
+          if (tid == 0) {
+            for (int w = 1; w < NW; w++) {
+              if (s_rv[w] > bv || (s_rv[w] == bv && s_ri[w] < bi)) {
+                bv = s_rv[w];
+                bi = s_ri[w];
+              }
+            }
+            s_thresh = bv;
+            if (bi != 0x7fffffff) merr[bi] = -CUDART_INF;
+          }
+          cta_sync<THREADS>();
         }
-        __syncthreads();
       }
       const double maxima_thresh = s_thresh;
       // ordered compaction of maxima with err > thresh (errB holds the untouched values)
       if (tid == 0) s_run = 0;
-      __syncthreads();
-      for (int i0 = 0; i0 < nmax_all; i0 += QT) {
+      cta_sync<THREADS>();
+      for (int i0 = 0; i0 < nmax_all; i0 += THREADS) {
         const int i = i0 + tid;
         bool keep = false;
         uint32_t idx = 0;
@@ -398,57 +522,58 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
           idx = midx[i];
           keep = !(errB[idx] <= maxima_thresh);
         }
-        unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_scan[wid] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int w = 0; w < QT / 32; w++) {
-          if (w < wid) woff += s_scan[w];
-          tot += s_scan[w];
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        int woff = 0, tot = __popc(bal);
+        if (NW > 1) {
+          if (lane == 0) s_scan[wid] = tot;
+          __syncthreads();
+          tot = 0;
+          for (int w = 0; w < NW; w++) {
+            if (w < wid) woff += s_scan[w];
+            tot += s_scan[w];
+          }
         }
         const int run = s_run;
         if (keep) {
           int pos = run + woff + __popc(bal & ((1u << lane) - 1));
           if (pos < MAXM) s_fm[pos] = (int)idx;
         }
-        __syncthreads();
+        cta_sync<THREADS>();
         if (tid == 0) s_run = run + tot;
-        __syncthreads();
+        cta_sync<THREADS>();
       }
       if (tid == 0) s_nm = min(s_run, MAXM);
     } else {
       if (tid < nmax_all) s_fm[tid] = (int)midx[tid];
       if (tid == 0) s_nm = nmax_all;
     }
-    __syncthreads();
+    cta_sync<THREADS>();
     const int nm = s_nm;
     if (nm < 4) continue;
 
     // ---- Phase J: line fits between every ordered pair of kept maxima ----
-    for (int t = tid; t < nm * nm; t += QT) {
-      int a = t / nm, b = t % nm;
+    for (int t = tid; t < nm * nm; t += THREADS) {
+      int a = t / nm, b = t - a * nm;
       if (a == b) continue;
       double lp[4], e, m;
-      fit_line_dev(lfps, sz, s_fm[a], s_fm[b], lp, &e, &m);
+      fit_line_dev(lf, sz, s_fm[a], s_fm[b], lp, &e, &m);
       p_err[a][b] = e;
       p_mse[a][b] = m;
       p_nx[a][b] = lp[2];
       p_ny[a][b] = lp[3];
     }
-    __syncthreads();
+    cta_sync<THREADS>();
 
     // ---- Phase K: best (m0<m1<m2<m3); ties resolved to the lexicographically first, like the serial loops ----
     double best = CUDART_INF;
     uint32_t brank = 0xffffffffu;
     {
       const double max_mse = (double)fp.max_line_fit_mse, max_dot = (double)fp.cos_critical_rad;
-      const int total = nm * nm * nm * nm;
-      for (int t = tid; t < total; t += QT) {
-        int m3 = t % nm, q = t / nm;
-        int m2 = q % nm;
-        q /= nm;
-        int m1 = q % nm, m0 = q / nm;
-        if (!(m0 < m1 && m1 < m2 && m2 < m3)) continue;
+      const uchar4 *ctab = combos.c + combos.off[nm];
+      const int ncomb = combos.off[nm + 1] - combos.off[nm];
+      for (int t = tid; t < ncomb; t += THREADS) {
+        const uchar4 c = ctab[t];
+        const int m0 = c.x, m1 = c.y, m2 = c.z, m3 = c.w;
         if (p_mse[m0][m1] > max_mse) continue;
         if (p_mse[m1][m2] > max_mse) continue;
         double dot = p_nx[m0][m1] * p_nx[m1][m2] + p_ny[m0][m1] * p_ny[m1][m2];
@@ -456,10 +581,10 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
         if (p_mse[m2][m3] > max_mse) continue;
         if (p_mse[m3][m0] > max_mse) continue;
         double err = p_err[m0][m1] + p_err[m1][m2] + p_err[m2][m3] + p_err[m3][m0];
-        uint32_t rank = (uint32_t)(((m0 * MAXM + m1) * MAXM + m2) * MAXM + m3);
-        if (err < best || (err == best && rank < brank)) {
+        // the table is in lexicographic order, so t itself is the lexicographic rank
+        if (err < best || (err == best && (uint32_t)t < brank)) {
           best = err;
-          brank = rank;
+          brank = (uint32_t)t;
         }
       }
     }
@@ -471,31 +596,32 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
         brank = orank;
       }
     }
-    if (lane == 0) {
-      s_rv[wid] = best;
-      s_rr[wid] = brank;
+    if (NW > 1) {
+      if (lane == 0) {
+        s_rv[wid] = best;
+        s_rr[wid] = brank;
+      }
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---- Phase L: final lines, corners, area / angle gates (thread 0) ----
     if (tid == 0) {
-      for (int w = 1; w < QT / 32; w++) {
-        if (s_rv[w] < best || (s_rv[w] == best && (uint32_t)s_rr[w] < brank)) {
+      for (int w = 1; w < NW; w++) {
+        if (s_rv[w] < best || (s_rv[w] == best && s_rr[w] < brank)) {
           best = s_rv[w];
-          brank = (uint32_t)s_rr[w];
+          brank = s_rr[w];
         }
       }
       bool ok = brank != 0xffffffffu;
       if (ok && !(best / sz < (double)fp.max_line_fit_mse)) ok = false;
       float qp[4][2];
       if (ok) {
-        int mm[4] = {(int)(brank / (MAXM * MAXM * MAXM)), (int)(brank / (MAXM * MAXM)) % MAXM, (int)(brank / MAXM) % MAXM,
-                     (int)(brank % MAXM)};
-        int indices[4] = {s_fm[mm[0]], s_fm[mm[1]], s_fm[mm[2]], s_fm[mm[3]]};
+        const uchar4 c = combos.c[combos.off[nm] + brank];
+        int indices[4] = {s_fm[c.x], s_fm[c.y], s_fm[c.z], s_fm[c.w]};
         double lines[4][4];
         for (int i = 0; i < 4 && ok; i++) {
           double mse;
-          fit_line_dev(lfps, sz, indices[i], indices[(i + 1) & 3], lines[i], nullptr, &mse);
+          fit_line_dev(lf, sz, indices[i], indices[(i + 1) & 3], lines[i], nullptr, &mse);
           if (mse > (double)fp.max_line_fit_mse) ok = false;
         }
         for (int i = 0; i < 4 && ok; i++) {
@@ -569,21 +695,67 @@ __global__ void __launch_bounds__(QT) k_quadfit(Geo g, FitParams fp, const Clust
   }
 }
 
+// clusters -> three size bins (index lists); one thread per cluster, warp-aggregated list allocation
+__global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *__restrict__ clusters, uint32_t *__restrict__ bin_idx,
+                                                      uint32_t *__restrict__ counters) {
+  const uint32_t ncl = min(counters[CNT_CLUSTERS], g.clu_cap);
+  for (uint32_t c0 = blockIdx.x * blockDim.x; c0 < ncl; c0 += gridDim.x * blockDim.x) {
+    const uint32_t c = c0 + threadIdx.x;
+    int bin = -1;
+    if (c < ncl) {
+      const uint32_t n = clusters[c].count;
+      bin = n <= 256 ? 0 : (n <= 1024 ? 1 : 2);
+    }
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const unsigned m = __ballot_sync(0xffffffffu, bin == b);
+      if (m == 0) continue;
+      uint32_t base = 0;
+      const int leader = __ffs(m) - 1;
+      if ((int)lane == leader) base = atomicAdd(&counters[CNT_BIN0 + b], (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (bin == b) bin_idx[(size_t)b * g.clu_cap + base + __popc(m & ((1u << lane) - 1))] = c;
+    }
+  }
+}
+
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   (void)nframes;
   const Geo &g = ws.g;
+  constexpr size_t smemA = (size_t)(2 * 256 + 6 * (256 + 1)) * 8;       // keys/errA + errB + moments
+  constexpr size_t smemB = (size_t)(2 * 1024 + 6 * (1024 + 1)) * 8;
+  constexpr size_t smemC = (size_t)(8192 + 6 * (SCAN_CH + 1)) * 8;      // keys/errA + scan staging
   static bool attr_set = false;
-  const size_t smem = (size_t)SORT_SMEM * sizeof(unsigned long long);
   if (!attr_set) {
-    cudaFuncSetAttribute(k_quadfit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_quadfit<32, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
+    cudaFuncSetAttribute(k_quadfit<128, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
+    cudaFuncSetAttribute(k_quadfit<256, 8192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC);
     attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  k_quadfit<<<sms * 5, QT, smem, s>>>(g, ws.fp, ws.clusters, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec, ws.quads, ws.counters,
-                                      at_Wp(g));
-  return 1;
+  ComboTable ct;
+  ct.c = reinterpret_cast<const uchar4 *>(ws.combos);
+  for (int i = 0; i < 18; i++) ct.off[i] = ws.combo_off[i];
+  const int Wp = at_Wp(g);
+  k_bin_clusters<<<sms * 2, 256, 0, s>>>(g, ws.clusters, ws.bin_idx, ws.counters);
+  // the three bins are independent: fork onto side streams so small-cluster warps fill the gaps the long poles leave
+  cudaEventRecord(ws.ev_fork, s);
+  cudaStreamWaitEvent(ws.aux[0], ws.ev_fork, 0);
+  cudaStreamWaitEvent(ws.aux[1], ws.ev_fork, 0);
+  k_quadfit<256, 8192, false><<<sms * 2, 256, smemC, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 2, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec,
+                                                          ws.quads, ws.counters, ct, Wp);
+  k_quadfit<128, 1024, true><<<sms * 3, 128, smemB, ws.aux[0]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 1, ws.pts, ws.keys, ws.lfps, ws.errs,
+                                                                 ws.dec, ws.quads, ws.counters, ct, Wp);
+  k_quadfit<32, 256, true><<<sms * 10, 32, smemA, ws.aux[1]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 0, ws.pts, ws.keys, ws.lfps, ws.errs,
+                                                               ws.dec, ws.quads, ws.counters, ct, Wp);
+  cudaEventRecord(ws.ev_join[0], ws.aux[0]);
+  cudaEventRecord(ws.ev_join[1], ws.aux[1]);
+  cudaStreamWaitEvent(s, ws.ev_join[0], 0);
+  cudaStreamWaitEvent(s, ws.ev_join[1], 0);
+  return 4;
 }
 
 }  // namespace b200at
