@@ -8,5 +8,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 # (2) full sets for the heavy kernels at a smaller batch (ncu replays each kernel ~40x)
 timeout 1500 ncu --set full --clock-control none --import-source on \
   -k regex:'k_quadfit|k_ccl_tile|k_ccl_border|k_ccl_flatten|k_ccl_mark|k_cluster_pass|k_cluster_select|k_threshold4|k_preprocess|k_decode|k_reconcile|k_pose' \
-  -s 36 -c 13 -o gpurun_out/prof_$TAG python bench.py --batch 32 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/prof_$TAG.log 2>&1
+  -s 51 -c 18 -o gpurun_out/prof_$TAG python bench.py --batch 32 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/prof_$TAG.log 2>&1
 ls -la gpurun_out | tail -8
