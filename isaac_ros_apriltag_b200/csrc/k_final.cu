@@ -208,7 +208,7 @@ __device__ void polar_UVt_dev(const double *A, double *R) {
   mm33_dev(At, A, S);
   for (int sweep = 0; sweep < 30; sweep++) {
     double off = fabs(S[1]) + fabs(S[2]) + fabs(S[5]);
-    if (off < 1e-300) break;
+    if (off <= 1e-32 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;  // converged far below double epsilon
     for (int pi = 0; pi < 3; pi++) {
       int p = pi == 2 ? 0 : pi, q = pi == 0 ? 1 : 2;
       double apq = S[p * 3 + q];

@@ -6,9 +6,8 @@
 // One CTA per boundary-point cluster, clusters binned by size so the CTA shape fits the work:
 //   bin A  n <= 256   : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (16 KB)
 //   bin B  n <= 1024  : 128-thread CTA, everything in shared memory (64 KB)
-//   bin C  n  > 1024  : 256-thread CTA, sort keys in shared memory (64 KB), moments / errors in an L2-resident scratch
-// Per cluster: slope keys (float) -> bitonic sort of u64 (slope|y|x) keys in shared memory (steps with stride < 64
-// need only warp-level sync) -> line-fit terms -> SEQUENTIAL double prefix sums (a parallel scan would change the
+//   bin C  n  > 1024  : 256-thread CTA, sort keys in shared memory (n <= 4096), moments / errors in an L2-resident scratch
+// Per cluster: slope keys (float) -> merge sort of u64 (slope|y|x) keys in shared memory -> line-fit terms -> SEQUENTIAL double prefix sums (a parallel scan would change the
 // roundings; the six moments run as six lanes reading shared memory) -> per-point window error -> 7-tap smoothing ->
 // local maxima -> top-(max_nmaxima) by rank counting -> pair table of line fits -> C(n,4) search over a precomputed
 // combination table with lexicographic arg-min -> corners, area and angle gates.
@@ -146,49 +145,75 @@ __device__ __forceinline__ void cta_sync() {
     __syncthreads();
 }
 
-__device__ __forceinline__ void cas_keys(unsigned long long *a, int i, int l, int n) {
-  if (l < n) {
-    unsigned long long x = a[i], y = a[l];
-    if (x > y) {
-      a[i] = y;
-      a[l] = x;
-    }
-  }
-}
-
-// Ascending bitonic network, "mirror" formulation (every compare-exchange puts the smaller key at the lower index, so
-// the virtual +inf padding above n is never stored).  Work is organised by PAIRS: pair p of a step with stride j touches
-// elements inside one aligned 2j window, so for 2j <= 64 a warp that owns 32 consecutive pairs owns a closed 64-element
-// window and the step needs only __syncwarp(); only strides >= 64 use the block barrier.
-template <int THREADS>
-__device__ void sort_keys(unsigned long long *a, int n) {
-  int N = 64;
-  while (N < n) N <<= 1;
-  const int half = N >> 1;
+// Sort of the u64 keys (unique within a cluster): every thread sorts ITEMS contiguous keys in registers (odd-even
+// transposition network), then log2(n/ITEMS) merge passes between two buffers; in a pass each thread produces ITEMS
+// consecutive outputs of its pair of runs, located with a merge-path binary search.  O(n log n) work instead of the
+// O(n log^2 n) of a bitonic network, one barrier per pass.  Works on shared or global memory (generic pointers).
+// The sorted sequence ends in `a`.
+template <int THREADS, int ITEMS>
+__device__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n) {
+  constexpr unsigned long long INF = ~0ull;
   const int tid = threadIdx.x;
-  for (int k = 2; k <= N; k <<= 1) {
-    // mirror step: element i (lower half of its k-block) with i ^ (k-1)
-    {
-      const int hk = k >> 1;
-      for (int p = tid; p < half; p += THREADS) {
-        int blk = p / hk, o = p - blk * hk;
-        int i = blk * k + o, l = blk * k + (k - 1 - o);
-        if (i < n) cas_keys(a, i, l, n);
+  for (int base = tid * ITEMS; base < n; base += THREADS * ITEMS) {
+    unsigned long long r[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) r[k] = (base + k < n) ? a[base + k] : INF;
+#pragma unroll
+    for (int pass = 0; pass < ITEMS; pass++) {
+#pragma unroll
+      for (int k = (pass & 1); k + 1 < ITEMS; k += 2) {
+        unsigned long long x = r[k], y = r[k + 1];
+        r[k] = x < y ? x : y;
+        r[k + 1] = x < y ? y : x;
       }
-      if (k <= 64) __syncwarp(); else cta_sync<THREADS>();
     }
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      for (int p = tid; p < half; p += THREADS) {
-        int blk = p / j, o = p - blk * j;
-        int i = blk * 2 * j + o, l = i + j;
-        if (i < n) cas_keys(a, i, l, n);
-      }
-      if (2 * j <= 64) __syncwarp(); else cta_sync<THREADS>();
-    }
-    // stages >= 64 are followed by a stage whose first steps cross warp-owned windows: block-wide visibility
-    if (k >= 64) cta_sync<THREADS>();
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+      if (base + k < n) a[base + k] = r[k];
   }
   cta_sync<THREADS>();
+  unsigned long long *src = a, *dst = tmp;
+  for (int width = ITEMS; width < n; width <<= 1) {
+    const int w2 = width << 1;
+    for (int ob = tid * ITEMS; ob < n; ob += THREADS * ITEMS) {
+      const int pair_lo = ob & ~(w2 - 1);
+      const int a0 = pair_lo, a1 = min(pair_lo + width, n), b0 = a1, b1 = min(pair_lo + w2, n);
+      const int na = a1 - a0, nb = b1 - b0;
+      const int diag = ob - pair_lo;
+      int lo = max(0, diag - nb), hi = min(diag, na);
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (src[a0 + mid] < src[b0 + diag - 1 - mid])
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      int ia = lo, ib = diag - lo;
+      unsigned long long va = ia < na ? src[a0 + ia] : INF, vb = ib < nb ? src[b0 + ib] : INF;
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++) {
+        if (ob + k < b1) {
+          const bool take_a = va <= vb;
+          dst[ob + k] = take_a ? va : vb;
+          if (take_a) {
+            ia++;
+            va = ia < na ? src[a0 + ia] : INF;
+          } else {
+            ib++;
+            vb = ib < nb ? src[b0 + ib] : INF;
+          }
+        }
+      }
+    }
+    cta_sync<THREADS>();
+    unsigned long long *t = src;
+    src = dst;
+    dst = t;
+  }
+  if (src != a) {
+    for (int i = tid; i < n; i += THREADS) a[i] = src[i];
+    cta_sync<THREADS>();
+  }
 }
 
 struct BBoxRed {
@@ -212,9 +237,9 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
   constexpr int NW = THREADS / 32;
   constexpr int MSTRIDE = (ALL_SMEM ? NCAP : SCAN_CH) + 1;
   extern __shared__ unsigned long long dsm[];
-  unsigned long long *skeys = dsm;                                  // [NCAP]  (later: errA)
-  double *s_errB = reinterpret_cast<double *>(dsm + NCAP);          // [NCAP]  (ALL_SMEM only)
-  double *s_M = reinterpret_cast<double *>(dsm + (ALL_SMEM ? 2 * NCAP : NCAP));  // [6][MSTRIDE]
+  unsigned long long *skeys = dsm;                                  // [NCAP]  keys (later: errA)
+  double *s_errB = reinterpret_cast<double *>(dsm + NCAP);          // [NCAP]  sort scratch, later errB (ALL_SMEM)
+  double *s_M = reinterpret_cast<double *>(dsm + 2 * NCAP);         // [6][MSTRIDE]
   __shared__ BBoxRed s_red[NW];
   __shared__ int s_cluster;
   __shared__ int s_fm[MAXM];
@@ -316,7 +341,10 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
       ka[i] = ((unsigned long long)float_orderable(slope) << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
     }
     cta_sync<THREADS>();
-    sort_keys<THREADS>(ka, sz);
+    // scratch for the merge passes: the (not yet used) errB area, or the L2-resident error scratch for oversize clusters
+    unsigned long long *ktmp = keys_in_smem ? reinterpret_cast<unsigned long long *>(s_errB)
+                                            : reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o);
+    sort_keys<THREADS, 8>(ka, ktmp, sz);
     if (keys_in_smem) {
       for (int i = tid; i < sz; i += THREADS) keys[o + i] = skeys[i];
     }
@@ -725,12 +753,12 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
   constexpr size_t smemA = (size_t)(2 * 256 + 6 * (256 + 1)) * 8;       // keys/errA + errB + moments
   constexpr size_t smemB = (size_t)(2 * 1024 + 6 * (1024 + 1)) * 8;
-  constexpr size_t smemC = (size_t)(8192 + 6 * (SCAN_CH + 1)) * 8;      // keys/errA + scan staging
+  constexpr size_t smemC = (size_t)(2 * 4096 + 6 * (SCAN_CH + 1)) * 8;  // keys/errA + sort scratch + scan staging
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_quadfit<32, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
     cudaFuncSetAttribute(k_quadfit<128, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
-    cudaFuncSetAttribute(k_quadfit<256, 8192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC);
+    cudaFuncSetAttribute(k_quadfit<256, 4096, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC);
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -745,7 +773,7 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaEventRecord(ws.ev_fork, s);
   cudaStreamWaitEvent(ws.aux[0], ws.ev_fork, 0);
   cudaStreamWaitEvent(ws.aux[1], ws.ev_fork, 0);
-  k_quadfit<256, 8192, false><<<sms * 2, 256, smemC, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 2, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec,
+  k_quadfit<256, 4096, false><<<sms * 2, 256, smemC, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 2, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec,
                                                           ws.quads, ws.counters, ct, Wp);
   k_quadfit<128, 1024, true><<<sms * 3, 128, smemB, ws.aux[0]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 1, ws.pts, ws.keys, ws.lfps, ws.errs,
                                                                  ws.dec, ws.quads, ws.counters, ct, Wp);

@@ -12,20 +12,33 @@ import os
 def main():
     rep, kern, so, cubsub = sys.argv[1:5]
     topn = int(sys.argv[5]) if len(sys.argv) > 5 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kern], capture_output=True, text=True).stdout
+    base_name = re.split(r"[<(]", kern)[0]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", base_name], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    # several kernels (template instances) may be concatenated: pick the section whose "Kernel Name" contains `kern`
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    norm = lambda t: re.sub(r"\((?:int|bool)\)", "", t).replace(" ", "")
+    sel = [i for i in starts if norm(kern) in norm(rows[i][1])]
+    s0 = sel[0]
+    s1 = min([i for i in starts if i > s0] + [len(rows)])
+    rows = rows[s0:s1]
     hdr_i = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
     hdr = rows[hdr_i]
     si = hdr.index("# Samples")
-    stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
     sass = [r for r in rows[hdr_i + 1:] if r and r[0].startswith("0x")]
+    mangled_hint = kern
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
         cub = [f for f in os.listdir(td) if cubsub in f][0]
         dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
     # locate the function
     lines = dis.splitlines()
-    start = [i for i, l in enumerate(lines) if re.search(r"\.text\..*" + kern, l)]
+    tmpl = re.findall(r"<(\d+),\s*(\d+),\s*(\d+)>", kern)
+    pat = base_name
+    if tmpl:
+        a, b, c = tmpl[0]
+        pat = base_name + "ILi" + a + "ELi" + b + "ELb" + c + "E"
+    start = [i for i, l in enumerate(lines) if re.search(r"\.text\..*" + pat, l)]
     start = start[0]
     cur = None
     per_instr = []
