@@ -133,19 +133,21 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
   }
 }
 
-// One CTA per frame.  Pass 1 totals, pass 2 ordered allocation (clusters appear in table-slot order).
+// One CTA per (frame, table segment).  Pass 1 totals -> one reservation in the global cluster / point pools,
+// pass 2 ordered allocation inside the reservation (clusters of a segment appear in table-slot order).
 __global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned long long *__restrict__ hkey,
                                                          const uint32_t *__restrict__ hcnt, uint32_t *__restrict__ hoff,
                                                          uint32_t *__restrict__ hcur, ClusterRec *__restrict__ clusters,
-                                                         uint32_t *__restrict__ counters) {
-  const int fr = blockIdx.x;
-  const size_t ho = (size_t)fr * g.hcap;
+                                                         uint32_t *__restrict__ counters, int segs) {
+  const int fr = blockIdx.x / segs, seg = blockIdx.x % segs;
+  const uint32_t seg_len = g.hcap / (uint32_t)segs;
+  const size_t ho = (size_t)fr * g.hcap + (size_t)seg * seg_len;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   __shared__ uint32_t s_c[32], s_p[32];
   __shared__ uint32_t s_base_c, s_base_p, s_run_c, s_run_p, s_ok;
   // pass 1
   uint32_t nc = 0, np = 0;
-  for (uint32_t i = tid; i < g.hcap; i += 1024) {
+  for (uint32_t i = tid; i < seg_len; i += 1024) {
     uint32_t c = hcnt[ho + i];
     if (c >= 24u && c <= g.max_cluster_pts) {
       nc++;
@@ -187,9 +189,9 @@ __global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned l
   __syncthreads();
   const bool ok = s_ok != 0;
   // pass 2: chunked block scan in slot order
-  for (uint32_t i0 = 0; i0 < g.hcap; i0 += 1024) {
+  for (uint32_t i0 = 0; i0 < seg_len; i0 += 1024) {
     const uint32_t i = i0 + tid;
-    uint32_t c = (i < g.hcap) ? hcnt[ho + i] : 0;
+    uint32_t c = (i < seg_len) ? hcnt[ho + i] : 0;
     const bool keep = ok && c >= 24u && c <= g.max_cluster_pts;
     uint32_t fc = keep ? 1u : 0u, fp = keep ? c : 0u;
     // inclusive warp scan
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned l
     const uint32_t run_c = s_run_c, run_p = s_run_p;
     const uint32_t ec = run_c + s_c[wid] + ic - fc;  // exclusive index of this slot's cluster
     const uint32_t ep = run_p + s_p[wid] + ip - fp;
-    if (i < g.hcap) {
+    if (i < seg_len) {
       if (keep) {
         ClusterRec r;
         r.key = hkey[ho + i];
@@ -255,7 +257,8 @@ int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
   dim3 gp((g.Wd - 2 + 255) / 256, g.Hd - 2, nframes);
   k_cluster_pass<false><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
-  k_cluster_select<<<nframes, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters);
+  const int segs = g.hcap >= 16384 ? 8 : 1;  // hcap is a power of two
+  k_cluster_select<<<nframes * segs, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters, segs);
   k_cluster_pass<true><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
   return 5;
 }

@@ -4,7 +4,7 @@
 // CPU oracle, so accept/reject decisions and the float corners are bit-identical (built with -fmad=false).
 //
 // One CTA per boundary-point cluster, clusters binned by size so the CTA shape fits the work:
-//   bin A  n <= 256   : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (16 KB)
+//   bin A0 n <= 128 / A1 n <= 256 : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (8 / 16 KB)
 //   bin B  n <= 1024  : 128-thread CTA, everything in shared memory (64 KB)
 //   bin C  n  > 1024  : 256-thread CTA, sort keys in shared memory (n <= 4096), moments / errors in an L2-resident scratch
 // Per cluster: slope keys (float) -> merge sort of u64 (slope|y|x) keys in shared memory -> line-fit terms -> SEQUENTIAL double prefix sums (a parallel scan would change the
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
   }
 }
 
-// clusters -> three size bins (index lists); one thread per cluster, warp-aggregated list allocation
+// clusters -> four size bins (index lists); one thread per cluster, warp-aggregated list allocation
 __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *__restrict__ clusters, uint32_t *__restrict__ bin_idx,
                                                       uint32_t *__restrict__ counters) {
   const uint32_t ncl = min(counters[CNT_CLUSTERS], g.clu_cap);
@@ -732,11 +732,11 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
     int bin = -1;
     if (c < ncl) {
       const uint32_t n = clusters[c].count;
-      bin = n <= 256 ? 0 : (n <= 1024 ? 1 : 2);
+      bin = n <= 128 ? 0 : (n <= 256 ? 1 : (n <= 1024 ? 2 : 3));
     }
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
+    for (int b = 0; b < 4; b++) {
       const unsigned m = __ballot_sync(0xffffffffu, bin == b);
       if (m == 0) continue;
       uint32_t base = 0;
@@ -751,12 +751,14 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   (void)nframes;
   const Geo &g = ws.g;
-  constexpr size_t smemA = (size_t)(2 * 256 + 6 * (256 + 1)) * 8;       // keys/errA + errB + moments
+  constexpr size_t smemA0 = (size_t)(2 * 128 + 6 * (128 + 1)) * 8;      // keys/errA + errB + moments
+  constexpr size_t smemA1 = (size_t)(2 * 256 + 6 * (256 + 1)) * 8;
   constexpr size_t smemB = (size_t)(2 * 1024 + 6 * (1024 + 1)) * 8;
   constexpr size_t smemC = (size_t)(2 * 4096 + 6 * (SCAN_CH + 1)) * 8;  // keys/errA + sort scratch + scan staging
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_quadfit<32, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
+    cudaFuncSetAttribute(k_quadfit<32, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA0);
+    cudaFuncSetAttribute(k_quadfit<32, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA1);
     cudaFuncSetAttribute(k_quadfit<128, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
     cudaFuncSetAttribute(k_quadfit<256, 4096, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC);
     attr_set = true;
@@ -769,21 +771,22 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < 18; i++) ct.off[i] = ws.combo_off[i];
   const int Wp = at_Wp(g);
   k_bin_clusters<<<sms * 2, 256, 0, s>>>(g, ws.clusters, ws.bin_idx, ws.counters);
-  // the three bins are independent: fork onto side streams so small-cluster warps fill the gaps the long poles leave
+  // the bins are independent: fork onto side streams; large clusters (the long poles) are issued first
   cudaEventRecord(ws.ev_fork, s);
-  cudaStreamWaitEvent(ws.aux[0], ws.ev_fork, 0);
-  cudaStreamWaitEvent(ws.aux[1], ws.ev_fork, 0);
-  k_quadfit<256, 4096, false><<<sms * 2, 256, smemC, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 2, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec,
+  for (int i = 0; i < 3; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
+  k_quadfit<256, 4096, false><<<sms * 2, 256, smemC, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 3, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec,
                                                           ws.quads, ws.counters, ct, Wp);
-  k_quadfit<128, 1024, true><<<sms * 3, 128, smemB, ws.aux[0]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 1, ws.pts, ws.keys, ws.lfps, ws.errs,
+  k_quadfit<128, 1024, true><<<sms * 3, 128, smemB, ws.aux[0]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 2, ws.pts, ws.keys, ws.lfps, ws.errs,
                                                                  ws.dec, ws.quads, ws.counters, ct, Wp);
-  k_quadfit<32, 256, true><<<sms * 10, 32, smemA, ws.aux[1]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 0, ws.pts, ws.keys, ws.lfps, ws.errs,
-                                                               ws.dec, ws.quads, ws.counters, ct, Wp);
-  cudaEventRecord(ws.ev_join[0], ws.aux[0]);
-  cudaEventRecord(ws.ev_join[1], ws.aux[1]);
-  cudaStreamWaitEvent(s, ws.ev_join[0], 0);
-  cudaStreamWaitEvent(s, ws.ev_join[1], 0);
-  return 4;
+  k_quadfit<32, 256, true><<<sms * 10, 32, smemA1, ws.aux[1]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 1, ws.pts, ws.keys, ws.lfps, ws.errs,
+                                                                ws.dec, ws.quads, ws.counters, ct, Wp);
+  k_quadfit<32, 128, true><<<sms * 16, 32, smemA0, ws.aux[2]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 0, ws.pts, ws.keys, ws.lfps, ws.errs,
+                                                                ws.dec, ws.quads, ws.counters, ct, Wp);
+  for (int i = 0; i < 3; i++) {
+    cudaEventRecord(ws.ev_join[i], ws.aux[i]);
+    cudaStreamWaitEvent(s, ws.ev_join[i], 0);
+  }
+  return 5;
 }
 
 }  // namespace b200at
