@@ -265,6 +265,32 @@ def main():
                 "algorithmic_bytes_per_launch": 2 * Pd * B, "launch_ms": stage_ms.get("threshold")}
     dominant = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else None
 
+    # ---- single-frame latency through the drop-in entry point (how the reference's README numbers were taken:
+    # 720p, one frame in flight; /root/reference/README.md:69 quotes 2.0-2.9 ms for cuAprilTags on other hardware) ----
+    latency = None
+    if args.gpus == 1 and not args.no_e2e:
+        import ctypes as C
+        from isaac_ros_apriltag_b200 import synth
+        f720, _, K7, ts7, _ = synth.make_config_frames("C1", 1)
+        bgr = np.ascontiguousarray(np.repeat(f720[0][:, :, None], 3, axis=2))
+        t720 = torch.from_numpy(bgr).cuda()
+        L = capi.lib()
+        hdl = C.c_void_p()
+        cam = capi.Intrinsics(float(K7[0, 0]), float(K7[1, 1]), float(K7[0, 2]), float(K7[1, 2]))
+        assert L.nvCreateAprilTagsDetector(C.byref(hdl), 1280, 720, 4, 0, C.byref(cam), C.c_float(ts7)) == 0
+        img = capi.ImageInput(t720.data_ptr(), 1280 * 3, 1280, 720)
+        tags = (capi.TagID * 64)()
+        ntags = C.c_uint32()
+        lat = []
+        for i in range(60):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = L.cuAprilTagsDetect(hdl, C.byref(img), tags, C.byref(ntags), 64, C.c_void_p(sh))
+            lat.append((time.perf_counter() - t0) * 1e3)
+        L.cuAprilTagsDestroy(hdl)
+        latency = {"workload": "1280x720 bgr8, 1 tag36h11, one frame in flight, cuAprilTagsDetect (synchronous)",
+                   "median_ms": float(np.median(lat[10:])), "p90_ms": float(np.percentile(lat[10:], 90)), "tags": int(ntags.value), "rc": int(rc)}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and args.gpus == 1:
         from oracle import oracle as O
@@ -296,7 +322,8 @@ def main():
                        "detections_per_batch": n_det, "status": status, "points_per_batch": int(counters["points"]),
                        "clusters_per_batch": int(counters["clusters"]), "quads_per_batch": int(counters["quads"])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "stages_ms_per_step": stage_ms, "stages_gbs": stage_gbs, "dominant_stage": dominant, "cpu_baseline": cpu_baseline}
+            "stages_ms_per_step": stage_ms, "stages_gbs": stage_gbs, "dominant_stage": dominant, "latency_720p": latency,
+            "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -6,7 +6,8 @@
 // the oracle's canonical label):
 //   1. k_ccl_tile   : 64x16 tile per CTA, union-find entirely in shared memory, writes flattened labels
 //   2. k_ccl_border : only links that cross tile borders are merged in global memory
-//   3. k_ccl_flatten: path-compress every pixel to its root; warp-aggregated component-size histogram
+//   3. k_ccl_flatten: every pixel to its root (4 px/thread, interleaved chases); sizes were counted per local root in
+//                     shared memory by k_ccl_tile, merged local roots move their count to the global root
 //   4. k_ccl_mark   : thr2 = thr, but pixels of components with < 25 px become 127 (folds the size gates of
 //                     gradient_clusters into one byte image)
 // Algorithmic bytes per frame: read Pd (thr) + write 4*Pd (labels) = 5*Pd (SURVEY 8d contract figure).
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
                                                   uint32_t *__restrict__ csize, int Wp) {
   __shared__ uint8_t t[TH + 1][TW + 4];  // [0] = row above the tile; column 0 = x0-1, column TW+1 = x0+TW
   __shared__ uint32_t L[TH * TW];
+  __shared__ uint32_t cnt[TH * TW];      // pixels per local root
   const int fr = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
@@ -114,7 +116,10 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
     if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
     t[r][c] = v;
   }
-  for (int i = tid; i < TH * TW; i += 256) L[i] = i;
+  for (int i = tid; i < TH * TW; i += 256) {
+    L[i] = i;
+    cnt[i] = 0;
+  }
   __syncthreads();
   for (int i = tid; i < TH * TW; i += 256) {
     int ly = i / TW, lx = i % TW;
@@ -132,14 +137,32 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
   __syncthreads();
   uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
   uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
+  // flatten inside the tile + count pixels per local root (lanes sharing a root issue one shared-memory atomic)
+  for (int i = tid; i < TH * TW; i += 256) {
+    int ly = i / TW, lx = i % TW;
+    int x = x0 + lx, y = y0 + ly;
+    const bool in = (x < g.Wd && y < g.Hd);
+    uint32_t r = 0xffffffffu;
+    bool counted = false;
+    if (in) {
+      r = find_s(L, i);
+      int ry = r / TW, rx = r % TW;
+      labf[(size_t)y * Wp + x] = (uint32_t)((y0 + ry) * Wp + (x0 + rx));
+      counted = t[ly + 1][lx + 1] != 127;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, counted);
+    if (counted) {
+      const unsigned peers = __match_any_sync(act, r);
+      if ((int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&cnt[r], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  // component size lives at the representative; 127 pixels are singletons (never connected upstream)
   for (int i = tid; i < TH * TW; i += 256) {
     int ly = i / TW, lx = i % TW;
     int x = x0 + lx, y = y0 + ly;
     if (x >= g.Wd || y >= g.Hd) continue;
-    uint32_t r = find_s(L, i);
-    int ry = r / TW, rx = r % TW;
-    labf[(size_t)y * Wp + x] = (uint32_t)((y0 + ry) * Wp + (x0 + rx));
-    szf[(size_t)y * Wp + x] = 0;
+    szf[(size_t)y * Wp + x] = (t[ly + 1][lx + 1] == 127) ? 1u : cnt[i];
   }
 }
 
@@ -178,45 +201,69 @@ __global__ void __launch_bounds__(128) k_ccl_border(Geo g, const uint8_t *__rest
   if (n.UR && (ly == 0 || lx == TW - 1)) unite_g(labf, me, me - Wp + 1);
 }
 
-// flatten + size histogram.  One thread per pixel; lanes of a warp that share a root issue one atomicAdd.
+// flatten: 4 consecutive pixels per thread (uchar4 / uint4 I/O), the four root chases interleaved so four independent
+// loads are in flight per thread.  Component sizes were counted per LOCAL root by k_ccl_tile; a local root that was
+// merged into another tile's root moves its count there (one atomic per merged local root, not per pixel).
 __global__ void __launch_bounds__(256) k_ccl_flatten(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                      uint32_t *__restrict__ csize, int Wp) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   const int fr = blockIdx.z;
+  if (x4 >= g.Wd) return;
   const size_t fo = (size_t)fr * g.Hd * Wp;
-  const bool in = x < g.Wd;
-  uint32_t root = 0xffffffffu;
-  bool counted = false;
-  if (in) {
-    const uint32_t me = (uint32_t)(y * Wp + x);
-    uint8_t v = thr[fo + me];
-    // AprilRobotics never connects 127 pixels: they stay singletons
-    root = (v == 127) ? me : find_g(lab + fo, me);
-    lab[fo + me] = root;
-    counted = true;
+  uint32_t *L = lab + fo;
+  const uint32_t me0 = (uint32_t)(y * Wp + x4);
+  const uchar4 tv = *reinterpret_cast<const uchar4 *>(thr + fo + me0);
+  uint4 pv = *reinterpret_cast<const uint4 *>(L + me0);
+  uint32_t a[4] = {me0, me0 + 1, me0 + 2, me0 + 3};
+  uint32_t p[4] = {pv.x, pv.y, pv.z, pv.w};
+  const uint8_t v[4] = {tv.x, tv.y, tv.z, tv.w};
+  bool done[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    // AprilRobotics never connects 127 pixels (singletons); padding columns are ignored
+    if (v[k] == 127 || x4 + k >= g.Wd) p[k] = a[k];
+    done[k] = (p[k] == a[k]);
   }
-  unsigned act = __ballot_sync(0xffffffffu, counted);
-  if (counted) {
-    unsigned peers = __match_any_sync(act, root);
-    int leader = __ffs(peers) - 1;
-    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&csize[fo + root], (uint32_t)__popc(peers));
+  while (!(done[0] && done[1] && done[2] && done[3])) {
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (!done[k]) {
+        a[k] = p[k];
+        p[k] = __ldcg(&L[a[k]]);
+      }
+#pragma unroll
+    for (int k = 0; k < 4; k++) done[k] = (p[k] == a[k]);
+  }
+  *reinterpret_cast<uint4 *>(L + me0) = make_uint4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (v[k] != 127 && x4 + k < g.Wd && a[k] != me0 + k) {
+      const uint32_t c = csize[fo + me0 + k];  // non-zero only for a (former) local root
+      if (c) atomicAdd(&csize[fo + a[k]], c);
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) k_ccl_mark(Geo g, const uint8_t *__restrict__ thr, const uint32_t *__restrict__ lab,
                                                   const uint32_t *__restrict__ csize, uint8_t *__restrict__ thr2, int Wp) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   const int fr = blockIdx.z;
-  if (x >= g.Wd) return;
+  if (x4 >= g.Wd) return;
   const size_t fo = (size_t)fr * g.Hd * Wp;
-  const size_t i = fo + (size_t)y * Wp + x;
-  uint8_t v = thr[i];
-  if (v != 127) {
-    if (csize[fo + lab[i]] < 25) v = 127;
-  }
-  thr2[i] = v;
+  const size_t i = fo + (size_t)y * Wp + x4;
+  const uchar4 tv = *reinterpret_cast<const uchar4 *>(thr + i);
+  const uint4 lv = *reinterpret_cast<const uint4 *>(lab + i);
+  uint8_t v[4] = {tv.x, tv.y, tv.z, tv.w};
+  const uint32_t l[4] = {lv.x, lv.y, lv.z, lv.w};
+  uint32_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) c[k] = (v[k] != 127 && x4 + k < g.Wd) ? csize[fo + l[k]] : 25u;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (c[k] < 25) v[k] = 127;
+  *reinterpret_cast<uchar4 *>(thr2 + i) = make_uchar4(v[0], v[1], v[2], v[3]);
 }
 
 int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
@@ -225,7 +272,7 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
   k_ccl_tile<<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
   k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
-  dim3 gp((g.Wd + 255) / 256, g.Hd, nframes);
+  dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);
   k_ccl_flatten<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
   k_ccl_mark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
   return 4;

@@ -35,7 +35,7 @@ def assert_exact(res, rep):
     assert res["refined_max"] <= TOL_REFINED_PX and res["det_corner_max"] <= TOL_CORNER_PX and res["det_margin_max"] <= TOL_MARGIN, res
 
 
-@pytest.mark.parametrize("config,n", [("C1", 2), ("C2", 2), ("C4", 1), ("C5", 2)])
+@pytest.mark.parametrize("config,n", [("C1", 2), ("C2", 2), ("C3", 1), ("C4", 1), ("C5", 2)])
 def test_stage_parity_configs(pu, config, n):
     from isaac_ros_apriltag_b200 import synth
     frames, truths, K, ts, fams = synth.make_config_frames(config, n)
