@@ -4,7 +4,7 @@
 //
 // Design: label-equivalence union-find with atomicMin (representative = minimum pixel index, which is also
 // the oracle's canonical label):
-//   1. k_ccl_tile   : 64x16 tile per CTA, union-find entirely in shared memory, writes flattened labels
+//   1. k_ccl_tile   : 32x32 tile per CTA, warp per row: runs by ballot, vertical links by shared-memory union-find
 //   2. k_ccl_border : only links that cross tile borders are merged in global memory
 //   3. k_ccl_flatten: every pixel to its root (4 px/thread, interleaved chases); sizes were counted per local root in
 //                     shared memory by k_ccl_tile, merged local roots move their count to the global root
@@ -15,7 +15,7 @@
 
 namespace b200at {
 
-constexpr int TW = 64, TH = 16;  // CCL tile
+constexpr int TW = 32, TH = 32;  // CCL tile: one warp per row
 
 struct Nb {
   bool L, U, UL, UR;
@@ -99,6 +99,8 @@ __device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {
   } while (!done);
 }
 
+// 32x32 tile per CTA, one warp per tile row (8 warps x 4 rows).  Horizontal runs are resolved with one ballot per row
+// (label = first pixel of the run, no atomics); only the vertical / diagonal links need shared-memory unions.
 __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                   uint32_t *__restrict__ csize, int Wp) {
   __shared__ uint8_t t[TH + 1][TW + 4];  // [0] = row above the tile; column 0 = x0-1, column TW+1 = x0+TW
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
   const int fr = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // stage (TH+1) x (TW+2) bytes; out-of-image = 127 (never links)
   for (int i = tid; i < (TH + 1) * (TW + 2); i += 256) {
     int r = i / (TW + 2), c = i % (TW + 2);
@@ -116,18 +118,32 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
     if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
     t[r][c] = v;
   }
-  for (int i = tid; i < TH * TW; i += 256) {
-    L[i] = i;
-    cnt[i] = 0;
+  __syncthreads();
+  // pass 1: per row, links + run starts
+  Nb nb[TH / 8];
+#pragma unroll
+  for (int k = 0; k < TH / 8; k++) {
+    const int ly = wid + 8 * k, lx = lane;
+    const int x = x0 + lx, y = y0 + ly;
+    Nb n = {false, false, false, false};
+    if (x < g.Wd && y < g.Hd) {
+      const int v = t[ly + 1][lx + 1];
+      n = ccl_links(v, t[ly + 1][lx], t[ly][lx + 1], t[ly][lx], t[ly][lx + 2], x, y, g.Wd);
+    }
+    nb[k] = n;
+    const unsigned ml = __ballot_sync(0xffffffffu, n.L && lx > 0);  // bit x: x is linked to x-1 inside the tile
+    const unsigned brk = ~ml & ((2u << lane) - 1u);                  // run breaks at or below this lane (bit 0 always set)
+    const int rs = 31 - __clz(brk);
+    L[ly * TW + lx] = (uint32_t)(ly * TW + rs);
+    cnt[ly * TW + lx] = 0;
   }
   __syncthreads();
-  for (int i = tid; i < TH * TW; i += 256) {
-    int ly = i / TW, lx = i % TW;
-    int x = x0 + lx, y = y0 + ly;
-    if (x >= g.Wd || y >= g.Hd) continue;
-    int v = t[ly + 1][lx + 1];
-    Nb n = ccl_links(v, t[ly + 1][lx], t[ly][lx + 1], t[ly][lx], t[ly][lx + 2], x, y, g.Wd);
-    if (n.L && lx > 0) unite_s(L, i, i - 1);
+  // pass 2: vertical / diagonal links (AprilRobotics' elisions already removed the redundant ones)
+#pragma unroll
+  for (int k = 0; k < TH / 8; k++) {
+    const int ly = wid + 8 * k, lx = lane;
+    const int i = ly * TW + lx;
+    const Nb n = nb[k];
     if (ly > 0) {
       if (n.U) unite_s(L, i, i - TW);
       if (n.UL && lx > 0) unite_s(L, i, i - TW - 1);
@@ -138,31 +154,34 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
   uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
   uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
   // flatten inside the tile + count pixels per local root (lanes sharing a root issue one shared-memory atomic)
-  for (int i = tid; i < TH * TW; i += 256) {
-    int ly = i / TW, lx = i % TW;
-    int x = x0 + lx, y = y0 + ly;
+#pragma unroll
+  for (int k = 0; k < TH / 8; k++) {
+    const int ly = wid + 8 * k, lx = lane;
+    const int i = ly * TW + lx;
+    const int x = x0 + lx, y = y0 + ly;
     const bool in = (x < g.Wd && y < g.Hd);
     uint32_t r = 0xffffffffu;
     bool counted = false;
     if (in) {
       r = find_s(L, i);
-      int ry = r / TW, rx = r % TW;
+      const int ry = r / TW, rx = r % TW;
       labf[(size_t)y * Wp + x] = (uint32_t)((y0 + ry) * Wp + (x0 + rx));
       counted = t[ly + 1][lx + 1] != 127;
     }
     const unsigned act = __ballot_sync(0xffffffffu, counted);
     if (counted) {
       const unsigned peers = __match_any_sync(act, r);
-      if ((int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&cnt[r], (uint32_t)__popc(peers));
+      if (lane == __ffs(peers) - 1) atomicAdd(&cnt[r], (uint32_t)__popc(peers));
     }
   }
   __syncthreads();
   // component size lives at the representative; 127 pixels are singletons (never connected upstream)
-  for (int i = tid; i < TH * TW; i += 256) {
-    int ly = i / TW, lx = i % TW;
-    int x = x0 + lx, y = y0 + ly;
+#pragma unroll
+  for (int k = 0; k < TH / 8; k++) {
+    const int ly = wid + 8 * k, lx = lane;
+    const int x = x0 + lx, y = y0 + ly;
     if (x >= g.Wd || y >= g.Hd) continue;
-    szf[(size_t)y * Wp + x] = (t[ly + 1][lx + 1] == 127) ? 1u : cnt[i];
+    szf[(size_t)y * Wp + x] = (t[ly + 1][lx + 1] == 127) ? 1u : cnt[ly * TW + lx];
   }
 }
 

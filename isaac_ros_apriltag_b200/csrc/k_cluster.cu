@@ -90,44 +90,62 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
   const int dxs[4] = {1, 0, -1, 1};
   const int dys[4] = {0, 1, 1, 1};
   const unsigned lane = threadIdx.x & 31;
+  // The four probes are processed in PHASES (all label loads, then all matches, then all table probes, then all
+  // atomics, then all stores) so the independent memory operations of the four probes are in flight together.
+  uint32_t rep1[4];
+  unsigned long long key[4];
+  unsigned peers[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) rep1[k] = pr.p[k] ? labf[(size_t)(y + dys[k]) * Wp + x + dxs[k]] : 0u;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    key[k] = rep0 < rep1[k] ? (((unsigned long long)rep1[k] << 32) | rep0) : (((unsigned long long)rep0 << 32) | rep1[k]);
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const bool has = pr.p[k];
-    const unsigned act = __ballot_sync(0xffffffffu, has);
-    if (!has) continue;
-    const int dx = dxs[k], dy = dys[k];
-    const uint32_t rep1 = labf[(size_t)(y + dy) * Wp + x + dx];
-    const unsigned long long key =
-        rep0 < rep1 ? (((unsigned long long)rep1 << 32) | rep0) : (((unsigned long long)rep0 << 32) | rep1);
-    const unsigned peers = __match_any_sync(act, key);
-    const int leader = __ffs(peers) - 1;
-    const int n = __popc(peers);
-    if (!EMIT) {
-      if ((int)lane == leader) {
-        uint32_t slot = hash_insert(hk, g.hcap, key);
-        if (slot == 0xffffffffu)
-          atomicOr(&counters[CNT_STATUS], (uint32_t)ST_HASH_FULL);
-        else
-          atomicAdd(&hcnt[ho + slot], (uint32_t)n);
-      }
-    } else {
-      uint32_t base = 0xffffffffu;
-      if ((int)lane == leader) {
-        uint32_t slot = hash_find(hk, g.hcap, key);
-        if (slot != 0xffffffffu) {
-          uint32_t off = hoff[ho + slot];
-          if (off != 0xffffffffu) base = off + atomicAdd(&hcur[ho + slot], (uint32_t)n);
-        }
-      }
-      base = __shfl_sync(peers, base, leader);
-      if (base != 0xffffffffu) {
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+    const unsigned act = __ballot_sync(0xffffffffu, pr.p[k]);
+    peers[k] = 0;
+    if (pr.p[k]) peers[k] = __match_any_sync(act, key[k]);
+  }
+  if (!EMIT) {
+    uint32_t slot[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      slot[k] = 0xfffffffeu;  // not a leader
+      if (pr.p[k] && (int)lane == __ffs(peers[k]) - 1) slot[k] = hash_insert(hk, g.hcap, key[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (slot[k] == 0xffffffffu)
+        atomicOr(&counters[CNT_STATUS], (uint32_t)ST_HASH_FULL);
+      else if (slot[k] != 0xfffffffeu)
+        atomicAdd(&hcnt[ho + slot[k]], (uint32_t)__popc(peers[k]));
+    }
+  } else {
+    uint32_t off[4], base[4];
+    uint32_t slotv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      slotv[k] = 0xffffffffu;
+      if (pr.p[k] && (int)lane == __ffs(peers[k]) - 1) slotv[k] = hash_find(hk, g.hcap, key[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) off[k] = slotv[k] != 0xffffffffu ? hoff[ho + slotv[k]] : 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      base[k] = off[k] != 0xffffffffu ? off[k] + atomicAdd(&hcur[ho + slotv[k]], (uint32_t)__popc(peers[k])) : 0xffffffffu;
+    const int v0 = in ? (int)img[(size_t)y * Wp + x] : 127;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (!pr.p[k]) continue;
+      const uint32_t b = __shfl_sync(peers[k], base[k], __ffs(peers[k]) - 1);
+      if (b != 0xffffffffu) {
+        const int dx = dxs[k], dy = dys[k];
+        const uint32_t rank = __popc(peers[k] & ((1u << lane) - 1));
         // packed point: x (14 bits) | y (14 bits) | gx code (2) | gy code (2); code 0 = 0, 1 = +255, 2 = -255
-        const int v0 = img[(size_t)y * Wp + x], v1 = img[(size_t)(y + dy) * Wp + x + dx];
-        const int d = v1 - v0;  // +-255
+        const int d = 255 - 2 * v0;  // v1 - v0 with v0 + v1 == 255
         const int gx = dx * d, gy = dy * d;
         const uint32_t cx = gx == 0 ? 0u : (gx > 0 ? 1u : 2u), cy = gy == 0 ? 0u : (gy > 0 ? 1u : 2u);
-        pts[base + rank] = (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 14) | (cx << 28) | (cy << 30);
+        pts[b + rank] = (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 14) | (cx << 28) | (cy << 30);
       }
     }
   }

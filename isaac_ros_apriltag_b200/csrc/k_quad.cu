@@ -432,10 +432,20 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     // errA aliases the (now dead) key area when the keys are in shared memory
     double *errA = keys_in_smem ? reinterpret_cast<double *>(skeys) : (errs_pool + (size_t)2 * o);
     double *errB = ALL_SMEM ? s_errB : (errs_pool + (size_t)2 * o + sz);
-    for (int i = tid; i < sz; i += THREADS) {
-      double e;
-      fit_line_dev(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, nullptr, &e, nullptr);
-      errA[i] = e;
+    // two independent line fits per iteration: their long double-precision division chains overlap
+    for (int i = tid; i < sz; i += 2 * THREADS) {
+      const int i2 = i + THREADS;
+      double e0, e1 = 0;
+      int a0 = i - ksz, b0 = i + ksz;
+      a0 = a0 < 0 ? a0 + sz : a0;
+      b0 = b0 >= sz ? b0 - sz : b0;
+      int a1 = i2 - ksz, b1 = i2 + ksz;
+      a1 = a1 < 0 ? a1 + sz : a1;
+      b1 = b1 >= sz ? b1 - sz : b1;
+      fit_line_dev(lf, sz, a0, b0, nullptr, &e0, nullptr);
+      if (i2 < sz) fit_line_dev(lf, sz, a1, b1, nullptr, &e1, nullptr);
+      errA[i] = e0;
+      if (i2 < sz) errA[i2] = e1;
     }
     cta_sync<THREADS>();
     for (int i = tid; i < sz; i += THREADS) {
@@ -632,8 +642,8 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
       __syncthreads();
     }
 
-    // ---- Phase L: final lines, corners, area / angle gates (thread 0) ----
-    if (tid == 0) {
+    // ---- Phase L: final lines, corners, area / angle gates: lanes 0..3 of warp 0, one line / corner / angle each ----
+    if (wid == 0) {
       for (int w = 1; w < NW; w++) {
         if (s_rv[w] < best || (s_rv[w] == best && s_rr[w] < brank)) {
           best = s_rv[w];
@@ -642,81 +652,81 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
       }
       bool ok = brank != 0xffffffffu;
       if (ok && !(best / sz < (double)fp.max_line_fit_mse)) ok = false;
-      float qp[4][2];
-      if (ok) {
+      if (ok) {  // warp-uniform
         const uchar4 c = combos.c[combos.off[nm] + brank];
-        int indices[4] = {s_fm[c.x], s_fm[c.y], s_fm[c.z], s_fm[c.w]};
-        double lines[4][4];
-        for (int i = 0; i < 4 && ok; i++) {
-          double mse;
-          fit_line_dev(lf, sz, indices[i], indices[(i + 1) & 3], lines[i], nullptr, &mse);
-          if (mse > (double)fp.max_line_fit_mse) ok = false;
+        const int indices[4] = {s_fm[c.x], s_fm[c.y], s_fm[c.z], s_fm[c.w]};
+        const int li = lane & 3;
+        double ln[4], mse;
+        fit_line_dev(lf, sz, indices[li], indices[(li + 1) & 3], ln, nullptr, &mse);
+        ok = __all_sync(0xffffffffu, !(mse > (double)fp.max_line_fit_mse));
+        // line of the next edge
+        double nn[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) nn[k] = __shfl_sync(0xffffffffu, ln[k], (li + 1) & 3);
+        const double A00 = ln[3], A01 = -nn[3];
+        const double A10 = -ln[2], A11 = nn[2];
+        const double B0 = -ln[0] + nn[0];
+        const double B1 = -ln[1] + nn[1];
+        const double det = A00 * A11 - A10 * A01;
+        const double W00 = A11 / det, W01 = -A01 / det;
+        const bool det_ok = !(fabs(det) < 0.001);
+        const double L0 = W00 * B0 + W01 * B1;
+        const float qx = (float)(ln[0] + L0 * A00);
+        const float qy = (float)(ln[1] + L0 * A10);
+        ok = ok && __all_sync(0xffffffffu, det_ok);
+        float qp[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          qp[k][0] = __shfl_sync(0xffffffffu, qx, k);
+          qp[k][1] = __shfl_sync(0xffffffffu, qy, k);
         }
-        for (int i = 0; i < 4 && ok; i++) {
-          double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
-          double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
-          double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
-          double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
-          double det = A00 * A11 - A10 * A01;
-          double W00 = A11 / det, W01 = -A01 / det;
-          if (fabs(det) < 0.001) {
-            ok = false;
-            break;
+        // area: triangle (0,1,2) on even lanes, (2,3,0) on odd lanes
+        double tri;
+        {
+          const int i0 = (lane & 1) ? 2 : 0, i1 = (lane & 1) ? 3 : 1, i2 = (lane & 1) ? 0 : 2;
+          const int ia[3] = {i0, i1, i2}, ib[3] = {i1, i2, i0};
+          double length[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            double ddx = (double)(qp[ib[k]][0] - qp[ia[k]][0]), ddy = (double)(qp[ib[k]][1] - qp[ia[k]][1]);
+            length[k] = sqrt(ddx * ddx + ddy * ddy);
           }
-          double L0 = W00 * B0 + W01 * B1;
-          qp[i][0] = (float)(lines[i][0] + L0 * A00);
-          qp[i][1] = (float)(lines[i][1] + L0 * A10);
+          const double p = (length[0] + length[1] + length[2]) / 2;
+          tri = sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
         }
-      }
-      if (ok) {
+        const double tri1 = __shfl_sync(0xffffffffu, tri, 1);
+        const double tri0 = __shfl_sync(0xffffffffu, tri, 0);
         double area = 0;
-        double length[3], p;
-        for (int i = 0; i < 3; i++) {
-          int idxa = i, idxb = (i + 1) % 3;
-          double ddx = (double)(qp[idxb][0] - qp[idxa][0]), ddy = (double)(qp[idxb][1] - qp[idxa][1]);
-          length[i] = sqrt(ddx * ddx + ddy * ddy);
-        }
-        p = (length[0] + length[1] + length[2]) / 2;
-        area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-        const int idxs[4] = {2, 3, 0, 2};
-        for (int i = 0; i < 3; i++) {
-          int idxa = idxs[i], idxb = idxs[i + 1];
-          double ddx = (double)(qp[idxb][0] - qp[idxa][0]), ddy = (double)(qp[idxb][1] - qp[idxa][1]);
-          length[i] = sqrt(ddx * ddx + ddy * ddy);
-        }
-        p = (length[0] + length[1] + length[2]) / 2;
-        area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+        area += tri0;
+        area += tri1;
         if (area < 0.95 * fp.tag_width * fp.tag_width) ok = false;
-      }
-      if (ok) {
-        const double ccr = (double)fp.cos_critical_rad;
-        for (int i = 0; i < 4; i++) {
-          int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+        // interior angles / winding: corner li
+        {
+          const double ccr = (double)fp.cos_critical_rad;
+          const int i0 = li, i1 = (li + 1) & 3, i2 = (li + 2) & 3;
           double dx1 = (double)(qp[i1][0] - qp[i0][0]);
           double dy1 = (double)(qp[i1][1] - qp[i0][1]);
           double dx2 = (double)(qp[i2][0] - qp[i1][0]);
           double dy2 = (double)(qp[i2][1] - qp[i1][1]);
           double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
-          if ((cos_dtheta > ccr || cos_dtheta < -ccr) || dx1 * dy2 < dy1 * dx2) {
-            ok = false;
-            break;
-          }
+          const bool bad = (cos_dtheta > ccr || cos_dtheta < -ccr) || dx1 * dy2 < dy1 * dx2;
+          ok = ok && __all_sync(0xffffffffu, !bad);
         }
-      }
-      if (ok) {
-        uint32_t qi = atomicAdd(&counters[CNT_QUADS], 1u);
-        if (qi < g.quad_cap) {
-          QuadRec q;
-          q.key = cr.key;
-          for (int i = 0; i < 4; i++) {
-            q.p[i][0] = qp[i][0];
-            q.p[i][1] = qp[i][1];
+        if (ok && lane == 0) {
+          uint32_t qi = atomicAdd(&counters[CNT_QUADS], 1u);
+          if (qi < g.quad_cap) {
+            QuadRec q;
+            q.key = cr.key;
+            for (int i = 0; i < 4; i++) {
+              q.p[i][0] = qp[i][0];
+              q.p[i][1] = qp[i][1];
+            }
+            q.frame = cr.frame;
+            q.reversed_border = reversed ? 1u : 0u;
+            quads[qi] = q;
+          } else {
+            atomicOr(&counters[CNT_STATUS], (uint32_t)ST_QUADS_FULL);
           }
-          q.frame = cr.frame;
-          q.reversed_border = reversed ? 1u : 0u;
-          quads[qi] = q;
-        } else {
-          atomicOr(&counters[CNT_STATUS], (uint32_t)ST_QUADS_FULL);
         }
       }
     }
