@@ -551,7 +551,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     return code;
   };
   // sub-batch size: small enough that copy(k+1) overlaps compute(k) inside one call, large enough to fill the GPU
-  const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 3) / 4)));
+  const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 7) / 8)));
   if (!h->d_stage) {
     h->stage_pitch = (row + 255) & ~(size_t)255;
     h->stage_sub = S;

@@ -67,11 +67,25 @@ __device__ __forceinline__ Probes eval_probes(const uint8_t *img, int Wp, int x,
   return pr;
 }
 
+// cheap 64->32 bit mix for the (rep_hi, rep_lo) keys
+__device__ __forceinline__ uint32_t hash_key2(unsigned long long k) {
+  uint32_t h = (uint32_t)(k >> 32) * 0x9E3779B1u ^ (uint32_t)k * 0x85EBCA6Bu;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 13;
+  return h;
+}
+
+// One thread per pixel evaluates the four probes; the (on average < 1 per pixel) resulting points are COMPACTED per
+// warp through shared memory so the expensive part (match / table probe / atomic) runs on dense lanes: one round per
+// 32 points instead of four rounds per 32 pixels.
 template <bool EMIT>
 __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
                                                       unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
                                                       const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
                                                       uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp) {
+  __shared__ unsigned long long s_key[8][128];
+  __shared__ uint32_t s_pt[8][128];
   const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int y = blockIdx.y + 1;
   const int fr = blockIdx.z;
@@ -80,73 +94,92 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
   const uint32_t *labf = lab + fo;
   unsigned long long *hk = hkey + (size_t)fr * g.hcap;
   const size_t ho = (size_t)fr * g.hcap;
+  const uint32_t hmask = g.hcap - 1;
   const bool in = (x <= g.Wd - 2) && (y <= g.Hd - 2);
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   Probes pr = {{false, false, false, false}};
   uint32_t rep0 = 0;
+  int v0 = 127;
   if (in) {
     pr = eval_probes(img, Wp, x, y);
+    v0 = img[(size_t)y * Wp + x];
     if (pr.p[0] || pr.p[1] || pr.p[2] || pr.p[3]) rep0 = labf[(size_t)y * Wp + x];
   }
   const int dxs[4] = {1, 0, -1, 1};
   const int dys[4] = {0, 1, 1, 1};
-  const unsigned lane = threadIdx.x & 31;
-  // The four probes are processed in PHASES (all label loads, then all matches, then all table probes, then all
-  // atomics, then all stores) so the independent memory operations of the four probes are in flight together.
   uint32_t rep1[4];
-  unsigned long long key[4];
-  unsigned peers[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) rep1[k] = pr.p[k] ? labf[(size_t)(y + dys[k]) * Wp + x + dxs[k]] : 0u;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    key[k] = rep0 < rep1[k] ? (((unsigned long long)rep1[k] << 32) | rep0) : (((unsigned long long)rep0 << 32) | rep1[k]);
+  // compaction: probe-major order inside the warp
+  int total = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const unsigned act = __ballot_sync(0xffffffffu, pr.p[k]);
-    peers[k] = 0;
-    if (pr.p[k]) peers[k] = __match_any_sync(act, key[k]);
-  }
-  if (!EMIT) {
-    uint32_t slot[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      slot[k] = 0xfffffffeu;  // not a leader
-      if (pr.p[k] && (int)lane == __ffs(peers[k]) - 1) slot[k] = hash_insert(hk, g.hcap, key[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (slot[k] == 0xffffffffu)
-        atomicOr(&counters[CNT_STATUS], (uint32_t)ST_HASH_FULL);
-      else if (slot[k] != 0xfffffffeu)
-        atomicAdd(&hcnt[ho + slot[k]], (uint32_t)__popc(peers[k]));
-    }
-  } else {
-    uint32_t off[4], base[4];
-    uint32_t slotv[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      slotv[k] = 0xffffffffu;
-      if (pr.p[k] && (int)lane == __ffs(peers[k]) - 1) slotv[k] = hash_find(hk, g.hcap, key[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) off[k] = slotv[k] != 0xffffffffu ? hoff[ho + slotv[k]] : 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      base[k] = off[k] != 0xffffffffu ? off[k] + atomicAdd(&hcur[ho + slotv[k]], (uint32_t)__popc(peers[k])) : 0xffffffffu;
-    const int v0 = in ? (int)img[(size_t)y * Wp + x] : 127;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (!pr.p[k]) continue;
-      const uint32_t b = __shfl_sync(peers[k], base[k], __ffs(peers[k]) - 1);
-      if (b != 0xffffffffu) {
+    const unsigned m = __ballot_sync(0xffffffffu, pr.p[k]);
+    if (pr.p[k]) {
+      const int pos = total + __popc(m & ((1u << lane) - 1));
+      const uint32_t r1 = rep1[k];
+      s_key[wid][pos] = rep0 < r1 ? (((unsigned long long)r1 << 32) | rep0) : (((unsigned long long)rep0 << 32) | r1);
+      if (EMIT) {
         const int dx = dxs[k], dy = dys[k];
-        const uint32_t rank = __popc(peers[k] & ((1u << lane) - 1));
-        // packed point: x (14 bits) | y (14 bits) | gx code (2) | gy code (2); code 0 = 0, 1 = +255, 2 = -255
         const int d = 255 - 2 * v0;  // v1 - v0 with v0 + v1 == 255
         const int gx = dx * d, gy = dy * d;
         const uint32_t cx = gx == 0 ? 0u : (gx > 0 ? 1u : 2u), cy = gy == 0 ? 0u : (gy > 0 ? 1u : 2u);
-        pts[b + rank] = (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 14) | (cx << 28) | (cy << 30);
+        // packed point: x (14 bits) | y (14 bits) | gx code (2) | gy code (2); code 0 = 0, 1 = +255, 2 = -255
+        s_pt[wid][pos] = (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 14) | (cx << 28) | (cy << 30);
       }
+    }
+    total += __popc(m);
+  }
+  __syncwarp();
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    const int j = c0 + (int)lane;
+    const bool has = j < total;
+    const unsigned act = __ballot_sync(0xffffffffu, has);
+    if (!has) continue;
+    const unsigned long long key = s_key[wid][j];
+    const unsigned peers = __match_any_sync(act, key);
+    const int leader = __ffs(peers) - 1;
+    const int n = __popc(peers);
+    uint32_t slot = hash_key2(key) & hmask;
+    if (!EMIT) {
+      if ((int)lane == leader) {
+        uint32_t found = 0xffffffffu;
+        for (uint32_t probe = 0; probe < g.hcap; probe++) {
+          unsigned long long cur = hk[slot];
+          if (cur == key) {
+            found = slot;
+            break;
+          }
+          if (cur == 0ULL) {
+            unsigned long long old = atomicCAS(&hk[slot], 0ULL, key);
+            if (old == 0ULL || old == key) {
+              found = slot;
+              break;
+            }
+          }
+          slot = (slot + 1) & hmask;
+        }
+        if (found == 0xffffffffu)
+          atomicOr(&counters[CNT_STATUS], (uint32_t)ST_HASH_FULL);
+        else
+          atomicAdd(&hcnt[ho + found], (uint32_t)n);
+      }
+    } else {
+      uint32_t base = 0xffffffffu;
+      if ((int)lane == leader) {
+        for (uint32_t probe = 0; probe < g.hcap; probe++) {
+          unsigned long long cur = hk[slot];
+          if (cur == key) {
+            uint32_t off = hoff[ho + slot];
+            if (off != 0xffffffffu) base = off + atomicAdd(&hcur[ho + slot], (uint32_t)n);
+            break;
+          }
+          if (cur == 0ULL) break;
+          slot = (slot + 1) & hmask;
+        }
+      }
+      base = __shfl_sync(peers, base, leader);
+      if (base != 0xffffffffu) pts[base + __popc(peers & ((1u << lane) - 1))] = s_pt[wid][j];
     }
   }
 }
