@@ -34,70 +34,88 @@ __device__ __forceinline__ void hproject(const double *H, double x, double y, do
   *oy = yy / zz;
 }
 
-__device__ bool homography_compute2_dev(const double c[4][4], double H[9]) {
-  double A[72];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    double *r0 = A + (2 * i) * 9, *r1 = A + (2 * i + 1) * 9;
-    r0[0] = c[i][0];
-    r0[1] = c[i][1];
-    r0[2] = 1;
-    r0[3] = 0;
-    r0[4] = 0;
-    r0[5] = 0;
-    r0[6] = -c[i][0] * c[i][2];
-    r0[7] = -c[i][1] * c[i][2];
-    r0[8] = c[i][2];
-    r1[0] = 0;
-    r1[1] = 0;
-    r1[2] = 0;
-    r1[3] = c[i][0];
-    r1[4] = c[i][1];
-    r1[5] = 1;
-    r1[6] = -c[i][0] * c[i][3];
-    r1[7] = -c[i][1] * c[i][3];
-    r1[8] = c[i][3];
+// homography_compute2 (8x9 Gaussian elimination with partial pivoting + back substitution), distributed over the
+// warp: lane (l & 7) holds row (l & 7) of the augmented matrix in registers (the four 8-lane groups compute the same
+// thing), pivot search / row swap / pivot-row broadcast are width-8 shuffles.  Operation order per element is the
+// serial algorithm's, so the result is bit-identical to it.
+__device__ __forceinline__ double shfl8(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
+
+__device__ bool homography_compute2_warp(const float p[4][2], double H[9]) {
+  const int row = threadIdx.x & 7;
+  const int ci = row >> 1;
+  const double c0 = (ci == 0 || ci == 3) ? -1 : 1, c1 = (ci == 0 || ci == 1) ? -1 : 1;
+  const double c2 = p[ci][0], c3 = p[ci][1];
+  double r[9];
+  if ((row & 1) == 0) {
+    r[0] = c0;
+    r[1] = c1;
+    r[2] = 1;
+    r[3] = 0;
+    r[4] = 0;
+    r[5] = 0;
+    r[6] = -c0 * c2;
+    r[7] = -c1 * c2;
+    r[8] = c2;
+  } else {
+    r[0] = 0;
+    r[1] = 0;
+    r[2] = 0;
+    r[3] = c0;
+    r[4] = c1;
+    r[5] = 1;
+    r[6] = -c0 * c3;
+    r[7] = -c1 * c3;
+    r[8] = c3;
   }
   const double epsilon = 1e-10;
+  bool ok = true;
+#pragma unroll
   for (int col = 0; col < 8; col++) {
-    double max_val = 0;
-    int max_val_idx = -1;
-    for (int row = col; row < 8; row++) {
-      double val = fabs(A[row * 9 + col]);
-      if (val > max_val) {
-        max_val = val;
-        max_val_idx = row;
+    // first row >= col with the largest |A[row][col]| (strictly-greater scan == lowest index among equal maxima)
+    double val = row >= col ? fabs(r[col]) : -1.0;
+    int idx = row;
+#pragma unroll
+    for (int of = 4; of > 0; of >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, val, of, 8);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, of, 8);
+      if (ov > val || (ov == val && oi < idx)) {
+        val = ov;
+        idx = oi;
       }
     }
-    if (max_val < epsilon) return false;
-    if (max_val_idx != col) {
-      for (int i = col; i < 9; i++) {
-        double tmp = A[col * 9 + i];
-        A[col * 9 + i] = A[max_val_idx * 9 + i];
-        A[max_val_idx * 9 + i] = tmp;
-      }
-    }
-    for (int i = col + 1; i < 8; i++) {
-      double f = A[i * 9 + col] / A[col * 9 + col];
-      A[i * 9 + col] = 0;
-      for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
+    if (val < epsilon) ok = false;  // "matrix is singular" (uniform across the warp)
+    // swap rows col <-> idx
+    const int partner = row == col ? idx : (row == idx ? col : row);
+#pragma unroll
+    for (int j = 0; j < 9; j++)
+      if (j >= col) r[j] = shfl8(r[j], partner);
+    // broadcast the pivot row, eliminate below
+    double pr[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) pr[j] = j >= col ? shfl8(r[j], col) : 0.0;
+    if (row > col) {
+      const double f = r[col] / pr[col];
+      r[col] = 0;
+#pragma unroll
+      for (int j = 0; j < 9; j++)
+        if (j > col) r[j] -= f * pr[j];
     }
   }
+  // back substitution
+  double xs[8];
+#pragma unroll
   for (int col = 7; col >= 0; col--) {
     double sum = 0;
-    for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
-    A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (i > col) sum += r[i] * xs[i];
+    const double mine = (r[8] - sum) / r[col];
+    xs[col] = shfl8(mine, col);
   }
-  H[0] = A[8];
-  H[1] = A[17];
-  H[2] = A[26];
-  H[3] = A[35];
-  H[4] = A[44];
-  H[5] = A[53];
-  H[6] = A[62];
-  H[7] = A[71];
+#pragma unroll
+  for (int k = 0; k < 8; k++) H[k] = xs[k];
   H[8] = 1;
-  return true;
+  return ok;
 }
 
 struct GrayModelD {
@@ -214,21 +232,32 @@ __global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams f
             double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
             double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
             double Mn = 0, Mcount = 0;
-            for (int k = 0; k < nsteps; k++) {
-              const double n = -range + 0.25 * k;
-              const double grange = 1;
-              int x1 = (int)(x0 + (n + grange) * nx);
-              int y1 = (int)(y0 + (n + grange) * ny);
-              if (x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) continue;
-              int x2 = (int)(x0 + (n - grange) * nx);
-              int y2 = (int)(y0 + (n - grange) * ny);
-              if (x2 < 0 || x2 >= width || y2 < 0 || y2 >= height) continue;
-              int g1 = gray_at(fd, enc, bpp, x1, y1);
-              int g2 = gray_at(fd, enc, bpp, x2, y2);
-              if (g1 < g2) continue;
-              double weight = (double)((g2 - g1) * (g2 - g1));
-              Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
-              Mcount += weight;
+            // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
+            for (int k0 = 0; k0 < nsteps; k0 += 8) {
+              int g1[8], g2[8];
+              bool okk[8];
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const int k = k0 + u;
+                const double n = -range + 0.25 * k;
+                const double grange = 1;
+                const int x1 = (int)(x0 + (n + grange) * nx);
+                const int y1 = (int)(y0 + (n + grange) * ny);
+                const int x2 = (int)(x0 + (n - grange) * nx);
+                const int y2 = (int)(y0 + (n - grange) * ny);
+                okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
+                         !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
+                g1[u] = okk[u] ? gray_at(fd, enc, bpp, x1, y1) : 0;
+                g2[u] = okk[u] ? gray_at(fd, enc, bpp, x2, y2) : 0;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                if (!okk[u] || g1[u] < g2[u]) continue;
+                const double n = -range + 0.25 * (k0 + u);
+                const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
+                Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
+                Mcount += weight;
+              }
             }
             if (Mcount != 0) {
               double n0 = Mn / Mcount;
@@ -290,15 +319,7 @@ __global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams f
     // ---- a13: homography ----
     double H[9];
     {
-      double corr[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        corr[i][0] = (i == 0 || i == 3) ? -1 : 1;
-        corr[i][1] = (i == 0 || i == 1) ? -1 : 1;
-        corr[i][2] = p[i][0];
-        corr[i][3] = p[i][1];
-      }
-      if (!homography_compute2_dev(corr, H)) continue;
+      if (!homography_compute2_warp(p, H)) continue;
       double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
       if (det == 0) continue;
     }
