@@ -115,7 +115,7 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < 5; i++) {
     if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
     if (h->ws.ev_join[i]) cudaEventDestroy(h->ws.ev_join[i]);
   }
@@ -353,7 +353,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.out, (size_t)B * g.max_tags);
   ALLOC(ws.out_count, B);
   ALLOC(ws.counters, CNT_N);
-  ALLOC(ws.bin_idx, (size_t)4 * g.clu_cap);
+  ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   {
     // combination tables: for every nm, all m0<m1<m2<m3<nm in lexicographic order (the serial loops' visiting order)
     std::vector<unsigned char> tab;
@@ -375,7 +375,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     if (rc == 0 && cudaMemcpy(dcomb, tab.data(), tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = B200AT_ERR_CUDA;
     ws.combos = dcomb;
   }
-  for (int i = 0; i < 3 && rc == 0; i++) {
+  for (int i = 0; i < 5 && rc == 0; i++) {
     if (cudaStreamCreateWithFlags(&ws.aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
     if (rc == 0 && cudaEventCreateWithFlags(&ws.ev_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }

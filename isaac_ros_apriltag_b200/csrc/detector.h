@@ -62,7 +62,8 @@ struct Cand {  // decoded candidate before reconcile
 
 // counters[] slots
 enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_WORK_DECODE = 7,
-       CNT_BIN0 = 8 /* ..11: clusters per size bin */, CNT_WORK0 = 12 /* ..15: quad-fit work queues */, CNT_N = 16 };
+       CNT_BIN0 = 8 /* ..13: clusters per size bin */, CNT_WORK0 = 14 /* ..19: quad-fit work queues */, CNT_N = 24 };
+constexpr int kQuadBins = 6;
 enum { ST_HASH_FULL = 1, ST_POINTS_FULL = 2, ST_CLUSTERS_FULL = 4, ST_QUADS_FULL = 8, ST_CANDS_FULL = 16, ST_OUT_TRUNC = 32 };
 
 struct Geo {
@@ -120,11 +121,11 @@ struct Workspace {
   b200AprilTagsDetection_t *out;
   uint32_t *out_count;   // [B]
   uint32_t *counters;    // [CNT_N]
-  uint32_t *bin_idx;     // [4][clu_cap] cluster indices per size bin
+  uint32_t *bin_idx;     // [kQuadBins][clu_cap] cluster indices per size bin
   const unsigned char *combos;  // per nm (4..kMaxNMaxima): all m0<m1<m2<m3 < nm in lexicographic order, uchar4 each
   int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
-  cudaStream_t aux[3];   // side streams: the quad-fit bins run concurrently
-  cudaEvent_t ev_fork, ev_join[3];
+  cudaStream_t aux[5];   // side streams: the quad-fit bins run concurrently
+  cudaEvent_t ev_fork, ev_join[5];
   uint8_t blur_k[32];
   int blur_ksz;
   int blur_sharpen;

@@ -24,6 +24,15 @@ __device__ __forceinline__ int gray_at(const FrameDesc &fd, int enc, int bpp, in
   return (int)((r * 4899u + c1 * 9617u + b * 1868u + 8192u) >> 14);
 }
 
+// branch-free variant for batched gathers: always three byte loads (for mono8 the three offsets coincide and the luma
+// formula reduces to the identity: (v*16384 + 8192) >> 14 == v)
+__device__ __forceinline__ int gray_at_bf(const uint8_t *base, size_t pitch, int bpp, int o1, int o2, bool bgr, int x, int y) {
+  const uint8_t *p = base + (size_t)y * pitch + (size_t)x * bpp;
+  const uint32_t c0 = p[0], c1 = p[o1], c2 = p[o2];
+  const uint32_t r = bgr ? c2 : c0, b = bgr ? c0 : c2;
+  return (int)((r * 4899u + c1 * 9617u + b * 1868u + 8192u) >> 14);
+}
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 __device__ __forceinline__ void hproject(const double *H, double x, double y, double *ox, double *oy) {
@@ -183,6 +192,8 @@ __global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams f
   const uint32_t nq = min(counters[CNT_QUADS], g.quad_cap);
   const int width = g.W, height = g.H;
   const int enc = g.enc, bpp = g.bpp;
+  const int o1 = bpp > 1 ? 1 : 0, o2 = bpp > 1 ? 2 : 0;
+  const bool is_bgr = (enc == B200AT_ENC_BGR8 || enc == B200AT_ENC_BGRA8);
 
   for (;;) {
     uint32_t qi = 0;
@@ -247,8 +258,9 @@ __global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams f
                 const int y2 = (int)(y0 + (n - grange) * ny);
                 okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
                          !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
-                g1[u] = okk[u] ? gray_at(fd, enc, bpp, x1, y1) : 0;
-                g2[u] = okk[u] ? gray_at(fd, enc, bpp, x2, y2) : 0;
+                // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
+                g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
+                g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
               }
 #pragma unroll
               for (int u = 0; u < 8; u++) {

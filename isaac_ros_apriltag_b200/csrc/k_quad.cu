@@ -4,9 +4,9 @@
 // CPU oracle, so accept/reject decisions and the float corners are bit-identical (built with -fmad=false).
 //
 // One CTA per boundary-point cluster, clusters binned by size so the CTA shape fits the work:
-//   bin A0 n <= 128 / A1 n <= 256 : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (8 / 16 KB)
-//   bin B  n <= 1024  : 128-thread CTA, everything in shared memory (64 KB)
-//   bin C  n  > 1024  : 256-thread CTA, sort keys in shared memory (n <= 4096), moments / errors in an L2-resident scratch
+//   n <= 128 / 256     : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (8 / 16 KB)
+//   n <= 512 / 1024    : 64 / 128-thread CTA, everything in shared memory (33 / 66 KB)
+//   n <= 2048 / larger : 256-thread CTA, sort keys in shared memory (n <= 4096), moments / errors in an L2-resident scratch
 // Per cluster: slope keys (float) -> merge sort of u64 (slope|y|x) keys in shared memory -> line-fit terms -> SEQUENTIAL double prefix sums (a parallel scan would change the
 // roundings; the six moments run as six lanes reading shared memory) -> per-point window error -> 7-tap smoothing ->
 // local maxima -> top-(max_nmaxima) by rank counting -> pair table of line fits -> C(n,4) search over a precomputed
@@ -227,7 +227,7 @@ struct ComboTable {
   int off[18];
 };
 
-template <int THREADS, int NCAP, bool ALL_SMEM>
+template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS>
 __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
                                                      const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
                                                      unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     // scratch for the merge passes: the (not yet used) errB area, or the L2-resident error scratch for oversize clusters
     unsigned long long *ktmp = keys_in_smem ? reinterpret_cast<unsigned long long *>(s_errB)
                                             : reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o);
-    sort_keys<THREADS, 8>(ka, ktmp, sz);
+    sort_keys<THREADS, ITEMS>(ka, ktmp, sz);
     if (keys_in_smem) {
       for (int i = tid; i < sz; i += THREADS) keys[o + i] = skeys[i];
     }
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
   }
 }
 
-// clusters -> four size bins (index lists); one thread per cluster, warp-aggregated list allocation
+// clusters -> kQuadBins size bins (index lists); one thread per cluster, warp-aggregated list allocation
 __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *__restrict__ clusters, uint32_t *__restrict__ bin_idx,
                                                       uint32_t *__restrict__ counters) {
   const uint32_t ncl = min(counters[CNT_CLUSTERS], g.clu_cap);
@@ -742,11 +742,11 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
     int bin = -1;
     if (c < ncl) {
       const uint32_t n = clusters[c].count;
-      bin = n <= 128 ? 0 : (n <= 256 ? 1 : (n <= 1024 ? 2 : 3));
+      bin = n <= 128 ? 0 : (n <= 256 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 3 : (n <= 2048 ? 4 : 5))));
     }
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
+    for (int b = 0; b < kQuadBins; b++) {
       const unsigned m = __ballot_sync(0xffffffffu, bin == b);
       if (m == 0) continue;
       uint32_t base = 0;
@@ -758,45 +758,44 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
   }
 }
 
+template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS>
+static void launch_bin(const Workspace &ws, int bin, int ctas_per_sm, int sms, const ComboTable &ct, cudaStream_t st) {
+  const Geo &g = ws.g;
+  constexpr size_t smem = (size_t)(2 * NCAP + 6 * ((ALL_SMEM ? NCAP : SCAN_CH) + 1)) * 8;  // keys/errA + errB|sort scratch + moments|staging
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS><<<sms * ctas_per_sm, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys,
+                                                                                  ws.lfps, ws.errs, ws.dec, ws.quads, ws.counters, ct,
+                                                                                  at_Wp(g));
+}
+
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   (void)nframes;
   const Geo &g = ws.g;
-  constexpr size_t smemA0 = (size_t)(2 * 128 + 6 * (128 + 1)) * 8;      // keys/errA + errB + moments
-  constexpr size_t smemA1 = (size_t)(2 * 256 + 6 * (256 + 1)) * 8;
-  constexpr size_t smemB = (size_t)(2 * 1024 + 6 * (1024 + 1)) * 8;
-  constexpr size_t smemC = (size_t)(2 * 4096 + 6 * (SCAN_CH + 1)) * 8;  // keys/errA + sort scratch + scan staging
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_quadfit<32, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA0);
-    cudaFuncSetAttribute(k_quadfit<32, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA1);
-    cudaFuncSetAttribute(k_quadfit<128, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
-    cudaFuncSetAttribute(k_quadfit<256, 4096, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC);
-    attr_set = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   ComboTable ct;
   ct.c = reinterpret_cast<const uchar4 *>(ws.combos);
   for (int i = 0; i < 18; i++) ct.off[i] = ws.combo_off[i];
-  const int Wp = at_Wp(g);
   k_bin_clusters<<<sms * 2, 256, 0, s>>>(g, ws.clusters, ws.bin_idx, ws.counters);
   // the bins are independent: fork onto side streams; large clusters (the long poles) are issued first
   cudaEventRecord(ws.ev_fork, s);
-  for (int i = 0; i < 3; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
-  k_quadfit<256, 4096, false><<<sms * 2, 256, smemC, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 3, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec,
-                                                          ws.quads, ws.counters, ct, Wp);
-  k_quadfit<128, 1024, true><<<sms * 3, 128, smemB, ws.aux[0]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 2, ws.pts, ws.keys, ws.lfps, ws.errs,
-                                                                 ws.dec, ws.quads, ws.counters, ct, Wp);
-  k_quadfit<32, 256, true><<<sms * 10, 32, smemA1, ws.aux[1]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 1, ws.pts, ws.keys, ws.lfps, ws.errs,
-                                                                ws.dec, ws.quads, ws.counters, ct, Wp);
-  k_quadfit<32, 128, true><<<sms * 16, 32, smemA0, ws.aux[2]>>>(g, ws.fp, ws.clusters, ws.bin_idx, 0, ws.pts, ws.keys, ws.lfps, ws.errs,
-                                                                ws.dec, ws.quads, ws.counters, ct, Wp);
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < 5; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
+  launch_bin<256, 4096, false, 16>(ws, 5, 2, sms, ct, s);          // n > 2048 (n > 4096: global-memory sort fallback)
+  launch_bin<256, 2048, false, 8>(ws, 4, 3, sms, ct, ws.aux[0]);   // n <= 2048
+  launch_bin<128, 1024, true, 8>(ws, 3, 3, sms, ct, ws.aux[1]);    // n <= 1024
+  launch_bin<64, 512, true, 8>(ws, 2, 6, sms, ct, ws.aux[2]);      // n <= 512
+  launch_bin<32, 256, true, 8>(ws, 1, 10, sms, ct, ws.aux[3]);     // n <= 256
+  launch_bin<32, 128, true, 4>(ws, 0, 16, sms, ct, ws.aux[4]);     // n <= 128
+  for (int i = 0; i < 5; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);
   }
-  return 5;
+  return 7;
 }
 
 }  // namespace b200at
