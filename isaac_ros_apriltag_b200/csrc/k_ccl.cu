@@ -36,18 +36,18 @@ __device__ __forceinline__ Nb ccl_links(int v, int vL, int vU, int vUL, int vUR,
   return n;
 }
 
-// find with compression of the start node.  Safe under concurrent atomicMin unions: unions only ever modify ROOT
-// entries, a non-root never becomes a root again, and every value written here is an ancestor of the start node.
+// find with path SPLITTING: every node on the walked path is re-pointed to its grandparent, so the pointer chases of
+// the other lanes / later unions get shorter quickly (the walks of a warp diverge: the longest chain sets the pace).
+// Safe under concurrent atomicMin unions: unions only ever modify ROOT entries, a non-root never becomes a root again,
+// and every value written here is an ancestor of the node it is written to.
 __device__ __forceinline__ uint32_t find_s(volatile uint32_t *L, uint32_t a) {
-  const uint32_t start = a;
   uint32_t p = L[a];
-  if (p == a) return a;
-  const uint32_t first = p;
-  do {
+  while (p != a) {
+    const uint32_t gp = L[p];
+    if (gp != p) L[a] = gp;
     a = p;
-    p = L[a];
-  } while (p != a);
-  if (first != a) L[start] = a;
+    p = gp;
+  }
   return a;
 }
 __device__ __forceinline__ void unite_s(uint32_t *L, uint32_t a, uint32_t b) {
@@ -69,15 +69,13 @@ __device__ __forceinline__ void unite_s(uint32_t *L, uint32_t a, uint32_t b) {
   } while (!done);
 }
 __device__ __forceinline__ uint32_t find_g(uint32_t *L, uint32_t a) {
-  const uint32_t start = a;
   uint32_t p = __ldcg(&L[a]);
-  if (p == a) return a;
-  const uint32_t first = p;
-  do {
+  while (p != a) {
+    const uint32_t gp = __ldcg(&L[p]);
+    if (gp != p) __stcg(&L[a], gp);  // path splitting (see find_s)
     a = p;
-    p = __ldcg(&L[a]);
-  } while (p != a);
-  if (first != a) __stcg(&L[start], a);  // compression (see find_s)
+    p = gp;
+  }
   return a;
 }
 __device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {

@@ -208,44 +208,90 @@ __global__ void k_unsharp(Geo g, const uint8_t *__restrict__ orig, uint8_t *__re
 __global__ void __launch_bounds__(256) k_threshold4(Geo g, const uint8_t *__restrict__ dec, const uint8_t *__restrict__ tmin,
                                                     const uint8_t *__restrict__ tmax, uint8_t *__restrict__ thr, int Wp,
                                                     int twp) {
+  // CTA = 32 x 8 threads = 128 tile columns x 8 tile rows.  The tile min/max of the region (+1 tile halo, neutral
+  // values outside the tile grid) are staged once in shared memory; the 3x3 dilate/erode of a thread's four tiles is
+  // then a handful of SIMD-in-word byte min/max ops instead of 72 byte loads.
+  __shared__ __align__(4) uint8_t s_mn[10][136], s_mx[10][136];  // column c <-> tile (tx0 - 4 + c): word aligned groups
   const int tq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 tile columns
   const int ty = blockIdx.y * blockDim.y + threadIdx.y;  // tile row (may be the partial one)
   const int fr = blockIdx.z;
   const int nty = (g.Hd + 3) >> 2;
-  if (tq * 16 >= Wp || ty >= nty) return;
   const uint8_t *mnb = tmin + (size_t)fr * g.th * twp;
   const uint8_t *mxb = tmax + (size_t)fr * g.th * twp;
-  const int tyc = min(ty, g.th - 1);
-  uint32_t th4[4], low4[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    int tx = tq * 4 + k;
-    int txc = min(tx, g.tw - 1);
-    uint32_t mn = 255, mx = 0;
-    for (int dy = -1; dy <= 1; dy++) {
-      int yy = tyc + dy;
-      if (yy < 0 || yy >= g.th) continue;
-      for (int dx = -1; dx <= 1; dx++) {
-        int xx = txc + dx;
-        if (xx < 0 || xx >= g.tw) continue;
-        mn = min(mn, (uint32_t)mnb[(size_t)yy * twp + xx]);
-        mx = max(mx, (uint32_t)mxb[(size_t)yy * twp + xx]);
-      }
+  const int tx0 = blockIdx.x * blockDim.x * 4, ty0 = blockIdx.y * blockDim.y;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < 10 * 136; i += 256) {
+    const int r = i / 136, c = i - r * 136;
+    const int tyy = ty0 - 1 + r, txx = tx0 - 4 + c;
+    uint8_t a = 255, b = 0;  // neutral for min / max: tiles outside the grid do not take part (upstream skips them)
+    if (tyy >= 0 && tyy < g.th && txx >= 0 && txx < g.tw) {
+      a = mnb[(size_t)tyy * twp + txx];
+      b = mxb[(size_t)tyy * twp + txx];
     }
-    bool partial = (tx >= g.tw) || (ty >= g.th);
-    low4[k] = (!partial && (int)(mx - mn) < g.min_wb_diff) ? 1u : 0u;
-    th4[k] = (mn + (mx - mn) / 2) * 0x01010101u;
+    s_mn[r][c] = a;
+    s_mx[r][c] = b;
+  }
+  __syncthreads();
+  if (tq * 16 >= Wp || ty >= nty) return;
+  uint32_t th4[4], low4[4];
+  const bool fast = (tq * 4 + 3 < g.tw) && (ty < g.th);
+  if (fast) {
+    // words of my 4 tiles in the three tile rows, plus the neighbouring words for the +-1 column shift
+    const int c = threadIdx.x * 4 + 4, r = threadIdx.y;
+    uint32_t mn = 0xffffffffu, mx = 0;
+#pragma unroll
+    for (int dr = 0; dr < 3; dr++) {
+      const uint32_t *wn = reinterpret_cast<const uint32_t *>(&s_mn[r + dr][c - 4]);
+      const uint32_t *wx = reinterpret_cast<const uint32_t *>(&s_mx[r + dr][c - 4]);
+      const uint32_t nl = wn[0], nc = wn[1], nr = wn[2];
+      const uint32_t xl = wx[0], xc = wx[1], xr = wx[2];
+      // left-shifted view [t-1,t0,t1,t2] and right-shifted view [t1,t2,t3,t4]
+      const uint32_t n_l = __byte_perm(nl, nc, 0x6543), n_r = __byte_perm(nc, nr, 0x4321);
+      const uint32_t x_l = __byte_perm(xl, xc, 0x6543), x_r = __byte_perm(xc, xr, 0x4321);
+      mn = __vminu4(mn, __vminu4(nc, __vminu4(n_l, n_r)));
+      mx = __vmaxu4(mx, __vmaxu4(xc, __vmaxu4(x_l, x_r)));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t a = (mn >> (8 * k)) & 0xff, b = (mx >> (8 * k)) & 0xff;
+      low4[k] = ((int)(b - a) < g.min_wb_diff) ? 1u : 0u;
+      th4[k] = (a + (b - a) / 2) * 0x01010101u;
+    }
+  } else {
+    const int tyc = min(ty, g.th - 1);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int tx = tq * 4 + k;
+      int txc = min(tx, g.tw - 1);
+      uint32_t mn = 255, mx = 0;
+      for (int dy = -1; dy <= 1; dy++) {
+        int yy = tyc + dy;
+        if (yy < 0 || yy >= g.th) continue;
+        for (int dx = -1; dx <= 1; dx++) {
+          int xx = txc + dx;
+          if (xx < 0 || xx >= g.tw) continue;
+          mn = min(mn, (uint32_t)mnb[(size_t)yy * twp + xx]);
+          mx = max(mx, (uint32_t)mxb[(size_t)yy * twp + xx]);
+        }
+      }
+      bool partial = (tx >= g.tw) || (ty >= g.th);
+      low4[k] = (!partial && (int)(mx - mn) < g.min_wb_diff) ? 1u : 0u;
+      th4[k] = (mn + (mx - mn) / 2) * 0x01010101u;
+    }
   }
   const size_t base = (size_t)fr * g.Hd * Wp + (size_t)(ty * 4) * Wp + tq * 16;
+  uint4 v[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    if (ty * 4 + r < g.Hd) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     if (ty * 4 + r >= g.Hd) break;
-    uint4 v = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
     uint4 o;
-    o.x = low4[0] ? 0x7f7f7f7fu : __vcmpgtu4(v.x, th4[0]);
-    o.y = low4[1] ? 0x7f7f7f7fu : __vcmpgtu4(v.y, th4[1]);
-    o.z = low4[2] ? 0x7f7f7f7fu : __vcmpgtu4(v.z, th4[2]);
-    o.w = low4[3] ? 0x7f7f7f7fu : __vcmpgtu4(v.w, th4[3]);
+    o.x = low4[0] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].x, th4[0]);
+    o.y = low4[1] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].y, th4[1]);
+    o.z = low4[2] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].z, th4[2]);
+    o.w = low4[3] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].w, th4[3]);
     *reinterpret_cast<uint4 *>(thr + base + (size_t)r * Wp) = o;
   }
 }
