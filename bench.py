@@ -168,6 +168,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the detector has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
