@@ -285,10 +285,12 @@ def main():
         tags = (capi.TagID * 64)()
         ntags = C.c_uint32()
         lat = []
+        lat_stream = torch.cuda.Stream()  # a real (non-legacy) stream, like the reference node's stream_ (apriltag_node.cpp:460):
+        lsh = lat_stream.cuda_stream      # lets the library replay its cached CUDA graph of the whole frame
         for i in range(60):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            rc = L.cuAprilTagsDetect(hdl, C.byref(img), tags, C.byref(ntags), 64, C.c_void_p(sh))
+            rc = L.cuAprilTagsDetect(hdl, C.byref(img), tags, C.byref(ntags), 64, C.c_void_p(lsh))
             lat.append((time.perf_counter() - t0) * 1e3)
         L.cuAprilTagsDestroy(hdl)
         latency = {"workload": "1280x720 bgr8, 1 tag36h11, one frame in flight, cuAprilTagsDetect (synchronous)",

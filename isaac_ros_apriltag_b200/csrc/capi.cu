@@ -80,6 +80,14 @@ struct cuAprilTagsHandle_st {
   cudaEvent_t ev[B200AT_NUM_STAGES + 1] = {};
   float stage_ms[B200AT_NUM_STAGES] = {};
   float tag_dim = 0;
+  // CUDA graph of one whole batch (all stage launches, fork/join of the quad-fit streams, D2H): replayed when the same
+  // (n, stream, alignment class, encoding) comes again, e.g. the one-frame-at-a-time node path
+  cudaGraphExec_t graph_exec = nullptr;
+  uint32_t graph_n = 0;
+  int graph_fast = -1, graph_enc = -1;
+  cudaStream_t graph_stream = nullptr;
+  uint32_t plain_calls = 0;
+  bool use_graph = true;
 };
 
 namespace {
@@ -101,6 +109,7 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void *p : h->dev_allocs) cudaFree(p);
   if (h->h_frames) cudaFreeHost(h->h_frames);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -375,6 +384,28 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     if (rc == 0 && cudaMemcpy(dcomb, tab.data(), tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = B200AT_ERR_CUDA;
     ws.combos = dcomb;
   }
+  // TMA descriptor for the CCL tile staging: thr viewed as a (Wp, Hd, B) u8 tensor, box = 48 x 33 x 1.
+  ws.use_tma = 0;
+  if (rc == 0) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+        qres == cudaDriverEntryPointSuccess && getenv("B200AT_NO_TMA") == nullptr) {
+      const cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)g.Hd, (cuuint64_t)B};
+      const cuuint64_t strides[2] = {(cuuint64_t)Wp, (cuuint64_t)Wp * g.Hd};  // bytes, dims 1..2
+      const cuuint32_t box[3] = {48, 33, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult cr = ((EncodeFn)fn)(&ws.thr_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ws.thr, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr == CUDA_SUCCESS) ws.use_tma = 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
   for (int i = 0; i < 5 && rc == 0; i++) {
     if (cudaStreamCreateWithFlags(&ws.aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
     if (rc == 0 && cudaEventCreateWithFlags(&ws.ev_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
@@ -415,7 +446,7 @@ int cuAprilTagsDestroy(cuAprilTagsHandle h) {
 int b200AprilTagsSetInputEncoding(cuAprilTagsHandle h, int32_t enc) {
   if (!h || bpp_of(enc) == 0) return B200AT_ERR_INVALID_ARG;
   h->ws.g.enc = enc;
-  h->ws.g.bpp = bpp_of(enc);
+  h->ws.g.bpp = bpp_of(enc);  // (a cached graph is keyed on the encoding and is re-captured when it changes)
   h->opt.input_encoding = enc;
   return B200AT_OK;
 }
@@ -428,10 +459,9 @@ int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable) {
 
 // Launch every stage of one batch on `stream` and queue the D2H of its results.  `hf` is a pinned frame-table slice
 // that must stay untouched until the stream has consumed it; results land in the pinned arrays `out`, `cnt`, `ctr`.
-static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream, FrameDesc *hf,
-                        b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, bool timing, int *launches_out) {
-  Workspace &ws = h->ws;
-  Geo &g = ws.g;
+// host side of a batch: validate the frames, fill the pinned frame table, classify the alignment
+static int fill_frame_table(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, FrameDesc *hf, int *fast_out) {
+  const Geo &g = h->ws.g;
   int fast = 1;
   const size_t min_pitch = (size_t)g.W * g.bpp;
   for (uint32_t i = 0; i < n; i++) {
@@ -440,7 +470,21 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
     hf[i].pitch = frames[i].pitch;
     if (((uintptr_t)frames[i].ptr & 15) || (frames[i].pitch & 15)) fast = 0;
   }
-  g.fast_align = fast;
+  *fast_out = fast;
+  return B200AT_OK;
+}
+
+static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream, FrameDesc *hf,
+                        b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, bool timing, int *launches_out,
+                        bool table_filled = false) {
+  Workspace &ws = h->ws;
+  Geo &g = ws.g;
+  if (!table_filled) {
+    int fast = 1;
+    int rcf = fill_frame_table(h, frames, n, hf, &fast);
+    if (rcf != B200AT_OK) return rcf;
+    g.fast_align = fast;
+  }
   int launches = 0;
   cudaError_t e = cudaMemcpyAsync(ws.frames, hf, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(uint32_t) * CNT_N, stream);
@@ -483,8 +527,49 @@ int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *f
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
-  int launches = 0;
-  int rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches);
+  int launches = h->launches;
+  int fast = 1;
+  int rc = fill_frame_table(h, frames, n, h->h_frames, &fast);
+  if (rc == B200AT_OK) {
+    h->ws.g.fast_align = fast;
+    const bool graph_ok = h->use_graph && !h->timing && h->plain_calls >= 1;  // first call runs plain (lazy attribute setup)
+    if (graph_ok && h->graph_exec && h->graph_n == n && h->graph_fast == fast && h->graph_enc == h->ws.g.enc && h->graph_stream == stream) {
+      if (cudaGraphLaunch(h->graph_exec, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    } else if (graph_ok) {
+      if (h->graph_exec) {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, false, &launches, true);
+        e = cudaStreamEndCapture(stream, &graph);
+        if (rc == B200AT_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == B200AT_OK && e == cudaSuccess && h->graph_exec) {
+          h->graph_n = n;
+          h->graph_fast = fast;
+          h->graph_enc = h->ws.g.enc;
+          h->graph_stream = stream;
+          if (cudaGraphLaunch(h->graph_exec, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        } else {
+          // capture not possible in this context: fall back to plain launches from now on
+          cudaGetLastError();
+          h->use_graph = false;
+          h->graph_exec = nullptr;
+          rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches, true);
+        }
+      } else {
+        cudaGetLastError();
+        h->use_graph = false;
+        rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches, true);
+      }
+    } else {
+      rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches, true);
+      h->plain_calls++;
+    }
+  }
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != B200AT_OK) return rc;
   h->launches = launches;

@@ -4,7 +4,8 @@
 //
 // Design: label-equivalence union-find with atomicMin (representative = minimum pixel index, which is also
 // the oracle's canonical label):
-//   1. k_ccl_tile   : 32x32 tile per CTA, warp per row: runs by ballot, vertical links by shared-memory union-find
+//   1. k_ccl_tile   : 32x32 tile per CTA (staged by ONE TMA bulk tensor copy incl. halo), warp per row: runs by ballot,
+//                     vertical links by shared-memory union-find
 //   2. k_ccl_border : only links that cross tile borders are merged in global memory
 //   3. k_ccl_flatten: every pixel to its root (4 px/thread, interleaved chases); sizes were counted per local root in
 //                     shared memory by k_ccl_tile, merged local roots move their count to the global root
@@ -99,24 +100,55 @@ __device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {
 
 // 32x32 tile per CTA, one warp per tile row (8 warps x 4 rows).  Horizontal runs are resolved with one ballot per row
 // (label = first pixel of the run, no atomics); only the vertical / diagonal links need shared-memory unions.
+constexpr int TPITCH = 48;  // shared-memory row pitch of the staged tile = TMA box width (x0-1 .. x0+46)
+
+template <bool USE_TMA>
 __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
-                                                  uint32_t *__restrict__ csize, int Wp) {
-  __shared__ uint8_t t[TH + 1][TW + 4];  // [0] = row above the tile; column 0 = x0-1, column TW+1 = x0+TW
+                                                  uint32_t *__restrict__ csize, int Wp, const __grid_constant__ CUtensorMap tmap) {
+  __shared__ __align__(128) uint8_t t[TH + 1][TPITCH];  // [0] = row above the tile; column 0 = x0-1
+  __shared__ __align__(8) unsigned long long mbar;
   __shared__ uint32_t L[TH * TW];
   __shared__ uint32_t cnt[TH * TW];      // pixels per local root
   const int fr = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // stage (TH+1) x (TW+2) bytes; out-of-image = 127 (never links)
-  for (int i = tid; i < (TH + 1) * (TW + 2); i += 256) {
-    int r = i / (TW + 2), c = i % (TW + 2);
-    int y = y0 - 1 + r, x = x0 - 1 + c;
-    uint8_t v = 127;
-    if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
-    t[r][c] = v;
+  if (USE_TMA) {
+    // TMA staging: one cp.async.bulk.tensor of the (48 x 33) u8 box at (x0-1, y0-1, frame); out-of-bounds elements are
+    // zero-filled by the hardware (the link predicates never consult pixels outside the image, see ccl_links).
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&t[0][0]);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(TPITCH * (TH + 1))) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+          "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - 1), "r"(y0 - 1), "r"(fr), "r"(mb)
+          : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_TMA:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@!p bra WAIT_TMA;\n"
+        "}\n" ::"r"(mb)
+        : "memory");
+  } else {
+    // fallback staging: (TH+1) x (TW+2) bytes; out-of-image = 127 (never links)
+    for (int i = tid; i < (TH + 1) * (TW + 2); i += 256) {
+      int r = i / (TW + 2), c = i % (TW + 2);
+      int y = y0 - 1 + r, x = x0 - 1 + c;
+      uint8_t v = 127;
+      if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
+      t[r][c] = v;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // pass 1: per row, links + run starts
   Nb nb[TH / 8];
 #pragma unroll
@@ -287,7 +319,10 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
   const int Wp = at_Wp(g);
   dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
-  k_ccl_tile<<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
+  if (ws.use_tma)
+    k_ccl_tile<true><<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+  else
+    k_ccl_tile<false><<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
   k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
   dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);
   k_ccl_flatten<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);

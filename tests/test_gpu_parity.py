@@ -211,3 +211,31 @@ def test_overflow_is_reported_not_ub(pu):
         det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream)
     assert e.value.code == 5 and det.status() != 0
     det.close()
+
+
+def test_cuda_graph_replay_matches_plain_launches(pu):
+    """EnqueueBatch caches a CUDA graph of the whole batch when the caller passes a real stream: call 1 runs plain,
+    call 2 captures + launches, later calls replay.  Results must be identical, and a replay must pick up NEW frame
+    pointers (the frame table is a pinned buffer read at execution time)."""
+    import torch
+    from isaac_ros_apriltag_b200 import capi, synth
+    frames, truths, K, ts, fams = synth.make_config_frames("C1", 4)
+    H, W = frames.shape[1:]
+    det = capi.Detector(W, H, families=fams, encoding="mono8", max_batch=2, max_tags=64)
+    t, ptrs, pitch = pu.upload(frames)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    ref = capi.Detector(W, H, families=fams, encoding="mono8", max_batch=2, max_tags=64)
+    want01 = ref.detect_device(ptrs[0:2], pitch, 0)
+    want23 = ref.detect_device(ptrs[2:4], pitch, 0)
+    got = []
+    for it in range(5):
+        sel = ptrs[0:2] if it % 2 == 0 else ptrs[2:4]
+        got.append(det.detect_device(sel, pitch, st.cuda_stream))
+    for it in range(5):
+        want = want01 if it % 2 == 0 else want23
+        for a, b in zip(got[it], want):
+            assert a.tobytes() == b.tobytes(), it
+    assert sum(len(x) for x in want01) >= 2
+    det.close()
+    ref.close()
