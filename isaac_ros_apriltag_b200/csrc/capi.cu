@@ -384,7 +384,8 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     if (rc == 0 && cudaMemcpy(dcomb, tab.data(), tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = B200AT_ERR_CUDA;
     ws.combos = dcomb;
   }
-  // TMA descriptor for the CCL tile staging: thr viewed as a (Wp, Hd, B) u8 tensor, box = 48 x 33 x 1.
+  // TMA descriptor for the CCL tile staging: thr viewed as a (Wp, Hd, B) u8 tensor, box = 64 x 33 x 1 (the box start
+  // must be 16-byte aligned in global memory, so it begins 16 pixels left of the tile: x0-16 .. x0+47).
   ws.use_tma = 0;
   if (rc == 0) {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -393,10 +394,10 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
-        qres == cudaDriverEntryPointSuccess && getenv("B200AT_NO_TMA") == nullptr) {
+        qres == cudaDriverEntryPointSuccess && getenv("B200AT_USE_TMA") != nullptr) {
       const cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)g.Hd, (cuuint64_t)B};
       const cuuint64_t strides[2] = {(cuuint64_t)Wp, (cuuint64_t)Wp * g.Hd};  // bytes, dims 1..2
-      const cuuint32_t box[3] = {48, 33, 1};
+      const cuuint32_t box[3] = {64, 33, 1};
       const cuuint32_t estr[3] = {1, 1, 1};
       CUresult cr = ((EncodeFn)fn)(&ws.thr_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ws.thr, dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,

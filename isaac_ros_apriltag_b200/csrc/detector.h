@@ -125,7 +125,7 @@ struct Workspace {
   uint32_t *bin_idx;     // [kQuadBins][clu_cap] cluster indices per size bin
   const unsigned char *combos;  // per nm (4..kMaxNMaxima): all m0<m1<m2<m3 < nm in lexicographic order, uchar4 each
   int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
-  CUtensorMap thr_tmap;  // TMA descriptor of thr as a (Wp, Hd, B) u8 tensor, box 48 x 33 x 1 (CCL tile + halo)
+  CUtensorMap thr_tmap;  // TMA descriptor of thr as a (Wp, Hd, B) u8 tensor, box 64 x 33 x 1 (CCL tile + halo)
   int use_tma;
   cudaStream_t aux[5];   // side streams: the quad-fit bins run concurrently
   cudaEvent_t ev_fork, ev_join[5];

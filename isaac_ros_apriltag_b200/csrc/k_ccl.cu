@@ -100,12 +100,13 @@ __device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {
 
 // 32x32 tile per CTA, one warp per tile row (8 warps x 4 rows).  Horizontal runs are resolved with one ballot per row
 // (label = first pixel of the run, no atomics); only the vertical / diagonal links need shared-memory unions.
-constexpr int TPITCH = 48;  // shared-memory row pitch of the staged tile = TMA box width (x0-1 .. x0+46)
+constexpr int TPITCH = 64;  // shared-memory row pitch of the staged tile = TMA box width: x0-16 .. x0+47
+constexpr int TOFF = 16;    // column of pixel x0 (TMA needs the box start 16-byte aligned: x0-16; the halo x0-1 is column 15)
 
 template <bool USE_TMA>
 __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                   uint32_t *__restrict__ csize, int Wp, const __grid_constant__ CUtensorMap tmap) {
-  __shared__ __align__(128) uint8_t t[TH + 1][TPITCH];  // [0] = row above the tile; column 0 = x0-1
+  __shared__ __align__(128) uint8_t t[TH + 1][TPITCH];  // [0] = row above the tile; column TOFF = x0
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ uint32_t L[TH * TW];
   __shared__ uint32_t cnt[TH * TW];      // pixels per local root
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
   const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (USE_TMA) {
-    // TMA staging: one cp.async.bulk.tensor of the (48 x 33) u8 box at (x0-1, y0-1, frame); out-of-bounds elements are
+    // TMA staging: one cp.async.bulk.tensor of the (64 x 33) u8 box at (x0-16, y0-1, frame); out-of-bounds elements are
     // zero-filled by the hardware (the link predicates never consult pixels outside the image, see ccl_links).
     const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&t[0][0]);
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(TPITCH * (TH + 1))) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-          "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - 1), "r"(y0 - 1), "r"(fr), "r"(mb)
+          "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - TOFF), "r"(y0 - 1), "r"(fr), "r"(mb)
           : "memory");
     }
     asm volatile(
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
       int y = y0 - 1 + r, x = x0 - 1 + c;
       uint8_t v = 127;
       if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
-      t[r][c] = v;
+      t[r][c + TOFF - 1] = v;
     }
     __syncthreads();
   }
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
     const int x = x0 + lx, y = y0 + ly;
     Nb n = {false, false, false, false};
     if (x < g.Wd && y < g.Hd) {
-      const int v = t[ly + 1][lx + 1];
-      n = ccl_links(v, t[ly + 1][lx], t[ly][lx + 1], t[ly][lx], t[ly][lx + 2], x, y, g.Wd);
+      const int v = t[ly + 1][lx + TOFF];
+      n = ccl_links(v, t[ly + 1][lx + TOFF - 1], t[ly][lx + TOFF], t[ly][lx + TOFF - 1], t[ly][lx + TOFF + 1], x, y, g.Wd);
     }
     nb[k] = n;
     const unsigned ml = __ballot_sync(0xffffffffu, n.L && lx > 0);  // bit x: x is linked to x-1 inside the tile
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
       r = find_s(L, i);
       const int ry = r / TW, rx = r % TW;
       labf[(size_t)y * Wp + x] = (uint32_t)((y0 + ry) * Wp + (x0 + rx));
-      counted = t[ly + 1][lx + 1] != 127;
+      counted = t[ly + 1][lx + TOFF] != 127;
     }
     const unsigned act = __ballot_sync(0xffffffffu, counted);
     if (counted) {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
     const int ly = wid + 8 * k, lx = lane;
     const int x = x0 + lx, y = y0 + ly;
     if (x >= g.Wd || y >= g.Hd) continue;
-    szf[(size_t)y * Wp + x] = (t[ly + 1][lx + 1] == 127) ? 1u : cnt[ly * TW + lx];
+    szf[(size_t)y * Wp + x] = (t[ly + 1][lx + TOFF] == 127) ? 1u : cnt[ly * TW + lx];
   }
 }
 
