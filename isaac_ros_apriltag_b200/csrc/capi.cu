@@ -82,6 +82,12 @@ struct cuAprilTagsHandle_st {
   float tag_dim = 0;
   // CUDA graph of one whole batch (all stage launches, fork/join of the quad-fit streams, D2H): replayed when the same
   // (n, stream, alignment class, encoding) comes again, e.g. the one-frame-at-a-time node path
+  // chunk pipelining: second lane stream + its own side streams / events
+  cudaStream_t lane_stream = nullptr;
+  cudaStream_t lane_aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_fork = nullptr, lane_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_pipe_start = nullptr, ev_offset = nullptr, ev_lane_done = nullptr;
+  bool pipeline = true;
   cudaGraphExec_t graph_exec = nullptr;
   uint32_t graph_n = 0;
   int graph_fast = -1, graph_enc = -1;
@@ -110,6 +116,15 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
+  for (int i = 0; i < 5; i++) {
+    if (h->lane_aux[i]) cudaStreamDestroy(h->lane_aux[i]);
+    if (h->lane_join[i]) cudaEventDestroy(h->lane_join[i]);
+  }
+  if (h->lane_fork) cudaEventDestroy(h->lane_fork);
+  if (h->ev_pipe_start) cudaEventDestroy(h->ev_pipe_start);
+  if (h->ev_offset) cudaEventDestroy(h->ev_offset);
+  if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
   for (void *p : h->dev_allocs) cudaFree(p);
   if (h->h_frames) cudaFreeHost(h->h_frames);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -361,7 +376,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.cand_count, B);
   ALLOC(ws.out, (size_t)B * g.max_tags);
   ALLOC(ws.out_count, B);
-  ALLOC(ws.counters, CNT_N);
+  ALLOC(ws.counters, (size_t)kMaxChunks * CNT_N);
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   {
     // combination tables: for every nm, all m0<m1<m2<m3<nm in lexicographic order (the serial loops' visiting order)
@@ -394,7 +409,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
-        qres == cudaDriverEntryPointSuccess && getenv("B200AT_USE_TMA") != nullptr) {
+        qres == cudaDriverEntryPointSuccess && getenv("B200AT_NO_TMA") == nullptr) {
       const cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)g.Hd, (cuuint64_t)B};
       const cuuint64_t strides[2] = {(cuuint64_t)Wp, (cuuint64_t)Wp * g.Hd};  // bytes, dims 1..2
       const cuuint32_t box[3] = {64, 33, 1};
@@ -416,8 +431,18 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   if (rc == 0 && cudaMallocHost(&h->h_frames, sizeof(FrameDesc) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaMallocHost(&h->h_out, sizeof(b200AprilTagsDetection_t) * B * g.max_tags) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaMallocHost(&h->h_out_count, sizeof(uint32_t) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
-  if (rc == 0 && cudaMallocHost(&h->h_counters, sizeof(uint32_t) * CNT_N) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+  if (rc == 0 && cudaMallocHost(&h->h_counters, sizeof(uint32_t) * CNT_N * kMaxChunks) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  if (rc == 0 && cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  for (int i = 0; i < 5 && rc == 0; i++) {
+    if (cudaStreamCreateWithFlags(&h->lane_aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    if (rc == 0 && cudaEventCreateWithFlags(&h->lane_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  }
+  if (rc == 0 && cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_pipe_start, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_offset, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  h->pipeline = getenv("B200AT_NO_PIPELINE") == nullptr;
   for (int i = 0; i <= B200AT_NUM_STAGES && rc == 0; i++)
     if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (rc != 0) {
@@ -475,6 +500,69 @@ static int fill_frame_table(cuAprilTagsHandle h, const b200AprilTagsFrame_t *fra
   return B200AT_OK;
 }
 
+// A view of the workspace for frames [f0, f0+..) processed as chunk c of nch: per-frame buffers are offset by f0 frames,
+// the pools (points, clusters, quads) and the counters are split evenly between the chunks.
+static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
+  Workspace v = h->ws;
+  const Geo &g = h->ws.g;
+  const size_t Pp = (size_t)at_Wp(g) * g.Hd;
+  v.frames += f0;
+  v.dec += (size_t)f0 * Pp;
+  v.dec_tmp += (h->ws.blur_ksz > 1) ? (size_t)f0 * Pp : 0;
+  v.thr += (size_t)f0 * Pp;
+  v.thr2 += (size_t)f0 * Pp;
+  v.tmin += (size_t)f0 * g.th * at_twp(g);
+  v.tmax += (size_t)f0 * g.th * at_twp(g);
+  v.lab += (size_t)f0 * Pp;
+  v.csize += (size_t)f0 * Pp;
+  v.hkey += (size_t)f0 * g.hcap;
+  v.hcnt += (size_t)f0 * g.hcap;
+  v.hoff += (size_t)f0 * g.hcap;
+  v.hcur += (size_t)f0 * g.hcap;
+  const uint32_t pc = g.pts_cap / nch, cc = g.clu_cap / nch, qc = g.quad_cap / nch;
+  v.g.pts_cap = pc;
+  v.g.clu_cap = cc;
+  v.g.quad_cap = qc;
+  v.pts += (size_t)c * pc;
+  v.keys += (size_t)c * pc;
+  v.lfps += (size_t)c * pc;
+  v.errs += (size_t)2 * c * pc;
+  v.clusters += (size_t)c * cc;
+  v.bin_idx += (size_t)c * kQuadBins * cc;
+  v.quads += (size_t)c * qc;
+  v.quads_refined += (size_t)c * qc;
+  v.cands += (size_t)f0 * g.cand_cap;
+  v.cand_count += f0;
+  v.out += (size_t)f0 * g.max_tags;
+  v.out_count += f0;
+  v.counters += (size_t)c * CNT_N;
+  v.g.tma_frame0 = f0;
+  if (c & 1) {  // lane 1 has its own side streams / events
+    for (int i = 0; i < 5; i++) {
+      v.aux[i] = h->lane_aux[i];
+      v.ev_join[i] = h->lane_join[i];
+    }
+    v.ev_fork = h->lane_fork;
+  }
+  return v;
+}
+
+static void sum_counters(const uint32_t *c, uint32_t *out) {
+  for (int k = 0; k < CNT_N; k++) out[k] = 0;
+  for (int ch = 0; ch < kMaxChunks; ch++)
+    for (int k = 0; k < CNT_N; k++) {
+      if (k == CNT_STATUS)
+        out[k] |= c[ch * CNT_N + k];
+      else
+        out[k] += c[ch * CNT_N + k];
+    }
+}
+
+// Launch every stage of one batch and queue the D2H of its results.  `hf` is a pinned frame-table slice that must stay
+// untouched until the stream has consumed it; results land in the pinned arrays `out`, `cnt`, `ctr` (kMaxChunks*CNT_N).
+// Large batches are split into frame chunks on two phase-shifted streams: the dense, issue-bound stages of one chunk
+// (threshold / CCL / clustering: many warps, little shared memory) co-run with the shared-memory-bound, latency-bound
+// quad fit of the previous chunk, which leaves most issue slots of an SM idle.
 static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream, FrameDesc *hf,
                         b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, bool timing, int *launches_out,
                         bool table_filled = false) {
@@ -488,29 +576,54 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
   }
   int launches = 0;
   cudaError_t e = cudaMemcpyAsync(ws.frames, hf, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(uint32_t) * CNT_N, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(uint32_t) * CNT_N * kMaxChunks, stream);
   const bool tm = timing;
+  const int nch = (tm || !h->pipeline || n < 32) ? 1 : (n >= 128 ? 4 : 2);
+  if (nch == 1) {
+    g.tma_frame0 = 0;
 #define STAMP(i) \
   if (tm) cudaEventRecord(h->ev[i], stream)
-  STAMP(0);
-  launches += launch_preprocess(ws, (int)n, stream);
-  STAMP(1);
-  launches += launch_threshold(ws, (int)n, stream);
-  STAMP(2);
-  launches += launch_ccl(ws, (int)n, stream);
-  STAMP(3);
-  launches += launch_cluster(ws, (int)n, stream);
-  STAMP(4);
-  launches += launch_quadfit(ws, (int)n, stream);
-  STAMP(5);
-  launches += launch_decode(ws, (int)n, stream);
-  STAMP(6);
-  launches += launch_finalize(ws, (int)n, stream);
-  STAMP(7);
+    STAMP(0);
+    launches += launch_preprocess(ws, (int)n, stream);
+    STAMP(1);
+    launches += launch_threshold(ws, (int)n, stream);
+    STAMP(2);
+    launches += launch_ccl(ws, (int)n, stream);
+    STAMP(3);
+    launches += launch_cluster(ws, (int)n, stream);
+    STAMP(4);
+    launches += launch_quadfit(ws, (int)n, stream);
+    STAMP(5);
+    launches += launch_decode(ws, (int)n, stream);
+    STAMP(6);
+    launches += launch_finalize(ws, (int)n, stream);
+    STAMP(7);
+  } else {
+    const int per = ((int)n + nch - 1) / nch;
+    cudaEventRecord(h->ev_pipe_start, stream);
+    cudaStreamWaitEvent(h->lane_stream, h->ev_pipe_start, 0);
+    for (int c = 0; c < nch; c++) {
+      const int f0 = c * per, m = std::min(per, (int)n - f0);
+      if (m <= 0) break;
+      const Workspace v = make_view(h, f0, c, nch);
+      cudaStream_t st = (c & 1) ? h->lane_stream : stream;
+      if (c == 1) cudaStreamWaitEvent(st, h->ev_offset, 0);  // phase shift: lane 1 starts when chunk 0 leaves its dense stages
+      launches += launch_preprocess(v, m, st);
+      launches += launch_threshold(v, m, st);
+      launches += launch_ccl(v, m, st);
+      launches += launch_cluster(v, m, st);
+      if (c == 0) cudaEventRecord(h->ev_offset, st);
+      launches += launch_quadfit(v, m, st);
+      launches += launch_decode(v, m, st);
+      launches += launch_finalize(v, m, st);
+    }
+    cudaEventRecord(h->ev_lane_done, h->lane_stream);
+    cudaStreamWaitEvent(stream, h->ev_lane_done, 0);
+  }
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(out, ws.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, ws.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, ws.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, ws.counters, sizeof(uint32_t) * CNT_N * kMaxChunks, cudaMemcpyDeviceToHost, stream);
   STAMP(8);
 #undef STAMP
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -604,14 +717,16 @@ int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *det
     if (ids_out)
       for (uint32_t k = 0; k < c; k++) to_id_struct(h->h_out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
   }
-  h->last_status = h->h_counters[CNT_STATUS];
+  uint32_t agg[CNT_N];
+  sum_counters(h->h_counters, agg);
+  h->last_status = agg[CNT_STATUS];
   h->last_counters[0] = (uint64_t)h->launches;
-  h->last_counters[1] = h->h_counters[CNT_POINTS];
-  h->last_counters[2] = h->h_counters[CNT_CLUSTERS];
-  h->last_counters[3] = h->h_counters[CNT_QUADS];
+  h->last_counters[1] = agg[CNT_POINTS];
+  h->last_counters[2] = agg[CNT_CLUSTERS];
+  h->last_counters[3] = agg[CNT_QUADS];
   uint64_t nc = 0;
   h->last_counters[4] = nc;
-  h->last_counters[5] = h->h_counters[CNT_DETS];
+  h->last_counters[5] = agg[CNT_DETS];
   return h->last_status ? B200AT_ERR_OVERFLOW : B200AT_OK;
 }
 
@@ -663,7 +778,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     h->hp_counters = nullptr;
     h->hp_cap_frames = h->hp_cap_subs = 0;
     if (cudaMallocHost(&h->hp_frames, sizeof(FrameDesc) * n) != cudaSuccess || cudaMallocHost(&h->hp_out, sizeof(b200AprilTagsDetection_t) * (size_t)n * mt) != cudaSuccess ||
-        cudaMallocHost(&h->hp_out_count, sizeof(uint32_t) * n) != cudaSuccess || cudaMallocHost(&h->hp_counters, sizeof(uint32_t) * CNT_N * nsub) != cudaSuccess)
+        cudaMallocHost(&h->hp_out_count, sizeof(uint32_t) * n) != cudaSuccess || cudaMallocHost(&h->hp_counters, sizeof(uint32_t) * CNT_N * kMaxChunks * nsub) != cudaSuccess)
       return fail(B200AT_ERR_NOMEM);
     h->hp_cap_frames = n;
     h->hp_cap_subs = nsub;
@@ -688,7 +803,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
     int l = 0;
     rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
-                      h->hp_counters + (size_t)k * CNT_N, false, &l);
+                      h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l);
     launches += l;
     if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], h->own_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
@@ -703,7 +818,8 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   uint32_t status = 0;
   uint64_t pts = 0, clu = 0, qd = 0, dt = 0;
   for (uint32_t k = 0; k < nsub; k++) {
-    const uint32_t *c = h->hp_counters + (size_t)k * CNT_N;
+    uint32_t c[CNT_N];
+    sum_counters(h->hp_counters + (size_t)k * CNT_N * kMaxChunks, c);
     status |= c[CNT_STATUS];
     pts += c[CNT_POINTS];
     clu += c[CNT_CLUSTERS];

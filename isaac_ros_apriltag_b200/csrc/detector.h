@@ -65,6 +65,7 @@ struct Cand {  // decoded candidate before reconcile
 enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_WORK_DECODE = 7,
        CNT_BIN0 = 8 /* ..13: clusters per size bin */, CNT_WORK0 = 14 /* ..19: quad-fit work queues */, CNT_N = 24 };
 constexpr int kQuadBins = 6;
+constexpr int kMaxChunks = 4;  // a batch is processed as up to 4 frame chunks on two phase-shifted streams
 enum { ST_HASH_FULL = 1, ST_POINTS_FULL = 2, ST_CLUSTERS_FULL = 4, ST_QUADS_FULL = 8, ST_CANDS_FULL = 16, ST_OUT_TRUNC = 32 };
 
 struct Geo {
@@ -84,6 +85,7 @@ struct Geo {
   uint32_t cand_cap;   // candidates per frame
   uint32_t max_tags;   // outputs per frame
   uint32_t max_cluster_pts;  // 2*(2*Wd+2*Hd)
+  int tma_frame0;      // frame offset of this workspace view inside the whole-batch TMA tensor
 };
 
 struct FitParams {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(TPITCH * (TH + 1))) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-          "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - TOFF), "r"(y0 - 1), "r"(fr), "r"(mb)
+          "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - TOFF), "r"(y0 - 1), "r"(fr + g.tma_frame0), "r"(mb)
           : "memory");
     }
     asm volatile(
