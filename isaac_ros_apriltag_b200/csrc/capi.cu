@@ -259,7 +259,9 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   }
   const uint32_t B = opt.max_batch;
   const size_t Wp = (size_t)at_Wp(g), Pp = Wp * g.Hd, Pd = (size_t)g.Wd * g.Hd;
-  g.hcap = opt.hash_slots_per_frame ? next_pow2(opt.hash_slots_per_frame) : next_pow2((uint32_t)std::max<size_t>(Pd / 2, 4096));
+  // one slot per (black component, white component) pair with both >= 25 px: measured ~1 k per 1080p frame even on the
+  // all-texture bench workload; Pd/8 slots leave room for ~40 k pairs (a 5x5-cell checkerboard) before ST_HASH_FULL
+  g.hcap = opt.hash_slots_per_frame ? next_pow2(opt.hash_slots_per_frame) : next_pow2((uint32_t)std::max<size_t>(Pd / 8, 4096));
   const size_t ppf = opt.points_per_frame ? opt.points_per_frame : Pd;
   const size_t cpf = opt.clusters_per_frame ? opt.clusters_per_frame : std::max<size_t>(Pd / 64, 1024);
   const size_t qpf = opt.quads_per_frame ? opt.quads_per_frame : 1024;
@@ -442,7 +444,9 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   if (rc == 0 && cudaEventCreateWithFlags(&h->ev_pipe_start, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (rc == 0 && cudaEventCreateWithFlags(&h->ev_offset, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (rc == 0 && cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  h->pipeline = getenv("B200AT_NO_PIPELINE") == nullptr;
+  // measured in round 1: no gain (the quad-fit CTAs fill the SMs' shared memory, so dense-stage CTAs cannot co-reside);
+  // kept as an opt-in experiment
+  h->pipeline = getenv("B200AT_PIPELINE") != nullptr;
   for (int i = 0; i <= B200AT_NUM_STAGES && rc == 0; i++)
     if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (rc != 0) {
@@ -752,7 +756,11 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     return code;
   };
   // sub-batch size: small enough that copy(k+1) overlaps compute(k) inside one call, large enough to fill the GPU
-  const uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 7) / 8)));
+  uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 15) / 16)));
+  if (const char *es = getenv("B200AT_HOST_SUB")) {
+    const int v = atoi(es);
+    if (v >= 1) S = std::min<uint32_t>(h->max_batch, (uint32_t)v);
+  }
   if (!h->d_stage) {
     h->stage_pitch = (row + 255) & ~(size_t)255;
     h->stage_sub = S;

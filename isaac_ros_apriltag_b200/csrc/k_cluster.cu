@@ -12,42 +12,6 @@
 
 namespace b200at {
 
-__device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdULL;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ULL;
-  k ^= k >> 33;
-  return (uint32_t)k;
-}
-
-// find-or-insert; returns slot or 0xffffffff when the table is full
-__device__ __forceinline__ uint32_t hash_insert(unsigned long long *hk, uint32_t hcap, unsigned long long key) {
-  const uint32_t mask = hcap - 1;
-  uint32_t slot = hash_key(key) & mask;
-  for (uint32_t probe = 0; probe < hcap; probe++) {
-    unsigned long long cur = hk[slot];
-    if (cur == key) return slot;
-    if (cur == 0ULL) {
-      unsigned long long old = atomicCAS(&hk[slot], 0ULL, key);
-      if (old == 0ULL || old == key) return slot;
-    }
-    slot = (slot + 1) & mask;
-  }
-  return 0xffffffffu;
-}
-__device__ __forceinline__ uint32_t hash_find(const unsigned long long *hk, uint32_t hcap, unsigned long long key) {
-  const uint32_t mask = hcap - 1;
-  uint32_t slot = hash_key(key) & mask;
-  for (uint32_t probe = 0; probe < hcap; probe++) {
-    unsigned long long cur = hk[slot];
-    if (cur == key) return slot;
-    if (cur == 0ULL) return 0xffffffffu;
-    slot = (slot + 1) & mask;
-  }
-  return 0xffffffffu;
-}
-
 // The four probes of pixel (x, y).  thr2 already folds both size gates (components < 25 px read as 127), so a
 // point exists iff v0 + v1 == 255.  `connected_last`: the (-1,1) probe is skipped when the previous pixel's
 // (1,1) probe produced a point; at x == 1 there is no previous pixel.
@@ -308,7 +272,7 @@ int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
   dim3 gp((g.Wd - 2 + 255) / 256, g.Hd - 2, nframes);
   k_cluster_pass<false><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
-  const int segs = g.hcap >= 16384 ? 8 : 1;  // hcap is a power of two
+  const int segs = g.hcap >= 65536 ? 4 : 1;  // hcap is a power of two
   k_cluster_select<<<nframes * segs, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters, segs);
   k_cluster_pass<true><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
   return 5;
