@@ -590,27 +590,15 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     if (nm < 4) continue;
 
     // ---- Phase J: line fits between every ordered pair of kept maxima ----
-    // two independent fits per iteration (their double-precision division chains overlap)
-    for (int t = tid; t < nm * nm; t += 2 * THREADS) {
-      const int t2 = t + THREADS;
-      const int a0 = t / nm, b0 = t - a0 * nm;
-      const int a1 = t2 / nm, b1 = t2 - a1 * nm;
-      const bool v0 = a0 != b0, v1 = (t2 < nm * nm) && (a1 != b1);
-      double lp0[4], e0 = 0, m0 = 0, lp1[4], e1 = 0, m1 = 0;
-      if (v0) fit_line_dev(lf, sz, s_fm[a0], s_fm[b0], lp0, &e0, &m0);
-      if (v1) fit_line_dev(lf, sz, s_fm[a1], s_fm[b1], lp1, &e1, &m1);
-      if (v0) {
-        p_err[a0][b0] = e0;
-        p_mse[a0][b0] = m0;
-        p_nx[a0][b0] = lp0[2];
-        p_ny[a0][b0] = lp0[3];
-      }
-      if (v1) {
-        p_err[a1][b1] = e1;
-        p_mse[a1][b1] = m1;
-        p_nx[a1][b1] = lp1[2];
-        p_ny[a1][b1] = lp1[3];
-      }
+    for (int t = tid; t < nm * nm; t += THREADS) {
+      int a = t / nm, b = t - a * nm;
+      if (a == b) continue;
+      double lp[4], e, m;
+      fit_line_dev(lf, sz, s_fm[a], s_fm[b], lp, &e, &m);
+      p_err[a][b] = e;
+      p_mse[a][b] = m;
+      p_nx[a][b] = lp[2];
+      p_ny[a][b] = lp[3];
     }
     cta_sync<THREADS>();
 
