@@ -220,16 +220,30 @@ __global__ void __launch_bounds__(256) k_threshold4(Geo g, const uint8_t *__rest
   const uint8_t *mxb = tmax + (size_t)fr * g.th * twp;
   const int tx0 = blockIdx.x * blockDim.x * 4, ty0 = blockIdx.y * blockDim.y;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < 10 * 136; i += 256) {
-    const int r = i / 136, c = i - r * 136;
-    const int tyy = ty0 - 1 + r, txx = tx0 - 4 + c;
-    uint8_t a = 255, b = 0;  // neutral for min / max: tiles outside the grid do not take part (upstream skips them)
-    if (tyy >= 0 && tyy < g.th && txx >= 0 && txx < g.tw) {
-      a = mnb[(size_t)tyy * twp + txx];
-      b = mxb[(size_t)tyy * twp + txx];
+  // staging: 10 rows x 34 words per array; a word = 4 consecutive tiles.  Whole-word loads when the tile pitch is a
+  // multiple of 4 and the word lies inside the tile grid, byte-wise with neutral fill otherwise.
+  const bool words_ok = (twp & 3) == 0;
+  for (int i = tid; i < 10 * 34; i += 256) {
+    const int r = i / 34, w = i - r * 34;
+    const int tyy = ty0 - 1 + r, txx = tx0 - 4 + 4 * w;
+    uint32_t a = 0xffffffffu, b = 0;  // neutral for min / max: tiles outside the grid do not take part
+    if (tyy >= 0 && tyy < g.th) {
+      if (words_ok && txx >= 0 && txx + 3 < g.tw) {
+        a = *reinterpret_cast<const uint32_t *>(mnb + (size_t)tyy * twp + txx);
+        b = *reinterpret_cast<const uint32_t *>(mxb + (size_t)tyy * twp + txx);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int tx = txx + k;
+          if (tx >= 0 && tx < g.tw) {
+            a = (a & ~(0xffu << (8 * k))) | ((uint32_t)mnb[(size_t)tyy * twp + tx] << (8 * k));
+            b |= (uint32_t)mxb[(size_t)tyy * twp + tx] << (8 * k);
+          }
+        }
+      }
     }
-    s_mn[r][c] = a;
-    s_mx[r][c] = b;
+    *reinterpret_cast<uint32_t *>(&s_mn[r][4 * w]) = a;
+    *reinterpret_cast<uint32_t *>(&s_mx[r][4 * w]) = b;
   }
   __syncthreads();
   if (tq * 16 >= Wp || ty >= nty) return;

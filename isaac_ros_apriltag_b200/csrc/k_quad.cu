@@ -14,12 +14,14 @@
 // Latency-bound stage (O(boundary points)); HBM bytes are ~12 B per point (read packed point, write sorted key).
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "detector.h"
 
 namespace b200at {
 
 constexpr int MAXM = kMaxNMaxima;  // max_nmaxima upper bound
-constexpr int SCAN_CH = 512;   // staging chunk of the sequential scan when moments live in global memory
 
 struct LF6 {
   double Mx, My, Mxx, Mxy, Myy, W;
@@ -227,7 +229,7 @@ struct ComboTable {
   int off[18];
 };
 
-template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS>
+template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS, int SCAN_CH>
 __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
                                                      const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
                                                      unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
@@ -758,16 +760,16 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
   }
 }
 
-template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS>
+template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS, int SCAN_CH>
 static void launch_bin(const Workspace &ws, int bin, int ctas_per_sm, int sms, const ComboTable &ct, cudaStream_t st) {
   const Geo &g = ws.g;
   constexpr size_t smem = (size_t)(2 * NCAP + 6 * ((ALL_SMEM ? NCAP : SCAN_CH) + 1)) * 8;  // keys/errA + errB|sort scratch + moments|staging
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS, SCAN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS><<<sms * ctas_per_sm, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys,
+  k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS, SCAN_CH><<<sms * ctas_per_sm, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys,
                                                                                   ws.lfps, ws.errs, ws.dec, ws.quads, ws.counters, ct,
                                                                                   at_Wp(g));
 }
@@ -785,12 +787,24 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   // the bins are independent: fork onto side streams; large clusters (the long poles) are issued first
   cudaEventRecord(ws.ev_fork, s);
   for (int i = 0; i < 5; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
-  launch_bin<256, 4096, false, 16>(ws, 5, 2, sms, ct, s);          // n > 2048 (n > 4096: global-memory sort fallback)
-  launch_bin<256, 2048, false, 8>(ws, 4, 3, sms, ct, ws.aux[0]);   // n <= 2048
-  launch_bin<128, 1024, true, 8>(ws, 3, 3, sms, ct, ws.aux[1]);    // n <= 1024
-  launch_bin<64, 512, true, 8>(ws, 2, 6, sms, ct, ws.aux[2]);      // n <= 512
-  launch_bin<32, 256, true, 8>(ws, 1, 10, sms, ct, ws.aux[3]);     // n <= 256
-  launch_bin<32, 128, true, 4>(ws, 0, 16, sms, ct, ws.aux[4]);     // n <= 128
+  // tuning knobs (experiments): B200AT_QF_SCALE scales the CTAs per SM of every bin (leave shared memory free for co-running
+  // dense kernels); B200AT_QF_GLOBAL=1 keeps the moments of the <=1024-point bins in the L2-resident scratch instead of
+  // shared memory (smaller CTAs, more of them per SM)
+  static const double qscale = getenv("B200AT_QF_SCALE") ? atof(getenv("B200AT_QF_SCALE")) : 1.0;
+  static const bool qglobal = getenv("B200AT_QF_GLOBAL") != nullptr;
+  auto sc = [&](int c) { return std::max(1, (int)(c * qscale + 0.5)); };
+  launch_bin<256, 4096, false, 16, 512>(ws, 5, sc(2), sms, ct, s);          // n > 2048 (n > 4096: global-memory sort fallback)
+  launch_bin<256, 2048, false, 8, 512>(ws, 4, sc(3), sms, ct, ws.aux[0]);   // n <= 2048
+  if (!qglobal) {
+    launch_bin<128, 1024, true, 8, 512>(ws, 3, sc(3), sms, ct, ws.aux[1]);  // n <= 1024
+    launch_bin<64, 512, true, 8, 512>(ws, 2, sc(6), sms, ct, ws.aux[2]);    // n <= 512
+    launch_bin<32, 256, true, 8, 512>(ws, 1, sc(10), sms, ct, ws.aux[3]);   // n <= 256
+  } else {
+    launch_bin<128, 1024, false, 8, 128>(ws, 3, sc(5), sms, ct, ws.aux[1]);
+    launch_bin<64, 512, false, 8, 128>(ws, 2, sc(12), sms, ct, ws.aux[2]);
+    launch_bin<32, 256, false, 8, 64>(ws, 1, sc(18), sms, ct, ws.aux[3]);
+  }
+  launch_bin<32, 128, true, 4, 512>(ws, 0, sc(16), sms, ct, ws.aux[4]);     // n <= 128
   for (int i = 0; i < 5; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);
