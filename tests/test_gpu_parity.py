@@ -239,3 +239,30 @@ def test_cuda_graph_replay_matches_plain_launches(pu):
     assert sum(len(x) for x in want01) >= 2
     det.close()
     ref.close()
+
+
+def test_bench_workload_frames_match_oracle(pu):
+    """The 32 distinct frames bench.py tiles into its 256-frame batch (C2, bgr8): tag IDs and Hamming distance exact,
+    corners / centre within TOL_CORNER_PX, pose within tolerance, for every frame, through the batch entry point."""
+    import torch
+    from isaac_ros_apriltag_b200 import capi, synth
+    from oracle import oracle as O
+    frames, truths, K, ts, fams = synth.make_config_frames("C2", 32)
+    bgr = np.ascontiguousarray(np.repeat(frames[:, :, :, None], 3, axis=3))
+    H, W = frames.shape[1:]
+    det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=ts, families=fams, encoding="bgr8",
+                        max_batch=32, max_tags=64)
+    t, ptrs, pitch = pu.upload(bgr)
+    gd = det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream)
+    assert det.status() == 0
+    od, _ = O.detect_batch(bgr, fams, nthreads=min(16, os.cpu_count() or 1), encoding="bgr8")
+    ndet = 0
+    for i in range(32):
+        assert [(d["id"], d["hamming"]) for d in od[i]] == [(int(a), int(b)) for a, b in zip(gd[i]["id"], gd[i]["hamming"])], i
+        assert sorted(d["id"] for d in od[i] if d["hamming"] == 0) == sorted(tr["id"] for tr in truths[i]), i
+        for a, b in zip(gd[i], od[i]):
+            assert np.abs(a["p"] - b["p"]).max() <= TOL_CORNER_PX and np.abs(a["c"] - b["c"]).max() <= TOL_CORNER_PX
+            assert abs(float(a["decision_margin"]) - b["decision_margin"]) <= TOL_MARGIN
+            ndet += 1
+    assert ndet == 320
+    det.close()
