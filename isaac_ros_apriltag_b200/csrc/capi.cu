@@ -774,7 +774,34 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
-  const uint32_t nsub = (n + S - 1) / S;
+  // sub-batch schedule: ramp up (S/4, S/2) and down (S/2, S/4) so the pipeline fill (first copy, nothing to overlap with)
+  // and drain (last kernels, no copy left to hide them) are short; full-size sub-batches in between
+  std::vector<uint32_t> sub_start, sub_len;
+  {
+    uint32_t pos = 0;
+    const uint32_t ramp[2] = {std::max<uint32_t>(1, S / 4), std::max<uint32_t>(1, S / 2)};
+    const bool use_ramp = n >= 4 * S;
+    const uint32_t tail_total = use_ramp ? ramp[0] + ramp[1] : 0;
+    if (use_ramp)
+      for (int r = 0; r < 2; r++) {
+        sub_start.push_back(pos);
+        sub_len.push_back(ramp[r]);
+        pos += ramp[r];
+      }
+    while (pos < n - tail_total) {
+      const uint32_t m = std::min<uint32_t>(S, n - tail_total - pos);
+      sub_start.push_back(pos);
+      sub_len.push_back(m);
+      pos += m;
+    }
+    if (use_ramp)
+      for (int r = 1; r >= 0; r--) {
+        sub_start.push_back(pos);
+        sub_len.push_back(ramp[r]);
+        pos += ramp[r];
+      }
+  }
+  const uint32_t nsub = (uint32_t)sub_start.size();
   if (h->hp_cap_frames < n || h->hp_cap_subs < nsub) {
     if (h->hp_frames) cudaFreeHost(h->hp_frames);
     if (h->hp_out) cudaFreeHost(h->hp_out);
@@ -794,7 +821,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   std::vector<b200AprilTagsFrame_t> dframes(S);
   int launches = 0;
   for (uint32_t k = 0; k < nsub && rc == B200AT_OK; k++) {
-    const uint32_t i0 = k * S, m = std::min(S, n - i0);
+    const uint32_t i0 = sub_start[k], m = sub_len[k];
     const int slot = (int)(k & 1);
     uint8_t *slot_base = h->d_stage + (size_t)slot * S * h->stage_pitch * g.H;
     cudaError_t e = cudaSuccess;
