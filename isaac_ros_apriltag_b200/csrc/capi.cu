@@ -774,32 +774,12 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
-  // sub-batch schedule: ramp up (S/4, S/2) and down (S/2, S/4) so the pipeline fill (first copy, nothing to overlap with)
-  // and drain (last kernels, no copy left to hide them) are short; full-size sub-batches in between
+  // uniform sub-batches (a ramped schedule -- small first/last sub-batches to shorten pipeline fill and drain -- was
+  // measured and did not pay: the tiny sub-batches cost more in launch overhead than they save)
   std::vector<uint32_t> sub_start, sub_len;
-  {
-    uint32_t pos = 0;
-    const uint32_t ramp[2] = {std::max<uint32_t>(1, S / 4), std::max<uint32_t>(1, S / 2)};
-    const bool use_ramp = n >= 4 * S;
-    const uint32_t tail_total = use_ramp ? ramp[0] + ramp[1] : 0;
-    if (use_ramp)
-      for (int r = 0; r < 2; r++) {
-        sub_start.push_back(pos);
-        sub_len.push_back(ramp[r]);
-        pos += ramp[r];
-      }
-    while (pos < n - tail_total) {
-      const uint32_t m = std::min<uint32_t>(S, n - tail_total - pos);
-      sub_start.push_back(pos);
-      sub_len.push_back(m);
-      pos += m;
-    }
-    if (use_ramp)
-      for (int r = 1; r >= 0; r--) {
-        sub_start.push_back(pos);
-        sub_len.push_back(ramp[r]);
-        pos += ramp[r];
-      }
+  for (uint32_t pos = 0; pos < n; pos += S) {
+    sub_start.push_back(pos);
+    sub_len.push_back(std::min<uint32_t>(S, n - pos));
   }
   const uint32_t nsub = (uint32_t)sub_start.size();
   if (h->hp_cap_frames < n || h->hp_cap_subs < nsub) {
