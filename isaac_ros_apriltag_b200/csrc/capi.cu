@@ -215,9 +215,10 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   if (opt.max_batch == 0 || opt.max_tags == 0 || opt.tile_size == 0) return B200AT_ERR_INVALID_ARG;
   if (opt.family_mask == 0 || (opt.family_mask >> B200AT_NUM_FAMILIES) != 0) return B200AT_ERR_UNSUPPORTED;
   if (bpp_of(opt.input_encoding) == 0) return B200AT_ERR_INVALID_ARG;
-  // integer decimation only (AprilRobotics' 3->2 "1.5" special case is not built)
+  // integer decimation factors, plus AprilRobotics' 3->2 "1.5" special case
   float qd = opt.quad_decimate;
-  if (!(qd >= 1.0f) || qd != floorf(qd) || qd > 8.0f) return B200AT_ERR_UNSUPPORTED;
+  const bool dec15 = (qd == 1.5f);
+  if (!dec15 && (!(qd >= 1.0f) || qd != floorf(qd) || qd > 8.0f)) return B200AT_ERR_UNSUPPORTED;
   if (opt.max_nmaxima < 4 || opt.max_nmaxima > kMaxNMaxima) return B200AT_ERR_UNSUPPORTED;
   if (opt.max_hamming < 0 || opt.max_hamming > 3) return B200AT_ERR_UNSUPPORTED;
   int ndev = 0;
@@ -240,12 +241,17 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   Workspace &ws = h->ws;
   memset(&ws, 0, sizeof(ws));
   Geo &g = ws.g;
-  const int f = (int)qd;
+  const int f = dec15 ? 0 : (int)qd;  // Geo::f == 0 marks the 1.5 mode
   g.W = (int)W;
   g.H = (int)H;
   g.f = f;
-  g.Wd = f > 1 ? 1 + ((int)W - 1) / f : (int)W;
-  g.Hd = f > 1 ? 1 + ((int)H - 1) / f : (int)H;
+  if (dec15) {
+    g.Wd = (int)W / 3 * 2;
+    g.Hd = (int)H / 3 * 2;
+  } else {
+    g.Wd = f > 1 ? 1 + ((int)W - 1) / f : (int)W;
+    g.Hd = f > 1 ? 1 + ((int)H - 1) / f : (int)H;
+  }
   g.ts = (int)opt.tile_size;
   g.tw = g.Wd / g.ts;
   g.th = g.Hd / g.ts;

@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(DT) k_decode(Geo g, FitParams fp, DecodeFams f
     // ---- a11: rescale to the full-resolution frame ----
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      if (fp.quad_decimate > 1) {
+      if (fp.quad_decimate == 1.5f) {
+        p[j][0] = q0.p[j][0] * fp.quad_decimate;  // float *= float, as upstream for the 1.5 special case
+        p[j][1] = q0.p[j][1] * fp.quad_decimate;
+      } else if (fp.quad_decimate > 1) {
         p[j][0] = (float)(((double)q0.p[j][0] - 0.5) * (double)fp.quad_decimate + 0.5);
         p[j][1] = (float)(((double)q0.p[j][1] - 0.5) * (double)fp.quad_decimate + 0.5);
       } else {

@@ -130,6 +130,30 @@ __global__ void __launch_bounds__(256) k_preprocess(Geo g, const FrameDesc *__re
   }
 }
 
+// quad_decimate == 1.5: AprilRobotics' special case (image_u8_decimate, ffactor == 1.5): every 3x3 block of the (gray)
+// input becomes a 2x2 block, each output a fixed integer-weighted mean of its 2x2 corner of the block, /9 truncating.
+// One thread per 2x2 output block.  Geo::f == 0 marks this mode.
+__global__ void __launch_bounds__(256) k_decimate_1p5(Geo g, const FrameDesc *__restrict__ frames, uint8_t *__restrict__ dec, int Wp) {
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int by = blockIdx.y * blockDim.y + threadIdx.y;
+  const int fr = blockIdx.z;
+  if (bx * 2 >= g.Wd || by * 2 >= g.Hd) return;
+  const FrameDesc fd = frames[fr];
+  int v[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const uint8_t *row = fd.ptr + (size_t)(by * 3 + r) * fd.pitch;
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[r][c] = (int)gray_generic(row, bx * 3 + c, g.enc, g.bpp);
+  }
+  const int a = v[0][0], b = v[0][1], c = v[0][2], d = v[1][0], e = v[1][1], f = v[1][2], gg = v[2][0], h = v[2][1], i = v[2][2];
+  uint8_t *o = dec + (size_t)fr * g.Hd * Wp + (size_t)(by * 2) * Wp + bx * 2;
+  o[0] = (uint8_t)((4 * a + 2 * b + 2 * d + e) / 9);
+  o[1] = (uint8_t)((4 * c + 2 * b + 2 * f + e) / 9);
+  o[Wp] = (uint8_t)((4 * gg + 2 * d + 2 * h + e) / 9);
+  o[Wp + 1] = (uint8_t)((4 * i + 2 * f + 2 * h + e) / 9);
+}
+
 // standalone per-tile min/max for tile sizes != 4 or after blur (thread per tile)
 __global__ void k_tile_minmax(Geo g, const uint8_t *__restrict__ dec, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax,
                               int Wp, int twp) {
@@ -349,7 +373,7 @@ int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s) {
   int launches = 0;
   dim3 blk(64, 4);
   dim3 grd(((g.Wd + 3) / 4 + 63) / 64, ((g.Hd + 3) / 4 + 3) / 4, nframes);
-  const int fused_minmax = (g.ts == 4 && ws.blur_ksz <= 1) ? 1 : 0;
+  const int fused_minmax = (g.ts == 4 && ws.blur_ksz <= 1 && g.f != 0) ? 1 : 0;
   // fast path legality (host side: the frame table was validated when it was uploaded; see capi)
   int ch = g.bpp;
   int fast = (g.f == 1 || g.f == 2) ? 1 : 0;
@@ -357,7 +381,10 @@ int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s) {
   Geo gg = g;
 #define LAUNCH_PP(CH, F) \
   k_preprocess<CH, F><<<grd, blk, 0, s>>>(gg, ws.frames, ws.dec, ws.tmin, ws.tmax, Wp, twp, fast, fused_minmax)
-  if (fast && g.f == 1) {
+  if (g.f == 0) {
+    dim3 b15(32, 8), g15((g.Wd / 2 + 31) / 32, (g.Hd / 2 + 7) / 8, nframes);
+    k_decimate_1p5<<<g15, b15, 0, s>>>(gg, ws.frames, ws.dec, Wp);
+  } else if (fast && g.f == 1) {
     if (ch == 1) LAUNCH_PP(1, 1);
     else if (ch == 3) LAUNCH_PP(3, 1);
     else LAUNCH_PP(4, 1);

@@ -43,8 +43,8 @@ def test_argument_validation_and_no_cpu_fallback():
     o = capi.default_options()
     cam = capi.Intrinsics(1, 1, 0, 0)
     assert L.b200AprilTagsCreate(C.byref(h), 0, 480, C.byref(cam), 1.0, C.byref(o)) == 1  # INVALID_ARG
-    o.quad_decimate = 1.5
-    assert L.b200AprilTagsCreate(C.byref(h), 640, 480, C.byref(cam), 1.0, C.byref(o)) == 2  # UNSUPPORTED
+    o.quad_decimate = 2.5
+    assert L.b200AprilTagsCreate(C.byref(h), 640, 480, C.byref(cam), 1.0, C.byref(o)) == 2  # UNSUPPORTED (only integers and 1.5)
     o = capi.default_options()
     o.family_mask = 1 << 7
     assert L.b200AprilTagsCreate(C.byref(h), 640, 480, C.byref(cam), 1.0, C.byref(o)) == 2

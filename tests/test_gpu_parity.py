@@ -80,7 +80,7 @@ def test_odd_sizes_partial_tiles(pu, w, h):
     assert_exact(res, rep)
 
 
-@pytest.mark.parametrize("opts", [dict(quad_decimate=1.0), dict(quad_decimate=3.0), dict(quad_sigma=0.8), dict(quad_sigma=-0.8),
+@pytest.mark.parametrize("opts", [dict(quad_decimate=1.0), dict(quad_decimate=1.5), dict(quad_decimate=3.0), dict(quad_sigma=0.8), dict(quad_sigma=-0.8),
                                   dict(tile_size=8), dict(refine_edges=0), dict(decode_sharpening=0.0), dict(max_hamming=1),
                                   dict(min_white_black_diff=20)])
 def test_detector_knobs(pu, opts):
