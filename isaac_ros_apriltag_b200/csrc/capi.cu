@@ -228,6 +228,14 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   }
   cuAprilTagsHandle_st *h = new (std::nothrow) cuAprilTagsHandle_st();
   if (!h) return B200AT_ERR_NOMEM;
+  int caller_device = -1;
+  cudaGetDevice(&caller_device);
+  struct RestoreDevice {  // the caller's current device is left as it was found
+    int d;
+    ~RestoreDevice() {
+      if (d >= 0) cudaSetDevice(d);
+    }
+  } restore_device{caller_device};
   if (opt.device >= 0) {
     if (cudaSetDevice(opt.device) != cudaSuccess) {
       delete h;

@@ -764,10 +764,13 @@ template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS, int SCAN_CH>
 static void launch_bin(const Workspace &ws, int bin, int ctas_per_sm, int sms, const ComboTable &ct, cudaStream_t st) {
   const Geo &g = ws.g;
   constexpr size_t smem = (size_t)(2 * NCAP + 6 * ((ALL_SMEM ? NCAP : SCAN_CH) + 1)) * 8;  // keys/errA + errB|sort scratch + moments|staging
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS, SCAN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev] = true;
   }
   k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS, SCAN_CH><<<sms * ctas_per_sm, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys,
                                                                                   ws.lfps, ws.errs, ws.dec, ws.quads, ws.counters, ct,

@@ -1,0 +1,39 @@
+"""Code tables: the committed generated files are what tools/gen_families.py produces from the OpenCV dictionaries, and the
+three copies (oracle .inc, device .inc, Python JSON) agree."""
+import importlib.util
+import os
+
+from isaac_ros_apriltag_b200.families import families, tag_cells
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("gen_families", os.path.join(ROOT, "tools", "gen_families.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_generated_tables_are_reproducible():
+    m = _gen()
+    text = m.emit()  # asserts the upstream table heads and the minimum inter-code distances while generating
+    for rel in ("oracle/tag_families_data.inc", "isaac_ros_apriltag_b200/csrc/tag_families_data.inc"):
+        assert open(os.path.join(ROOT, rel)).read() == text, rel
+
+
+def test_json_matches_generator_and_layout():
+    m = _gen()
+    fams = families()
+    for name, dict_id, d, h in m.FAMILIES:
+        codes, bx, by = m.family_codes(dict_id, d)
+        f = fams[name]
+        assert f["codes"] == codes and f["bit_x"] == bx and f["bit_y"] == by
+        assert f["nbits"] == d * d and f["width_at_border"] == d + 2 and f["total_width"] == d + 4 and f["h"] == h
+        # spiral layout: a quarter turn of the cell grid is a cyclic shift of the bit string by nbits/4 (rotate90)
+        q = (d * d) // 4
+        for k in range(q):
+            x, y = bx[k], by[k]
+            assert (bx[k + q], by[k + q]) == (d + 1 - y, x)
+    cells = tag_cells("tag36h11", 0)
+    assert cells.shape == (10, 10) and cells[0].all() and not cells[1, 1:9].any()  # white ring, black border

@@ -268,3 +268,31 @@ def test_bench_workload_frames_match_oracle(pu):
             ndet += 1
     assert ndet >= 0.97 * 320
     det.close()
+
+
+def test_two_devices_one_process(pu):
+    """One process, one handle per GPU (b200AprilTagsOptions_t::device): the per-device kernel attributes, workspaces and
+    streams are independent, the caller's current device is left untouched, results are identical on both GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from isaac_ros_apriltag_b200 import capi, synth
+    frames, truths, K, ts, fams = synth.make_config_frames("C2", 2)
+    H, W = frames.shape[1:]
+    torch.cuda.set_device(0)
+    dets, bufs = [], []
+    for dev in (0, 1):
+        d = capi.Detector(W, H, families=fams, encoding="mono8", max_batch=2, max_tags=64, device=dev)
+        assert torch.cuda.current_device() == 0
+        t = torch.from_numpy(frames).to(f"cuda:{dev}")
+        bufs.append(t)
+        dets.append(d)
+    res = []
+    for dev, (d, t) in enumerate(zip(dets, bufs)):
+        fb = t[0].numel()
+        res.append(d.detect_device([t.data_ptr(), t.data_ptr() + fb], W, 0))
+        assert torch.cuda.current_device() == 0
+    for a, b in zip(res[0], res[1]):
+        assert a.tobytes() == b.tobytes() and len(a) == 10
+    for d in dets:
+        d.close()
