@@ -30,6 +30,27 @@ METRIC = "frames_per_sec_1080p_tag36h11"
 UNIT = "frames/s"
 
 
+def load_ncu_traffic(kernel="k_threshold4"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/, same command and batch as this bench); None when the file is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_final_ncu_full_dense_batch256.csv")
+    try:
+        rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("#"))]
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel in r[0]:
+                tot = 0.0
+                for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(name)
+                    tot += float(r[i]) * scale[units[i]]
+                return tot
+    except Exception:
+        return None
+    return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -271,7 +292,10 @@ def main():
     stage_gbs = {k: (alg[k] * B / (stage_ms[k] / 1e3) / 1e9) if stage_ms.get(k, 0) > 0 else None for k in alg}
     thr_gbs = stage_gbs["threshold"]
     roofline = {"kernel": "k_threshold4", "bound": "hbm", "achieved": thr_gbs, "peak": peak, "unit": "GB/s",
-                "frac": (thr_gbs / peak) if thr_gbs else None, "traffic": None, "peak_source": peak_kind,
+                "frac": (thr_gbs / peak) if thr_gbs else None,
+                "traffic": load_ncu_traffic() if (args.config == "C2" and B == 256 and args.encoding == "bgr8") else None,
+                "traffic_source": "profiles/r01_final_ncu_full_dense_batch256.csv (ncu --set full, bytes per launch)",
+                "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": 2 * Pd * B, "launch_ms": stage_ms.get("threshold")}
     dominant = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else None
 

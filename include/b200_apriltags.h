@@ -14,6 +14,10 @@
  *
  * All functions return 0 on success, non-zero error codes otherwise; no C++ exception crosses this ABI.
  * Plain pointers and sizes only.
+ *
+ * Threading: a handle is not thread-safe (one call in flight per handle, like the reference's single callback group,
+ * apriltag_node.cpp:605-610); independent handles -- e.g. one per GPU via b200AprilTagsOptions_t::device -- may be used
+ * from different threads or from one thread.  The caller's current CUDA device is left unchanged by every call.
  */
 #ifndef B200_APRILTAGS_H_
 #define B200_APRILTAGS_H_
