@@ -84,8 +84,8 @@ struct cuAprilTagsHandle_st {
   // (n, stream, alignment class, encoding) comes again, e.g. the one-frame-at-a-time node path
   // chunk pipelining: second lane stream + its own side streams / events
   cudaStream_t lane_stream = nullptr;
-  cudaStream_t lane_aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t lane_fork = nullptr, lane_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t lane_aux[kQuadAux] = {};
+  cudaEvent_t lane_fork = nullptr, lane_join[kQuadAux] = {};
   cudaEvent_t ev_pipe_start = nullptr, ev_offset = nullptr, ev_lane_done = nullptr;
   bool pipeline = true;
   cudaGraphExec_t graph_exec = nullptr;
@@ -117,7 +117,7 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
-  for (int i = 0; i < 5; i++) {
+  for (int i = 0; i < kQuadAux; i++) {
     if (h->lane_aux[i]) cudaStreamDestroy(h->lane_aux[i]);
     if (h->lane_join[i]) cudaEventDestroy(h->lane_join[i]);
   }
@@ -139,7 +139,7 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (int i = 0; i < 5; i++) {
+  for (int i = 0; i < kQuadAux; i++) {
     if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
     if (h->ws.ev_join[i]) cudaEventDestroy(h->ws.ev_join[i]);
   }
@@ -438,7 +438,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
       cudaGetLastError();
     }
   }
-  for (int i = 0; i < 5 && rc == 0; i++) {
+  for (int i = 0; i < kQuadAux && rc == 0; i++) {
     if (cudaStreamCreateWithFlags(&ws.aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
     if (rc == 0 && cudaEventCreateWithFlags(&ws.ev_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
@@ -450,7 +450,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   if (rc == 0 && cudaMallocHost(&h->h_counters, sizeof(uint32_t) * CNT_N * kMaxChunks) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (rc == 0 && cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  for (int i = 0; i < 5 && rc == 0; i++) {
+  for (int i = 0; i < kQuadAux && rc == 0; i++) {
     if (cudaStreamCreateWithFlags(&h->lane_aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
     if (rc == 0 && cudaEventCreateWithFlags(&h->lane_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
@@ -556,7 +556,7 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
   v.counters += (size_t)c * CNT_N;
   v.g.tma_frame0 = f0;
   if (c & 1) {  // lane 1 has its own side streams / events
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < kQuadAux; i++) {
       v.aux[i] = h->lane_aux[i];
       v.ev_join[i] = h->lane_join[i];
     }

@@ -63,8 +63,9 @@ struct Cand {  // decoded candidate before reconcile
 
 // counters[] slots
 enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_WORK_DECODE = 7,
-       CNT_BIN0 = 8 /* ..13: clusters per size bin */, CNT_WORK0 = 14 /* ..19: quad-fit work queues */, CNT_N = 24 };
-constexpr int kQuadBins = 6;
+       CNT_BIN0 = 8 /* ..15: clusters per size bin */, CNT_WORK0 = 16 /* ..23: quad-fit work queues */, CNT_N = 24 };
+constexpr int kQuadBins = 8;
+constexpr int kQuadAux = kQuadBins - 1;  // side streams: the quad-fit bins run concurrently
 constexpr int kMaxChunks = 4;  // a batch is processed as up to 4 frame chunks on two phase-shifted streams
 enum { ST_HASH_FULL = 1, ST_POINTS_FULL = 2, ST_CLUSTERS_FULL = 4, ST_QUADS_FULL = 8, ST_CANDS_FULL = 16, ST_OUT_TRUNC = 32 };
 
@@ -129,8 +130,8 @@ struct Workspace {
   int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
   CUtensorMap thr_tmap;  // TMA descriptor of thr as a (Wp, Hd, B) u8 tensor, box 64 x 33 x 1 (CCL tile + halo)
   int use_tma;
-  cudaStream_t aux[5];   // side streams: the quad-fit bins run concurrently
-  cudaEvent_t ev_fork, ev_join[5];
+  cudaStream_t aux[kQuadAux];
+  cudaEvent_t ev_fork, ev_join[kQuadAux];
   uint8_t blur_k[32];
   int blur_ksz;
   int blur_sharpen;

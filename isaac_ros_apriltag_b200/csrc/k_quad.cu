@@ -3,14 +3,18 @@
 // (apriltag_quad_thresh.c) with the SAME floating-point types and evaluation order as the
 // CPU oracle, so accept/reject decisions and the float corners are bit-identical (built with -fmad=false).
 //
-// One CTA per boundary-point cluster, clusters binned by size so the CTA shape fits the work:
-//   n <= 128 / 256     : 32-thread CTA (one warp, every barrier is warp-local), everything in shared memory (8 / 16 KB)
-//   n <= 512 / 1024    : 64 / 128-thread CTA, everything in shared memory (33 / 66 KB)
-//   n <= 2048 / larger : 256-thread CTA, sort keys in shared memory (n <= 4096), moments / errors in an L2-resident scratch
-// Per cluster: slope keys (float) -> merge sort of u64 (slope|y|x) keys in shared memory -> line-fit terms -> SEQUENTIAL double prefix sums (a parallel scan would change the
-// roundings; the six moments run as six lanes reading shared memory) -> per-point window error -> 7-tap smoothing ->
-// local maxima -> top-(max_nmaxima) by rank counting -> pair table of line fits -> C(n,4) search over a precomputed
-// combination table with lexicographic arg-min -> corners, area and angle gates.
+// One CTA per boundary-point cluster; clusters are binned by size so that CTA shape and shared-memory footprint fit the
+// work, and every per-point array has a compile-time address space (no generic loads):
+//   QF_ALL   n <= 128 / 256 (one warp), <= 512 (2 warps), <= 1024 (4 warps): keys, errors AND the six prefix moments in
+//            shared memory (64 B per point)
+//   QF_KEYS  n <= 2048 / 4096 (8 warps), <= 8192 (16 warps): keys and errors in shared memory (16 B per point), prefix
+//            moments in an L2-resident scratch; the serial prefix sum is software-pipelined: warp 0 scans chunk c out of one
+//            half of a double-buffered staging ring while the other warps produce the terms of chunk c+1 into the other half
+//   QF_GLOBAL n > 8192 (4K-class frames only): every per-point array in global memory
+// Per cluster: slope keys (float) -> merge sort of u64 (slope|y|x) keys -> line-fit terms -> SEQUENTIAL double prefix sums
+// (a parallel scan would change the roundings; the six moments run as six lanes) -> per-point window error -> 7-tap
+// smoothing -> local maxima -> top-(max_nmaxima) by rank counting -> pair table of line fits -> C(n,4) search over a
+// precomputed combination table with lexicographic arg-min -> corners, area and angle gates.
 // Latency-bound stage (O(boundary points)); HBM bytes are ~12 B per point (read packed point, write sorted key).
 #include <math_constants.h>
 
@@ -44,13 +48,15 @@ struct LfAcc {
       r.Myy = m[4 * stride + i];
       r.W = m[5 * stride + i];
     } else {
-      const LineFitPt p = g[i];
-      r.Mx = p.Mx;
-      r.My = p.My;
-      r.Mxx = p.Mxx;
-      r.Mxy = p.Mxy;
-      r.Myy = p.Myy;
-      r.W = p.W;
+      // 48-byte record, 16-byte aligned: three 128-bit loads
+      const double2 *p = reinterpret_cast<const double2 *>(g + i);
+      const double2 a = p[0], b = p[1], c = p[2];
+      r.Mx = a.x;
+      r.My = a.y;
+      r.Mxx = b.x;
+      r.Mxy = b.y;
+      r.Myy = c.x;
+      r.W = c.y;
     }
     return r;
   }
@@ -150,10 +156,11 @@ __device__ __forceinline__ void cta_sync() {
 // Sort of the u64 keys (unique within a cluster): every thread sorts ITEMS contiguous keys in registers (odd-even
 // transposition network), then log2(n/ITEMS) merge passes between two buffers; in a pass each thread produces ITEMS
 // consecutive outputs of its pair of runs, located with a merge-path binary search.  O(n log n) work instead of the
-// O(n log^2 n) of a bitonic network, one barrier per pass.  Works on shared or global memory (generic pointers).
+// O(n log^2 n) of a bitonic network, one barrier per pass.  Inlined: the address space of the buffers (shared or global)
+// is known at every call site.
 // The sorted sequence ends in `a`.
 template <int THREADS, int ITEMS>
-__device__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n) {
+__device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n) {
   constexpr unsigned long long INF = ~0ull;
   const int tid = threadIdx.x;
   for (int base = tid * ITEMS; base < n; base += THREADS * ITEMS) {
@@ -223,37 +230,182 @@ struct BBoxRed {
   long long s1;
 };
 
+__device__ __forceinline__ void bbox_add(BBoxRed &r, uint32_t p) {
+  const int x = p & 0x3fff, y = (p >> 14) & 0x3fff;
+  const int cxg = (p >> 28) & 3, cyg = (p >> 30) & 3;
+  const int gx = cxg == 0 ? 0 : (cxg == 1 ? 255 : -255), gy = cyg == 0 ? 0 : (cyg == 1 ? 255 : -255);
+  r.xmin = min(r.xmin, x);
+  r.xmax = max(r.xmax, x);
+  r.ymin = min(r.ymin, y);
+  r.ymax = max(r.ymax, y);
+  r.sgx += gx;
+  r.sgy += gy;
+  r.s1 += (long long)x * gx + (long long)y * gy;
+}
+
+// sort key of one boundary point: float slope (monotone angle measure around the bounding-box centre) | y | x
+__device__ __forceinline__ unsigned long long slope_key(uint32_t p, float cx, float cy) {
+  const int x = p & 0x3fff, y = (p >> 14) & 0x3fff;
+  float dx = (float)x - cx;
+  float dy = (float)y - cy;
+  float quadrant;
+  if (dy > 0)
+    quadrant = (dx > 0) ? 65536.0f : 131072.0f;
+  else
+    quadrant = (dx > 0) ? 0.0f : -65536.0f;
+  if (dy < 0) {
+    dy = -dy;
+    dx = -dx;
+  }
+  if (dx < 0) {
+    float tmp = dx;
+    dx = dy;
+    dy = -tmp;
+  }
+  const float slope = quadrant + dy / dx;
+  return ((unsigned long long)float_orderable(slope) << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
+}
+
+// squared gradient magnitude of the decimated image at the (half-resolution) point of a sorted key; 0 on the image
+// border, where the reference uses weight 1 = sqrt(0) + 1
+__device__ __forceinline__ int grad2_at(const uint8_t *__restrict__ im, int Wp, int Wd, int Hd, unsigned long long k) {
+  const int px = (int)(k & 0xffff), py = (int)((k >> 16) & 0xffff);
+  const int ix = (int)(px * .5 + 0.5), iy = (int)(py * .5 + 0.5);
+  int g2 = 0;
+  if (ix > 0 && ix + 1 < Wd && iy > 0 && iy + 1 < Hd) {
+    const uint8_t *c = im + (size_t)iy * Wp + ix;
+    const int grad_x = (int)c[1] - (int)c[-1];
+    const int grad_y = (int)c[Wp] - (int)c[-Wp];
+    g2 = grad_x * grad_x + grad_y * grad_y;
+  }
+  return g2;
+}
+
+// the six line-fit terms of one point (compute_lfps): W*x, W*y, W*x*x, W*x*y, W*y*y, W with x = px/2 + 0.5
+__device__ __forceinline__ void lfp_terms(unsigned long long k, int g2, double t[6]) {
+  const int px = (int)(k & 0xffff), py = (int)((k >> 16) & 0xffff);
+  const double fx = px * .5 + 0.5;
+  const double fy = py * .5 + 0.5;
+  const double W = sqrt((double)g2) + 1;
+  t[0] = W * fx;
+  t[1] = W * fy;
+  t[2] = W * fx * fx;
+  t[3] = W * fx * fy;
+  t[4] = W * fy * fy;
+  t[5] = W;
+}
+
+// sequential prefix sum of `cn` terms (one moment per calling lane): acc carries across chunks
+template <class Store>
+__device__ __forceinline__ double scan_chain(const double *t, int cn, double acc, Store store) {
+  int i = 0;
+  for (; i + 8 <= cn; i += 8) {
+    const double t0 = t[i], t1 = t[i + 1], t2 = t[i + 2], t3 = t[i + 3], t4 = t[i + 4], t5 = t[i + 5], t6 = t[i + 6],
+                 t7 = t[i + 7];
+    acc += t0;
+    store(i, acc);
+    acc += t1;
+    store(i + 1, acc);
+    acc += t2;
+    store(i + 2, acc);
+    acc += t3;
+    store(i + 3, acc);
+    acc += t4;
+    store(i + 4, acc);
+    acc += t5;
+    store(i + 5, acc);
+    acc += t6;
+    store(i + 6, acc);
+    acc += t7;
+    store(i + 7, acc);
+  }
+  for (; i < cn; i++) {
+    acc += t[i];
+    store(i, acc);
+  }
+  return acc;
+}
+
+// Ordered stream compaction of the indices i < n with pred(i): emit(i, position).  Warp w owns a contiguous range of
+// 32-element strips; one count pass, one exclusive scan over the warps, one write pass (a single pass for one-warp CTAs).
+// Returns the number of selected elements (all threads).  The caller synchronises before consuming the emitted data.
+template <int NW, class Pred, class Emit>
+__device__ __forceinline__ int ordered_compact(int n, int lane, int wid, int *s_scan, Pred pred, Emit emit) {
+  const int strips = (n + 31) >> 5;
+  const int spw = (strips + NW - 1) / NW;
+  const int s0 = wid * spw, s1 = min(strips, s0 + spw);
+  int base = 0, total = 0;
+  if (NW > 1) {
+    int cnt = 0;
+    for (int s = s0; s < s1; s++) {
+      const int i = s * 32 + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, i < n && pred(i)));
+    }
+    if (lane == 0) s_scan[wid] = cnt;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      const int v = s_scan[w];
+      base += w < wid ? v : 0;
+      total += v;
+    }
+  }
+  int run = base;
+  for (int s = s0; s < s1; s++) {
+    const int i = s * 32 + lane;
+    const bool p = i < n && pred(i);
+    const unsigned bal = __ballot_sync(0xffffffffu, p);
+    if (p) emit(i, run + __popc(bal & ((1u << lane) - 1)));
+    run += __popc(bal);
+  }
+  return NW > 1 ? total : run;
+}
+
 // combination table for the current nm: all (m0<m1<m2<m3) < nm in lexicographic order, one byte each
 struct ComboTable {
   const uchar4 *c;
   int off[18];
 };
 
-template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS, int SCAN_CH>
-__global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
+enum { QF_ALL = 0, QF_KEYS = 1, QF_GLOBAL = 2 };
+
+template <int NCAP, int MODE, int CH>
+struct QfSmem {
+  static constexpr int TBL = MAXM * MAXM;  // entries per pair table (mse, nx, ny)
+  // region 0: keys (later errA, maxima) | sort scratch (later staging ring / errB); the pair tables alias its start
+  static constexpr int R0 = MODE == QF_GLOBAL ? 3 * TBL : (2 * NCAP > 3 * TBL ? 2 * NCAP : 3 * TBL);
+  static constexpr int WORDS = R0 + (MODE == QF_ALL ? 6 * (NCAP + 1) : 0);
+  static constexpr size_t BYTES = (size_t)WORDS * 8;
+  static_assert(MODE != QF_KEYS || 2 * 6 * (CH + 1) <= NCAP, "staging ring must fit the sort scratch");
+};
+
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
                                                      const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
                                                      unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
                                                      double *__restrict__ errs_pool, const uint8_t *__restrict__ dec,
                                                      QuadRec *__restrict__ quads, uint32_t *__restrict__ counters, ComboTable combos,
                                                      int Wp) {
   constexpr int NW = THREADS / 32;
-  constexpr int MSTRIDE = (ALL_SMEM ? NCAP : SCAN_CH) + 1;
+  constexpr bool SM = MODE != QF_GLOBAL;      // per-point keys / errors in shared memory
+  constexpr bool MSM = MODE == QF_ALL;        // prefix moments in shared memory
+  constexpr int PPT = SM ? NCAP / THREADS : 1;  // points per thread (register cache between the bbox and the key pass)
+  using L = QfSmem<NCAP, MODE, CH>;
+  constexpr int MSTRIDE = NCAP + 1;
+  static_assert(MODE != QF_KEYS || NW >= 2, "the pipelined scan needs producer warps");
   extern __shared__ unsigned long long dsm[];
-  unsigned long long *skeys = dsm;                                  // [NCAP]  keys (later: errA)
-  double *s_errB = reinterpret_cast<double *>(dsm + NCAP);          // [NCAP]  sort scratch, later errB (ALL_SMEM)
-  double *s_M = reinterpret_cast<double *>(dsm + 2 * NCAP);         // [6][MSTRIDE]
+  unsigned long long *skeys = dsm;                              // [NCAP]  keys (later: errA, maxima)
+  double *s_ring = reinterpret_cast<double *>(dsm + NCAP);      // [NCAP]  sort scratch, staging ring (QF_KEYS), errB
+  double *s_M = reinterpret_cast<double *>(dsm + L::R0);        // [6][MSTRIDE] (QF_ALL)
+  double *pt_mse = reinterpret_cast<double *>(dsm), *pt_nx = pt_mse + L::TBL, *pt_ny = pt_nx + L::TBL;
   __shared__ BBoxRed s_red[NW];
   __shared__ int s_cluster;
   __shared__ int s_fm[MAXM];
-  __shared__ int s_nm;
   __shared__ int s_scan[NW];
-  __shared__ int s_run;
   __shared__ double s_rv[NW];
   __shared__ int s_ri[NW];
   __shared__ unsigned int s_rr[NW];
   __shared__ double s_thresh;
-  __shared__ double s_carry[6];
-  __shared__ double p_err[MAXM][MAXM], p_mse[MAXM][MAXM], p_nx[MAXM][MAXM], p_ny[MAXM][MAXM];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
@@ -268,22 +420,23 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     const int sz = (int)cr.count;
     const uint32_t o = cr.offset;
     const uint8_t *im = dec + (size_t)cr.frame * g.Hd * Wp;
-    const bool keys_in_smem = sz <= NCAP;  // bin C clusters larger than its capacity fall back to global memory
+    unsigned long long *keys_g = keys + o;
+    LineFitPt *lfps_g = lfps_pool + o;
 
     // ---- Phase A: bounding box + integer sums for the border-polarity test ----
+    uint32_t pr[PPT];
     BBoxRed r = {1 << 30, -1, 1 << 30, -1, 0, 0, 0};
-    for (int i = tid; i < sz; i += THREADS) {
-      uint32_t p = pts[o + i];
-      int x = p & 0x3fff, y = (p >> 14) & 0x3fff;
-      int cxg = (p >> 28) & 3, cyg = (p >> 30) & 3;
-      int gx = cxg == 0 ? 0 : (cxg == 1 ? 255 : -255), gy = cyg == 0 ? 0 : (cyg == 1 ? 255 : -255);
-      r.xmin = min(r.xmin, x);
-      r.xmax = max(r.xmax, x);
-      r.ymin = min(r.ymin, y);
-      r.ymax = max(r.ymax, y);
-      r.sgx += gx;
-      r.sgy += gy;
-      r.s1 += (long long)x * gx + (long long)y * gy;
+    if (SM) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const int i = tid + k * THREADS;
+        pr[k] = i < sz ? pts[o + i] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; k++)
+        if (tid + k * THREADS < sz) bbox_add(r, pr[k]);
+    } else {
+      for (int i = tid; i < sz; i += THREADS) bbox_add(r, pts[o + i]);
     }
     for (int of = 16; of > 0; of >>= 1) {
       r.xmin = min(r.xmin, __shfl_xor_sync(0xffffffffu, r.xmin, of));
@@ -319,111 +472,117 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     if (!fp.normal_border && !reversed) continue;
 
     // ---- Phase C: sort keys (slope | y | x) ----
-    unsigned long long *ka = keys_in_smem ? skeys : (keys + o);
-    for (int i = tid; i < sz; i += THREADS) {
-      uint32_t p = pts[o + i];
-      int x = p & 0x3fff, y = (p >> 14) & 0x3fff;
-      float dx = (float)x - cx;
-      float dy = (float)y - cy;
-      float quadrant;
-      if (dy > 0)
-        quadrant = (dx > 0) ? 65536.0f : 131072.0f;
-      else
-        quadrant = (dx > 0) ? 0.0f : -65536.0f;
-      if (dy < 0) {
-        dy = -dy;
-        dx = -dx;
+    if (SM) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const int i = tid + k * THREADS;
+        if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
       }
-      if (dx < 0) {
-        float tmp = dx;
-        dx = dy;
-        dy = -tmp;
-      }
-      float slope = quadrant + dy / dx;
-      ka[i] = ((unsigned long long)float_orderable(slope) << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
-    }
-    cta_sync<THREADS>();
-    // scratch for the merge passes: the (not yet used) errB area, or the L2-resident error scratch for oversize clusters
-    unsigned long long *ktmp = keys_in_smem ? reinterpret_cast<unsigned long long *>(s_errB)
-                                            : reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o);
-    sort_keys<THREADS, ITEMS>(ka, ktmp, sz);
-    if (keys_in_smem) {
-      for (int i = tid; i < sz; i += THREADS) keys[o + i] = skeys[i];
+      cta_sync<THREADS>();
+      sort_keys<THREADS, ITEMS>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz);
+    } else {
+      for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
+      cta_sync<THREADS>();
+      // scratch for the merge passes: the (not yet used) error area
+      sort_keys<THREADS, ITEMS>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz);
     }
 
     // ---- Phase E: line-fit terms, then SEQUENTIAL prefix sums (six lanes, one per moment) ----
-    LineFitPt *lfps_g = lfps_pool + o;
-    const int chunk = ALL_SMEM ? NCAP : SCAN_CH;
-    if (!ALL_SMEM && tid < 6) s_carry[tid] = 0.0;
-    for (int c0 = 0; c0 < sz; c0 += chunk) {
-      const int cn = min(chunk, sz - c0);
-      for (int ii = tid; ii < cn; ii += THREADS) {
-        const unsigned long long k = ka[c0 + ii];
-        const int px = (int)(k & 0xffff), py = (int)((k >> 16) & 0xffff);
-        const double x = px * .5 + 0.5;
-        const double y = py * .5 + 0.5;
-        const int ix = (int)x, iy = (int)y;
-        double W = 1;
-        if (ix > 0 && ix + 1 < g.Wd && iy > 0 && iy + 1 < g.Hd) {
-          int grad_x = (int)im[(size_t)iy * Wp + ix + 1] - (int)im[(size_t)iy * Wp + ix - 1];
-          int grad_y = (int)im[(size_t)(iy + 1) * Wp + ix] - (int)im[(size_t)(iy - 1) * Wp + ix];
-          W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+    if (MODE == QF_ALL) {
+      // terms of all points straight into the moment arrays (two points per iteration: eight gathers in flight)
+      for (int i = tid; i < sz; i += 2 * THREADS) {
+        const int i2 = i + THREADS;
+        const bool h2 = i2 < sz;
+        const unsigned long long k0 = skeys[i], k1 = h2 ? skeys[i2] : 0ull;
+        const int ga = grad2_at(im, Wp, g.Wd, g.Hd, k0);
+        const int gb = h2 ? grad2_at(im, Wp, g.Wd, g.Hd, k1) : 0;
+        keys_g[i] = k0;
+        double t[6];
+        lfp_terms(k0, ga, t);
+#pragma unroll
+        for (int m = 0; m < 6; m++) s_M[m * MSTRIDE + i] = t[m];
+        if (h2) {
+          keys_g[i2] = k1;
+          lfp_terms(k1, gb, t);
+#pragma unroll
+          for (int m = 0; m < 6; m++) s_M[m * MSTRIDE + i2] = t[m];
         }
-        const double fx = x, fy = y;
-        s_M[ii] = W * fx;
-        s_M[MSTRIDE + ii] = W * fy;
-        s_M[2 * MSTRIDE + ii] = W * fx * fx;
-        s_M[3 * MSTRIDE + ii] = W * fx * fy;
-        s_M[4 * MSTRIDE + ii] = W * fy * fy;
-        s_M[5 * MSTRIDE + ii] = W;
       }
       cta_sync<THREADS>();
       if (tid < 6) {
         double *base = s_M + tid * MSTRIDE;
-        double acc = ALL_SMEM ? 0.0 : s_carry[tid];
-        int i = 0;
-        for (; i + 8 <= cn; i += 8) {
-          double t0 = base[i], t1 = base[i + 1], t2 = base[i + 2], t3 = base[i + 3], t4 = base[i + 4], t5 = base[i + 5],
-                 t6 = base[i + 6], t7 = base[i + 7];
-          acc += t0;
-          base[i] = acc;
-          acc += t1;
-          base[i + 1] = acc;
-          acc += t2;
-          base[i + 2] = acc;
-          acc += t3;
-          base[i + 3] = acc;
-          acc += t4;
-          base[i + 4] = acc;
-          acc += t5;
-          base[i + 5] = acc;
-          acc += t6;
-          base[i + 6] = acc;
-          acc += t7;
-          base[i + 7] = acc;
-        }
-        for (; i < cn; i++) {
-          acc += base[i];
-          base[i] = acc;
-        }
-        if (!ALL_SMEM) s_carry[tid] = acc;
+        scan_chain(base, sz, 0.0, [&](int i, double v) { base[i] = v; });
       }
       cta_sync<THREADS>();
-      if (!ALL_SMEM) {
-        for (int ii = tid; ii < cn; ii += THREADS) {
-          LineFitPt t;
-          t.Mx = s_M[ii];
-          t.My = s_M[MSTRIDE + ii];
-          t.Mxx = s_M[2 * MSTRIDE + ii];
-          t.Mxy = s_M[3 * MSTRIDE + ii];
-          t.Myy = s_M[4 * MSTRIDE + ii];
-          t.W = s_M[5 * MSTRIDE + ii];
-          lfps_g[c0 + ii] = t;
+    } else if (MODE == QF_KEYS) {
+      // gradient pass: the slope half of a sorted key is dead, it now carries the squared gradient magnitude
+      for (int i = tid; i < sz; i += 4 * THREADS) {
+        unsigned long long k[4];
+        int g2[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = (i + u * THREADS < sz) ? skeys[i + u * THREADS] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, k[u]) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (i + u * THREADS < sz) {
+            keys_g[i + u * THREADS] = k[u];
+            skeys[i + u * THREADS] = (k[u] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[u] << 32);
+          }
+        }
+      }
+      __syncthreads();
+      // software-pipelined scan: warp 0 scans chunk c out of ring half (c & 1) and streams the prefix moments to the
+      // L2-resident scratch; the other warps fill half ((c + 1) & 1) with the terms of chunk c + 1
+      constexpr int HALF = 6 * (CH + 1);
+      auto produce = [&](int c, int t0, int nt) {
+        double *b = s_ring + (c & 1) * HALF;
+        const int c0 = c * CH, cn = min(CH, sz - c0);
+        for (int ii = t0; ii < cn; ii += nt) {
+          const unsigned long long k = skeys[c0 + ii];
+          double t[6];
+          lfp_terms(k, (int)(k >> 32), t);
+#pragma unroll
+          for (int m = 0; m < 6; m++) b[m * (CH + 1) + ii] = t[m];
+        }
+      };
+      const int nchunks = (sz + CH - 1) / CH;
+      produce(0, tid, THREADS);
+      __syncthreads();
+      double acc = 0.0;
+      for (int c = 0; c < nchunks; c++) {
+        if (wid == 0) {
+          if (lane < 6) {
+            const double *b = s_ring + (c & 1) * HALF + lane * (CH + 1);
+            double *gp = reinterpret_cast<double *>(lfps_g + (size_t)c * CH) + lane;
+            acc = scan_chain(b, min(CH, sz - c * CH), acc, [&](int i, double v) { gp[(size_t)i * 6] = v; });
+          }
+        } else if (c + 1 < nchunks) {
+          produce(c + 1, tid - 32, THREADS - 32);
         }
         __syncthreads();
       }
+    } else {
+      for (int i = tid; i < sz; i += THREADS) {
+        const unsigned long long k = keys_g[i];
+        double t[6];
+        lfp_terms(k, grad2_at(im, Wp, g.Wd, g.Hd, k), t);
+        double *gp = reinterpret_cast<double *>(lfps_g + i);
+#pragma unroll
+        for (int m = 0; m < 6; m++) gp[m] = t[m];
+      }
+      __syncthreads();
+      if (tid < 6) {
+        double *gp = reinterpret_cast<double *>(lfps_g) + tid;
+        double acc = 0.0;
+        for (int i = 0; i < sz; i++) {
+          acc += gp[(size_t)i * 6];
+          gp[(size_t)i * 6] = acc;
+        }
+      }
+      __syncthreads();
     }
-    LfAcc<ALL_SMEM> lf;
+    LfAcc<MSM> lf;
     lf.m = s_M;
     lf.stride = MSTRIDE;
     lf.g = lfps_g;
@@ -431,9 +590,9 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     // ---- Phase F/G: per-point line-fit error over a +-ksz window, then 7-tap smoothing (circular) ----
     const int ksz = min(20, sz / 12);
     if (ksz < 2) continue;
-    // errA aliases the (now dead) key area when the keys are in shared memory
-    double *errA = keys_in_smem ? reinterpret_cast<double *>(skeys) : (errs_pool + (size_t)2 * o);
-    double *errB = ALL_SMEM ? s_errB : (errs_pool + (size_t)2 * o + sz);
+    // errA takes over the (now dead) key area, errB the sort scratch / staging ring
+    double *errA = SM ? reinterpret_cast<double *>(skeys) : (errs_pool + (size_t)2 * o);
+    double *errB = SM ? s_ring : (errs_pool + (size_t)2 * o + sz);
     // two independent line fits per iteration: their long double-precision division chains overlap
     for (int i = tid; i < sz; i += 2 * THREADS) {
       const int i2 = i + THREADS;
@@ -465,41 +624,21 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
     // ---- Phase H: local maxima, compacted in index order (errA area is dead again: reuse it) ----
     double *merr = errA;                                                  // values of the maxima
     uint32_t *midx = reinterpret_cast<uint32_t *>(errA + (sz + 1) / 2);    // their indices
-    if (tid == 0) s_run = 0;
-    cta_sync<THREADS>();
-    for (int i0 = 0; i0 < sz; i0 += THREADS) {
-      const int i = i0 + tid;
-      bool is_max = false;
-      double e = 0;
-      if (i < sz) {
-        e = errB[i];
-        is_max = e > errB[i + 1 == sz ? 0 : i + 1] && e > errB[i == 0 ? sz - 1 : i - 1];
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, is_max);
-      int woff = 0, tot = __popc(bal);
-      if (NW > 1) {
-        if (lane == 0) s_scan[wid] = tot;
-        __syncthreads();
-        tot = 0;
-        for (int w = 0; w < NW; w++) {
-          if (w < wid) woff += s_scan[w];
-          tot += s_scan[w];
-        }
-      }
-      const int run = s_run;
-      if (is_max) {
-        int pos = run + woff + __popc(bal & ((1u << lane) - 1));
-        midx[pos] = (uint32_t)i;
-        merr[pos] = e;
-      }
-      cta_sync<THREADS>();
-      if (tid == 0) s_run = run + tot;
-      cta_sync<THREADS>();
-    }
-    const int nmax_all = s_run;
+    const int nmax_all = ordered_compact<NW>(
+        sz, lane, wid, s_scan,
+        [&](int i) {
+          const double e = errB[i];
+          return e > errB[i + 1 == sz ? 0 : i + 1] && e > errB[i == 0 ? sz - 1 : i - 1];
+        },
+        [&](int i, int pos) {
+          midx[pos] = (uint32_t)i;
+          merr[pos] = errB[i];
+        });
     if (nmax_all < 4) continue;
+    cta_sync<THREADS>();
 
     // ---- Phase I: keep the max_nmaxima best maxima: threshold = value of descending rank max_nmaxima ----
+    int nm;
     if (nmax_all > fp.max_nmaxima) {
       if (nmax_all <= 1024) {
         // rank by counting (unique ranks: ties broken by position), O(n^2 / THREADS)
@@ -552,55 +691,28 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
       }
       const double maxima_thresh = s_thresh;
       // ordered compaction of maxima with err > thresh (errB holds the untouched values)
-      if (tid == 0) s_run = 0;
-      cta_sync<THREADS>();
-      for (int i0 = 0; i0 < nmax_all; i0 += THREADS) {
-        const int i = i0 + tid;
-        bool keep = false;
-        uint32_t idx = 0;
-        if (i < nmax_all) {
-          idx = midx[i];
-          keep = !(errB[idx] <= maxima_thresh);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        int woff = 0, tot = __popc(bal);
-        if (NW > 1) {
-          if (lane == 0) s_scan[wid] = tot;
-          __syncthreads();
-          tot = 0;
-          for (int w = 0; w < NW; w++) {
-            if (w < wid) woff += s_scan[w];
-            tot += s_scan[w];
-          }
-        }
-        const int run = s_run;
-        if (keep) {
-          int pos = run + woff + __popc(bal & ((1u << lane) - 1));
-          if (pos < MAXM) s_fm[pos] = (int)idx;
-        }
-        cta_sync<THREADS>();
-        if (tid == 0) s_run = run + tot;
-        cta_sync<THREADS>();
-      }
-      if (tid == 0) s_nm = min(s_run, MAXM);
+      const int kept = ordered_compact<NW>(
+          nmax_all, lane, wid, s_scan, [&](int i) { return !(errB[midx[i]] <= maxima_thresh); },
+          [&](int i, int pos) {
+            if (pos < MAXM) s_fm[pos] = (int)midx[i];
+          });
+      nm = min(kept, MAXM);
     } else {
       if (tid < nmax_all) s_fm[tid] = (int)midx[tid];
-      if (tid == 0) s_nm = nmax_all;
+      nm = nmax_all;
     }
     cta_sync<THREADS>();
-    const int nm = s_nm;
     if (nm < 4) continue;
 
-    // ---- Phase J: line fits between every ordered pair of kept maxima ----
+    // ---- Phase J: line fits between every ordered pair of kept maxima (tables over the dead key / error area) ----
     for (int t = tid; t < nm * nm; t += THREADS) {
       int a = t / nm, b = t - a * nm;
       if (a == b) continue;
-      double lp[4], e, m;
-      fit_line_dev(lf, sz, s_fm[a], s_fm[b], lp, &e, &m);
-      p_err[a][b] = e;
-      p_mse[a][b] = m;
-      p_nx[a][b] = lp[2];
-      p_ny[a][b] = lp[3];
+      double lp[4], m;
+      fit_line_dev(lf, sz, s_fm[a], s_fm[b], lp, nullptr, &m);
+      pt_mse[a * MAXM + b] = m;
+      pt_nx[a * MAXM + b] = lp[2];
+      pt_ny[a * MAXM + b] = lp[3];
     }
     cta_sync<THREADS>();
 
@@ -611,16 +723,26 @@ __global__ void __launch_bounds__(THREADS) k_quadfit(Geo g, FitParams fp, const 
       const double max_mse = (double)fp.max_line_fit_mse, max_dot = (double)fp.cos_critical_rad;
       const uchar4 *ctab = combos.c + combos.off[nm];
       const int ncomb = combos.off[nm + 1] - combos.off[nm];
+      // err of a segment = N * mse (fit_line), N = number of points on the circular index range [i0, i1]
+      auto seg_err = [&](int a, int b, double mse) {
+        const int i0 = s_fm[a], i1 = s_fm[b];
+        const int N = i0 < i1 ? i1 - i0 + 1 : sz - i0 + i1 + 1;
+        return N * mse;
+      };
       for (int t = tid; t < ncomb; t += THREADS) {
         const uchar4 c = ctab[t];
         const int m0 = c.x, m1 = c.y, m2 = c.z, m3 = c.w;
-        if (p_mse[m0][m1] > max_mse) continue;
-        if (p_mse[m1][m2] > max_mse) continue;
-        double dot = p_nx[m0][m1] * p_nx[m1][m2] + p_ny[m0][m1] * p_ny[m1][m2];
+        const double mse01 = pt_mse[m0 * MAXM + m1];
+        if (mse01 > max_mse) continue;
+        const double mse12 = pt_mse[m1 * MAXM + m2];
+        if (mse12 > max_mse) continue;
+        double dot = pt_nx[m0 * MAXM + m1] * pt_nx[m1 * MAXM + m2] + pt_ny[m0 * MAXM + m1] * pt_ny[m1 * MAXM + m2];
         if (fabs(dot) > max_dot) continue;
-        if (p_mse[m2][m3] > max_mse) continue;
-        if (p_mse[m3][m0] > max_mse) continue;
-        double err = p_err[m0][m1] + p_err[m1][m2] + p_err[m2][m3] + p_err[m3][m0];
+        const double mse23 = pt_mse[m2 * MAXM + m3];
+        if (mse23 > max_mse) continue;
+        const double mse30 = pt_mse[m3 * MAXM + m0];
+        if (mse30 > max_mse) continue;
+        double err = seg_err(m0, m1, mse01) + seg_err(m1, m2, mse12) + seg_err(m2, m3, mse23) + seg_err(m3, m0, mse30);
         // the table is in lexicographic order, so t itself is the lexicographic rank
         if (err < best || (err == best && (uint32_t)t < brank)) {
           best = err;
@@ -744,7 +866,8 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
     int bin = -1;
     if (c < ncl) {
       const uint32_t n = clusters[c].count;
-      bin = n <= 128 ? 0 : (n <= 256 ? 1 : (n <= 512 ? 2 : (n <= 1024 ? 3 : (n <= 2048 ? 4 : 5))));
+      // ceil(log2(n)) - 7 clamped to [0, kQuadBins - 1]: <=128, <=256, ..., <=8192, larger
+      bin = n <= 128 ? 0 : min(kQuadBins - 1, 32 - __clz((int)n - 1) - 7);
     }
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
@@ -760,21 +883,26 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
   }
 }
 
-template <int THREADS, int NCAP, bool ALL_SMEM, int ITEMS, int SCAN_CH>
-static void launch_bin(const Workspace &ws, int bin, int ctas_per_sm, int sms, const ComboTable &ct, cudaStream_t st) {
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB>
+static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
   const Geo &g = ws.g;
-  constexpr size_t smem = (size_t)(2 * NCAP + 6 * ((ALL_SMEM ? NCAP : SCAN_CH) + 1)) * 8;  // keys/errA + errB|sort scratch + moments|staging
-  // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute
-  static bool attr_set[64] = {};
+  constexpr size_t smem = QfSmem<NCAP, MODE, CH>::BYTES;
+  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB>;
+  // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute; the persistent grid is sized to
+  // the number of CTAs that are resident at once
+  static int ctas_per_sm[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS, SCAN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set[dev] = true;
+  dev = dev >= 0 && dev < 64 ? dev : 0;
+  if (!ctas_per_sm[dev]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, smem);
+    ctas_per_sm[dev] = std::max(1, n);
   }
-  k_quadfit<THREADS, NCAP, ALL_SMEM, ITEMS, SCAN_CH><<<sms * ctas_per_sm, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys,
-                                                                                  ws.lfps, ws.errs, ws.dec, ws.quads, ws.counters, ct,
-                                                                                  at_Wp(g));
+  const int grid = std::max(1, (int)(sms * ctas_per_sm[dev] * scale + 0.5));
+  kern<<<grid, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec, ws.quads,
+                                    ws.counters, ct, at_Wp(g));
 }
 
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
@@ -789,30 +917,29 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   k_bin_clusters<<<sms * 2, 256, 0, s>>>(g, ws.clusters, ws.bin_idx, ws.counters);
   // the bins are independent: fork onto side streams; large clusters (the long poles) are issued first
   cudaEventRecord(ws.ev_fork, s);
-  for (int i = 0; i < 5; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
-  // tuning knobs (experiments): B200AT_QF_SCALE scales the CTAs per SM of every bin (leave shared memory free for co-running
-  // dense kernels); B200AT_QF_GLOBAL=1 keeps the moments of the <=1024-point bins in the L2-resident scratch instead of
-  // shared memory (smaller CTAs, more of them per SM)
+  for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
+  // tuning knobs (experiments): B200AT_QF_SCALE scales the persistent grid of every bin; B200AT_QF_KEYS23=1 runs the
+  // 512 / 1024-point bins with the prefix moments in the L2-resident scratch (16 B instead of 64 B of shared memory per point)
   static const double qscale = getenv("B200AT_QF_SCALE") ? atof(getenv("B200AT_QF_SCALE")) : 1.0;
-  static const bool qglobal = getenv("B200AT_QF_GLOBAL") != nullptr;
-  auto sc = [&](int c) { return std::max(1, (int)(c * qscale + 0.5)); };
-  launch_bin<256, 4096, false, 16, 512>(ws, 5, sc(2), sms, ct, s);          // n > 2048 (n > 4096: global-memory sort fallback)
-  launch_bin<256, 2048, false, 8, 512>(ws, 4, sc(3), sms, ct, ws.aux[0]);   // n <= 2048
-  if (!qglobal) {
-    launch_bin<128, 1024, true, 8, 512>(ws, 3, sc(3), sms, ct, ws.aux[1]);  // n <= 1024
-    launch_bin<64, 512, true, 8, 512>(ws, 2, sc(6), sms, ct, ws.aux[2]);    // n <= 512
-    launch_bin<32, 256, true, 8, 512>(ws, 1, sc(10), sms, ct, ws.aux[3]);   // n <= 256
+  static const bool keys23 = getenv("B200AT_QF_KEYS23") != nullptr;
+  launch_bin<256, 0, QF_GLOBAL, 16, 1, 2>(ws, 7, qscale, sms, ct, s);               // n > 8192
+  launch_bin<512, 8192, QF_KEYS, 16, 480, 1>(ws, 6, qscale, sms, ct, ws.aux[0]);    // n <= 8192
+  launch_bin<256, 4096, QF_KEYS, 16, 224, 3>(ws, 5, qscale, sms, ct, ws.aux[1]);    // n <= 4096
+  launch_bin<256, 2048, QF_KEYS, 8, 160, 4>(ws, 4, qscale, sms, ct, ws.aux[2]);     // n <= 2048
+  if (!keys23) {
+    launch_bin<128, 1024, QF_ALL, 8, 1, 3>(ws, 3, qscale, sms, ct, ws.aux[3]);      // n <= 1024
+    launch_bin<64, 512, QF_ALL, 8, 1, 6>(ws, 2, qscale, sms, ct, ws.aux[4]);        // n <= 512
   } else {
-    launch_bin<128, 1024, false, 8, 128>(ws, 3, sc(5), sms, ct, ws.aux[1]);
-    launch_bin<64, 512, false, 8, 128>(ws, 2, sc(12), sms, ct, ws.aux[2]);
-    launch_bin<32, 256, false, 8, 64>(ws, 1, sc(18), sms, ct, ws.aux[3]);
+    launch_bin<128, 1024, QF_KEYS, 8, 64, 8>(ws, 3, qscale, sms, ct, ws.aux[3]);
+    launch_bin<64, 512, QF_KEYS, 8, 32, 16>(ws, 2, qscale, sms, ct, ws.aux[4]);
   }
-  launch_bin<32, 128, true, 4, 512>(ws, 0, sc(16), sms, ct, ws.aux[4]);     // n <= 128
-  for (int i = 0; i < 5; i++) {
+  launch_bin<32, 256, QF_ALL, 8, 1, 12>(ws, 1, qscale, sms, ct, ws.aux[5]);          // n <= 256
+  launch_bin<32, 128, QF_ALL, 4, 1, 18>(ws, 0, qscale, sms, ct, ws.aux[6]);          // n <= 128
+  for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);
   }
-  return 7;
+  return 1 + kQuadBins;
 }
 
 }  // namespace b200at

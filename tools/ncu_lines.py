@@ -33,7 +33,7 @@ def main():
         dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
     # locate the function
     lines = dis.splitlines()
-    tmpl = re.findall(r"<(\d+),\s*(\d+),\s*(\d+)>", kern)
+    tmpl = re.findall(r"<(\d+),\s*(\d+),\s*(\d+)", kern)
     pat = base_name
     if tmpl:
         a, b, c = tmpl[0]
