@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#ifndef B200AT_EMU  // (tools/emu compiles this file with g++: no PTX there, the plain staging below is used)
   if (USE_TMA) {
     // TMA staging: one cp.async.bulk.tensor of the (64 x 33) u8 box at (x0-16, y0-1, frame); out-of-bounds elements are
     // zero-filled by the hardware (the link predicates never consult pixels outside the image, see ccl_links).
@@ -139,7 +140,9 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
         "@!p bra WAIT_TMA;\n"
         "}\n" ::"r"(mb)
         : "memory");
-  } else {
+  } else
+#endif
+  {
     // fallback staging: (TH+1) x (TW+2) bytes; out-of-image = 127 (never links)
     for (int i = tid; i < (TH + 1) * (TW + 2); i += 256) {
       int r = i / (TW + 2), c = i % (TW + 2);

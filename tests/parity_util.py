@@ -8,8 +8,53 @@ from isaac_ros_apriltag_b200 import capi
 from oracle import oracle as O
 
 
+# Set by tests/test_emu_parity.py (use_emulator()): the kernels then run under the CPU SIMT emulator of tools/emu (test
+# infrastructure; "device" memory is host memory there), otherwise on the GPU through libb200apriltags.so.
+EMU = False
+
+
+def use_emulator():
+    """Point the ctypes binding at the emulated build of the SAME kernel sources (tools/emu/build_emu.py)."""
+    global EMU
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "emu", "build_emu.py")
+    spec = importlib.util.spec_from_file_location("build_emu", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    saved = (capi.LIB_PATH, capi._lib, EMU)
+    capi.LIB_PATH = mod.build()
+    capi._lib = None
+    EMU = True
+    return saved
+
+
+def restore(saved):
+    global EMU
+    capi.LIB_PATH, capi._lib, EMU = saved
+
+
+def current_stream():
+    if EMU:
+        return 0
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _HostFrames:
+    """numpy stand-in for the torch tensor that keeps the frames alive (emulator runs only)"""
+
+    def __init__(self, a):
+        self.a = a
+
+
 def upload(frames):
     """host (n,H,W[,C]) uint8 -> torch cuda tensor; returns (tensor, ptrs, pitch)"""
+    if EMU:
+        a = np.ascontiguousarray(frames)
+        fb = a[0].size
+        pitch = a.shape[2] * (a.shape[3] if a.ndim == 4 else 1)
+        return _HostFrames(a), [a.ctypes.data + i * fb for i in range(a.shape[0])], pitch
     import torch
     t = torch.from_numpy(np.ascontiguousarray(frames)).cuda()
     n = t.shape[0]
@@ -28,11 +73,10 @@ def to_gray_batch(frames, encoding):
 def compare_stages(frames, encoding="mono8", families=("tag36h11",), report=None, **opts):
     """Runs the batch through the GPU detector and every frame through the oracle; returns a dict of per-stage
     mismatch counts (all zeros = bit-exact) plus float deviations for the tolerance-level stages."""
-    import torch
     n, H, W = frames.shape[:3]
     det = capi.Detector(W, H, families=families, encoding=encoding, max_batch=n, max_tags=256, **opts)
     t, ptrs, pitch = upload(frames)
-    gdets = det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream, strict=False)
+    gdets = det.detect_device(ptrs, pitch, current_stream(), strict=False)
     res = {"status": det.status(), "dec": 0, "tile": 0, "thr": 0, "labels": 0, "sizes": 0, "clusters": 0, "points": 0,
            "quads_n": 0, "quads_bits": 0, "quads_max": 0.0, "refined_n": 0, "refined_bits": 0, "refined_max": 0.0,
            "det_n": 0, "det_id": 0, "det_margin_max": 0.0, "det_corner_max": 0.0, "det_H_max": 0.0, "n_det": 0, "n_quads": 0,

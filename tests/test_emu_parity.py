@@ -1,0 +1,86 @@
+"""Kernel LOGIC check without a GPU: the detector's own .cu sources, compiled for the CPU SIMT emulator of tools/emu (one
+fiber per CUDA thread; barriers, warp collectives, atomics and shared-memory aliasing behave as on the device), run through
+the same C ABI and compared stage by stage with the oracle.
+
+This is test infrastructure, like the oracle: the emulated library is built under tools/emu/_build, is loaded only here
+(and by `B200AT_TEST_EMU=1 pytest -m gpu`, the developer switch), is never timed and never shipped -- the package itself
+only ever loads libb200apriltags.so and fails without a GPU.  The parity tests proper remain tests/test_gpu_parity.py
+(-m gpu, on the B200); what this file adds is that a kernel change which breaks a stage is caught in the CPU suite already.
+What the emulator cannot show: memory-model races between CTAs, TMA staging (the plain-load staging path is used), timing."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import assert_exact
+
+
+@pytest.fixture(scope="module")
+def pu():
+    import parity_util
+    saved = parity_util.use_emulator()
+    yield parity_util
+    parity_util.restore(saved)
+
+
+def small_frame(seed, w, h, tags, side=(40, 90)):
+    from isaac_ros_apriltag_b200 import synth
+    rng = np.random.default_rng(seed)
+    g, _ = synth.make_frame(rng, w, h, tags, side_px=side)
+    return g
+
+
+def test_emulated_chain_matches_oracle_mono8(pu):
+    frames = np.stack([small_frame(7, 322, 242, [("tag36h11", 3), ("tag36h11", 17)], side=(50, 90)),
+                       small_frame(8, 322, 242, [("tag36h11", 100)], side=(60, 120))])
+    rep = []
+    res, gd = pu.compare_stages(frames, "mono8", ("tag36h11",), report=rep)
+    assert_exact(res, rep)
+    assert sorted(int(i) for i in gd[0]["id"]) == [3, 17] and list(gd[1]["id"]) == [100]
+    assert res["n_clusters"] > 20 and res["n_quads"] >= 3
+
+
+@pytest.mark.parametrize("encoding", ["bgr8", "rgba8"])
+def test_emulated_chain_colour(pu, encoding):
+    g = small_frame(21, 400, 300, [("tag36h11", 5), ("tag25h9", 9)], side=(60, 110))
+    rng = np.random.default_rng(3)
+    ch = 3 if encoding == "bgr8" else 4
+    col = rng.integers(0, 40, g.shape + (ch,), dtype=np.int16) + g[:, :, None].astype(np.int16) - 20
+    frames = np.clip(col, 0, 255).astype(np.uint8)[None]
+    rep = []
+    res, gd = pu.compare_stages(frames, encoding, ("tag36h11", "tag25h9"), report=rep)
+    assert_exact(res, rep)
+    assert len(gd[0]) == 2
+
+
+@pytest.mark.parametrize("opts", [dict(quad_decimate=1.0), dict(quad_decimate=1.5), dict(quad_decimate=3.0), dict(quad_sigma=0.8),
+                                  dict(tile_size=8), dict(refine_edges=0)])
+def test_emulated_knobs(pu, opts):
+    g = small_frame(5, 333, 251, [("tag36h11", 1), ("tag36h11", 2)], side=(60, 100))  # odd size: partial tiles, padded pitch
+    rep = []
+    res, _ = pu.compare_stages(np.stack([g, g[::-1].copy()]), "mono8", ("tag36h11",), report=rep, **opts)
+    assert_exact(res, rep)
+
+
+def test_emulated_large_cluster_bins(pu):
+    """One big tag: its outer border cluster has thousands of points, which exercises the multi-warp quad-fit bins (keys in
+    shared memory, pipelined prefix scan) that small frames never reach."""
+    from isaac_ros_apriltag_b200 import synth
+    rng = np.random.default_rng(11)
+    g, _ = synth.make_frame(rng, 1600, 1200, [("tag36h11", 42)], side_px=(680, 720), max_tilt_deg=10.0, noise_sigma=0.0)
+    rep = []
+    res, gd = pu.compare_stages(g[None], "mono8", ("tag36h11",), report=rep)
+    assert_exact(res, rep)
+    assert list(gd[0]["id"]) == [42]
+    assert res["n_points"] > 4096
+
+
+def test_emulated_host_entry_point_matches_device_entry_point(pu):
+    from isaac_ros_apriltag_b200 import capi
+    frames = np.stack([small_frame(30 + i, 322, 242, [("tag36h11", 10 + i)], side=(60, 110)) for i in range(5)])
+    bgr = np.ascontiguousarray(np.repeat(frames[:, :, :, None], 3, axis=3))
+    det = capi.Detector(322, 242, encoding="bgr8", max_batch=2, max_tags=16)
+    t, ptrs, pitch = pu.upload(bgr)
+    want = [det.detect_device(ptrs[i:i + 1], pitch, 0)[0] for i in range(5)]
+    got = det.detect_host(bgr)   # 5 frames through a 2-frame workspace: sub-batches + staging slots
+    for a, b in zip(got, want):
+        assert a.tobytes() == b.tobytes() and len(a) == 1
+    det.close()

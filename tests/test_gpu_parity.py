@@ -20,11 +20,23 @@ TOL_POSE_R = 1e-5
 
 @pytest.fixture(scope="module")
 def pu():
+    """B200AT_TEST_EMU=1 (developer switch, no GPU needed) runs this same suite against the kernels compiled for the CPU
+    SIMT emulator of tools/emu instead of the GPU: a logic check before spending GPU time, never a substitute for -m gpu."""
+    import parity_util
+    if os.environ.get("B200AT_TEST_EMU") == "1":
+        saved = parity_util.use_emulator()
+        yield parity_util
+        parity_util.restore(saved)
+        return
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    import parity_util
-    return parity_util
+    yield parity_util
+
+
+def needs_real_gpu(pu):
+    if pu.EMU:
+        pytest.skip("needs a real GPU (torch device tensors / CUDA graphs)")
 
 
 def assert_exact(res, rep):
@@ -111,7 +123,7 @@ def test_pose_against_oracle_and_truth(pu):
     det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=ts, families=fams, encoding="mono8",
                         max_batch=2, max_tags=64)
     t, ptrs, pitch = pu.upload(frames)
-    gd = det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream)
+    gd = det.detect_device(ptrs, pitch, pu.current_stream())
     orc = O.Oracle(fams)
     fx, fy, cx, cy = np.float32(K[0, 0]), np.float32(K[1, 1]), np.float32(K[0, 2]), np.float32(K[1, 2])
     for i in range(2):
@@ -129,6 +141,7 @@ def test_pose_against_oracle_and_truth(pu):
 def test_pol_golden_through_cuapriltags_abi(pu):
     """The reference's POL golden test (isaac_ros_apriltag_pol_test.py:117-175) through the drop-in entry points
     nvCreateAprilTagsDetector / cuAprilTagsDetect and through the node core, with the reference's own tolerances."""
+    needs_real_gpu(pu)
     import ctypes as C
     import torch
     from isaac_ros_apriltag_b200 import capi, node, synth
@@ -180,7 +193,7 @@ def test_full_batch_properties(pu):
     det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=ts, families=fams, encoding="mono8",
                         max_batch=B, max_tags=64)
     t, ptrs, pitch = pu.upload(batch)
-    gd = det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream)
+    gd = det.detect_device(ptrs, pitch, pu.current_stream())
     assert det.status() == 0
     for i in range(B):
         assert gd[i].tobytes() == gd[i % distinct].tobytes(), i
@@ -208,7 +221,7 @@ def test_overflow_is_reported_not_ub(pu):
     det = capi.Detector(W, H, encoding="mono8", max_batch=1, hash_slots_per_frame=1024, points_per_frame=4096, clusters_per_frame=64)
     t, ptrs, pitch = pu.upload(frames)
     with pytest.raises(capi.B200ATError) as e:
-        det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream)
+        det.detect_device(ptrs, pitch, pu.current_stream())
     assert e.value.code == 5 and det.status() != 0
     det.close()
 
@@ -217,6 +230,7 @@ def test_cuda_graph_replay_matches_plain_launches(pu):
     """EnqueueBatch caches a CUDA graph of the whole batch when the caller passes a real stream: call 1 runs plain,
     call 2 captures + launches, later calls replay.  Results must be identical, and a replay must pick up NEW frame
     pointers (the frame table is a pinned buffer read at execution time)."""
+    needs_real_gpu(pu)
     import torch
     from isaac_ros_apriltag_b200 import capi, synth
     frames, truths, K, ts, fams = synth.make_config_frames("C1", 4)
@@ -253,7 +267,7 @@ def test_bench_workload_frames_match_oracle(pu):
     det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=ts, families=fams, encoding="bgr8",
                         max_batch=32, max_tags=64)
     t, ptrs, pitch = pu.upload(bgr)
-    gd = det.detect_device(ptrs, pitch, torch.cuda.current_stream().cuda_stream)
+    gd = det.detect_device(ptrs, pitch, pu.current_stream())
     assert det.status() == 0
     od, _ = O.detect_batch(bgr, fams, nthreads=min(16, os.cpu_count() or 1), encoding="bgr8")
     ndet = 0
@@ -273,6 +287,7 @@ def test_bench_workload_frames_match_oracle(pu):
 def test_two_devices_one_process(pu):
     """One process, one handle per GPU (b200AprilTagsOptions_t::device): the per-device kernel attributes, workspaces and
     streams are independent, the caller's current device is left untouched, results are identical on both GPUs."""
+    needs_real_gpu(pu)
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
