@@ -192,7 +192,7 @@ enum {
 int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable);
 int b200AprilTagsGetStageTimes(cuAprilTagsHandle h, float *ms /* [B200AT_NUM_STAGES] */);
 /* launches issued by the last Enqueue (for the bench's gpu_launches claim) and counters of the last batch */
-int b200AprilTagsGetCounters(cuAprilTagsHandle h, uint64_t *counters /* [8]: launches, points, clusters, quads, candidates, detections, 0, 0 */);
+int b200AprilTagsGetCounters(cuAprilTagsHandle h, uint64_t *counters /* [8]: launches, points, clusters, quads, candidates, detections, host->device bytes of the last DetectBatchHost, 1 if it staged rows sparsely */);
 
 /* Intermediate buffers of the last batch, copied to HOST memory (parity tests). */
 enum {

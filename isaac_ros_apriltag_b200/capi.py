@@ -227,7 +227,8 @@ class Detector:
     def counters(self):
         c = (C.c_uint64 * 8)()
         lib().b200AprilTagsGetCounters(self.h, c)
-        return {"launches": c[0], "points": c[1], "clusters": c[2], "quads": c[3], "detections": c[5]}
+        return {"launches": c[0], "points": c[1], "clusters": c[2], "quads": c[3], "detections": c[5], "h2d_bytes": c[6],
+                "sparse_h2d": c[7]}
 
     def dims(self):
         v = [C.c_uint32() for _ in range(4)]

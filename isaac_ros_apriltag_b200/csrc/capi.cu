@@ -37,6 +37,9 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
     }                                                                                                         \
   } while (0)
 
+// Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
+constexpr bool kSparseHostPathDefault = false;
+
 uint32_t next_pow2(uint32_t v) {
   uint32_t p = 1;
   while (p < v) p <<= 1;
@@ -65,10 +68,12 @@ struct cuAprilTagsHandle_st {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   FrameDesc *hp_frames = nullptr;
+  FrameDesc *hp_src = nullptr;         // sparse host path: device-mapped addresses of the caller's frames
+  bool sparse_bufs = false;            // need1 / need2 / src_frames / quad_H allocated
   b200AprilTagsDetection_t *hp_out = nullptr;
   uint32_t *hp_out_count = nullptr;
   uint32_t *hp_counters = nullptr;
-  size_t hp_cap_frames = 0, hp_cap_subs = 0;
+  size_t hp_cap_frames = 0, hp_cap_subs = 0, hp_src_cap = 0;
   // state of the batch in flight
   cudaStream_t cur_stream = nullptr;
   uint32_t cur_n = 0;
@@ -131,6 +136,7 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->h_out_count) cudaFreeHost(h->h_out_count);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->hp_frames) cudaFreeHost(h->hp_frames);
+  if (h->hp_src) cudaFreeHost(h->hp_src);
   if (h->hp_out) cudaFreeHost(h->hp_out);
   if (h->hp_out_count) cudaFreeHost(h->hp_out_count);
   if (h->hp_counters) cudaFreeHost(h->hp_counters);
@@ -554,6 +560,12 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
   v.out += (size_t)f0 * g.max_tags;
   v.out_count += f0;
   v.counters += (size_t)c * CNT_N;
+  if (v.need1) {
+    v.need1 += (size_t)f0 * g.H;
+    v.need2 += (size_t)f0 * g.H;
+    v.src_frames += f0;
+    v.quad_H += (size_t)c * qc * 10;
+  }
   v.g.tma_frame0 = f0;
   if (c & 1) {  // lane 1 has its own side streams / events
     for (int i = 0; i < kQuadAux; i++) {
@@ -583,9 +595,21 @@ static void sum_counters(const uint32_t *c, uint32_t *out) {
 // quad fit of the previous chunk, which leaves most issue slots of an SM idle.
 static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream, FrameDesc *hf,
                         b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, bool timing, int *launches_out,
-                        bool table_filled = false) {
+                        bool table_filled = false, const FrameDesc *sparse_src = nullptr) {
   Workspace &ws = h->ws;
   Geo &g = ws.g;
+  // sparse host path: `frames` are staged copies that hold only every f-th row; `sparse_src` (pinned) lists the
+  // device-mapped host frames the missing rows are fetched from where a quad needs them (k_decode.cu)
+  struct SparseScope {
+    Geo &g;
+    ~SparseScope() { g.row_step = 0; }
+  } sparse_scope{g};
+  g.row_step = 0;
+  if (sparse_src) {
+    g.row_step = g.f;
+    g.seg_shift = 5;
+    while (((g.W + (1 << g.seg_shift) - 1) >> g.seg_shift) > 64) g.seg_shift++;
+  }
   if (!table_filled) {
     int fast = 1;
     int rcf = fill_frame_table(h, frames, n, hf, &fast);
@@ -595,6 +619,11 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
   int launches = 0;
   cudaError_t e = cudaMemcpyAsync(ws.frames, hf, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(ws.counters, 0, sizeof(uint32_t) * CNT_N * kMaxChunks, stream);
+  if (sparse_src) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws.src_frames, sparse_src, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.need1, 0, sizeof(unsigned long long) * (size_t)n * g.H, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.need2, 0, sizeof(unsigned long long) * (size_t)n * g.H, stream);
+  }
   const bool tm = timing;
   const int nch = (tm || !h->pipeline || n < 32) ? 1 : (n >= 128 ? 4 : 2);
   if (nch == 1) {
@@ -788,6 +817,50 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
+  // Sparse staging (see k_decode.cu): with an integer quad_decimate f >= 2 the detector reads only every f-th row until the
+  // quads are known, so only those rows are DMA'd; the full-resolution rows around the quads are fetched afterwards straight
+  // from the caller's frames.  That needs pinned, device-mapped, 16-byte aligned host frames; anything else takes the full
+  // copy.  B200AT_SPARSE_H2D=0/1 overrides the default.
+  bool sparse = kSparseHostPathDefault;
+  if (const char *es = getenv("B200AT_SPARSE_H2D")) sparse = atoi(es) != 0;
+  if (g.f < 2 || (h->stage_pitch & 15)) sparse = false;
+  if (sparse) {
+    if (h->hp_src_cap < n) {
+      if (h->hp_src) cudaFreeHost(h->hp_src);
+      h->hp_src = nullptr;
+      h->hp_src_cap = 0;
+      if (cudaMallocHost(&h->hp_src, sizeof(FrameDesc) * n) != cudaSuccess) return fail(B200AT_ERR_NOMEM);
+      h->hp_src_cap = n;
+    }
+    for (uint32_t i = 0; i < n && sparse; i++) {
+      cudaPointerAttributes pa;
+      if (!frames[i].ptr || cudaPointerGetAttributes(&pa, frames[i].ptr) != cudaSuccess) {
+        cudaGetLastError();
+        sparse = false;
+        break;
+      }
+      if (pa.type != cudaMemoryTypeHost || !pa.devicePointer || ((uintptr_t)pa.devicePointer & 15) || (frames[i].pitch & 15)) {
+        sparse = false;
+        break;
+      }
+      h->hp_src[i].ptr = (const uint8_t *)pa.devicePointer;
+      h->hp_src[i].pitch = frames[i].pitch;
+    }
+  }
+  if (sparse && !h->sparse_bufs) {
+    Workspace &w = h->ws;
+    const size_t B = h->max_batch;
+    int rca = dev_alloc(h, &w.need1, B * g.H);
+    if (rca == 0) rca = dev_alloc(h, &w.need2, B * g.H);
+    if (rca == 0) rca = dev_alloc(h, &w.src_frames, B);
+    if (rca == 0) rca = dev_alloc(h, &w.quad_H, (size_t)g.quad_cap * 10);
+    if (rca != 0) return fail(rca);
+    h->sparse_bufs = true;
+  }
+  const int row_step = sparse ? g.f : 1;
+  const int rows_dma = 1 + (g.H - 1) / row_step;
+  static const bool sparse_debug = getenv("B200AT_SPARSE_DEBUG") != nullptr;  // poison the slot: an unfetched row cannot go unnoticed
+  uint64_t dma_bytes = 0;
   // uniform sub-batches (a ramped schedule -- small first/last sub-batches to shorten pipeline fill and drain -- was
   // measured and did not pay: the tiny sub-batches cost more in launch overhead than they save)
   std::vector<uint32_t> sub_start, sub_len;
@@ -820,10 +893,14 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     uint8_t *slot_base = h->d_stage + (size_t)slot * S * h->stage_pitch * g.H;
     cudaError_t e = cudaSuccess;
     if (k >= 2) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
+    if (sparse && sparse_debug && e == cudaSuccess) e = cudaMemsetAsync(slot_base, 0xA5, (size_t)m * h->stage_pitch * g.H, h->copy_stream);
     for (uint32_t j = 0; j < m && e == cudaSuccess; j++) {
       if (!frames[i0 + j].ptr || frames[i0 + j].pitch < row) return fail(B200AT_ERR_INVALID_ARG);
       uint8_t *dst = slot_base + (size_t)j * h->stage_pitch * g.H;
-      e = cudaMemcpy2DAsync(dst, h->stage_pitch, frames[i0 + j].ptr, frames[i0 + j].pitch, row, g.H, cudaMemcpyHostToDevice, h->copy_stream);
+      // rows 0, f, 2f, ... (all rows on the full-copy path)
+      e = cudaMemcpy2DAsync(dst, h->stage_pitch * row_step, frames[i0 + j].ptr, frames[i0 + j].pitch * row_step, row, rows_dma,
+                            cudaMemcpyHostToDevice, h->copy_stream);
+      dma_bytes += (uint64_t)row * rows_dma;
       dframes[j].ptr = dst;
       dframes[j].pitch = h->stage_pitch;
     }
@@ -832,7 +909,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
     int l = 0;
     rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
-                      h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l);
+                      h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l, false, sparse ? h->hp_src + i0 : nullptr);
     launches += l;
     if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], h->own_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
@@ -845,11 +922,12 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     return B200AT_ERR_CUDA;
   }
   uint32_t status = 0;
-  uint64_t pts = 0, clu = 0, qd = 0, dt = 0;
+  uint64_t pts = 0, clu = 0, qd = 0, dt = 0, fetched = 0;
   for (uint32_t k = 0; k < nsub; k++) {
     uint32_t c[CNT_N];
     sum_counters(h->hp_counters + (size_t)k * CNT_N * kMaxChunks, c);
     status |= c[CNT_STATUS];
+    fetched += c[CNT_FETCHED];
     pts += c[CNT_POINTS];
     clu += c[CNT_CLUSTERS];
     qd += c[CNT_QUADS];
@@ -869,6 +947,8 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   h->last_counters[2] = clu;
   h->last_counters[3] = qd;
   h->last_counters[5] = dt;
+  h->last_counters[6] = dma_bytes + fetched * 16;  // host->device bytes of this call: DMA + rows fetched on demand
+  h->last_counters[7] = sparse ? 1 : 0;
   return status ? B200AT_ERR_OVERFLOW : B200AT_OK;
 }
 

@@ -62,7 +62,8 @@ struct Cand {  // decoded candidate before reconcile
 };
 
 // counters[] slots
-enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5, CNT_WORK_DECODE = 7,
+enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5,
+       CNT_FETCHED = 6 /* 16-byte chunks fetched on demand from the caller's host frames (sparse host path) */, CNT_WORK_DECODE = 7,
        CNT_BIN0 = 8 /* ..15: clusters per size bin */, CNT_WORK0 = 16 /* ..23: quad-fit work queues */, CNT_N = 24 };
 constexpr int kQuadBins = 8;
 constexpr int kQuadAux = kQuadBins - 1;  // side streams: the quad-fit bins run concurrently
@@ -87,6 +88,10 @@ struct Geo {
   uint32_t max_tags;   // outputs per frame
   uint32_t max_cluster_pts;  // 2*(2*Wd+2*Hd)
   int tma_frame0;      // frame offset of this workspace view inside the whole-batch TMA tensor
+  // sparse host path (capi.cu, b200AprilTagsDetectBatchHost): only every row_step-th source row is staged by DMA; the other
+  // rows are fetched on demand, in segments of (1 << seg_shift) pixels, where a quad needs them (k_decode.cu)
+  int row_step;        // 0 = every row of the frame is present
+  int seg_shift;       // log2 of the segment width in pixels (<= 64 segments per row)
 };
 
 struct FitParams {
@@ -126,6 +131,11 @@ struct Workspace {
   uint32_t *out_count;   // [B]
   uint32_t *counters;    // [CNT_N]
   uint32_t *bin_idx;     // [kQuadBins][clu_cap] cluster indices per size bin
+  // sparse host path: per-row segment bitmaps (bit s of word [frame][y] = pixels [s << seg_shift, (s+1) << seg_shift) of row y),
+  // the host-mapped source frames the segments are fetched from, and the per-quad homographies handed from k_refine to k_decode_bits
+  unsigned long long *need1, *need2;  // [B][H] rows needed by refine_edges / by the decode samples
+  FrameDesc *src_frames;       // [B] device-accessible addresses of the caller's (pinned) host frames
+  double *quad_H;              // [quad_cap][10]: H[0..8], valid flag
   const unsigned char *combos;  // per nm (4..kMaxNMaxima): all m0<m1<m2<m3 < nm in lexicographic order, uchar4 each
   int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
   CUtensorMap thr_tmap;  // TMA descriptor of thr as a (Wp, Hd, B) u8 tensor, box 64 x 33 x 1 (CCL tile + halo)

@@ -84,3 +84,33 @@ def test_emulated_host_entry_point_matches_device_entry_point(pu):
     for a, b in zip(got, want):
         assert a.tobytes() == b.tobytes() and len(a) == 1
     det.close()
+
+
+@pytest.mark.parametrize("enc,dec", [("bgr8", 2.0), ("mono8", 2.0), ("rgba8", 3.0)])
+def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
+    """Sparse staging of the host entry point (only every f-th row by DMA, the rows around the quads fetched on demand): same
+    bytes out as the device-pointer path.  B200AT_SPARSE_DEBUG poisons the staging slot, and the emulator poisons fresh
+    device memory, so a full-resolution pixel that is read without having been fetched changes the result."""
+    from isaac_ros_apriltag_b200 import capi
+    monkeypatch.setenv("B200AT_SPARSE_DEBUG", "1")
+    frames = np.stack([small_frame(40 + i, 416, 320, [("tag36h11", 20 + i), ("tag36h11", 50 + i)], side=(50, 120)) for i in range(3)])
+    ch = {"bgr8": 3, "mono8": 1, "rgba8": 4}[enc]
+    if ch > 1:
+        frames = np.ascontiguousarray(np.repeat(frames[:, :, :, None], ch, axis=3))
+    det = capi.Detector(416, 320, encoding=enc, max_batch=2, max_tags=16, quad_decimate=dec)
+    t, ptrs, pitch = pu.upload(frames)
+    want = [det.detect_device(ptrs[i:i + 1], pitch, 0)[0] for i in range(3)]
+    monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
+    got = det.detect_host(frames)
+    c = det.counters()
+    assert c["sparse_h2d"] == 1 and c["h2d_bytes"] < 0.8 * frames.nbytes
+    for a, b in zip(got, want):
+        assert a.tobytes() == b.tobytes() and len(a) >= 1
+    # pageable (not device-mapped) frames fall back to the full copy
+    monkeypatch.setenv("B200AT_EMU_HOSTMEM", "pageable")
+    got2 = det.detect_host(frames)
+    c2 = det.counters()
+    assert c2["sparse_h2d"] == 0 and c2["h2d_bytes"] == frames.nbytes
+    for a, b in zip(got2, want):
+        assert a.tobytes() == b.tobytes()
+    det.close()

@@ -311,3 +311,45 @@ def test_two_devices_one_process(pu):
         assert a.tobytes() == b.tobytes() and len(a) == 10
     for d in dets:
         d.close()
+
+
+@pytest.mark.parametrize("config,enc", [("C2", "bgr8"), ("C4", "mono8")])
+def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
+    """b200AprilTagsDetectBatchHost with pinned frames: staging only every f-th row by DMA and fetching the rows around the quads
+    on demand (B200AT_SPARSE_H2D=1) gives byte-identical results to the full copy and to the device-pointer entry point, and
+    moves fewer bytes over PCIe.  B200AT_SPARSE_DEBUG poisons the staging slots."""
+    from isaac_ros_apriltag_b200 import capi, synth
+    monkeypatch.setenv("B200AT_SPARSE_DEBUG", "1")
+    n = 6
+    frames, truths, K, ts, fams = synth.make_config_frames(config, n)
+    if enc == "bgr8":
+        frames = np.ascontiguousarray(np.repeat(frames[:, :, :, None], 3, axis=3))
+    H, W = frames.shape[1:3]
+    det = capi.Detector(W, H, families=fams, encoding=enc, max_batch=4, max_tags=128)
+    t, ptrs, pitch = pu.upload(frames)
+    want = det.detect_device(ptrs[:4], pitch, pu.current_stream()) + det.detect_device(ptrs[4:], pitch, pu.current_stream())
+    if pu.EMU:
+        host = frames
+    else:
+        import torch
+        host = torch.from_numpy(frames).pin_memory().numpy()
+    monkeypatch.setenv("B200AT_SPARSE_H2D", "0")
+    full = det.detect_host(host)
+    cf = det.counters()
+    monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
+    got = det.detect_host(host)
+    cs = det.counters()
+    assert cf["sparse_h2d"] == 0 and cf["h2d_bytes"] == frames.nbytes
+    # C2 (10 tags / frame) needs a fraction of the odd rows; C4 (a 13 x 7 grid of tags) needs nearly all of them
+    assert cs["sparse_h2d"] == 1 and cs["h2d_bytes"] < (0.85 if config == "C2" else 1.05) * frames.nbytes
+    for i in range(n):
+        assert full[i].tobytes() == want[i].tobytes(), i
+        assert got[i].tobytes() == want[i].tobytes(), i
+    assert sum(len(x) for x in got) >= n
+    # frames in pageable memory: the call falls back to the full copy by itself
+    if not pu.EMU:
+        got2 = det.detect_host(frames.copy())
+        assert det.counters()["sparse_h2d"] == 0
+        for i in range(n):
+            assert got2[i].tobytes() == want[i].tobytes(), i
+    det.close()
