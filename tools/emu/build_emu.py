@@ -94,7 +94,7 @@ def build(force=False, opt="-O1", verbose=False):
             sys.stderr.write(out)
     if bad:
         raise RuntimeError("emulator build failed")
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + [rt_obj, "-Wl,--no-undefined", "-lm"])
+    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + [rt_obj, "-Wl,--no-undefined", "-Wl,-Bsymbolic", "-lm"])
     return LIB
 
 
