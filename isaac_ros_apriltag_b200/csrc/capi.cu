@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "detector.h"
@@ -39,6 +40,47 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
 
 // Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
 constexpr bool kSparseHostPathDefault = false;
+constexpr int kTuneDefaultThrEarly = 0;
+constexpr int kTuneDefaultCclSweep = 0;
+constexpr int kTuneDefaultClusterEager = 0;
+
+// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0": performance knobs of one handle (detector.h,
+// struct Tune).  Unknown keys are reported and ignored.
+Tune parse_tune() {
+  Tune t;
+  t.thr_early = kTuneDefaultThrEarly;
+  t.ccl_sweep = kTuneDefaultCclSweep;
+  t.cluster_eager = kTuneDefaultClusterEager;
+  t.decode_split = 0;
+  t.decode_ctas = 4;
+  t.qf_scale = 1.0f;
+  t.qf_keys23 = 0;
+  const char *e = getenv("B200AT_TUNE");
+  if (!e) return t;
+  std::string str(e);
+  size_t pos = 0;
+  while (pos < str.size()) {
+    size_t end = str.find(',', pos);
+    if (end == std::string::npos) end = str.size();
+    const std::string kv = str.substr(pos, end - pos);
+    pos = end + 1;
+    const size_t eq = kv.find('=');
+    if (eq == std::string::npos) continue;
+    const std::string k = kv.substr(0, eq);
+    const double v = atof(kv.c_str() + eq + 1);
+    if (k == "thr_early") t.thr_early = (int)v;
+    else if (k == "ccl_sweep") t.ccl_sweep = (int)v;
+    else if (k == "cluster_eager") t.cluster_eager = (int)v;
+    else if (k == "decode_split") t.decode_split = (int)v;
+    else if (k == "decode_ctas") t.decode_ctas = (int)v;
+    else if (k == "qf_scale") t.qf_scale = (float)v;
+    else if (k == "qf_keys23") t.qf_keys23 = (int)v;
+    else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
+  }
+  if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;
+  if (!(t.qf_scale > 0.05f && t.qf_scale < 16.0f)) t.qf_scale = 1.0f;
+  return t;
+}
 
 uint32_t next_pow2(uint32_t v) {
   uint32_t p = 1;
@@ -400,6 +442,8 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.out_count, B);
   ALLOC(ws.counters, (size_t)kMaxChunks * CNT_N);
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
+  ws.tune = parse_tune();
+  if (ws.tune.decode_split) ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
   {
     // combination tables: for every nm, all m0<m1<m2<m3<nm in lexicographic order (the serial loops' visiting order)
     std::vector<unsigned char> tab;
@@ -564,8 +608,8 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
     v.need1 += (size_t)f0 * g.H;
     v.need2 += (size_t)f0 * g.H;
     v.src_frames += f0;
-    v.quad_H += (size_t)c * qc * 10;
   }
+  if (v.quad_H) v.quad_H += (size_t)c * qc * 10;
   v.g.tma_frame0 = f0;
   if (c & 1) {  // lane 1 has its own side streams / events
     for (int i = 0; i < kQuadAux; i++) {
@@ -853,7 +897,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     int rca = dev_alloc(h, &w.need1, B * g.H);
     if (rca == 0) rca = dev_alloc(h, &w.need2, B * g.H);
     if (rca == 0) rca = dev_alloc(h, &w.src_frames, B);
-    if (rca == 0) rca = dev_alloc(h, &w.quad_H, (size_t)g.quad_cap * 10);
+    if (rca == 0 && !w.quad_H) rca = dev_alloc(h, &w.quad_H, (size_t)g.quad_cap * 10);
     if (rca != 0) return fail(rca);
     h->sparse_bufs = true;
   }

@@ -110,9 +110,22 @@ struct FitParams {
   float tagsize;
 };
 
+// Performance knobs, read once per handle from the environment (B200AT_TUNE="key=value,key=value"; see capi.cu).  They never
+// change results, only how the work is mapped; tools/gpu_tune.py sweeps them on the GPU.
+struct Tune {
+  int thr_early;      // k_threshold4: pixel loads issued before the tile min/max staging barrier
+  int ccl_sweep;      // k_ccl_tile_sweep (warp per tile, label inheritance) instead of k_ccl_tile; 2 = without TMA staging
+  int cluster_eager;  // k_cluster_pass: unconditional label loads + speculative offset load (fewer dependent round trips)
+  int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
+  int decode_ctas;    // persistent decode CTAs per SM
+  float qf_scale;     // scales the persistent grid of every quad-fit bin
+  int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
+};
+
 struct Workspace {
   Geo g;
   FitParams fp;
+  Tune tune;
   DevFamily fams[kMaxFamilies];
   FrameDesc *frames;
   uint8_t *dec, *dec_tmp, *tmin, *tmax, *thr, *thr2;

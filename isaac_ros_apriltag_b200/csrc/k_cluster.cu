@@ -43,7 +43,9 @@ __device__ __forceinline__ uint32_t hash_key2(unsigned long long k) {
 // One thread per pixel evaluates the four probes; the (on average < 1 per pixel) resulting points are COMPACTED per
 // warp through shared memory so the expensive part (match / table probe / atomic) runs on dense lanes: one round per
 // 32 points instead of four rounds per 32 pixels.
-template <bool EMIT>
+// EAGER: the label loads do not wait for the probe results and the segment offset is loaded together with the table key, so a
+// warp's critical path has three dependent memory round trips (pixels + labels, table slot, atomic) instead of five.
+template <bool EMIT, bool EAGER>
 __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
                                                       unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
                                                       const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
@@ -64,16 +66,30 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
   Probes pr = {{false, false, false, false}};
   uint32_t rep0 = 0;
   int v0 = 127;
-  if (in) {
-    pr = eval_probes(img, Wp, x, y);
-    v0 = img[(size_t)y * Wp + x];
-    if (pr.p[0] || pr.p[1] || pr.p[2] || pr.p[3]) rep0 = labf[(size_t)y * Wp + x];
-  }
   const int dxs[4] = {1, 0, -1, 1};
   const int dys[4] = {0, 1, 1, 1};
   uint32_t rep1[4];
+  if (EAGER) {
+    if (in) {
+      // (x, y) is interior: all five label addresses are inside the frame
+      rep0 = labf[(size_t)y * Wp + x];
 #pragma unroll
-  for (int k = 0; k < 4; k++) rep1[k] = pr.p[k] ? labf[(size_t)(y + dys[k]) * Wp + x + dxs[k]] : 0u;
+      for (int k = 0; k < 4; k++) rep1[k] = labf[(size_t)(y + dys[k]) * Wp + x + dxs[k]];
+      pr = eval_probes(img, Wp, x, y);
+      v0 = img[(size_t)y * Wp + x];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) rep1[k] = 0u;
+    }
+  } else {
+    if (in) {
+      pr = eval_probes(img, Wp, x, y);
+      v0 = img[(size_t)y * Wp + x];
+      if (pr.p[0] || pr.p[1] || pr.p[2] || pr.p[3]) rep0 = labf[(size_t)y * Wp + x];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) rep1[k] = pr.p[k] ? labf[(size_t)(y + dys[k]) * Wp + x + dxs[k]] : 0u;
+  }
   // compaction: probe-major order inside the warp
   int total = 0;
 #pragma unroll
@@ -133,8 +149,10 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
       if ((int)lane == leader) {
         for (uint32_t probe = 0; probe < g.hcap; probe++) {
           unsigned long long cur = hk[slot];
+          uint32_t off = 0;
+          if (EAGER) off = hoff[ho + slot];  // issued together with the key load
           if (cur == key) {
-            uint32_t off = hoff[ho + slot];
+            if (!EAGER) off = hoff[ho + slot];
             if (off != 0xffffffffu) base = off + atomicAdd(&hcur[ho + slot], (uint32_t)n);
             break;
           }
@@ -271,10 +289,16 @@ int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.hkey, 0, (size_t)nframes * g.hcap * sizeof(unsigned long long), s);
   cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
   dim3 gp((g.Wd - 2 + 255) / 256, g.Hd - 2, nframes);
-  k_cluster_pass<false><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+  if (ws.tune.cluster_eager)
+    k_cluster_pass<false, true><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+  else
+    k_cluster_pass<false, false><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
   const int segs = g.hcap >= 65536 ? 4 : 1;  // hcap is a power of two
   k_cluster_select<<<nframes * segs, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters, segs);
-  k_cluster_pass<true><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+  if (ws.tune.cluster_eager)
+    k_cluster_pass<true, true><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+  else
+    k_cluster_pass<true, false><<<gp, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
   return 5;
 }
 

@@ -730,17 +730,23 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ctas = sms * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
   if (g.row_step == 0) {
-    k_decode<<<sms * 4, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.cands, ws.cand_count, ws.counters);
+    if (ws.tune.decode_split && ws.quad_H) {
+      k_refine<false><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+      k_decode_bits<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+      return 3;
+    }
+    k_decode<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.cands, ws.cand_count, ws.counters);
     return 2;
   }
   // sparse host path: the caller (capi.cu) zeroed need1 / need2 when it staged the frames
   const dim3 gf((g.W * g.bpp + 16 * 128 - 1) / (16 * 128), g.H, nframes);
   k_mark_quads<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.quads, ws.counters, ws.need1);
   k_fetch_rows<<<gf, 128, 0, s>>>(g, ws.src_frames, ws.frames, ws.need1, nullptr, ws.counters);
-  k_refine<true><<<sms * 4, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
+  k_refine<true><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
   k_fetch_rows<<<gf, 128, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
-  k_decode_bits<<<sms * 4, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+  k_decode_bits<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
   return 6;
 }
 

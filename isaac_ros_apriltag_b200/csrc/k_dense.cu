@@ -229,7 +229,10 @@ __global__ void k_unsharp(Geo g, const uint8_t *__restrict__ orig, uint8_t *__re
 // threshold (tile size 4): one thread per 4 horizontally adjacent tiles = 16 px x 4 rows; uint4 loads/stores.
 // Algorithmic bytes per frame: Pd read + Pd written (the metric's "threshold HBM GB/s": 2*Pd).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_threshold4(Geo g, const uint8_t *__restrict__ dec, const uint8_t *__restrict__ tmin,
+// EARLY: the pixel loads are issued before the tile min/max staging and its barrier (they do not depend on it), so the two
+// memory latencies of a CTA overlap instead of adding up.
+template <int EARLY>  // 0 = off, 1 = on, 2 = on with the register budget of 6 CTAs per SM
+__global__ void __launch_bounds__(256, EARLY == 2 ? 6 : 0) k_threshold4(Geo g, const uint8_t *__restrict__ dec, const uint8_t *__restrict__ tmin,
                                                     const uint8_t *__restrict__ tmax, uint8_t *__restrict__ thr, int Wp,
                                                     int twp) {
   // CTA = 32 x 8 threads = 128 tile columns x 8 tile rows.  The tile min/max of the region (+1 tile halo, neutral
@@ -244,6 +247,13 @@ __global__ void __launch_bounds__(256) k_threshold4(Geo g, const uint8_t *__rest
   const uint8_t *mxb = tmax + (size_t)fr * g.th * twp;
   const int tx0 = blockIdx.x * blockDim.x * 4, ty0 = blockIdx.y * blockDim.y;
   const int tid = threadIdx.y * 32 + threadIdx.x;
+  const size_t base = (size_t)fr * g.Hd * Wp + (size_t)(ty * 4) * Wp + tq * 16;
+  uint4 v[4];
+  if (EARLY && tq * 16 < Wp && ty < nty) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (ty * 4 + r < g.Hd) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
+  }
   // staging: 10 rows x 34 words per array; a word = 4 consecutive tiles.  Whole-word loads when the tile pitch is a
   // multiple of 4 and the word lies inside the tile grid, byte-wise with neutral fill otherwise.
   const bool words_ok = (twp & 3) == 0;
@@ -317,11 +327,11 @@ __global__ void __launch_bounds__(256) k_threshold4(Geo g, const uint8_t *__rest
       th4[k] = (mn + (mx - mn) / 2) * 0x01010101u;
     }
   }
-  const size_t base = (size_t)fr * g.Hd * Wp + (size_t)(ty * 4) * Wp + tq * 16;
-  uint4 v[4];
+  if (!EARLY) {
 #pragma unroll
-  for (int r = 0; r < 4; r++)
-    if (ty * 4 + r < g.Hd) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
+    for (int r = 0; r < 4; r++)
+      if (ty * 4 + r < g.Hd) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
+  }
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     if (ty * 4 + r >= g.Hd) break;
@@ -432,7 +442,12 @@ int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s) {
   if (g.ts == 4) {
     dim3 blk(32, 8);
     dim3 grd((Wp / 16 + 31) / 32, ((g.Hd + 3) / 4 + 7) / 8, nframes);
-    k_threshold4<<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
+    if (ws.tune.thr_early == 2)
+      k_threshold4<2><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
+    else if (ws.tune.thr_early)
+      k_threshold4<1><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
+    else
+      k_threshold4<0><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
   } else {
     dim3 blk(256), grd((g.Wd + 255) / 256, g.Hd, nframes);
     k_threshold_generic<<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);

@@ -918,10 +918,10 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   // the bins are independent: fork onto side streams; large clusters (the long poles) are issued first
   cudaEventRecord(ws.ev_fork, s);
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
-  // tuning knobs (experiments): B200AT_QF_SCALE scales the persistent grid of every bin; B200AT_QF_KEYS23=1 runs the
-  // 512 / 1024-point bins with the prefix moments in the L2-resident scratch (16 B instead of 64 B of shared memory per point)
-  static const double qscale = getenv("B200AT_QF_SCALE") ? atof(getenv("B200AT_QF_SCALE")) : 1.0;
-  static const bool keys23 = getenv("B200AT_QF_KEYS23") != nullptr;
+  // tuning knobs (Tune, detector.h): qf_scale scales the persistent grid of every bin; qf_keys23 runs the 512 / 1024-point
+  // bins with the prefix moments in the L2-resident scratch (16 B instead of 64 B of shared memory per point)
+  const double qscale = ws.tune.qf_scale;
+  const bool keys23 = ws.tune.qf_keys23 != 0;
   launch_bin<256, 0, QF_GLOBAL, 16, 1, 2>(ws, 7, qscale, sms, ct, s);               // n > 8192
   launch_bin<512, 8192, QF_KEYS, 16, 480, 1>(ws, 6, qscale, sms, ct, ws.aux[0]);    // n <= 8192
   launch_bin<256, 4096, QF_KEYS, 16, 224, 3>(ws, 5, qscale, sms, ct, ws.aux[1]);    // n <= 4096
