@@ -42,9 +42,10 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
 constexpr bool kSparseHostPathDefault = false;
 constexpr int kTuneDefaultThrEarly = 0;
 constexpr int kTuneDefaultCclSweep = 0;
+constexpr int kTuneDefaultQfMc = 0;
 constexpr int kTuneDefaultClusterEager = 0;
 
-// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0": performance knobs of one handle (detector.h,
+// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0,qf_mc=0": performance knobs of one handle (detector.h,
 // struct Tune).  Unknown keys are reported and ignored.
 Tune parse_tune() {
   Tune t;
@@ -55,6 +56,7 @@ Tune parse_tune() {
   t.decode_ctas = 4;
   t.qf_scale = 1.0f;
   t.qf_keys23 = 0;
+  t.qf_mc = kTuneDefaultQfMc;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -75,6 +77,7 @@ Tune parse_tune() {
     else if (k == "decode_ctas") t.decode_ctas = (int)v;
     else if (k == "qf_scale") t.qf_scale = (float)v;
     else if (k == "qf_keys23") t.qf_keys23 = (int)v;
+    else if (k == "qf_mc") t.qf_mc = (int)v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;

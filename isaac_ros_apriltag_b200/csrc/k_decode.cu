@@ -649,8 +649,8 @@ __global__ void __launch_bounds__(128) k_fetch_rows(Geo g, const FrameDesc *__re
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&counters[CNT_FETCHED], (uint32_t)__popc(bal));
 }
 
-template <bool MARK>
-__global__ void __launch_bounds__(DT, 4) k_refine(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
+template <bool MARK, int MINB>
+__global__ void __launch_bounds__(DT, MINB) k_refine(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
                                                const QuadRec *__restrict__ quads, QuadRec *__restrict__ quads_refined,
                                                double *__restrict__ quad_H, const uint32_t *__restrict__ counters,
                                                unsigned long long *__restrict__ need2) {
@@ -700,7 +700,8 @@ __global__ void __launch_bounds__(DT, 4) k_refine(Geo g, FitParams fp, DecodeFam
   }
 }
 
-__global__ void __launch_bounds__(DT, 4) k_decode_bits(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
+template <int MINB>
+__global__ void __launch_bounds__(DT, MINB) k_decode_bits(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
                                                     const QuadRec *__restrict__ quads, const double *__restrict__ quad_H,
                                                     Cand *__restrict__ cands, uint32_t *__restrict__ cand_count,
                                                     uint32_t *__restrict__ counters) {
@@ -732,9 +733,14 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = sms * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
   if (g.row_step == 0) {
+    if (ws.tune.decode_split == 2 && ws.quad_H) {  // register budget of 6 CTAs (24 warps) per SM
+      k_refine<false, 6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+      k_decode_bits<6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+      return 3;
+    }
     if (ws.tune.decode_split && ws.quad_H) {
-      k_refine<false><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
-      k_decode_bits<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+      k_refine<false, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+      k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
       return 3;
     }
     k_decode<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.cands, ws.cand_count, ws.counters);
@@ -744,9 +750,9 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
   const dim3 gf((g.W * g.bpp + 16 * 128 - 1) / (16 * 128), g.H, nframes);
   k_mark_quads<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.quads, ws.counters, ws.need1);
   k_fetch_rows<<<gf, 128, 0, s>>>(g, ws.src_frames, ws.frames, ws.need1, nullptr, ws.counters);
-  k_refine<true><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
+  k_refine<true, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
   k_fetch_rows<<<gf, 128, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
-  k_decode_bits<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+  k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
   return 6;
 }
 

@@ -160,9 +160,8 @@ __device__ __forceinline__ void cta_sync() {
 // is known at every call site.
 // The sorted sequence ends in `a`.
 template <int THREADS, int ITEMS>
-__device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n) {
+__device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n, int tid) {
   constexpr unsigned long long INF = ~0ull;
-  const int tid = threadIdx.x;
   for (int base = tid * ITEMS; base < n; base += THREADS * ITEMS) {
     unsigned long long r[ITEMS];
 #pragma unroll
@@ -379,8 +378,12 @@ struct QfSmem {
   static_assert(MODE != QF_KEYS || 2 * 6 * (CH + 1) <= NCAP, "staging ring must fit the sort scratch");
 };
 
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
+// CPB > 1 (one-warp clusters only): CPB clusters per CTA, one per warp, each with its own shared-memory slice, and the warps
+// of a CTA walk through the phases TOGETHER (block barriers at the phase boundaries, rejected clusters idle instead of
+// leaving).  The kernel is ~80 KB of straight-line code per cluster; warps that sit in the same phase share the instruction
+// lines they fetch, warps in unrelated phases (18 independent one-warp CTAs per SM) thrash the 32 KB instruction cache.
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB>
+__global__ void __launch_bounds__(THREADS * CPB, MINB) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
                                                      const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
                                                      unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
                                                      double *__restrict__ errs_pool, const uint8_t *__restrict__ dec,
@@ -393,31 +396,55 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
   using L = QfSmem<NCAP, MODE, CH>;
   constexpr int MSTRIDE = NCAP + 1;
   static_assert(MODE != QF_KEYS || NW >= 2, "the pipelined scan needs producer warps");
-  extern __shared__ unsigned long long dsm[];
+  static_assert(CPB == 1 || THREADS == 32, "several clusters per CTA: one-warp clusters only (warp-level barriers inside a cluster)");
+  extern __shared__ unsigned long long dsm_all[];
+  const int grp = CPB > 1 ? (int)(threadIdx.x / THREADS) : 0;   // cluster slot of this thread inside the CTA
+  unsigned long long *dsm = dsm_all + (size_t)grp * L::WORDS;
   unsigned long long *skeys = dsm;                              // [NCAP]  keys (later: errA, maxima)
   double *s_ring = reinterpret_cast<double *>(dsm + NCAP);      // [NCAP]  sort scratch, staging ring (QF_KEYS), errB
   double *s_M = reinterpret_cast<double *>(dsm + L::R0);        // [6][MSTRIDE] (QF_ALL)
   double *pt_mse = reinterpret_cast<double *>(dsm), *pt_nx = pt_mse + L::TBL, *pt_ny = pt_nx + L::TBL;
-  __shared__ BBoxRed s_red[NW];
-  __shared__ int s_cluster;
-  __shared__ int s_fm[MAXM];
-  __shared__ int s_scan[NW];
-  __shared__ double s_rv[NW];
-  __shared__ int s_ri[NW];
-  __shared__ unsigned int s_rr[NW];
-  __shared__ double s_thresh;
+  __shared__ BBoxRed s_red_a[CPB][NW];
+  __shared__ int s_cluster_a[CPB];
+  __shared__ int s_fm_a[CPB][MAXM];
+  __shared__ int s_scan_a[CPB][NW];
+  __shared__ double s_rv_a[CPB][NW];
+  __shared__ int s_ri_a[CPB][NW];
+  __shared__ unsigned int s_rr_a[CPB][NW];
+  __shared__ double s_thresh_a[CPB];
+  BBoxRed *s_red = s_red_a[grp];
+  int &s_cluster = s_cluster_a[grp];
+  int *s_fm = s_fm_a[grp], *s_scan = s_scan_a[grp], *s_ri = s_ri_a[grp];
+  double *s_rv = s_rv_a[grp];
+  unsigned int *s_rr = s_rr_a[grp];
+  double &s_thresh = s_thresh_a[grp];
 
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = CPB > 1 ? (int)(threadIdx.x % THREADS) : (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
+  // CPB == 1: a rejected cluster leaves the iteration (continue).  CPB > 1: it stays, idle, so that every warp of the CTA
+  // reaches the phase barriers.
+#define QF_DROP()           \
+  {                         \
+    if (CPB == 1) continue; \
+    alive = false;          \
+    sz = 0; /* every later per-point loop is empty, the per-cluster tails see no maxima / no combination */ \
+  }
+#define QF_PHASE() \
+  if (CPB > 1) __syncthreads()
 
   for (;;) {
     cta_sync<THREADS>();
     if (tid == 0) s_cluster = (int)atomicAdd(&counters[CNT_WORK0 + bin], 1u);
     cta_sync<THREADS>();
     const int cw = s_cluster;
-    if ((uint32_t)cw >= nbin) break;
-    const ClusterRec cr = clusters[bin_idx[(size_t)bin * g.clu_cap + cw]];
-    const int sz = (int)cr.count;
+    bool alive = (uint32_t)cw < nbin;
+    if (CPB > 1) {
+      if (!__syncthreads_or(alive ? 1 : 0)) break;  // every cluster slot of the CTA ran out of work
+    } else if (!alive) {
+      break;
+    }
+    const ClusterRec cr = alive ? clusters[bin_idx[(size_t)bin * g.clu_cap + cw]] : ClusterRec{0ull, 0u, 0u, 0u, 0u};
+    int sz = (int)cr.count;
     const uint32_t o = cr.offset;
     const uint8_t *im = dec + (size_t)cr.frame * g.Hd * Wp;
     unsigned long long *keys_g = keys + o;
@@ -462,15 +489,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
         r.s1 += q.s1;
       }
     }
-    if ((r.xmax - r.xmin) * (r.ymax - r.ymin) < fp.tag_width) continue;
+    if (alive && (r.xmax - r.xmin) * (r.ymax - r.ymin) < fp.tag_width) QF_DROP();
     const float cx = (float)((r.xmin + r.xmax) * 0.5 + 0.05118);
     const float cy = (float)((r.ymin + r.ymax) * 0.5 + -0.028581);
     // dot = sum (x-cx)*gx + (y-cy)*gy, evaluated exactly on the integer parts (order independent)
     const double dotd = (double)r.s1 - (double)cx * (double)r.sgx - (double)cy * (double)r.sgy;
     const bool reversed = dotd < 0;
-    if (!fp.reversed_border && reversed) continue;
-    if (!fp.normal_border && !reversed) continue;
+    if (alive && !fp.reversed_border && reversed) QF_DROP();
+    if (alive && !fp.normal_border && !reversed) QF_DROP();
 
+    QF_PHASE();
     // ---- Phase C: sort keys (slope | y | x) ----
     if (SM) {
 #pragma unroll
@@ -479,14 +507,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
         if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
       }
       cta_sync<THREADS>();
-      sort_keys<THREADS, ITEMS>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz);
+      sort_keys<THREADS, ITEMS>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz, tid);
     } else {
       for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
       cta_sync<THREADS>();
       // scratch for the merge passes: the (not yet used) error area
-      sort_keys<THREADS, ITEMS>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz);
+      sort_keys<THREADS, ITEMS>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
     }
 
+    QF_PHASE();
     // ---- Phase E: line-fit terms, then SEQUENTIAL prefix sums (six lanes, one per moment) ----
     if (MODE == QF_ALL) {
       // terms of all points straight into the moment arrays (two points per iteration: eight gathers in flight)
@@ -587,9 +616,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
     lf.stride = MSTRIDE;
     lf.g = lfps_g;
 
+    QF_PHASE();
     // ---- Phase F/G: per-point line-fit error over a +-ksz window, then 7-tap smoothing (circular) ----
     const int ksz = min(20, sz / 12);
-    if (ksz < 2) continue;
+    if (ksz < 2) QF_DROP();
     // errA takes over the (now dead) key area, errB the sort scratch / staging ring
     double *errA = SM ? reinterpret_cast<double *>(skeys) : (errs_pool + (size_t)2 * o);
     double *errB = SM ? s_ring : (errs_pool + (size_t)2 * o + sz);
@@ -621,6 +651,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
     }
     cta_sync<THREADS>();
 
+    QF_PHASE();
     // ---- Phase H: local maxima, compacted in index order (errA area is dead again: reuse it) ----
     double *merr = errA;                                                  // values of the maxima
     uint32_t *midx = reinterpret_cast<uint32_t *>(errA + (sz + 1) / 2);    // their indices
@@ -634,7 +665,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
           midx[pos] = (uint32_t)i;
           merr[pos] = errB[i];
         });
-    if (nmax_all < 4) continue;
+    if (nmax_all < 4) QF_DROP();
     cta_sync<THREADS>();
 
     // ---- Phase I: keep the max_nmaxima best maxima: threshold = value of descending rank max_nmaxima ----
@@ -702,8 +733,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
       nm = nmax_all;
     }
     cta_sync<THREADS>();
-    if (nm < 4) continue;
+    if (nm < 4) QF_DROP();
 
+    QF_PHASE();
     // ---- Phase J: line fits between every ordered pair of kept maxima (tables over the dead key / error area) ----
     for (int t = tid; t < nm * nm; t += THREADS) {
       int a = t / nm, b = t - a * nm;
@@ -766,6 +798,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_quadfit(Geo g, FitParams fp, 
       __syncthreads();
     }
 
+    QF_PHASE();
     // ---- Phase L: final lines, corners, area / angle gates: lanes 0..3 of warp 0, one line / corner / angle each ----
     if (wid == 0) {
       for (int w = 1; w < NW; w++) {
@@ -883,11 +916,14 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
   }
 }
 
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB>
+#undef QF_DROP
+#undef QF_PHASE
+
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB = 1>
 static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
   const Geo &g = ws.g;
-  constexpr size_t smem = QfSmem<NCAP, MODE, CH>::BYTES;
-  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB>;
+  constexpr size_t smem = QfSmem<NCAP, MODE, CH>::BYTES * CPB;
+  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB>;
   // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute; the persistent grid is sized to
   // the number of CTAs that are resident at once
   static int ctas_per_sm[64] = {};
@@ -897,11 +933,11 @@ static void launch_bin(const Workspace &ws, int bin, double scale, int sms, cons
   if (!ctas_per_sm[dev]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS * CPB, smem);
     ctas_per_sm[dev] = std::max(1, n);
   }
   const int grid = std::max(1, (int)(sms * ctas_per_sm[dev] * scale + 0.5));
-  kern<<<grid, THREADS, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec, ws.quads,
+  kern<<<grid, THREADS * CPB, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec, ws.quads,
                                     ws.counters, ct, at_Wp(g));
 }
 
@@ -933,8 +969,14 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
     launch_bin<128, 1024, QF_KEYS, 8, 64, 8>(ws, 3, qscale, sms, ct, ws.aux[3]);
     launch_bin<64, 512, QF_KEYS, 8, 32, 16>(ws, 2, qscale, sms, ct, ws.aux[4]);
   }
-  launch_bin<32, 256, QF_ALL, 8, 1, 12>(ws, 1, qscale, sms, ct, ws.aux[5]);          // n <= 256
-  launch_bin<32, 128, QF_ALL, 4, 1, 18>(ws, 0, qscale, sms, ct, ws.aux[6]);          // n <= 128
+  if (ws.tune.qf_mc) {
+    // one-warp clusters, several per CTA in phase lockstep (MINB = CTAs per SM the register budget is sized for)
+    launch_bin<32, 256, QF_ALL, 8, 1, 2, 6>(ws, 1, qscale, sms, ct, ws.aux[5]);      // n <= 256: 6 clusters per CTA
+    launch_bin<32, 128, QF_ALL, 4, 1, 2, 8>(ws, 0, qscale, sms, ct, ws.aux[6]);      // n <= 128: 8 clusters per CTA
+  } else {
+    launch_bin<32, 256, QF_ALL, 8, 1, 12>(ws, 1, qscale, sms, ct, ws.aux[5]);        // n <= 256
+    launch_bin<32, 128, QF_ALL, 4, 1, 18>(ws, 0, qscale, sms, ct, ws.aux[6]);        // n <= 128
+  }
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);

@@ -63,6 +63,7 @@ int cur_lane();
 void *dyn_smem();
 
 void block_barrier();
+void block_barrier_reduce(int pred, int *o_or, int *o_and, int *o_cnt);
 enum Kind { K_SYNCWARP = 1, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_BALLOT, K_MATCH, K_VOTE, K_REDUX };
 // all live lanes of `mask` deposit (val, aux); returns the group's snapshot (release it with done())
 Snapshot *exchange(unsigned mask, int kind, unsigned long long val, int aux, unsigned *live_mask);
@@ -111,6 +112,21 @@ inline T from_bits(unsigned long long b) {
 
 // ---- barriers / warp collectives ----
 inline void __syncthreads() { emu::block_barrier(); }
+inline int __syncthreads_or(int pred) {
+  int o, a, c;
+  emu::block_barrier_reduce(pred, &o, &a, &c);
+  return o;
+}
+inline int __syncthreads_and(int pred) {
+  int o, a, c;
+  emu::block_barrier_reduce(pred, &o, &a, &c);
+  return a;
+}
+inline int __syncthreads_count(int pred) {
+  int o, a, c;
+  emu::block_barrier_reduce(pred, &o, &a, &c);
+  return c;
+}
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
   unsigned live;
   emu::done(emu::exchange(mask, emu::K_SYNCWARP, 0, 0, &live));

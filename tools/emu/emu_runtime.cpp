@@ -28,6 +28,7 @@ struct Fiber {
   uint3 tid;
   int lane, warp;
   unsigned bar_gen;
+  unsigned red_seq;
   // pending warp collective
   unsigned c_mask;
   int c_kind;
@@ -111,6 +112,26 @@ void block_barrier() {
   f->state = S_WAIT_BAR;
   while (g_bar_gen == f->bar_gen) yield();
   f->state = S_READY;
+}
+
+// __syncthreads_or / _and / _count: three accumulator slots in rotation.  Call k accumulates into slot k % 3 and clears slot
+// (k + 1) % 3: nobody can be accumulating into that one yet (that needs barrier k to complete), and nobody can still be
+// reading it (it was last read after barrier k - 2, and every thread has since arrived at barrier k - 1).
+static int g_red_or[3], g_red_and[3], g_red_cnt[3];
+void block_barrier_reduce(int pred, int *o_or, int *o_and, int *o_cnt) {
+  Fiber *f = g_cur;
+  const int slot = (int)(f->red_seq % 3u), next = (int)((f->red_seq + 1u) % 3u);
+  f->red_seq++;
+  g_red_or[next] = 0;
+  g_red_and[next] = 1;
+  g_red_cnt[next] = 0;
+  g_red_or[slot] |= pred ? 1 : 0;
+  g_red_and[slot] &= pred ? 1 : 0;
+  g_red_cnt[slot] += pred ? 1 : 0;
+  block_barrier();
+  *o_or = g_red_or[slot];
+  *o_and = g_red_and[slot];
+  *o_cnt = g_red_cnt[slot];
 }
 
 static unsigned live_lanes_of_warp(int warp) {
@@ -224,6 +245,7 @@ static void init_fiber(Fiber &f, int t, dim3 block) {
   f.warp = t >> 5;
   f.c_snap = nullptr;
   f.c_mask = 0;
+  f.red_seq = 0;
   uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
   void **sp = (void **)top;
   *--sp = nullptr;                 // fake return address of fiber_main
@@ -258,6 +280,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*fn)(void *), void *arg)
         g_live = nthreads;
         g_bar_count = 0;
         g_bar_gen = 0;
+        g_red_or[0] = g_red_cnt[0] = 0;
+        g_red_and[0] = 1;
         while (g_live > 0) {
           bool progress = false;
           for (int t = 0; t < nthreads; t++) {

@@ -1,0 +1,122 @@
+#!/usr/bin/env python3
+"""One-process sweep of the per-handle performance knobs (B200AT_TUNE, csrc/detector.h struct Tune) and of the host-path
+staging modes on the bench workload (C2: 256 x 1080p bgr8).  For every configuration: results compared byte for byte with the
+default configuration's (the knobs must never change results), whole-batch time from CUDA events, per-stage times.
+Prints one JSON line per configuration; run on the GPU box:  python tools/gpu_tune.py > gpurun_out/tune.jsonl"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from isaac_ros_apriltag_b200 import capi, synth  # noqa: E402
+
+ALL_ON = "thr_early=1,ccl_sweep=1,cluster_eager=2,decode_split=1,qf_mc=1"
+DEVICE_CONFIGS = ["", "thr_early=1", "thr_early=2", "ccl_sweep=1", "ccl_sweep=2", "cluster_eager=1", "cluster_eager=2", "decode_split=1",
+                  "decode_split=2", "qf_mc=1", "qf_scale=0.75", "qf_scale=1.5", "qf_keys23=1",
+                  "ccl_sweep=1,cluster_eager=2", "thr_early=1,ccl_sweep=1,cluster_eager=2,decode_split=2", "thr_early=1,ccl_sweep=1,cluster_eager=2,qf_mc=1",
+                  ALL_ON, ""]
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def same(a, b):
+    return len(a) == len(b) and all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--distinct", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    t_start = time.time()
+    frames, truths, K, tagsize, fams = synth.make_config_frames("C2", args.distinct)
+    frames = np.ascontiguousarray(np.repeat(frames[:, :, :, None], 3, axis=3))
+    H, W = frames.shape[1:3]
+    B = args.batch
+    reps = (B + args.distinct - 1) // args.distinct
+    dev = torch.from_numpy(frames).cuda().repeat((reps, 1, 1, 1))[:B].contiguous()
+    fb = dev[0].numel()
+    ptrs = [dev.data_ptr() + i * fb for i in range(B)]
+    pitch = W * 3
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    emit(event="setup", seconds=time.time() - t_start, gpu=torch.cuda.get_device_name(0))
+
+    def make(tune):
+        if tune:
+            os.environ["B200AT_TUNE"] = tune
+        else:
+            os.environ.pop("B200AT_TUNE", None)
+        return capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=tagsize, families=fams, encoding="bgr8",
+                             max_batch=B, max_tags=64)
+
+    base = None
+    configs = DEVICE_CONFIGS[:4] + [ALL_ON] if args.quick else DEVICE_CONFIGS
+    for tune in configs:
+        try:
+            det = make(tune)
+            for _ in range(2):
+                dets = det.detect_device(ptrs, pitch, sh)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(args.steps):
+                det.detect_device(ptrs, pitch, sh)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / args.steps
+            det.enable_timing(True)
+            acc = {}
+            for _ in range(2):
+                det.detect_device(ptrs, pitch, sh)
+                for k, v in det.stage_times().items():
+                    acc[k] = acc.get(k, 0.0) + v / 2
+            det.enable_timing(False)
+            if base is None:
+                base = dets
+            emit(event="device", tune=tune or "default", ms_per_step=ms, fps=B / ms * 1e3, parity=same(dets, base), status=det.status(),
+                 detections=int(sum(len(d) for d in dets)), stages_ms={k: round(v, 4) for k, v in acc.items()})
+            det.close()
+        except Exception as e:  # keep sweeping: one bad configuration must not cost the others
+            emit(event="device", tune=tune or "default", error=repr(e))
+    # ---- host path: staging mode x sub-batch size x knobs ----
+    host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
+    for tune in ("", ALL_ON):
+        for mode in ("0", "1"):
+            for sub in ("8", "16", "32"):
+                if args.quick and sub != "16":
+                    continue
+                try:
+                    os.environ["B200AT_SPARSE_H2D"] = mode
+                    os.environ["B200AT_HOST_SUB"] = sub
+                    det = make(tune)
+                    det.detect_host(host)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        r = det.detect_host(host)
+                    torch.cuda.synchronize()
+                    dt = (time.perf_counter() - t0) / 3
+                    c = det.counters()
+                    emit(event="host", tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), ms_per_step=dt * 1e3, fps=B / dt,
+                         h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
+                    det.close()
+                except Exception as e:
+                    emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), error=repr(e))
+    os.environ.pop("B200AT_SPARSE_H2D", None)
+    os.environ.pop("B200AT_HOST_SUB", None)
+    emit(event="done", seconds=time.time() - t_start)
+
+
+if __name__ == "__main__":
+    main()
