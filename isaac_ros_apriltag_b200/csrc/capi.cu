@@ -40,6 +40,7 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
 
 // Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
 constexpr bool kSparseHostPathDefault = false;
+constexpr int kHostStreamsDefault = 1;
 constexpr int kTuneDefaultThrEarly = 0;
 constexpr int kTuneDefaultCclSweep = 0;
 constexpr int kTuneDefaultQfMc = 0;
@@ -729,6 +730,52 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
   return B200AT_OK;
 }
 
+// One sub-batch of the host path on a VIEW of the workspace (frames [f0, f0 + n), pool slice c of 2), so that two sub-batches
+// can be in flight on two streams: the latency-bound tails of one (large-cluster quad fits, decode, pose: a few busy SMs)
+// overlap the dense stages of the next.  Everything the launch chain writes is inside the view.
+static int enqueue_view(cuAprilTagsHandle h, Workspace v, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream,
+                        FrameDesc *hf, b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, int *launches_out,
+                        const FrameDesc *sparse_src) {
+  Geo &g = v.g;
+  int fast = 1;
+  int rcf = fill_frame_table(h, frames, n, hf, &fast);
+  if (rcf != B200AT_OK) return rcf;
+  g.fast_align = fast;
+  g.row_step = 0;
+  if (sparse_src) {
+    g.row_step = g.f;
+    g.seg_shift = 5;
+    while (((g.W + (1 << g.seg_shift) - 1) >> g.seg_shift) > 64) g.seg_shift++;
+  }
+  cudaError_t e = cudaMemcpyAsync(v.frames, hf, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(v.counters, 0, sizeof(uint32_t) * CNT_N, stream);
+  if (sparse_src) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v.src_frames, sparse_src, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(v.need1, 0, sizeof(unsigned long long) * (size_t)n * g.H, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(v.need2, 0, sizeof(unsigned long long) * (size_t)n * g.H, stream);
+  }
+  int launches = 0;
+  launches += launch_preprocess(v, (int)n, stream);
+  launches += launch_threshold(v, (int)n, stream);
+  launches += launch_ccl(v, (int)n, stream);
+  launches += launch_cluster(v, (int)n, stream);
+  launches += launch_quadfit(v, (int)n, stream);
+  launches += launch_decode(v, (int)n, stream);
+  launches += launch_finalize(v, (int)n, stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out, v.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, v.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
+  memset(ctr, 0, sizeof(uint32_t) * CNT_N * kMaxChunks);  // (host) only the first CNT_N entries are produced by this view
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, v.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[b200apriltags] enqueue failed: %s\n", cudaGetErrorString(e));
+    return B200AT_ERR_CUDA;
+  }
+  if (launches_out) *launches_out = launches;
+  return B200AT_OK;
+}
+
 int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream) {
   if (!h || !frames || n == 0 || n > h->max_batch) return B200AT_ERR_INVALID_ARG;
   if (h->in_flight) return B200AT_ERR_INVALID_ARG;
@@ -904,6 +951,10 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (rca != 0) return fail(rca);
     h->sparse_bufs = true;
   }
+  // two sub-batches in flight on two streams (B200AT_HOST_STREAMS=1/2 overrides the default); needs two disjoint frame ranges
+  int nstreams = kHostStreamsDefault;
+  if (const char *es = getenv("B200AT_HOST_STREAMS")) nstreams = atoi(es);
+  if (nstreams != 2 || 2 * S > h->max_batch) nstreams = 1;
   const int row_step = sparse ? g.f : 1;
   const int rows_dma = 1 + (g.H - 1) / row_step;
   static const bool sparse_debug = getenv("B200AT_SPARSE_DEBUG") != nullptr;  // poison the slot: an unfetched row cannot go unnoticed
@@ -951,16 +1002,25 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       dframes[j].ptr = dst;
       dframes[j].pitch = h->stage_pitch;
     }
+    cudaStream_t cs = (nstreams == 2 && slot) ? h->lane_stream : h->own_stream;
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[slot], h->copy_stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->own_stream, h->ev_copied[slot], 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied[slot], 0);
     if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
     int l = 0;
-    rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
-                      h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l, false, sparse ? h->hp_src + i0 : nullptr);
+    if (nstreams == 2)
+      rc = enqueue_view(h, make_view(h, slot * (int)S, slot, 2), dframes.data(), m, cs, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt,
+                        h->hp_out_count + i0, h->hp_counters + (size_t)k * CNT_N * kMaxChunks, &l, sparse ? h->hp_src + i0 : nullptr);
+    else
+      rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
+                        h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l, false, sparse ? h->hp_src + i0 : nullptr);
     launches += l;
-    if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], h->own_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
   cudaError_t es = cudaStreamSynchronize(h->own_stream);
+  if (nstreams == 2) {
+    const cudaError_t es2 = cudaStreamSynchronize(h->lane_stream);
+    if (es == cudaSuccess) es = es2;
+  }
   cudaStreamSynchronize(h->copy_stream);
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != B200AT_OK) return rc;

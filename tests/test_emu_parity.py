@@ -106,6 +106,14 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
     assert c["sparse_h2d"] == 1 and c["h2d_bytes"] < 0.8 * frames.nbytes
     for a, b in zip(got, want):
         assert a.tobytes() == b.tobytes() and len(a) >= 1
+    # two sub-batches in flight on two streams, each on its own view of the workspace
+    monkeypatch.setenv("B200AT_HOST_STREAMS", "2")
+    monkeypatch.setenv("B200AT_HOST_SUB", "1")
+    got3 = det.detect_host(frames)
+    for a, b in zip(got3, want):
+        assert a.tobytes() == b.tobytes()
+    monkeypatch.delenv("B200AT_HOST_STREAMS")
+    monkeypatch.delenv("B200AT_HOST_SUB")
     # pageable (not device-mapped) frames fall back to the full copy
     monkeypatch.setenv("B200AT_EMU_HOSTMEM", "pageable")
     got2 = det.detect_host(frames)

@@ -346,6 +346,18 @@ def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
         assert full[i].tobytes() == want[i].tobytes(), i
         assert got[i].tobytes() == want[i].tobytes(), i
     assert sum(len(x) for x in got) >= n
+    # two sub-batches in flight on two streams (disjoint workspace views), both staging modes
+    monkeypatch.setenv("B200AT_HOST_STREAMS", "2")
+    monkeypatch.setenv("B200AT_HOST_SUB", "2")
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200AT_SPARSE_H2D", mode)
+        got3 = det.detect_host(host)
+        assert det.counters()["sparse_h2d"] == int(mode)
+        for i in range(n):
+            assert got3[i].tobytes() == want[i].tobytes(), (mode, i)
+    monkeypatch.delenv("B200AT_HOST_STREAMS")
+    monkeypatch.delenv("B200AT_HOST_SUB")
+    monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
     # frames in pageable memory: the call falls back to the full copy by itself
     if not pu.EMU:
         got2 = det.detect_host(frames.copy())

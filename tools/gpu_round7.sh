@@ -10,7 +10,7 @@ timeout 400 python tools/gpu_tune.py > gpurun_out/r02_tune.jsonl 2> gpurun_out/r
 tail -2 gpurun_out/r02_tune.err
 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu_default.log 2>&1
 tail -3 gpurun_out/r02_pytest_gpu_default.log
-B200AT_TUNE=$ALL B200AT_SPARSE_H2D=1 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu_allon.log 2>&1
+B200AT_TUNE=$ALL B200AT_SPARSE_H2D=1 B200AT_HOST_STREAMS=2 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu_allon.log 2>&1
 tail -3 gpurun_out/r02_pytest_gpu_allon.log
 timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err
 cut -c1-300 gpurun_out/r02_bench_default.json

@@ -94,12 +94,13 @@ def main():
     host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
     for tune in ("", ALL_ON):
         for mode in ("0", "1"):
-            for sub in ("8", "16", "32"):
+            for sub, streams in (("8", "1"), ("16", "1"), ("32", "1"), ("8", "2"), ("16", "2"), ("32", "2")):
                 if args.quick and sub != "16":
                     continue
                 try:
                     os.environ["B200AT_SPARSE_H2D"] = mode
                     os.environ["B200AT_HOST_SUB"] = sub
+                    os.environ["B200AT_HOST_STREAMS"] = streams
                     det = make(tune)
                     det.detect_host(host)
                     t0 = time.perf_counter()
@@ -108,13 +109,14 @@ def main():
                     torch.cuda.synchronize()
                     dt = (time.perf_counter() - t0) / 3
                     c = det.counters()
-                    emit(event="host", tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), ms_per_step=dt * 1e3, fps=B / dt,
+                    emit(event="host", tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), ms_per_step=dt * 1e3, fps=B / dt,
                          h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
                     det.close()
                 except Exception as e:
-                    emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), error=repr(e))
+                    emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), streams=int(streams), error=repr(e))
     os.environ.pop("B200AT_SPARSE_H2D", None)
     os.environ.pop("B200AT_HOST_SUB", None)
+    os.environ.pop("B200AT_HOST_STREAMS", None)
     emit(event="done", seconds=time.time() - t_start)
 
 
