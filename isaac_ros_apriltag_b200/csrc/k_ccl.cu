@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restri
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Row-sweep variant of the tile kernel: ONE WARP per 32x32 tile (lane = column), rows top to bottom.  A run of a row that
-// touches the component(s) above INHERITS a label (segmented min over the run with redux.sync); shared-memory unions are
+// touches the component(s) above INHERITS a label (segmented min over the run, full-mask shuffles); shared-memory unions are
 // only needed where a run touches two different labels.  On thresholded noise (0.5 vertical / diagonal links per pixel, run
 // length 2.3) that replaces ~490 pointer-chasing unions per tile by a few dozen.  Per-run pixel counts go to the run's
 // label and are moved to the final local roots at the end.  Same outputs as k_ccl_tile: lab = global index of the local
@@ -315,7 +315,16 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
       if (n.UL && lane > 0) c2 = pl_l;
       if (n.UR && lane < TW - 1) c3 = pl_r;
     }
-    uint32_t rl = __reduce_min_sync(run_mask, min(c1, min(c2, c3)));
+    // segmented min over the run with FULL-mask shuffles: inclusive min-scan from the run's first lane, then the value of its
+    // last lane.  (redux.sync with one member mask per run makes the hardware execute the runs one after the other.)
+    uint32_t rl = min(c1, min(c2, c3));
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t2 = __shfl_up_sync(0xffffffffu, rl, d);
+      if ((int)lane - d >= rs) rl = min(rl, t2);
+    }
+    const int rlast = above ? (__ffs(above) - 2) : 31;  // last lane of my run
+    rl = __shfl_sync(0xffffffffu, rl, rlast);
     const int i = ly * TW + lane;
     if (rl == NONE) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
     L[i] = rl;

@@ -8,6 +8,8 @@
 // lane-parallel.  Colour frames are converted to gray on the fly at each gather.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "detector.h"
 
 namespace b200at {
@@ -622,31 +624,48 @@ __global__ void __launch_bounds__(256) k_mark_quads(Geo g, FitParams fp, const Q
   }
 }
 
-// grid (chunks of 16 B along a row, H, frames): copies the chunks of row y whose segment is in need & ~have
-__global__ void __launch_bounds__(128) k_fetch_rows(Geo g, const FrameDesc *__restrict__ src, const FrameDesc *__restrict__ dst,
+// One warp per (frame, row): copies the 16-byte chunks of row y whose segment is in need & ~have (most rows need nothing and
+// cost one word load).  grid (ceil(H / 8), frames), 8 warps per CTA.
+__global__ void __launch_bounds__(256) k_fetch_rows(Geo g, const FrameDesc *__restrict__ src, const FrameDesc *__restrict__ dst,
                                                     const unsigned long long *__restrict__ need,
                                                     const unsigned long long *__restrict__ have, uint32_t *__restrict__ counters) {
-  const int y = blockIdx.y, fr = blockIdx.z;
-  if ((y % g.row_step) == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int y = blockIdx.x * 8 + (threadIdx.x >> 5), fr = blockIdx.y;
+  if (y >= g.H || (y % g.row_step) == 0) return;
   unsigned long long w = need[(size_t)fr * g.H + y];
   if (have) w &= ~have[(size_t)fr * g.H + y];
   if (w == 0) return;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk of the row
+  const FrameDesc s = src[fr], d = dst[fr];
+  // both frames are 16-byte aligned with 16-byte-multiple pitches (checked on the host), so a chunk never leaves its row
+  const uint8_t *srow = s.ptr + (size_t)y * s.pitch;
+  uint8_t *drow = const_cast<uint8_t *>(d.ptr) + (size_t)y * d.pitch;
   const int row_bytes = g.W * g.bpp;
-  const int b0 = c * 16;
-  bool take = false;
-  if (b0 < row_bytes) {
-    const int pa = b0 / g.bpp, pb = min(g.W - 1, (b0 + 15) / g.bpp);  // first / last pixel with a byte in the chunk
-    take = ((w >> (pa >> g.seg_shift)) | (w >> (pb >> g.seg_shift))) & 1ull;
+  const int nchunks = (row_bytes + 15) >> 4;
+  uint32_t copied = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 128) {
+    uint4 v[4];
+    bool take[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {  // four independent PCIe reads in flight per lane
+      const int c = c0 + u * 32 + lane;
+      const int b0 = c * 16;
+      take[u] = false;
+      if (c < nchunks) {
+        const int pa = b0 / g.bpp, pb = min(g.W - 1, (b0 + 15) / g.bpp);  // first / last pixel with a byte in the chunk
+        take[u] = ((w >> (pa >> g.seg_shift)) | (w >> (pb >> g.seg_shift))) & 1ull;
+      }
+      if (take[u]) v[u] = *reinterpret_cast<const uint4 *>(srow + b0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (take[u]) {
+        *reinterpret_cast<uint4 *>(drow + (size_t)(c0 + u * 32 + lane) * 16) = v[u];
+        copied++;
+      }
+    }
   }
-  if (take) {
-    const FrameDesc s = src[fr], d = dst[fr];
-    // both frames are 16-byte aligned with 16-byte-multiple pitches (checked on the host), so a chunk never leaves its row
-    const uint4 v = *reinterpret_cast<const uint4 *>(s.ptr + (size_t)y * s.pitch + b0);
-    *reinterpret_cast<uint4 *>(const_cast<uint8_t *>(d.ptr) + (size_t)y * d.pitch + b0) = v;
-  }
-  const unsigned bal = __ballot_sync(0xffffffffu, take);
-  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&counters[CNT_FETCHED], (uint32_t)__popc(bal));
+  copied = __reduce_add_sync(0xffffffffu, copied);
+  if (lane == 0 && copied) atomicAdd(&counters[CNT_FETCHED], copied);
 }
 
 template <bool MARK, int MINB>
@@ -747,11 +766,13 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
     return 2;
   }
   // sparse host path: the caller (capi.cu) zeroed need1 / need2 when it staged the frames
-  const dim3 gf((g.W * g.bpp + 16 * 128 - 1) / (16 * 128), g.H, nframes);
+  const dim3 gf((g.H + 7) / 8, nframes);
+  // (measurement switch: B200AT_SPARSE_NOFETCH=1 skips the on-demand fetches -- WRONG results, shows what they cost)
+  static const bool nofetch = getenv("B200AT_SPARSE_NOFETCH") != nullptr;
   k_mark_quads<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.quads, ws.counters, ws.need1);
-  k_fetch_rows<<<gf, 128, 0, s>>>(g, ws.src_frames, ws.frames, ws.need1, nullptr, ws.counters);
+  if (!nofetch) k_fetch_rows<<<gf, 256, 0, s>>>(g, ws.src_frames, ws.frames, ws.need1, nullptr, ws.counters);
   k_refine<true, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
-  k_fetch_rows<<<gf, 128, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
+  if (!nofetch) k_fetch_rows<<<gf, 256, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
   k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
   return 6;
 }

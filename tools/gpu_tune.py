@@ -17,11 +17,9 @@ import torch  # noqa: E402
 
 from isaac_ros_apriltag_b200 import capi, synth  # noqa: E402
 
-ALL_ON = "thr_early=1,ccl_sweep=1,cluster_eager=2,decode_split=1,qf_mc=1"
-DEVICE_CONFIGS = ["", "thr_early=1", "thr_early=2", "ccl_sweep=1", "ccl_sweep=2", "cluster_eager=1", "cluster_eager=2", "decode_split=1",
-                  "decode_split=2", "qf_mc=1", "qf_scale=0.75", "qf_scale=1.5", "qf_keys23=1",
-                  "ccl_sweep=1,cluster_eager=2", "thr_early=1,ccl_sweep=1,cluster_eager=2,decode_split=2", "thr_early=1,ccl_sweep=1,cluster_eager=2,qf_mc=1",
-                  ALL_ON, ""]
+ALL_ON = "cluster_eager=2,decode_split=1,qf_mc=1,qf_keys23=1"
+DEVICE_CONFIGS = ["", "ccl_sweep=1", "ccl_sweep=2", "cluster_eager=2", "decode_split=1", "qf_mc=1", "qf_keys23=1", "qf_mc=1,qf_keys23=1",
+                  ALL_ON, ALL_ON + ",ccl_sweep=1", ""]
 
 
 def emit(**kw):
@@ -38,6 +36,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=32)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--host-only", action="store_true")
+    ap.add_argument("--tag", default="")
     args = ap.parse_args()
     t_start = time.time()
     frames, truths, K, tagsize, fams = synth.make_config_frames("C2", args.distinct)
@@ -63,6 +63,11 @@ def main():
 
     base = None
     configs = DEVICE_CONFIGS[:4] + [ALL_ON] if args.quick else DEVICE_CONFIGS
+    if args.host_only:
+        det = make("")
+        base = det.detect_device(ptrs, pitch, sh)
+        det.close()
+        configs = []
     for tune in configs:
         try:
             det = make(tune)
@@ -90,11 +95,33 @@ def main():
             det.close()
         except Exception as e:  # keep sweeping: one bad configuration must not cost the others
             emit(event="device", tune=tune or "default", error=repr(e))
+    # ---- device path in sub-batch sized calls (what the host path's sub-batching costs by itself) ----
+    for sub in (() if args.host_only else (16, 32, 64)):
+        try:
+            os.environ.pop("B200AT_TUNE", None)
+            det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=tagsize, families=fams, encoding="bgr8",
+                                max_batch=sub, max_tags=64)
+            for i0 in range(0, B, sub):
+                det.detect_device(ptrs[i0:i0 + sub], pitch, sh)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(2):
+                for i0 in range(0, B, sub):
+                    det.detect_device(ptrs[i0:i0 + sub], pitch, sh)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            emit(event="device_subbatched", sub=sub, ms_per_256=ev0.elapsed_time(ev1) / 2)
+            det.close()
+        except Exception as e:
+            emit(event="device_subbatched", sub=sub, error=repr(e))
     # ---- host path: staging mode x sub-batch size x knobs ----
     host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
     for tune in ("", ALL_ON):
         for mode in ("0", "1"):
-            for sub, streams in (("8", "1"), ("16", "1"), ("32", "1"), ("8", "2"), ("16", "2"), ("32", "2")):
+            for sub, streams in (("16", "1"), ("32", "1"), ("64", "1"), ("16", "2"), ("32", "2"), ("64", "2")):
+                if mode == "0" and (sub != "16" or tune):
+                    continue
                 if args.quick and sub != "16":
                     continue
                 try:
@@ -109,7 +136,7 @@ def main():
                     torch.cuda.synchronize()
                     dt = (time.perf_counter() - t0) / 3
                     c = det.counters()
-                    emit(event="host", tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), ms_per_step=dt * 1e3, fps=B / dt,
+                    emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), ms_per_step=dt * 1e3, fps=B / dt,
                          h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
                     det.close()
                 except Exception as e:
