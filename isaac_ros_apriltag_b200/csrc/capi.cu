@@ -41,12 +41,13 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
 // Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
 constexpr bool kSparseHostPathDefault = false;
 constexpr int kHostStreamsDefault = 1;
+constexpr bool kHostPipeDefault = false;
 constexpr int kTuneDefaultThrEarly = 0;
 constexpr int kTuneDefaultCclSweep = 0;
 constexpr int kTuneDefaultQfMc = 0;
 constexpr int kTuneDefaultClusterEager = 0;
 
-// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0,qf_mc=0": performance knobs of one handle (detector.h,
+// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0,qf_mc=0,qf_net=0": performance knobs of one handle (detector.h,
 // struct Tune).  Unknown keys are reported and ignored.
 Tune parse_tune() {
   Tune t;
@@ -58,6 +59,7 @@ Tune parse_tune() {
   t.qf_scale = 1.0f;
   t.qf_keys23 = 0;
   t.qf_mc = kTuneDefaultQfMc;
+  t.qf_net = 0;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -79,6 +81,7 @@ Tune parse_tune() {
     else if (k == "qf_scale") t.qf_scale = (float)v;
     else if (k == "qf_keys23") t.qf_keys23 = (int)v;
     else if (k == "qf_mc") t.qf_mc = (int)v;
+    else if (k == "qf_net") t.qf_net = (int)v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;
@@ -112,7 +115,11 @@ struct cuAprilTagsHandle_st {
   uint32_t stage_sub = 0;  // frames per staging slot
   cudaStream_t own_stream = nullptr;   // compute stream of the host path
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_consumed[3] = {nullptr, nullptr, nullptr};
+  // pipelined sparse host path: fetches of sub-batch k on their own stream while sub-batch k+1 is being detected
+  cudaStream_t fetch_stream = nullptr;
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fetched[2] = {nullptr, nullptr};
+  uint32_t stage_slots = 0;
   FrameDesc *hp_frames = nullptr;
   FrameDesc *hp_src = nullptr;         // sparse host path: device-mapped addresses of the caller's frames
   bool sparse_bufs = false;            // need1 / need2 / src_frames / quad_H allocated
@@ -186,10 +193,15 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->hp_out) cudaFreeHost(h->hp_out);
   if (h->hp_out_count) cudaFreeHost(h->hp_out_count);
   if (h->hp_counters) cudaFreeHost(h->hp_counters);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
+  for (int i = 0; i < 2; i++) {
+    if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]);
+    if (h->ev_fetched[i]) cudaEventDestroy(h->ev_fetched[i]);
+  }
+  if (h->fetch_stream) cudaStreamDestroy(h->fetch_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < kQuadAux; i++) {
     if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
@@ -733,20 +745,53 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
 // One sub-batch of the host path on a VIEW of the workspace (frames [f0, f0 + n), pool slice c of 2), so that two sub-batches
 // can be in flight on two streams: the latency-bound tails of one (large-cluster quad fits, decode, pose: a few busy SMs)
 // overlap the dense stages of the next.  Everything the launch chain writes is inside the view.
+enum { VIEW_ALL = 0, VIEW_FRONT = 1, VIEW_FETCH = 2, VIEW_BACK = 3 };
+static void view_sparse_geo(Geo &g, bool sparse) {
+  g.row_step = 0;
+  if (sparse) {
+    g.row_step = g.f;
+    g.seg_shift = 5;
+    while (((g.W + (1 << g.seg_shift) - 1) >> g.seg_shift) > 64) g.seg_shift++;
+  }
+}
+// Pipelined sparse host path: the same chain cut in three.  FRONT = table upload + preprocess .. quad fit (compute stream);
+// FETCH = mark + fetch of the rows refine_edges needs (fetch stream, overlaps the next sub-batch's FRONT); BACK = refine,
+// second fetch, decode, reconcile, pose, D2H (compute stream, after FETCH).
+static int enqueue_view_part(cuAprilTagsHandle h, Workspace v, int part, uint32_t n, cudaStream_t stream, b200AprilTagsDetection_t *out,
+                             uint32_t *cnt, uint32_t *ctr, int *launches_out) {
+  (void)h;
+  Geo &g = v.g;
+  view_sparse_geo(g, true);
+  int launches = 0;
+  cudaError_t e = cudaSuccess;
+  if (part == VIEW_FETCH) {
+    launches += launch_sparse_fetch1(v, (int)n, stream);
+  } else {  // VIEW_BACK
+    launches += launch_sparse_back(v, (int)n, stream);
+    launches += launch_finalize(v, (int)n, stream);
+    e = cudaMemcpyAsync(out, v.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, v.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
+    memset(ctr, 0, sizeof(uint32_t) * CNT_N * kMaxChunks);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, v.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[b200apriltags] enqueue failed: %s\n", cudaGetErrorString(e));
+    return B200AT_ERR_CUDA;
+  }
+  if (launches_out) *launches_out = launches;
+  return B200AT_OK;
+}
+
 static int enqueue_view(cuAprilTagsHandle h, Workspace v, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream,
                         FrameDesc *hf, b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, int *launches_out,
-                        const FrameDesc *sparse_src) {
+                        const FrameDesc *sparse_src, int part = VIEW_ALL) {
   Geo &g = v.g;
   int fast = 1;
   int rcf = fill_frame_table(h, frames, n, hf, &fast);
   if (rcf != B200AT_OK) return rcf;
   g.fast_align = fast;
-  g.row_step = 0;
-  if (sparse_src) {
-    g.row_step = g.f;
-    g.seg_shift = 5;
-    while (((g.W + (1 << g.seg_shift) - 1) >> g.seg_shift) > 64) g.seg_shift++;
-  }
+  view_sparse_geo(g, sparse_src != nullptr);
   cudaError_t e = cudaMemcpyAsync(v.frames, hf, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(v.counters, 0, sizeof(uint32_t) * CNT_N, stream);
   if (sparse_src) {
@@ -760,13 +805,15 @@ static int enqueue_view(cuAprilTagsHandle h, Workspace v, const b200AprilTagsFra
   launches += launch_ccl(v, (int)n, stream);
   launches += launch_cluster(v, (int)n, stream);
   launches += launch_quadfit(v, (int)n, stream);
-  launches += launch_decode(v, (int)n, stream);
-  launches += launch_finalize(v, (int)n, stream);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(out, v.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, v.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
-  memset(ctr, 0, sizeof(uint32_t) * CNT_N * kMaxChunks);  // (host) only the first CNT_N entries are produced by this view
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, v.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+  if (part == VIEW_ALL) {
+    launches += launch_decode(v, (int)n, stream);
+    launches += launch_finalize(v, (int)n, stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(out, v.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, v.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
+    memset(ctr, 0, sizeof(uint32_t) * CNT_N * kMaxChunks);  // (host) only the first CNT_N entries are produced by this view
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, v.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+  }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     fprintf(stderr, "[b200apriltags] enqueue failed: %s\n", cudaGetErrorString(e));
@@ -898,17 +945,17 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     const int v = atoi(es);
     if (v >= 1) S = std::min<uint32_t>(h->max_batch, (uint32_t)v);
   }
-  if (!h->d_stage) {
+  if (!h->copy_stream) {
     h->stage_pitch = (row + 255) & ~(size_t)255;
-    h->stage_sub = S;
-    void *p = nullptr;
-    if (cudaMalloc(&p, h->stage_pitch * g.H * (size_t)S * 2) != cudaSuccess) return fail(B200AT_ERR_NOMEM);
-    h->dev_allocs.push_back(p);
-    h->d_stage = (uint8_t *)p;
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    for (int i = 0; i < 2; i++) {
+    if (cudaStreamCreateWithFlags(&h->fetch_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    for (int i = 0; i < 3; i++) {
       if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
       if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    }
+    for (int i = 0; i < 2; i++) {
+      if (cudaEventCreateWithFlags(&h->ev_front[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+      if (cudaEventCreateWithFlags(&h->ev_fetched[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
   // Sparse staging (see k_decode.cu): with an integer quad_decimate f >= 2 the detector reads only every f-th row until the
@@ -955,6 +1002,33 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   int nstreams = kHostStreamsDefault;
   if (const char *es = getenv("B200AT_HOST_STREAMS")) nstreams = atoi(es);
   if (nstreams != 2 || 2 * S > h->max_batch) nstreams = 1;
+  // Pipelined sparse path (B200AT_HOST_PIPE=0/1): the on-demand fetches of sub-batch k run on their own stream while the
+  // compute stream already detects the quads of sub-batch k+1; needs two workspace views and three staging slots.
+  bool pipe = kHostPipeDefault;
+  if (const char *es = getenv("B200AT_HOST_PIPE")) pipe = atoi(es) != 0;
+  if (!sparse || 2 * S > h->max_batch) pipe = false;
+  if (pipe) nstreams = 1;
+  const uint32_t nslots = pipe ? 3 : 2;
+  if (!h->d_stage || h->stage_sub < S || h->stage_slots < nslots) {
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->own_stream);
+    if (h->d_stage) {
+      for (size_t i = 0; i < h->dev_allocs.size(); i++)
+        if (h->dev_allocs[i] == h->d_stage) {
+          h->dev_allocs.erase(h->dev_allocs.begin() + (long)i);
+          break;
+        }
+      cudaFree(h->d_stage);
+      h->d_stage = nullptr;
+    }
+    void *p = nullptr;
+    const uint32_t ss = std::max(S, h->stage_sub), sl = std::max(nslots, h->stage_slots);
+    if (cudaMalloc(&p, h->stage_pitch * g.H * (size_t)ss * sl) != cudaSuccess) return fail(B200AT_ERR_NOMEM);
+    h->dev_allocs.push_back(p);
+    h->d_stage = (uint8_t *)p;
+    h->stage_sub = ss;
+    h->stage_slots = sl;
+  }
   const int row_step = sparse ? g.f : 1;
   const int rows_dma = 1 + (g.H - 1) / row_step;
   static const bool sparse_debug = getenv("B200AT_SPARSE_DEBUG") != nullptr;  // poison the slot: an unfetched row cannot go unnoticed
@@ -987,10 +1061,10 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   int launches = 0;
   for (uint32_t k = 0; k < nsub && rc == B200AT_OK; k++) {
     const uint32_t i0 = sub_start[k], m = sub_len[k];
-    const int slot = (int)(k & 1);
-    uint8_t *slot_base = h->d_stage + (size_t)slot * S * h->stage_pitch * g.H;
+    const int slot = (int)(k % nslots);
+    uint8_t *slot_base = h->d_stage + (size_t)slot * h->stage_sub * h->stage_pitch * g.H;
     cudaError_t e = cudaSuccess;
-    if (k >= 2) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
+    if (k >= nslots) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
     if (sparse && sparse_debug && e == cudaSuccess) e = cudaMemsetAsync(slot_base, 0xA5, (size_t)m * h->stage_pitch * g.H, h->copy_stream);
     for (uint32_t j = 0; j < m && e == cudaSuccess; j++) {
       if (!frames[i0 + j].ptr || frames[i0 + j].pitch < row) return fail(B200AT_ERR_INVALID_ARG);
@@ -1007,6 +1081,33 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied[slot], 0);
     if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
     int l = 0;
+    if (pipe) {
+      // compute stream: FRONT(k), BACK(k-1), FRONT(k+1), ...; fetch stream: FETCH(k) between FRONT(k) and BACK(k)
+      const int vw = (int)(k & 1);
+      rc = enqueue_view(h, make_view(h, vw * (int)S, vw, 2), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l,
+                        h->hp_src + i0, VIEW_FRONT);
+      launches += l;
+      if (rc == B200AT_OK && cudaEventRecord(h->ev_front[vw], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == B200AT_OK) rc = enqueue_view_part(h, make_view(h, vw * (int)S, vw, 2), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
+      launches += l;
+      if (rc == B200AT_OK && cudaEventRecord(h->ev_fetched[vw], h->fetch_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      for (int last = 0; last < 2 && rc == B200AT_OK; last++) {
+        // BACK of the previous sub-batch; after the last FRONT also the BACK of this one
+        if (last == 0 && k == 0) continue;
+        if (last == 1 && k + 1 != nsub) break;
+        const uint32_t kb = last ? k : k - 1;
+        const int vb = (int)(kb & 1);
+        const uint32_t ib = sub_start[kb], mb = sub_len[kb];
+        if (cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK)
+          rc = enqueue_view_part(h, make_view(h, vb * (int)S, vb, 2), VIEW_BACK, mb, cs, h->hp_out + (size_t)ib * mt, h->hp_out_count + ib,
+                                 h->hp_counters + (size_t)kb * CNT_N * kMaxChunks, &l);
+        launches += l;
+        if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[kb % nslots], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      }
+      continue;
+    }
     if (nstreams == 2)
       rc = enqueue_view(h, make_view(h, slot * (int)S, slot, 2), dframes.data(), m, cs, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt,
                         h->hp_out_count + i0, h->hp_counters + (size_t)k * CNT_N * kMaxChunks, &l, sparse ? h->hp_src + i0 : nullptr);

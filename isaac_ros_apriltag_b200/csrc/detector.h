@@ -119,6 +119,7 @@ struct Tune {
   int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
   int decode_ctas;    // persistent decode CTAs per SM
   int qf_mc;          // quad fit, one-warp bins: several clusters per CTA in phase lockstep (shared instruction stream)
+  int qf_net;         // quad fit sort: register bitonic networks instead of odd-even transposition + serial merge
   float qf_scale;     // scales the persistent grid of every quad-fit bin
   int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
 };
@@ -171,6 +172,8 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_decode(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_sparse_fetch1(const Workspace &ws, int nframes, cudaStream_t s);  // sparse host path: mark + fetch for refine_edges
+int launch_sparse_back(const Workspace &ws, int nframes, cudaStream_t s);    // ... refine, second fetch, decode
 int launch_finalize(const Workspace &ws, int nframes, cudaStream_t s);
 
 }  // namespace b200at

@@ -742,39 +742,61 @@ __global__ void __launch_bounds__(DT, MINB) k_decode_bits(Geo g, FitParams fp, D
   }
 }
 
-int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
-  const Geo &g = ws.g;
-  cudaMemsetAsync(ws.cand_count, 0, (size_t)nframes * sizeof(uint32_t), s);
-  DecodeFams df;
-  for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
+static int sm_count() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int ctas = sms * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
-  if (g.row_step == 0) {
-    if (ws.tune.decode_split == 2 && ws.quad_H) {  // register budget of 6 CTAs (24 warps) per SM
-      k_refine<false, 6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
-      k_decode_bits<6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
-      return 3;
-    }
-    if (ws.tune.decode_split && ws.quad_H) {
-      k_refine<false, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
-      k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
-      return 3;
-    }
-    k_decode<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.cands, ws.cand_count, ws.counters);
-    return 2;
-  }
-  // sparse host path: the caller (capi.cu) zeroed need1 / need2 when it staged the frames
+  return sms;
+}
+
+// sparse host path, first half: mark the rows refine_edges will read and fetch them from the caller's frames.  May run on a
+// side stream while the next sub-batch's quad detection occupies the compute stream (capi.cu).
+int launch_sparse_fetch1(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
   const dim3 gf((g.H + 7) / 8, nframes);
   // (measurement switch: B200AT_SPARSE_NOFETCH=1 skips the on-demand fetches -- WRONG results, shows what they cost)
   static const bool nofetch = getenv("B200AT_SPARSE_NOFETCH") != nullptr;
-  k_mark_quads<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.quads, ws.counters, ws.need1);
+  k_mark_quads<<<sm_count() * 2, 256, 0, s>>>(g, ws.fp, ws.quads, ws.counters, ws.need1);
   if (!nofetch) k_fetch_rows<<<gf, 256, 0, s>>>(g, ws.src_frames, ws.frames, ws.need1, nullptr, ws.counters);
+  return 2;
+}
+
+// sparse host path, second half: refine (marks the decoder's sample rows), fetch what is still missing, decode
+int launch_sparse_back(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
+  static const bool nofetch = getenv("B200AT_SPARSE_NOFETCH") != nullptr;
+  cudaMemsetAsync(ws.cand_count, 0, (size_t)nframes * sizeof(uint32_t), s);
+  DecodeFams df;
+  for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
+  const int ctas = sm_count() * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
+  const dim3 gf((g.H + 7) / 8, nframes);
   k_refine<true, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
   if (!nofetch) k_fetch_rows<<<gf, 256, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
   k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
-  return 6;
+  return 4;
+}
+
+int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
+  if (g.row_step != 0)  // sparse host path: the caller (capi.cu) zeroed need1 / need2 when it staged the frames
+    return launch_sparse_fetch1(ws, nframes, s) + launch_sparse_back(ws, nframes, s);
+  cudaMemsetAsync(ws.cand_count, 0, (size_t)nframes * sizeof(uint32_t), s);
+  DecodeFams df;
+  for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
+  const int sms = sm_count();
+  const int ctas = sms * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
+  if (ws.tune.decode_split == 2 && ws.quad_H) {  // register budget of 6 CTAs (24 warps) per SM
+    k_refine<false, 6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    k_decode_bits<6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+    return 3;
+  }
+  if (ws.tune.decode_split && ws.quad_H) {
+    k_refine<false, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+    return 3;
+  }
+  k_decode<<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.cands, ws.cand_count, ws.counters);
+  return 2;
 }
 
 }  // namespace b200at

@@ -113,6 +113,13 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
     for a, b in zip(got3, want):
         assert a.tobytes() == b.tobytes()
     monkeypatch.delenv("B200AT_HOST_STREAMS")
+    # pipelined: fetches of sub-batch k on their own stream, between FRONT(k) and BACK(k), three staging slots
+    monkeypatch.setenv("B200AT_HOST_PIPE", "1")
+    got4 = det.detect_host(frames)
+    assert det.counters()["sparse_h2d"] == 1
+    for a, b in zip(got4, want):
+        assert a.tobytes() == b.tobytes()
+    monkeypatch.delenv("B200AT_HOST_PIPE")
     monkeypatch.delenv("B200AT_HOST_SUB")
     # pageable (not device-mapped) frames fall back to the full copy
     monkeypatch.setenv("B200AT_EMU_HOSTMEM", "pageable")

@@ -356,6 +356,18 @@ def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
         for i in range(n):
             assert got3[i].tobytes() == want[i].tobytes(), (mode, i)
     monkeypatch.delenv("B200AT_HOST_STREAMS")
+    # pipelined sparse path: FRONT(k+1) on the compute stream while the fetch stream serves sub-batch k (three staging slots);
+    # sub-batches of 1 and 2 frames so that the 6 frames exercise slot reuse
+    monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
+    monkeypatch.setenv("B200AT_HOST_PIPE", "1")
+    for sub in ("1", "2"):
+        monkeypatch.setenv("B200AT_HOST_SUB", sub)
+        for _ in range(2):
+            got4 = det.detect_host(host)
+            assert det.counters()["sparse_h2d"] == 1
+            for i in range(n):
+                assert got4[i].tobytes() == want[i].tobytes(), (sub, i)
+    monkeypatch.delenv("B200AT_HOST_PIPE")
     monkeypatch.delenv("B200AT_HOST_SUB")
     monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
     # frames in pageable memory: the call falls back to the full copy by itself

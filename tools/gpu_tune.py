@@ -17,9 +17,13 @@ import torch  # noqa: E402
 
 from isaac_ros_apriltag_b200 import capi, synth  # noqa: E402
 
-ALL_ON = "cluster_eager=2,decode_split=1,qf_mc=1,qf_keys23=1"
-DEVICE_CONFIGS = ["", "ccl_sweep=1", "ccl_sweep=2", "cluster_eager=2", "decode_split=1", "qf_mc=1", "qf_keys23=1", "qf_mc=1,qf_keys23=1",
-                  ALL_ON, ALL_ON + ",ccl_sweep=1", ""]
+ALL_ON = "ccl_sweep=1,cluster_eager=2,decode_split=1,qf_mc=1,qf_keys23=1"
+DEVICE_CONFIGS = ["", "qf_net=1", "qf_net=1,qf_keys23=1", ALL_ON, ALL_ON + ",qf_net=1", ""]
+# host entry point: (knobs, sparse staging, sub-batch, streams, pipelined fetch)
+HOST_CONFIGS = [("", 0, 16, 1, 0), (ALL_ON, 0, 16, 1, 0),
+                (ALL_ON, 1, 16, 1, 0), (ALL_ON, 1, 32, 1, 0), (ALL_ON, 1, 64, 1, 0),
+                (ALL_ON, 1, 16, 1, 1), (ALL_ON, 1, 32, 1, 1), (ALL_ON, 1, 64, 1, 1), (ALL_ON, 1, 24, 1, 1), (ALL_ON, 1, 48, 1, 1),
+                (ALL_ON + ",qf_net=1", 1, 32, 1, 1), (ALL_ON + ",qf_net=1", 1, 64, 1, 1), ("", 1, 32, 1, 1)]
 
 
 def emit(**kw):
@@ -96,7 +100,7 @@ def main():
         except Exception as e:  # keep sweeping: one bad configuration must not cost the others
             emit(event="device", tune=tune or "default", error=repr(e))
     # ---- device path in sub-batch sized calls (what the host path's sub-batching costs by itself) ----
-    for sub in (() if args.host_only else (16, 32, 64)):
+    for sub in ():
         try:
             os.environ.pop("B200AT_TUNE", None)
             det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=tagsize, families=fams, encoding="bgr8",
@@ -117,30 +121,27 @@ def main():
             emit(event="device_subbatched", sub=sub, error=repr(e))
     # ---- host path: staging mode x sub-batch size x knobs ----
     host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
-    for tune in ("", ALL_ON):
-        for mode in ("0", "1"):
-            for sub, streams in (("16", "1"), ("32", "1"), ("64", "1"), ("16", "2"), ("32", "2"), ("64", "2")):
-                if mode == "0" and (sub != "16" or tune):
-                    continue
-                if args.quick and sub != "16":
-                    continue
-                try:
-                    os.environ["B200AT_SPARSE_H2D"] = mode
-                    os.environ["B200AT_HOST_SUB"] = sub
-                    os.environ["B200AT_HOST_STREAMS"] = streams
-                    det = make(tune)
-                    det.detect_host(host)
-                    t0 = time.perf_counter()
-                    for _ in range(3):
-                        r = det.detect_host(host)
-                    torch.cuda.synchronize()
-                    dt = (time.perf_counter() - t0) / 3
-                    c = det.counters()
-                    emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), ms_per_step=dt * 1e3, fps=B / dt,
-                         h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
-                    det.close()
-                except Exception as e:
-                    emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), streams=int(streams), error=repr(e))
+    for tune, sparse_on, sub_i, streams_i, pipe_i in HOST_CONFIGS:
+        mode, sub, streams = str(sparse_on), str(sub_i), str(streams_i)
+        try:
+            os.environ["B200AT_SPARSE_H2D"] = mode
+            os.environ["B200AT_HOST_SUB"] = sub
+            os.environ["B200AT_HOST_STREAMS"] = streams
+            os.environ["B200AT_HOST_PIPE"] = str(pipe_i)
+            det = make(tune)
+            det.detect_host(host)
+            t0 = time.perf_counter()
+            for _ in range(4):
+                r = det.detect_host(host)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 4
+            c = det.counters()
+            emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), pipe=pipe_i,
+                 ms_per_step=dt * 1e3, fps=B / dt, h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
+            det.close()
+        except Exception as e:
+            emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), streams=int(streams), pipe=pipe_i, error=repr(e))
+    os.environ.pop("B200AT_HOST_PIPE", None)
     os.environ.pop("B200AT_SPARSE_H2D", None)
     os.environ.pop("B200AT_HOST_SUB", None)
     os.environ.pop("B200AT_HOST_STREAMS", None)
