@@ -39,27 +39,28 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
   } while (0)
 
 // Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
-constexpr bool kSparseHostPathDefault = false;
+constexpr bool kSparseHostPathDefault = true;
 constexpr int kHostStreamsDefault = 1;
-constexpr bool kHostPipeDefault = false;
+constexpr bool kHostPipeDefault = true;
 constexpr int kTuneDefaultThrEarly = 0;
-constexpr int kTuneDefaultCclSweep = 0;
-constexpr int kTuneDefaultQfMc = 0;
-constexpr int kTuneDefaultClusterEager = 0;
+constexpr int kTuneDefaultCclSweep = 1;
+constexpr int kTuneDefaultQfMc = 1;
+constexpr int kTuneDefaultQfKeys23 = 1;
+constexpr int kTuneDefaultDecodeSplit = 1;
+constexpr int kTuneDefaultClusterEager = 2;
 
-// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0,qf_mc=0,qf_net=0": performance knobs of one handle (detector.h,
+// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0,qf_mc=0": performance knobs of one handle (detector.h,
 // struct Tune).  Unknown keys are reported and ignored.
 Tune parse_tune() {
   Tune t;
   t.thr_early = kTuneDefaultThrEarly;
   t.ccl_sweep = kTuneDefaultCclSweep;
   t.cluster_eager = kTuneDefaultClusterEager;
-  t.decode_split = 0;
+  t.decode_split = kTuneDefaultDecodeSplit;
   t.decode_ctas = 4;
   t.qf_scale = 1.0f;
-  t.qf_keys23 = 0;
+  t.qf_keys23 = kTuneDefaultQfKeys23;
   t.qf_mc = kTuneDefaultQfMc;
-  t.qf_net = 0;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -81,7 +82,6 @@ Tune parse_tune() {
     else if (k == "qf_scale") t.qf_scale = (float)v;
     else if (k == "qf_keys23") t.qf_keys23 = (int)v;
     else if (k == "qf_mc") t.qf_mc = (int)v;
-    else if (k == "qf_net") t.qf_net = (int)v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;
@@ -117,8 +117,9 @@ struct cuAprilTagsHandle_st {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_consumed[3] = {nullptr, nullptr, nullptr};
   // pipelined sparse host path: fetches of sub-batch k on their own stream while sub-batch k+1 is being detected
-  cudaStream_t fetch_stream = nullptr;
-  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fetched[2] = {nullptr, nullptr};
+  cudaStream_t fetch_stream = nullptr, tail_stream = nullptr;  // (high priority: few, latency-bound CTAs)
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fetched[2] = {nullptr, nullptr}, ev_decoded[2] = {nullptr, nullptr},
+              ev_tail[2] = {nullptr, nullptr};
   uint32_t stage_slots = 0;
   FrameDesc *hp_frames = nullptr;
   FrameDesc *hp_src = nullptr;         // sparse host path: device-mapped addresses of the caller's frames
@@ -200,8 +201,11 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   for (int i = 0; i < 2; i++) {
     if (h->ev_front[i]) cudaEventDestroy(h->ev_front[i]);
     if (h->ev_fetched[i]) cudaEventDestroy(h->ev_fetched[i]);
+    if (h->ev_decoded[i]) cudaEventDestroy(h->ev_decoded[i]);
+    if (h->ev_tail[i]) cudaEventDestroy(h->ev_tail[i]);
   }
   if (h->fetch_stream) cudaStreamDestroy(h->fetch_stream);
+  if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < kQuadAux; i++) {
     if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
@@ -758,7 +762,7 @@ static void view_sparse_geo(Geo &g, bool sparse) {
 // FETCH = mark + fetch of the rows refine_edges needs (fetch stream, overlaps the next sub-batch's FRONT); BACK = refine,
 // second fetch, decode, reconcile, pose, D2H (compute stream, after FETCH).
 static int enqueue_view_part(cuAprilTagsHandle h, Workspace v, int part, uint32_t n, cudaStream_t stream, b200AprilTagsDetection_t *out,
-                             uint32_t *cnt, uint32_t *ctr, int *launches_out) {
+                             uint32_t *cnt, uint32_t *ctr, int *launches_out, cudaStream_t tail = nullptr, cudaEvent_t ev_decoded = nullptr) {
   (void)h;
   Geo &g = v.g;
   view_sparse_geo(g, true);
@@ -766,13 +770,18 @@ static int enqueue_view_part(cuAprilTagsHandle h, Workspace v, int part, uint32_
   cudaError_t e = cudaSuccess;
   if (part == VIEW_FETCH) {
     launches += launch_sparse_fetch1(v, (int)n, stream);
-  } else {  // VIEW_BACK
+  } else {  // VIEW_BACK: decode on the compute stream; reconcile, pose and the D2H of the results on the tail stream
     launches += launch_sparse_back(v, (int)n, stream);
-    launches += launch_finalize(v, (int)n, stream);
-    e = cudaMemcpyAsync(out, v.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, v.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
+    cudaStream_t ts = tail ? tail : stream;
+    if (tail) {
+      e = cudaEventRecord(ev_decoded, stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(tail, ev_decoded, 0);
+    }
+    launches += launch_finalize(v, (int)n, ts);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, v.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, ts);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, v.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ts);
     memset(ctr, 0, sizeof(uint32_t) * CNT_N * kMaxChunks);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, v.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctr, v.counters, sizeof(uint32_t) * CNT_N, cudaMemcpyDeviceToHost, ts);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -941,14 +950,25 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   };
   // sub-batch size: small enough that copy(k+1) overlaps compute(k) inside one call, large enough to fill the GPU
   uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 15) / 16)));
+  bool S_forced = false;
   if (const char *es = getenv("B200AT_HOST_SUB")) {
     const int v = atoi(es);
-    if (v >= 1) S = std::min<uint32_t>(h->max_batch, (uint32_t)v);
+    if (v >= 1) {
+      S = std::min<uint32_t>(h->max_batch, (uint32_t)v);
+      S_forced = true;
+    }
   }
   if (!h->copy_stream) {
     h->stage_pitch = (row + 255) & ~(size_t)255;
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&h->fetch_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    {
+      // the fetch and tail kernels are a handful of latency-bound CTAs (PCIe reads; one thread per detection): at the highest
+      // priority they get the first free SM slots instead of queueing behind the next sub-batch's full grids
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if (cudaStreamCreateWithPriority(&h->fetch_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+      if (cudaStreamCreateWithPriority(&h->tail_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    }
     for (int i = 0; i < 3; i++) {
       if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
       if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
@@ -956,6 +976,8 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     for (int i = 0; i < 2; i++) {
       if (cudaEventCreateWithFlags(&h->ev_front[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
       if (cudaEventCreateWithFlags(&h->ev_fetched[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+      if (cudaEventCreateWithFlags(&h->ev_decoded[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+      if (cudaEventCreateWithFlags(&h->ev_tail[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
   // Sparse staging (see k_decode.cu): with an integer quad_decimate f >= 2 the detector reads only every f-th row until the
@@ -998,6 +1020,9 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (rca != 0) return fail(rca);
     h->sparse_bufs = true;
   }
+  // The full copy is PCIe-bound and likes small sub-batches (short pipeline fill); the sparse path is compute-bound and likes
+  // large ones (the fixed cost per sub-batch -- ~30 launches, persistent-kernel tails -- is ~0.4 ms): max_batch / 4.
+  if (sparse && !S_forced) S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch / 2, std::max<uint32_t>(16, (h->max_batch + 3) / 4)));
   // two sub-batches in flight on two streams (B200AT_HOST_STREAMS=1/2 overrides the default); needs two disjoint frame ranges
   int nstreams = kHostStreamsDefault;
   if (const char *es = getenv("B200AT_HOST_STREAMS")) nstreams = atoi(es);
@@ -1035,10 +1060,20 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   uint64_t dma_bytes = 0;
   // uniform sub-batches (a ramped schedule -- small first/last sub-batches to shorten pipeline fill and drain -- was
   // measured and did not pay: the tiny sub-batches cost more in launch overhead than they save)
+  // In the pipelined sparse mode the call is compute-bound: the first sub-batches are small, so that the kernels start after
+  // a short first DMA, the later ones large, so that the fixed cost per sub-batch (launches, persistent-kernel tails) is paid
+  // fewer times (B200AT_HOST_RAMP=0 turns the ramp off).
+  bool ramp = pipe;
+  if (const char *es = getenv("B200AT_HOST_RAMP")) ramp = ramp && atoi(es) != 0;
   std::vector<uint32_t> sub_start, sub_len;
-  for (uint32_t pos = 0; pos < n; pos += S) {
+  for (uint32_t pos = 0, k = 0; pos < n; k++) {
+    uint32_t len = S;
+    if (ramp && k == 0) len = std::max<uint32_t>(1, S / 4);
+    if (ramp && k == 1) len = std::max<uint32_t>(1, S / 2);
+    len = std::min<uint32_t>(len, n - pos);
     sub_start.push_back(pos);
-    sub_len.push_back(std::min<uint32_t>(S, n - pos));
+    sub_len.push_back(len);
+    pos += len;
   }
   const uint32_t nsub = (uint32_t)sub_start.size();
   if (h->hp_cap_frames < n || h->hp_cap_subs < nsub) {
@@ -1084,8 +1119,11 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (pipe) {
       // compute stream: FRONT(k), BACK(k-1), FRONT(k+1), ...; fetch stream: FETCH(k) between FRONT(k) and BACK(k)
       const int vw = (int)(k & 1);
-      rc = enqueue_view(h, make_view(h, vw * (int)S, vw, 2), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l,
-                        h->hp_src + i0, VIEW_FRONT);
+      // the view's previous user (sub-batch k-2) may still have its reconcile / pose / D2H on the tail stream
+      if (k >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == B200AT_OK)
+        rc = enqueue_view(h, make_view(h, vw * (int)S, vw, 2), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l,
+                          h->hp_src + i0, VIEW_FRONT);
       launches += l;
       if (rc == B200AT_OK && cudaEventRecord(h->ev_front[vw], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
       if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
@@ -1102,9 +1140,11 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
         if (cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
         if (rc == B200AT_OK)
           rc = enqueue_view_part(h, make_view(h, vb * (int)S, vb, 2), VIEW_BACK, mb, cs, h->hp_out + (size_t)ib * mt, h->hp_out_count + ib,
-                                 h->hp_counters + (size_t)kb * CNT_N * kMaxChunks, &l);
+                                 h->hp_counters + (size_t)kb * CNT_N * kMaxChunks, &l, h->tail_stream, h->ev_decoded[vb]);
         launches += l;
+        // the staged frames are dead once the decoder has run (the tail does not read them)
         if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[kb % nslots], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK && cudaEventRecord(h->ev_tail[vb], h->tail_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
       }
       continue;
     }
@@ -1118,6 +1158,10 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
   cudaError_t es = cudaStreamSynchronize(h->own_stream);
+  if (pipe) {
+    const cudaError_t es2 = cudaStreamSynchronize(h->tail_stream);
+    if (es == cudaSuccess) es = es2;
+  }
   if (nstreams == 2) {
     const cudaError_t es2 = cudaStreamSynchronize(h->lane_stream);
     if (es == cudaSuccess) es = es2;

@@ -119,7 +119,6 @@ struct Tune {
   int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
   int decode_ctas;    // persistent decode CTAs per SM
   int qf_mc;          // quad fit, one-warp bins: several clusters per CTA in phase lockstep (shared instruction stream)
-  int qf_net;         // quad fit sort: register bitonic networks instead of odd-even transposition + serial merge
   float qf_scale;     // scales the persistent grid of every quad-fit bin
   int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
 };

@@ -159,37 +159,16 @@ __device__ __forceinline__ void cta_sync() {
 // O(n log^2 n) of a bitonic network, one barrier per pass.  Inlined: the address space of the buffers (shared or global)
 // is known at every call site.
 // The sorted sequence ends in `a`.
-// NET: the ITEMS outputs of a thread are produced without a dependent chain of shared-memory loads: it reads the next ITEMS
-// keys of both runs at once, takes min(A[k], B[ITEMS-1-k]) -- the ITEMS smallest of the union, a bitonic sequence -- and sorts
-// them with a register bitonic-merge network (log2(ITEMS) compare-exchange stages); the initial in-register sort is a bitonic
-// network instead of odd-even transposition.  (ncu: the serial merge's dependent loads made sort_keys 30-45 % of the multi-warp
-// bins' time, half of it short-scoreboard stalls.)
-template <int THREADS, int ITEMS, bool NET>
+// (Tried and measured slower on B200: register bitonic networks for the per-thread sort and for the merge step -- reading the
+// next ITEMS keys of both runs at once and merging min(A[k], B[ITEMS-1-k]) -- instead of the serial merge: +2 % quad-fit time.)
+template <int THREADS, int ITEMS>
 __device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n, int tid) {
   constexpr unsigned long long INF = ~0ull;
   for (int base = tid * ITEMS; base < n; base += THREADS * ITEMS) {
     unsigned long long r[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) r[k] = (base + k < n) ? a[base + k] : INF;
-    if (NET) {
-#pragma unroll
-      for (int kk = 2; kk <= ITEMS; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-#pragma unroll
-          for (int i = 0; i < ITEMS; i++) {
-            const int l = i ^ j;
-            if (l > i) {
-              const bool up = (i & kk) == 0;
-              const unsigned long long x = r[i], y = r[l];
-              const bool sw = up ? (y < x) : (x < y);
-              r[i] = sw ? y : x;
-              r[l] = sw ? x : y;
-            }
-          }
-        }
-      }
-    } else {
+    {
 #pragma unroll
       for (int pass = 0; pass < ITEMS; pass++) {
 #pragma unroll
@@ -222,32 +201,6 @@ __device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long l
           hi = mid;
       }
       int ia = lo, ib = diag - lo;
-      if (NET) {
-        unsigned long long ra[ITEMS], rb[ITEMS];
-#pragma unroll
-        for (int k = 0; k < ITEMS; k++) {
-          ra[k] = ia + k < na ? src[a0 + ia + k] : INF;
-          rb[k] = ib + k < nb ? src[b0 + ib + k] : INF;
-        }
-        unsigned long long r[ITEMS];
-#pragma unroll
-        for (int k = 0; k < ITEMS; k++) r[k] = ra[k] < rb[ITEMS - 1 - k] ? ra[k] : rb[ITEMS - 1 - k];
-#pragma unroll
-        for (int j = ITEMS >> 1; j > 0; j >>= 1) {
-#pragma unroll
-          for (int i = 0; i < ITEMS; i++) {
-            if ((i & j) == 0) {
-              const unsigned long long x = r[i], y = r[i + j];
-              r[i] = x < y ? x : y;
-              r[i + j] = x < y ? y : x;
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < ITEMS; k++)
-          if (ob + k < b1) dst[ob + k] = r[k];
-        continue;
-      }
       unsigned long long va = ia < na ? src[a0 + ia] : INF, vb = ib < nb ? src[b0 + ib] : INF;
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {
@@ -433,7 +386,7 @@ struct QfSmem {
 // of a CTA walk through the phases TOGETHER (block barriers at the phase boundaries, rejected clusters idle instead of
 // leaving).  The kernel is ~80 KB of straight-line code per cluster; warps that sit in the same phase share the instruction
 // lines they fetch, warps in unrelated phases (18 independent one-warp CTAs per SM) thrash the 32 KB instruction cache.
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB, bool NET>
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB>
 __global__ void __launch_bounds__(THREADS * CPB, MINB) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
                                                      const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
                                                      unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
@@ -558,12 +511,12 @@ __global__ void __launch_bounds__(THREADS * CPB, MINB) k_quadfit(Geo g, FitParam
         if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
       }
       cta_sync<THREADS>();
-      sort_keys<THREADS, ITEMS, NET>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz, tid);
+      sort_keys<THREADS, ITEMS>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz, tid);
     } else {
       for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
       cta_sync<THREADS>();
       // scratch for the merge passes: the (not yet used) error area
-      sort_keys<THREADS, ITEMS, NET>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
+      sort_keys<THREADS, ITEMS>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
     }
 
     QF_PHASE();
@@ -970,11 +923,11 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
 #undef QF_DROP
 #undef QF_PHASE
 
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB, bool NET>
-static void launch_bin_t(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB = 1>
+static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
   const Geo &g = ws.g;
   constexpr size_t smem = QfSmem<NCAP, MODE, CH>::BYTES * CPB;
-  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, NET>;
+  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB>;
   // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute; the persistent grid is sized to
   // the number of CTAs that are resident at once
   static int ctas_per_sm[64] = {};
@@ -990,14 +943,6 @@ static void launch_bin_t(const Workspace &ws, int bin, double scale, int sms, co
   const int grid = std::max(1, (int)(sms * ctas_per_sm[dev] * scale + 0.5));
   kern<<<grid, THREADS * CPB, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec, ws.quads,
                                     ws.counters, ct, at_Wp(g));
-}
-
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB = 1>
-static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
-  if (ws.tune.qf_net)
-    launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, true>(ws, bin, scale, sms, ct, st);
-  else
-    launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, false>(ws, bin, scale, sms, ct, st);
 }
 
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {

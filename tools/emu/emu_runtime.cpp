@@ -428,6 +428,11 @@ cudaError_t cudaStreamCreate(cudaStream_t *s) {
 }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { return cudaStreamCreate(s); }
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { return cudaStreamCreate(s); }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) {
+  *lo = 0;
+  *hi = -5;
+  return cudaSuccess;
+}
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }

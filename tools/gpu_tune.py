@@ -17,13 +17,13 @@ import torch  # noqa: E402
 
 from isaac_ros_apriltag_b200 import capi, synth  # noqa: E402
 
-ALL_ON = "ccl_sweep=1,cluster_eager=2,decode_split=1,qf_mc=1,qf_keys23=1"
-DEVICE_CONFIGS = ["", "qf_net=1", "qf_net=1,qf_keys23=1", ALL_ON, ALL_ON + ",qf_net=1", ""]
-# host entry point: (knobs, sparse staging, sub-batch, streams, pipelined fetch)
-HOST_CONFIGS = [("", 0, 16, 1, 0), (ALL_ON, 0, 16, 1, 0),
-                (ALL_ON, 1, 16, 1, 0), (ALL_ON, 1, 32, 1, 0), (ALL_ON, 1, 64, 1, 0),
-                (ALL_ON, 1, 16, 1, 1), (ALL_ON, 1, 32, 1, 1), (ALL_ON, 1, 64, 1, 1), (ALL_ON, 1, 24, 1, 1), (ALL_ON, 1, 48, 1, 1),
-                (ALL_ON + ",qf_net=1", 1, 32, 1, 1), (ALL_ON + ",qf_net=1", 1, 64, 1, 1), ("", 1, 32, 1, 1)]
+ALL_OFF = "thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,qf_mc=0,qf_keys23=0"   # the round-1 kernels
+ALL_ON = ""                                                                               # library defaults
+DEVICE_CONFIGS = [ALL_OFF, "", "thr_early=1", ALL_OFF]
+# host entry point: (knobs, sparse staging, sub-batch (0 = library default), streams, pipelined fetch, ramp)
+HOST_CONFIGS = [(ALL_OFF, 0, 16, 1, 0, 0), ("", 0, 16, 1, 0, 0), ("", 1, 64, 1, 0, 0),
+                ("", 1, 32, 1, 1, 0), ("", 1, 64, 1, 1, 0), ("", 1, 32, 1, 1, 1), ("", 1, 48, 1, 1, 1), ("", 1, 64, 1, 1, 1), ("", 1, 96, 1, 1, 1),
+                ("", 1, 128, 1, 1, 1), ("", -1, 0, 1, -1, -1)]
 
 
 def emit(**kw):
@@ -121,13 +121,20 @@ def main():
             emit(event="device_subbatched", sub=sub, error=repr(e))
     # ---- host path: staging mode x sub-batch size x knobs ----
     host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
-    for tune, sparse_on, sub_i, streams_i, pipe_i in HOST_CONFIGS:
+    for tune, sparse_on, sub_i, streams_i, pipe_i, ramp_i in HOST_CONFIGS:
         mode, sub, streams = str(sparse_on), str(sub_i), str(streams_i)
         try:
-            os.environ["B200AT_SPARSE_H2D"] = mode
-            os.environ["B200AT_HOST_SUB"] = sub
+            for k in ("B200AT_SPARSE_H2D", "B200AT_HOST_SUB", "B200AT_HOST_STREAMS", "B200AT_HOST_PIPE", "B200AT_HOST_RAMP"):
+                os.environ.pop(k, None)
+            if sparse_on >= 0:
+                os.environ["B200AT_SPARSE_H2D"] = mode
+            if sub_i > 0:
+                os.environ["B200AT_HOST_SUB"] = sub
             os.environ["B200AT_HOST_STREAMS"] = streams
-            os.environ["B200AT_HOST_PIPE"] = str(pipe_i)
+            if pipe_i >= 0:
+                os.environ["B200AT_HOST_PIPE"] = str(pipe_i)
+            if ramp_i >= 0:
+                os.environ["B200AT_HOST_RAMP"] = str(ramp_i)
             det = make(tune)
             det.detect_host(host)
             t0 = time.perf_counter()
@@ -136,12 +143,13 @@ def main():
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 4
             c = det.counters()
-            emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), pipe=pipe_i,
+            emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), pipe=pipe_i, ramp=ramp_i,
                  ms_per_step=dt * 1e3, fps=B / dt, h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
             det.close()
         except Exception as e:
             emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), streams=int(streams), pipe=pipe_i, error=repr(e))
     os.environ.pop("B200AT_HOST_PIPE", None)
+    os.environ.pop("B200AT_HOST_RAMP", None)
     os.environ.pop("B200AT_SPARSE_H2D", None)
     os.environ.pop("B200AT_HOST_SUB", None)
     os.environ.pop("B200AT_HOST_STREAMS", None)

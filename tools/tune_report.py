@@ -25,5 +25,5 @@ for r in host:
     if "error" in r:
         print(f"| {r['tune']} | {r.get('sparse')} | {r.get('host_sub')} | {r.get('streams')} | error: {r['error'][:80]} |")
         continue
-    print(f"| {r.get('tag', '')} {r['tune']} | {'sparse' if r['sparse'] else 'full copy'} | {r['host_sub']} | {r['streams']} | {r.get('pipe', 0)} | {r['ms_per_step']:.2f} | {r['fps']:.0f} | "
+    print(f"| {r.get('tag', '')} {r['tune']} | {'sparse' if r['sparse'] else 'full copy'} | {r['host_sub']} | {r['streams']} | {r.get('pipe', 0)}{'+ramp' if r.get('ramp', 0) == 1 else ''} | {r['ms_per_step']:.2f} | {r['fps']:.0f} | "
           f"{r['h2d_bytes'] / 256 / 1e6:.2f} | {'ok' if r['parity'] and r['status'] == 0 else 'MISMATCH'} |")
