@@ -42,6 +42,7 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
 constexpr bool kSparseHostPathDefault = true;
 constexpr int kHostStreamsDefault = 1;
 constexpr bool kHostPipeDefault = true;
+constexpr int kHostCopyStreamsDefault = 1;
 constexpr int kTuneDefaultThrEarly = 0;
 constexpr int kTuneDefaultCclSweep = 1;
 constexpr int kTuneDefaultQfMc = 1;
@@ -115,6 +116,8 @@ struct cuAprilTagsHandle_st {
   uint32_t stage_sub = 0;  // frames per staging slot
   cudaStream_t own_stream = nullptr;   // compute stream of the host path
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream2 = nullptr;  // second DMA queue: the row-strided copies of the sparse path do not saturate PCIe from one
+  cudaEvent_t ev_copied2[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_consumed[3] = {nullptr, nullptr, nullptr};
   // pipelined sparse host path: fetches of sub-batch k on their own stream while sub-batch k+1 is being detected
   cudaStream_t fetch_stream = nullptr, tail_stream = nullptr;  // (high priority: few, latency-bound CTAs)
@@ -207,6 +210,9 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->fetch_stream) cudaStreamDestroy(h->fetch_stream);
   if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
+  for (int i = 0; i < 3; i++)
+    if (h->ev_copied2[i]) cudaEventDestroy(h->ev_copied2[i]);
   for (int i = 0; i < kQuadAux; i++) {
     if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
     if (h->ws.ev_join[i]) cudaEventDestroy(h->ws.ev_join[i]);
@@ -961,6 +967,9 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   if (!h->copy_stream) {
     h->stage_pitch = (row + 255) & ~(size_t)255;
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+    for (int i = 0; i < 3; i++)
+      if (cudaEventCreateWithFlags(&h->ev_copied2[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     {
       // the fetch and tail kernels are a handful of latency-bound CTAs (PCIe reads; one thread per detection): at the highest
       // priority they get the first free SM slots instead of queueing behind the next sub-batch's full grids
@@ -1057,6 +1066,10 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   const int row_step = sparse ? g.f : 1;
   const int rows_dma = 1 + (g.H - 1) / row_step;
   static const bool sparse_debug = getenv("B200AT_SPARSE_DEBUG") != nullptr;  // poison the slot: an unfetched row cannot go unnoticed
+  // DMA queues: frames alternate between two copy streams (two copy engines) when B200AT_HOST_COPY_STREAMS=2
+  int ncopy = kHostCopyStreamsDefault;
+  if (const char *es = getenv("B200AT_HOST_COPY_STREAMS")) ncopy = atoi(es);
+  if (ncopy != 2 || (sparse && sparse_debug)) ncopy = 1;
   uint64_t dma_bytes = 0;
   // uniform sub-batches (a ramped schedule -- small first/last sub-batches to shorten pipeline fill and drain -- was
   // measured and did not pay: the tiny sub-batches cost more in launch overhead than they save)
@@ -1100,13 +1113,14 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     uint8_t *slot_base = h->d_stage + (size_t)slot * h->stage_sub * h->stage_pitch * g.H;
     cudaError_t e = cudaSuccess;
     if (k >= nslots) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
+    if (k >= nslots && ncopy == 2 && e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream2, h->ev_consumed[slot], 0);
     if (sparse && sparse_debug && e == cudaSuccess) e = cudaMemsetAsync(slot_base, 0xA5, (size_t)m * h->stage_pitch * g.H, h->copy_stream);
     for (uint32_t j = 0; j < m && e == cudaSuccess; j++) {
       if (!frames[i0 + j].ptr || frames[i0 + j].pitch < row) return fail(B200AT_ERR_INVALID_ARG);
       uint8_t *dst = slot_base + (size_t)j * h->stage_pitch * g.H;
       // rows 0, f, 2f, ... (all rows on the full-copy path)
       e = cudaMemcpy2DAsync(dst, h->stage_pitch * row_step, frames[i0 + j].ptr, frames[i0 + j].pitch * row_step, row, rows_dma,
-                            cudaMemcpyHostToDevice, h->copy_stream);
+                            cudaMemcpyHostToDevice, (ncopy == 2 && (j & 1)) ? h->copy_stream2 : h->copy_stream);
       dma_bytes += (uint64_t)row * rows_dma;
       dframes[j].ptr = dst;
       dframes[j].pitch = h->stage_pitch;
@@ -1114,6 +1128,10 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     cudaStream_t cs = (nstreams == 2 && slot) ? h->lane_stream : h->own_stream;
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[slot], h->copy_stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied[slot], 0);
+    if (ncopy == 2) {
+      if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied2[slot], h->copy_stream2);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied2[slot], 0);
+    }
     if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
     int l = 0;
     if (pipe) {
@@ -1167,6 +1185,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (es == cudaSuccess) es = es2;
   }
   cudaStreamSynchronize(h->copy_stream);
+  cudaStreamSynchronize(h->copy_stream2);
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != B200AT_OK) return rc;
   if (es != cudaSuccess) {

@@ -21,9 +21,8 @@ ALL_OFF = "thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,qf_mc=0,qf_key
 ALL_ON = ""                                                                               # library defaults
 DEVICE_CONFIGS = [ALL_OFF, "", "thr_early=1", ALL_OFF]
 # host entry point: (knobs, sparse staging, sub-batch (0 = library default), streams, pipelined fetch, ramp)
-HOST_CONFIGS = [(ALL_OFF, 0, 16, 1, 0, 0), ("", 0, 16, 1, 0, 0), ("", 1, 64, 1, 0, 0),
-                ("", 1, 32, 1, 1, 0), ("", 1, 64, 1, 1, 0), ("", 1, 32, 1, 1, 1), ("", 1, 48, 1, 1, 1), ("", 1, 64, 1, 1, 1), ("", 1, 96, 1, 1, 1),
-                ("", 1, 128, 1, 1, 1), ("", -1, 0, 1, -1, -1)]
+HOST_CONFIGS = [("", -1, 0, 1, -1, -1, 1), ("", -1, 0, 1, -1, -1, 2), ("", 1, 64, 1, 0, 0, 2), ("", 1, 32, 1, 1, 1, 2), ("", 1, 48, 1, 1, 1, 2),
+                ("", 1, 32, 1, 0, 0, 2), ("", 0, 16, 1, 0, 0, 2), ("", 0, 32, 1, 0, 0, 2), ("", -1, 0, 1, -1, -1, 1)]
 
 
 def emit(**kw):
@@ -121,7 +120,7 @@ def main():
             emit(event="device_subbatched", sub=sub, error=repr(e))
     # ---- host path: staging mode x sub-batch size x knobs ----
     host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
-    for tune, sparse_on, sub_i, streams_i, pipe_i, ramp_i in HOST_CONFIGS:
+    for tune, sparse_on, sub_i, streams_i, pipe_i, ramp_i, ncopy_i in HOST_CONFIGS:
         mode, sub, streams = str(sparse_on), str(sub_i), str(streams_i)
         try:
             for k in ("B200AT_SPARSE_H2D", "B200AT_HOST_SUB", "B200AT_HOST_STREAMS", "B200AT_HOST_PIPE", "B200AT_HOST_RAMP"):
@@ -131,6 +130,7 @@ def main():
             if sub_i > 0:
                 os.environ["B200AT_HOST_SUB"] = sub
             os.environ["B200AT_HOST_STREAMS"] = streams
+            os.environ["B200AT_HOST_COPY_STREAMS"] = str(ncopy_i)
             if pipe_i >= 0:
                 os.environ["B200AT_HOST_PIPE"] = str(pipe_i)
             if ramp_i >= 0:
@@ -143,13 +143,14 @@ def main():
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 4
             c = det.counters()
-            emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), pipe=pipe_i, ramp=ramp_i,
+            emit(event="host", tag=args.tag, tune=tune or "default", sparse=int(c["sparse_h2d"]), host_sub=int(sub), streams=int(streams), pipe=pipe_i, ramp=ramp_i, copy_streams=ncopy_i,
                  ms_per_step=dt * 1e3, fps=B / dt, h2d_bytes=int(c["h2d_bytes"]), input_bytes=int(host.nbytes), parity=same(r, base), status=det.status())
             det.close()
         except Exception as e:
             emit(event="host", tune=tune or "default", sparse=int(mode), host_sub=int(sub), streams=int(streams), pipe=pipe_i, error=repr(e))
     os.environ.pop("B200AT_HOST_PIPE", None)
     os.environ.pop("B200AT_HOST_RAMP", None)
+    os.environ.pop("B200AT_HOST_COPY_STREAMS", None)
     os.environ.pop("B200AT_SPARSE_H2D", None)
     os.environ.pop("B200AT_HOST_SUB", None)
     os.environ.pop("B200AT_HOST_STREAMS", None)

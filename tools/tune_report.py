@@ -19,11 +19,11 @@ for r in rows:
     if r.get("event") == "device_subbatched":
         print(f"\ndevice path in calls of {r.get('sub')} frames: {r.get('ms_per_256', r.get('error'))} ms per 256 frames")
 print()
-print("| knobs (host entry point) | staging | sub-batch | streams | pipelined fetch | ms/step | frames/s | H2D MB/frame | parity |")
+print("| knobs (host entry point) | staging | sub-batch | compute/copy streams | pipelined fetch | ms/step | frames/s | H2D MB/frame | parity |")
 print("|---|---|---|---|---|---|---|---|---|")
 for r in host:
     if "error" in r:
         print(f"| {r['tune']} | {r.get('sparse')} | {r.get('host_sub')} | {r.get('streams')} | error: {r['error'][:80]} |")
         continue
-    print(f"| {r.get('tag', '')} {r['tune']} | {'sparse' if r['sparse'] else 'full copy'} | {r['host_sub']} | {r['streams']} | {r.get('pipe', 0)}{'+ramp' if r.get('ramp', 0) == 1 else ''} | {r['ms_per_step']:.2f} | {r['fps']:.0f} | "
+    print(f"| {r.get('tag', '')} {r['tune']} | {'sparse' if r['sparse'] else 'full copy'} | {r['host_sub']} | {r['streams']}/{r.get('copy_streams', 1)} | {r.get('pipe', 0)}{'+ramp' if r.get('ramp', 0) == 1 else ''} | {r['ms_per_step']:.2f} | {r['fps']:.0f} | "
           f"{r['h2d_bytes'] / 256 / 1e6:.2f} | {'ok' if r['parity'] and r['status'] == 0 else 'MISMATCH'} |")
