@@ -381,7 +381,7 @@ def main():
                        "clusters_per_batch": int(counters["clusters"]), "quads_per_batch": int(counters["quads"])},
             "clocks": clocks, "e2e": e2e, "e2e_modes": {k: {kk: v[kk] for kk in ("value", "h2d_bytes_per_step")} for k, v in e2e_modes.items()},
             "gpu_launches": int(launches), "roofline": roofline,
-            "stages_ms_per_step": stage_ms, "stages_note": "stage times from unpipelined extra steps (sum > ms_per_step: in the timed steps the stages of different frame chunks overlap)", "stages_gbs": stage_gbs, "dominant_stage": dominant, "latency_720p": latency,
+            "stages_ms_per_step": stage_ms, "stages_note": "stage times from extra steps with CUDA events between the stages (outside the timed region)", "stages_gbs": stage_gbs, "dominant_stage": dominant, "latency_720p": latency,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
     if world > 1:
