@@ -59,6 +59,7 @@ Tune parse_tune() {
   t.cluster_eager = kTuneDefaultClusterEager;
   t.decode_split = kTuneDefaultDecodeSplit;
   t.decode_ctas = 4;
+  t.decode_pair = 0;
   t.qf_scale = 1.0f;
   t.qf_keys23 = kTuneDefaultQfKeys23;
   t.qf_mc = kTuneDefaultQfMc;
@@ -80,6 +81,7 @@ Tune parse_tune() {
     else if (k == "cluster_eager") t.cluster_eager = (int)v;
     else if (k == "decode_split") t.decode_split = (int)v;
     else if (k == "decode_ctas") t.decode_ctas = (int)v;
+    else if (k == "decode_pair") t.decode_pair = (int)v;
     else if (k == "qf_scale") t.qf_scale = (float)v;
     else if (k == "qf_keys23") t.qf_keys23 = (int)v;
     else if (k == "qf_mc") t.qf_mc = (int)v;
@@ -1107,6 +1109,22 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   }
   std::vector<b200AprilTagsFrame_t> dframes(S);
   int launches = 0;
+  // B200AT_HOST_TRACE=1: timestamps (CUDA events) of every sub-batch's DMA / FRONT / FETCH / BACK / tail, printed to stderr
+  static const bool trace = getenv("B200AT_HOST_TRACE") != nullptr;
+  struct Mark {
+    const char *what;
+    uint32_t k;
+    cudaEvent_t ev;
+  };
+  std::vector<Mark> marks;
+  auto mark = [&](const char *what, uint32_t k, cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    marks.push_back({what, k, ev});
+  };
+  mark("t0", 0, h->own_stream);
   for (uint32_t k = 0; k < nsub && rc == B200AT_OK; k++) {
     const uint32_t i0 = sub_start[k], m = sub_len[k];
     const int slot = (int)(k % nslots);
@@ -1115,6 +1133,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (k >= nslots) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
     if (k >= nslots && ncopy == 2 && e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream2, h->ev_consumed[slot], 0);
     if (sparse && sparse_debug && e == cudaSuccess) e = cudaMemsetAsync(slot_base, 0xA5, (size_t)m * h->stage_pitch * g.H, h->copy_stream);
+    mark("dma_begin", k, h->copy_stream);
     for (uint32_t j = 0; j < m && e == cudaSuccess; j++) {
       if (!frames[i0 + j].ptr || frames[i0 + j].pitch < row) return fail(B200AT_ERR_INVALID_ARG);
       uint8_t *dst = slot_base + (size_t)j * h->stage_pitch * g.H;
@@ -1126,6 +1145,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       dframes[j].pitch = h->stage_pitch;
     }
     cudaStream_t cs = (nstreams == 2 && slot) ? h->lane_stream : h->own_stream;
+    mark("dma_end", k, h->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[slot], h->copy_stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied[slot], 0);
     if (ncopy == 2) {
@@ -1139,14 +1159,17 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       const int vw = (int)(k & 1);
       // the view's previous user (sub-batch k-2) may still have its reconcile / pose / D2H on the tail stream
       if (k >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      mark("front_begin", k, cs);
       if (rc == B200AT_OK)
         rc = enqueue_view(h, make_view(h, vw * (int)S, vw, 2), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l,
                           h->hp_src + i0, VIEW_FRONT);
       launches += l;
+      mark("front_end", k, cs);
       if (rc == B200AT_OK && cudaEventRecord(h->ev_front[vw], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
       if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
       if (rc == B200AT_OK) rc = enqueue_view_part(h, make_view(h, vw * (int)S, vw, 2), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
       launches += l;
+      mark("fetch_end", k, h->fetch_stream);
       if (rc == B200AT_OK && cudaEventRecord(h->ev_fetched[vw], h->fetch_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
       for (int last = 0; last < 2 && rc == B200AT_OK; last++) {
         // BACK of the previous sub-batch; after the last FRONT also the BACK of this one
@@ -1156,12 +1179,15 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
         const int vb = (int)(kb & 1);
         const uint32_t ib = sub_start[kb], mb = sub_len[kb];
         if (cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        mark("back_begin", kb, cs);
         if (rc == B200AT_OK)
           rc = enqueue_view_part(h, make_view(h, vb * (int)S, vb, 2), VIEW_BACK, mb, cs, h->hp_out + (size_t)ib * mt, h->hp_out_count + ib,
                                  h->hp_counters + (size_t)kb * CNT_N * kMaxChunks, &l, h->tail_stream, h->ev_decoded[vb]);
         launches += l;
         // the staged frames are dead once the decoder has run (the tail does not read them)
         if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[kb % nslots], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        mark("back_end", kb, cs);
+        mark("tail_end", kb, h->tail_stream);
         if (rc == B200AT_OK && cudaEventRecord(h->ev_tail[vb], h->tail_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
       }
       continue;
@@ -1173,6 +1199,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
                         h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l, false, sparse ? h->hp_src + i0 : nullptr);
     launches += l;
+    mark("compute_end", k, cs);
     if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
   cudaError_t es = cudaStreamSynchronize(h->own_stream);
@@ -1186,6 +1213,15 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   }
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(h->copy_stream2);
+  if (trace && !marks.empty()) {
+    fprintf(stderr, "[b200apriltags] host-path trace: n=%u S=%u sparse=%d pipe=%d (ms since the call's first event)\n", n, S, (int)sparse, (int)pipe);
+    for (size_t i = 1; i < marks.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[0].ev, marks[i].ev);
+      fprintf(stderr, "  %-12s k=%-3u len=%-3u %8.3f\n", marks[i].what, marks[i].k, sub_len[marks[i].k], ms);
+    }
+    for (auto &mk : marks) cudaEventDestroy(mk.ev);
+  }
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != B200AT_OK) return rc;
   if (es != cudaSuccess) {

@@ -114,9 +114,10 @@ struct FitParams {
 // change results, only how the work is mapped; tools/gpu_tune.py sweeps them on the GPU.
 struct Tune {
   int thr_early;      // k_threshold4: pixel loads issued before the tile min/max staging barrier
-  int ccl_sweep;      // k_ccl_tile_sweep (warp per tile, label inheritance) instead of k_ccl_tile; 2 = without TMA staging
+  int ccl_sweep;      // k_ccl_tile_sweep (warp per tile, label inheritance) instead of k_ccl_tile; 2 = without TMA staging; 3 = ILP variant
   int cluster_eager;  // k_cluster_pass: 1 = unconditional label loads + speculative offset load; 2 = k_cluster_pass4 (4 px / thread)
   int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
+  int decode_pair;    // k_refine: two short edges per pass (lanes 0-15 / 16-31)
   int decode_ctas;    // persistent decode CTAs per SM
   int qf_mc;          // quad fit, one-warp bins: several clusters per CTA in phase lockstep (shared instruction stream)
   float qf_scale;     // scales the persistent grid of every quad-fit bin

@@ -235,7 +235,9 @@ constexpr int SWEEP_TILES = 4;
 constexpr int TBYTES = TPITCH * (TH + 1);              // one staged tile + halo row
 constexpr int TSLOT = (TBYTES + 127) & ~127;           // 128-byte aligned slots
 
-template <bool USE_TMA>
+// ILP variant (ccl_sweep=3): the three bytes of the next row are loaded while the current row is processed (the row above
+// stays in registers), and the final flatten chases four rows' pointers interleaved instead of one find after the other.
+template <bool USE_TMA, bool ILP>
 __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                                       uint32_t *__restrict__ csize, int Wp,
                                                                       const __grid_constant__ CUtensorMap tmap) {
@@ -298,11 +300,33 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
   const int x = x0 + lane;
   const int rows = min(TH, g.Hd - y0);
   uint32_t plab = NONE;  // label of the pixel above (row ly - 1) in this lane's column
+  // ILP: bytes of the row above (u*) and of the current row (c*) live in registers; the next row (n*) is in flight
+  int ul = 0, uc = 0, ur = 0, cl = 0, cc = 0, cr = 0;
+  if (ILP) {
+    const uint8_t *t0 = t + lane + TOFF;
+    ul = t0[-1];
+    uc = t0[0];
+    ur = t0[1];
+    cl = t0[TPITCH - 1];
+    cc = t0[TPITCH];
+    cr = t0[TPITCH + 1];
+  }
   for (int ly = 0; ly < rows; ly++) {
     const int y = y0 + ly;
     const uint8_t *tr = t + (ly + 1) * TPITCH + lane + TOFF, *tu = tr - TPITCH;
     Nb n = {false, false, false, false};
-    if (x < g.Wd) n = ccl_links(tr[0], tr[-1], tu[0], tu[-1], tu[1], x, y, g.Wd);
+    int nl = 0, nc = 0, nr = 0;
+    if (ILP) {
+      if (ly + 1 < rows) {  // (row ly + 2 of the staged tile exists: it has TH + 1 rows)
+        nl = tr[TPITCH - 1];
+        nc = tr[TPITCH];
+        nr = tr[TPITCH + 1];
+      }
+      if (x < g.Wd) n = ccl_links(cc, cl, uc, ul, ur, x, y, g.Wd);
+    } else {
+      if (x < g.Wd) n = ccl_links(tr[0], tr[-1], tu[0], tu[-1], tu[1], x, y, g.Wd);
+    }
+    const int vcur = ILP ? cc : (int)tr[0];
     const unsigned ml = __ballot_sync(0xffffffffu, n.L && lane > 0);  // bit x: x is linked to x-1 inside the tile
     const unsigned upto = (2u << lane) - 1u;                          // lanes 0..lane (lane 31: all ones)
     const int rs = 31 - __clz(~ml & upto);                            // first lane of my run (bit 0 of ~ml is always set)
@@ -334,21 +358,70 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     if (c1 != NONE && c1 != rl) unite_s(L, c1, rl);
     if (c2 != NONE && c2 != rl) unite_s(L, c2, rl);
     if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
-    if (lane == rs && x < g.Wd && tr[0] != 127) atomicAdd(&cnt[rl], (uint32_t)__popc(run_mask));
+    if (lane == rs && x < g.Wd && vcur != 127) atomicAdd(&cnt[rl], (uint32_t)__popc(run_mask));
     plab = rl;
+    if (ILP) {
+      ul = cl;
+      uc = cc;
+      ur = cr;
+      cl = nl;
+      cc = nc;
+      cr = nr;
+    }
   }
   __syncwarp();
   uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
   uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
   // flatten inside the tile; counts collected at merged labels move to their final local root
-  for (int ly = 0; ly < rows; ly++) {
-    const int i = ly * TW + lane;
-    const uint32_t r = find_s(L, i);
-    if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
-    const uint32_t c = cnt[i];  // non-zero only at labels; a non-root entry is touched by this lane alone
-    if (r != (uint32_t)i && c) {
-      atomicAdd(&cnt[r], c);
-      cnt[i] = 0;
+  if (ILP) {
+    for (int ly0 = 0; ly0 < rows; ly0 += 4) {
+      // find_s of four rows, step by step and interleaved: four independent shared-memory chases in flight per lane
+      uint32_t a[4], p[4];
+      bool done[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        a[u] = (uint32_t)(min(ly0 + u, rows - 1) * TW + lane);
+        p[u] = L[a[u]];
+        done[u] = p[u] == a[u];
+      }
+      while (!(done[0] && done[1] && done[2] && done[3])) {
+        uint32_t gp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) gp[u] = done[u] ? p[u] : L[p[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (!done[u]) {
+            if (gp[u] != p[u]) L[a[u]] = gp[u];  // path splitting, as find_s
+            a[u] = p[u];
+            p[u] = gp[u];
+            done[u] = p[u] == a[u];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ly = ly0 + u;
+        if (ly >= rows) break;
+        const int i = ly * TW + lane;
+        const uint32_t r = a[u];
+        if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
+        const uint32_t c = cnt[i];
+        if (r != (uint32_t)i && c) {
+          atomicAdd(&cnt[r], c);
+          cnt[i] = 0;
+        }
+      }
+    }
+  } else {
+    for (int ly = 0; ly < rows; ly++) {
+      const int i = ly * TW + lane;
+      const uint32_t r = find_s(L, i);
+      if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
+      const uint32_t c = cnt[i];  // non-zero only at labels; a non-root entry is touched by this lane alone
+      if (r != (uint32_t)i && c) {
+        atomicAdd(&cnt[r], c);
+        cnt[i] = 0;
+      }
     }
   }
   __syncwarp();
@@ -464,10 +537,14 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
   if (ws.tune.ccl_sweep) {
     dim3 gs((gt.x + SWEEP_TILES - 1) / SWEEP_TILES, gt.y, gt.z);
-    if (ws.use_tma && ws.tune.ccl_sweep != 2)
-      k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+    if (ws.use_tma && ws.tune.ccl_sweep == 3)
+      k_ccl_tile_sweep<true, true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+    else if (ws.tune.ccl_sweep == 3)
+      k_ccl_tile_sweep<false, true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+    else if (ws.use_tma && ws.tune.ccl_sweep != 2)
+      k_ccl_tile_sweep<true, false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
     else
-      k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+      k_ccl_tile_sweep<false, false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
   } else if (ws.use_tma) {
     k_ccl_tile<true><<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
   } else {

@@ -245,12 +245,76 @@ __device__ __forceinline__ void rescale_quad(const FitParams &fp, const QuadRec 
 }
 
 // ---- a12: refine_edges (one warp; every lane ends with the same refined corners) ----
+// one sample point of an edge: search along the normal for the strongest step (returns 0 if no pixel pair qualified)
+__device__ __forceinline__ int refine_sample(const FrameDesc &fd, int width, int height, int bpp, int o1, int o2, bool is_bgr, float pax,
+                                             float pay, float pbx, float pby, double nx, double ny, int s, int nsamples, double range,
+                                             int nsteps, double *bestx, double *besty) {
+  double alpha = (1.0 + s) / (nsamples + 1);
+  double x0 = alpha * pax + (1 - alpha) * pbx;
+  double y0 = alpha * pay + (1 - alpha) * pby;
+  double Mn = 0, Mcount = 0;
+  // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
+  for (int k0 = 0; k0 < nsteps; k0 += 8) {
+    int g1[8], g2[8];
+    bool okk[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int k = k0 + u;
+      const double n = -range + 0.25 * k;
+      const double grange = 1;
+      const int x1 = (int)(x0 + (n + grange) * nx);
+      const int y1 = (int)(y0 + (n + grange) * ny);
+      const int x2 = (int)(x0 + (n - grange) * nx);
+      const int y2 = (int)(y0 + (n - grange) * ny);
+      okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) && !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
+      // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
+      g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
+      g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (!okk[u] || g1[u] < g2[u]) continue;
+      const double n = -range + 0.25 * (k0 + u);
+      const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
+      Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
+      Mcount += weight;
+    }
+  }
+  if (Mcount == 0) return 0;
+  double n0 = Mn / Mcount;
+  *bestx = x0 + n0 * nx;
+  *besty = y0 + n0 * ny;
+  return 1;
+}
+
+// line through the refined sample points of one edge: centroid + normal direction (float trigonometry as upstream)
+__device__ __forceinline__ void refine_line(double Mx, double My, double Mxx, double Mxy, double Myy, double N, double line[4]) {
+  double Ex = Mx / N, Ey = My / N;
+  double Cxx = Mxx / N - Ex * Ex;
+  double Cxy = Mxy / N - Ex * Ey;
+  double Cyy = Myy / N - Ey * Ey;
+  // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
+  float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
+  double normal_theta = .5 * th;
+  float nth = (float)normal_theta;
+  line[0] = Ex;
+  line[1] = Ey;
+  line[2] = (double)(float)cos((double)nth);
+  line[3] = (double)(float)sin((double)nth);
+}
+
+// PAIR: two consecutive edges that both take the minimum of 16 samples (edges shorter than 136 px: nearly every candidate
+// quad) are processed in ONE pass, lanes 0-15 on the first, lanes 16-31 on the second; each half accumulates its own edge's
+// samples in sample order, so every sum is formed exactly as in the one-edge-at-a-time loop.
+template <bool PAIR>
 __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
                                                   int o2, bool is_bgr, bool reversed, int lane, float p[4][2]) {
   double lines[4][4];
   const double range = (double)(fp.quad_decimate + 1.0f);
   const int nsteps = (int)floor(2.0 * range / 0.25) + 1;
-#pragma unroll 1
+  double enx[4], eny[4];
+  int ens[4];
+#pragma unroll
   for (int edge = 0; edge < 4; edge++) {
     const int a = edge, b = (edge + 1) & 3;
     double nx = (double)(p[b][1] - p[a][1]);
@@ -262,56 +326,25 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
       nx = -nx;
       ny = -ny;
     }
-    const int nsamples = max(16, (int)(mag / 8));
-    double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
-    for (int s0 = 0; s0 < nsamples; s0 += 32) {
-      const int s = s0 + lane;
+    enx[edge] = nx;
+    eny[edge] = ny;
+    ens[edge] = max(16, (int)(mag / 8));
+  }
+#pragma unroll
+  for (int e0 = 0; e0 < 4; e0 += 2) {
+    if (PAIR && ens[e0] == 16 && ens[e0 + 1] == 16) {
+      const bool hi = lane >= 16;
+      const int a1 = e0 + 1, b1 = (e0 + 2) & 3;
+      const float pax = hi ? p[a1][0] : p[e0][0], pay = hi ? p[a1][1] : p[e0][1];
+      const float pbx = hi ? p[b1][0] : p[a1][0], pby = hi ? p[b1][1] : p[a1][1];
+      const double nx = hi ? enx[a1] : enx[e0], ny = hi ? eny[a1] : eny[e0];
       double bestx = 0, besty = 0;
-      int has = 0;
-      if (s < nsamples) {
-        double alpha = (1.0 + s) / (nsamples + 1);
-        double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
-        double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
-        double Mn = 0, Mcount = 0;
-        // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
-        for (int k0 = 0; k0 < nsteps; k0 += 8) {
-          int g1[8], g2[8];
-          bool okk[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int k = k0 + u;
-            const double n = -range + 0.25 * k;
-            const double grange = 1;
-            const int x1 = (int)(x0 + (n + grange) * nx);
-            const int y1 = (int)(y0 + (n + grange) * ny);
-            const int x2 = (int)(x0 + (n - grange) * nx);
-            const int y2 = (int)(y0 + (n - grange) * ny);
-            okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
-                     !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
-            // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
-            g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
-            g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            if (!okk[u] || g1[u] < g2[u]) continue;
-            const double n = -range + 0.25 * (k0 + u);
-            const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
-            Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
-            Mcount += weight;
-          }
-        }
-        if (Mcount != 0) {
-          double n0 = Mn / Mcount;
-          bestx = x0 + n0 * nx;
-          besty = y0 + n0 * ny;
-          has = 1;
-        }
-      }
-      const int cnt = min(32, nsamples - s0);
-      for (int k = 0; k < cnt; k++) {
-        const int h = __shfl_sync(0xffffffffu, has, k);
-        const double bx = shfl_d(bestx, k), by = shfl_d(besty, k);
+      const int has = refine_sample(fd, width, height, bpp, o1, o2, is_bgr, pax, pay, pbx, pby, nx, ny, lane & 15, 16, range, nsteps, &bestx, &besty);
+      double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+      for (int k = 0; k < 16; k++) {
+        const int src = (lane & 16) + k;
+        const int h = __shfl_sync(0xffffffffu, has, src);
+        const double bx = shfl_d(bestx, src), by = shfl_d(besty, src);
         if (h) {
           Mx += bx;
           My += by;
@@ -321,19 +354,43 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
           N++;
         }
       }
+      double ln[4];
+      refine_line(Mx, My, Mxx, Mxy, Myy, N, ln);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        lines[e0][j] = shfl_d(ln[j], 0);
+        lines[e0 + 1][j] = shfl_d(ln[j], 16);
+      }
+      continue;
     }
-    double Ex = Mx / N, Ey = My / N;
-    double Cxx = Mxx / N - Ex * Ex;
-    double Cxy = Mxy / N - Ex * Ey;
-    double Cyy = Myy / N - Ey * Ey;
-    // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
-    float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
-    double normal_theta = .5 * th;
-    float nth = (float)normal_theta;
-    lines[edge][0] = Ex;
-    lines[edge][1] = Ey;
-    lines[edge][2] = (double)(float)cos((double)nth);
-    lines[edge][3] = (double)(float)sin((double)nth);
+#pragma unroll 1
+    for (int edge = e0; edge < e0 + 2; edge++) {
+      const int a = edge, b = (edge + 1) & 3;
+      const int nsamples = ens[edge];
+      double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+      for (int s0 = 0; s0 < nsamples; s0 += 32) {
+        const int s = s0 + lane;
+        double bestx = 0, besty = 0;
+        int has = 0;
+        if (s < nsamples)
+          has = refine_sample(fd, width, height, bpp, o1, o2, is_bgr, p[a][0], p[a][1], p[b][0], p[b][1], enx[edge], eny[edge], s, nsamples, range,
+                              nsteps, &bestx, &besty);
+        const int cnt = min(32, nsamples - s0);
+        for (int k = 0; k < cnt; k++) {
+          const int h = __shfl_sync(0xffffffffu, has, k);
+          const double bx = shfl_d(bestx, k), by = shfl_d(besty, k);
+          if (h) {
+            Mx += bx;
+            My += by;
+            Mxx += bx * bx;
+            Mxy += bx * by;
+            Myy += by * by;
+            N++;
+          }
+        }
+      }
+      refine_line(Mx, My, Mxx, Mxy, Myy, N, lines[edge]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -545,7 +602,7 @@ __global__ void __launch_bounds__(DT, 4) k_decode(Geo g, FitParams fp, DecodeFam
     const bool reversed = q0.reversed_border != 0;
     float p[4][2];
     rescale_quad(fp, q0, p);
-    if (fp.refine_edges) refine_edges_warp(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
+    if (fp.refine_edges) refine_edges_warp<false>(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
     if (lane == 0) {
       QuadRec qr = q0;
       for (int j = 0; j < 4; j++) {
@@ -668,7 +725,7 @@ __global__ void __launch_bounds__(256) k_fetch_rows(Geo g, const FrameDesc *__re
   if (lane == 0 && copied) atomicAdd(&counters[CNT_FETCHED], copied);
 }
 
-template <bool MARK, int MINB>
+template <bool MARK, int MINB, bool PAIR>
 __global__ void __launch_bounds__(DT, MINB) k_refine(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
                                                const QuadRec *__restrict__ quads, QuadRec *__restrict__ quads_refined,
                                                double *__restrict__ quad_H, const uint32_t *__restrict__ counters,
@@ -685,7 +742,7 @@ __global__ void __launch_bounds__(DT, MINB) k_refine(Geo g, FitParams fp, Decode
     const bool reversed = q0.reversed_border != 0;
     float p[4][2];
     rescale_quad(fp, q0, p);
-    if (fp.refine_edges) refine_edges_warp(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
+    if (fp.refine_edges) refine_edges_warp<PAIR>(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
     if (lane == 0) {
       QuadRec qr = q0;
       for (int j = 0; j < 4; j++) {
@@ -770,7 +827,10 @@ int launch_sparse_back(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
   const int ctas = sm_count() * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
   const dim3 gf((g.H + 7) / 8, nframes);
-  k_refine<true, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
+  if (ws.tune.decode_pair)
+    k_refine<true, 4, true><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
+  else
+    k_refine<true, 4, false><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
   if (!nofetch) k_fetch_rows<<<gf, 256, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
   k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
   return 4;
@@ -786,12 +846,15 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
   const int sms = sm_count();
   const int ctas = sms * (ws.tune.decode_ctas > 0 ? ws.tune.decode_ctas : 4);
   if (ws.tune.decode_split == 2 && ws.quad_H) {  // register budget of 6 CTAs (24 warps) per SM
-    k_refine<false, 6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    k_refine<false, 6, false><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
     k_decode_bits<6><<<sms * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
     return 3;
   }
   if (ws.tune.decode_split && ws.quad_H) {
-    k_refine<false, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    if (ws.tune.decode_pair)
+      k_refine<false, 4, true><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    else
+      k_refine<false, 4, false><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
     k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
     return 3;
   }
