@@ -245,6 +245,113 @@ __device__ __forceinline__ void rescale_quad(const FitParams &fp, const QuadRec 
 }
 
 // ---- a12: refine_edges (one warp; every lane ends with the same refined corners) ----
+__device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
+                                                  int o2, bool is_bgr, bool reversed, int lane, float p[4][2]) {
+  double lines[4][4];
+  const double range = (double)(fp.quad_decimate + 1.0f);
+  const int nsteps = (int)floor(2.0 * range / 0.25) + 1;
+#pragma unroll 1
+  for (int edge = 0; edge < 4; edge++) {
+    const int a = edge, b = (edge + 1) & 3;
+    double nx = (double)(p[b][1] - p[a][1]);
+    double ny = (double)(-p[b][0] + p[a][0]);
+    double mag = sqrt(nx * nx + ny * ny);
+    nx /= mag;
+    ny /= mag;
+    if (reversed) {
+      nx = -nx;
+      ny = -ny;
+    }
+    const int nsamples = max(16, (int)(mag / 8));
+    double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+    for (int s0 = 0; s0 < nsamples; s0 += 32) {
+      const int s = s0 + lane;
+      double bestx = 0, besty = 0;
+      int has = 0;
+      if (s < nsamples) {
+        double alpha = (1.0 + s) / (nsamples + 1);
+        double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
+        double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
+        double Mn = 0, Mcount = 0;
+        // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
+        for (int k0 = 0; k0 < nsteps; k0 += 8) {
+          int g1[8], g2[8];
+          bool okk[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int k = k0 + u;
+            const double n = -range + 0.25 * k;
+            const double grange = 1;
+            const int x1 = (int)(x0 + (n + grange) * nx);
+            const int y1 = (int)(y0 + (n + grange) * ny);
+            const int x2 = (int)(x0 + (n - grange) * nx);
+            const int y2 = (int)(y0 + (n - grange) * ny);
+            okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
+                     !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
+            // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
+            g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
+            g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (!okk[u] || g1[u] < g2[u]) continue;
+            const double n = -range + 0.25 * (k0 + u);
+            const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
+            Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
+            Mcount += weight;
+          }
+        }
+        if (Mcount != 0) {
+          double n0 = Mn / Mcount;
+          bestx = x0 + n0 * nx;
+          besty = y0 + n0 * ny;
+          has = 1;
+        }
+      }
+      const int cnt = min(32, nsamples - s0);
+      for (int k = 0; k < cnt; k++) {
+        const int h = __shfl_sync(0xffffffffu, has, k);
+        const double bx = shfl_d(bestx, k), by = shfl_d(besty, k);
+        if (h) {
+          Mx += bx;
+          My += by;
+          Mxx += bx * bx;
+          Mxy += bx * by;
+          Myy += by * by;
+          N++;
+        }
+      }
+    }
+    double Ex = Mx / N, Ey = My / N;
+    double Cxx = Mxx / N - Ex * Ex;
+    double Cxy = Mxy / N - Ex * Ey;
+    double Cyy = Myy / N - Ey * Ey;
+    // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
+    float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
+    double normal_theta = .5 * th;
+    float nth = (float)normal_theta;
+    lines[edge][0] = Ex;
+    lines[edge][1] = Ey;
+    lines[edge][2] = (double)(float)cos((double)nth);
+    lines[edge][3] = (double)(float)sin((double)nth);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
+    double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
+    double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
+    double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
+    double det = A00 * A11 - A10 * A01;
+    if (fabs(det) > 0.001) {
+      double W00 = A11 / det, W01 = -A01 / det;
+      double L0 = W00 * B0 + W01 * B1;
+      p[i][0] = (float)(lines[i][0] + L0 * A00);
+      p[i][1] = (float)(lines[i][1] + L0 * A10);
+    }
+  }
+}
+
+// ---- a12, opt-in variant (decode_pair=1): refine_edges with two short edges per pass ----
 // one sample point of an edge: search along the normal for the strongest step (returns 0 if no pixel pair qualified)
 __device__ __forceinline__ int refine_sample(const FrameDesc &fd, int width, int height, int bpp, int o1, int o2, bool is_bgr, float pax,
                                              float pay, float pbx, float pby, double nx, double ny, int s, int nsamples, double range,
@@ -307,7 +414,7 @@ __device__ __forceinline__ void refine_line(double Mx, double My, double Mxx, do
 // quad) are processed in ONE pass, lanes 0-15 on the first, lanes 16-31 on the second; each half accumulates its own edge's
 // samples in sample order, so every sum is formed exactly as in the one-edge-at-a-time loop.
 template <bool PAIR>
-__device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
+__device__ __forceinline__ void refine_edges_warp_pair(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
                                                   int o2, bool is_bgr, bool reversed, int lane, float p[4][2]) {
   double lines[4][4];
   const double range = (double)(fp.quad_decimate + 1.0f);
@@ -602,7 +709,7 @@ __global__ void __launch_bounds__(DT, 4) k_decode(Geo g, FitParams fp, DecodeFam
     const bool reversed = q0.reversed_border != 0;
     float p[4][2];
     rescale_quad(fp, q0, p);
-    if (fp.refine_edges) refine_edges_warp<false>(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
+    if (fp.refine_edges) refine_edges_warp(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
     if (lane == 0) {
       QuadRec qr = q0;
       for (int j = 0; j < 4; j++) {
@@ -742,7 +849,12 @@ __global__ void __launch_bounds__(DT, MINB) k_refine(Geo g, FitParams fp, Decode
     const bool reversed = q0.reversed_border != 0;
     float p[4][2];
     rescale_quad(fp, q0, p);
-    if (fp.refine_edges) refine_edges_warp<PAIR>(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
+    if (fp.refine_edges) {
+      if (PAIR)
+        refine_edges_warp_pair<true>(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
+      else
+        refine_edges_warp(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
+    }
     if (lane == 0) {
       QuadRec qr = q0;
       for (int j = 0; j < 4; j++) {
