@@ -124,7 +124,7 @@ struct cuAprilTagsHandle_st {
   // pipelined sparse host path: fetches of sub-batch k on their own stream while sub-batch k+1 is being detected
   cudaStream_t fetch_stream = nullptr, tail_stream = nullptr;  // (high priority: few, latency-bound CTAs)
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fetched[2] = {nullptr, nullptr}, ev_decoded[2] = {nullptr, nullptr},
-              ev_tail[2] = {nullptr, nullptr};
+              ev_tail[2] = {nullptr, nullptr}, ev_backdone[2] = {nullptr, nullptr};
   uint32_t stage_slots = 0;
   FrameDesc *hp_frames = nullptr;
   FrameDesc *hp_src = nullptr;         // sparse host path: device-mapped addresses of the caller's frames
@@ -208,6 +208,7 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
     if (h->ev_fetched[i]) cudaEventDestroy(h->ev_fetched[i]);
     if (h->ev_decoded[i]) cudaEventDestroy(h->ev_decoded[i]);
     if (h->ev_tail[i]) cudaEventDestroy(h->ev_tail[i]);
+    if (h->ev_backdone[i]) cudaEventDestroy(h->ev_backdone[i]);
   }
   if (h->fetch_stream) cudaStreamDestroy(h->fetch_stream);
   if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
@@ -989,6 +990,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       if (cudaEventCreateWithFlags(&h->ev_fetched[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
       if (cudaEventCreateWithFlags(&h->ev_decoded[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
       if (cudaEventCreateWithFlags(&h->ev_tail[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
+      if (cudaEventCreateWithFlags(&h->ev_backdone[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     }
   }
   // Sparse staging (see k_decode.cu): with an integer quad_decimate f >= 2 the detector reads only every f-th row until the
@@ -1040,8 +1042,16 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   if (nstreams != 2 || 2 * S > h->max_batch) nstreams = 1;
   // Pipelined sparse path (B200AT_HOST_PIPE=0/1): the on-demand fetches of sub-batch k run on their own stream while the
   // compute stream already detects the quads of sub-batch k+1; needs two workspace views and three staging slots.
+  // B200AT_HOST_PIPE=2 (not yet measured; schedule derived from profiles/r02_host_path_trace.txt): FETCH(k) starts only after
+  // BACK(k-1), whose own second fetch otherwise competes with it for PCIe (BACK took 1.3-1.5 ms instead of ~0.4), and every
+  // sub-batch has its own counters block, so that FRONT(k) need not wait for the tail (reconcile / pose / D2H) of k-2.
   bool pipe = kHostPipeDefault;
-  if (const char *es = getenv("B200AT_HOST_PIPE")) pipe = atoi(es) != 0;
+  int pipe_level = kHostPipeDefault ? 1 : 0;
+  if (const char *es = getenv("B200AT_HOST_PIPE")) {
+    pipe_level = atoi(es);
+    pipe = pipe_level != 0;
+  }
+  const bool pipe2 = pipe_level == 2;
   if (!sparse || 2 * S > h->max_batch) pipe = false;
   if (pipe) nstreams = 1;
   const uint32_t nslots = pipe ? 3 : 2;
@@ -1157,39 +1167,49 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     if (pipe) {
       // compute stream: FRONT(k), BACK(k-1), FRONT(k+1), ...; fetch stream: FETCH(k) between FRONT(k) and BACK(k)
       const int vw = (int)(k & 1);
+      auto view_of = [&](uint32_t kk) {
+        Workspace v = make_view(h, (int)(kk & 1) * (int)S, (int)(kk & 1), 2);
+        if (pipe2) v.counters = h->ws.counters + (size_t)(kk % kMaxChunks) * CNT_N;  // FRONT(kk + 2) zeroes another block
+        return v;
+      };
       // the view's previous user (sub-batch k-2) may still have its reconcile / pose / D2H on the tail stream
-      if (k >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (!pipe2 && k >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
       mark("front_begin", k, cs);
       if (rc == B200AT_OK)
-        rc = enqueue_view(h, make_view(h, vw * (int)S, vw, 2), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l,
-                          h->hp_src + i0, VIEW_FRONT);
+        rc = enqueue_view(h, view_of(k), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l, h->hp_src + i0, VIEW_FRONT);
       launches += l;
       mark("front_end", k, cs);
       if (rc == B200AT_OK && cudaEventRecord(h->ev_front[vw], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      if (rc == B200AT_OK) rc = enqueue_view_part(h, make_view(h, vw * (int)S, vw, 2), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
-      launches += l;
-      mark("fetch_end", k, h->fetch_stream);
-      if (rc == B200AT_OK && cudaEventRecord(h->ev_fetched[vw], h->fetch_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      for (int last = 0; last < 2 && rc == B200AT_OK; last++) {
-        // BACK of the previous sub-batch; after the last FRONT also the BACK of this one
-        if (last == 0 && k == 0) continue;
-        if (last == 1 && k + 1 != nsub) break;
-        const uint32_t kb = last ? k : k - 1;
+      auto enqueue_fetch = [&]() {
+        if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK && pipe2 && k >= 1 && cudaStreamWaitEvent(h->fetch_stream, h->ev_backdone[vw ^ 1], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK) rc = enqueue_view_part(h, view_of(k), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
+        launches += l;
+        mark("fetch_end", k, h->fetch_stream);
+        if (rc == B200AT_OK && cudaEventRecord(h->ev_fetched[vw], h->fetch_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      };
+      auto enqueue_back = [&](uint32_t kb) {
         const int vb = (int)(kb & 1);
         const uint32_t ib = sub_start[kb], mb = sub_len[kb];
-        if (cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK && cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        // (level 2) the decoder overwrites the candidates / outputs that the tail of this view's previous user still reads
+        if (rc == B200AT_OK && pipe2 && kb >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
         mark("back_begin", kb, cs);
         if (rc == B200AT_OK)
-          rc = enqueue_view_part(h, make_view(h, vb * (int)S, vb, 2), VIEW_BACK, mb, cs, h->hp_out + (size_t)ib * mt, h->hp_out_count + ib,
+          rc = enqueue_view_part(h, view_of(kb), VIEW_BACK, mb, cs, h->hp_out + (size_t)ib * mt, h->hp_out_count + ib,
                                  h->hp_counters + (size_t)kb * CNT_N * kMaxChunks, &l, h->tail_stream, h->ev_decoded[vb]);
         launches += l;
         // the staged frames are dead once the decoder has run (the tail does not read them)
         if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[kb % nslots], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK && cudaEventRecord(h->ev_backdone[vb], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
         mark("back_end", kb, cs);
         mark("tail_end", kb, h->tail_stream);
         if (rc == B200AT_OK && cudaEventRecord(h->ev_tail[vb], h->tail_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      }
+      };
+      if (!pipe2) enqueue_fetch();
+      if (k >= 1) enqueue_back(k - 1);
+      if (pipe2) enqueue_fetch();
+      if (k + 1 == nsub) enqueue_back(k);  // after the last FRONT also the BACK of this sub-batch
       continue;
     }
     if (nstreams == 2)

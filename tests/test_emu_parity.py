@@ -114,11 +114,13 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
         assert a.tobytes() == b.tobytes()
     monkeypatch.delenv("B200AT_HOST_STREAMS")
     # pipelined: fetches of sub-batch k on their own stream, between FRONT(k) and BACK(k), three staging slots
-    monkeypatch.setenv("B200AT_HOST_PIPE", "1")
-    got4 = det.detect_host(frames)
-    assert det.counters()["sparse_h2d"] == 1
-    for a, b in zip(got4, want):
-        assert a.tobytes() == b.tobytes()
+    for level in ("1", "2"):  # 2 = fetch after the previous sub-batch's decode, per-sub-batch counters (opt-in schedule)
+        monkeypatch.setenv("B200AT_HOST_PIPE", level)
+        got4 = det.detect_host(frames)
+        c4 = det.counters()
+        assert c4["sparse_h2d"] == 1 and c4["detections"] == sum(len(x) for x in want)
+        for a, b in zip(got4, want):
+            assert a.tobytes() == b.tobytes()
     monkeypatch.delenv("B200AT_HOST_PIPE")
     monkeypatch.delenv("B200AT_HOST_SUB")
     # pageable (not device-mapped) frames fall back to the full copy

@@ -359,14 +359,17 @@ def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
     # pipelined sparse path: FRONT(k+1) on the compute stream while the fetch stream serves sub-batch k (three staging slots);
     # sub-batches of 1 and 2 frames so that the 6 frames exercise slot reuse
     monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
-    monkeypatch.setenv("B200AT_HOST_PIPE", "1")
-    for sub in ("1", "2"):
+    # (level 2 -- fetch after the previous sub-batch's decode, per-sub-batch counters -- is logic-checked under the emulator,
+    # tests/test_emu_parity.py; it joins this list once it has been measured and raced on a GPU)
+    for level, sub in (("1", "1"), ("1", "2")):
+        monkeypatch.setenv("B200AT_HOST_PIPE", level)
         monkeypatch.setenv("B200AT_HOST_SUB", sub)
         for _ in range(2):
             got4 = det.detect_host(host)
-            assert det.counters()["sparse_h2d"] == 1
+            c4 = det.counters()
+            assert c4["sparse_h2d"] == 1 and c4["detections"] == sum(len(x) for x in want)
             for i in range(n):
-                assert got4[i].tobytes() == want[i].tobytes(), (sub, i)
+                assert got4[i].tobytes() == want[i].tobytes(), (level, sub, i)
     monkeypatch.delenv("B200AT_HOST_PIPE")
     monkeypatch.delenv("B200AT_HOST_SUB")
     monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
