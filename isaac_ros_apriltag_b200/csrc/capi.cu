@@ -57,6 +57,7 @@ Tune parse_tune() {
   t.thr_early = kTuneDefaultThrEarly;
   t.ccl_sweep = kTuneDefaultCclSweep;
   t.cluster_eager = kTuneDefaultClusterEager;
+  t.ccl_flat = 0;
   t.decode_split = kTuneDefaultDecodeSplit;
   t.decode_ctas = 4;
   t.decode_pair = 0;
@@ -79,6 +80,7 @@ Tune parse_tune() {
     if (k == "thr_early") t.thr_early = (int)v;
     else if (k == "ccl_sweep") t.ccl_sweep = (int)v;
     else if (k == "cluster_eager") t.cluster_eager = (int)v;
+    else if (k == "ccl_flat") t.ccl_flat = (int)v;
     else if (k == "decode_split") t.decode_split = (int)v;
     else if (k == "decode_ctas") t.decode_ctas = (int)v;
     else if (k == "decode_pair") t.decode_pair = (int)v;

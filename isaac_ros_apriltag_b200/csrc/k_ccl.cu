@@ -531,6 +531,66 @@ __global__ void __launch_bounds__(256) k_ccl_mark(Geo g, const uint8_t *__restri
   *reinterpret_cast<uchar4 *>(thr2 + i) = make_uchar4(v[0], v[1], v[2], v[3]);
 }
 
+// Two-phase variant of flatten + mark (ccl_flat=1).  After the tile and border kernels every pixel points at a (former) tile
+// root, and only those carry a count.  Phase A: the former tile roots (csize != 0; ~5 % of the pixels) chase to their global
+// root, point at it directly and hand over their count.  Phase B: every pixel needs exactly ONE gather, lab[lab[p]], and the
+// size gate (k_ccl_mark) is applied in the same pass: lab and thr are read once instead of twice.
+__global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__ lab, uint32_t *__restrict__ csize, int Wp) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int fr = blockIdx.z;
+  if (x4 >= g.Wd) return;
+  const size_t fo = (size_t)fr * g.Hd * Wp;
+  uint32_t *L = lab + fo;
+  const uint32_t me0 = (uint32_t)(y * Wp + x4);
+  const uint4 cv = *reinterpret_cast<const uint4 *>(csize + fo + me0);
+  const uint32_t c[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (c[k] == 0 || x4 + k >= g.Wd) continue;
+    const uint32_t me = me0 + k;
+    uint32_t a = me, p = __ldcg(&L[a]);
+    while (p != a) {
+      a = p;
+      p = __ldcg(&L[a]);
+    }
+    if (a != me) {
+      __stcg(&L[me], a);
+      atomicAdd(&csize[fo + a], c[k]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatmark(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
+                                                      const uint32_t *__restrict__ csize, uint8_t *__restrict__ thr2, int Wp) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int fr = blockIdx.z;
+  if (x4 >= g.Wd) return;
+  const size_t fo = (size_t)fr * g.Hd * Wp;
+  uint32_t *L = lab + fo;
+  const uint32_t me0 = (uint32_t)(y * Wp + x4);
+  const uchar4 tv = *reinterpret_cast<const uchar4 *>(thr + fo + me0);
+  const uint4 pv = *reinterpret_cast<const uint4 *>(L + me0);
+  uint8_t v[4] = {tv.x, tv.y, tv.z, tv.w};
+  const uint32_t p[4] = {pv.x, pv.y, pv.z, pv.w};
+  uint32_t r[4], c[4];
+  bool live[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    // AprilRobotics never connects 127 pixels (singletons); padding columns are ignored
+    live[k] = v[k] != 127 && x4 + k < g.Wd;
+    r[k] = live[k] ? __ldcg(&L[p[k]]) : me0 + k;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) c[k] = live[k] ? __ldcg(&csize[fo + r[k]]) : 25u;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (c[k] < 25) v[k] = 127;
+  *reinterpret_cast<uint4 *>(L + me0) = make_uint4(r[0], r[1], r[2], r[3]);
+  *reinterpret_cast<uchar4 *>(thr2 + fo + me0) = make_uchar4(v[0], v[1], v[2], v[3]);
+}
+
 int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
   const int Wp = at_Wp(g);
@@ -552,6 +612,11 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   }
   k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
   dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);
+  if (ws.tune.ccl_flat) {
+    k_ccl_roots<<<gp, 256, 0, s>>>(g, ws.lab, ws.csize, Wp);
+    k_ccl_flatmark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
+    return 4;
+  }
   k_ccl_flatten<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
   k_ccl_mark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
   return 4;

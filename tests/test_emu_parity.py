@@ -131,3 +131,19 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
     for a, b in zip(got2, want):
         assert a.tobytes() == b.tobytes()
     det.close()
+
+
+@pytest.mark.parametrize("tune", ["thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,qf_mc=0,qf_keys23=0",  # the round-1 kernels
+                                  "ccl_sweep=2", "ccl_sweep=3", "ccl_flat=1", "cluster_eager=1", "thr_early=1", "thr_early=2",
+                                  "decode_split=0", "decode_split=2", "decode_pair=1", "qf_mc=0,qf_keys23=0", "qf_scale=0.5,decode_ctas=2",
+                                  "ccl_sweep=3,ccl_flat=1,decode_pair=1,thr_early=1"])
+def test_emulated_kernel_variants(pu, tune, monkeypatch):
+    """Every kernel variant behind B200AT_TUNE (csrc/detector.h, struct Tune) stays bit-exact against the oracle, whether or not it
+    is the current default -- the measured-slower and the not-yet-measured ones included, so that none of them rots."""
+    monkeypatch.setenv("B200AT_TUNE", tune)
+    frames = np.stack([small_frame(50, 400, 300, [("tag36h11", 7), ("tag36h11", 8)], side=(60, 120)),
+                       small_frame(51, 400, 300, [("tag36h11", 9)], side=(150, 200))])
+    rep = []
+    res, gd = pu.compare_stages(frames, "mono8", ("tag36h11",), report=rep)
+    assert_exact(res, rep)
+    assert sorted(int(i) for i in gd[0]["id"]) == [7, 8] and list(gd[1]["id"]) == [9]
