@@ -120,7 +120,8 @@ struct Tune {
   int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
   int decode_pair;    // k_refine: two short edges per pass (lanes 0-15 / 16-31)
   int decode_ctas;    // persistent decode CTAs per SM
-  int qf_mc;          // quad fit, one-warp bins: several clusters per CTA in phase lockstep (shared instruction stream)
+  int qf_mc;          // quad fit, one-warp bins: 1 = several clusters per CTA in phase lockstep (shared instruction stream);
+                      // 2 = same with more warps for the 128 bin; 3 = occupancy variants instead (k_quad.cu, launch_quadfit)
   float qf_scale;     // scales the persistent grid of every quad-fit bin
   int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
 };

@@ -973,7 +973,17 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
     launch_bin<128, 1024, QF_KEYS, 8, 64, 8>(ws, 3, qscale, sms, ct, ws.aux[3]);
     launch_bin<64, 512, QF_KEYS, 8, 32, 16>(ws, 2, qscale, sms, ct, ws.aux[4]);
   }
-  if (ws.tune.qf_mc) {
+  if (ws.tune.qf_mc == 2) {
+    // (not measured yet) the smallest bin with 7 clusters per CTA and the register budget of 3 CTAs per SM: 21 warps instead of 16
+    launch_bin<32, 256, QF_ALL, 8, 1, 2, 6>(ws, 1, qscale, sms, ct, ws.aux[5]);
+    launch_bin<32, 128, QF_ALL, 4, 1, 3, 7>(ws, 0, qscale, sms, ct, ws.aux[6]);
+  } else if (ws.tune.qf_mc == 3) {
+    // (not measured yet) occupancy instead of lockstep: the 256 bin as two-warp clusters with the moments in the L2 scratch
+    // (4 KB instead of 16 KB of shared memory, 64 registers: 32 warps per SM instead of 12), the 128 bin one cluster per
+    // CTA with the register budget of 28 CTAs per SM (72 registers without spills; shared memory then allows 23 warps)
+    launch_bin<64, 256, QF_KEYS, 4, 20, 16>(ws, 1, qscale, sms, ct, ws.aux[5]);
+    launch_bin<32, 128, QF_ALL, 4, 1, 28>(ws, 0, qscale, sms, ct, ws.aux[6]);
+  } else if (ws.tune.qf_mc) {
     // one-warp clusters, several per CTA in phase lockstep (MINB = CTAs per SM the register budget is sized for)
     launch_bin<32, 256, QF_ALL, 8, 1, 2, 6>(ws, 1, qscale, sms, ct, ws.aux[5]);      // n <= 256: 6 clusters per CTA
     launch_bin<32, 128, QF_ALL, 4, 1, 2, 8>(ws, 0, qscale, sms, ct, ws.aux[6]);      // n <= 128: 8 clusters per CTA
