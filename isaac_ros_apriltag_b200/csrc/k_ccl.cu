@@ -431,6 +431,127 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
   }
 }
 
+// Occupancy variant of the row sweep (ccl_sweep=4, not measured yet).  The sweep is latency-bound at 20 warps per SM (ncu: 26 %
+// warps active, 50 % issue), and what limits the warps is shared memory: 10.4 KB per tile.  Here the tile is not staged at all
+// -- a lane reads its column's bytes straight from global memory, four rows ahead of their use, neighbours by shuffle, the two
+// halo columns by lanes 0 / 31 -- and the per-label pixel counts are 16-bit halves of shared words (a tile has 1024 pixels):
+// 6 KB per tile, 36 warps per SM.
+__global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep_direct(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
+                                                                             uint32_t *__restrict__ csize, int Wp) {
+  __shared__ uint32_t s_L[SWEEP_TILES][TH * TW];
+  __shared__ uint32_t s_cnt[SWEEP_TILES][TH * TW / 2];  // two 16-bit counts per word
+  const int fr = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int x0 = (blockIdx.x * SWEEP_TILES + wid) * TW, y0 = blockIdx.y * TH;
+  if (x0 >= g.Wd) return;  // (no block-wide barrier in this kernel)
+  const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
+  uint32_t *L = s_L[wid], *cnt = s_cnt[wid];
+  for (int i = lane; i < TH * TW / 2; i += 32) cnt[i] = 0;
+  const uint32_t NONE = 0xffffffffu;
+  const int x = x0 + lane;
+  const int rows = min(TH, g.Hd - y0);
+  // bytes of image row y in this lane's column and, on lanes 0 / 31, of the halo column; outside the image 127 (never links)
+  const int hx = lane == 0 ? x0 - 1 : x0 + TW;  // halo column of the edge lanes
+  const bool has_halo = (lane == 0 || lane == 31) && hx >= 0 && hx < g.Wd;
+  auto load_group = [&](int ly0) -> uint2 {  // rows ly0 .. ly0+3 of the tile, packed: .x centre bytes, .y halo bytes
+    uint32_t c = 0x7f7f7f7fu, hh = 0x7f7f7f7fu;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int y = y0 + ly0 + u;
+      if (y >= 0 && y < g.Hd && ly0 + u < rows) {
+        if (x < g.Wd) c = (c & ~(0xffu << (8 * u))) | ((uint32_t)img[(size_t)y * Wp + x] << (8 * u));
+        if (has_halo) hh = (hh & ~(0xffu << (8 * u))) | ((uint32_t)img[(size_t)y * Wp + hx] << (8 * u));
+      }
+    }
+    return make_uint2(c, hh);
+  };
+  // the row above the tile
+  int uc = 127, uh = 127;
+  if (y0 > 0) {
+    if (x < g.Wd) uc = img[(size_t)(y0 - 1) * Wp + x];
+    if (has_halo) uh = img[(size_t)(y0 - 1) * Wp + hx];
+  }
+  uint2 cur = load_group(0);
+  uint32_t plab = NONE;  // label of the pixel above (row ly - 1) in this lane's column
+  __syncwarp();
+  for (int ly0 = 0; ly0 < rows; ly0 += 4) {
+    const uint2 nxt = load_group(ly0 + 4);  // in flight while this group is processed
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int ly = ly0 + u;
+      if (ly >= rows) break;
+      const int y = y0 + ly;
+      const int cc = (int)((cur.x >> (8 * u)) & 0xffu), ch = (int)((cur.y >> (8 * u)) & 0xffu);
+      // neighbours by shuffle; the edge lanes take the halo column
+      int cl = __shfl_up_sync(0xffffffffu, cc, 1), cr = __shfl_down_sync(0xffffffffu, cc, 1);
+      int ul = __shfl_up_sync(0xffffffffu, uc, 1), ur = __shfl_down_sync(0xffffffffu, uc, 1);
+      if (lane == 0) {
+        cl = ch;
+        ul = uh;
+      }
+      if (lane == 31) {
+        cr = ch;
+        ur = uh;
+      }
+      Nb n = {false, false, false, false};
+      if (x < g.Wd) n = ccl_links(cc, cl, uc, ul, ur, x, y, g.Wd);
+      const unsigned ml = __ballot_sync(0xffffffffu, n.L && lane > 0);  // bit x: x is linked to x-1 inside the tile
+      const unsigned upto = (2u << lane) - 1u;
+      const int rs = 31 - __clz(~ml & upto);
+      const unsigned above = ~ml & ~upto;
+      const unsigned run_mask = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << rs) - 1u);
+      const uint32_t pl_l = __shfl_up_sync(0xffffffffu, plab, 1), pl_r = __shfl_down_sync(0xffffffffu, plab, 1);
+      uint32_t c1 = NONE, c2 = NONE, c3 = NONE;
+      if (ly > 0) {
+        if (n.U) c1 = plab;
+        if (n.UL && lane > 0) c2 = pl_l;
+        if (n.UR && lane < TW - 1) c3 = pl_r;
+      }
+      uint32_t rl = min(c1, min(c2, c3));
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t2 = __shfl_up_sync(0xffffffffu, rl, d);
+        if (lane - d >= rs) rl = min(rl, t2);
+      }
+      const int rlast = above ? (__ffs(above) - 2) : 31;
+      rl = __shfl_sync(0xffffffffu, rl, rlast);
+      const int i = ly * TW + lane;
+      if (rl == NONE) rl = (uint32_t)(ly * TW + rs);
+      L[i] = rl;
+      __syncwarp();
+      if (c1 != NONE && c1 != rl) unite_s(L, c1, rl);
+      if (c2 != NONE && c2 != rl) unite_s(L, c2, rl);
+      if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
+      if (lane == rs && x < g.Wd && cc != 127) atomicAdd(&cnt[rl >> 1], (uint32_t)__popc(run_mask) << (16 * (rl & 1)));
+      plab = rl;
+      uc = cc;
+      uh = ch;
+    }
+    cur = nxt;
+  }
+  __syncwarp();
+  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
+  uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
+  for (int ly = 0; ly < rows; ly++) {
+    const int i = ly * TW + lane;
+    const uint32_t r = find_s(L, i);
+    if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
+    const uint32_t c = (cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu;  // non-zero only at labels
+    if (r != (uint32_t)i && c) {
+      atomicAdd(&cnt[r >> 1], c << (16 * (r & 1)));
+      atomicSub(&cnt[i >> 1], c << (16 * (i & 1)));  // (the other half of the word may be in use: no plain store)
+    }
+  }
+  __syncwarp();
+  // 127 pixels are singletons; the pixel values are read once more (L2-resident)
+  for (int ly = 0; ly < rows; ly++) {
+    if (x >= g.Wd) break;
+    const int i = ly * TW + lane;
+    const uint8_t v = img[(size_t)(y0 + ly) * Wp + x];
+    szf[(size_t)(y0 + ly) * Wp + x] = (v == 127) ? 1u : ((cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+  }
+}
+
 // one thread per tile-border pixel: top row (TW), left column rows 1..TH-1, right column rows 1..TH-1
 __global__ void __launch_bounds__(128) k_ccl_border(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab, int Wp) {
   const int fr = blockIdx.z;
@@ -597,7 +718,9 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
   if (ws.tune.ccl_sweep) {
     dim3 gs((gt.x + SWEEP_TILES - 1) / SWEEP_TILES, gt.y, gt.z);
-    if (ws.use_tma && ws.tune.ccl_sweep == 3)
+    if (ws.tune.ccl_sweep == 4)
+      k_ccl_tile_sweep_direct<<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
+    else if (ws.use_tma && ws.tune.ccl_sweep == 3)
       k_ccl_tile_sweep<true, true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
     else if (ws.tune.ccl_sweep == 3)
       k_ccl_tile_sweep<false, true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
