@@ -41,7 +41,7 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
 // Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
 constexpr bool kSparseHostPathDefault = true;
 constexpr int kHostStreamsDefault = 1;
-constexpr bool kHostPipeDefault = true;
+constexpr int kHostPipeDefault = 3;
 constexpr int kHostCopyStreamsDefault = 1;
 constexpr int kTuneDefaultThrEarly = 0;
 constexpr int kTuneDefaultCclSweep = 1;
@@ -1044,16 +1044,17 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   if (nstreams != 2 || 2 * S > h->max_batch) nstreams = 1;
   // Pipelined sparse path (B200AT_HOST_PIPE=0/1): the on-demand fetches of sub-batch k run on their own stream while the
   // compute stream already detects the quads of sub-batch k+1; needs two workspace views and three staging slots.
-  // B200AT_HOST_PIPE=2 (not yet measured; schedule derived from profiles/r02_host_path_trace.txt): FETCH(k) starts only after
-  // BACK(k-1), whose own second fetch otherwise competes with it for PCIe (BACK took 1.3-1.5 ms instead of ~0.4), and every
-  // sub-batch has its own counters block, so that FRONT(k) need not wait for the tail (reconcile / pose / D2H) of k-2.
-  bool pipe = kHostPipeDefault;
-  int pipe_level = kHostPipeDefault ? 1 : 0;
-  if (const char *es = getenv("B200AT_HOST_PIPE")) {
-    pipe_level = atoi(es);
-    pipe = pipe_level != 0;
-  }
+  // Levels (B200AT_HOST_PIPE): 1 = FETCH(k) is enqueued right after FRONT(k) (the schedule measured in round 2).  The trace
+  // of that schedule (profiles/r02_host_path_trace.txt) shows BACK(k-1) taking 1.3-1.5 ms instead of ~0.4: it starts together
+  // with FETCH(k), and its own second fetch queues behind that on PCIe.  3 (default) = FETCH(k) additionally waits for
+  // BACK(k-1): one more ordering constraint on the same dataflow, so every execution it allows was already allowed by level 1.
+  // 2 = 3 plus a counters block per sub-batch, so that FRONT(k) need not wait for the tail (reconcile / pose / D2H) of k-2
+  // (drops an ordering constraint: emulator-checked, to be raced on a GPU before it becomes the default).
+  int pipe_level = kHostPipeDefault;
+  if (const char *es = getenv("B200AT_HOST_PIPE")) pipe_level = atoi(es);
+  bool pipe = pipe_level != 0;
   const bool pipe2 = pipe_level == 2;
+  const bool fetch_late = pipe_level >= 2;
   if (!sparse || 2 * S > h->max_batch) pipe = false;
   if (pipe) nstreams = 1;
   const uint32_t nslots = pipe ? 3 : 2;
@@ -1184,7 +1185,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       if (rc == B200AT_OK && cudaEventRecord(h->ev_front[vw], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
       auto enqueue_fetch = [&]() {
         if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        if (rc == B200AT_OK && pipe2 && k >= 1 && cudaStreamWaitEvent(h->fetch_stream, h->ev_backdone[vw ^ 1], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK && fetch_late && k >= 1 && cudaStreamWaitEvent(h->fetch_stream, h->ev_backdone[vw ^ 1], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
         if (rc == B200AT_OK) rc = enqueue_view_part(h, view_of(k), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
         launches += l;
         mark("fetch_end", k, h->fetch_stream);
@@ -1208,9 +1209,9 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
         mark("tail_end", kb, h->tail_stream);
         if (rc == B200AT_OK && cudaEventRecord(h->ev_tail[vb], h->tail_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
       };
-      if (!pipe2) enqueue_fetch();
+      if (!fetch_late) enqueue_fetch();
       if (k >= 1) enqueue_back(k - 1);
-      if (pipe2) enqueue_fetch();
+      if (fetch_late) enqueue_fetch();
       if (k + 1 == nsub) enqueue_back(k);  // after the last FRONT also the BACK of this sub-batch
       continue;
     }

@@ -114,7 +114,7 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
         assert a.tobytes() == b.tobytes()
     monkeypatch.delenv("B200AT_HOST_STREAMS")
     # pipelined: fetches of sub-batch k on their own stream, between FRONT(k) and BACK(k), three staging slots
-    for level in ("1", "2"):  # 2 = fetch after the previous sub-batch's decode, per-sub-batch counters (opt-in schedule)
+    for level in ("1", "2", "3"):  # 3 (default) = fetch after the previous sub-batch's decode; 2 = 3 + per-sub-batch counters (opt-in)
         monkeypatch.setenv("B200AT_HOST_PIPE", level)
         got4 = det.detect_host(frames)
         c4 = det.counters()

@@ -359,9 +359,10 @@ def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
     # pipelined sparse path: FRONT(k+1) on the compute stream while the fetch stream serves sub-batch k (three staging slots);
     # sub-batches of 1 and 2 frames so that the 6 frames exercise slot reuse
     monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
-    # (level 2 -- fetch after the previous sub-batch's decode, per-sub-batch counters -- is logic-checked under the emulator,
-    # tests/test_emu_parity.py; it joins this list once it has been measured and raced on a GPU)
-    for level, sub in (("1", "1"), ("1", "2")):
+    # level 3 (default): as 1, but the first fetch of sub-batch k also waits for the decode of k-1.  (Level 2 -- 3 plus a
+    # counters block per sub-batch -- is logic-checked under the emulator, tests/test_emu_parity.py; it joins this list once it
+    # has been raced on a GPU.)
+    for level, sub in (("1", "1"), ("1", "2"), ("3", "1"), ("3", "2")):
         monkeypatch.setenv("B200AT_HOST_PIPE", level)
         monkeypatch.setenv("B200AT_HOST_SUB", sub)
         for _ in range(2):
