@@ -116,7 +116,7 @@ struct Tune {
   int thr_early;      // k_threshold4: pixel loads issued before the tile min/max staging barrier
   int ccl_sweep;      // k_ccl_tile_sweep (warp per tile, label inheritance) instead of k_ccl_tile; 2 = without TMA staging; 3 = ILP variant; 4 = no staging, 6 KB of shared memory per tile
   int ccl_flat;       // k_ccl_roots + k_ccl_flatmark (roots first, then one gather per pixel with the size gate fused) instead of flatten + mark
-  int cluster_eager;  // k_cluster_pass: 1 = unconditional label loads + speculative offset load; 2 = k_cluster_pass4 (4 px / thread)
+  int cluster_eager;  // k_cluster_pass: 1 = unconditional label loads + speculative offset load; 2 = k_cluster_pass4 (4 px / thread); 3 = 2 with deferred stores in the emit pass
   int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
   int decode_pair;    // k_refine: two short edges per pass (lanes 0-15 / 16-31)
   int decode_ctas;    // persistent decode CTAs per SM

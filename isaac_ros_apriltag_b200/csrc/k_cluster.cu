@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
 // scan of per-thread counts per half instead of one ballot per (pixel, probe).  Same table protocol as k_cluster_pass; the
 // kernels are instruction-issue bound (ncu: 66 % of peak issue at 82 % warps active), this variant executes about half the
 // instructions per pixel.  The order of the points inside a cluster's segment differs, which is irrelevant (sorted later).
-template <bool EMIT>
+// DEFER (emit pass, cluster_eager=3): ncu puts 35 % of the emit pass's stall samples on the wait for the segment-cursor atomic's
+// return value.  Here a round's points are stored one round LATER: the leader issues the atomic, the warp goes on to the next
+// round's match / probe, and only then picks up the previous round's base -- the atomic has had a whole round to come back.
+template <bool EMIT, bool DEFER = false>
 __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
                                                        unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
                                                        const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
@@ -224,6 +227,18 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
   const uint32_t lrow1[6] = {lbm, lb.x, lb.y, lb.z, lb.w, lb4};       // labels of row y+1, columns x4-1 .. x4+4
   const int dxs[4] = {1, 0, -1, 1};
   const int dys[4] = {0, 1, 1, 1};
+  // DEFER: the round whose points have not been stored yet
+  bool p_has = false;
+  unsigned p_peers = 0;
+  int p_leader = 0;
+  uint32_t p_base = 0xffffffffu, p_pt = 0;
+  auto flush_pending = [&]() {
+    if (p_has) {
+      const uint32_t b = __shfl_sync(p_peers, p_base, p_leader);
+      if (b != 0xffffffffu) pts[b + __popc(p_peers & ((1u << lane) - 1))] = p_pt;
+    }
+    p_has = false;
+  };
 #pragma unroll
   for (int half = 0; half < 2; half++) {
     // my points of pixels 2*half, 2*half+1: bit (2 * jj + k) of `mask` = probe k of pixel jj produced a point
@@ -275,6 +290,44 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
       }
     }
     __syncwarp();
+    if (EMIT && DEFER) {
+      // every lane walks every round (no early `continue`): the deferred store of the previous round is one warp-uniform
+      // program point, reached together by all lanes of that round's groups
+      for (int c0 = 0; c0 < total; c0 += 32) {
+        const int j = c0 + (int)lane;
+        const bool has = j < total;
+        const unsigned act = __ballot_sync(0xffffffffu, has);
+        unsigned peers = 0;
+        int leader = 0;
+        uint32_t base = 0xffffffffu, pt = 0;
+        if (has) {
+          const unsigned long long key = s_key[wid][j];
+          pt = s_pt[wid][j];
+          peers = __match_any_sync(act, key);
+          leader = __ffs(peers) - 1;
+          if ((int)lane == leader) {
+            const int n = __popc(peers);
+            uint32_t slot = hash_key2(key) & hmask;
+            for (uint32_t probe = 0; probe < g.hcap; probe++) {
+              const unsigned long long cur = hk[slot];
+              const uint32_t off = hoff[ho + slot];
+              if (cur == key) {
+                if (off != 0xffffffffu) base = off + atomicAdd(&hcur[ho + slot], (uint32_t)n);  // consumed one round later
+                break;
+              }
+              if (cur == 0ULL) break;
+              slot = (slot + 1) & hmask;
+            }
+          }
+        }
+        flush_pending();
+        p_has = has;
+        p_peers = peers;
+        p_leader = leader;
+        p_base = base;
+        p_pt = pt;
+      }
+    } else
     for (int c0 = 0; c0 < total; c0 += 32) {
       const int j = c0 + (int)lane;
       const bool has = j < total;
@@ -328,6 +381,7 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
     }
     __syncwarp();  // the buffer is reused by the second half
   }
+  if (EMIT && DEFER) flush_pending();
 }
 
 // One CTA per (frame, table segment).  Pass 1 totals -> one reservation in the global cluster / point pools,
@@ -454,11 +508,14 @@ int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
   dim3 gp((g.Wd - 2 + 255) / 256, g.Hd - 2, nframes);
   const int segs = g.hcap >= 65536 ? 4 : 1;  // hcap is a power of two
-  if (ws.tune.cluster_eager == 2) {
+  if (ws.tune.cluster_eager >= 2) {
     dim3 g4(((g.Wd + 3) / 4 + 255) / 256, g.Hd - 2, nframes);
     k_cluster_pass4<false><<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
     k_cluster_select<<<nframes * segs, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters, segs);
-    k_cluster_pass4<true><<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+    if (ws.tune.cluster_eager == 3)
+      k_cluster_pass4<true, true><<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
+    else
+      k_cluster_pass4<true><<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
     return 5;
   }
   if (ws.tune.cluster_eager)
