@@ -64,6 +64,7 @@ Tune parse_tune() {
   t.qf_scale = 1.0f;
   t.qf_keys23 = kTuneDefaultQfKeys23;
   t.qf_mc = kTuneDefaultQfMc;
+  t.qf_sort = 0;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -87,6 +88,7 @@ Tune parse_tune() {
     else if (k == "qf_scale") t.qf_scale = (float)v;
     else if (k == "qf_keys23") t.qf_keys23 = (int)v;
     else if (k == "qf_mc") t.qf_mc = (int)v;
+    else if (k == "qf_sort") t.qf_sort = (int)v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;

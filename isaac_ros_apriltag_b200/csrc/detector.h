@@ -122,6 +122,7 @@ struct Tune {
   int decode_ctas;    // persistent decode CTAs per SM
   int qf_mc;          // quad fit, one-warp bins: 1 = several clusters per CTA in phase lockstep (shared instruction stream);
                       // 2 = same with more warps for the 128 bin; 3 = occupancy variants instead (k_quad.cu, launch_quadfit)
+  int qf_sort;        // quad fit sort: serial merge with one-key lookahead per run (refill loads off the critical path)
   float qf_scale;     // scales the persistent grid of every quad-fit bin
   int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
 };

@@ -161,7 +161,10 @@ __device__ __forceinline__ void cta_sync() {
 // The sorted sequence ends in `a`.
 // (Tried and measured slower on B200: register bitonic networks for the per-thread sort and for the merge step -- reading the
 // next ITEMS keys of both runs at once and merging min(A[k], B[ITEMS-1-k]) -- instead of the serial merge: +2 % quad-fit time.)
-template <int THREADS, int ITEMS>
+// LOOKAHEAD (qf_sort=1, not measured yet): the serial merge keeps the NEXT key of both runs in registers, so the load that
+// refills a side is issued one output ahead of its use instead of sitting on the critical path of every output (ncu: half of
+// sort_keys' stall samples in the multi-warp bins are short-scoreboard waits on exactly these dependent loads).
+template <int THREADS, int ITEMS, bool LOOKAHEAD>
 __device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long long *tmp, int n, int tid) {
   constexpr unsigned long long INF = ~0ull;
   for (int base = tid * ITEMS; base < n; base += THREADS * ITEMS) {
@@ -202,17 +205,37 @@ __device__ __forceinline__ void sort_keys(unsigned long long *a, unsigned long l
       }
       int ia = lo, ib = diag - lo;
       unsigned long long va = ia < na ? src[a0 + ia] : INF, vb = ib < nb ? src[b0 + ib] : INF;
+      if (LOOKAHEAD) {
+        unsigned long long na1 = ia + 1 < na ? src[a0 + ia + 1] : INF, nb1 = ib + 1 < nb ? src[b0 + ib + 1] : INF;
 #pragma unroll
-      for (int k = 0; k < ITEMS; k++) {
-        if (ob + k < b1) {
-          const bool take_a = va <= vb;
-          dst[ob + k] = take_a ? va : vb;
-          if (take_a) {
-            ia++;
-            va = ia < na ? src[a0 + ia] : INF;
-          } else {
-            ib++;
-            vb = ib < nb ? src[b0 + ib] : INF;
+        for (int k = 0; k < ITEMS; k++) {
+          if (ob + k < b1) {
+            const bool take_a = va <= vb;
+            dst[ob + k] = take_a ? va : vb;
+            if (take_a) {
+              ia++;
+              va = na1;
+              na1 = ia + 1 < na ? src[a0 + ia + 1] : INF;  // needed two outputs from now at the earliest
+            } else {
+              ib++;
+              vb = nb1;
+              nb1 = ib + 1 < nb ? src[b0 + ib + 1] : INF;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+          if (ob + k < b1) {
+            const bool take_a = va <= vb;
+            dst[ob + k] = take_a ? va : vb;
+            if (take_a) {
+              ia++;
+              va = ia < na ? src[a0 + ia] : INF;
+            } else {
+              ib++;
+              vb = ib < nb ? src[b0 + ib] : INF;
+            }
           }
         }
       }
@@ -386,7 +409,7 @@ struct QfSmem {
 // of a CTA walk through the phases TOGETHER (block barriers at the phase boundaries, rejected clusters idle instead of
 // leaving).  The kernel is ~80 KB of straight-line code per cluster; warps that sit in the same phase share the instruction
 // lines they fetch, warps in unrelated phases (18 independent one-warp CTAs per SM) thrash the 32 KB instruction cache.
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB>
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB, bool LOOKAHEAD>
 __global__ void __launch_bounds__(THREADS * CPB, MINB) k_quadfit(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters,
                                                      const uint32_t *__restrict__ bin_idx, int bin, const uint32_t *__restrict__ pts,
                                                      unsigned long long *__restrict__ keys, LineFitPt *__restrict__ lfps_pool,
@@ -511,12 +534,12 @@ __global__ void __launch_bounds__(THREADS * CPB, MINB) k_quadfit(Geo g, FitParam
         if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
       }
       cta_sync<THREADS>();
-      sort_keys<THREADS, ITEMS>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz, tid);
+      sort_keys<THREADS, ITEMS, LOOKAHEAD>(skeys, reinterpret_cast<unsigned long long *>(s_ring), sz, tid);
     } else {
       for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
       cta_sync<THREADS>();
       // scratch for the merge passes: the (not yet used) error area
-      sort_keys<THREADS, ITEMS>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
+      sort_keys<THREADS, ITEMS, LOOKAHEAD>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
     }
 
     QF_PHASE();
@@ -923,11 +946,11 @@ __global__ void __launch_bounds__(256) k_bin_clusters(Geo g, const ClusterRec *_
 #undef QF_DROP
 #undef QF_PHASE
 
-template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB = 1>
-static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB, bool LOOKAHEAD>
+static void launch_bin_t(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
   const Geo &g = ws.g;
   constexpr size_t smem = QfSmem<NCAP, MODE, CH>::BYTES * CPB;
-  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB>;
+  auto kern = k_quadfit<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, LOOKAHEAD>;
   // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute; the persistent grid is sized to
   // the number of CTAs that are resident at once
   static int ctas_per_sm[64] = {};
@@ -943,6 +966,14 @@ static void launch_bin(const Workspace &ws, int bin, double scale, int sms, cons
   const int grid = std::max(1, (int)(sms * ctas_per_sm[dev] * scale + 0.5));
   kern<<<grid, THREADS * CPB, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.lfps, ws.errs, ws.dec, ws.quads,
                                     ws.counters, ct, at_Wp(g));
+}
+
+template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB = 1>
+static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
+  if (ws.tune.qf_sort)
+    launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, true>(ws, bin, scale, sms, ct, st);
+  else
+    launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, false>(ws, bin, scale, sms, ct, st);
 }
 
 int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
