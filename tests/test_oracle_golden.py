@@ -122,6 +122,36 @@ def test_against_opencv_aruco(oracle_mod):
         assert np.abs(a - b).max() <= 2.0
 
 
+def test_candidate_quads_against_opencv_aruco(oracle_mod):
+    """Intermediate stage, independent port: OpenCV's CORNER_REFINE_APRILTAG runs its own port of apriltag_quad_thresh (threshold,
+    union-find, gradient clusters, fit_quads) and returns EVERY candidate quad -- accepted markers and rejected junk -- as the float
+    line-intersection corners, i.e. what the oracle calls the (un-refined) quads.  The two ports are different AprilTag-3 vintages
+    (cluster size bounds, duplicate suppression, weighting details), so the sets are not identical; measured on this frame: 30 of the
+    oracle's 116 quads coincide with an OpenCV candidate to < 0.05 px in all four corners, 53 to < 0.5 px, 73 to < 2 px (same pixel
+    convention: offset 0), and the near-misses share one to three corners exactly.  Asserted with slack."""
+    O = oracle_mod
+    rng = np.random.default_rng(11)
+    frame, _ = synth.make_frame(rng, 1280, 720, [("tag36h11", 3), ("tag36h11", 77), ("tag36h11", 400)], noise_sigma=1.0)
+    orc = O.Oracle(("tag36h11",), quad_decimate=1.0)
+    orc.detect(frame)
+    oq = [np.asarray(q["p"], np.float64) for q in orc.quads(refined=False)]
+    par = cv2.aruco.DetectorParameters()
+    par.cornerRefinementMethod = cv2.aruco.CORNER_REFINE_APRILTAG
+    par.aprilTagQuadDecimate = 0.0
+    det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_APRILTAG_36h11), par)
+    corners, ids, rejected = det.detectMarkers(frame)
+    cand = [c.reshape(4, 2).astype(np.float64) for c in list(corners) + list(rejected)]
+    assert len(oq) >= 50 and len(cand) >= 50
+
+    def dist(a, b):  # same quad up to the starting corner and the winding
+        return min(np.abs(a - np.roll(b[::-1] if rev else b, sh, axis=0)).max() for sh in range(4) for rev in (False, True))
+
+    d = np.array([min(dist(p, c) for c in cand) for p in oq])
+    assert (d < 0.05).sum() >= 0.2 * len(oq), ((d < 0.05).sum(), len(oq))
+    assert (d < 0.5).sum() >= 0.35 * len(oq), ((d < 0.5).sum(), len(oq))
+    assert (d < 2.0).sum() >= 0.5 * len(oq), ((d < 2.0).sum(), len(oq))
+
+
 def test_encodings_agree(oracle_mod):
     O = oracle_mod
     frames, _, _, _, fams = synth.make_config_frames("C1", 1)
