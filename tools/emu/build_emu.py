@@ -20,7 +20,8 @@ NAME_BEFORE = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;(){}]*>)?)\s*$")
 
 
 def translate(text):
-    """NAME<<<CFG>>>(ARGS) -> emu::launch(CFG, [&]() { NAME(ARGS); })   (balanced-parenthesis scan, newlines kept)."""
+    """NAME<<<CFG>>>(ARGS) -> emu::launch("NAME", CFG, [=]() { NAME(ARGS); })   (balanced-parenthesis scan, newlines kept; the
+    lambda copies what the argument expressions refer to, because in the asynchronous mode the launch runs later)."""
     out, pos = [], 0
     while True:
         i = text.find("<<<", pos)
@@ -45,7 +46,7 @@ def translate(text):
                     break
             e += 1
         out.append(text[pos:m.start(1)])
-        out.append(f"(emu::g_kernel_name = \"{m.group(1)}\", emu::launch({text[i + 3:j]}, [&]() {{ {m.group(1)}({text[k + 1:e]}); }}))")
+        out.append(f"emu::launch(\"{m.group(1)}\", {text[i + 3:j]}, [=]() {{ {m.group(1)}({text[k + 1:e]}); }})")
         pos = e + 1
     text = "".join(out)
 

@@ -9,6 +9,8 @@
 // round-robin and switched only at __syncthreads / warp collectives.  A collective with mask m completes when every live lane
 // named in m has arrived at a collective of the same kind with the same mask (anything else is reported as a divergence bug);
 // a full scheduler pass without progress is reported as a deadlock.  Atomics are plain read-modify-writes (one host thread).
+// Streams: synchronous by default (every operation runs at issue); b200at_emu_async(1, seed) queues them and runs the queues in
+// random dependency-respecting interleavings (emu_runtime.cpp) -- a check of the host code's event wiring.
 // Force-included (g++ -include) in front of every translated source; see tools/emu/build_emu.py.
 #pragma once
 #define B200AT_EMU 1
@@ -28,6 +30,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <functional>
 #include <type_traits>
 
 #undef __launch_bounds__
@@ -71,22 +74,20 @@ void done(Snapshot *s);
 
 typedef void (*ThreadFn)(void *);
 void run_grid(dim3 grid, dim3 block, size_t smem, ThreadFn fn, void *arg);
+// a launch is an entry of its stream's queue (executed at once in the synchronous mode): `body` holds COPIES of the arguments
+void enqueue_kernel(cudaStream_t s, const char *name, dim3 grid, dim3 block, size_t smem, std::function<void()> body);
 
 template <class F>
-static void thunk(void *p) {
-  (*static_cast<F *>(p))();
+inline void launch(const char *name, dim3 grid, dim3 block, size_t smem, cudaStream_t s, F f) {
+  enqueue_kernel(s, name, grid, block, smem, std::function<void()>(f));
 }
 template <class F>
-inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F f) {
-  run_grid(grid, block, smem, &thunk<F>, &f);
+inline void launch(const char *name, dim3 grid, dim3 block, size_t smem, F f) {
+  enqueue_kernel(nullptr, name, grid, block, smem, std::function<void()>(f));
 }
 template <class F>
-inline void launch(dim3 grid, dim3 block, size_t smem, F f) {
-  run_grid(grid, block, smem, &thunk<F>, &f);
-}
-template <class F>
-inline void launch(dim3 grid, dim3 block, F f) {
-  run_grid(grid, block, 0, &thunk<F>, &f);
+inline void launch(const char *name, dim3 grid, dim3 block, F f) {
+  enqueue_kernel(nullptr, name, grid, block, 0, std::function<void()>(f));
 }
 
 template <class T>

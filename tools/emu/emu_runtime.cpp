@@ -8,6 +8,9 @@
 #include <string.h>
 
 #include <chrono>
+#include <deque>
+#include <functional>
+#include <random>
 #include <vector>
 
 namespace emu {
@@ -314,9 +317,103 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*fn)(void *), void *arg)
 }  // namespace emu
 
 // ---------------------------------------------------------------------------------------------------------------------
-// CUDA runtime subset on host memory.  Streams and events are tokens: every operation executes synchronously at issue,
-// which is a valid serialisation because the library issues work in dependency order.
+// CUDA runtime subset on host memory.
+// Default mode: streams and events are tokens, every operation executes synchronously at issue -- a valid serialisation,
+// because the library issues work in dependency order.
+// Asynchronous mode (b200at_emu_async(1, seed) or B200AT_EMU_ASYNC=seed): every stream is a queue; kernels, async copies /
+// memsets, event records and event waits are queue entries; the queues only run at synchronisation points, and then in a
+// RANDOM interleaving that respects stream order and event dependencies and nothing else.  A missing dependency between two
+// streams (the class of bug the synchronous mode and a lucky GPU run both hide) turns into wrong results for some seeds.
 // ---------------------------------------------------------------------------------------------------------------------
+namespace emu {
+
+struct EmuEvent {
+  double t_ms = 0.0;
+  unsigned long long recorded = 0;  // record operations issued
+  unsigned long long done = 0;      // ... completed
+};
+struct Op {
+  std::function<void()> fn;
+  EmuEvent *wait_ev = nullptr;
+  unsigned long long wait_gen = 0;
+  EmuEvent *rec_ev = nullptr;
+  unsigned long long rec_gen = 0;
+};
+struct EmuStream {
+  std::deque<Op> q;
+};
+static EmuStream g_default_stream;
+static std::vector<EmuStream *> g_all_streams{&g_default_stream};
+static bool g_async = false;
+static std::mt19937 g_rng(1);
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static EmuStream *stream_of(cudaStream_t s) { return s ? reinterpret_cast<EmuStream *>(s) : &g_default_stream; }
+static bool runnable(const Op &op) { return op.wait_ev == nullptr || op.wait_ev->done >= op.wait_gen; }
+static void execute(Op &op) {
+  if (op.rec_ev) {
+    op.rec_ev->t_ms = now_ms();
+    if (op.rec_ev->done < op.rec_gen) op.rec_ev->done = op.rec_gen;
+  }
+  if (op.fn) op.fn();
+}
+// run ONE runnable queue head, chosen at random; false if every queue is empty
+static bool step() {
+  EmuStream *cand[64];
+  int n = 0;
+  bool pending = false;
+  for (EmuStream *st : g_all_streams) {
+    if (st->q.empty()) continue;
+    pending = true;
+    if (runnable(st->q.front()) && n < 64) cand[n++] = st;
+  }
+  if (!pending) return false;
+  if (n == 0) {
+    fprintf(stderr, "[emu] stream DEADLOCK: every pending queue head waits for an event nobody will record\n");
+    abort();
+  }
+  EmuStream *st = cand[g_rng() % (unsigned)n];
+  Op op = std::move(st->q.front());
+  st->q.pop_front();
+  execute(op);
+  return true;
+}
+static void drain_all() {
+  while (step()) {
+  }
+}
+static void drain_stream(EmuStream *st) {
+  while (!st->q.empty()) step();
+}
+static void enqueue(cudaStream_t s, Op op) {
+  if (!g_async) {
+    execute(op);
+    return;
+  }
+  stream_of(s)->q.push_back(std::move(op));
+}
+void enqueue_kernel(cudaStream_t s, const char *name, dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+  Op op;
+  op.fn = [name, grid, block, smem, body]() {
+    g_kernel_name = name;
+    struct Ctx {
+      const std::function<void()> *b;
+    } ctx{&body};
+    run_grid(grid, block, smem, [](void *p) { (*static_cast<Ctx *>(p)->b)(); }, &ctx);
+  };
+  enqueue(s, std::move(op));
+}
+
+}  // namespace emu
+
+extern "C" void b200at_emu_async(int on, unsigned seed) {
+  emu::drain_all();
+  emu::g_async = on != 0;
+  emu::g_rng.seed(seed);
+}
+
 extern "C" {
 
 static cudaError_t g_last = cudaSuccess;
@@ -331,7 +428,10 @@ cudaError_t cudaGetDevice(int *d) {
   return cudaSuccess;
 }
 cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
-cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) {
+  emu::drain_all();
+  return cudaSuccess;
+}
 cudaError_t cudaGetLastError(void) {
   cudaError_t e = g_last;
   g_last = cudaSuccess;
@@ -352,6 +452,7 @@ cudaError_t cudaDeviceGetAttribute(int *v, enum cudaDeviceAttr attr, int) {
 
 // device allocations are filled with a poison pattern: code that depends on uninitialised memory shows up as a mismatch
 cudaError_t cudaMalloc(void **p, size_t n) {
+  emu::drain_all();
   void *q = nullptr;
   if (posix_memalign(&q, 256, n ? n : 256) != 0) return cudaErrorMemoryAllocation;
   memset(q, 0xCD, n);
@@ -359,6 +460,7 @@ cudaError_t cudaMalloc(void **p, size_t n) {
   return cudaSuccess;
 }
 cudaError_t cudaFree(void *p) {
+  emu::drain_all();
   free(p);
   return cudaSuccess;
 }
@@ -371,6 +473,7 @@ cudaError_t cudaMallocHost(void **p, size_t n) {
 }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMallocHost(p, n); }
 cudaError_t cudaFreeHost(void *p) {
+  emu::drain_all();
   free(p);
   return cudaSuccess;
 }
@@ -394,36 +497,54 @@ cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes *a, const void
   return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) {
+  emu::drain_all();
   memmove(d, s, n);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t) {
-  memmove(d, s, n);
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t st) {
+  emu::Op op;
+  op.fn = [d, s, n]() { memmove(d, s, n); };
+  emu::enqueue(st, std::move(op));
   return cudaSuccess;
+}
+static void copy2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h) {
+  for (size_t r = 0; r < h; r++) memmove((char *)d + r * dp, (const char *)s + r * sp, w);
 }
 cudaError_t cudaMemcpy2D(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind) {
-  for (size_t r = 0; r < h; r++) memmove((char *)d + r * dp, (const char *)s + r * sp, w);
+  emu::drain_all();
+  copy2d(d, dp, s, sp, w, h);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind k, cudaStream_t) {
-  return cudaMemcpy2D(d, dp, s, sp, w, h, k);
+cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t st) {
+  emu::Op op;
+  op.fn = [d, dp, s, sp, w, h]() { copy2d(d, dp, s, sp, w, h); };
+  emu::enqueue(st, std::move(op));
+  return cudaSuccess;
 }
 cudaError_t cudaMemset(void *d, int v, size_t n) {
+  emu::drain_all();
   memset(d, v, n);
   return cudaSuccess;
 }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) {
-  memset(d, v, n);
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) {
+  emu::Op op;
+  op.fn = [d, v, n]() { memset(d, v, n); };
+  emu::enqueue(st, std::move(op));
   return cudaSuccess;
 }
-cudaError_t cudaMemset2DAsync(void *d, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
-  for (size_t r = 0; r < h; r++) memset((char *)d + r * pitch, v, w);
+cudaError_t cudaMemset2DAsync(void *d, size_t pitch, int v, size_t w, size_t h, cudaStream_t st) {
+  emu::Op op;
+  op.fn = [d, pitch, v, w, h]() {
+    for (size_t r = 0; r < h; r++) memset((char *)d + r * pitch, v, w);
+  };
+  emu::enqueue(st, std::move(op));
   return cudaSuccess;
 }
 
-static uintptr_t g_token = 0x1000;
 cudaError_t cudaStreamCreate(cudaStream_t *s) {
-  *s = (cudaStream_t)(g_token += 16);
+  emu::EmuStream *st = new emu::EmuStream();
+  emu::g_all_streams.push_back(st);
+  *s = reinterpret_cast<cudaStream_t>(st);
   return cudaSuccess;
 }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { return cudaStreamCreate(s); }
@@ -433,33 +554,63 @@ cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) {
   *hi = -5;
   return cudaSuccess;
 }
-cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-
-struct EmuEvent {
-  double t_ms;
-};
-static double now_ms() {
-  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  if (!s) return cudaSuccess;
+  emu::EmuStream *st = emu::stream_of(s);
+  emu::drain_stream(st);
+  for (size_t i = 0; i < emu::g_all_streams.size(); i++)
+    if (emu::g_all_streams[i] == st) {
+      emu::g_all_streams.erase(emu::g_all_streams.begin() + (long)i);
+      break;
+    }
+  delete st;
+  return cudaSuccess;
 }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+  emu::drain_stream(emu::stream_of(s));
+  return cudaSuccess;
+}
+// (waiting for an event that has never been recorded is a no-op, as in CUDA; the wait refers to the records issued so far)
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+  emu::EmuEvent *ev = reinterpret_cast<emu::EmuEvent *>(e);
+  if (ev->recorded == 0) return cudaSuccess;
+  emu::Op op;
+  op.wait_ev = ev;
+  op.wait_gen = ev->recorded;
+  emu::enqueue(s, std::move(op));
+  return cudaSuccess;
+}
+
 cudaError_t cudaEventCreate(cudaEvent_t *e) {
-  *e = (cudaEvent_t) new EmuEvent{0.0};
+  *e = reinterpret_cast<cudaEvent_t>(new emu::EmuEvent());
   return cudaSuccess;
 }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e) {
-  delete (EmuEvent *)e;
+  emu::drain_all();
+  delete reinterpret_cast<emu::EmuEvent *>(e);
   return cudaSuccess;
 }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
-  ((EmuEvent *)e)->t_ms = now_ms();
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+  emu::EmuEvent *ev = reinterpret_cast<emu::EmuEvent *>(e);
+  emu::Op op;
+  op.rec_ev = ev;
+  op.rec_gen = ++ev->recorded;
+  emu::enqueue(s, std::move(op));
   return cudaSuccess;
 }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+  emu::EmuEvent *ev = reinterpret_cast<emu::EmuEvent *>(e);
+  while (ev->done < ev->recorded && emu::step()) {
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaEventQuery(cudaEvent_t e) {
+  emu::EmuEvent *ev = reinterpret_cast<emu::EmuEvent *>(e);
+  return ev->done >= ev->recorded ? cudaSuccess : cudaErrorNotReady;
+}
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
-  *ms = (float)(((EmuEvent *)b)->t_ms - ((EmuEvent *)a)->t_ms);
+  *ms = (float)(reinterpret_cast<emu::EmuEvent *>(b)->t_ms - reinterpret_cast<emu::EmuEvent *>(a)->t_ms);
   return cudaSuccess;
 }
 
