@@ -408,6 +408,15 @@ void enqueue_kernel(cudaStream_t s, const char *name, dim3 grid, dim3 block, siz
 
 }  // namespace emu
 
+// B200AT_EMU_ASYNC=<seed> in the environment turns the asynchronous mode on for the whole process
+static const bool g_async_from_env = []() {
+  if (const char *e = getenv("B200AT_EMU_ASYNC")) {
+    emu::g_async = true;
+    emu::g_rng.seed((unsigned)atoi(e));
+  }
+  return true;
+}();
+
 extern "C" void b200at_emu_async(int on, unsigned seed) {
   emu::drain_all();
   emu::g_async = on != 0;
