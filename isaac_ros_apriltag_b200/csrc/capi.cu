@@ -971,8 +971,11 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       S_forced = true;
     }
   }
+  // (the encoding, hence the row size, can change between calls: b200AprilTagsSetInputEncoding)
+  const size_t need_pitch = (row + 255) & ~(size_t)255;
+  const bool pitch_grew = need_pitch > h->stage_pitch;
+  if (pitch_grew) h->stage_pitch = need_pitch;
   if (!h->copy_stream) {
-    h->stage_pitch = (row + 255) & ~(size_t)255;
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
     for (int i = 0; i < 3; i++)
@@ -1060,7 +1063,7 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   if (!sparse || 2 * S > h->max_batch) pipe = false;
   if (pipe) nstreams = 1;
   const uint32_t nslots = pipe ? 3 : 2;
-  if (!h->d_stage || h->stage_sub < S || h->stage_slots < nslots) {
+  if (!h->d_stage || h->stage_sub < S || h->stage_slots < nslots || pitch_grew) {
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->own_stream);
     if (h->d_stage) {

@@ -183,3 +183,20 @@ def test_emulated_host_schedules_under_random_stream_interleavings(pu, level, mo
     finally:
         L.b200at_emu_async(0, 0)
     det.close()
+
+
+def test_emulated_host_path_after_encoding_change(pu):
+    """b200AprilTagsSetInputEncoding between host calls: the staging slots are re-sized for the larger rows (mono8 -> bgr8)."""
+    from isaac_ros_apriltag_b200 import capi
+    gray = np.stack([small_frame(70 + i, 320, 240, [("tag36h11", 40 + i)], side=(60, 110)) for i in range(3)])
+    bgr = np.ascontiguousarray(np.repeat(gray[:, :, :, None], 3, axis=3))
+    det = capi.Detector(320, 240, encoding="mono8", max_batch=2, max_tags=16)
+    got_m = det.detect_host(gray)
+    assert capi.lib().b200AprilTagsSetInputEncoding(det.h, capi.ENCODINGS["bgr8"]) == 0
+    got_c = det.detect_host(bgr)
+    t, ptrs, pitch = pu.upload(bgr)
+    want = [det.detect_device(ptrs[i:i + 1], pitch, 0)[0] for i in range(3)]
+    for a, b, c in zip(got_m, got_c, want):
+        assert len(c) == 1 and b.tobytes() == c.tobytes()
+        assert list(a["id"]) == list(c["id"])  # same image content through the mono8 path
+    det.close()
