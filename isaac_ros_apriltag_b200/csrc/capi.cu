@@ -477,6 +477,11 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   ws.tune = parse_tune();
   if (ws.tune.decode_split) ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
+  if (ws.tune.cluster_eager == 4) {
+    ws.rec_cap = 2 * (int)Wp;  // points of one row: 0.64 per pixel on thresholded noise, at most 4
+    ALLOC(ws.rec, (size_t)B * g.Hd * ws.rec_cap);
+    ALLOC(ws.rec_cnt, (size_t)B * g.Hd);
+  }
   {
     // combination tables: for every nm, all m0<m1<m2<m3<nm in lexicographic order (the serial loops' visiting order)
     std::vector<unsigned char> tab;
@@ -643,6 +648,10 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
     v.src_frames += f0;
   }
   if (v.quad_H) v.quad_H += (size_t)c * qc * 10;
+  if (v.rec) {
+    v.rec += (size_t)f0 * g.Hd * v.rec_cap;
+    v.rec_cnt += (size_t)f0 * g.Hd;
+  }
   v.g.tma_frame0 = f0;
   if (c & 1) {  // lane 1 has its own side streams / events
     for (int i = 0; i < kQuadAux; i++) {

@@ -116,7 +116,7 @@ struct Tune {
   int thr_early;      // k_threshold4: pixel loads issued before the tile min/max staging barrier
   int ccl_sweep;      // k_ccl_tile_sweep (warp per tile, label inheritance) instead of k_ccl_tile; 2 = without TMA staging; 3 = ILP variant; 4 = no staging, 6 KB of shared memory per tile
   int ccl_flat;       // k_ccl_roots + k_ccl_flatmark (roots first, then one gather per pixel with the size gate fused) instead of flatten + mark
-  int cluster_eager;  // k_cluster_pass: 1 = unconditional label loads + speculative offset load; 2 = k_cluster_pass4 (4 px / thread); 3 = 2 with deferred stores in the emit pass
+  int cluster_eager;  // k_cluster_pass: 1 = unconditional label loads + speculative offset load; 2 = k_cluster_pass4 (4 px / thread); 3 = 2 with deferred stores in the emit pass; 4 = count pass records the points, scatter pass instead of emit
   int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
   int decode_pair;    // k_refine: two short edges per pass (lanes 0-15 / 16-31)
   int decode_ctas;    // persistent decode CTAs per SM
@@ -154,6 +154,10 @@ struct Workspace {
   unsigned long long *need1, *need2;  // [B][H] rows needed by refine_edges / by the decode samples
   FrameDesc *src_frames;       // [B] device-accessible addresses of the caller's (pinned) host frames
   double *quad_H;              // [quad_cap][10]: H[0..8], valid flag
+  // cluster_eager=4: per-row lists of (table slot, packed point) written by the count pass, consumed by k_cluster_scatter
+  uint2 *rec;
+  uint32_t *rec_cnt;
+  int rec_cap;
   const unsigned char *combos;  // per nm (4..kMaxNMaxima): all m0<m1<m2<m3 < nm in lexicographic order, uchar4 each
   int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
   CUtensorMap thr_tmap;  // TMA descriptor of thr as a (Wp, Hd, B) u8 tensor, box 64 x 33 x 1 (CCL tile + halo)

@@ -174,11 +174,20 @@ __global__ void __launch_bounds__(256) k_cluster_pass(Geo g, const uint8_t *__re
 // DEFER (emit pass, cluster_eager=3): ncu puts 35 % of the emit pass's stall samples on the wait for the segment-cursor atomic's
 // return value.  Here a round's points are stored one round LATER: the leader issues the atomic, the warp goes on to the next
 // round's match / probe, and only then picks up the previous round's base -- the atomic has had a whole round to come back.
-template <bool EMIT, bool DEFER = false>
-__global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
-                                                       unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
-                                                       const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
-                                                       uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp) {
+// RECORD (cluster_eager=4, not measured yet): the count pass also writes every point, with the table slot it was counted in,
+// to a per-row record list; the emit pass -- which repeats the whole count pass (pixels, labels, probes, match, table probe)
+// only to learn where each point goes -- is replaced by k_cluster_scatter, which reads the 8-byte records.
+struct RecArgs {
+  uint2 *rec;         // [frame][row][cap]: .x = table slot of the point's cluster, .y = packed point
+  uint32_t *cnt;      // [frame][row]
+  int cap;
+};
+
+template <bool EMIT, bool DEFER, bool RECORD>
+__device__ __forceinline__ void cluster_pass4_body(const Geo &g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
+                                                   unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
+                                                   const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
+                                                   uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp, RecArgs ra) {
   __shared__ unsigned long long s_key[8][256];
   __shared__ uint32_t s_pt[8][256];
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
           const int pos = base0 + __popc(mask & ((1u << bit) - 1u));
           const uint32_t q1 = rep1[k];
           s_key[wid][pos] = rep0 < q1 ? (((unsigned long long)q1 << 32) | rep0) : (((unsigned long long)rep0 << 32) | q1);
-          if (EMIT) {
+          if (EMIT || RECORD) {
             const int dx = dxs[k], dy = dys[k];
             const int d = 255 - 2 * v0;  // v1 - v0 with v0 + v1 == 255
             const int gx = dx * d, gy = dy * d;
@@ -290,7 +299,58 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
       }
     }
     __syncwarp();
-    if (EMIT && DEFER) {
+    if (RECORD) {
+      // room in the row's record list for this warp's points: the atomic is issued now and picked up after the first table probe
+      uint32_t rb = 0;
+      uint2 *rrow = ra.rec + ((size_t)fr * g.Hd + y) * ra.cap;
+      if (lane == 0 && total > 0) rb = atomicAdd(&ra.cnt[(size_t)fr * g.Hd + y], (uint32_t)total);
+      bool rb_ready = false;
+      for (int c0 = 0; c0 < total; c0 += 32) {  // (every lane walks every round: the pick-up below is a full-warp shuffle)
+        const int j = c0 + (int)lane;
+        const bool has = j < total;
+        const unsigned act = __ballot_sync(0xffffffffu, has);
+        uint32_t found = 0xffffffffu, pt = 0;
+        if (has) {
+          const unsigned long long key = s_key[wid][j];
+          pt = s_pt[wid][j];
+          const unsigned peers = __match_any_sync(act, key);
+          const int leader = __ffs(peers) - 1;
+          if ((int)lane == leader) {
+            uint32_t slot = hash_key2(key) & hmask;
+            for (uint32_t probe = 0; probe < g.hcap; probe++) {
+              unsigned long long cur = hk[slot];
+              if (cur == key) {
+                found = slot;
+                break;
+              }
+              if (cur == 0ULL) {
+                unsigned long long old = atomicCAS(&hk[slot], 0ULL, key);
+                if (old == 0ULL || old == key) {
+                  found = slot;
+                  break;
+                }
+              }
+              slot = (slot + 1) & hmask;
+            }
+            if (found == 0xffffffffu)
+              atomicOr(&counters[CNT_STATUS], (uint32_t)ST_HASH_FULL);
+            else
+              atomicAdd(&hcnt[ho + found], (uint32_t)__popc(peers));
+          }
+          found = __shfl_sync(peers, found, leader);
+        }
+        if (!rb_ready) {
+          rb = __shfl_sync(0xffffffffu, rb, 0);
+          rb_ready = true;
+        }
+        if (has) {
+          if (rb + (uint32_t)j < (uint32_t)ra.cap)
+            rrow[rb + j] = make_uint2(found, pt);
+          else
+            atomicOr(&counters[CNT_STATUS], (uint32_t)ST_POINTS_FULL);
+        }
+      }
+    } else if (EMIT && DEFER) {
       // every lane walks every round (no early `continue`): the deferred store of the previous round is one warp-uniform
       // program point, reached together by all lanes of that round's groups
       for (int c0 = 0; c0 < total; c0 += 32) {
@@ -382,6 +442,50 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
     __syncwarp();  // the buffer is reused by the second half
   }
   if (EMIT && DEFER) flush_pending();
+}
+
+template <bool EMIT, bool DEFER = false>
+__global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
+                                                       unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
+                                                       const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
+                                                       uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp) {
+  cluster_pass4_body<EMIT, DEFER, false>(g, thr2, lab, hkey, hcnt, hoff, hcur, pts, counters, Wp, RecArgs{nullptr, nullptr, 0});
+}
+
+__global__ void __launch_bounds__(256) k_cluster_record(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
+                                                        unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
+                                                        uint32_t *__restrict__ counters, int Wp, RecArgs ra) {
+  cluster_pass4_body<false, false, true>(g, thr2, lab, hkey, hcnt, nullptr, nullptr, nullptr, counters, Wp, ra);
+}
+
+// one CTA per (row, frame): the row's records -> their clusters' segments (same aggregation as the emit pass: lanes that hold
+// points of one cluster share one atomic on its cursor)
+__global__ void __launch_bounds__(256) k_cluster_scatter(Geo g, RecArgs ra, const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
+                                                         uint32_t *__restrict__ pts) {
+  const int y = blockIdx.x + 1, fr = blockIdx.y;
+  const size_t ho = (size_t)fr * g.hcap;
+  const uint32_t n = min(ra.cnt[(size_t)fr * g.Hd + y], (uint32_t)ra.cap);
+  const uint2 *rrow = ra.rec + ((size_t)fr * g.Hd + y) * ra.cap;
+  const unsigned lane = threadIdx.x & 31;
+  for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+    const uint32_t i = i0 + threadIdx.x;
+    uint32_t off = 0xffffffffu, slot = 0, pt = 0;
+    if (i < n) {
+      const uint2 r = rrow[i];
+      slot = r.x;
+      pt = r.y;
+      if (slot != 0xffffffffu) off = hoff[ho + slot];
+    }
+    const bool has = off != 0xffffffffu;
+    const unsigned act = __ballot_sync(0xffffffffu, has);
+    if (!has) continue;
+    const unsigned peers = __match_any_sync(act, slot);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&hcur[ho + slot], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    pts[off + base + __popc(peers & ((1u << lane) - 1))] = pt;
+  }
 }
 
 // One CTA per (frame, table segment).  Pass 1 totals -> one reservation in the global cluster / point pools,
@@ -508,6 +612,15 @@ int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
   dim3 gp((g.Wd - 2 + 255) / 256, g.Hd - 2, nframes);
   const int segs = g.hcap >= 65536 ? 4 : 1;  // hcap is a power of two
+  if (ws.tune.cluster_eager == 4 && ws.rec) {
+    dim3 g4(((g.Wd + 3) / 4 + 255) / 256, g.Hd - 2, nframes);
+    RecArgs ra{ws.rec, ws.rec_cnt, ws.rec_cap};
+    cudaMemsetAsync(ws.rec_cnt, 0, (size_t)nframes * g.Hd * sizeof(uint32_t), s);
+    k_cluster_record<<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.counters, Wp, ra);
+    k_cluster_select<<<nframes * segs, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters, segs);
+    k_cluster_scatter<<<dim3(g.Hd - 2, nframes), 256, 0, s>>>(g, ra, ws.hoff, ws.hcur, ws.pts);
+    return 6;
+  }
   if (ws.tune.cluster_eager >= 2) {
     dim3 g4(((g.Wd + 3) / 4 + 255) / 256, g.Hd - 2, nframes);
     k_cluster_pass4<false><<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);

@@ -134,7 +134,7 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
 
 
 @pytest.mark.parametrize("tune", ["thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,qf_mc=0,qf_keys23=0",  # the round-1 kernels
-                                  "ccl_sweep=2", "ccl_sweep=3", "ccl_sweep=4", "ccl_flat=1", "cluster_eager=1", "cluster_eager=3", "thr_early=1", "thr_early=2",
+                                  "ccl_sweep=2", "ccl_sweep=3", "ccl_sweep=4", "ccl_flat=1", "cluster_eager=1", "cluster_eager=3", "cluster_eager=4", "thr_early=1", "thr_early=2",
                                   "decode_split=0", "decode_split=2", "decode_pair=1", "qf_mc=0,qf_keys23=0", "qf_mc=2", "qf_mc=3", "qf_sort=1", "qf_scale=0.5,decode_ctas=2",
                                   "ccl_sweep=3,ccl_flat=1,decode_pair=1,thr_early=1"])
 def test_emulated_kernel_variants(pu, tune, monkeypatch):
