@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 300 python tools/gpu_tune.py > gpurun_out/next_tune.jsonl 2> gpurun_out/next_tune.err
 tail -2 gpurun_out/next_tune.err
 python tools/tune_report.py gpurun_out/next_tune.jsonl > gpurun_out/next_tune.md
-B200AT_TUNE="ccl_flat=1,decode_pair=1" B200AT_HOST_PIPE=2 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest_gpu_optin.log 2>&1
+B200AT_TUNE="cluster_eager=4,ccl_sweep=4,ccl_flat=1,qf_mc=3,qf_sort=1,decode_pair=1" B200AT_HOST_PIPE=2 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest_gpu_optin.log 2>&1
 tail -3 gpurun_out/next_pytest_gpu_optin.log
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest_gpu.log 2>&1
 tail -3 gpurun_out/next_pytest_gpu.log

@@ -20,10 +20,10 @@ from isaac_ros_apriltag_b200 import capi, synth  # noqa: E402
 ALL_OFF = "thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,qf_mc=0,qf_keys23=0"   # the round-1 kernels
 ALL_ON = ""                                                                               # library defaults
 # what the next GPU session should measure first (all bit-exact under the emulator, none measured yet except decode_pair)
-DEVICE_CONFIGS = [ALL_OFF, "", "ccl_flat=1", "decode_pair=1", "qf_mc=2", "qf_mc=3", "qf_sort=1", "cluster_eager=3", "cluster_eager=4", "ccl_sweep=4", "ccl_sweep=4,ccl_flat=1,decode_pair=1,qf_mc=3", "ccl_sweep=3,ccl_flat=1,decode_pair=1", ""]
+DEVICE_CONFIGS = [ALL_OFF, "", "ccl_flat=1", "decode_pair=1", "qf_mc=2", "qf_mc=3", "qf_sort=1", "cluster_eager=3", "cluster_eager=4", "ccl_sweep=4", "cluster_eager=4,ccl_sweep=4,ccl_flat=1,qf_mc=3,qf_sort=1,decode_pair=1", "ccl_sweep=3,ccl_flat=1,decode_pair=1", ""]
 # host entry point: (knobs, sparse staging (-1 = library default), sub-batch (0 = default), streams, pipelined fetch level, ramp, copy streams)
 HOST_CONFIGS = [("", 0, 16, 1, 0, 0, 1), ("", -1, 0, 1, -1, -1, 1), ("", 1, 64, 1, 2, 1, 1), ("", 1, 48, 1, 2, 1, 1), ("", 1, 32, 1, 2, 1, 1),
-                ("", 1, 64, 1, 2, 0, 1), ("ccl_flat=1,decode_pair=1", 1, 64, 1, 2, 1, 1), ("", -1, 0, 1, -1, -1, 1)]
+                ("", 1, 64, 1, 2, 0, 1), ("cluster_eager=4,ccl_sweep=4,ccl_flat=1,qf_mc=3,qf_sort=1,decode_pair=1", 1, 64, 1, 2, 1, 1), ("", -1, 0, 1, -1, -1, 1)]
 
 
 def emit(**kw):
