@@ -69,7 +69,7 @@ void block_barrier();
 void block_barrier_reduce(int pred, int *o_or, int *o_and, int *o_cnt);
 enum Kind { K_SYNCWARP = 1, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_BALLOT, K_MATCH, K_VOTE, K_REDUX };
 // all live lanes of `mask` deposit (val, aux); returns the group's snapshot (release it with done())
-Snapshot *exchange(unsigned mask, int kind, unsigned long long val, int aux, unsigned *live_mask);
+Snapshot *exchange(unsigned mask, int kind, unsigned long long val, int aux, unsigned *live_mask, const void *site = nullptr);
 void done(Snapshot *s);
 
 typedef void (*ThreadFn)(void *);
@@ -128,17 +128,17 @@ inline int __syncthreads_count(int pred) {
   emu::block_barrier_reduce(pred, &o, &a, &c);
   return c;
 }
-inline void __syncwarp(unsigned mask = 0xffffffffu) {
+__attribute__((noinline)) inline void __syncwarp(unsigned mask = 0xffffffffu) {
   unsigned live;
-  emu::done(emu::exchange(mask, emu::K_SYNCWARP, 0, 0, &live));
+  emu::done(emu::exchange(mask, emu::K_SYNCWARP, 0, 0, &live, __builtin_return_address(0)));
 }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 
 template <class T>
-inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+__attribute__((noinline)) inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL, emu::to_bits(v), 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL, emu::to_bits(v), 0, &live, __builtin_return_address(0));
   const int lane = emu::cur_lane();
   const int base = lane & ~(width - 1);
   const int sl = base + (src & (width - 1));
@@ -147,9 +147,9 @@ inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
   return r;
 }
 template <class T>
-inline T __shfl_xor_sync(unsigned mask, T v, int lm, int width = 32) {
+__attribute__((noinline)) inline T __shfl_xor_sync(unsigned mask, T v, int lm, int width = 32) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL_XOR, emu::to_bits(v), 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL_XOR, emu::to_bits(v), 0, &live, __builtin_return_address(0));
   const int lane = emu::cur_lane();
   const int sl = lane ^ lm;
   T r = (sl < 32 && ((live >> sl) & 1) && (sl & ~(width - 1)) == (lane & ~(width - 1))) ? emu::from_bits<T>(s->v[sl]) : v;
@@ -157,9 +157,9 @@ inline T __shfl_xor_sync(unsigned mask, T v, int lm, int width = 32) {
   return r;
 }
 template <class T>
-inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
+__attribute__((noinline)) inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL_UP, emu::to_bits(v), 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL_UP, emu::to_bits(v), 0, &live, __builtin_return_address(0));
   const int lane = emu::cur_lane();
   const int sl = lane - (int)d;
   T r = (sl >= (lane & ~(width - 1)) && ((live >> sl) & 1)) ? emu::from_bits<T>(s->v[sl]) : v;
@@ -167,36 +167,36 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
   return r;
 }
 template <class T>
-inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) {
+__attribute__((noinline)) inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL_DOWN, emu::to_bits(v), 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_SHFL_DOWN, emu::to_bits(v), 0, &live, __builtin_return_address(0));
   const int lane = emu::cur_lane();
   const int sl = lane + (int)d;
   T r = (sl < (lane & ~(width - 1)) + width && sl < 32 && ((live >> sl) & 1)) ? emu::from_bits<T>(s->v[sl]) : v;
   emu::done(s);
   return r;
 }
-inline unsigned __ballot_sync(unsigned mask, int pred) {
+__attribute__((noinline)) inline unsigned __ballot_sync(unsigned mask, int pred) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_BALLOT, pred ? 1ull : 0ull, 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_BALLOT, pred ? 1ull : 0ull, 0, &live, __builtin_return_address(0));
   unsigned r = 0;
   for (int l = 0; l < 32; l++)
     if (((live >> l) & 1) && s->v[l]) r |= 1u << l;
   emu::done(s);
   return r;
 }
-inline int __all_sync(unsigned mask, int pred) {
+__attribute__((noinline)) inline int __all_sync(unsigned mask, int pred) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_VOTE, pred ? 1ull : 0ull, 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_VOTE, pred ? 1ull : 0ull, 0, &live, __builtin_return_address(0));
   int r = 1;
   for (int l = 0; l < 32; l++)
     if (((live >> l) & 1) && !s->v[l]) r = 0;
   emu::done(s);
   return r;
 }
-inline int __any_sync(unsigned mask, int pred) {
+__attribute__((noinline)) inline int __any_sync(unsigned mask, int pred) {
   unsigned live;
-  emu::Snapshot *s = emu::exchange(mask, emu::K_VOTE, pred ? 1ull : 0ull, 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_VOTE, pred ? 1ull : 0ull, 0, &live, __builtin_return_address(0));
   int r = 0;
   for (int l = 0; l < 32; l++)
     if (((live >> l) & 1) && s->v[l]) r = 1;
@@ -204,10 +204,10 @@ inline int __any_sync(unsigned mask, int pred) {
   return r;
 }
 template <class T>
-inline unsigned __match_any_sync(unsigned mask, T v) {
+__attribute__((noinline)) inline unsigned __match_any_sync(unsigned mask, T v) {
   unsigned live;
   const unsigned long long b = emu::to_bits(v);
-  emu::Snapshot *s = emu::exchange(mask, emu::K_MATCH, b, 0, &live);
+  emu::Snapshot *s = emu::exchange(mask, emu::K_MATCH, b, 0, &live, __builtin_return_address(0));
   unsigned r = 0;
   for (int l = 0; l < 32; l++)
     if (((live >> l) & 1) && s->v[l] == b) r |= 1u << l;
@@ -215,9 +215,9 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
   return r;
 }
 #define EMU_REDUX(name, T, init, op)                                                  \
-  inline T name(unsigned mask, T v) {                                                 \
+  __attribute__((noinline)) inline T name(unsigned mask, T v) {                                                 \
     unsigned live;                                                                    \
-    emu::Snapshot *s = emu::exchange(mask, emu::K_REDUX, emu::to_bits(v), 0, &live);  \
+    emu::Snapshot *s = emu::exchange(mask, emu::K_REDUX, emu::to_bits(v), 0, &live, __builtin_return_address(0));  \
     T r = init;                                                                       \
     for (int l = 0; l < 32; l++)                                                      \
       if ((live >> l) & 1) {                                                          \

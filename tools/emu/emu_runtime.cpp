@@ -37,6 +37,7 @@ struct Fiber {
   int c_kind;
   unsigned long long c_val;
   int c_aux;
+  const void *c_site;
   Snapshot *c_snap;
   unsigned c_live;
 };
@@ -160,6 +161,15 @@ static bool try_complete(Fiber *f) {
     // never complete shows up as a deadlock
     if (o.c_mask != f->c_mask) return false;
     if (o.c_kind != f->c_kind) fail("lanes of one mask arrived at different collective operations");
+    // hardware needs the lanes of one collective at ONE instruction; the same source line reached through two inlined copies
+    // (a lambda called from two places, say) is two instructions.  g++ also duplicates calls on its own (both arms of a
+    // short-circuit `&&` in front of a ballot, for one), so under B200AT_EMU_STRICT this is a note to look at, not an error.
+    if (g_strict && o.c_site != f->c_site) {
+      static int notes = 0;
+      if (notes++ < 8)
+        fprintf(stderr, "[emu] note: collective kind %d, mask %08x in %s: lane %d at %p, lane %d at %p (addr2line -e <emu .so>)\n", f->c_kind,
+                f->c_mask, g_kernel_name, f->lane, f->c_site, o.lane, o.c_site);
+    }
   }
   Snapshot *s = g_free_snaps;
   if (s)
@@ -181,8 +191,9 @@ static bool try_complete(Fiber *f) {
   return true;
 }
 
-Snapshot *exchange(unsigned mask, int kind, unsigned long long val, int aux, unsigned *live_mask) {
+Snapshot *exchange(unsigned mask, int kind, unsigned long long val, int aux, unsigned *live_mask, const void *site) {
   Fiber *f = g_cur;
+  f->c_site = site;
   if (!((mask >> f->lane) & 1)) fail("calling lane is not in the collective's mask");
   f->c_mask = mask;
   f->c_kind = kind;
