@@ -133,6 +133,7 @@ struct cuAprilTagsHandle_st {
   FrameDesc *hp_frames = nullptr;
   FrameDesc *hp_src = nullptr;         // sparse host path: device-mapped addresses of the caller's frames
   bool sparse_bufs = false;            // need1 / need2 / src_frames / quad_H allocated
+  uint32_t sparse_skip = 0;            // calls left on the full copy after a sparse call that fetched nearly every row anyway
   b200AprilTagsDetection_t *hp_out = nullptr;
   uint32_t *hp_out_count = nullptr;
   uint32_t *hp_counters = nullptr;
@@ -1013,8 +1014,18 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   // quads are known, so only those rows are DMA'd; the full-resolution rows around the quads are fetched afterwards straight
   // from the caller's frames.  That needs pinned, device-mapped, 16-byte aligned host frames; anything else takes the full
   // copy.  B200AT_SPARSE_H2D=0/1 overrides the default.
+  // A frame that is covered with tags (a calibration grid) needs nearly every row: the sparse path then moves as many bytes as
+  // the full copy, in smaller pieces.  After such a call the next eight take the full copy, then sparse staging is tried again.
   bool sparse = kSparseHostPathDefault;
-  if (const char *es = getenv("B200AT_SPARSE_H2D")) sparse = atoi(es) != 0;
+  bool sparse_forced = false;
+  if (const char *es = getenv("B200AT_SPARSE_H2D")) {
+    sparse = atoi(es) != 0;
+    sparse_forced = true;
+  }
+  if (sparse && !sparse_forced && h->sparse_skip > 0) {
+    h->sparse_skip--;
+    sparse = false;
+  }
   if (g.f < 2 || (h->stage_pitch & 15)) sparse = false;
   if (sparse) {
     if (h->hp_src_cap < n) {
@@ -1293,6 +1304,11 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   h->last_counters[5] = dt;
   h->last_counters[6] = dma_bytes + fetched * 16;  // host->device bytes of this call: DMA + rows fetched on demand
   h->last_counters[7] = sparse ? 1 : 0;
+  {
+    const char *eb = getenv("B200AT_SPARSE_BACKOFF");
+    const double backoff = eb ? atof(eb) : 0.85;
+    if (sparse && (double)(dma_bytes + fetched * 16) > backoff * (double)row * g.H * n) h->sparse_skip = 8;
+  }
   return status ? B200AT_ERR_OVERFLOW : B200AT_OK;
 }
 

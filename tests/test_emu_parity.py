@@ -200,3 +200,25 @@ def test_emulated_host_path_after_encoding_change(pu):
         assert len(c) == 1 and b.tobytes() == c.tobytes()
         assert list(a["id"]) == list(c["id"])  # same image content through the mono8 path
     det.close()
+
+
+def test_emulated_sparse_staging_backs_off_on_tag_covered_frames(pu, monkeypatch):
+    """A frame covered with tags needs most full-resolution rows: after a sparse call that moved more than the back-off fraction of
+    the input (0.85 by default, B200AT_SPARSE_BACKOFF; 0.5 here so that a small frame triggers it) the next calls take the full
+    copy by themselves (B200AT_SPARSE_H2D unset), with identical results."""
+    from isaac_ros_apriltag_b200 import capi, synth
+    monkeypatch.setenv("B200AT_SPARSE_BACKOFF", "0.5")
+    rng = np.random.default_rng(4)
+    tags = [("tag36h11", i) for i in range(20)]
+    g, _ = synth.make_frame(rng, 400, 320, tags, grid=(5, 4, 80, 66))
+    frames = np.ascontiguousarray(np.repeat(g[None, :, :, None], 3, axis=3))
+    det = capi.Detector(400, 320, encoding="bgr8", max_batch=2, max_tags=32)
+    modes, res = [], []
+    for _ in range(3):
+        res.append(det.detect_host(frames)[0])
+        c = det.counters()
+        modes.append((c["sparse_h2d"], c["h2d_bytes"] / frames.nbytes))
+    assert modes[0][0] == 1 and modes[0][1] > 0.5, modes
+    assert modes[1][0] == 0 and modes[2][0] == 0 and modes[1][1] == 1.0, modes
+    assert len(res[0]) >= 4 and all(r.tobytes() == res[0].tobytes() for r in res)
+    det.close()
