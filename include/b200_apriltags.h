@@ -31,7 +31,14 @@
 #else
 /* layout-compatible stand-ins so plain C / ctypes / cgo callers need no CUDA headers */
 #ifndef __VECTOR_TYPES_H__
-typedef struct { float x, y; } float2;
+/* CUDA's float2 is __align__(8): the stand-in must be too, or cuAprilTagsID_t shrinks from 88 to 84 bytes */
+#if defined(__cplusplus)
+typedef struct alignas(8) { float x, y; } float2;
+#elif defined(_MSC_VER)
+typedef __declspec(align(8)) struct { float x, y; } float2;
+#else
+typedef struct { float x, y; } __attribute__((aligned(8))) float2;
+#endif
 typedef struct { unsigned char x, y, z; } uchar3;
 #endif
 #ifndef __DRIVER_TYPES_H__
@@ -56,7 +63,7 @@ typedef struct {
   uint8_t hamming_error;
   float orientation[9]; /* 3x3 rotation, COLUMN major, camera optical frame */
   float translation[3]; /* in units of tag_dim */
-} cuAprilTagsID_t;
+} cuAprilTagsID_t;         /* 88 bytes, 8-byte aligned (float2), orientation at offset 36 -- asserted in capi.cu and the node core */
 
 /* apriltag_node.cpp:481-486 */
 typedef struct {

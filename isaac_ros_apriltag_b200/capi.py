@@ -41,9 +41,9 @@ class Float2(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float)]
 
 
-class TagID(C.Structure):  # cuAprilTagsID_t
+class TagID(C.Structure):  # cuAprilTagsID_t: 88 bytes (CUDA's float2 is 8-byte aligned, so the struct has 4 bytes of tail padding)
     _fields_ = [("corners", Float2 * 4), ("id", C.c_uint16), ("hamming_error", C.c_uint8),
-                ("orientation", C.c_float * 9), ("translation", C.c_float * 3)]
+                ("orientation", C.c_float * 9), ("translation", C.c_float * 3), ("_tail_pad", C.c_uint32)]
 
 
 class ImageInput(C.Structure):  # cuAprilTagsImageInput_t
@@ -76,7 +76,7 @@ class Frame(C.Structure):  # b200AprilTagsFrame_t
 DET_DTYPE = np.dtype([("family", "<i4"), ("id", "<i4"), ("hamming", "<i4"), ("decision_margin", "<f4"), ("H", "<f8", (9,)),
                       ("c", "<f8", (2,)), ("p", "<f8", (4, 2)), ("R", "<f8", (9,)), ("t", "<f8", (3,)), ("pose_err", "<f8")])
 ID_DTYPE = np.dtype([("corners", "<f4", (4, 2)), ("id", "<u2"), ("hamming_error", "u1"), ("_pad", "u1"),
-                     ("orientation", "<f4", (9,)), ("translation", "<f4", (3,))])
+                     ("orientation", "<f4", (9,)), ("translation", "<f4", (3,)), ("_tail_pad", "<u4")])
 QUAD_DTYPE = np.dtype([("key", "<u8"), ("p", "<f4", (4, 2)), ("frame", "<u4"), ("reversed_border", "<u4")])
 CLUSTER_DTYPE = np.dtype([("key", "<u8"), ("offset", "<u4"), ("count", "<u4"), ("frame", "<u4"), ("pad", "<u4")])
 assert DET_DTYPE.itemsize == C.sizeof(Detection) and ID_DTYPE.itemsize == C.sizeof(TagID)

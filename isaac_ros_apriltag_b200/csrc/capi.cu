@@ -2,6 +2,7 @@
 // Part 1 entry points are the three symbols the reference node binds
 // (/root/reference/isaac_ros_apriltag/src/apriltag_node.cpp:450-452, 491-493, 556).
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,12 @@
 #include "tag_families_data.inc"
 
 using namespace b200at;
+
+// cuAprilTagsID_t as the reference node (compiled against CUDA's 8-byte aligned float2) lays it out; every in-repo caller
+// built WITHOUT CUDA headers must agree (include/b200_apriltags.h stand-in, capi.py TagID, apriltag_node_core.cpp)
+static_assert(sizeof(cuAprilTagsID_t) == 88 && alignof(cuAprilTagsID_t) == 8, "cuAprilTagsID_t layout");
+static_assert(offsetof(cuAprilTagsID_t, id) == 32 && offsetof(cuAprilTagsID_t, orientation) == 36 && offsetof(cuAprilTagsID_t, translation) == 72,
+              "cuAprilTagsID_t layout");
 
 namespace {
 
@@ -65,6 +72,7 @@ Tune parse_tune() {
   t.qf_keys23 = kTuneDefaultQfKeys23;
   t.qf_mc = kTuneDefaultQfMc;
   t.qf_sort = 0;
+  t.qf_exact = 0;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -89,6 +97,7 @@ Tune parse_tune() {
     else if (k == "qf_keys23") t.qf_keys23 = (int)v;
     else if (k == "qf_mc") t.qf_mc = (int)v;
     else if (k == "qf_sort") t.qf_sort = (int)v;
+    else if (k == "qf_exact") t.qf_exact = (int)v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;
@@ -478,6 +487,14 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   ws.tune = parse_tune();
   if (ws.tune.decode_split) ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
+  if (!ws.tune.qf_exact) {
+    ws.qwork_cap = (uint32_t)std::min<size_t>((size_t)g.pts_cap / kQfChunkMax + g.clu_cap, 0xfffffff0ull);
+    ALLOC(ws.qinfo, g.clu_cap);
+    ALLOC(ws.qwbase, g.clu_cap);
+    ALLOC(ws.qwork, ws.qwork_cap);
+    ALLOC(ws.qwtot, (size_t)ws.qwork_cap * 6);
+    ALLOC(ws.qwnmax, ws.qwork_cap);
+  }
   if (ws.tune.cluster_eager == 4) {
     ws.rec_cap = 2 * (int)Wp;  // points of one row: 0.64 per pixel on thresholded noise, at most 4
     ALLOC(ws.rec, (size_t)B * g.Hd * ws.rec_cap);
@@ -567,6 +584,9 @@ int nvCreateAprilTagsDetector(cuAprilTagsHandle *hApriltags, const uint32_t img_
   b200AprilTagsOptions_t opt;
   b200AprilTagsDefaultOptions(&opt);
   opt.tile_size = tile_size;
+  // the create call carries no max_tags (the node passes its parameter to cuAprilTagsDetect, apriltag_node.cpp:490-493): size the
+  // handle so that the caller's max_tags is the only truncation
+  opt.max_tags = 1024;
   return b200AprilTagsCreate(hApriltags, img_width, img_height, cam, tag_dim, &opt);
 }
 
@@ -636,6 +656,15 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
   v.errs += (size_t)2 * c * pc;
   v.clusters += (size_t)c * cc;
   v.bin_idx += (size_t)c * kQuadBins * cc;
+  if (v.qinfo) {
+    const uint32_t wc = h->ws.qwork_cap / nch;
+    v.qinfo += (size_t)c * cc;
+    v.qwbase += (size_t)c * cc;
+    v.qwork += (size_t)c * wc;
+    v.qwtot += (size_t)c * wc * 6;
+    v.qwnmax += (size_t)c * wc;
+    v.qwork_cap = wc;
+  }
   v.quads += (size_t)c * qc;
   v.quads_refined += (size_t)c * qc;
   v.cands += (size_t)f0 * g.cand_cap;
@@ -950,9 +979,12 @@ int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *det
   return h->last_status ? B200AT_ERR_OVERFLOW : B200AT_OK;
 }
 
+static cudaStream_t resolve_sync_stream(cuAprilTagsHandle h, cudaStream_t stream);
+
 int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, b200AprilTagsDetection_t *dets_out,
                              cuAprilTagsID_t *ids_out, uint32_t *counts, cudaStream_t stream) {
-  int rc = b200AprilTagsEnqueueBatch(h, frames, n, stream);
+  if (!h) return B200AT_ERR_INVALID_ARG;
+  int rc = b200AprilTagsEnqueueBatch(h, frames, n, resolve_sync_stream(h, stream));
   if (rc != B200AT_OK) return rc;
   return b200AprilTagsCollectBatch(h, dets_out, ids_out, counts);
 }
@@ -1312,6 +1344,23 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
   return status ? B200AT_ERR_OVERFLOW : B200AT_OK;
 }
 
+// A caller that passes the legacy default stream (nullptr) still gets the CUDA-graph replay path: capture is not possible on
+// the legacy stream, so the batch runs on the handle's own stream, ordered after whatever the caller queued on the legacy
+// stream before the call (the call is synchronous, so everything the caller queues afterwards is ordered by the host).
+static cudaStream_t resolve_sync_stream(cuAprilTagsHandle h, cudaStream_t stream) {
+  if (stream != nullptr) return stream;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaStream_t use = h->own_stream;
+  if (cudaEventRecord(h->ev_pipe_start, cudaStreamLegacy) != cudaSuccess || cudaStreamWaitEvent(h->own_stream, h->ev_pipe_start, 0) != cudaSuccess) {
+    cudaGetLastError();
+    use = nullptr;  // (cannot order against the legacy stream: run there, without the graph)
+  }
+  if (prev != h->device) cudaSetDevice(prev);
+  return use;
+}
+
 uint32_t cuAprilTagsDetect(cuAprilTagsHandle h, const cuAprilTagsImageInput_t *img, cuAprilTagsID_t *tags_out, uint32_t *num_tags,
                            const uint32_t max_tags, cudaStream_t stream) {
   if (!h || !img || !tags_out || !num_tags) return B200AT_ERR_INVALID_ARG;
@@ -1321,14 +1370,17 @@ uint32_t cuAprilTagsDetect(cuAprilTagsHandle h, const cuAprilTagsImageInput_t *i
   fr.ptr = img->dev_ptr;
   fr.pitch = img->pitch;
   uint32_t cnt = 0;
-  int rc = b200AprilTagsEnqueueBatch(h, &fr, 1, stream);
+  int rc = b200AprilTagsEnqueueBatch(h, &fr, 1, resolve_sync_stream(h, stream));
   if (rc != B200AT_OK) return (uint32_t)rc;
   rc = b200AprilTagsCollectBatch(h, nullptr, nullptr, &cnt);
   if (rc != B200AT_OK && rc != B200AT_ERR_OVERFLOW) return (uint32_t)rc;
   if (cnt > max_tags) cnt = max_tags;
   for (uint32_t k = 0; k < cnt; k++) to_id_struct(h->h_out[k], tags_out + k);
   *num_tags = cnt;
-  return rc == B200AT_ERR_OVERFLOW ? (uint32_t)rc : 0u;
+  // A bounded buffer that overflowed truncates the list; the detections that were written are valid.  The reference's caller
+  // drops the whole frame on ANY non-zero return (apriltag_node.cpp:494-497), so truncation is reported through
+  // b200AprilTagsLastStatus only, like a cuAprilTags detector that fills max_tags entries and returns success.
+  return 0u;
 }
 
 int b200AprilTagsLastStatus(cuAprilTagsHandle h, uint32_t *status) {

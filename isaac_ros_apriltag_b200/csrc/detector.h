@@ -64,8 +64,15 @@ struct Cand {  // decoded candidate before reconcile
 // counters[] slots
 enum { CNT_CLUSTERS = 0, CNT_POINTS = 1, CNT_QUADS = 2, CNT_STATUS = 3, CNT_CANDS = 4, CNT_DETS = 5,
        CNT_FETCHED = 6 /* 16-byte chunks fetched on demand from the caller's host frames (sparse host path) */, CNT_WORK_DECODE = 7,
-       CNT_BIN0 = 8 /* ..15: clusters per size bin */, CNT_WORK0 = 16 /* ..23: quad-fit work queues */, CNT_N = 24 };
+       CNT_BIN0 = 8 /* ..15: clusters per size bin */, CNT_WORK0 = 16 /* ..23: quad-fit work queues */,
+       CNT_QWORK = 24 /* (cluster, chunk) work items registered by k_qf_sort */, CNT_Q2 = 25, CNT_Q3 = 26 /* work queues of k_qf_window / k_qf_tail */,
+       CNT_N = 32 };
 constexpr int kQuadBins = 8;
+// windowed quad fit (k_quad2.cu): a warp of k_qf_window holds kQfSlotsPerLane * 32 sorted points (chunk + circular halo of at most
+// 2 * 20 + 9 points) in shared memory; a cluster of n points is cut into qf_nchunks(n) balanced chunks
+constexpr int kQfSlotsPerLane = 7;   // odd: the lane-blocked 8-byte accesses are bank-conflict free
+constexpr int kQfChunkMax = 32 * kQfSlotsPerLane - 49;
+__host__ __device__ inline int qf_nchunks(int n) { return (n + kQfChunkMax - 1) / kQfChunkMax; }
 constexpr int kQuadAux = kQuadBins - 1;  // side streams: the quad-fit bins run concurrently
 constexpr int kMaxChunks = 4;  // a batch is processed as up to 4 frame chunks on two phase-shifted streams
 enum { ST_HASH_FULL = 1, ST_POINTS_FULL = 2, ST_CLUSTERS_FULL = 4, ST_QUADS_FULL = 8, ST_CANDS_FULL = 16, ST_OUT_TRUNC = 32 };
@@ -125,6 +132,8 @@ struct Tune {
   int qf_sort;        // quad fit sort: serial merge with one-key lookahead per run (refill loads off the critical path)
   float qf_scale;     // scales the persistent grid of every quad-fit bin
   int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
+  int qf_exact;       // 1 = k_quad.cu (one CTA per cluster, serial prefix sums: float corners bit-identical to the CPU oracle);
+                      // 0 = k_quad2.cu (sort / windowed moments / tail: same formulas, prefix sums associated differently)
 };
 
 struct Workspace {
@@ -154,6 +163,13 @@ struct Workspace {
   unsigned long long *need1, *need2;  // [B][H] rows needed by refine_edges / by the decode samples
   FrameDesc *src_frames;       // [B] device-accessible addresses of the caller's (pinned) host frames
   double *quad_H;              // [quad_cap][10]: H[0..8], valid flag
+  // windowed quad fit (k_quad2.cu)
+  uint32_t *qinfo;             // [clu_cap] 0 = rejected before the sort, else point count | reversed_border << 31
+  uint32_t *qwbase;            // [clu_cap] first work item of the cluster (its chunks are consecutive)
+  uint2 *qwork;                // [qwork_cap] (cluster, chunk)
+  uint32_t qwork_cap;
+  double *qwtot;               // [qwork_cap][6] moment totals of the chunk
+  uint32_t *qwnmax;            // [qwork_cap] local maxima found in the chunk
   // cluster_eager=4: per-row lists of (table slot, packed point) written by the count pass, consumed by k_cluster_scatter
   uint2 *rec;
   uint32_t *rec_cnt;
@@ -177,7 +193,9 @@ int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s);
-int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s);
+int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s);           // dispatches on Tune::qf_exact
+int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s);  // k_quad2.cu
+void launch_bin_clusters(const Workspace &ws, int sms, cudaStream_t s);         // k_quad.cu (shared by both)
 int launch_decode(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_sparse_fetch1(const Workspace &ws, int nframes, cudaStream_t s);  // sparse host path: mark + fetch for refine_edges
 int launch_sparse_back(const Workspace &ws, int nframes, cudaStream_t s);    // ... refine, second fetch, decode

@@ -547,8 +547,9 @@ __global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned l
   for (uint32_t i0 = 0; i0 < seg_len; i0 += 1024) {
     const uint32_t i = i0 + tid;
     uint32_t c = (i < seg_len) ? hcnt[ho + i] : 0;
-    const bool keep = ok && c >= 24u && c <= g.max_cluster_pts;
-    uint32_t fc = keep ? 1u : 0u, fp = keep ? c : 0u;
+    const bool would_keep = c >= 24u && c <= g.max_cluster_pts;
+    const bool keep = ok && would_keep;
+    uint32_t fc = would_keep ? 1u : 0u, fp = would_keep ? c : 0u;  // (positions are those of the reservation, kept or not)
     // inclusive warp scan
     uint32_t ic = fc, ip = fp;
     for (int o = 1; o < 32; o <<= 1) {
@@ -591,6 +592,9 @@ __global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned l
         clusters[s_base_c + ec] = r;
         hoff[ho + i] = s_base_p + ep;
       } else {
+        // A reservation that did not fit keeps its range of the cluster list (the counter stays advanced): its records are
+        // written EMPTY (count 0), so that a consumer that walks [0, min(CNT_CLUSTERS, clu_cap)) never reads a stale record.
+        if (!ok && would_keep && s_base_c + ec < g.clu_cap) clusters[s_base_c + ec] = ClusterRec{hkey[ho + i], 0u, 0u, (uint32_t)fr, 0u};
         hoff[ho + i] = 0xffffffffu;
       }
       hcur[ho + i] = 0;

@@ -1,0 +1,721 @@
+// k_quad2.cu -- fit_quads (a10), windowed three-kernel pipeline (the default; k_quad.cu is the bit-exact one-CTA-per-cluster form).
+// Restates AprilRobotics fit_quad / ptsort / compute_lfps / quad_segment_maxima / fit_line (apriltag_quad_thresh.c; SURVEY
+// App. A.5; oracle/apriltag_oracle.cpp:454-764).
+//
+// What makes fit_quad expensive per boundary point is (1) the sort by angle and (2) one line fit per point over a +-ksz
+// window (ksz <= 20), smoothing and local maxima.  Only (1) needs the whole cluster in one place.  (2) is LOCAL: the window
+// moments are differences of prefix sums taken 2*ksz+1 points apart, so any prefix base cancels -- a chunk of consecutive
+// sorted points plus a circular halo of ksz+5 / ksz+4 points is enough, and what the later stages need from the global prefix
+// sums is their value at <= max_nmaxima points per cluster.  Hence:
+//   k_qf_sort   per cluster (size bins): bounding box, polarity, slope keys, shared-memory merge sort; writes the sorted points
+//               with their gradient magnitude (8 B / point: y, x, |grad|^2) and registers the cluster's chunks as work items.
+//               Shared memory: 16 B / point (the exact kernel keeps 64 B / point resident: keys, errors, six prefix moments).
+//   k_qf_window flat over (cluster, chunk) work items, one warp each: line-fit terms, chunk-local prefix moments (lane-serial +
+//               one warp scan), window error, 7-tap smoothing, local maxima -> per maximum {index, error, chunk-local prefix
+//               moments}, per chunk its moment totals.  No dependence between work items: the 8192-point cluster that took
+//               one 512-thread CTA for a millisecond is now 47 independent warps.
+//   k_qf_tail   per cluster, one warp: the max_nmaxima best maxima, their global prefix moments (chunk totals + local prefix),
+//               pair table of line fits, C(n,4) search, corners, area / angle gates (same code shape as the exact kernel).
+// Floating point: every formula is the oracle's; what differs is the ASSOCIATION of the prefix sums (lane-serial + tree instead
+// of one serial chain) and one reciprocal-multiply instead of five divisions in the per-point window fit.  Effect: window
+// errors agree to ~1e-12 relative; the float quad corners are bit-identical except where a double lands within that distance
+// of a float rounding boundary or two maxima tie within it (tests state the tolerance and count the differences).
+#include <algorithm>
+#include <cstdlib>
+
+#include "k_quad_common.cuh"
+
+namespace b200at {
+
+struct MaxRec {  // one local maximum of the smoothed window error, written by k_qf_window
+  uint32_t idx, pad;
+  double y;
+  double P[6];   // inclusive prefix moments at idx relative to the first point of its chunk
+};
+static_assert(sizeof(MaxRec) == 64, "MaxRec layout");
+
+// chunk c of nch of a cluster of n sorted points: [s, e)
+__device__ __forceinline__ void qf_chunk_bounds(int n, int nch, int c, int &s, int &e) {
+  s = (int)((long long)c * n / nch);
+  e = (int)((long long)(c + 1) * n / nch);
+}
+// first record of chunk c in the cluster's maxima region (a chunk of len points has at most ceil(len / 2) maxima)
+__device__ __forceinline__ int qf_chunk_rec0(int s, int c) { return (s + 1) / 2 + c; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_qf_sort
+// ---------------------------------------------------------------------------------------------------------------------
+// WPC > 1 (one-warp clusters): WPC independent cluster workers per CTA, one warp each, no block-wide barrier anywhere.
+template <int THREADS, int NCAP, bool SM, int ITEMS, int MINB, int WPC>
+__global__ void __launch_bounds__(THREADS *WPC, MINB)
+    k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
+              const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
+              const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work,
+              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
+  constexpr int NW = THREADS / 32;
+  constexpr int PPT = SM ? NCAP / THREADS : 1;
+  static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
+  extern __shared__ unsigned long long dsm_sort[];
+  const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
+  unsigned long long *skeys = dsm_sort + (size_t)grp * 2 * NCAP;
+  unsigned long long *stmp = skeys + NCAP;
+  __shared__ BBoxRed s_red_a[WPC][NW];
+  __shared__ int s_cluster_a[WPC];
+  BBoxRed *s_red = s_red_a[grp];
+  const int tid = WPC > 1 ? (int)(threadIdx.x % THREADS) : (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
+  for (;;) {
+    cta_sync<THREADS>();
+    if (tid == 0) s_cluster_a[grp] = (int)atomicAdd(&counters[CNT_WORK0 + bin], 1u);
+    cta_sync<THREADS>();
+    const int cw = s_cluster_a[grp];
+    if ((uint32_t)cw >= nbin) break;
+    const uint32_t ci = bin_idx[(size_t)bin * g.clu_cap + cw];
+    const ClusterRec cr = clusters[ci];
+    const int sz = (int)cr.count;
+    const uint32_t o = cr.offset;
+    const uint8_t *im = dec + (size_t)cr.frame * g.Hd * Wp;
+    unsigned long long *keys_g = keys + o;
+
+    // ---- bounding box + integer sums for the border-polarity test ----
+    uint32_t pr[PPT];
+    BBoxRed r = {1 << 30, -1, 1 << 30, -1, 0, 0, 0};
+    if (SM) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const int i = tid + k * THREADS;
+        pr[k] = i < sz ? pts[o + i] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; k++)
+        if (tid + k * THREADS < sz) bbox_add(r, pr[k]);
+    } else {
+      for (int i = tid; i < sz; i += THREADS) bbox_add(r, pts[o + i]);
+    }
+    for (int of = 16; of > 0; of >>= 1) {
+      r.xmin = min(r.xmin, __shfl_xor_sync(0xffffffffu, r.xmin, of));
+      r.xmax = max(r.xmax, __shfl_xor_sync(0xffffffffu, r.xmax, of));
+      r.ymin = min(r.ymin, __shfl_xor_sync(0xffffffffu, r.ymin, of));
+      r.ymax = max(r.ymax, __shfl_xor_sync(0xffffffffu, r.ymax, of));
+      r.sgx += __shfl_xor_sync(0xffffffffu, r.sgx, of);
+      r.sgy += __shfl_xor_sync(0xffffffffu, r.sgy, of);
+      r.s1 += __shfl_xor_sync(0xffffffffu, r.s1, of);
+    }
+    if (NW > 1) {
+      if (lane == 0) s_red[wid] = r;
+      __syncthreads();
+      r = s_red[0];
+      for (int w = 1; w < NW; w++) {
+        BBoxRed q = s_red[w];
+        r.xmin = min(r.xmin, q.xmin);
+        r.xmax = max(r.xmax, q.xmax);
+        r.ymin = min(r.ymin, q.ymin);
+        r.ymax = max(r.ymax, q.ymax);
+        r.sgx += q.sgx;
+        r.sgy += q.sgy;
+        r.s1 += q.s1;
+      }
+    }
+    const float cx = (float)((r.xmin + r.xmax) * 0.5 + 0.05118);
+    const float cy = (float)((r.ymin + r.ymax) * 0.5 + -0.028581);
+    // dot = sum (x-cx)*gx + (y-cy)*gy, evaluated exactly on the integer parts (order independent)
+    const double dotd = (double)r.s1 - (double)cx * (double)r.sgx - (double)cy * (double)r.sgy;
+    const bool reversed = dotd < 0;
+    bool drop = (r.xmax - r.xmin) * (r.ymax - r.ymin) < fp.tag_width;
+    drop = drop || (!fp.reversed_border && reversed) || (!fp.normal_border && !reversed);
+    if (drop) {  // (uniform over the cluster's threads)
+      if (tid == 0) qinfo[ci] = 0u;
+      continue;
+    }
+
+    // ---- sort keys (slope | y | x) ----
+    if (SM) {
+#pragma unroll
+      for (int k = 0; k < PPT; k++) {
+        const int i = tid + k * THREADS;
+        if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
+      }
+      cta_sync<THREADS>();
+      sort_keys<THREADS, ITEMS, false>(skeys, stmp, sz, tid);
+      // sorted points out; the slope half of a key is dead, it now carries the squared gradient magnitude of the decimated image
+      // at the point (compute_lfps' weight is sqrt of it, + 1): four gathers in flight per thread
+      for (int i = tid; i < sz; i += 4 * THREADS) {
+        unsigned long long k[4];
+        int g2[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) k[u] = (i + u * THREADS < sz) ? skeys[i + u * THREADS] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, k[u]) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (k[u] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[u] << 32);
+      }
+    } else {
+      for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
+      cta_sync<THREADS>();
+      sort_keys<THREADS, ITEMS, false>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
+      for (int i = tid; i < sz; i += THREADS) {
+        const unsigned long long k = keys_g[i];
+        keys_g[i] = (k & 0xffffffffull) | ((unsigned long long)(uint32_t)grad2_at(im, Wp, g.Wd, g.Hd, k) << 32);
+      }
+    }
+    // ---- the cluster's chunks become work items of k_qf_window ----
+    if (tid == 0) {
+      const int nch = qf_nchunks(sz);
+      const uint32_t wb = atomicAdd(&counters[CNT_QWORK], (uint32_t)nch);
+      if (wb + (uint32_t)nch <= work_cap) {
+        for (int c = 0; c < nch; c++) work[wb + c] = make_uint2(ci, (uint32_t)c);
+        qwbase[ci] = wb;
+        qinfo[ci] = (uint32_t)sz | (reversed ? 0x80000000u : 0u);
+      } else {  // (cannot happen with the capacity capi.cu allocates: pts_cap / kQfChunkMax + clu_cap)
+        qinfo[ci] = 0u;
+        atomicOr(&counters[CNT_STATUS], (uint32_t)ST_QUADS_FULL);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_qf_window
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int QW_WARPS = 4;
+constexpr int QW_SLOTS = 32 * kQfSlotsPerLane;
+
+__global__ void __launch_bounds__(32 * QW_WARPS)
+    k_qf_window(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ qinfo,
+                const uint2 *__restrict__ work, uint32_t work_cap, const unsigned long long *__restrict__ keys,
+                LineFitPt *__restrict__ lfps_pool, double *__restrict__ wtot, uint32_t *__restrict__ wnmax,
+                uint32_t *__restrict__ counters) {
+  constexpr int PPL = kQfSlotsPerLane, SLOTS = QW_SLOTS;
+  extern __shared__ double dsm_win[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *P = dsm_win + (size_t)wid * (8 * SLOTS);  // [6][SLOTS] prefix moments (SoA)
+  double *E = P + 6 * SLOTS;                        // [SLOTS] staged keys, then window errors
+  double *Y = E + SLOTS;                            // [SLOTS] smoothed errors
+  const uint32_t nwork = min(counters[CNT_QWORK], work_cap);
+  const double f0 = (double)fp.smooth[0], f1 = (double)fp.smooth[1], f2 = (double)fp.smooth[2], f3 = (double)fp.smooth[3],
+               f4 = (double)fp.smooth[4], f5 = (double)fp.smooth[5], f6 = (double)fp.smooth[6];
+  for (;;) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&counters[CNT_Q2], 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= nwork) break;
+    const uint2 wk = work[w];
+    const uint32_t off = clusters[wk.x].offset;
+    const int n = (int)(qinfo[wk.x] & 0x7fffffffu);
+    const int nch = qf_nchunks(n), c = (int)wk.y;
+    int s, e;
+    qf_chunk_bounds(n, nch, c, s, e);
+    const int len = e - s;
+    const int ksz = min(20, n / 12);
+    const int HL = ksz + 5;            // halo: ksz + 5 points before the chunk, ksz + 4 after (circular)
+    const int L = len + 2 * ksz + 9;   // <= SLOTS by the choice of kQfChunkMax
+    const unsigned long long *kg = keys + off;
+    unsigned long long *Ek = reinterpret_cast<unsigned long long *>(E);
+    for (int j = lane; j < L; j += 32) {
+      int gi = s - HL + j;
+      gi = gi < 0 ? gi + n : gi;
+      gi = gi >= n ? gi - n : gi;
+      Ek[j] = kg[gi];
+    }
+    __syncwarp();
+    // line-fit terms and prefix moments: a lane owns PPL consecutive slots (serial chain), one warp scan joins the lanes
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < PPL; q++) {
+      const int sl = lane * PPL + q;
+      if (sl < L) {
+        const unsigned long long k = Ek[sl];
+        double t[6];
+        lfp_terms(k, (int)(k >> 32), t);
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          acc[m] += t[m];
+          P[m * SLOTS + sl] = acc[m];
+        }
+      }
+    }
+    double lo[6];
+#pragma unroll
+    for (int m = 0; m < 6; m++) {
+      double v = acc[m];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += u;
+      }
+      lo[m] = __shfl_up_sync(0xffffffffu, v, 1);  // sum of the lanes before mine
+    }
+    if (lane > 0) {
+#pragma unroll
+      for (int q = 0; q < PPL; q++) {
+        const int sl = lane * PPL + q;
+        if (sl < L) {
+#pragma unroll
+          for (int m = 0; m < 6; m++) P[m * SLOTS + sl] += lo[m];
+        }
+      }
+    }
+    __syncwarp();
+    // window error of slot j: line fit over slots [j - ksz, j + ksz] (fit_line(i - ksz, i + ksz): N = 2 ksz + 1 points)
+    const double Nd = (double)(2 * ksz + 1);
+    for (int j = ksz + 1 + lane; j < ksz + len + 9; j += 32) {
+      const int a = j - ksz - 1, b = j + ksz;
+      const double Mx = P[b] - P[a];
+      const double My = P[SLOTS + b] - P[SLOTS + a];
+      const double Mxx = P[2 * SLOTS + b] - P[2 * SLOTS + a];
+      const double Mxy = P[3 * SLOTS + b] - P[3 * SLOTS + a];
+      const double Myy = P[4 * SLOTS + b] - P[4 * SLOTS + a];
+      const double W = P[5 * SLOTS + b] - P[5 * SLOTS + a];
+      const double rw = __drcp_rn(W);
+      const double Ex = Mx * rw, Ey = My * rw;
+      const double Cxx = Mxx * rw - Ex * Ex;
+      const double Cxy = Mxy * rw - Ex * Ey;
+      const double Cyy = Myy * rw - Ey * Ey;
+      const double disc = (double)sqrtf((float)((Cxx - Cyy) * (Cxx - Cyy) + 4 * Cxy * Cxy));
+      E[j] = Nd * (0.5 * (Cxx + Cyy - disc));
+    }
+    __syncwarp();
+    // 7-tap smoothing (the oracle's accumulation order)
+    for (int j = HL - 1 + lane; j < HL + len + 1; j += 32) {
+      double y = 0;
+      y += E[j - 3] * f0;
+      y += E[j - 2] * f1;
+      y += E[j - 1] * f2;
+      y += E[j] * f3;
+      y += E[j + 1] * f4;
+      y += E[j + 2] * f5;
+      y += E[j + 3] * f6;
+      Y[j] = y;
+    }
+    __syncwarp();
+    // local maxima of the chunk's own points, in index order, into the chunk's slice of the cluster's maxima region
+    MaxRec *mr = reinterpret_cast<MaxRec *>(lfps_pool + off) + qf_chunk_rec0(s, c);
+    int run = 0;
+    for (int j0 = HL; j0 < HL + len; j0 += 32) {
+      const int j = j0 + lane;
+      bool is = false;
+      double y = 0;
+      if (j < HL + len) {
+        y = Y[j];
+        is = y > Y[j + 1] && y > Y[j - 1];
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, is);
+      if (is) {
+        MaxRec rec;
+        rec.idx = (uint32_t)(s + j - HL);
+        rec.pad = 0;
+        rec.y = y;
+#pragma unroll
+        for (int m = 0; m < 6; m++) rec.P[m] = P[m * SLOTS + j] - P[m * SLOTS + HL - 1];
+        mr[run + __popc(bal & ((1u << lane) - 1u))] = rec;
+      }
+      run += __popc(bal);
+    }
+    if (lane < 6) wtot[(size_t)w * 6 + lane] = P[lane * SLOTS + HL + len - 1] - P[lane * SLOTS + HL - 1];
+    if (lane == 0) wnmax[w] = (uint32_t)run;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_qf_tail
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int QT_WARPS = 4;
+constexpr int QT_LIN = 512;  // maxima of a cluster held in shared memory for the top-k selection (more: the global scratch)
+
+__global__ void __launch_bounds__(32 * QT_WARPS)
+    k_qf_tail(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ qinfo,
+              const uint32_t *__restrict__ qwbase, const unsigned long long *__restrict__ keys, const LineFitPt *__restrict__ lfps_pool,
+              double *__restrict__ errs_pool, const double *__restrict__ wtot, const uint32_t *__restrict__ wnmax,
+              QuadRec *__restrict__ quads, uint32_t *__restrict__ counters, ComboTable combos) {
+  constexpr int TBL = MAXM * MAXM;
+  __shared__ double s_G_a[QT_WARPS][MAXM][6];    // global inclusive prefix moments at the kept maxima
+  __shared__ double s_H_a[QT_WARPS][MAXM][6];    // ... at the point before each kept maximum (0 for point 0)
+  __shared__ double s_T_a[QT_WARPS][6];          // moments of the whole cluster
+  __shared__ double s_tab_a[QT_WARPS][3 * TBL];  // pair tables: mse, nx, ny
+  __shared__ double s_val_a[QT_WARPS][QT_LIN];
+  __shared__ int s_fm_a[QT_WARPS][MAXM];
+  __shared__ int s_kp_a[QT_WARPS][MAXM];         // ordinal (position in index order) of each kept maximum
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double(*s_G)[6] = s_G_a[wid];
+  double(*s_H)[6] = s_H_a[wid];
+  double *s_T = s_T_a[wid];
+  double *pt_mse = s_tab_a[wid], *pt_nx = pt_mse + TBL, *pt_ny = pt_nx + TBL;
+  double *s_val = s_val_a[wid];
+  int *s_fm = s_fm_a[wid], *s_kp = s_kp_a[wid];
+  const uint32_t ncl = min(counters[CNT_CLUSTERS], g.clu_cap);
+  for (;;) {
+    __syncwarp();
+    uint32_t ci = 0;
+    if (lane == 0) ci = atomicAdd(&counters[CNT_Q3], 1u);
+    ci = __shfl_sync(0xffffffffu, ci, 0);
+    if (ci >= ncl) break;
+    const uint32_t info = qinfo[ci];
+    if (info == 0u) continue;
+    const int sz = (int)(info & 0x7fffffffu);
+    const bool reversed = (info >> 31) != 0u;
+    const ClusterRec cr = clusters[ci];
+    const uint32_t wb = qwbase[ci];
+    const int nch = qf_nchunks(sz);
+    const MaxRec *mbase = reinterpret_cast<const MaxRec *>(lfps_pool + cr.offset);
+    int m = 0;
+    for (int c = 0; c < nch; c++) m += (int)wnmax[wb + c];
+    if (m < 4) continue;
+    // record of the maximum with ordinal p (index order: chunk by chunk)
+    auto rec_of = [&](int p, int &chunk) -> const MaxRec * {
+      int c = 0, base = 0;
+      for (;;) {
+        const int cnt = (int)wnmax[wb + c];
+        if (p < base + cnt || c == nch - 1) break;
+        base += cnt;
+        c++;
+      }
+      int s, e;
+      qf_chunk_bounds(sz, nch, c, s, e);
+      chunk = c;
+      return mbase + qf_chunk_rec0(s, c) + (p - base);
+    };
+    // ---- keep the max_nmaxima best: threshold = value of descending rank max_nmaxima, keep err > threshold ----
+    int nm = 0;
+    if (m <= 32) {
+      int chunk = 0;
+      double v = -CUDART_INF;
+      if (lane < m) v = rec_of(lane, chunk)->y;
+      bool keep = lane < m;
+      if (m > fp.max_nmaxima) {
+        int rank = 0;
+        for (int j = 0; j < m; j++) {
+          const double u = __shfl_sync(0xffffffffu, v, j);
+          rank += (u > v || (u == v && j < lane)) ? 1 : 0;
+        }
+        const unsigned tb = __ballot_sync(0xffffffffu, lane < m && rank == fp.max_nmaxima);
+        const double thresh = __shfl_sync(0xffffffffu, v, __ffs(tb) - 1);
+        keep = keep && !(v <= thresh);
+      }
+      const unsigned kb = __ballot_sync(0xffffffffu, keep);
+      nm = min(__popc(kb), MAXM);
+      if (keep) {
+        const int pos = __popc(kb & ((1u << lane) - 1u));
+        if (pos < MAXM) s_kp[pos] = lane;
+      }
+    } else {
+      // values in index order into a linear array (shared memory, or the cluster's slice of the global scratch)
+      double *val = m <= QT_LIN ? s_val : errs_pool + (size_t)2 * cr.offset;
+      {
+        int base = 0;
+        for (int c = 0; c < nch; c++) {
+          const int cnt = (int)wnmax[wb + c];
+          int s, e;
+          qf_chunk_bounds(sz, nch, c, s, e);
+          const MaxRec *rc = mbase + qf_chunk_rec0(s, c);
+          for (int p = lane; p < cnt; p += 32) val[base + p] = rc[p].y;
+          base += cnt;
+        }
+      }
+      __syncwarp();
+      // element of rank r in the order (value descending, position ascending), r = 0 .. max_nmaxima: one pass per rank
+      double pv = CUDART_INF;
+      int pp = -1;
+      for (int round = 0; round <= fp.max_nmaxima; round++) {
+        double bv = -CUDART_INF;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < m; i += 32) {
+          const double v = val[i];
+          const bool after = v < pv || (v == pv && i > pp);  // not yet taken
+          if (after && (v > bv || (v == bv && i < bi))) {
+            bv = v;
+            bi = i;
+          }
+        }
+        for (int of = 16; of > 0; of >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, of);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, of);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        pv = bv;
+        pp = bi;
+      }
+      const double thresh = pv;  // value of rank max_nmaxima (m > 32 > max_nmaxima here)
+      int run = 0;
+      for (int i0 = 0; i0 < m; i0 += 32) {
+        const int i = i0 + lane;
+        const bool keep = i < m && !(val[i] <= thresh);
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int pos = run + __popc(kb & ((1u << lane) - 1u));
+          if (pos < MAXM) s_kp[pos] = i;
+        }
+        run += __popc(kb);
+      }
+      nm = min(run, MAXM);
+    }
+    __syncwarp();
+    if (nm < 4) continue;
+    // ---- global prefix moments at the kept maxima: totals of the chunks before + chunk-local prefix ----
+    if (lane < nm) {
+      int chunk = 0;
+      const MaxRec *rc = rec_of(s_kp[lane], chunk);
+      const uint32_t idx = rc->idx;
+      double G[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) G[q] = 0;
+      for (int c = 0; c < chunk; c++) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) G[q] += wtot[(size_t)(wb + c) * 6 + q];
+      }
+      const unsigned long long k = keys[cr.offset + idx];
+      double t[6];
+      lfp_terms(k, (int)(k >> 32), t);
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        G[q] += rc->P[q];
+        s_G[lane][q] = G[q];
+        s_H[lane][q] = idx == 0 ? 0.0 : G[q] - t[q];
+      }
+      s_fm[lane] = (int)idx;
+    }
+    if (lane < 6) {
+      double T = 0;
+      for (int c = 0; c < nch; c++) T += wtot[(size_t)(wb + c) * 6 + lane];
+      s_T[lane] = T;
+    }
+    __syncwarp();
+    // fit_line between kept maxima a -> b (oracle fit_line: prefix difference, wrapping when i0 > i1)
+    auto fit_pair = [&](int a, int b, double *lineparm, double *mse) {
+      const int i0 = s_fm[a], i1 = s_fm[b];
+      double M[6];
+      int N;
+      if (i0 < i1) {
+        N = i1 - i0 + 1;
+#pragma unroll
+        for (int q = 0; q < 6; q++) M[q] = s_G[b][q];
+        if (i0 > 0) {
+#pragma unroll
+          for (int q = 0; q < 6; q++) M[q] -= s_H[a][q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          M[q] = s_T[q] - s_H[a][q];
+          M[q] += s_G[b][q];
+        }
+        N = sz - i0 + i1 + 1;
+      }
+      fit_moments_dev(M[0], M[1], M[2], M[3], M[4], M[5], N, lineparm, nullptr, mse);
+    };
+    // ---- pair table ----
+    for (int t = lane; t < nm * nm; t += 32) {
+      const int a = t / nm, b = t - a * nm;
+      if (a == b) continue;
+      double lp[4], ms;
+      fit_pair(a, b, lp, &ms);
+      pt_mse[a * MAXM + b] = ms;
+      pt_nx[a * MAXM + b] = lp[2];
+      pt_ny[a * MAXM + b] = lp[3];
+    }
+    __syncwarp();
+    // ---- best (m0<m1<m2<m3); ties resolved to the lexicographically first, like the serial loops ----
+    double best = CUDART_INF;
+    uint32_t brank = 0xffffffffu;
+    {
+      const double max_mse = (double)fp.max_line_fit_mse, max_dot = (double)fp.cos_critical_rad;
+      const uchar4 *ctab = combos.c + combos.off[nm];
+      const int ncomb = combos.off[nm + 1] - combos.off[nm];
+      auto seg_err = [&](int a, int b, double mse) {
+        const int i0 = s_fm[a], i1 = s_fm[b];
+        const int N = i0 < i1 ? i1 - i0 + 1 : sz - i0 + i1 + 1;
+        return N * mse;
+      };
+      for (int t = lane; t < ncomb; t += 32) {
+        const uchar4 c = ctab[t];
+        const int m0 = c.x, m1 = c.y, m2 = c.z, m3 = c.w;
+        const double mse01 = pt_mse[m0 * MAXM + m1];
+        if (mse01 > max_mse) continue;
+        const double mse12 = pt_mse[m1 * MAXM + m2];
+        if (mse12 > max_mse) continue;
+        const double dot = pt_nx[m0 * MAXM + m1] * pt_nx[m1 * MAXM + m2] + pt_ny[m0 * MAXM + m1] * pt_ny[m1 * MAXM + m2];
+        if (fabs(dot) > max_dot) continue;
+        const double mse23 = pt_mse[m2 * MAXM + m3];
+        if (mse23 > max_mse) continue;
+        const double mse30 = pt_mse[m3 * MAXM + m0];
+        if (mse30 > max_mse) continue;
+        const double err = seg_err(m0, m1, mse01) + seg_err(m1, m2, mse12) + seg_err(m2, m3, mse23) + seg_err(m3, m0, mse30);
+        if (err < best || (err == best && (uint32_t)t < brank)) {
+          best = err;
+          brank = (uint32_t)t;
+        }
+      }
+    }
+    for (int of = 16; of > 0; of >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, of);
+      const uint32_t orank = __shfl_xor_sync(0xffffffffu, brank, of);
+      if (ov < best || (ov == best && orank < brank)) {
+        best = ov;
+        brank = orank;
+      }
+    }
+    // ---- final lines, corners, area / angle gates: lanes 0..3, one line / corner / angle each ----
+    bool ok = brank != 0xffffffffu;
+    if (ok && !(best / sz < (double)fp.max_line_fit_mse)) ok = false;
+    if (!ok) continue;  // warp-uniform
+    {
+      const uchar4 c = combos.c[combos.off[nm] + brank];
+      const int kept[4] = {c.x, c.y, c.z, c.w};
+      const int li = lane & 3;
+      double ln[4], mse;
+      fit_pair(kept[li], kept[(li + 1) & 3], ln, &mse);
+      ok = __all_sync(0xffffffffu, !(mse > (double)fp.max_line_fit_mse));
+      double nn[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) nn[k] = __shfl_sync(0xffffffffu, ln[k], (li + 1) & 3);
+      const double A00 = ln[3], A01 = -nn[3];
+      const double A10 = -ln[2], A11 = nn[2];
+      const double B0 = -ln[0] + nn[0];
+      const double B1 = -ln[1] + nn[1];
+      const double det = A00 * A11 - A10 * A01;
+      const double W00 = A11 / det, W01 = -A01 / det;
+      const bool det_ok = !(fabs(det) < 0.001);
+      const double L0 = W00 * B0 + W01 * B1;
+      const float qx = (float)(ln[0] + L0 * A00);
+      const float qy = (float)(ln[1] + L0 * A10);
+      ok = ok && __all_sync(0xffffffffu, det_ok);
+      float qp[4][2];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        qp[k][0] = __shfl_sync(0xffffffffu, qx, k);
+        qp[k][1] = __shfl_sync(0xffffffffu, qy, k);
+      }
+      // area: triangle (0,1,2) on even lanes, (2,3,0) on odd lanes
+      double tri;
+      {
+        const int i0 = (lane & 1) ? 2 : 0, i1 = (lane & 1) ? 3 : 1, i2 = (lane & 1) ? 0 : 2;
+        const int ia[3] = {i0, i1, i2}, ib[3] = {i1, i2, i0};
+        double length[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double ddx = (double)(qp[ib[k]][0] - qp[ia[k]][0]), ddy = (double)(qp[ib[k]][1] - qp[ia[k]][1]);
+          length[k] = sqrt(ddx * ddx + ddy * ddy);
+        }
+        const double p = (length[0] + length[1] + length[2]) / 2;
+        tri = sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+      }
+      const double tri1 = __shfl_sync(0xffffffffu, tri, 1);
+      const double tri0 = __shfl_sync(0xffffffffu, tri, 0);
+      double area = 0;
+      area += tri0;
+      area += tri1;
+      if (area < 0.95 * fp.tag_width * fp.tag_width) ok = false;
+      {
+        const double ccr = (double)fp.cos_critical_rad;
+        const int i0 = li, i1 = (li + 1) & 3, i2 = (li + 2) & 3;
+        const double dx1 = (double)(qp[i1][0] - qp[i0][0]);
+        const double dy1 = (double)(qp[i1][1] - qp[i0][1]);
+        const double dx2 = (double)(qp[i2][0] - qp[i1][0]);
+        const double dy2 = (double)(qp[i2][1] - qp[i1][1]);
+        const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
+        const bool bad = (cos_dtheta > ccr || cos_dtheta < -ccr) || dx1 * dy2 < dy1 * dx2;
+        ok = ok && __all_sync(0xffffffffu, !bad);
+      }
+      if (ok && lane == 0) {
+        const uint32_t qi = atomicAdd(&counters[CNT_QUADS], 1u);
+        if (qi < g.quad_cap) {
+          QuadRec q;
+          q.key = cr.key;
+          for (int i = 0; i < 4; i++) {
+            q.p[i][0] = qp[i][0];
+            q.p[i][1] = qp[i][1];
+          }
+          q.frame = cr.frame;
+          q.reversed_border = reversed ? 1u : 0u;
+          quads[qi] = q;
+        } else {
+          atomicOr(&counters[CNT_STATUS], (uint32_t)ST_QUADS_FULL);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------------------------------------------------
+static int device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < 64 ? dev : 0;
+}
+
+template <int THREADS, int NCAP, bool SM, int ITEMS, int MINB, int WPC>
+static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t st) {
+  const Geo &g = ws.g;
+  constexpr size_t smem = SM ? (size_t)2 * NCAP * 8 * WPC : 0;
+  auto kern = k_qf_sort<THREADS, NCAP, SM, ITEMS, MINB, WPC>;
+  static int ctas_per_sm[64] = {};
+  const int dev = device_index();
+  if (!ctas_per_sm[dev]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS * WPC, smem);
+    ctas_per_sm[dev] = std::max(1, n);
+  }
+  kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo,
+                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
+}
+
+int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
+  (void)nframes;
+  const Geo &g = ws.g;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ComboTable ct;
+  ct.c = reinterpret_cast<const uchar4 *>(ws.combos);
+  for (int i = 0; i < 18; i++) ct.off[i] = ws.combo_off[i];
+  launch_bin_clusters(ws, sms, s);
+  // the size bins are independent: fork onto side streams, large clusters (the long poles) first
+  cudaEventRecord(ws.ev_fork, s);
+  for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
+  launch_sort_bin<256, 0, false, 16, 2, 1>(ws, 7, sms, s);             // n > 8192 (4K-class frames): sort in global memory
+  launch_sort_bin<512, 8192, true, 16, 1, 1>(ws, 6, sms, ws.aux[0]);   // n <= 8192
+  launch_sort_bin<256, 4096, true, 16, 3, 1>(ws, 5, sms, ws.aux[1]);   // n <= 4096
+  launch_sort_bin<256, 2048, true, 8, 4, 1>(ws, 4, sms, ws.aux[2]);    // n <= 2048
+  launch_sort_bin<128, 1024, true, 8, 8, 1>(ws, 3, sms, ws.aux[3]);    // n <= 1024
+  launch_sort_bin<64, 512, true, 8, 16, 1>(ws, 2, sms, ws.aux[4]);     // n <= 512
+  launch_sort_bin<32, 256, true, 8, 4, 8>(ws, 1, sms, ws.aux[5]);      // n <= 256: one warp per cluster, 8 workers per CTA
+  launch_sort_bin<32, 128, true, 4, 4, 8>(ws, 0, sms, ws.aux[6]);      // n <= 128
+  for (int i = 0; i < kQuadAux; i++) {
+    cudaEventRecord(ws.ev_join[i], ws.aux[i]);
+    cudaStreamWaitEvent(s, ws.ev_join[i], 0);
+  }
+  {
+    constexpr size_t smem = (size_t)QW_WARPS * 8 * QW_SLOTS * sizeof(double);
+    static int ctas_per_sm[64] = {};
+    const int di = device_index();
+    if (!ctas_per_sm[di]) {
+      cudaFuncSetAttribute(k_qf_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      int n = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_qf_window, 32 * QW_WARPS, smem);
+      ctas_per_sm[di] = std::max(1, n);
+    }
+    k_qf_window<<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(g, ws.fp, ws.clusters, ws.qinfo, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps,
+                                                                    ws.qwtot, ws.qwnmax, ws.counters);
+  }
+  {
+    static int ctas_per_sm[64] = {};
+    const int di = device_index();
+    if (!ctas_per_sm[di]) {
+      int n = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_qf_tail, 32 * QT_WARPS, 0);
+      ctas_per_sm[di] = std::max(1, n);
+    }
+    k_qf_tail<<<sms * ctas_per_sm[di], 32 * QT_WARPS, 0, s>>>(g, ws.fp, ws.clusters, ws.qinfo, ws.qwbase, ws.keys, ws.lfps, ws.errs, ws.qwtot,
+                                                              ws.qwnmax, ws.quads, ws.counters, ct);
+  }
+  return 3 + kQuadBins;
+}
+
+}  // namespace b200at

@@ -5,8 +5,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <map>
 #include <sstream>
+
+// the library writes cuAprilTagsID_t at the stride the reference node (CUDA headers: float2 is 8-byte aligned) reads it
+static_assert(sizeof(cuAprilTagsID_t) == 88 && alignof(cuAprilTagsID_t) == 8 && offsetof(cuAprilTagsID_t, orientation) == 36,
+              "cuAprilTagsID_t layout differs from libb200apriltags.so");
 
 namespace nvidia {
 namespace isaac_ros {

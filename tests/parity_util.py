@@ -144,16 +144,19 @@ def compare_stages(frames, encoding="mono8", families=("tag36h11",), report=None
                 pass
             gq = garr[garr["frame"] == i]
             gq = gq[np.argsort(gq["key"], kind="stable")]
-            okeys = [q["key"] for q in oq]
             if not which:
                 res["n_quads"] += len(oq)
-            if list(gq["key"]) != okeys:
-                res[tagn] += len(set(int(k) for k in gq["key"]) ^ set(okeys)) + (0 if len(gq) == len(oq) else 1)
-                continue
-            if len(oq):
-                op = np.stack([q["p"] for q in oq])
-                res[tagb] += int((gq["p"].view(np.uint32) != op.view(np.uint32)).sum())
-                res[tagm] = max(res[tagm], float(np.abs(gq["p"] - op).max()))
+            # quads are matched by their cluster key (a cluster yields at most one quad): set difference counted, corners of
+            # the common ones compared
+            omap = {int(q["key"]): q["p"] for q in oq}
+            gmap2 = {int(k): p for k, p in zip(gq["key"], gq["p"])}
+            res[tagn] += len(set(omap) ^ set(gmap2)) + (0 if len(gmap2) == len(gq) else 1)
+            common = sorted(set(omap) & set(gmap2))
+            if common:
+                op = np.stack([omap[k] for k in common])
+                gp2 = np.stack([gmap2[k] for k in common])
+                res[tagb] += int((gp2.view(np.uint32) != op.view(np.uint32)).sum())
+                res[tagm] = max(res[tagm], float(np.abs(gp2 - op).max()))
         # detections
         g = gdets[i]
         res["n_det"] += len(odets)

@@ -28,7 +28,7 @@ def test_exports_match_header():
 
 
 def test_struct_layouts():
-    assert C.sizeof(capi.TagID) == 84 and capi.TagID.id.offset == 32 and capi.TagID.orientation.offset == 36
+    assert C.sizeof(capi.TagID) == capi.ID_DTYPE.itemsize == 88 and capi.TagID.id.offset == 32 and capi.TagID.orientation.offset == 36
     assert C.sizeof(capi.ImageInput) == 24 and C.sizeof(capi.Intrinsics) == 16
     assert C.sizeof(capi.Detection) == capi.DET_DTYPE.itemsize == 272
     o = capi.default_options()

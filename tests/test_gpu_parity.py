@@ -1,8 +1,9 @@
 """GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
 frames.  Bar: bit-exact for every integer/byte/index stage (decimated image, tile min/max, threshold, labels, component
-sizes, cluster keys and point sets, sort order), bit-exact float corners for the quad fit, tag IDs and Hamming distance
-exact; refined corners / homography / decision margin / pose within the tolerances stated below (the only
-non-reproducible operations are refine_edges' atan2f/cosf/sinf, whose last bit differs between glibc and CUDA)."""
+sizes, cluster keys and point sets, sort order), tag IDs and Hamming distance exact; float corners of the quad fit
+bit-exact in the exact mode (B200AT_TUNE=qf_exact=1) and within TOL_QUAD_PX in the default windowed mode; refined corners /
+homography / decision margin / pose within the tolerances stated below (refine_edges' atan2f/cosf/sinf differ in the last
+bit between glibc and CUDA)."""
 import json
 import os
 
@@ -39,11 +40,27 @@ def needs_real_gpu(pu):
         pytest.skip("needs a real GPU (torch device tensors / CUDA graphs)")
 
 
+TOL_QUAD_PX = 1e-3      # windowed quad fit: float quad corners vs the oracle's (bit-identical in the exact mode)
+MAX_QUAD_SET_DIFF = 0.005  # ... and the fraction of candidate quads that may be accepted on one side only (ties within rounding)
+
+
+def exact_mode():
+    return "qf_exact=1" in os.environ.get("B200AT_TUNE", "")
+
+
 def assert_exact(res, rep):
+    """Bit-exact for every integer / index stage and for tag id, Hamming distance, family.  Quad corners: bit-identical to the
+    oracle in the exact quad-fit mode (B200AT_TUNE=qf_exact=1); in the default windowed mode (prefix sums associated differently,
+    see k_quad2.cu) within TOL_QUAD_PX, the set of accepted candidate quads equal up to MAX_QUAD_SET_DIFF."""
     assert res["status"] == 0, res
-    for k in ("dec", "tile", "thr", "labels", "sizes", "clusters", "points", "quads_n", "quads_bits", "refined_n", "det_n", "det_id"):
+    for k in ("dec", "tile", "thr", "labels", "sizes", "clusters", "points", "det_n", "det_id"):
         assert res[k] == 0, (k, res, rep)
     assert res.get("order", 0) == 0, res
+    if exact_mode():
+        assert res["quads_n"] == 0 and res["quads_bits"] == 0 and res["refined_n"] == 0, res
+    else:
+        allowed = int(MAX_QUAD_SET_DIFF * res["n_quads"])
+        assert res["quads_n"] <= allowed and res["refined_n"] <= allowed and res["quads_max"] <= TOL_QUAD_PX, res
     assert res["refined_max"] <= TOL_REFINED_PX and res["det_corner_max"] <= TOL_CORNER_PX and res["det_margin_max"] <= TOL_MARGIN, res
 
 

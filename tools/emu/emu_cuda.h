@@ -376,6 +376,7 @@ inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned 
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline double __dsqrt_rn(double a) { return sqrt(a); }
+inline double __drcp_rn(double a) { return 1.0 / a; }
 inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 inline double rsqrt(double a) { return 1.0 / sqrt(a); }
 inline void __nanosleep(unsigned) {}

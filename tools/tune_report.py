@@ -13,7 +13,7 @@ for r in dev:
         print(f"| {r['tune']} | error: {r['error'][:80]} |")
         continue
     s = r["stages_ms"]
-    print(f"| {r['tune']} | {r['ms_per_step']:.2f} | {r['fps']:.0f} | {'ok' if r['parity'] and r['status'] == 0 else 'MISMATCH'} | "
+    print(f"| {r['tune']} | {r['ms_per_step']:.2f} | {r['fps']:.0f} | {('ok' if r.get('identical', True) else 'ok (ids exact, corners <= %.1e px)' % (r.get('max_corner_diff') or 0)) if r['parity'] and r['status'] == 0 else 'MISMATCH'} | "
           + " | ".join(f"{s.get(k, 0):.3f}" for k in ("preprocess", "threshold", "ccl", "cluster", "quadfit", "decode", "finalize")) + " |")
 for r in rows:
     if r.get("event") == "device_subbatched":
