@@ -51,7 +51,7 @@ constexpr int kHostStreamsDefault = 1;
 constexpr int kHostPipeDefault = 3;
 constexpr int kHostCopyStreamsDefault = 1;
 constexpr int kTuneDefaultThrEarly = 0;
-constexpr int kTuneDefaultCclSweep = 1;
+constexpr int kTuneDefaultCclSweep = 4;
 constexpr int kTuneDefaultQfMc = 1;
 constexpr int kTuneDefaultQfKeys23 = 1;
 constexpr int kTuneDefaultDecodeSplit = 1;
@@ -64,7 +64,7 @@ Tune parse_tune() {
   t.thr_early = kTuneDefaultThrEarly;
   t.ccl_sweep = kTuneDefaultCclSweep;
   t.cluster_eager = kTuneDefaultClusterEager;
-  t.ccl_flat = 0;
+  t.ccl_flat = 1;
   t.decode_split = kTuneDefaultDecodeSplit;
   t.decode_ctas = 4;
   t.decode_pair = 0;

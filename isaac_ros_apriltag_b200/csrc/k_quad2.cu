@@ -45,23 +45,79 @@ __device__ __forceinline__ int qf_chunk_rec0(int s, int c) { return (s + 1) / 2 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_qf_sort
 // ---------------------------------------------------------------------------------------------------------------------
+// Bounding box + polarity sums of the cluster over all THREADS threads of its worker (reduced value in every thread).
+template <int THREADS>
+__device__ __forceinline__ BBoxRed bbox_reduce(BBoxRed r, BBoxRed *s_red, int lane, int wid) {
+  constexpr int NW = THREADS / 32;
+  for (int of = 16; of > 0; of >>= 1) {
+    r.xmin = min(r.xmin, __shfl_xor_sync(0xffffffffu, r.xmin, of));
+    r.xmax = max(r.xmax, __shfl_xor_sync(0xffffffffu, r.xmax, of));
+    r.ymin = min(r.ymin, __shfl_xor_sync(0xffffffffu, r.ymin, of));
+    r.ymax = max(r.ymax, __shfl_xor_sync(0xffffffffu, r.ymax, of));
+    r.sgx += __shfl_xor_sync(0xffffffffu, r.sgx, of);
+    r.sgy += __shfl_xor_sync(0xffffffffu, r.sgy, of);
+    r.s1 += __shfl_xor_sync(0xffffffffu, r.s1, of);
+  }
+  if (NW > 1) {
+    if (lane == 0) s_red[wid] = r;
+    __syncthreads();
+    r = s_red[0];
+    for (int w = 1; w < NW; w++) {
+      const BBoxRed q = s_red[w];
+      r.xmin = min(r.xmin, q.xmin);
+      r.xmax = max(r.xmax, q.xmax);
+      r.ymin = min(r.ymin, q.ymin);
+      r.ymax = max(r.ymax, q.ymax);
+      r.sgx += q.sgx;
+      r.sgy += q.sgy;
+      r.s1 += q.s1;
+    }
+  }
+  return r;
+}
+
+// fit_quad's gates before the sort: bounding-box area, border polarity (the dot product is evaluated exactly on integers)
+__device__ __forceinline__ bool qf_pregate(const BBoxRed &r, const FitParams &fp, float &cx, float &cy, bool &reversed) {
+  cx = (float)((r.xmin + r.xmax) * 0.5 + 0.05118);
+  cy = (float)((r.ymin + r.ymax) * 0.5 + -0.028581);
+  const double dotd = (double)r.s1 - (double)cx * (double)r.sgx - (double)cy * (double)r.sgy;
+  reversed = dotd < 0;
+  bool drop = (r.xmax - r.xmin) * (r.ymax - r.ymin) < fp.tag_width;
+  drop = drop || (!fp.reversed_border && reversed) || (!fp.normal_border && !reversed);
+  return !drop;
+}
+
+// the cluster's chunks become work items of k_qf_window (one thread)
+__device__ __forceinline__ void qf_register_work(uint32_t ci, int sz, bool reversed, uint32_t *qinfo, uint32_t *qwbase, uint2 *work,
+                                                 uint32_t work_cap, uint32_t *counters) {
+  const int nch = qf_nchunks(sz);
+  const uint32_t wb = atomicAdd(&counters[CNT_QWORK], (uint32_t)nch);
+  if (wb + (uint32_t)nch <= work_cap) {
+    for (int c = 0; c < nch; c++) work[wb + c] = make_uint2(ci, (uint32_t)c);
+    qwbase[ci] = wb;
+    qinfo[ci] = (uint32_t)sz | (reversed ? 0x80000000u : 0u);
+  } else {  // (cannot happen with the capacity capi.cu allocates: pts_cap / kQfChunkMax + clu_cap)
+    qinfo[ci] = 0u;
+    atomicOr(&counters[CNT_STATUS], (uint32_t)ST_QUADS_FULL);
+  }
+}
+
+// Clusters of at most THREADS * E points.  Every warp sorts 32 * E keys in registers (bitonic network on double-ordered keys);
+// one-warp clusters (THREADS == 32) never touch shared memory, larger ones merge the warps' runs there (merge path).
 // WPC > 1 (one-warp clusters): WPC independent cluster workers per CTA, one warp each, no block-wide barrier anywhere.
-template <int THREADS, int NCAP, bool SM, int ITEMS, int MINB, int WPC>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC>
 __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
-              const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
-              const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work,
-              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
-  constexpr int NW = THREADS / 32;
-  constexpr int PPT = SM ? NCAP / THREADS : 1;
+              const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, const uint8_t *__restrict__ dec,
+              uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work, uint32_t work_cap,
+              uint32_t *__restrict__ counters, int Wp) {
+  constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
-  extern __shared__ unsigned long long dsm_sort[];
-  const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
-  unsigned long long *skeys = dsm_sort + (size_t)grp * 2 * NCAP;
-  unsigned long long *stmp = skeys + NCAP;
-  __shared__ BBoxRed s_red_a[WPC][NW];
+  extern __shared__ unsigned long long dsm_sort[];  // [2 * NCAP] when NW > 1
+  unsigned long long *skeys = dsm_sort, *stmp = dsm_sort + NCAP;
+  __shared__ BBoxRed s_red[NW];
   __shared__ int s_cluster_a[WPC];
-  BBoxRed *s_red = s_red_a[grp];
+  const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
   const int tid = WPC > 1 ? (int)(threadIdx.x % THREADS) : (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
   for (;;) {
@@ -76,102 +132,104 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
     const uint32_t o = cr.offset;
     const uint8_t *im = dec + (size_t)cr.frame * g.Hd * Wp;
     unsigned long long *keys_g = keys + o;
-
-    // ---- bounding box + integer sums for the border-polarity test ----
-    uint32_t pr[PPT];
+    // warp w takes points [w * 32 E, (w + 1) * 32 E): register r of lane l holds point w * 32 E + r * 32 + l (coalesced loads; the
+    // assignment of unsorted points to registers is free)
+    const int wbase = wid * 32 * E;
+    uint32_t pr[E];
     BBoxRed r = {1 << 30, -1, 1 << 30, -1, 0, 0, 0};
-    if (SM) {
 #pragma unroll
-      for (int k = 0; k < PPT; k++) {
-        const int i = tid + k * THREADS;
-        pr[k] = i < sz ? pts[o + i] : 0u;
-      }
+    for (int k = 0; k < E; k++) {
+      const int i = wbase + k * 32 + lane;
+      pr[k] = i < sz ? pts[o + i] : 0u;
+    }
 #pragma unroll
-      for (int k = 0; k < PPT; k++)
-        if (tid + k * THREADS < sz) bbox_add(r, pr[k]);
-    } else {
-      for (int i = tid; i < sz; i += THREADS) bbox_add(r, pts[o + i]);
-    }
-    for (int of = 16; of > 0; of >>= 1) {
-      r.xmin = min(r.xmin, __shfl_xor_sync(0xffffffffu, r.xmin, of));
-      r.xmax = max(r.xmax, __shfl_xor_sync(0xffffffffu, r.xmax, of));
-      r.ymin = min(r.ymin, __shfl_xor_sync(0xffffffffu, r.ymin, of));
-      r.ymax = max(r.ymax, __shfl_xor_sync(0xffffffffu, r.ymax, of));
-      r.sgx += __shfl_xor_sync(0xffffffffu, r.sgx, of);
-      r.sgy += __shfl_xor_sync(0xffffffffu, r.sgy, of);
-      r.s1 += __shfl_xor_sync(0xffffffffu, r.s1, of);
-    }
-    if (NW > 1) {
-      if (lane == 0) s_red[wid] = r;
-      __syncthreads();
-      r = s_red[0];
-      for (int w = 1; w < NW; w++) {
-        BBoxRed q = s_red[w];
-        r.xmin = min(r.xmin, q.xmin);
-        r.xmax = max(r.xmax, q.xmax);
-        r.ymin = min(r.ymin, q.ymin);
-        r.ymax = max(r.ymax, q.ymax);
-        r.sgx += q.sgx;
-        r.sgy += q.sgy;
-        r.s1 += q.s1;
-      }
-    }
-    const float cx = (float)((r.xmin + r.xmax) * 0.5 + 0.05118);
-    const float cy = (float)((r.ymin + r.ymax) * 0.5 + -0.028581);
-    // dot = sum (x-cx)*gx + (y-cy)*gy, evaluated exactly on the integer parts (order independent)
-    const double dotd = (double)r.s1 - (double)cx * (double)r.sgx - (double)cy * (double)r.sgy;
-    const bool reversed = dotd < 0;
-    bool drop = (r.xmax - r.xmin) * (r.ymax - r.ymin) < fp.tag_width;
-    drop = drop || (!fp.reversed_border && reversed) || (!fp.normal_border && !reversed);
-    if (drop) {  // (uniform over the cluster's threads)
+    for (int k = 0; k < E; k++)
+      if (wbase + k * 32 + lane < sz) bbox_add(r, pr[k]);
+    r = bbox_reduce<THREADS>(r, s_red, lane, wid);
+    float cx, cy;
+    bool reversed;
+    if (!qf_pregate(r, fp, cx, cy, reversed)) {  // (uniform over the cluster's threads)
       if (tid == 0) qinfo[ci] = 0u;
       continue;
     }
-
-    // ---- sort keys (slope | y | x) ----
-    if (SM) {
+    double v[E];
 #pragma unroll
-      for (int k = 0; k < PPT; k++) {
-        const int i = tid + k * THREADS;
-        if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
-      }
-      cta_sync<THREADS>();
-      sort_keys<THREADS, ITEMS, false>(skeys, stmp, sz, tid);
-      // sorted points out; the slope half of a key is dead, it now carries the squared gradient magnitude of the decimated image
-      // at the point (compute_lfps' weight is sqrt of it, + 1): four gathers in flight per thread
+    for (int k = 0; k < E; k++) v[k] = (wbase + k * 32 + lane < sz) ? key60(pr[k], cx, cy) : key60_inf();
+    warp_bitonic_sort<E>(v, lane);
+    // element wbase + lane * E + k of the sorted sequence (of the warp's run) is now v[k]
+    if (NW == 1) {
+      // sorted points out, straight from the registers; the slope half of a key is dead, it now carries the squared gradient
+      // magnitude of the decimated image at the point (compute_lfps' weight is sqrt of it, + 1): E gathers in flight per lane
+      uint32_t yx[E];
+      int g2[E];
+#pragma unroll
+      for (int k = 0; k < E; k++) yx[k] = key60_yx(v[k]);
+#pragma unroll
+      for (int k = 0; k < E; k++) g2[k] = (lane * E + k < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, (unsigned long long)yx[k]) : 0;
+#pragma unroll
+      for (int k = 0; k < E; k++)
+        if (lane * E + k < sz) keys_g[lane * E + k] = (unsigned long long)yx[k] | ((unsigned long long)(uint32_t)g2[k] << 32);
+    } else {
+#pragma unroll
+      for (int k = 0; k < E; k++) skeys[wbase + lane * E + k] = (unsigned long long)__double_as_longlong(v[k]);
+      __syncthreads();
+      merge_runs<THREADS, ITEMS>(skeys, stmp, sz, tid, 32 * E);
       for (int i = tid; i < sz; i += 4 * THREADS) {
-        unsigned long long k[4];
+        uint32_t yx[4];
         int g2[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) k[u] = (i + u * THREADS < sz) ? skeys[i + u * THREADS] : 0ull;
+        for (int u = 0; u < 4; u++) yx[u] = (i + u * THREADS < sz) ? key60_yx(__longlong_as_double((long long)skeys[i + u * THREADS])) : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, k[u]) : 0;
+        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, (unsigned long long)yx[u]) : 0;
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (k[u] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[u] << 32);
-      }
-    } else {
-      for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
-      cta_sync<THREADS>();
-      sort_keys<THREADS, ITEMS, false>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
-      for (int i = tid; i < sz; i += THREADS) {
-        const unsigned long long k = keys_g[i];
-        keys_g[i] = (k & 0xffffffffull) | ((unsigned long long)(uint32_t)grad2_at(im, Wp, g.Wd, g.Hd, k) << 32);
+          if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (unsigned long long)yx[u] | ((unsigned long long)(uint32_t)g2[u] << 32);
       }
     }
-    // ---- the cluster's chunks become work items of k_qf_window ----
-    if (tid == 0) {
-      const int nch = qf_nchunks(sz);
-      const uint32_t wb = atomicAdd(&counters[CNT_QWORK], (uint32_t)nch);
-      if (wb + (uint32_t)nch <= work_cap) {
-        for (int c = 0; c < nch; c++) work[wb + c] = make_uint2(ci, (uint32_t)c);
-        qwbase[ci] = wb;
-        qinfo[ci] = (uint32_t)sz | (reversed ? 0x80000000u : 0u);
-      } else {  // (cannot happen with the capacity capi.cu allocates: pts_cap / kQfChunkMax + clu_cap)
-        qinfo[ci] = 0u;
-        atomicOr(&counters[CNT_STATUS], (uint32_t)ST_QUADS_FULL);
-      }
+    if (tid == 0) qf_register_work(ci, sz, reversed, qinfo, qwbase, work, work_cap, counters);
+  }
+}
+
+// Clusters of more than 8192 points (4K-class frames only): keys and merge scratch in global memory.
+__global__ void __launch_bounds__(256, 2)
+    k_qf_sort_global(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
+                     const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
+                     const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work,
+                     uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
+  constexpr int THREADS = 256;
+  __shared__ BBoxRed s_red[THREADS / 32];
+  __shared__ int s_cluster;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_cluster = (int)atomicAdd(&counters[CNT_WORK0 + bin], 1u);
+    __syncthreads();
+    const int cw = s_cluster;
+    if ((uint32_t)cw >= nbin) break;
+    const uint32_t ci = bin_idx[(size_t)bin * g.clu_cap + cw];
+    const ClusterRec cr = clusters[ci];
+    const int sz = (int)cr.count;
+    const uint32_t o = cr.offset;
+    const uint8_t *im = dec + (size_t)cr.frame * g.Hd * Wp;
+    unsigned long long *keys_g = keys + o;
+    BBoxRed r = {1 << 30, -1, 1 << 30, -1, 0, 0, 0};
+    for (int i = tid; i < sz; i += THREADS) bbox_add(r, pts[o + i]);
+    r = bbox_reduce<THREADS>(r, s_red, lane, wid);
+    float cx, cy;
+    bool reversed;
+    if (!qf_pregate(r, fp, cx, cy, reversed)) {
+      if (tid == 0) qinfo[ci] = 0u;
+      continue;
     }
+    for (int i = tid; i < sz; i += THREADS) keys_g[i] = slope_key(pts[o + i], cx, cy);
+    __syncthreads();
+    sort_keys<THREADS, 16, false>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
+    for (int i = tid; i < sz; i += THREADS) {
+      const unsigned long long k = keys_g[i];
+      keys_g[i] = (k & 0xffffffffull) | ((unsigned long long)(uint32_t)grad2_at(im, Wp, g.Wd, g.Hd, k) << 32);
+    }
+    if (tid == 0) qf_register_work(ci, sz, reversed, qinfo, qwbase, work, work_cap, counters);
   }
 }
 
@@ -195,30 +253,58 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
   const uint32_t nwork = min(counters[CNT_QWORK], work_cap);
   const double f0 = (double)fp.smooth[0], f1 = (double)fp.smooth[1], f2 = (double)fp.smooth[2], f3 = (double)fp.smooth[3],
                f4 = (double)fp.smooth[4], f5 = (double)fp.smooth[5], f6 = (double)fp.smooth[6];
-  for (;;) {
+  // One work item ahead: while an item is being processed, the next one's queue ticket, metadata and keys are already in
+  // flight (the dependent chain atomic -> work[] -> cluster record -> keys is ~4 memory round trips; without the prefetch it
+  // was 35 % of the kernel's stall samples).
+  struct Item {
+    uint32_t w, off;
+    int n, c, s, len, ksz;
+    bool valid;
+  };
+  unsigned long long kq[PPL];
+  auto fetch = [&](Item &it) {
     uint32_t w = 0;
     if (lane == 0) w = atomicAdd(&counters[CNT_Q2], 1u);
     w = __shfl_sync(0xffffffffu, w, 0);
-    if (w >= nwork) break;
+    it.w = w;
+    it.valid = w < nwork;
+    if (!it.valid) return;
     const uint2 wk = work[w];
-    const uint32_t off = clusters[wk.x].offset;
-    const int n = (int)(qinfo[wk.x] & 0x7fffffffu);
-    const int nch = qf_nchunks(n), c = (int)wk.y;
-    int s, e;
-    qf_chunk_bounds(n, nch, c, s, e);
-    const int len = e - s;
-    const int ksz = min(20, n / 12);
+    it.off = clusters[wk.x].offset;
+    it.n = (int)(qinfo[wk.x] & 0x7fffffffu);
+    it.c = (int)wk.y;
+    int e;
+    qf_chunk_bounds(it.n, qf_nchunks(it.n), it.c, it.s, e);
+    it.len = e - it.s;
+    it.ksz = min(20, it.n / 12);
+    const int HLn = it.ksz + 5, Ln = it.len + 2 * it.ksz + 9;
+    const unsigned long long *kg = keys + it.off;
+#pragma unroll
+    for (int q = 0; q < PPL; q++) {
+      const int j = lane + 32 * q;
+      int gi = it.s - HLn + j;
+      gi = gi < 0 ? gi + it.n : gi;
+      gi = gi >= it.n ? gi - it.n : gi;
+      kq[q] = j < Ln ? kg[gi] : 0ull;
+    }
+  };
+  Item cur;
+  fetch(cur);
+  while (cur.valid) {
+    const uint32_t w = cur.w, off = cur.off;
+    const int n = cur.n, c = cur.c, s = cur.s, len = cur.len, ksz = cur.ksz;
+    (void)n;
     const int HL = ksz + 5;            // halo: ksz + 5 points before the chunk, ksz + 4 after (circular)
     const int L = len + 2 * ksz + 9;   // <= SLOTS by the choice of kQfChunkMax
-    const unsigned long long *kg = keys + off;
     unsigned long long *Ek = reinterpret_cast<unsigned long long *>(E);
-    for (int j = lane; j < L; j += 32) {
-      int gi = s - HL + j;
-      gi = gi < 0 ? gi + n : gi;
-      gi = gi >= n ? gi - n : gi;
-      Ek[j] = kg[gi];
+#pragma unroll
+    for (int q = 0; q < PPL; q++) {
+      const int j = lane + 32 * q;
+      if (j < L) Ek[j] = kq[q];
     }
     __syncwarp();
+    Item nxt;
+    fetch(nxt);
     // line-fit terms and prefix moments: a lane owns PPL consecutive slots (serial chain), one warp scan joins the lanes
     double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -315,6 +401,7 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
     if (lane < 6) wtot[(size_t)w * 6 + lane] = P[lane * SLOTS + HL + len - 1] - P[lane * SLOTS + HL - 1];
     if (lane == 0) wnmax[w] = (uint32_t)run;
     __syncwarp();
+    cur = nxt;
   }
 }
 
@@ -484,8 +571,10 @@ __global__ void __launch_bounds__(32 * QT_WARPS)
       s_T[lane] = T;
     }
     __syncwarp();
-    // fit_line between kept maxima a -> b (oracle fit_line: prefix difference, wrapping when i0 > i1)
-    auto fit_pair = [&](int a, int b, double *lineparm, double *mse) {
+    // fit_line between kept maxima a -> b (oracle fit_line: prefix difference, wrapping when i0 > i1).  FAST (the pair table,
+    // which only SELECTS the four corners): reciprocal-multiply instead of the seven divisions; the four final lines, which
+    // give the corners, use the oracle's divisions.
+    auto fit_pair = [&](int a, int b, double *lineparm, double *mse, bool fast) {
       const int i0 = s_fm[a], i1 = s_fm[b];
       double M[6];
       int N;
@@ -505,14 +594,31 @@ __global__ void __launch_bounds__(32 * QT_WARPS)
         }
         N = sz - i0 + i1 + 1;
       }
-      fit_moments_dev(M[0], M[1], M[2], M[3], M[4], M[5], N, lineparm, nullptr, mse);
+      if (!fast) {
+        fit_moments_dev(M[0], M[1], M[2], M[3], M[4], M[5], N, lineparm, nullptr, mse);
+        return;
+      }
+      const double rw = __drcp_rn(M[5]);
+      const double Ex = M[0] * rw, Ey = M[1] * rw;
+      const double Cxx = M[2] * rw - Ex * Ex, Cxy = M[3] * rw - Ex * Ey, Cyy = M[4] * rw - Ey * Ey;
+      const double disc = (double)sqrtf((float)((Cxx - Cyy) * (Cxx - Cyy) + 4 * Cxy * Cxy));
+      *mse = 0.5 * (Cxx + Cyy - disc);
+      const double eig = 0.5 * (Cxx + Cyy + disc);
+      const double nx1 = Cxx - eig, ny1 = Cxy, M1 = nx1 * nx1 + ny1 * ny1;
+      const double nx2 = Cxy, ny2 = Cyy - eig, M2 = nx2 * nx2 + ny2 * ny2;
+      const bool first = M1 > M2;
+      const double nx = first ? nx1 : nx2, ny = first ? ny1 : ny2;
+      const double length = (double)sqrtf((float)(first ? M1 : M2));
+      const double rl = fabs(length) < 1e-12 ? 0.0 : __drcp_rn(length);
+      lineparm[2] = nx * rl;
+      lineparm[3] = ny * rl;
     };
     // ---- pair table ----
     for (int t = lane; t < nm * nm; t += 32) {
       const int a = t / nm, b = t - a * nm;
       if (a == b) continue;
       double lp[4], ms;
-      fit_pair(a, b, lp, &ms);
+      fit_pair(a, b, lp, &ms, true);
       pt_mse[a * MAXM + b] = ms;
       pt_nx[a * MAXM + b] = lp[2];
       pt_ny[a * MAXM + b] = lp[3];
@@ -567,7 +673,7 @@ __global__ void __launch_bounds__(32 * QT_WARPS)
       const int kept[4] = {c.x, c.y, c.z, c.w};
       const int li = lane & 3;
       double ln[4], mse;
-      fit_pair(kept[li], kept[(li + 1) & 3], ln, &mse);
+      fit_pair(kept[li], kept[(li + 1) & 3], ln, &mse, false);
       ok = __all_sync(0xffffffffu, !(mse > (double)fp.max_line_fit_mse));
       double nn[4];
 #pragma unroll
@@ -649,11 +755,11 @@ static int device_index() {
   return dev >= 0 && dev < 64 ? dev : 0;
 }
 
-template <int THREADS, int NCAP, bool SM, int ITEMS, int MINB, int WPC>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC>
 static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t st) {
   const Geo &g = ws.g;
-  constexpr size_t smem = SM ? (size_t)2 * NCAP * 8 * WPC : 0;
-  auto kern = k_qf_sort<THREADS, NCAP, SM, ITEMS, MINB, WPC>;
+  constexpr size_t smem = THREADS > 32 ? (size_t)2 * THREADS * E * 8 : 0;
+  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC>;
   static int ctas_per_sm[64] = {};
   const int dev = device_index();
   if (!ctas_per_sm[dev]) {
@@ -662,8 +768,8 @@ static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS * WPC, smem);
     ctas_per_sm[dev] = std::max(1, n);
   }
-  kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo,
-                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
+  kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.dec, ws.qinfo, ws.qwbase,
+                                                           ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
 }
 
 int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
@@ -679,14 +785,15 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
   // the size bins are independent: fork onto side streams, large clusters (the long poles) first
   cudaEventRecord(ws.ev_fork, s);
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
-  launch_sort_bin<256, 0, false, 16, 2, 1>(ws, 7, sms, s);             // n > 8192 (4K-class frames): sort in global memory
-  launch_sort_bin<512, 8192, true, 16, 1, 1>(ws, 6, sms, ws.aux[0]);   // n <= 8192
-  launch_sort_bin<256, 4096, true, 16, 3, 1>(ws, 5, sms, ws.aux[1]);   // n <= 4096
-  launch_sort_bin<256, 2048, true, 8, 4, 1>(ws, 4, sms, ws.aux[2]);    // n <= 2048
-  launch_sort_bin<128, 1024, true, 8, 8, 1>(ws, 3, sms, ws.aux[3]);    // n <= 1024
-  launch_sort_bin<64, 512, true, 8, 16, 1>(ws, 2, sms, ws.aux[4]);     // n <= 512
-  launch_sort_bin<32, 256, true, 8, 4, 8>(ws, 1, sms, ws.aux[5]);      // n <= 256: one warp per cluster, 8 workers per CTA
-  launch_sort_bin<32, 128, true, 4, 4, 8>(ws, 0, sms, ws.aux[6]);      // n <= 128
+  k_qf_sort_global<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 7, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo, ws.qwbase, ws.qwork,
+                                          ws.qwork_cap, ws.counters, at_Wp(g));                 // n > 8192 (4K-class frames)
+  launch_sort_bin<512, 16, 8, 1, 1>(ws, 6, sms, ws.aux[0]);   // n <= 8192: 16 warps x 512 keys, 4 merge passes
+  launch_sort_bin<256, 16, 8, 2, 1>(ws, 5, sms, ws.aux[1]);   // n <= 4096:  8 warps x 512 keys, 3 merge passes
+  launch_sort_bin<256, 8, 8, 3, 1>(ws, 4, sms, ws.aux[2]);    // n <= 2048:  8 warps x 256 keys, 3 merge passes
+  launch_sort_bin<128, 8, 8, 6, 1>(ws, 3, sms, ws.aux[3]);    // n <= 1024:  4 warps x 256 keys, 2 merge passes
+  launch_sort_bin<32, 16, 8, 2, 8>(ws, 2, sms, ws.aux[4]);    // n <= 512: one warp per cluster, registers only, 8 workers per CTA
+  launch_sort_bin<32, 8, 8, 3, 8>(ws, 1, sms, ws.aux[5]);     // n <= 256
+  launch_sort_bin<32, 4, 8, 4, 8>(ws, 0, sms, ws.aux[6]);     // n <= 128
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);

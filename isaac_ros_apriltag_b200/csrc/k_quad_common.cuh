@@ -288,6 +288,122 @@ __device__ __forceinline__ unsigned long long slope_key(uint32_t p, float cx, fl
   return ((unsigned long long)float_orderable(slope) << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Register bitonic sort of 32 * E keys per warp (k_quad2.cu).  A key is slope (32 bits, float_orderable) | y (14) | x (14) in
+// the low 60 bits of a 64-bit word: read as an IEEE double it is positive and finite, and for positive doubles the floating
+// point order IS the order of the bit patterns -- one DMNMX (fmin / fmax) replaces the compare + four selects a 64-bit integer
+// compare-exchange costs.  Element i of the warp's chunk lives in lane i / E, register i % E.  Ascending-only network: the
+// first step of every merge level pairs i with i ^ (2^k - 1), the following ones i with i ^ j.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double key60(uint32_t p, float cx, float cy) {
+  const unsigned long long k = slope_key(p, cx, cy);  // slope << 32 | y << 16 | x
+  return __longlong_as_double((long long)(((k >> 32) << 28) | (((k >> 16) & 0x3fffull) << 14) | (k & 0x3fffull)));
+}
+// y << 16 | x of a key60 (the layout of the sorted-point stream)
+__device__ __forceinline__ uint32_t key60_yx(double d) {
+  const unsigned long long k = (unsigned long long)__double_as_longlong(d);
+  return (uint32_t)(((k >> 14) & 0x3fffull) << 16) | (uint32_t)(k & 0x3fffull);
+}
+__device__ __forceinline__ double key60_inf() { return __longlong_as_double(0x7fefffffffffffffll); }  // above every key60
+
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(double (&v)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int k2 = 2; k2 <= N; k2 <<= 1) {
+    // step 1: partner i ^ (k2 - 1)
+    if (k2 <= E) {
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        const int q = r ^ (k2 - 1);
+        if (q > r) {
+          const double lo = fmin(v[r], v[q]), hi = fmax(v[r], v[q]);
+          v[r] = lo;
+          v[q] = hi;
+        }
+      }
+    } else {
+      const int lm = k2 / E - 1;                        // lane bits flipped
+      const bool lower = (lane & (k2 / E / 2)) == 0;    // the highest flipped bit of my index is 0: I keep the minimum
+      double p[E];
+#pragma unroll
+      for (int r = 0; r < E; r++) p[r] = __shfl_xor_sync(0xffffffffu, v[E - 1 - r], lm);
+#pragma unroll
+      for (int r = 0; r < E; r++) v[r] = lower ? fmin(v[r], p[r]) : fmax(v[r], p[r]);
+    }
+    // following steps: partner i ^ j
+#pragma unroll
+    for (int j = k2 >> 2; j >= 1; j >>= 1) {
+      if (j < E) {
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          if ((r & j) == 0) {
+            const double lo = fmin(v[r], v[r | j]), hi = fmax(v[r], v[r | j]);
+            v[r] = lo;
+            v[r | j] = hi;
+          }
+        }
+      } else {
+        const int lm = j / E;
+        const bool lower = (lane & lm) == 0;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          const double p = __shfl_xor_sync(0xffffffffu, v[r], lm);
+          v[r] = lower ? fmin(v[r], p) : fmax(v[r], p);
+        }
+      }
+    }
+  }
+}
+
+// merge passes of sort_keys from sorted runs of `width0` keys (the last run may be partial); the sorted sequence ends in `a`
+template <int THREADS, int ITEMS>
+__device__ __forceinline__ void merge_runs(unsigned long long *a, unsigned long long *tmp, int n, int tid, int width0) {
+  constexpr unsigned long long INF = ~0ull;
+  unsigned long long *src = a, *dst = tmp;
+  for (int width = width0; width < n; width <<= 1) {
+    const int w2 = width << 1;
+    for (int ob = tid * ITEMS; ob < n; ob += THREADS * ITEMS) {
+      const int pair_lo = ob & ~(w2 - 1);
+      const int a0 = pair_lo, a1 = min(pair_lo + width, n), b0 = a1, b1 = min(pair_lo + w2, n);
+      const int na = a1 - a0, nb = b1 - b0;
+      const int diag = ob - pair_lo;
+      int lo = max(0, diag - nb), hi = min(diag, na);
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (src[a0 + mid] < src[b0 + diag - 1 - mid])
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      int ia = lo, ib = diag - lo;
+      unsigned long long va = ia < na ? src[a0 + ia] : INF, vb = ib < nb ? src[b0 + ib] : INF;
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++) {
+        if (ob + k < b1) {
+          const bool take_a = va <= vb;
+          dst[ob + k] = take_a ? va : vb;
+          if (take_a) {
+            ia++;
+            va = ia < na ? src[a0 + ia] : INF;
+          } else {
+            ib++;
+            vb = ib < nb ? src[b0 + ib] : INF;
+          }
+        }
+      }
+    }
+    cta_sync<THREADS>();
+    unsigned long long *t = src;
+    src = dst;
+    dst = t;
+  }
+  if (src != a) {
+    for (int i = tid; i < n; i += THREADS) a[i] = src[i];
+    cta_sync<THREADS>();
+  }
+}
+
 // squared gradient magnitude of the decimated image at the (half-resolution) point of a sorted key; 0 on the image
 // border, where the reference uses weight 1 = sqrt(0) + 1
 __device__ __forceinline__ int grad2_at(const uint8_t *__restrict__ im, int Wp, int Wd, int Hd, unsigned long long k) {
