@@ -180,6 +180,16 @@ int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *fr
 int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,
                                  b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts);
 
+/* Asynchronous halves of DetectBatchHost: Enqueue validates every frame, queues the copies and kernels of the whole batch and
+ * returns; Collect waits for the OLDEST batch in flight and unpacks it.  Up to TWO batches may be in flight per handle, so the
+ * host->device copies and quad detection of batch k+1 overlap the decode / pose / device->host copy of batch k:
+ *     Enqueue(b0); Enqueue(b1); Collect(b0); Enqueue(b2); Collect(b1); ...
+ * The caller's frames must stay valid and unmodified until their batch has been collected.  Enqueue returns
+ * B200AT_ERR_INVALID_ARG when two batches are already in flight; on any error nothing of the failed call is left running. */
+int b200AprilTagsEnqueueBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames);
+int b200AprilTagsCollectBatchHost(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out,
+                                  uint32_t *counts);
+
 /* Asynchronous halves of DetectBatch for pipelined callers (bench, multi-stream): Enqueue launches the kernels
  * and the D2H copy on `stream`; Collect synchronises and unpacks into host arrays. */
 int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,

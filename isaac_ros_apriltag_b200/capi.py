@@ -25,7 +25,7 @@ STAGES = ["preprocess", "threshold", "ccl", "cluster", "quadfit", "decode", "fin
 EXPORTED_SYMBOLS = [
     "nvCreateAprilTagsDetector", "cuAprilTagsDetect", "cuAprilTagsDestroy",
     "b200AprilTagsDefaultOptions", "b200AprilTagsCreate", "b200AprilTagsSetInputEncoding", "b200AprilTagsDetectBatch",
-    "b200AprilTagsDetectBatchHost", "b200AprilTagsEnqueueBatch", "b200AprilTagsCollectBatch", "b200AprilTagsLastStatus",
+    "b200AprilTagsDetectBatchHost", "b200AprilTagsEnqueueBatchHost", "b200AprilTagsCollectBatchHost", "b200AprilTagsEnqueueBatch", "b200AprilTagsCollectBatch", "b200AprilTagsLastStatus",
     "b200AprilTagsEnableStageTiming", "b200AprilTagsGetStageTimes", "b200AprilTagsGetCounters", "b200AprilTagsGetDims",
     "b200AprilTagsReadBuffer", "b200AprilTagsVersion",
 ]
@@ -112,6 +112,8 @@ def lib():
         L.b200AprilTagsSetInputEncoding.argtypes = [vp, C.c_int32]
         L.b200AprilTagsDetectBatch.argtypes = [vp, C.POINTER(Frame), u32, vp, vp, vp, vp]
         L.b200AprilTagsDetectBatchHost.argtypes = [vp, C.POINTER(Frame), u32, vp, vp, vp]
+        L.b200AprilTagsEnqueueBatchHost.argtypes = [vp, C.POINTER(Frame), u32]
+        L.b200AprilTagsCollectBatchHost.argtypes = [vp, vp, vp, vp]
         L.b200AprilTagsEnqueueBatch.argtypes = [vp, C.POINTER(Frame), u32, vp]
         L.b200AprilTagsCollectBatch.argtypes = [vp, vp, vp, vp]
         L.b200AprilTagsLastStatus.argtypes = [vp, C.POINTER(u32)]
@@ -209,6 +211,27 @@ class Detector:
         rc = lib().b200AprilTagsDetectBatchHost(self.h, fr, n, dets.ctypes.data, None, counts.ctypes.data)
         if rc != 0 and (strict or rc != 5):
             raise B200ATError(rc, "b200AprilTagsDetectBatchHost")
+        return [dets[i, :counts[i]].copy() for i in range(n)]
+
+    def enqueue_host(self, frames):
+        """Asynchronous half of detect_host: queues one batch (up to two may be in flight); `frames` must stay alive and
+        unmodified until the matching collect_host()."""
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+        n = frames.shape[0]
+        fr = self._frames([frames[i].ctypes.data for i in range(n)], frames.strides[1])
+        rc = lib().b200AprilTagsEnqueueBatchHost(self.h, fr, n)
+        if rc != 0:
+            raise B200ATError(rc, "b200AprilTagsEnqueueBatchHost")
+        self._host_q = getattr(self, "_host_q", []) + [(n, frames)]
+
+    def collect_host(self, strict=True):
+        """Waits for the oldest batch queued with enqueue_host and returns its detections (list of DET_DTYPE arrays)."""
+        n, _keep = self._host_q.pop(0)
+        dets = np.zeros((n, self.max_tags), DET_DTYPE)
+        counts = np.zeros(n, np.uint32)
+        rc = lib().b200AprilTagsCollectBatchHost(self.h, dets.ctypes.data, None, counts.ctypes.data)
+        if rc != 0 and (strict or rc != 5):
+            raise B200ATError(rc, "b200AprilTagsCollectBatchHost")
         return [dets[i, :counts[i]].copy() for i in range(n)]
 
     def status(self):

@@ -45,33 +45,10 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
     }                                                                                                         \
   } while (0)
 
-// Default of the sparse host path (see b200AprilTagsDetectBatchHost); B200AT_SPARSE_H2D overrides it.
-constexpr bool kSparseHostPathDefault = true;
-constexpr int kHostStreamsDefault = 1;
-constexpr int kHostPipeDefault = 3;
-constexpr int kHostCopyStreamsDefault = 1;
-constexpr int kTuneDefaultThrEarly = 0;
-constexpr int kTuneDefaultCclSweep = 4;
-constexpr int kTuneDefaultQfMc = 1;
-constexpr int kTuneDefaultQfKeys23 = 1;
-constexpr int kTuneDefaultDecodeSplit = 1;
-constexpr int kTuneDefaultClusterEager = 2;
-
-// B200AT_TUNE="thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,decode_ctas=4,qf_scale=1.0,qf_keys23=0,qf_mc=0": performance knobs of one handle (detector.h,
-// struct Tune).  Unknown keys are reported and ignored.
+// B200AT_TUNE="ccl_tma=0,qf_exact=1": the per-handle knobs (detector.h, struct Tune).  Unknown keys are reported and ignored.
 Tune parse_tune() {
   Tune t;
-  t.thr_early = kTuneDefaultThrEarly;
-  t.ccl_sweep = kTuneDefaultCclSweep;
-  t.cluster_eager = kTuneDefaultClusterEager;
-  t.ccl_flat = 1;
-  t.decode_split = kTuneDefaultDecodeSplit;
-  t.decode_ctas = 4;
-  t.decode_pair = 0;
-  t.qf_scale = 1.0f;
-  t.qf_keys23 = kTuneDefaultQfKeys23;
-  t.qf_mc = kTuneDefaultQfMc;
-  t.qf_sort = 0;
+  t.ccl_tma = 1;
   t.qf_exact = 0;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
@@ -85,23 +62,11 @@ Tune parse_tune() {
     const size_t eq = kv.find('=');
     if (eq == std::string::npos) continue;
     const std::string k = kv.substr(0, eq);
-    const double v = atof(kv.c_str() + eq + 1);
-    if (k == "thr_early") t.thr_early = (int)v;
-    else if (k == "ccl_sweep") t.ccl_sweep = (int)v;
-    else if (k == "cluster_eager") t.cluster_eager = (int)v;
-    else if (k == "ccl_flat") t.ccl_flat = (int)v;
-    else if (k == "decode_split") t.decode_split = (int)v;
-    else if (k == "decode_ctas") t.decode_ctas = (int)v;
-    else if (k == "decode_pair") t.decode_pair = (int)v;
-    else if (k == "qf_scale") t.qf_scale = (float)v;
-    else if (k == "qf_keys23") t.qf_keys23 = (int)v;
-    else if (k == "qf_mc") t.qf_mc = (int)v;
-    else if (k == "qf_sort") t.qf_sort = (int)v;
-    else if (k == "qf_exact") t.qf_exact = (int)v;
+    const int v = atoi(kv.c_str() + eq + 1);
+    if (k == "ccl_tma") t.ccl_tma = v;
+    else if (k == "qf_exact") t.qf_exact = v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
-  if (t.decode_ctas < 1 || t.decode_ctas > 16) t.decode_ctas = 4;
-  if (!(t.qf_scale > 0.05f && t.qf_scale < 16.0f)) t.qf_scale = 1.0f;
   return t;
 }
 
@@ -112,6 +77,25 @@ uint32_t next_pow2(uint32_t v) {
 }
 
 }  // namespace
+
+// one host call in flight: its pinned tables and result buffers
+struct HostCall {
+  bool active = false, failed = false, sparse = false;
+  uint32_t n = 0, nsub = 0;
+  uint64_t seq = 0, dma_bytes = 0;
+  int launches = 0;
+  FrameDesc *frames_tab = nullptr, *src_tab = nullptr;   // [cap_frames] staged frames / device-mapped caller frames
+  b200AprilTagsDetection_t *out = nullptr;               // [cap_frames][max_tags]
+  uint32_t *out_count = nullptr, *counters = nullptr;    // [cap_frames], [cap_subs][kMaxChunks * CNT_N]
+  size_t cap_frames = 0, cap_subs = 0;
+  cudaEvent_t done = nullptr;
+};
+struct HostPendingBack {
+  bool valid = false, last = false;
+  int call = 0;
+  uint64_t k = 0;
+  uint32_t sub = 0, start = 0, len = 0;
+};
 
 struct cuAprilTagsHandle_st {
   Workspace ws;
@@ -125,28 +109,24 @@ struct cuAprilTagsHandle_st {
   b200AprilTagsDetection_t *h_out = nullptr;
   uint32_t *h_out_count = nullptr;
   uint32_t *h_counters = nullptr;
-  // host-input path: double-buffered staging + copy stream, so H2D of sub-batch k+1 overlaps the kernels of sub-batch k
+  // host entry points: staging slots, streams and events of the persistent sub-batch pipeline (see host_enqueue)
   uint8_t *d_stage = nullptr;
   size_t stage_pitch = 0;
-  uint32_t stage_sub = 0;  // frames per staging slot
+  uint32_t stage_sub = 0;    // frames per staging slot
+  uint32_t stage_slots = 0;
   cudaStream_t own_stream = nullptr;   // compute stream of the host path
   cudaStream_t copy_stream = nullptr;
-  cudaStream_t copy_stream2 = nullptr;  // second DMA queue: the row-strided copies of the sparse path do not saturate PCIe from one
-  cudaEvent_t ev_copied2[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_consumed[3] = {nullptr, nullptr, nullptr};
-  // pipelined sparse host path: fetches of sub-batch k on their own stream while sub-batch k+1 is being detected
   cudaStream_t fetch_stream = nullptr, tail_stream = nullptr;  // (high priority: few, latency-bound CTAs)
+  cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_consumed[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fetched[2] = {nullptr, nullptr}, ev_decoded[2] = {nullptr, nullptr},
               ev_tail[2] = {nullptr, nullptr}, ev_backdone[2] = {nullptr, nullptr};
-  uint32_t stage_slots = 0;
-  FrameDesc *hp_frames = nullptr;
-  FrameDesc *hp_src = nullptr;         // sparse host path: device-mapped addresses of the caller's frames
   bool sparse_bufs = false;            // need1 / need2 / src_frames / quad_H allocated
   uint32_t sparse_skip = 0;            // calls left on the full copy after a sparse call that fetched nearly every row anyway
-  b200AprilTagsDetection_t *hp_out = nullptr;
-  uint32_t *hp_out_count = nullptr;
-  uint32_t *hp_counters = nullptr;
-  size_t hp_cap_frames = 0, hp_cap_subs = 0, hp_src_cap = 0;
+  HostCall calls[2];                   // up to two host calls in flight
+  HostPendingBack pending_back;        // BACK of the last sub-batch queued so far (queued after the next FRONT, or at collect)
+  uint64_t host_k = 0, host_seq = 0;   // global sub-batch / call counters
+  bool host_pipe = false;              // shape of what is in flight
+  uint32_t host_S = 0;
   // state of the batch in flight
   cudaStream_t cur_stream = nullptr;
   uint32_t cur_n = 0;
@@ -158,14 +138,12 @@ struct cuAprilTagsHandle_st {
   cudaEvent_t ev[B200AT_NUM_STAGES + 1] = {};
   float stage_ms[B200AT_NUM_STAGES] = {};
   float tag_dim = 0;
-  // CUDA graph of one whole batch (all stage launches, fork/join of the quad-fit streams, D2H): replayed when the same
-  // (n, stream, alignment class, encoding) comes again, e.g. the one-frame-at-a-time node path
-  // chunk pipelining: second lane stream + its own side streams / events
-  cudaStream_t lane_stream = nullptr;
+  // the second workspace view of the host path has its own side streams / events for the quad-fit fork / join
   cudaStream_t lane_aux[kQuadAux] = {};
   cudaEvent_t lane_fork = nullptr, lane_join[kQuadAux] = {};
-  cudaEvent_t ev_pipe_start = nullptr, ev_offset = nullptr, ev_lane_done = nullptr;
-  bool pipeline = true;
+  cudaEvent_t ev_in = nullptr;  // orders the handle's own stream after the caller's legacy default stream (resolve_sync_stream)
+  // CUDA graph of one whole batch (all stage launches, fork/join of the quad-fit streams, D2H): replayed when the same
+  // (n, stream, alignment class, encoding) comes again, e.g. the one-frame-at-a-time node path
   cudaGraphExec_t graph_exec = nullptr;
   uint32_t graph_n = 0;
   int graph_fast = -1, graph_enc = -1;
@@ -193,26 +171,29 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->fetch_stream) cudaStreamSynchronize(h->fetch_stream);
+  if (h->tail_stream) cudaStreamSynchronize(h->tail_stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
-  if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
   for (int i = 0; i < kQuadAux; i++) {
     if (h->lane_aux[i]) cudaStreamDestroy(h->lane_aux[i]);
     if (h->lane_join[i]) cudaEventDestroy(h->lane_join[i]);
   }
   if (h->lane_fork) cudaEventDestroy(h->lane_fork);
-  if (h->ev_pipe_start) cudaEventDestroy(h->ev_pipe_start);
-  if (h->ev_offset) cudaEventDestroy(h->ev_offset);
-  if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
   for (void *p : h->dev_allocs) cudaFree(p);
   if (h->h_frames) cudaFreeHost(h->h_frames);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_out_count) cudaFreeHost(h->h_out_count);
   if (h->h_counters) cudaFreeHost(h->h_counters);
-  if (h->hp_frames) cudaFreeHost(h->hp_frames);
-  if (h->hp_src) cudaFreeHost(h->hp_src);
-  if (h->hp_out) cudaFreeHost(h->hp_out);
-  if (h->hp_out_count) cudaFreeHost(h->hp_out_count);
-  if (h->hp_counters) cudaFreeHost(h->hp_counters);
+  for (auto &c : h->calls) {
+    if (c.frames_tab) cudaFreeHost(c.frames_tab);
+    if (c.src_tab) cudaFreeHost(c.src_tab);
+    if (c.out) cudaFreeHost(c.out);
+    if (c.out_count) cudaFreeHost(c.out_count);
+    if (c.counters) cudaFreeHost(c.counters);
+    if (c.done) cudaEventDestroy(c.done);
+  }
   for (int i = 0; i < 3; i++) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
@@ -227,9 +208,6 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->fetch_stream) cudaStreamDestroy(h->fetch_stream);
   if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
-  for (int i = 0; i < 3; i++)
-    if (h->ev_copied2[i]) cudaEventDestroy(h->ev_copied2[i]);
   for (int i = 0; i < kQuadAux; i++) {
     if (h->ws.aux[i]) cudaStreamDestroy(h->ws.aux[i]);
     if (h->ws.ev_join[i]) cudaEventDestroy(h->ws.ev_join[i]);
@@ -486,7 +464,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.counters, (size_t)kMaxChunks * CNT_N);
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   ws.tune = parse_tune();
-  if (ws.tune.decode_split) ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
+  ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
   if (!ws.tune.qf_exact) {
     ws.qwork_cap = (uint32_t)std::min<size_t>((size_t)g.pts_cap / kQfChunkMax + g.clu_cap, 0xfffffff0ull);
     ALLOC(ws.qinfo, g.clu_cap);
@@ -494,11 +472,6 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     ALLOC(ws.qwork, ws.qwork_cap);
     ALLOC(ws.qwtot, (size_t)ws.qwork_cap * 6);
     ALLOC(ws.qwnmax, ws.qwork_cap);
-  }
-  if (ws.tune.cluster_eager == 4) {
-    ws.rec_cap = 2 * (int)Wp;  // points of one row: 0.64 per pixel on thresholded noise, at most 4
-    ALLOC(ws.rec, (size_t)B * g.Hd * ws.rec_cap);
-    ALLOC(ws.rec_cnt, (size_t)B * g.Hd);
   }
   {
     // combination tables: for every nm, all m0<m1<m2<m3<nm in lexicographic order (the serial loops' visiting order)
@@ -555,18 +528,12 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   if (rc == 0 && cudaMallocHost(&h->h_out_count, sizeof(uint32_t) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaMallocHost(&h->h_counters, sizeof(uint32_t) * CNT_N * kMaxChunks) != cudaSuccess) rc = B200AT_ERR_NOMEM;
   if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  if (rc == 0 && cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
   for (int i = 0; i < kQuadAux && rc == 0; i++) {
     if (cudaStreamCreateWithFlags(&h->lane_aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
     if (rc == 0 && cudaEventCreateWithFlags(&h->lane_join[i], cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
   if (rc == 0 && cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_pipe_start, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_offset, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
-  // measured in round 1: no gain (the quad-fit CTAs fill the SMs' shared memory, so dense-stage CTAs cannot co-reside);
-  // kept as an opt-in experiment
-  h->pipeline = getenv("B200AT_PIPELINE") != nullptr;
+  if (rc == 0 && cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
   for (int i = 0; i <= B200AT_NUM_STAGES && rc == 0; i++)
     if (cudaEventCreate(&h->ev[i]) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (rc != 0) {
@@ -678,10 +645,6 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
     v.src_frames += f0;
   }
   if (v.quad_H) v.quad_H += (size_t)c * qc * 10;
-  if (v.rec) {
-    v.rec += (size_t)f0 * g.Hd * v.rec_cap;
-    v.rec_cnt += (size_t)f0 * g.Hd;
-  }
   v.g.tma_frame0 = f0;
   if (c & 1) {  // lane 1 has its own side streams / events
     for (int i = 0; i < kQuadAux; i++) {
@@ -706,9 +669,6 @@ static void sum_counters(const uint32_t *c, uint32_t *out) {
 
 // Launch every stage of one batch and queue the D2H of its results.  `hf` is a pinned frame-table slice that must stay
 // untouched until the stream has consumed it; results land in the pinned arrays `out`, `cnt`, `ctr` (kMaxChunks*CNT_N).
-// Large batches are split into frame chunks on two phase-shifted streams: the dense, issue-bound stages of one chunk
-// (threshold / CCL / clustering: many warps, little shared memory) co-run with the shared-memory-bound, latency-bound
-// quad fit of the previous chunk, which leaves most issue slots of an SM idle.
 static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream, FrameDesc *hf,
                         b200AprilTagsDetection_t *out, uint32_t *cnt, uint32_t *ctr, bool timing, int *launches_out,
                         bool table_filled = false, const FrameDesc *sparse_src = nullptr) {
@@ -741,48 +701,24 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.need2, 0, sizeof(unsigned long long) * (size_t)n * g.H, stream);
   }
   const bool tm = timing;
-  const int nch = (tm || !h->pipeline || n < 32) ? 1 : (n >= 128 ? 4 : 2);
-  if (nch == 1) {
-    g.tma_frame0 = 0;
+  g.tma_frame0 = 0;
 #define STAMP(i) \
   if (tm) cudaEventRecord(h->ev[i], stream)
-    STAMP(0);
-    launches += launch_preprocess(ws, (int)n, stream);
-    STAMP(1);
-    launches += launch_threshold(ws, (int)n, stream);
-    STAMP(2);
-    launches += launch_ccl(ws, (int)n, stream);
-    STAMP(3);
-    launches += launch_cluster(ws, (int)n, stream);
-    STAMP(4);
-    launches += launch_quadfit(ws, (int)n, stream);
-    STAMP(5);
-    launches += launch_decode(ws, (int)n, stream);
-    STAMP(6);
-    launches += launch_finalize(ws, (int)n, stream);
-    STAMP(7);
-  } else {
-    const int per = ((int)n + nch - 1) / nch;
-    cudaEventRecord(h->ev_pipe_start, stream);
-    cudaStreamWaitEvent(h->lane_stream, h->ev_pipe_start, 0);
-    for (int c = 0; c < nch; c++) {
-      const int f0 = c * per, m = std::min(per, (int)n - f0);
-      if (m <= 0) break;
-      const Workspace v = make_view(h, f0, c, nch);
-      cudaStream_t st = (c & 1) ? h->lane_stream : stream;
-      if (c == 1) cudaStreamWaitEvent(st, h->ev_offset, 0);  // phase shift: lane 1 starts when chunk 0 leaves its dense stages
-      launches += launch_preprocess(v, m, st);
-      launches += launch_threshold(v, m, st);
-      launches += launch_ccl(v, m, st);
-      launches += launch_cluster(v, m, st);
-      if (c == 0) cudaEventRecord(h->ev_offset, st);
-      launches += launch_quadfit(v, m, st);
-      launches += launch_decode(v, m, st);
-      launches += launch_finalize(v, m, st);
-    }
-    cudaEventRecord(h->ev_lane_done, h->lane_stream);
-    cudaStreamWaitEvent(stream, h->ev_lane_done, 0);
-  }
+  STAMP(0);
+  launches += launch_preprocess(ws, (int)n, stream);
+  STAMP(1);
+  launches += launch_threshold(ws, (int)n, stream);
+  STAMP(2);
+  launches += launch_ccl(ws, (int)n, stream);
+  STAMP(3);
+  launches += launch_cluster(ws, (int)n, stream);
+  STAMP(4);
+  launches += launch_quadfit(ws, (int)n, stream);
+  STAMP(5);
+  launches += launch_decode(ws, (int)n, stream);
+  STAMP(6);
+  launches += launch_finalize(ws, (int)n, stream);
+  STAMP(7);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(out, ws.out, sizeof(b200AprilTagsDetection_t) * (size_t)n * g.max_tags, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, ws.out_count, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream);
@@ -886,7 +822,7 @@ static int enqueue_view(cuAprilTagsHandle h, Workspace v, const b200AprilTagsFra
 
 int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream) {
   if (!h || !frames || n == 0 || n > h->max_batch) return B200AT_ERR_INVALID_ARG;
-  if (h->in_flight) return B200AT_ERR_INVALID_ARG;
+  if (h->in_flight || h->calls[0].active || h->calls[1].active) return B200AT_ERR_INVALID_ARG;  // one workspace: collect what is in flight first
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
@@ -989,67 +925,167 @@ int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *fr
   return b200AprilTagsCollectBatch(h, dets_out, ids_out, counts);
 }
 
-int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, b200AprilTagsDetection_t *dets_out,
-                                 cuAprilTagsID_t *ids_out, uint32_t *counts) {
-  if (!h || !frames || n == 0 || h->in_flight) return B200AT_ERR_INVALID_ARG;
-  int prev = -1;
-  cudaGetDevice(&prev);
-  if (prev != h->device) cudaSetDevice(h->device);
+// ---------------------------------------------------------------------------------------------------------------------
+// Host entry points: frames in HOST memory.  One persistent pipeline of SUB-BATCHES per handle; a call appends its sub-batches
+// to it, and up to two calls may be in flight (b200AprilTagsEnqueueBatchHost / CollectBatchHost), so that the DMA and the quad
+// detection of the next call overlap the decode / pose / D2H of the previous one -- a synchronous call pays the pipeline's fill
+// and drain (~7 ms of a 28 ms call at batch 256, profiles/r02_host_path_trace.txt) every time.
+//
+// Sparse staging (frames pinned + device-mapped + 16-byte aligned, integer quad_decimate f >= 2; k_decode.cu): only rows 0, f,
+// 2f.. are DMA'd, the full-resolution rows around the fitted quads are fetched afterwards straight from the caller's frames.
+// Per sub-batch k (global counter: staging slot k % 3, workspace view k & 1, counters block k % 4):
+//   copy stream    DMA(k)                                   after BACK(k-3) released the slot
+//   compute stream FRONT(k) = frame table .. quad fit       after DMA(k)
+//                  BACK(k-1) = refine, 2nd fetch, decode    after FETCH(k-1) and the tail of k-3 (same view: candidates / outputs)
+//   fetch stream   FETCH(k) = mark + fetch for refine_edges after FRONT(k) and BACK(k-1)
+//   tail stream    reconcile, pose, D2H of k-1              after BACK(k-1)
+// The BACK of a call's last sub-batch is deferred until the next call's first FRONT has been queued (or until the call is
+// collected), so the compute stream never idles behind a fetch.
+// Anything else (pageable frames, f < 2, tiny max_batch) takes the full copy: sequential sub-batches on the whole workspace, two
+// staging slots, copy(k+1) overlapping compute(k).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint32_t kHostSlotsMax = 3;
+
+int host_streams_create(cuAprilTagsHandle h) {
+  if (h->copy_stream) return B200AT_OK;
+  // the fetch and tail kernels are a handful of latency-bound CTAs (PCIe reads; a warp per detection): at the highest priority
+  // they get the first free SM slots instead of queueing behind the next sub-batch's full grids
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  bool ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&h->fetch_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&h->tail_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; i++) {
+    ok = ok && cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  for (int i = 0; i < 2 && ok; i++) {
+    ok = ok && cudaEventCreateWithFlags(&h->ev_front[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fetched[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_decoded[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_tail[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_backdone[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->calls[i].done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (ok) return B200AT_OK;
+  // all or nothing: a half-created set would be taken for a complete one by the next call
+  cudaGetLastError();
+  auto ds = [](cudaStream_t &s) {
+    if (s) cudaStreamDestroy(s);
+    s = nullptr;
+  };
+  auto de = [](cudaEvent_t &e) {
+    if (e) cudaEventDestroy(e);
+    e = nullptr;
+  };
+  ds(h->copy_stream);
+  ds(h->fetch_stream);
+  ds(h->tail_stream);
+  for (int i = 0; i < 3; i++) {
+    de(h->ev_copied[i]);
+    de(h->ev_consumed[i]);
+  }
+  for (int i = 0; i < 2; i++) {
+    de(h->ev_front[i]);
+    de(h->ev_fetched[i]);
+    de(h->ev_decoded[i]);
+    de(h->ev_tail[i]);
+    de(h->ev_backdone[i]);
+    de(h->calls[i].done);
+  }
+  return B200AT_ERR_CUDA;
+}
+
+// every stream the host path queues work on is idle afterwards
+void host_drain(cuAprilTagsHandle h) {
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->fetch_stream) cudaStreamSynchronize(h->fetch_stream);
+  if (h->tail_stream) cudaStreamSynchronize(h->tail_stream);
+}
+
+Workspace host_view_of(cuAprilTagsHandle h, uint64_t k, uint32_t S) {
+  Workspace v = make_view(h, (int)(k & 1) * (int)S, (int)(k & 1), 2);
+  v.counters = h->ws.counters + (size_t)(k % kMaxChunks) * CNT_N;  // FRONT(k + 2) zeroes another block than the tail of k reads
+  return v;
+}
+
+// BACK of sub-batch `pb` (pipelined sparse path): refine, second fetch, decode on the compute stream; reconcile, pose and the D2H of
+// the results on the tail stream
+int host_enqueue_back(cuAprilTagsHandle h, const HostPendingBack &pb) {
+  HostCall &call = h->calls[pb.call];
+  const uint32_t mt = h->ws.g.max_tags;
+  const int vb = (int)(pb.k & 1);
+  cudaStream_t cs = h->own_stream;
+  bool ok = cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) == cudaSuccess;
+  // the decoder overwrites the candidates / outputs that the tail of this view's previous user (k - 2) still reads
+  ok = ok && cudaStreamWaitEvent(cs, h->ev_tail[vb], 0) == cudaSuccess;
+  if (!ok) return B200AT_ERR_CUDA;
+  int l = 0;
+  int rc = enqueue_view_part(h, host_view_of(h, pb.k, h->host_S), VIEW_BACK, pb.len, cs, call.out + (size_t)pb.start * mt, call.out_count + pb.start,
+                             call.counters + (size_t)pb.sub * CNT_N * kMaxChunks, &l, h->tail_stream, h->ev_decoded[vb]);
+  call.launches += l;
+  if (rc != B200AT_OK) return rc;
+  // the staged frames are dead once the decoder has run (the tail does not read them)
+  ok = cudaEventRecord(h->ev_consumed[pb.k % kHostSlotsMax], cs) == cudaSuccess;
+  ok = ok && cudaEventRecord(h->ev_backdone[vb], cs) == cudaSuccess;
+  ok = ok && cudaEventRecord(h->ev_tail[vb], h->tail_stream) == cudaSuccess;
+  if (ok && pb.last) ok = cudaEventRecord(call.done, h->tail_stream) == cudaSuccess;
+  return ok ? B200AT_OK : B200AT_ERR_CUDA;
+}
+
+int host_flush_pending(cuAprilTagsHandle h) {
+  if (!h->pending_back.valid) return B200AT_OK;
+  h->pending_back.valid = false;
+  return host_enqueue_back(h, h->pending_back);
+}
+
+int host_call_buffers(HostCall &c, uint32_t n, uint32_t nsub, uint32_t mt) {
+  if (c.cap_frames >= n && c.cap_subs >= nsub) return B200AT_OK;
+  if (c.frames_tab) cudaFreeHost(c.frames_tab);
+  if (c.src_tab) cudaFreeHost(c.src_tab);
+  if (c.out) cudaFreeHost(c.out);
+  if (c.out_count) cudaFreeHost(c.out_count);
+  if (c.counters) cudaFreeHost(c.counters);
+  c.frames_tab = c.src_tab = nullptr;
+  c.out = nullptr;
+  c.out_count = c.counters = nullptr;
+  c.cap_frames = c.cap_subs = 0;
+  const uint32_t nf = std::max(n, (uint32_t)c.cap_frames), ns = std::max(nsub, (uint32_t)c.cap_subs);
+  if (cudaMallocHost(&c.frames_tab, sizeof(FrameDesc) * nf) != cudaSuccess || cudaMallocHost(&c.src_tab, sizeof(FrameDesc) * nf) != cudaSuccess ||
+      cudaMallocHost(&c.out, sizeof(b200AprilTagsDetection_t) * (size_t)nf * mt) != cudaSuccess ||
+      cudaMallocHost(&c.out_count, sizeof(uint32_t) * nf) != cudaSuccess ||
+      cudaMallocHost(&c.counters, sizeof(uint32_t) * CNT_N * kMaxChunks * ns) != cudaSuccess) {
+    cudaGetLastError();
+    return B200AT_ERR_NOMEM;
+  }
+  c.cap_frames = nf;
+  c.cap_subs = ns;
+  return B200AT_OK;
+}
+
+int host_enqueue(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n) {
   const Geo &g = h->ws.g;
   const uint32_t mt = g.max_tags;
   const size_t row = (size_t)g.W * g.bpp;
-  int rc = B200AT_OK;
-  auto fail = [&](int code) {
-    if (prev != h->device) cudaSetDevice(prev);
-    return code;
-  };
-  // sub-batch size: small enough that copy(k+1) overlaps compute(k) inside one call, large enough to fill the GPU
-  uint32_t S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 15) / 16)));
-  bool S_forced = false;
-  if (const char *es = getenv("B200AT_HOST_SUB")) {
-    const int v = atoi(es);
-    if (v >= 1) {
-      S = std::min<uint32_t>(h->max_batch, (uint32_t)v);
-      S_forced = true;
-    }
-  }
+  // ---- everything that can fail on the arguments is checked before anything is queued ----
+  for (uint32_t i = 0; i < n; i++)
+    if (!frames[i].ptr || frames[i].pitch < row) return B200AT_ERR_INVALID_ARG;
+  const int slot_id = h->calls[0].active ? 1 : 0;
+  if (h->calls[slot_id].active) return B200AT_ERR_INVALID_ARG;  // two calls in flight already: collect one first
+  const uint32_t in_flight = (h->calls[0].active ? 1u : 0u) + (h->calls[1].active ? 1u : 0u);
+  int rc = host_streams_create(h);
+  if (rc != B200AT_OK) return rc;
+  HostCall &call = h->calls[slot_id];
   // (the encoding, hence the row size, can change between calls: b200AprilTagsSetInputEncoding)
   const size_t need_pitch = (row + 255) & ~(size_t)255;
-  const bool pitch_grew = need_pitch > h->stage_pitch;
-  if (pitch_grew) h->stage_pitch = need_pitch;
-  if (!h->copy_stream) {
-    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    for (int i = 0; i < 3; i++)
-      if (cudaEventCreateWithFlags(&h->ev_copied2[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    {
-      // the fetch and tail kernels are a handful of latency-bound CTAs (PCIe reads; one thread per detection): at the highest
-      // priority they get the first free SM slots instead of queueing behind the next sub-batch's full grids
-      int prio_lo = 0, prio_hi = 0;
-      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-      if (cudaStreamCreateWithPriority(&h->fetch_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-      if (cudaStreamCreateWithPriority(&h->tail_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    }
-    for (int i = 0; i < 3; i++) {
-      if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-      if (cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    }
-    for (int i = 0; i < 2; i++) {
-      if (cudaEventCreateWithFlags(&h->ev_front[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-      if (cudaEventCreateWithFlags(&h->ev_fetched[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-      if (cudaEventCreateWithFlags(&h->ev_decoded[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-      if (cudaEventCreateWithFlags(&h->ev_tail[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-      if (cudaEventCreateWithFlags(&h->ev_backdone[i], cudaEventDisableTiming) != cudaSuccess) return fail(B200AT_ERR_CUDA);
-    }
-  }
-  // Sparse staging (see k_decode.cu): with an integer quad_decimate f >= 2 the detector reads only every f-th row until the
-  // quads are known, so only those rows are DMA'd; the full-resolution rows around the quads are fetched afterwards straight
-  // from the caller's frames.  That needs pinned, device-mapped, 16-byte aligned host frames; anything else takes the full
-  // copy.  B200AT_SPARSE_H2D=0/1 overrides the default.
-  // A frame that is covered with tags (a calibration grid) needs nearly every row: the sparse path then moves as many bytes as
-  // the full copy, in smaller pieces.  After such a call the next eight take the full copy, then sparse staging is tried again.
-  bool sparse = kSparseHostPathDefault;
-  bool sparse_forced = false;
+  // Sparse staging needs pinned, device-mapped, 16-byte aligned host frames; anything else takes the full copy.
+  // B200AT_SPARSE_H2D=0/1 overrides the default.  A frame that is covered with tags (a calibration grid) needs nearly every row:
+  // the sparse path then moves as many bytes as the full copy, in smaller pieces -- after such a call the next eight take the
+  // full copy, then sparse staging is tried again.
+  bool sparse = true, sparse_forced = false;
   if (const char *es = getenv("B200AT_SPARSE_H2D")) {
     sparse = atoi(es) != 0;
     sparse_forced = true;
@@ -1058,66 +1094,42 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     h->sparse_skip--;
     sparse = false;
   }
-  if (g.f < 2 || (h->stage_pitch & 15)) sparse = false;
-  if (sparse) {
-    if (h->hp_src_cap < n) {
-      if (h->hp_src) cudaFreeHost(h->hp_src);
-      h->hp_src = nullptr;
-      h->hp_src_cap = 0;
-      if (cudaMallocHost(&h->hp_src, sizeof(FrameDesc) * n) != cudaSuccess) return fail(B200AT_ERR_NOMEM);
-      h->hp_src_cap = n;
+  if (g.f < 2) sparse = false;
+  std::vector<FrameDesc> src(sparse ? n : 0);
+  for (uint32_t i = 0; i < n && sparse; i++) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, frames[i].ptr) != cudaSuccess) {
+      cudaGetLastError();
+      sparse = false;
+      break;
     }
-    for (uint32_t i = 0; i < n && sparse; i++) {
-      cudaPointerAttributes pa;
-      if (!frames[i].ptr || cudaPointerGetAttributes(&pa, frames[i].ptr) != cudaSuccess) {
-        cudaGetLastError();
-        sparse = false;
-        break;
-      }
-      if (pa.type != cudaMemoryTypeHost || !pa.devicePointer || ((uintptr_t)pa.devicePointer & 15) || (frames[i].pitch & 15)) {
-        sparse = false;
-        break;
-      }
-      h->hp_src[i].ptr = (const uint8_t *)pa.devicePointer;
-      h->hp_src[i].pitch = frames[i].pitch;
+    if (pa.type != cudaMemoryTypeHost || !pa.devicePointer || ((uintptr_t)pa.devicePointer & 15) || (frames[i].pitch & 15)) {
+      sparse = false;
+      break;
     }
+    src[i].ptr = (const uint8_t *)pa.devicePointer;
+    src[i].pitch = frames[i].pitch;
   }
-  if (sparse && !h->sparse_bufs) {
-    Workspace &w = h->ws;
-    const size_t B = h->max_batch;
-    int rca = dev_alloc(h, &w.need1, B * g.H);
-    if (rca == 0) rca = dev_alloc(h, &w.need2, B * g.H);
-    if (rca == 0) rca = dev_alloc(h, &w.src_frames, B);
-    if (rca == 0 && !w.quad_H) rca = dev_alloc(h, &w.quad_H, (size_t)g.quad_cap * 10);
-    if (rca != 0) return fail(rca);
-    h->sparse_bufs = true;
+  // sub-batch size.  Sparse: the call is compute-bound and likes large sub-batches (the fixed cost per sub-batch -- ~30 launches,
+  // persistent-kernel tails -- is ~0.4 ms): max_batch / 4, two workspace views.  Full copy: PCIe-bound, short pipeline fill.
+  uint32_t S = sparse ? std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch / 2, std::max<uint32_t>(16, (h->max_batch + 3) / 4)))
+                      : std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch, std::max<uint32_t>(16, (h->max_batch + 15) / 16)));
+  if (const char *es = getenv("B200AT_HOST_SUB")) {
+    const int v = atoi(es);
+    if (v >= 1) S = std::min<uint32_t>(sparse ? std::max<uint32_t>(1, h->max_batch / 2) : h->max_batch, (uint32_t)v);
   }
-  // The full copy is PCIe-bound and likes small sub-batches (short pipeline fill); the sparse path is compute-bound and likes
-  // large ones (the fixed cost per sub-batch -- ~30 launches, persistent-kernel tails -- is ~0.4 ms): max_batch / 4.
-  if (sparse && !S_forced) S = std::max<uint32_t>(1, std::min<uint32_t>(h->max_batch / 2, std::max<uint32_t>(16, (h->max_batch + 3) / 4)));
-  // two sub-batches in flight on two streams (B200AT_HOST_STREAMS=1/2 overrides the default); needs two disjoint frame ranges
-  int nstreams = kHostStreamsDefault;
-  if (const char *es = getenv("B200AT_HOST_STREAMS")) nstreams = atoi(es);
-  if (nstreams != 2 || 2 * S > h->max_batch) nstreams = 1;
-  // Pipelined sparse path (B200AT_HOST_PIPE=0/1): the on-demand fetches of sub-batch k run on their own stream while the
-  // compute stream already detects the quads of sub-batch k+1; needs two workspace views and three staging slots.
-  // Levels (B200AT_HOST_PIPE): 1 = FETCH(k) is enqueued right after FRONT(k) (the schedule measured in round 2).  The trace
-  // of that schedule (profiles/r02_host_path_trace.txt) shows BACK(k-1) taking 1.3-1.5 ms instead of ~0.4: it starts together
-  // with FETCH(k), and its own second fetch queues behind that on PCIe.  3 (default) = FETCH(k) additionally waits for
-  // BACK(k-1): one more ordering constraint on the same dataflow, so every execution it allows was already allowed by level 1.
-  // 2 = 3 plus a counters block per sub-batch, so that FRONT(k) need not wait for the tail (reconcile / pose / D2H) of k-2
-  // (drops an ordering constraint: emulator-checked, to be raced on a GPU before it becomes the default).
-  int pipe_level = kHostPipeDefault;
-  if (const char *es = getenv("B200AT_HOST_PIPE")) pipe_level = atoi(es);
-  bool pipe = pipe_level != 0;
-  const bool pipe2 = pipe_level == 2;
-  const bool fetch_late = pipe_level >= 2;
-  if (!sparse || 2 * S > h->max_batch) pipe = false;
-  if (pipe) nstreams = 1;
+  const bool pipe = sparse && 2 * S <= h->max_batch;
+  if (!pipe) S = std::min<uint32_t>(S, h->max_batch);
   const uint32_t nslots = pipe ? 3 : 2;
-  if (!h->d_stage || h->stage_sub < S || h->stage_slots < nslots || pitch_grew) {
-    cudaStreamSynchronize(h->copy_stream);
-    cudaStreamSynchronize(h->own_stream);
+  // a change of mode, sub-batch size or staging geometry re-shapes what the calls in flight are using: drain first
+  const bool reshape = !h->d_stage || need_pitch > h->stage_pitch || h->stage_sub < S || h->stage_slots < nslots;
+  if (in_flight && (reshape || h->host_pipe != pipe || h->host_S != S)) {
+    rc = host_flush_pending(h);
+    host_drain(h);
+    if (rc != B200AT_OK) return rc;
+  }
+  if (reshape) {
+    host_drain(h);
     if (h->d_stage) {
       for (size_t i = 0; i < h->dev_allocs.size(); i++)
         if (h->dev_allocs[i] == h->d_stage) {
@@ -1128,191 +1140,151 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
       h->d_stage = nullptr;
     }
     void *p = nullptr;
+    const size_t pitch = std::max(need_pitch, h->stage_pitch);
     const uint32_t ss = std::max(S, h->stage_sub), sl = std::max(nslots, h->stage_slots);
-    if (cudaMalloc(&p, h->stage_pitch * g.H * (size_t)ss * sl) != cudaSuccess) return fail(B200AT_ERR_NOMEM);
+    if (cudaMalloc(&p, pitch * g.H * (size_t)ss * sl) != cudaSuccess) {
+      cudaGetLastError();
+      h->stage_sub = h->stage_slots = 0;
+      return B200AT_ERR_NOMEM;
+    }
     h->dev_allocs.push_back(p);
     h->d_stage = (uint8_t *)p;
+    h->stage_pitch = pitch;
     h->stage_sub = ss;
     h->stage_slots = sl;
   }
-  const int row_step = sparse ? g.f : 1;
-  const int rows_dma = 1 + (g.H - 1) / row_step;
-  static const bool sparse_debug = getenv("B200AT_SPARSE_DEBUG") != nullptr;  // poison the slot: an unfetched row cannot go unnoticed
-  // DMA queues: frames alternate between two copy streams (two copy engines) when B200AT_HOST_COPY_STREAMS=2
-  int ncopy = kHostCopyStreamsDefault;
-  if (const char *es = getenv("B200AT_HOST_COPY_STREAMS")) ncopy = atoi(es);
-  if (ncopy != 2 || (sparse && sparse_debug)) ncopy = 1;
-  uint64_t dma_bytes = 0;
-  // uniform sub-batches (a ramped schedule -- small first/last sub-batches to shorten pipeline fill and drain -- was
-  // measured and did not pay: the tiny sub-batches cost more in launch overhead than they save)
-  // In the pipelined sparse mode the call is compute-bound: the first sub-batches are small, so that the kernels start after
-  // a short first DMA, the later ones large, so that the fixed cost per sub-batch (launches, persistent-kernel tails) is paid
-  // fewer times (B200AT_HOST_RAMP=0 turns the ramp off).
-  bool ramp = pipe;
+  if (sparse && !h->sparse_bufs) {
+    Workspace &w = h->ws;
+    const size_t B = h->max_batch;
+    int rca = dev_alloc(h, &w.need1, B * g.H);
+    if (rca == 0) rca = dev_alloc(h, &w.need2, B * g.H);
+    if (rca == 0) rca = dev_alloc(h, &w.src_frames, B);
+    if (rca == 0 && !w.quad_H) rca = dev_alloc(h, &w.quad_H, (size_t)g.quad_cap * 10);
+    if (rca != 0) return rca;
+    h->sparse_bufs = true;
+  }
+  // sub-batches.  With nothing in flight the first two are small, so that the kernels start after a short first DMA
+  // (B200AT_HOST_RAMP=0 turns the ramp off); with a call in flight the pipeline is full already.
+  bool ramp = pipe && in_flight == 0;
   if (const char *es = getenv("B200AT_HOST_RAMP")) ramp = ramp && atoi(es) != 0;
   std::vector<uint32_t> sub_start, sub_len;
-  for (uint32_t pos = 0, k = 0; pos < n; k++) {
+  for (uint32_t pos = 0, j = 0; pos < n; j++) {
     uint32_t len = S;
-    if (ramp && k == 0) len = std::max<uint32_t>(1, S / 4);
-    if (ramp && k == 1) len = std::max<uint32_t>(1, S / 2);
+    if (ramp && j == 0) len = std::max<uint32_t>(1, S / 4);
+    if (ramp && j == 1) len = std::max<uint32_t>(1, S / 2);
     len = std::min<uint32_t>(len, n - pos);
     sub_start.push_back(pos);
     sub_len.push_back(len);
     pos += len;
   }
   const uint32_t nsub = (uint32_t)sub_start.size();
-  if (h->hp_cap_frames < n || h->hp_cap_subs < nsub) {
-    if (h->hp_frames) cudaFreeHost(h->hp_frames);
-    if (h->hp_out) cudaFreeHost(h->hp_out);
-    if (h->hp_out_count) cudaFreeHost(h->hp_out_count);
-    if (h->hp_counters) cudaFreeHost(h->hp_counters);
-    h->hp_frames = nullptr;
-    h->hp_out = nullptr;
-    h->hp_out_count = nullptr;
-    h->hp_counters = nullptr;
-    h->hp_cap_frames = h->hp_cap_subs = 0;
-    if (cudaMallocHost(&h->hp_frames, sizeof(FrameDesc) * n) != cudaSuccess || cudaMallocHost(&h->hp_out, sizeof(b200AprilTagsDetection_t) * (size_t)n * mt) != cudaSuccess ||
-        cudaMallocHost(&h->hp_out_count, sizeof(uint32_t) * n) != cudaSuccess || cudaMallocHost(&h->hp_counters, sizeof(uint32_t) * CNT_N * kMaxChunks * nsub) != cudaSuccess)
-      return fail(B200AT_ERR_NOMEM);
-    h->hp_cap_frames = n;
-    h->hp_cap_subs = nsub;
-  }
+  rc = host_call_buffers(call, n, nsub, mt);
+  if (rc != B200AT_OK) return rc;
+  if (sparse) memcpy(call.src_tab, src.data(), sizeof(FrameDesc) * n);
+  call.n = n;
+  call.nsub = nsub;
+  call.sparse = sparse;
+  call.launches = 0;
+  call.dma_bytes = 0;
+  call.active = true;
+  call.seq = h->host_seq++;
+  h->host_pipe = pipe;
+  h->host_S = S;
+  const int row_step = sparse ? g.f : 1;
+  const int rows_dma = 1 + (g.H - 1) / row_step;
+  static const bool sparse_debug = getenv("B200AT_SPARSE_DEBUG") != nullptr;  // poison the slot: an unfetched row cannot go unnoticed
   std::vector<b200AprilTagsFrame_t> dframes(S);
-  int launches = 0;
-  // B200AT_HOST_TRACE=1: timestamps (CUDA events) of every sub-batch's DMA / FRONT / FETCH / BACK / tail, printed to stderr
-  static const bool trace = getenv("B200AT_HOST_TRACE") != nullptr;
-  struct Mark {
-    const char *what;
-    uint32_t k;
-    cudaEvent_t ev;
-  };
-  std::vector<Mark> marks;
-  auto mark = [&](const char *what, uint32_t k, cudaStream_t st) {
-    if (!trace) return;
-    cudaEvent_t ev = nullptr;
-    if (cudaEventCreate(&ev) != cudaSuccess) return;
-    cudaEventRecord(ev, st);
-    marks.push_back({what, k, ev});
-  };
-  mark("t0", 0, h->own_stream);
-  for (uint32_t k = 0; k < nsub && rc == B200AT_OK; k++) {
-    const uint32_t i0 = sub_start[k], m = sub_len[k];
+  cudaStream_t cs = h->own_stream;
+  rc = B200AT_OK;
+  for (uint32_t j = 0; j < nsub && rc == B200AT_OK; j++) {
+    const uint64_t k = h->host_k++;
+    const uint32_t i0 = sub_start[j], m = sub_len[j];
     const int slot = (int)(k % nslots);
     uint8_t *slot_base = h->d_stage + (size_t)slot * h->stage_sub * h->stage_pitch * g.H;
-    cudaError_t e = cudaSuccess;
-    if (k >= nslots) e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again
-    if (k >= nslots && ncopy == 2 && e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream2, h->ev_consumed[slot], 0);
+    cudaError_t e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again (no-op before its first use)
     if (sparse && sparse_debug && e == cudaSuccess) e = cudaMemsetAsync(slot_base, 0xA5, (size_t)m * h->stage_pitch * g.H, h->copy_stream);
-    mark("dma_begin", k, h->copy_stream);
-    for (uint32_t j = 0; j < m && e == cudaSuccess; j++) {
-      if (!frames[i0 + j].ptr || frames[i0 + j].pitch < row) return fail(B200AT_ERR_INVALID_ARG);
-      uint8_t *dst = slot_base + (size_t)j * h->stage_pitch * g.H;
+    for (uint32_t q = 0; q < m && e == cudaSuccess; q++) {
+      uint8_t *dst = slot_base + (size_t)q * h->stage_pitch * g.H;
       // rows 0, f, 2f, ... (all rows on the full-copy path)
-      e = cudaMemcpy2DAsync(dst, h->stage_pitch * row_step, frames[i0 + j].ptr, frames[i0 + j].pitch * row_step, row, rows_dma,
-                            cudaMemcpyHostToDevice, (ncopy == 2 && (j & 1)) ? h->copy_stream2 : h->copy_stream);
-      dma_bytes += (uint64_t)row * rows_dma;
-      dframes[j].ptr = dst;
-      dframes[j].pitch = h->stage_pitch;
+      e = cudaMemcpy2DAsync(dst, h->stage_pitch * row_step, frames[i0 + q].ptr, frames[i0 + q].pitch * row_step, row, rows_dma,
+                            cudaMemcpyHostToDevice, h->copy_stream);
+      call.dma_bytes += (uint64_t)row * rows_dma;
+      dframes[q].ptr = dst;
+      dframes[q].pitch = h->stage_pitch;
     }
-    cudaStream_t cs = (nstreams == 2 && slot) ? h->lane_stream : h->own_stream;
-    mark("dma_end", k, h->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[slot], h->copy_stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied[slot], 0);
-    if (ncopy == 2) {
-      if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied2[slot], h->copy_stream2);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied2[slot], 0);
+    if (e != cudaSuccess) {
+      rc = B200AT_ERR_CUDA;
+      break;
     }
-    if (e != cudaSuccess) return fail(B200AT_ERR_CUDA);
     int l = 0;
     if (pipe) {
-      // compute stream: FRONT(k), BACK(k-1), FRONT(k+1), ...; fetch stream: FETCH(k) between FRONT(k) and BACK(k)
       const int vw = (int)(k & 1);
-      auto view_of = [&](uint32_t kk) {
-        Workspace v = make_view(h, (int)(kk & 1) * (int)S, (int)(kk & 1), 2);
-        if (pipe2) v.counters = h->ws.counters + (size_t)(kk % kMaxChunks) * CNT_N;  // FRONT(kk + 2) zeroes another block
-        return v;
-      };
-      // the view's previous user (sub-batch k-2) may still have its reconcile / pose / D2H on the tail stream
-      if (!pipe2 && k >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      mark("front_begin", k, cs);
-      if (rc == B200AT_OK)
-        rc = enqueue_view(h, view_of(k), dframes.data(), m, cs, h->hp_frames + i0, nullptr, nullptr, nullptr, &l, h->hp_src + i0, VIEW_FRONT);
-      launches += l;
-      mark("front_end", k, cs);
+      rc = enqueue_view(h, host_view_of(h, k, S), dframes.data(), m, cs, call.frames_tab + i0, nullptr, nullptr, nullptr, &l, call.src_tab + i0, VIEW_FRONT);
+      call.launches += l;
       if (rc == B200AT_OK && cudaEventRecord(h->ev_front[vw], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      auto enqueue_fetch = [&]() {
-        if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        if (rc == B200AT_OK && fetch_late && k >= 1 && cudaStreamWaitEvent(h->fetch_stream, h->ev_backdone[vw ^ 1], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        if (rc == B200AT_OK) rc = enqueue_view_part(h, view_of(k), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
-        launches += l;
-        mark("fetch_end", k, h->fetch_stream);
-        if (rc == B200AT_OK && cudaEventRecord(h->ev_fetched[vw], h->fetch_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      };
-      auto enqueue_back = [&](uint32_t kb) {
-        const int vb = (int)(kb & 1);
-        const uint32_t ib = sub_start[kb], mb = sub_len[kb];
-        if (rc == B200AT_OK && cudaStreamWaitEvent(cs, h->ev_fetched[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        // (level 2) the decoder overwrites the candidates / outputs that the tail of this view's previous user still reads
-        if (rc == B200AT_OK && pipe2 && kb >= 2 && cudaStreamWaitEvent(cs, h->ev_tail[vb], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        mark("back_begin", kb, cs);
-        if (rc == B200AT_OK)
-          rc = enqueue_view_part(h, view_of(kb), VIEW_BACK, mb, cs, h->hp_out + (size_t)ib * mt, h->hp_out_count + ib,
-                                 h->hp_counters + (size_t)kb * CNT_N * kMaxChunks, &l, h->tail_stream, h->ev_decoded[vb]);
-        launches += l;
-        // the staged frames are dead once the decoder has run (the tail does not read them)
-        if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[kb % nslots], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        if (rc == B200AT_OK && cudaEventRecord(h->ev_backdone[vb], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
-        mark("back_end", kb, cs);
-        mark("tail_end", kb, h->tail_stream);
-        if (rc == B200AT_OK && cudaEventRecord(h->ev_tail[vb], h->tail_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
-      };
-      if (!fetch_late) enqueue_fetch();
-      if (k >= 1) enqueue_back(k - 1);
-      if (fetch_late) enqueue_fetch();
-      if (k + 1 == nsub) enqueue_back(k);  // after the last FRONT also the BACK of this sub-batch
+      // BACK of the previous sub-batch (this call's, or the one the previous call left pending)
+      if (rc == B200AT_OK) rc = host_flush_pending(h);
+      // FETCH(k): after FRONT(k) and after BACK(k - 1), whose second fetch would otherwise queue behind this one on PCIe
+      if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_front[vw], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == B200AT_OK && cudaStreamWaitEvent(h->fetch_stream, h->ev_backdone[vw ^ 1], 0) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == B200AT_OK) rc = enqueue_view_part(h, host_view_of(h, k, S), VIEW_FETCH, m, h->fetch_stream, nullptr, nullptr, nullptr, &l);
+      call.launches += l;
+      if (rc == B200AT_OK && cudaEventRecord(h->ev_fetched[vw], h->fetch_stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == B200AT_OK) {
+        HostPendingBack &pb = h->pending_back;
+        pb.valid = true;
+        pb.call = slot_id;
+        pb.k = k;
+        pb.sub = j;
+        pb.start = i0;
+        pb.len = m;
+        pb.last = j + 1 == nsub;
+      }
       continue;
     }
-    if (nstreams == 2)
-      rc = enqueue_view(h, make_view(h, slot * (int)S, slot, 2), dframes.data(), m, cs, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt,
-                        h->hp_out_count + i0, h->hp_counters + (size_t)k * CNT_N * kMaxChunks, &l, sparse ? h->hp_src + i0 : nullptr);
-    else
-      rc = enqueue_core(h, dframes.data(), m, h->own_stream, h->hp_frames + i0, h->hp_out + (size_t)i0 * mt, h->hp_out_count + i0,
-                        h->hp_counters + (size_t)k * CNT_N * kMaxChunks, false, &l, false, sparse ? h->hp_src + i0 : nullptr);
-    launches += l;
-    mark("compute_end", k, cs);
+    rc = enqueue_core(h, dframes.data(), m, cs, call.frames_tab + i0, call.out + (size_t)i0 * mt, call.out_count + i0,
+                      call.counters + (size_t)j * CNT_N * kMaxChunks, false, &l, false, sparse ? call.src_tab + i0 : nullptr);
+    call.launches += l;
     if (rc == B200AT_OK && cudaEventRecord(h->ev_consumed[slot], cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    if (rc == B200AT_OK && j + 1 == nsub && cudaEventRecord(call.done, cs) != cudaSuccess) rc = B200AT_ERR_CUDA;
   }
-  cudaError_t es = cudaStreamSynchronize(h->own_stream);
-  if (pipe) {
-    const cudaError_t es2 = cudaStreamSynchronize(h->tail_stream);
-    if (es == cudaSuccess) es = es2;
+  if (rc != B200AT_OK) {
+    // nothing of this call may still be running when the error is reported (the caller is free to release its frames)
+    h->pending_back.valid = false;
+    host_drain(h);
+    call.active = false;
+    if (h->calls[slot_id ^ 1].active) h->calls[slot_id ^ 1].failed = true;  // (the drain cut its pending work short)
+    return rc;
   }
-  if (nstreams == 2) {
-    const cudaError_t es2 = cudaStreamSynchronize(h->lane_stream);
-    if (es == cudaSuccess) es = es2;
-  }
-  cudaStreamSynchronize(h->copy_stream);
-  cudaStreamSynchronize(h->copy_stream2);
-  if (trace && !marks.empty()) {
-    fprintf(stderr, "[b200apriltags] host-path trace: n=%u S=%u sparse=%d pipe=%d (ms since the call's first event)\n", n, S, (int)sparse, (int)pipe);
-    for (size_t i = 1; i < marks.size(); i++) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, marks[0].ev, marks[i].ev);
-      fprintf(stderr, "  %-12s k=%-3u len=%-3u %8.3f\n", marks[i].what, marks[i].k, sub_len[marks[i].k], ms);
-    }
-    for (auto &mk : marks) cudaEventDestroy(mk.ev);
-  }
-  if (prev != h->device) cudaSetDevice(prev);
-  if (rc != B200AT_OK) return rc;
-  if (es != cudaSuccess) {
-    fprintf(stderr, "[b200apriltags] batch failed: %s\n", cudaGetErrorString(es));
-    return B200AT_ERR_CUDA;
+  return B200AT_OK;
+}
+
+int host_collect(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts) {
+  // the older of the calls in flight
+  int id = -1;
+  for (int i = 0; i < 2; i++)
+    if (h->calls[i].active && (id < 0 || h->calls[i].seq < h->calls[id].seq)) id = i;
+  if (id < 0) return B200AT_ERR_INVALID_ARG;
+  HostCall &call = h->calls[id];
+  const Geo &g = h->ws.g;
+  const uint32_t mt = g.max_tags, n = call.n;
+  int rc = B200AT_OK;
+  if (h->pending_back.valid && h->pending_back.call == id) rc = host_flush_pending(h);
+  cudaError_t es = rc == B200AT_OK ? cudaEventSynchronize(call.done) : cudaSuccess;
+  call.active = false;
+  if (rc != B200AT_OK || es != cudaSuccess || call.failed) {
+    call.failed = false;
+    host_drain(h);
+    if (es != cudaSuccess) fprintf(stderr, "[b200apriltags] batch failed: %s\n", cudaGetErrorString(es));
+    return rc != B200AT_OK ? rc : B200AT_ERR_CUDA;
   }
   uint32_t status = 0;
   uint64_t pts = 0, clu = 0, qd = 0, dt = 0, fetched = 0;
-  for (uint32_t k = 0; k < nsub; k++) {
+  for (uint32_t k = 0; k < call.nsub; k++) {
     uint32_t c[CNT_N];
-    sum_counters(h->hp_counters + (size_t)k * CNT_N * kMaxChunks, c);
+    sum_counters(call.counters + (size_t)k * CNT_N * kMaxChunks, c);
     status |= c[CNT_STATUS];
     fetched += c[CNT_FETCHED];
     pts += c[CNT_POINTS];
@@ -1321,27 +1293,58 @@ int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t
     dt += c[CNT_DETS];
   }
   for (uint32_t i = 0; i < n; i++) {
-    uint32_t c = std::min(h->hp_out_count[i], mt);
+    const uint32_t c = std::min(call.out_count[i], mt);
     if (counts) counts[i] = c;
-    if (dets_out) memcpy(dets_out + (size_t)i * mt, h->hp_out + (size_t)i * mt, sizeof(b200AprilTagsDetection_t) * c);
+    if (dets_out) memcpy(dets_out + (size_t)i * mt, call.out + (size_t)i * mt, sizeof(b200AprilTagsDetection_t) * c);
     if (ids_out)
-      for (uint32_t k = 0; k < c; k++) to_id_struct(h->hp_out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
+      for (uint32_t k = 0; k < c; k++) to_id_struct(call.out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
   }
   h->last_status = status;
-  h->launches = launches;
-  h->last_counters[0] = (uint64_t)launches;
+  h->launches = call.launches;
+  h->last_counters[0] = (uint64_t)call.launches;
   h->last_counters[1] = pts;
   h->last_counters[2] = clu;
   h->last_counters[3] = qd;
   h->last_counters[5] = dt;
-  h->last_counters[6] = dma_bytes + fetched * 16;  // host->device bytes of this call: DMA + rows fetched on demand
-  h->last_counters[7] = sparse ? 1 : 0;
+  h->last_counters[6] = call.dma_bytes + fetched * 16;  // host->device bytes of this call: DMA + rows fetched on demand
+  h->last_counters[7] = call.sparse ? 1 : 0;
   {
     const char *eb = getenv("B200AT_SPARSE_BACKOFF");
     const double backoff = eb ? atof(eb) : 0.85;
-    if (sparse && (double)(dma_bytes + fetched * 16) > backoff * (double)row * g.H * n) h->sparse_skip = 8;
+    const size_t row = (size_t)g.W * g.bpp;
+    if (call.sparse && (double)(call.dma_bytes + fetched * 16) > backoff * (double)row * g.H * n) h->sparse_skip = 8;
   }
   return status ? B200AT_ERR_OVERFLOW : B200AT_OK;
+}
+
+}  // namespace
+
+int b200AprilTagsEnqueueBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n) {
+  if (!h || !frames || n == 0 || h->in_flight) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  const int rc = host_enqueue(h, frames, n);
+  if (prev != h->device) cudaSetDevice(prev);
+  return rc;
+}
+
+int b200AprilTagsCollectBatchHost(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts) {
+  if (!h) return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  const int rc = host_collect(h, dets_out, ids_out, counts);
+  if (prev != h->device) cudaSetDevice(prev);
+  return rc;
+}
+
+int b200AprilTagsDetectBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, b200AprilTagsDetection_t *dets_out,
+                                 cuAprilTagsID_t *ids_out, uint32_t *counts) {
+  if (!h || h->calls[0].active || h->calls[1].active) return B200AT_ERR_INVALID_ARG;  // (asynchronous calls in flight: collect them first)
+  const int rc = b200AprilTagsEnqueueBatchHost(h, frames, n);
+  if (rc != B200AT_OK) return rc;
+  return b200AprilTagsCollectBatchHost(h, dets_out, ids_out, counts);
 }
 
 // A caller that passes the legacy default stream (nullptr) still gets the CUDA-graph replay path: capture is not possible on
@@ -1353,7 +1356,7 @@ static cudaStream_t resolve_sync_stream(cuAprilTagsHandle h, cudaStream_t stream
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
   cudaStream_t use = h->own_stream;
-  if (cudaEventRecord(h->ev_pipe_start, cudaStreamLegacy) != cudaSuccess || cudaStreamWaitEvent(h->own_stream, h->ev_pipe_start, 0) != cudaSuccess) {
+  if (cudaEventRecord(h->ev_in, cudaStreamLegacy) != cudaSuccess || cudaStreamWaitEvent(h->own_stream, h->ev_in, 0) != cudaSuccess) {
     cudaGetLastError();
     use = nullptr;  // (cannot order against the legacy stream: run there, without the graph)
   }

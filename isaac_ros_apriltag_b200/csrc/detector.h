@@ -117,23 +117,13 @@ struct FitParams {
   float tagsize;
 };
 
-// Performance knobs, read once per handle from the environment (B200AT_TUNE="key=value,key=value"; see capi.cu).  They never
-// change results, only how the work is mapped; tools/gpu_tune.py sweeps them on the GPU.
+// Per-handle knobs, read once from the environment (B200AT_TUNE="key=value,key=value"; see capi.cu).  Every variant that did not
+// win its measurement was deleted (profiles/r03_variants.md); what is left are two real trade-offs.
 struct Tune {
-  int thr_early;      // k_threshold4: pixel loads issued before the tile min/max staging barrier
-  int ccl_sweep;      // k_ccl_tile_sweep (warp per tile, label inheritance) instead of k_ccl_tile; 2 = without TMA staging; 3 = ILP variant; 4 = no staging, 6 KB of shared memory per tile
-  int ccl_flat;       // k_ccl_roots + k_ccl_flatmark (roots first, then one gather per pixel with the size gate fused) instead of flatten + mark
-  int cluster_eager;  // k_cluster_pass: 1 = unconditional label loads + speculative offset load; 2 = k_cluster_pass4 (4 px / thread); 3 = 2 with deferred stores in the emit pass; 4 = count pass records the points, scatter pass instead of emit
-  int decode_split;   // device-pointer path: k_refine + k_decode_bits instead of the fused k_decode
-  int decode_pair;    // k_refine: two short edges per pass (lanes 0-15 / 16-31)
-  int decode_ctas;    // persistent decode CTAs per SM
-  int qf_mc;          // quad fit, one-warp bins: 1 = several clusters per CTA in phase lockstep (shared instruction stream);
-                      // 2 = same with more warps for the 128 bin; 3 = occupancy variants instead (k_quad.cu, launch_quadfit)
-  int qf_sort;        // quad fit sort: serial merge with one-key lookahead per run (refill loads off the critical path)
-  float qf_scale;     // scales the persistent grid of every quad-fit bin
-  int qf_keys23;      // 512 / 1024-point bins with the prefix moments in the L2-resident scratch
-  int qf_exact;       // 1 = k_quad.cu (one CTA per cluster, serial prefix sums: float corners bit-identical to the CPU oracle);
-                      // 0 = k_quad2.cu (sort / windowed moments / tail: same formulas, prefix sums associated differently)
+  int ccl_tma;    // 1 (default) = CCL tiles staged in shared memory by TMA; 0 = no staging (measured 0.16 ms per 256 frames faster,
+                  // and the pipeline is then TMA-free)
+  int qf_exact;   // 1 = k_quad.cu (one CTA per cluster, serial prefix sums: float corners bit-identical to the CPU oracle);
+                  // 0 (default) = k_quad2.cu (sort / windowed moments / tail: same formulas, prefix sums associated differently)
 };
 
 struct Workspace {
@@ -170,10 +160,6 @@ struct Workspace {
   uint32_t qwork_cap;
   double *qwtot;               // [qwork_cap][6] moment totals of the chunk
   uint32_t *qwnmax;            // [qwork_cap] local maxima found in the chunk
-  // cluster_eager=4: per-row lists of (table slot, packed point) written by the count pass, consumed by k_cluster_scatter
-  uint2 *rec;
-  uint32_t *rec_cnt;
-  int rec_cap;
   const unsigned char *combos;  // per nm (4..kMaxNMaxima): all m0<m1<m2<m3 < nm in lexicographic order, uchar4 each
   int combo_off[18];     // combos for nm start at combo_off[nm], count combo_off[nm+1]-combo_off[nm]
   CUtensorMap thr_tmap;  // TMA descriptor of thr as a (Wp, Hd, B) u8 tensor, box 64 x 33 x 1 (CCL tile + halo)

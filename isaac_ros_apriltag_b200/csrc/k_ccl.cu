@@ -4,13 +4,12 @@
 //
 // Design: label-equivalence union-find with atomicMin (representative = minimum pixel index, which is also
 // the oracle's canonical label):
-//   1. k_ccl_tile   : 32x32 tile per CTA (staged by ONE TMA bulk tensor copy incl. halo), warp per row: runs by ballot,
-//                     vertical links by shared-memory union-find
-//   2. k_ccl_border : only links that cross tile borders are merged in global memory
-//   3. k_ccl_flatten: every pixel to its root (4 px/thread, interleaved chases); sizes were counted per local root in
-//                     shared memory by k_ccl_tile, merged local roots move their count to the global root
-//   4. k_ccl_mark   : thr2 = thr, but pixels of components with < 25 px become 127 (folds the size gates of
-//                     gradient_clusters into one byte image)
+//   1. k_ccl_tile_sweep : ONE WARP per 32x32 tile (staged incl. halo by a TMA bulk tensor copy), rows top to bottom: runs by ballot,
+//                         a run that touches the component above inherits its label, shared-memory unions only where a run
+//                         touches two labels; pixel counts per local root
+//   2. k_ccl_border     : only links that cross tile borders are merged in global memory
+//   3. k_ccl_roots      : the former tile roots (~5 % of the pixels) chase to their global root and hand over their count
+//   4. k_ccl_flatmark   : one gather per pixel lab[lab[p]], fused with the size gate thr2 (components < 25 px -> 127)
 // Algorithmic bytes per frame: read Pd (thr) + write 4*Pd (labels) = 5*Pd (SURVEY 8d contract figure).
 #include "detector.h"
 
@@ -98,129 +97,8 @@ __device__ __forceinline__ void unite_g(uint32_t *L, uint32_t a, uint32_t b) {
   } while (!done);
 }
 
-// 32x32 tile per CTA, one warp per tile row (8 warps x 4 rows).  Horizontal runs are resolved with one ballot per row
-// (label = first pixel of the run, no atomics); only the vertical / diagonal links need shared-memory unions.
 constexpr int TPITCH = 64;  // shared-memory row pitch of the staged tile = TMA box width: x0-16 .. x0+47
 constexpr int TOFF = 16;    // column of pixel x0 (TMA needs the box start 16-byte aligned: x0-16; the halo x0-1 is column 15)
-
-// (A vertical link whose left neighbour already joins the same two runs needs no elision here: AprilRobotics' own rule
-// `!(vL == vUL && vUL == vU)` in ccl_links removes exactly those.  On the bench workload -- thresholded noise, mean run length
-// 2.3 px -- that leaves 0.34 vertical + 0.15 diagonal unions per pixel.)
-template <bool USE_TMA>
-__global__ void __launch_bounds__(256) k_ccl_tile(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
-                                                  uint32_t *__restrict__ csize, int Wp, const __grid_constant__ CUtensorMap tmap) {
-  __shared__ __align__(128) uint8_t t[TH + 1][TPITCH];  // [0] = row above the tile; column TOFF = x0
-  __shared__ __align__(8) unsigned long long mbar;
-  __shared__ uint32_t L[TH * TW];
-  __shared__ uint32_t cnt[TH * TW];      // pixels per local root
-  const int fr = blockIdx.z;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-#ifndef B200AT_EMU  // (tools/emu compiles this file with g++: no PTX there, the plain staging below is used)
-  if (USE_TMA) {
-    // TMA staging: one cp.async.bulk.tensor of the (64 x 33) u8 box at (x0-16, y0-1, frame); out-of-bounds elements are
-    // zero-filled by the hardware (the link predicates never consult pixels outside the image, see ccl_links).
-    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&t[0][0]);
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(TPITCH * (TH + 1))) : "memory");
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-          "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - TOFF), "r"(y0 - 1), "r"(fr + g.tma_frame0), "r"(mb)
-          : "memory");
-    }
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_TMA:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@!p bra WAIT_TMA;\n"
-        "}\n" ::"r"(mb)
-        : "memory");
-  } else
-#endif
-  {
-    // fallback staging: (TH+1) x (TW+2) bytes; out-of-image = 127 (never links)
-    for (int i = tid; i < (TH + 1) * (TW + 2); i += 256) {
-      int r = i / (TW + 2), c = i % (TW + 2);
-      int y = y0 - 1 + r, x = x0 - 1 + c;
-      uint8_t v = 127;
-      if (y >= 0 && y < g.Hd && x >= 0 && x < g.Wd) v = img[(size_t)y * Wp + x];
-      t[r][c + TOFF - 1] = v;
-    }
-    __syncthreads();
-  }
-  // pass 1: per row, links + run starts
-  Nb nb[TH / 8];
-#pragma unroll
-  for (int k = 0; k < TH / 8; k++) {
-    const int ly = wid + 8 * k, lx = lane;
-    const int x = x0 + lx, y = y0 + ly;
-    Nb n = {false, false, false, false};
-    if (x < g.Wd && y < g.Hd) {
-      const int v = t[ly + 1][lx + TOFF];
-      n = ccl_links(v, t[ly + 1][lx + TOFF - 1], t[ly][lx + TOFF], t[ly][lx + TOFF - 1], t[ly][lx + TOFF + 1], x, y, g.Wd);
-    }
-    nb[k] = n;
-    const unsigned ml = __ballot_sync(0xffffffffu, n.L && lx > 0);  // bit x: x is linked to x-1 inside the tile
-    const unsigned brk = ~ml & ((2u << lane) - 1u);                  // run breaks at or below this lane (bit 0 always set)
-    const int rs = 31 - __clz(brk);
-    L[ly * TW + lx] = (uint32_t)(ly * TW + rs);
-    cnt[ly * TW + lx] = 0;
-  }
-  __syncthreads();
-  // pass 2: vertical / diagonal links (AprilRobotics' elisions already removed the redundant ones)
-#pragma unroll
-  for (int k = 0; k < TH / 8; k++) {
-    const int ly = wid + 8 * k, lx = lane;
-    const int i = ly * TW + lx;
-    const Nb n = nb[k];
-    if (ly > 0) {
-      if (n.U) unite_s(L, i, i - TW);
-      if (n.UL && lx > 0) unite_s(L, i, i - TW - 1);
-      if (n.UR && lx < TW - 1) unite_s(L, i, i - TW + 1);
-    }
-  }
-  __syncthreads();
-  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
-  uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
-  // flatten inside the tile + count pixels per local root (lanes sharing a root issue one shared-memory atomic)
-#pragma unroll
-  for (int k = 0; k < TH / 8; k++) {
-    const int ly = wid + 8 * k, lx = lane;
-    const int i = ly * TW + lx;
-    const int x = x0 + lx, y = y0 + ly;
-    const bool in = (x < g.Wd && y < g.Hd);
-    uint32_t r = 0xffffffffu;
-    bool counted = false;
-    if (in) {
-      r = find_s(L, i);
-      const int ry = r / TW, rx = r % TW;
-      labf[(size_t)y * Wp + x] = (uint32_t)((y0 + ry) * Wp + (x0 + rx));
-      counted = t[ly + 1][lx + TOFF] != 127;
-    }
-    const unsigned act = __ballot_sync(0xffffffffu, counted);
-    if (counted) {
-      const unsigned peers = __match_any_sync(act, r);
-      if (lane == __ffs(peers) - 1) atomicAdd(&cnt[r], (uint32_t)__popc(peers));
-    }
-  }
-  __syncthreads();
-  // component size lives at the representative; 127 pixels are singletons (never connected upstream)
-#pragma unroll
-  for (int k = 0; k < TH / 8; k++) {
-    const int ly = wid + 8 * k, lx = lane;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= g.Wd || y >= g.Hd) continue;
-    szf[(size_t)y * Wp + x] = (t[ly + 1][lx + TOFF] == 127) ? 1u : cnt[ly * TW + lx];
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Row-sweep variant of the tile kernel: ONE WARP per 32x32 tile (lane = column), rows top to bottom.  A run of a row that
@@ -235,9 +113,7 @@ constexpr int SWEEP_TILES = 4;
 constexpr int TBYTES = TPITCH * (TH + 1);              // one staged tile + halo row
 constexpr int TSLOT = (TBYTES + 127) & ~127;           // 128-byte aligned slots
 
-// ILP variant (ccl_sweep=3): the three bytes of the next row are loaded while the current row is processed (the row above
-// stays in registers), and the final flatten chases four rows' pointers interleaved instead of one find after the other.
-template <bool USE_TMA, bool ILP>
+template <bool USE_TMA>
 __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                                       uint32_t *__restrict__ csize, int Wp,
                                                                       const __grid_constant__ CUtensorMap tmap) {
@@ -300,33 +176,12 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
   const int x = x0 + lane;
   const int rows = min(TH, g.Hd - y0);
   uint32_t plab = NONE;  // label of the pixel above (row ly - 1) in this lane's column
-  // ILP: bytes of the row above (u*) and of the current row (c*) live in registers; the next row (n*) is in flight
-  int ul = 0, uc = 0, ur = 0, cl = 0, cc = 0, cr = 0;
-  if (ILP) {
-    const uint8_t *t0 = t + lane + TOFF;
-    ul = t0[-1];
-    uc = t0[0];
-    ur = t0[1];
-    cl = t0[TPITCH - 1];
-    cc = t0[TPITCH];
-    cr = t0[TPITCH + 1];
-  }
   for (int ly = 0; ly < rows; ly++) {
     const int y = y0 + ly;
     const uint8_t *tr = t + (ly + 1) * TPITCH + lane + TOFF, *tu = tr - TPITCH;
     Nb n = {false, false, false, false};
-    int nl = 0, nc = 0, nr = 0;
-    if (ILP) {
-      if (ly + 1 < rows) {  // (row ly + 2 of the staged tile exists: it has TH + 1 rows)
-        nl = tr[TPITCH - 1];
-        nc = tr[TPITCH];
-        nr = tr[TPITCH + 1];
-      }
-      if (x < g.Wd) n = ccl_links(cc, cl, uc, ul, ur, x, y, g.Wd);
-    } else {
-      if (x < g.Wd) n = ccl_links(tr[0], tr[-1], tu[0], tu[-1], tu[1], x, y, g.Wd);
-    }
-    const int vcur = ILP ? cc : (int)tr[0];
+    if (x < g.Wd) n = ccl_links(tr[0], tr[-1], tu[0], tu[-1], tu[1], x, y, g.Wd);
+    const int vcur = (int)tr[0];
     const unsigned ml = __ballot_sync(0xffffffffu, n.L && lane > 0);  // bit x: x is linked to x-1 inside the tile
     const unsigned upto = (2u << lane) - 1u;                          // lanes 0..lane (lane 31: all ones)
     const int rs = 31 - __clz(~ml & upto);                            // first lane of my run (bit 0 of ~ml is always set)
@@ -360,59 +215,12 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
     if (lane == rs && x < g.Wd && vcur != 127) atomicAdd(&cnt[rl], (uint32_t)__popc(run_mask));
     plab = rl;
-    if (ILP) {
-      ul = cl;
-      uc = cc;
-      ur = cr;
-      cl = nl;
-      cc = nc;
-      cr = nr;
-    }
   }
   __syncwarp();
   uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
   uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
   // flatten inside the tile; counts collected at merged labels move to their final local root
-  if (ILP) {
-    for (int ly0 = 0; ly0 < rows; ly0 += 4) {
-      // find_s of four rows, step by step and interleaved: four independent shared-memory chases in flight per lane
-      uint32_t a[4], p[4];
-      bool done[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        a[u] = (uint32_t)(min(ly0 + u, rows - 1) * TW + lane);
-        p[u] = L[a[u]];
-        done[u] = p[u] == a[u];
-      }
-      while (!(done[0] && done[1] && done[2] && done[3])) {
-        uint32_t gp[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) gp[u] = done[u] ? p[u] : L[p[u]];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (!done[u]) {
-            if (gp[u] != p[u]) L[a[u]] = gp[u];  // path splitting, as find_s
-            a[u] = p[u];
-            p[u] = gp[u];
-            done[u] = p[u] == a[u];
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int ly = ly0 + u;
-        if (ly >= rows) break;
-        const int i = ly * TW + lane;
-        const uint32_t r = a[u];
-        if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
-        const uint32_t c = cnt[i];
-        if (r != (uint32_t)i && c) {
-          atomicAdd(&cnt[r], c);
-          cnt[i] = 0;
-        }
-      }
-    }
-  } else {
+  {
     for (int ly = 0; ly < rows; ly++) {
       const int i = ly * TW + lane;
       const uint32_t r = find_s(L, i);
@@ -587,75 +395,12 @@ __global__ void __launch_bounds__(128) k_ccl_border(Geo g, const uint8_t *__rest
   if (n.UR && (ly == 0 || lx == TW - 1)) unite_g(labf, me, me - Wp + 1);
 }
 
-// flatten: 4 consecutive pixels per thread (uchar4 / uint4 I/O), the four root chases interleaved so four independent
-// loads are in flight per thread.  Component sizes were counted per LOCAL root by k_ccl_tile; a local root that was
-// merged into another tile's root moves its count there (one atomic per merged local root, not per pixel).
-__global__ void __launch_bounds__(256) k_ccl_flatten(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
-                                                     uint32_t *__restrict__ csize, int Wp) {
-  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y;
-  const int fr = blockIdx.z;
-  if (x4 >= g.Wd) return;
-  const size_t fo = (size_t)fr * g.Hd * Wp;
-  uint32_t *L = lab + fo;
-  const uint32_t me0 = (uint32_t)(y * Wp + x4);
-  const uchar4 tv = *reinterpret_cast<const uchar4 *>(thr + fo + me0);
-  uint4 pv = *reinterpret_cast<const uint4 *>(L + me0);
-  uint32_t a[4] = {me0, me0 + 1, me0 + 2, me0 + 3};
-  uint32_t p[4] = {pv.x, pv.y, pv.z, pv.w};
-  const uint8_t v[4] = {tv.x, tv.y, tv.z, tv.w};
-  bool done[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    // AprilRobotics never connects 127 pixels (singletons); padding columns are ignored
-    if (v[k] == 127 || x4 + k >= g.Wd) p[k] = a[k];
-    done[k] = (p[k] == a[k]);
-  }
-  while (!(done[0] && done[1] && done[2] && done[3])) {
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (!done[k]) {
-        a[k] = p[k];
-        p[k] = __ldcg(&L[a[k]]);
-      }
-#pragma unroll
-    for (int k = 0; k < 4; k++) done[k] = (p[k] == a[k]);
-  }
-  *reinterpret_cast<uint4 *>(L + me0) = make_uint4(a[0], a[1], a[2], a[3]);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (v[k] != 127 && x4 + k < g.Wd && a[k] != me0 + k) {
-      const uint32_t c = csize[fo + me0 + k];  // non-zero only for a (former) local root
-      if (c) atomicAdd(&csize[fo + a[k]], c);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_ccl_mark(Geo g, const uint8_t *__restrict__ thr, const uint32_t *__restrict__ lab,
-                                                  const uint32_t *__restrict__ csize, uint8_t *__restrict__ thr2, int Wp) {
-  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y;
-  const int fr = blockIdx.z;
-  if (x4 >= g.Wd) return;
-  const size_t fo = (size_t)fr * g.Hd * Wp;
-  const size_t i = fo + (size_t)y * Wp + x4;
-  const uchar4 tv = *reinterpret_cast<const uchar4 *>(thr + i);
-  const uint4 lv = *reinterpret_cast<const uint4 *>(lab + i);
-  uint8_t v[4] = {tv.x, tv.y, tv.z, tv.w};
-  const uint32_t l[4] = {lv.x, lv.y, lv.z, lv.w};
-  uint32_t c[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) c[k] = (v[k] != 127 && x4 + k < g.Wd) ? csize[fo + l[k]] : 25u;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (c[k] < 25) v[k] = 127;
-  *reinterpret_cast<uchar4 *>(thr2 + i) = make_uchar4(v[0], v[1], v[2], v[3]);
-}
-
-// Two-phase variant of flatten + mark (ccl_flat=1).  After the tile and border kernels every pixel points at a (former) tile
-// root, and only those carry a count.  Phase A: the former tile roots (csize != 0; ~5 % of the pixels) chase to their global
+// Flatten + size gate in two phases.  After the tile and border kernels every pixel points at a (former) tile root, and only
+// those carry a count.  Phase A: the former tile roots (csize != 0; ~5 % of the pixels) chase to their global
 // root, point at it directly and hand over their count.  Phase B: every pixel needs exactly ONE gather, lab[lab[p]], and the
-// size gate (k_ccl_mark) is applied in the same pass: lab and thr are read once instead of twice.
+// size gate (thr2 = thr with pixels of components < 25 px forced to 127: folds the size gates of gradient_clusters into one byte
+// image) is applied in the same pass: lab and thr are read once.  (Measured against a per-pixel chase + separate mark pass:
+// 1.34 -> 1.00 ms per 256 frames, profiles/r03_variants.md.)
 __global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__ lab, uint32_t *__restrict__ csize, int Wp) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
@@ -716,32 +461,19 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
   const int Wp = at_Wp(g);
   dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
-  if (ws.tune.ccl_sweep) {
-    dim3 gs((gt.x + SWEEP_TILES - 1) / SWEEP_TILES, gt.y, gt.z);
-    if (ws.tune.ccl_sweep == 4)
-      k_ccl_tile_sweep_direct<<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
-    else if (ws.use_tma && ws.tune.ccl_sweep == 3)
-      k_ccl_tile_sweep<true, true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-    else if (ws.tune.ccl_sweep == 3)
-      k_ccl_tile_sweep<false, true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-    else if (ws.use_tma && ws.tune.ccl_sweep != 2)
-      k_ccl_tile_sweep<true, false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-    else
-      k_ccl_tile_sweep<false, false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-  } else if (ws.use_tma) {
-    k_ccl_tile<true><<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-  } else {
-    k_ccl_tile<false><<<gt, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-  }
+  dim3 gs((gt.x + SWEEP_TILES - 1) / SWEEP_TILES, gt.y, gt.z);
+  // Tune::ccl_tma: 1 = tiles staged in shared memory by TMA (k_ccl_tile_sweep), 0 = no staging, lanes read their column straight from
+  // global memory (k_ccl_tile_sweep_direct: 6 KB instead of 10.4 KB of shared memory per tile)
+  if (ws.tune.ccl_tma && ws.use_tma)
+    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+  else if (ws.tune.ccl_tma)
+    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+  else
+    k_ccl_tile_sweep_direct<<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
   k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
   dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);
-  if (ws.tune.ccl_flat) {
-    k_ccl_roots<<<gp, 256, 0, s>>>(g, ws.lab, ws.csize, Wp);
-    k_ccl_flatmark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
-    return 4;
-  }
-  k_ccl_flatten<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
-  k_ccl_mark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
+  k_ccl_roots<<<gp, 256, 0, s>>>(g, ws.lab, ws.csize, Wp);
+  k_ccl_flatmark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
   return 4;
 }
 

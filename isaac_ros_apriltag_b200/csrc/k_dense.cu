@@ -442,12 +442,7 @@ int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s) {
   if (g.ts == 4) {
     dim3 blk(32, 8);
     dim3 grd((Wp / 16 + 31) / 32, ((g.Hd + 3) / 4 + 7) / 8, nframes);
-    if (ws.tune.thr_early == 2)
-      k_threshold4<2><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
-    else if (ws.tune.thr_early)
-      k_threshold4<1><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
-    else
-      k_threshold4<0><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
+    k_threshold4<0><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
   } else {
     dim3 blk(256), grd((g.Wd + 255) / 256, g.Hd, nframes);
     k_threshold_generic<<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);

@@ -1,4 +1,4 @@
-// k_quad.cu -- fit_quads (a10).
+// k_quad.cu -- fit_quads (a10), the bit-exact form (B200AT_TUNE=qf_exact=1; the default is the windowed pipeline of k_quad2.cu).
 // Restates AprilRobotics fit_quad / ptsort / compute_lfps / quad_segment_maxima / fit_line
 // (apriltag_quad_thresh.c) with the SAME floating-point types and evaluation order as the
 // CPU oracle, so accept/reject decisions and the float corners are bit-identical (built with -fmad=false).
@@ -604,10 +604,7 @@ static void launch_bin_t(const Workspace &ws, int bin, double scale, int sms, co
 
 template <int THREADS, int NCAP, int MODE, int ITEMS, int CH, int MINB, int CPB = 1>
 static void launch_bin(const Workspace &ws, int bin, double scale, int sms, const ComboTable &ct, cudaStream_t st) {
-  if (ws.tune.qf_sort)
-    launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, true>(ws, bin, scale, sms, ct, st);
-  else
-    launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, false>(ws, bin, scale, sms, ct, st);
+  launch_bin_t<THREADS, NCAP, MODE, ITEMS, CH, MINB, CPB, false>(ws, bin, scale, sms, ct, st);
 }
 
 void launch_bin_clusters(const Workspace &ws, int sms, cudaStream_t s) {
@@ -627,39 +624,17 @@ int launch_quadfit(const Workspace &ws, int nframes, cudaStream_t s) {
   // the bins are independent: fork onto side streams; large clusters (the long poles) are issued first
   cudaEventRecord(ws.ev_fork, s);
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
-  // tuning knobs (Tune, detector.h): qf_scale scales the persistent grid of every bin; qf_keys23 runs the 512 / 1024-point
-  // bins with the prefix moments in the L2-resident scratch (16 B instead of 64 B of shared memory per point)
-  const double qscale = ws.tune.qf_scale;
-  const bool keys23 = ws.tune.qf_keys23 != 0;
+  // (configuration measured best in round 1, profiles/r02_sweep_*.md: 512 / 1024-point bins with the prefix moments in the
+  // L2-resident scratch, one-warp bins with several clusters per CTA in phase lockstep)
+  const double qscale = 1.0;
   launch_bin<256, 0, QF_GLOBAL, 16, 1, 2>(ws, 7, qscale, sms, ct, s);               // n > 8192
   launch_bin<512, 8192, QF_KEYS, 16, 480, 1>(ws, 6, qscale, sms, ct, ws.aux[0]);    // n <= 8192
   launch_bin<256, 4096, QF_KEYS, 16, 224, 3>(ws, 5, qscale, sms, ct, ws.aux[1]);    // n <= 4096
   launch_bin<256, 2048, QF_KEYS, 8, 160, 4>(ws, 4, qscale, sms, ct, ws.aux[2]);     // n <= 2048
-  if (!keys23) {
-    launch_bin<128, 1024, QF_ALL, 8, 1, 3>(ws, 3, qscale, sms, ct, ws.aux[3]);      // n <= 1024
-    launch_bin<64, 512, QF_ALL, 8, 1, 6>(ws, 2, qscale, sms, ct, ws.aux[4]);        // n <= 512
-  } else {
-    launch_bin<128, 1024, QF_KEYS, 8, 64, 8>(ws, 3, qscale, sms, ct, ws.aux[3]);
-    launch_bin<64, 512, QF_KEYS, 8, 32, 16>(ws, 2, qscale, sms, ct, ws.aux[4]);
-  }
-  if (ws.tune.qf_mc == 2) {
-    // (not measured yet) the smallest bin with 7 clusters per CTA and the register budget of 3 CTAs per SM: 21 warps instead of 16
-    launch_bin<32, 256, QF_ALL, 8, 1, 2, 6>(ws, 1, qscale, sms, ct, ws.aux[5]);
-    launch_bin<32, 128, QF_ALL, 4, 1, 3, 7>(ws, 0, qscale, sms, ct, ws.aux[6]);
-  } else if (ws.tune.qf_mc == 3) {
-    // (not measured yet) occupancy instead of lockstep: the 256 bin as two-warp clusters with the moments in the L2 scratch
-    // (4 KB instead of 16 KB of shared memory, 64 registers: 32 warps per SM instead of 12), the 128 bin one cluster per
-    // CTA with the register budget of 28 CTAs per SM (72 registers without spills; shared memory then allows 23 warps)
-    launch_bin<64, 256, QF_KEYS, 4, 20, 16>(ws, 1, qscale, sms, ct, ws.aux[5]);
-    launch_bin<32, 128, QF_ALL, 4, 1, 28>(ws, 0, qscale, sms, ct, ws.aux[6]);
-  } else if (ws.tune.qf_mc) {
-    // one-warp clusters, several per CTA in phase lockstep (MINB = CTAs per SM the register budget is sized for)
-    launch_bin<32, 256, QF_ALL, 8, 1, 2, 6>(ws, 1, qscale, sms, ct, ws.aux[5]);      // n <= 256: 6 clusters per CTA
-    launch_bin<32, 128, QF_ALL, 4, 1, 2, 8>(ws, 0, qscale, sms, ct, ws.aux[6]);      // n <= 128: 8 clusters per CTA
-  } else {
-    launch_bin<32, 256, QF_ALL, 8, 1, 12>(ws, 1, qscale, sms, ct, ws.aux[5]);        // n <= 256
-    launch_bin<32, 128, QF_ALL, 4, 1, 18>(ws, 0, qscale, sms, ct, ws.aux[6]);        // n <= 128
-  }
+  launch_bin<128, 1024, QF_KEYS, 8, 64, 8>(ws, 3, qscale, sms, ct, ws.aux[3]);      // n <= 1024
+  launch_bin<64, 512, QF_KEYS, 8, 32, 16>(ws, 2, qscale, sms, ct, ws.aux[4]);       // n <= 512
+  launch_bin<32, 256, QF_ALL, 8, 1, 2, 6>(ws, 1, qscale, sms, ct, ws.aux[5]);       // n <= 256: 6 clusters per CTA
+  launch_bin<32, 128, QF_ALL, 4, 1, 2, 8>(ws, 0, qscale, sms, ct, ws.aux[6]);       // n <= 128: 8 clusters per CTA
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);

@@ -102,10 +102,13 @@ __device__ __forceinline__ void qf_register_work(uint32_t ci, int sz, bool rever
   }
 }
 
-// Clusters of at most THREADS * E points.  Every warp sorts 32 * E keys in registers (bitonic network on double-ordered keys);
-// one-warp clusters (THREADS == 32) never touch shared memory, larger ones merge the warps' runs there (merge path).
+// Clusters of at most THREADS * E points.
+// BIT: the warp sorts its 32 * E keys in registers (bitonic network, warp_bitonic_sort) -- one-warp clusters then never touch
+// shared memory.  Measured (profiles/r03_quadfit_sort.md): the network wins only at E = 4 (n <= 128); from E = 8 on its
+// O(log^2) stages cost more instructions than the shared-memory merge sort (ITEMS keys sorted per thread, then merge-path
+// passes), which is what the larger bins use.
 // WPC > 1 (one-warp clusters): WPC independent cluster workers per CTA, one warp each, no block-wide barrier anywhere.
-template <int THREADS, int E, int ITEMS, int MINB, int WPC>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC, bool BIT>
 __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
               const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, const uint8_t *__restrict__ dec,
@@ -113,11 +116,11 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
               uint32_t *__restrict__ counters, int Wp) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
-  extern __shared__ unsigned long long dsm_sort[];  // [2 * NCAP] when NW > 1
-  unsigned long long *skeys = dsm_sort, *stmp = dsm_sort + NCAP;
+  extern __shared__ unsigned long long dsm_sort[];  // [WPC][2 * NCAP] unless the sort stays in registers
+  const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
+  unsigned long long *skeys = dsm_sort + (size_t)grp * 2 * NCAP, *stmp = skeys + NCAP;
   __shared__ BBoxRed s_red[NW];
   __shared__ int s_cluster_a[WPC];
-  const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
   const int tid = WPC > 1 ? (int)(threadIdx.x % THREADS) : (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
   for (;;) {
@@ -152,38 +155,38 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
       if (tid == 0) qinfo[ci] = 0u;
       continue;
     }
-    double v[E];
+    if (BIT && NW == 1) {
+      unsigned long long v[E];
 #pragma unroll
-    for (int k = 0; k < E; k++) v[k] = (wbase + k * 32 + lane < sz) ? key60(pr[k], cx, cy) : key60_inf();
-    warp_bitonic_sort<E>(v, lane);
-    // element wbase + lane * E + k of the sorted sequence (of the warp's run) is now v[k]
-    if (NW == 1) {
-      // sorted points out, straight from the registers; the slope half of a key is dead, it now carries the squared gradient
-      // magnitude of the decimated image at the point (compute_lfps' weight is sqrt of it, + 1): E gathers in flight per lane
-      uint32_t yx[E];
+      for (int k = 0; k < E; k++) v[k] = (k * 32 + lane < sz) ? slope_key(pr[k], cx, cy) : ~0ull;
+      warp_bitonic_sort<E>(v, lane);
+      // element lane * E + k of the sorted sequence is now v[k]: sorted points out, straight from the registers; the slope half of
+      // a key is dead, it now carries the squared gradient magnitude of the decimated image at the point (compute_lfps' weight is
+      // sqrt of it, + 1): E gathers in flight per lane
       int g2[E];
 #pragma unroll
-      for (int k = 0; k < E; k++) yx[k] = key60_yx(v[k]);
-#pragma unroll
-      for (int k = 0; k < E; k++) g2[k] = (lane * E + k < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, (unsigned long long)yx[k]) : 0;
+      for (int k = 0; k < E; k++) g2[k] = (lane * E + k < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, v[k]) : 0;
 #pragma unroll
       for (int k = 0; k < E; k++)
-        if (lane * E + k < sz) keys_g[lane * E + k] = (unsigned long long)yx[k] | ((unsigned long long)(uint32_t)g2[k] << 32);
+        if (lane * E + k < sz) keys_g[lane * E + k] = (v[k] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[k] << 32);
     } else {
 #pragma unroll
-      for (int k = 0; k < E; k++) skeys[wbase + lane * E + k] = (unsigned long long)__double_as_longlong(v[k]);
-      __syncthreads();
-      merge_runs<THREADS, ITEMS>(skeys, stmp, sz, tid, 32 * E);
+      for (int k = 0; k < E; k++) {
+        const int i = wbase + k * 32 + lane;
+        if (i < sz) skeys[i] = slope_key(pr[k], cx, cy);
+      }
+      cta_sync<THREADS>();
+      sort_keys<THREADS, ITEMS, false>(skeys, stmp, sz, tid);
       for (int i = tid; i < sz; i += 4 * THREADS) {
-        uint32_t yx[4];
+        unsigned long long k[4];
         int g2[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) yx[u] = (i + u * THREADS < sz) ? key60_yx(__longlong_as_double((long long)skeys[i + u * THREADS])) : 0u;
+        for (int u = 0; u < 4; u++) k[u] = (i + u * THREADS < sz) ? skeys[i + u * THREADS] : 0ull;
 #pragma unroll
-        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, (unsigned long long)yx[u]) : 0;
+        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, k[u]) : 0;
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (unsigned long long)yx[u] | ((unsigned long long)(uint32_t)g2[u] << 32);
+          if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (k[u] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[u] << 32);
       }
     }
     if (tid == 0) qf_register_work(ci, sz, reversed, qinfo, qwbase, work, work_cap, counters);
@@ -755,11 +758,11 @@ static int device_index() {
   return dev >= 0 && dev < 64 ? dev : 0;
 }
 
-template <int THREADS, int E, int ITEMS, int MINB, int WPC>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC, bool BIT>
 static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t st) {
   const Geo &g = ws.g;
-  constexpr size_t smem = THREADS > 32 ? (size_t)2 * THREADS * E * 8 : 0;
-  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC>;
+  constexpr size_t smem = (BIT && THREADS == 32) ? 0 : (size_t)2 * THREADS * E * 8 * WPC;
+  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC, BIT>;
   static int ctas_per_sm[64] = {};
   const int dev = device_index();
   if (!ctas_per_sm[dev]) {
@@ -787,13 +790,13 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
   k_qf_sort_global<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 7, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo, ws.qwbase, ws.qwork,
                                           ws.qwork_cap, ws.counters, at_Wp(g));                 // n > 8192 (4K-class frames)
-  launch_sort_bin<512, 16, 8, 1, 1>(ws, 6, sms, ws.aux[0]);   // n <= 8192: 16 warps x 512 keys, 4 merge passes
-  launch_sort_bin<256, 16, 8, 2, 1>(ws, 5, sms, ws.aux[1]);   // n <= 4096:  8 warps x 512 keys, 3 merge passes
-  launch_sort_bin<256, 8, 8, 3, 1>(ws, 4, sms, ws.aux[2]);    // n <= 2048:  8 warps x 256 keys, 3 merge passes
-  launch_sort_bin<128, 8, 8, 6, 1>(ws, 3, sms, ws.aux[3]);    // n <= 1024:  4 warps x 256 keys, 2 merge passes
-  launch_sort_bin<32, 16, 8, 2, 8>(ws, 2, sms, ws.aux[4]);    // n <= 512: one warp per cluster, registers only, 8 workers per CTA
-  launch_sort_bin<32, 8, 8, 3, 8>(ws, 1, sms, ws.aux[5]);     // n <= 256
-  launch_sort_bin<32, 4, 8, 4, 8>(ws, 0, sms, ws.aux[6]);     // n <= 128
+  launch_sort_bin<512, 16, 16, 1, 1, false>(ws, 6, sms, ws.aux[0]);  // n <= 8192
+  launch_sort_bin<256, 16, 16, 3, 1, false>(ws, 5, sms, ws.aux[1]);  // n <= 4096
+  launch_sort_bin<256, 8, 8, 4, 1, false>(ws, 4, sms, ws.aux[2]);    // n <= 2048
+  launch_sort_bin<128, 8, 8, 8, 1, false>(ws, 3, sms, ws.aux[3]);    // n <= 1024
+  launch_sort_bin<64, 8, 8, 16, 1, false>(ws, 2, sms, ws.aux[4]);    // n <= 512
+  launch_sort_bin<32, 8, 8, 4, 8, false>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
+  launch_sort_bin<32, 4, 4, 4, 8, true>(ws, 0, sms, ws.aux[6]);      // n <= 128: registers only
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);

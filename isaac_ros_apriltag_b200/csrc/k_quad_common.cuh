@@ -289,25 +289,22 @@ __device__ __forceinline__ unsigned long long slope_key(uint32_t p, float cx, fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Register bitonic sort of 32 * E keys per warp (k_quad2.cu).  A key is slope (32 bits, float_orderable) | y (14) | x (14) in
-// the low 60 bits of a 64-bit word: read as an IEEE double it is positive and finite, and for positive doubles the floating
-// point order IS the order of the bit patterns -- one DMNMX (fmin / fmax) replaces the compare + four selects a 64-bit integer
-// compare-exchange costs.  Element i of the warp's chunk lives in lane i / E, register i % E.  Ascending-only network: the
+// Register bitonic sort of 32 * E 64-bit keys per warp (k_quad2.cu).  Element i of the warp's chunk lives in lane i / E, register
+// i % E, so the low log2(E) index bits are compare-exchanges between registers (one 64-bit compare = ISETP + ISETP.EX, four
+// SELs per pair) and the five lane bits are shuffles (two SHFLs, the compare, two SELs per key).  Ascending-only network: the
 // first step of every merge level pairs i with i ^ (2^k - 1), the following ones i with i ^ j.
+// (Measured dead end: keys packed as positive doubles with fmin / fmax as the compare-exchange -- sm_100a has no DMNMX, the
+// pair compiles to DSETP + selects + NaN fix-ups and the network executed 1.7x the instructions of the merge sort it replaced.)
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double key60(uint32_t p, float cx, float cy) {
-  const unsigned long long k = slope_key(p, cx, cy);  // slope << 32 | y << 16 | x
-  return __longlong_as_double((long long)(((k >> 32) << 28) | (((k >> 16) & 0x3fffull) << 14) | (k & 0x3fffull)));
+__device__ __forceinline__ void key_ce(unsigned long long &a, unsigned long long &b) {  // a <= b afterwards
+  const bool sw = b < a;
+  const unsigned long long t = a;
+  a = sw ? b : a;
+  b = sw ? t : b;
 }
-// y << 16 | x of a key60 (the layout of the sorted-point stream)
-__device__ __forceinline__ uint32_t key60_yx(double d) {
-  const unsigned long long k = (unsigned long long)__double_as_longlong(d);
-  return (uint32_t)(((k >> 14) & 0x3fffull) << 16) | (uint32_t)(k & 0x3fffull);
-}
-__device__ __forceinline__ double key60_inf() { return __longlong_as_double(0x7fefffffffffffffll); }  // above every key60
 
 template <int E>
-__device__ __forceinline__ void warp_bitonic_sort(double (&v)[E], int lane) {
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&v)[E], int lane) {
   constexpr int N = 32 * E;
 #pragma unroll
   for (int k2 = 2; k2 <= N; k2 <<= 1) {
@@ -316,40 +313,35 @@ __device__ __forceinline__ void warp_bitonic_sort(double (&v)[E], int lane) {
 #pragma unroll
       for (int r = 0; r < E; r++) {
         const int q = r ^ (k2 - 1);
-        if (q > r) {
-          const double lo = fmin(v[r], v[q]), hi = fmax(v[r], v[q]);
-          v[r] = lo;
-          v[q] = hi;
-        }
+        if (q > r) key_ce(v[r], v[q]);
       }
     } else {
       const int lm = k2 / E - 1;                        // lane bits flipped
       const bool lower = (lane & (k2 / E / 2)) == 0;    // the highest flipped bit of my index is 0: I keep the minimum
-      double p[E];
+      // my register r pairs with the partner's register E - 1 - r: walk the registers from both ends so that no copy of the old
+      // values is needed
 #pragma unroll
-      for (int r = 0; r < E; r++) p[r] = __shfl_xor_sync(0xffffffffu, v[E - 1 - r], lm);
-#pragma unroll
-      for (int r = 0; r < E; r++) v[r] = lower ? fmin(v[r], p[r]) : fmax(v[r], p[r]);
+      for (int r = 0; r < E / 2; r++) {
+        const unsigned long long pa = __shfl_xor_sync(0xffffffffu, v[E - 1 - r], lm);  // partner of v[r]
+        const unsigned long long pb = __shfl_xor_sync(0xffffffffu, v[r], lm);          // partner of v[E - 1 - r]
+        v[r] = ((pa < v[r]) == lower) ? pa : v[r];
+        v[E - 1 - r] = ((pb < v[E - 1 - r]) == lower) ? pb : v[E - 1 - r];
+      }
     }
     // following steps: partner i ^ j
 #pragma unroll
     for (int j = k2 >> 2; j >= 1; j >>= 1) {
       if (j < E) {
 #pragma unroll
-        for (int r = 0; r < E; r++) {
-          if ((r & j) == 0) {
-            const double lo = fmin(v[r], v[r | j]), hi = fmax(v[r], v[r | j]);
-            v[r] = lo;
-            v[r | j] = hi;
-          }
-        }
+        for (int r = 0; r < E; r++)
+          if ((r & j) == 0) key_ce(v[r], v[r | j]);
       } else {
         const int lm = j / E;
         const bool lower = (lane & lm) == 0;
 #pragma unroll
         for (int r = 0; r < E; r++) {
-          const double p = __shfl_xor_sync(0xffffffffu, v[r], lm);
-          v[r] = lower ? fmin(v[r], p) : fmax(v[r], p);
+          const unsigned long long p = __shfl_xor_sync(0xffffffffu, v[r], lm);
+          v[r] = ((p < v[r]) == lower) ? p : v[r];
         }
       }
     }
@@ -408,7 +400,7 @@ __device__ __forceinline__ void merge_runs(unsigned long long *a, unsigned long 
 // border, where the reference uses weight 1 = sqrt(0) + 1
 __device__ __forceinline__ int grad2_at(const uint8_t *__restrict__ im, int Wp, int Wd, int Hd, unsigned long long k) {
   const int px = (int)(k & 0xffff), py = (int)((k >> 16) & 0xffff);
-  const int ix = (int)(px * .5 + 0.5), iy = (int)(py * .5 + 0.5);
+  const int ix = (px + 1) >> 1, iy = (py + 1) >> 1;  // == (int)(px * .5 + 0.5) for the non-negative half-pixel coordinates
   int g2 = 0;
   if (ix > 0 && ix + 1 < Wd && iy > 0 && iy + 1 < Hd) {
     const uint8_t *c = im + (size_t)iy * Wp + ix;

@@ -120,29 +120,30 @@ Quaternion RotationToQuaternion(const float *m, bool col_major, bool normalize) 
 }
 
 // ---- apriltag_node.cpp:93-130 ----
-struct AprilTagNode::AprilTagImpl {
+struct AprilTagNodeCore::AprilTagImpl {
   virtual ~AprilTagImpl() = default;
+  cudaStream_t stream_ = nullptr;  // created in Initialize, destroyed in the strategy's destructor iff initialised (:460, :552-558)
   bool IsInitialized() const { return initialized_; }
   virtual std::unordered_set<int> SupportedTagFamilies() const = 0;
-  virtual void Initialize(const AprilTagNode &node, const ImageView &, const CameraInfo &) {
+  virtual void Initialize(const AprilTagNodeCore &node, const ImageView &, const CameraInfo &) {
     initialized_ = true;
     tag_family_str_ = node.params_.tag_family;
     tag_family_ = ToFamily(tag_family_str_);
   }
-  virtual void OnCameraFrame(AprilTagNode &node, const ImageView &image, const CameraInfo &camera_info) = 0;
+  virtual void OnCameraFrame(AprilTagNodeCore &node, const ImageView &image, const CameraInfo &camera_info) = 0;
   bool initialized_{false};
   FamilyId tag_family_{FAM_INVALID};
   std::string tag_family_str_{};
 };
 
 // ---- apriltag_node.cpp:389-559: the default backend, behind the cuAprilTags-shaped entry points ----
-struct AprilTagNode::CUAprilTagImpl : AprilTagNode::AprilTagImpl {
+struct AprilTagNodeCore::CUAprilTagImpl : AprilTagNodeCore::AprilTagImpl {
   cuAprilTagsHandle detector_ = nullptr;
   cuAprilTagsCameraIntrinsics_t cam_intrinsics_{};
 
   std::unordered_set<int> SupportedTagFamilies() const override { return {FAM_36H11}; }  // :429-432
 
-  void Initialize(const AprilTagNode &node, const ImageView &image, const CameraInfo &camera_info) override {
+  void Initialize(const AprilTagNodeCore &node, const ImageView &image, const CameraInfo &camera_info) override {
     AprilTagImpl::Initialize(node, image, camera_info);
     const double *k = camera_info.k.data();  // :442-447
     cam_intrinsics_ = {static_cast<float>(k[0]), static_cast<float>(k[4]), static_cast<float>(k[2]), static_cast<float>(k[5])};
@@ -152,9 +153,10 @@ struct AprilTagNode::CUAprilTagImpl : AprilTagNode::AprilTagImpl {
       initialized_ = false;
       throw std::runtime_error("Failed to create cuAprilTags detector (error code " + std::to_string(error) + ")");
     }
+    cudaStreamCreate(&stream_);  // :460 "Create stream for detection"
   }
 
-  void OnCameraFrame(AprilTagNode &node, const ImageView &image, const CameraInfo &camera_info) override {
+  void OnCameraFrame(AprilTagNodeCore &node, const ImageView &image, const CameraInfo &camera_info) override {
     if (image.encoding != "rgb8" && image.encoding != "bgr8") {  // :469-476
       node.Log(1, "Unsupported image encoding: " + image.encoding + " (only 'rgb8' or 'bgr8' supported)");
       throw std::runtime_error("cuAprilTags detector only supports 'rgb8' or 'bgr8' image input");
@@ -167,7 +169,7 @@ struct AprilTagNode::CUAprilTagImpl : AprilTagNode::AprilTagImpl {
     input_image.pitch = image.step;
     uint32_t num_detections = 0;
     std::vector<cuAprilTagsID_t> tags(node.params_.max_tags);  // :490
-    const int error = (int)cuAprilTagsDetect(detector_, &input_image, tags.data(), &num_detections, node.params_.max_tags, nullptr);
+    const int error = (int)cuAprilTagsDetect(detector_, &input_image, tags.data(), &num_detections, node.params_.max_tags, stream_);  // :491-493
     if (error != 0) {  // :494-497 log and drop the frame
       node.Log(1, "Failed to run AprilTags detector (error code " + std::to_string(error) + ")");
       return;
@@ -210,14 +212,15 @@ struct AprilTagNode::CUAprilTagImpl : AprilTagNode::AprilTagImpl {
     node.Publish(msg_detections, tfs);  // :548-549
   }
 
-  ~CUAprilTagImpl() override {
-    if (detector_) cuAprilTagsDestroy(detector_);  // :552-558
+  ~CUAprilTagImpl() override {  // :552-558
+    if (stream_) cudaStreamDestroy(stream_);
+    if (detector_) cuAprilTagsDestroy(detector_);
   }
 };
 
 // ---- apriltag_node.cpp:133-387: the "any other backends" strategy (VPI in the reference): all families with a
 // code table, all five encodings, centre from the library, normalised quaternion ----
-struct AprilTagNode::VPIAprilTagImpl : AprilTagNode::AprilTagImpl {
+struct AprilTagNodeCore::VPIAprilTagImpl : AprilTagNodeCore::AprilTagImpl {
   cuAprilTagsHandle detector_ = nullptr;
 
   std::unordered_set<int> SupportedTagFamilies() const override {  // :182-191
@@ -225,7 +228,7 @@ struct AprilTagNode::VPIAprilTagImpl : AprilTagNode::AprilTagImpl {
             FAM_STANDARD52H13};
   }
 
-  void Initialize(const AprilTagNode &node, const ImageView &image, const CameraInfo &camera_info) override {
+  void Initialize(const AprilTagNodeCore &node, const ImageView &image, const CameraInfo &camera_info) override {
     AprilTagImpl::Initialize(node, image, camera_info);
     const int fam = ToB200Family(tag_family_);
     if (fam < 0) {
@@ -251,17 +254,18 @@ struct AprilTagNode::VPIAprilTagImpl : AprilTagNode::AprilTagImpl {
       initialized_ = false;
       throw std::runtime_error("Failed to create AprilTag detector (error code " + std::to_string(error) + ")");
     }
+    cudaStreamCreate(&stream_);  // :211 (the VPI strategy's cuda_stream_)
     node.Log(0, "AprilTag detector: " + std::to_string(camera_info.width) + "x" + std::to_string(camera_info.height) + " " + tag_family_str_);
   }
 
-  void OnCameraFrame(AprilTagNode &node, const ImageView &image, const CameraInfo &camera_info) override {
+  void OnCameraFrame(AprilTagNodeCore &node, const ImageView &image, const CameraInfo &camera_info) override {
     const int enc = ToB200Encoding(image.encoding);
     if (enc < 0) throw std::runtime_error("Unsupported image encoding: " + image.encoding);
     b200AprilTagsSetInputEncoding(detector_, enc);
     b200AprilTagsFrame_t fr{image.dev_ptr, image.step};
     std::vector<b200AprilTagsDetection_t> dets(node.params_.max_tags);
     uint32_t n = 0;
-    const int error = b200AprilTagsDetectBatch(detector_, &fr, 1, dets.data(), nullptr, &n, nullptr);
+    const int error = b200AprilTagsDetectBatch(detector_, &fr, 1, dets.data(), nullptr, &n, stream_);
     if (error != 0 && error != B200AT_ERR_OVERFLOW) {
       node.Log(1, "Failed to run AprilTags detector (error code " + std::to_string(error) + ")");
       return;
@@ -299,13 +303,14 @@ struct AprilTagNode::VPIAprilTagImpl : AprilTagNode::AprilTagImpl {
   }
 
   ~VPIAprilTagImpl() override {
+    if (stream_) cudaStreamDestroy(stream_);
     if (detector_) cuAprilTagsDestroy(detector_);
   }
 };
 
 // ---- apriltag_node.cpp:562-611 ----
-AprilTagNode::AprilTagNode(const NodeParams &params, DetectionsSink det, TfSink tf, LogSink log)
-    : params_(params), backends_(ParseBackends(params.backends)), det_sink_(std::move(det)), tf_sink_(std::move(tf)),
+AprilTagNodeCore::AprilTagNodeCore(const NodeParams &params, DetectionsSink det, TfSink tf, LogSink log)
+    : params_(params), backends_(params.backends_mask ? params.backends_mask : ParseBackends(params.backends)), det_sink_(std::move(det)), tf_sink_(std::move(tf)),
       log_sink_(std::move(log)) {
   if (backends_ == BACKEND_CUDA) {  // :576-582
     Log(0, "Using cuAprilTag implementation.");
@@ -325,23 +330,25 @@ AprilTagNode::AprilTagNode(const NodeParams &params, DetectionsSink det, TfSink 
   }
 }
 
-AprilTagNode::~AprilTagNode() = default;
+AprilTagNodeCore::~AprilTagNodeCore() = default;
 
-bool AprilTagNode::UsingCuAprilTagImpl() const { return backends_ == BACKEND_CUDA; }
+bool AprilTagNodeCore::UsingCuAprilTagImpl() const { return backends_ == BACKEND_CUDA; }
 
-void AprilTagNode::CameraImageCallback(const ImageView &image, const CameraInfo &camera_info) {  // :613-623
+cudaStream_t AprilTagNodeCore::cuda_stream() const { return impl_ ? impl_->stream_ : nullptr; }
+
+void AprilTagNodeCore::CameraImageCallback(const ImageView &image, const CameraInfo &camera_info) {  // :613-623
   if (!impl_->IsInitialized()) impl_->Initialize(*this, image, camera_info);
   impl_->OnCameraFrame(*this, image, camera_info);
 }
 
-void AprilTagNode::Publish(const AprilTagDetectionArray &d, const std::vector<TransformStamped> &t) {
+void AprilTagNodeCore::Publish(const AprilTagDetectionArray &d, const std::vector<TransformStamped> &t) {
   last_detections_ = d;
   last_tfs_ = t;
   if (det_sink_) det_sink_(d);
   if (tf_sink_) tf_sink_(t);
 }
 
-void AprilTagNode::Log(int level, const std::string &m) const {
+void AprilTagNodeCore::Log(int level, const std::string &m) const {
   if (log_sink_) log_sink_(level, m);
 }
 

@@ -1,4 +1,4 @@
-// apriltag_node_core.hpp -- ROS-free mirror of nvidia::isaac_ros::apriltag::AprilTagNode
+// apriltag_node_core.hpp -- AprilTagNodeCore: ROS-free mirror of nvidia::isaac_ros::apriltag::AprilTagNode
 // (/root/reference/isaac_ros_apriltag/include/isaac_ros_apriltag/apriltag_node.hpp:48-91,
 //  /root/reference/isaac_ros_apriltag/src/apriltag_node.cpp:93-130, 389-559, 562-623).
 //
@@ -17,6 +17,8 @@
 #include <unordered_set>
 #include <vector>
 
+// compiled against the CUDA headers like the reference node (float2 / uchar3 / cudaStream_t are the real types)
+#define B200_APRILTAGS_USE_CUDA_HEADERS 1
 #include "../../include/b200_apriltags.h"
 
 namespace nvidia {
@@ -83,29 +85,33 @@ struct NodeParams {
   double size = 0.22;                   // :565
   uint32_t tile_size = 4;               // :566
   std::string tag_family = "tag36h11";  // :567
-  std::string backends = "CUDA";        // :568
+  std::string backends = "CUDA";        // :568 (the string DeclareVPIBackendParameter parses) ...
+  uint32_t backends_mask = 0;           // ... or, when non-zero, the VPIBackend flags it returned (the rclcpp wrapper passes these)
 };
 
 // 3x3 rotation -> quaternion exactly as Eigen::Quaternion<float>(Matrix3f) does (trace method with the
 // largest-diagonal fallback); col_major selects the cuAprilTags layout (apriltag_node.cpp:409-427).
 Quaternion RotationToQuaternion(const float *m, bool col_major, bool normalize);
 
-class AprilTagNode {
+class AprilTagNodeCore {
  public:
   using DetectionsSink = std::function<void(const AprilTagDetectionArray &)>;
   using TfSink = std::function<void(const std::vector<TransformStamped> &)>;
   using LogSink = std::function<void(int level, const std::string &)>;  // 0 info, 1 error, 2 fatal
 
-  explicit AprilTagNode(const NodeParams &params, DetectionsSink det = nullptr, TfSink tf = nullptr, LogSink log = nullptr);
-  ~AprilTagNode();
-  AprilTagNode(const AprilTagNode &) = delete;
-  AprilTagNode &operator=(const AprilTagNode &) = delete;
+  explicit AprilTagNodeCore(const NodeParams &params, DetectionsSink det = nullptr, TfSink tf = nullptr, LogSink log = nullptr);
+  ~AprilTagNodeCore();
+  AprilTagNodeCore(const AprilTagNodeCore &) = delete;
+  AprilTagNodeCore &operator=(const AprilTagNodeCore &) = delete;
 
   // apriltag_node.cpp:613-623: lazy Initialize on the first frame, then OnCameraFrame.
   void CameraImageCallback(const ImageView &image, const CameraInfo &camera_info);
 
   const NodeParams &params() const { return params_; }
   bool UsingCuAprilTagImpl() const;
+  // The strategy's own CUDA stream (apriltag_node.cpp:460, :211): created at the first frame like the reference's stream_, nullptr
+  // before.  The rclcpp wrapper hands it to NitrosImage::get_read_handle so the image is ordered against the detector's work.
+  cudaStream_t cuda_stream() const;
   // last published messages (also delivered to the sinks)
   const AprilTagDetectionArray &last_detections() const { return last_detections_; }
   const std::vector<TransformStamped> &last_transforms() const { return last_tfs_; }

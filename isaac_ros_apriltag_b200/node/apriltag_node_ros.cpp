@@ -12,6 +12,7 @@
 #include "isaac_ros_apriltag_interfaces/msg/april_tag_detection_array.hpp"
 #include "isaac_ros_nitros/types/nitros_type_message_filter_traits.hpp"
 #include "isaac_ros_nitros_image_type/nitros_image.hpp"
+#include "isaac_ros_vpi_utils/vpi_utilities.hpp"
 #include "message_filters/subscriber.h"
 #include "message_filters/sync_policies/exact_time.h"
 #include "message_filters/synchronizer.h"
@@ -25,9 +26,9 @@ namespace apriltag {
 
 namespace core = ::nvidia::isaac_ros::apriltag;
 
-class AprilTagRosNode : public rclcpp::Node {
+class AprilTagNode : public rclcpp::Node {
  public:
-  explicit AprilTagRosNode(const rclcpp::NodeOptions &options = rclcpp::NodeOptions())
+  explicit AprilTagNode(const rclcpp::NodeOptions &options = rclcpp::NodeOptions())
       : rclcpp::Node("apriltag_node", options),
         camera_image_sync_{ExactPolicy{3}, image_sub_, camera_info_sub_},
         detections_pub_{create_publisher<isaac_ros_apriltag_interfaces::msg::AprilTagDetectionArray>("tag_detections", rclcpp::QoS(1))} {
@@ -36,8 +37,9 @@ class AprilTagRosNode : public rclcpp::Node {
     p.size = declare_parameter<double>("size", 0.22);
     p.tile_size = declare_parameter<uint16_t>("tile_size", 4);
     p.tag_family = declare_parameter<std::string>("tag_family", "tag36h11");
-    p.backends = declare_parameter<std::string>("backends", "CUDA");
-    core_ = std::make_unique<core::AprilTagNode>(
+    // apriltag_node.cpp:568: the `backends` parameter is declared and parsed by isaac_ros_vpi_utils, which returns VPIBackend flags
+    p.backends_mask = static_cast<uint32_t>(nvidia::isaac_ros::vpi_utils::DeclareVPIBackendParameter(this, VPI_BACKEND_CUDA));
+    core_ = std::make_unique<core::AprilTagNodeCore>(
         p, [this](const core::AprilTagDetectionArray &a) { PublishDetections(a); },
         [this](const std::vector<core::TransformStamped> &t) { PublishTf(t); },
         [this](int lvl, const std::string &m) {
@@ -46,7 +48,7 @@ class AprilTagRosNode : public rclcpp::Node {
           else RCLCPP_FATAL(get_logger(), "%s", m.c_str());
         });
     tf_broadcaster_ = std::make_unique<tf2_ros::TransformBroadcaster>(this);
-    camera_image_sync_.registerCallback(std::bind(&AprilTagRosNode::Callback, this, std::placeholders::_1, std::placeholders::_2));
+    camera_image_sync_.registerCallback(std::bind(&AprilTagNode::Callback, this, std::placeholders::_1, std::placeholders::_2));
     image_sub_.subscribe(this, "image");
     camera_info_sub_.subscribe(this, "camera_info");
   }
@@ -54,7 +56,9 @@ class AprilTagRosNode : public rclcpp::Node {
  private:
   void Callback(const nvidia::isaac_ros::nitros::NitrosImage::ConstSharedPtr &img,
                 const sensor_msgs::msg::CameraInfo::ConstSharedPtr &ci) {
-    auto read_handle = img->get_read_handle(nullptr);  // kept alive across the call (apriltag_node.cpp:479-480)
+    // kept alive across the call, on the strategy's own stream (apriltag_node.cpp:479-480; nullptr only before the first frame,
+    // when the strategy has not created its stream yet)
+    auto read_handle = img->get_read_handle(core_->cuda_stream());
     core::ImageView v{img->encoding, img->width, img->height, img->step, read_handle.get_ptr()};
     core::CameraInfo c;
     c.header.stamp_sec = ci->header.stamp.sec;
@@ -113,7 +117,7 @@ class AprilTagRosNode : public rclcpp::Node {
   message_filters::Synchronizer<ExactPolicy> camera_image_sync_;
   rclcpp::Publisher<isaac_ros_apriltag_interfaces::msg::AprilTagDetectionArray>::SharedPtr detections_pub_;
   std::unique_ptr<tf2_ros::TransformBroadcaster> tf_broadcaster_;
-  std::unique_ptr<core::AprilTagNode> core_;
+  std::unique_ptr<core::AprilTagNodeCore> core_;
   std_msgs::msg::Header header_;
 };
 
@@ -122,5 +126,7 @@ class AprilTagRosNode : public rclcpp::Node {
 }  // namespace nvidia
 
 #include "rclcpp_components/register_node_macro.hpp"
-RCLCPP_COMPONENTS_REGISTER_NODE(nvidia::isaac_ros::apriltag::AprilTagRosNode)
+// the plugin name every launch file of the reference asks for (launch/isaac_ros_apriltag.launch.py:26, CMakeLists.txt:46-48,
+// apriltag_node.cpp:633)
+RCLCPP_COMPONENTS_REGISTER_NODE(nvidia::isaac_ros::apriltag::AprilTagNode)
 #endif  // B200_APRILTAG_WITH_ROS

@@ -1,4 +1,4 @@
-// node_capi.cpp -- flat C entry points over AprilTagNode (node core) so tests and non-C++ hosts can drive the
+// node_capi.cpp -- flat C entry points over AprilTagNodeCore (node core) so tests and non-C++ hosts can drive the
 // plugin surface without ROS.  Exceptions are converted to error codes + message (none crosses the ABI).
 #include <cstring>
 #include <string>
@@ -38,7 +38,7 @@ int b200NodeCreate(void **node, const char *tag_family, const char *backends, do
     p.size = size;
     p.max_tags = max_tags;
     p.tile_size = (uint32_t)tile_size;
-    *node = new AprilTagNode(p);
+    *node = new AprilTagNodeCore(p);
     return 0;
   } catch (const std::exception &e) {
     set_err(err, errlen, e.what());
@@ -46,16 +46,16 @@ int b200NodeCreate(void **node, const char *tag_family, const char *backends, do
   }
 }
 
-void b200NodeDestroy(void *node) { delete static_cast<AprilTagNode *>(node); }
+void b200NodeDestroy(void *node) { delete static_cast<AprilTagNodeCore *>(node); }
 
-int b200NodeUsingCuAprilTagImpl(void *node) { return static_cast<AprilTagNode *>(node)->UsingCuAprilTagImpl() ? 1 : 0; }
+int b200NodeUsingCuAprilTagImpl(void *node) { return static_cast<AprilTagNodeCore *>(node)->UsingCuAprilTagImpl() ? 1 : 0; }
 
 // one synchronised (image, camera_info) pair; out receives the published AprilTagDetectionArray
 int b200NodeOnFrame(void *node, const char *encoding, uint32_t width, uint32_t height, uint32_t step, const void *dev_ptr,
                     const double *K9, uint32_t ci_width, uint32_t ci_height, const char *frame_id, b200NodeDetectionMsg *out,
                     int max_out, int *n_out, char *err, size_t errlen) {
   try {
-    AprilTagNode *n = static_cast<AprilTagNode *>(node);
+    AprilTagNodeCore *n = static_cast<AprilTagNodeCore *>(node);
     ImageView im;
     im.encoding = encoding ? encoding : "";
     im.width = width;

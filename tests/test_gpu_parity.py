@@ -12,9 +12,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-TOL_REFINED_PX = 2e-2   # refined corners of ALL quads incl. undecodable junk quads whose edge fits are ill-conditioned (atan2f of ~0/~0)
+TOL_REFINED_PX = 5e-2   # refined corners of ALL quads incl. undecodable junk quads whose edge fits are ill-conditioned (atan2f of ~0/~0: a last-bit difference of the angle moves such a corner by up to ~0.02 px)
 TOL_CORNER_PX = 1e-3    # detection corners / centre
-TOL_MARGIN = 1e-3       # decision margin
+TOL_MARGIN = 5e-3       # decision margin (gray levels, typically 40-100): a 1e-4 px corner difference moves a bilinear sample on a tag edge by ~0.02
 TOL_POSE_T = 1e-5       # metres (relative to tag distance ~1-5 m)
 TOL_POSE_R = 1e-5
 
@@ -64,12 +64,27 @@ def assert_exact(res, rep):
     assert res["refined_max"] <= TOL_REFINED_PX and res["det_corner_max"] <= TOL_CORNER_PX and res["det_margin_max"] <= TOL_MARGIN, res
 
 
-@pytest.mark.parametrize("config,n", [("C1", 2), ("C2", 2), ("C3", 1), ("C4", 1), ("C5", 2)])
-def test_stage_parity_configs(pu, config, n):
+def _as_encoding(frames, enc):
+    if enc == "mono8":
+        return frames
+    ch = 3 if enc in ("rgb8", "bgr8") else 4
+    col = np.repeat(frames[:, :, :, None], ch, axis=3)
+    if ch == 4:
+        col[..., 3] = 255
+    return np.ascontiguousarray(col)
+
+
+@pytest.mark.parametrize("config,n,enc", [("C1", 2, "mono8"), ("C2", 2, "mono8"), ("C2", 2, "bgr8"), ("C3", 8, "mono8"), ("C4", 1, "mono8"),
+                                           ("C5", 2, "mono8"), ("C5", 2, "bgr8")])
+def test_stage_parity_configs(pu, config, n, enc):
+    """Every BASELINE.json config, stage by stage against the oracle (C3 = 4K with eight frames; C2 / C5 also in the node's bgr8 wire
+    format)."""
     from isaac_ros_apriltag_b200 import synth
+    if pu.EMU and config == "C3":
+        n = 1  # (the emulator runs a 4K frame in ~20 s)
     frames, truths, K, ts, fams = synth.make_config_frames(config, n)
     rep = []
-    res, gdets = pu.compare_stages(frames, "mono8", fams, report=rep)
+    res, gdets = pu.compare_stages(_as_encoding(frames, enc), enc, fams, report=rep)
     assert_exact(res, rep)
     assert res["n_det"] >= n  # the frames do contain detectable tags
     # and the detections are the ground truth tags
@@ -80,6 +95,44 @@ def test_stage_parity_configs(pu, config, n):
             assert got == want
         else:
             assert len(set(got) & set(want)) >= 0.9 * len(want)
+
+
+@pytest.mark.parametrize("tune", ["qf_exact=1", "ccl_tma=0", "ccl_tma=0,qf_exact=1"])
+def test_every_tune_variant_on_the_gpu(pu, tune, monkeypatch):
+    """The kernel variants behind B200AT_TUNE (csrc/detector.h, struct Tune: the bit-exact quad fit, the CCL sweep without TMA staging)
+    run on the GPU against the oracle like the defaults do -- a variant that only ever ran under the emulator is inventory."""
+    from isaac_ros_apriltag_b200 import synth
+    monkeypatch.setenv("B200AT_TUNE", tune)
+    frames, truths, K, ts, fams = synth.make_config_frames("C2", 2)
+    big = synth.make_frame(np.random.default_rng(11), 1600, 1200, [("tag36h11", 42)], side_px=(680, 720), max_tilt_deg=10.0, noise_sigma=0.0)[0]
+    for fr, fam in ((_as_encoding(frames, "bgr8"), fams), (big[None], ("tag36h11",))):
+        rep = []
+        res, gd = pu.compare_stages(fr, "bgr8" if fr.ndim == 4 else "mono8", fam, report=rep)
+        assert_exact(res, rep)
+        assert res["n_det"] >= 1
+    if "qf_exact=1" in tune:
+        assert res["quads_bits"] == 0
+
+
+@pytest.mark.parametrize("family,ids", [("tag16h5", [0, 7, 29]), ("tag36h10", [0, 1000, 2319]), ("tag25h9", [0, 34])])
+def test_other_families_decode_on_the_gpu(pu, family, ids):
+    """The families beyond tag36h11 that have a code table (apriltag_node.cpp:47-58): rendered, detected on the GPU, compared with the
+    oracle stage by stage; id / Hamming distance / family exact.  (tag16h5 is known for false positives on texture: both sides must
+    report the SAME ones.)"""
+    from isaac_ros_apriltag_b200 import synth
+    rng = np.random.default_rng(len(family))
+    g, truth = synth.make_frame(rng, 960, 720, [(family, i) for i in ids], side_px=(90, 170), max_tilt_deg=30.0)
+    rep = []
+    res, gd = pu.compare_stages(np.stack([g, g[:, ::-1].copy()]), "mono8", (family,), report=rep)
+    assert_exact(res, rep)
+    got = sorted(int(d["id"]) for d in gd[0] if d["hamming"] == 0)
+    assert set(ids) <= set(got), (ids, got)
+    # and with every family registered at once (multi-family decode path, like config C5)
+    rep = []
+    res, gd = pu.compare_stages(g[None], "mono8", ("tag36h11", "tag25h9", "tag16h5", "tag36h10"), report=rep)
+    assert_exact(res, rep)
+    fi = ["tag36h11", "tag25h9", "tag16h5", "tag36h10"].index(family)
+    assert set(ids) <= set(int(d["id"]) for d in gd[0] if d["family"] == fi and d["hamming"] == 0)
 
 
 @pytest.mark.parametrize("encoding", ["bgr8", "rgb8", "rgba8", "bgra8"])
@@ -196,6 +249,53 @@ def test_pol_golden_through_cuapriltags_abi(pu):
     n2.close()
 
 
+def test_multi_tag_frame_through_cuapriltags_abi_and_node(pu):
+    """Ten tags in one frame through cuAprilTagsDetect (array of cuAprilTagsID_t: 88-byte stride, CUDA's 8-byte aligned float2) and
+    through both node strategies: every entry, not only the first, carries the id / corners / pose of the batch entry point."""
+    needs_real_gpu(pu)
+    import ctypes as C
+    import torch
+    from isaac_ros_apriltag_b200 import capi, node, synth
+    frames, truths, K, ts, fams = synth.make_config_frames("C2", 1)
+    bgr = _as_encoding(frames, "bgr8")
+    H, W = frames.shape[1:]
+    t = torch.from_numpy(bgr).cuda()
+    det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=ts, families=fams, encoding="bgr8", max_batch=1, max_tags=64)
+    want = det.detect_device([t.data_ptr()], W * 3, 0)[0]
+    assert len(want) == 10
+    L = capi.lib()
+    hdl = C.c_void_p()
+    cam = capi.Intrinsics(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]))
+    assert L.nvCreateAprilTagsDetector(C.byref(hdl), W, H, 4, 0, C.byref(cam), C.c_float(ts)) == 0
+    img = capi.ImageInput(t.data_ptr(), W * 3, W, H)
+    tags = np.zeros(64, capi.ID_DTYPE)
+    ntags = C.c_uint32()
+    for stream in (0, torch.cuda.Stream().cuda_stream):  # legacy default stream and a real one (graph replay from the third call on)
+        for _ in range(3):
+            tags[:] = 0
+            rc = L.cuAprilTagsDetect(hdl, C.byref(img), tags.ctypes.data_as(C.POINTER(capi.TagID)), C.byref(ntags), 64, C.c_void_p(stream))
+            assert rc == 0 and ntags.value == 10
+            for k in range(10):
+                assert int(tags[k]["id"]) == int(want[k]["id"]) and int(tags[k]["hamming_error"]) == int(want[k]["hamming"])
+                assert np.abs(tags[k]["corners"] - want[k]["p"][::-1].astype(np.float32)).max() < 1e-3
+                assert np.abs(tags[k]["translation"] - want[k]["t"]).max() < 1e-5
+                assert np.abs(tags[k]["orientation"].reshape(3, 3).T - want[k]["R"].reshape(3, 3)).max() < 1e-5
+    # a caller's max_tags smaller than the scene: a truncated list and success, as a full cuAprilTags list would be
+    rc = L.cuAprilTagsDetect(hdl, C.byref(img), tags.ctypes.data_as(C.POINTER(capi.TagID)), C.byref(ntags), 4, None)
+    assert rc == 0 and ntags.value == 4
+    L.cuAprilTagsDestroy(hdl)
+    for backends in ("CUDA", "CPU"):
+        n = node.AprilTagNode(tag_family="tag36h11", backends=backends, size=ts, max_tags=64, tile_size=4)
+        for _ in range(3):
+            dets = n.on_frame("bgr8", W, H, W * 3, t.data_ptr(), K)
+        assert [d["id"] for d in dets] == [int(i) for i in want["id"]]
+        for d, w_ in zip(dets, want):
+            assert np.abs(d["corners"] - w_["p"][::-1]).max() < 1e-2 and np.abs(d["center"] - w_["c"]).max() < 0.6
+            assert np.abs(d["position"] - w_["t"]).max() < 1e-4
+        n.close()
+    det.close()
+
+
 def test_full_batch_properties(pu):
     """BASELINE size (batch 256 @1080p would take the oracle minutes): size-independent properties instead.
     Every replica of the same frame inside one batch gives the byte-identical result (idempotence / no cross-frame
@@ -301,6 +401,95 @@ def test_bench_workload_frames_match_oracle(pu):
     det.close()
 
 
+def test_async_host_calls_two_in_flight(pu, monkeypatch):
+    """b200AprilTagsEnqueueBatchHost / CollectBatchHost: two batches in flight, the second one's DMA and quad detection overlapping
+    the first one's decode / pose / D2H.  Batches of different content and length, several rounds, both staging modes: every batch
+    comes back byte-identical to the device-pointer entry point's result for ITS frames, in order."""
+    from isaac_ros_apriltag_b200 import capi, synth
+    monkeypatch.setenv("B200AT_SPARSE_DEBUG", "1")
+    frames, truths, K, ts, fams = synth.make_config_frames("C1", 10)
+    frames = _as_encoding(frames, "bgr8")
+    H, W = frames.shape[1:3]
+    det = capi.Detector(W, H, families=fams, encoding="bgr8", max_batch=4, max_tags=16)
+    t, ptrs, pitch = pu.upload(frames)
+    want = [det.detect_device([ptrs[i]], pitch, pu.current_stream())[0] for i in range(10)]
+    assert all(len(w) == 1 for w in want)
+    if pu.EMU:
+        host = frames
+    else:
+        import torch
+        host = torch.from_numpy(frames).pin_memory().numpy()
+    batches = [list(range(0, 4)), list(range(4, 7)), list(range(7, 10)), [9, 3, 5, 1], [2], list(range(0, 8))]
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200AT_SPARSE_H2D", mode)
+        for sub in (None, "1"):
+            if sub:
+                monkeypatch.setenv("B200AT_HOST_SUB", sub)
+            keep = [np.ascontiguousarray(host[b]) if pu.EMU else __import__("torch").from_numpy(np.ascontiguousarray(host[b])).pin_memory().numpy() for b in batches]
+            got = []
+            det.enqueue_host(keep[0])
+            for i in range(1, len(batches)):
+                det.enqueue_host(keep[i])          # two in flight
+                with pytest.raises(capi.B200ATError):
+                    det.enqueue_host(keep[i])      # a third is refused (and leaves the two untouched)
+                det._host_q.pop()                  # (the refused call was never queued)
+                got.append(det.collect_host())
+                assert det.counters()["sparse_h2d"] == int(mode)
+            got.append(det.collect_host())
+            for b, g in zip(batches, got):
+                assert len(g) == len(b)
+                for i, a in zip(b, g):
+                    assert a.tobytes() == want[i].tobytes(), (mode, sub, b, i)
+            if sub:
+                monkeypatch.delenv("B200AT_HOST_SUB")
+    # the synchronous entry point refuses to run while asynchronous batches are in flight, and works again afterwards
+    det.enqueue_host(keep[0])
+    with pytest.raises(capi.B200ATError):
+        det.detect_host(keep[1])
+    det.collect_host()
+    assert det.detect_host(keep[1])[0].tobytes() == want[4].tobytes()
+    det.close()
+
+
+def test_full_size_batch_every_position_against_oracle(pu):
+    """BASELINE config C2 at its full batch (256 x 1080p bgr8, the 32 distinct seeded frames bench.py tiles): EVERY one of the 256
+    positions of the batch is compared with the oracle's result for the frame it holds -- tag ids and Hamming distance exact,
+    corners / centre / decision margin within tolerance."""
+    if pu.EMU:
+        pytest.skip("batch 256 x 1080p is a GPU-size test")
+    import torch
+    from isaac_ros_apriltag_b200 import capi, synth
+    from oracle import oracle as O
+    distinct, B = 32, 256
+    frames, truths, K, ts, fams = synth.make_config_frames("C2", distinct)
+    bgr = _as_encoding(frames, "bgr8")
+    H, W = frames.shape[1:]
+    det = capi.Detector(W, H, intrinsics=(K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tag_size=ts, families=fams, encoding="bgr8", max_batch=B, max_tags=64)
+    dev = torch.from_numpy(bgr).cuda()
+    fb = dev[0].numel()
+    # position i holds distinct frame (5 i + i // 32) % 32: neighbouring positions differ, every frame appears at 8 positions
+    order = [(5 * i + i // 32) % distinct for i in range(B)]
+    ptrs = [dev.data_ptr() + order[i] * fb for i in range(B)]
+    gd = det.detect_device(ptrs, W * 3, pu.current_stream())
+    assert det.status() == 0
+    od, _ = O.detect_batch(bgr, fams, nthreads=min(16, os.cpu_count() or 1), encoding="bgr8")
+    ndet = 0
+    for i in range(B):
+        o = od[order[i]]
+        assert [(d["id"], d["hamming"]) for d in o] == [(int(a), int(b)) for a, b in zip(gd[i]["id"], gd[i]["hamming"])], i
+        for a, b in zip(gd[i], o):
+            assert np.abs(a["p"] - b["p"]).max() <= TOL_CORNER_PX and np.abs(a["c"] - b["c"]).max() <= TOL_CORNER_PX, i
+            assert abs(float(a["decision_margin"]) - b["decision_margin"]) <= TOL_MARGIN
+            ndet += 1
+    assert ndet >= 0.97 * 10 * B
+    # the host entry point on the same batch (pinned frames, sparse staging, four sub-batches, two workspace views)
+    host = torch.from_numpy(bgr[order]).pin_memory().numpy()
+    hd = det.detect_host(host)
+    for i in range(B):
+        assert hd[i].tobytes() == gd[i].tobytes(), i
+    det.close()
+
+
 def test_two_devices_one_process(pu):
     """One process, one handle per GPU (b200AprilTagsOptions_t::device): the per-device kernel attributes, workspaces and
     streams are independent, the caller's current device is left untouched, results are identical on both GPUs."""
@@ -363,32 +552,18 @@ def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
         assert full[i].tobytes() == want[i].tobytes(), i
         assert got[i].tobytes() == want[i].tobytes(), i
     assert sum(len(x) for x in got) >= n
-    # two sub-batches in flight on two streams (disjoint workspace views), both staging modes
-    monkeypatch.setenv("B200AT_HOST_STREAMS", "2")
-    monkeypatch.setenv("B200AT_HOST_SUB", "2")
-    for mode in ("0", "1"):
-        monkeypatch.setenv("B200AT_SPARSE_H2D", mode)
-        got3 = det.detect_host(host)
-        assert det.counters()["sparse_h2d"] == int(mode)
-        for i in range(n):
-            assert got3[i].tobytes() == want[i].tobytes(), (mode, i)
-    monkeypatch.delenv("B200AT_HOST_STREAMS")
-    # pipelined sparse path: FRONT(k+1) on the compute stream while the fetch stream serves sub-batch k (three staging slots);
-    # sub-batches of 1 and 2 frames so that the 6 frames exercise slot reuse
-    monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
-    # level 3 (default): as 1, but the first fetch of sub-batch k also waits for the decode of k-1.  (Level 2 -- 3 plus a
-    # counters block per sub-batch -- is logic-checked under the emulator, tests/test_emu_parity.py; it joins this list once it
-    # has been raced on a GPU.)
-    for level, sub in (("1", "1"), ("1", "2"), ("3", "1"), ("3", "2")):
-        monkeypatch.setenv("B200AT_HOST_PIPE", level)
+    # sub-batches of 1 and 2 frames: the 6 frames then cycle through the three staging slots, the two workspace views and the four
+    # counter blocks of the pipelined path (FRONT(k+1) on the compute stream while the fetch stream serves sub-batch k)
+    for sub in ("1", "2"):
         monkeypatch.setenv("B200AT_HOST_SUB", sub)
-        for _ in range(2):
-            got4 = det.detect_host(host)
-            c4 = det.counters()
-            assert c4["sparse_h2d"] == 1 and c4["detections"] == sum(len(x) for x in want)
-            for i in range(n):
-                assert got4[i].tobytes() == want[i].tobytes(), (level, sub, i)
-    monkeypatch.delenv("B200AT_HOST_PIPE")
+        for mode in ("0", "1"):
+            monkeypatch.setenv("B200AT_SPARSE_H2D", mode)
+            for _ in range(2):
+                got4 = det.detect_host(host)
+                c4 = det.counters()
+                assert c4["sparse_h2d"] == int(mode) and c4["detections"] == sum(len(x) for x in want)
+                for i in range(n):
+                    assert got4[i].tobytes() == want[i].tobytes(), (sub, mode, i)
     monkeypatch.delenv("B200AT_HOST_SUB")
     monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
     # frames in pageable memory: the call falls back to the full copy by itself
