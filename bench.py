@@ -30,11 +30,14 @@ METRIC = "frames_per_sec_1080p_tag36h11"
 UNIT = "frames/s"
 
 
+NCU_TRAFFIC_FILE = "r03_ncu_full_dense_batch256.csv"  # ncu --set full of the same command and batch (tools/gpu_final.sh)
+
+
 def load_ncu_traffic(kernel="k_threshold4"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
     (profiles/, same command and batch as this bench); None when the file is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_final_ncu_full_dense_batch256.csv")
+    path = os.path.join(ROOT, "profiles", NCU_TRAFFIC_FILE)
     try:
         rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("#"))]
         hdr, units = rows[0], rows[1]
@@ -129,8 +132,7 @@ def run_reference(args):
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     frames, _, _, _, fams = make_workload(args.config, args.distinct, args.encoding)
-    n_step = max(cores, 16)
-    n_step = min(n_step, 256)
+    n_step = args.batch  # the same step as the GPU arm: one batch of the workload (256 frames of C2 take the 16-core port ~1 s)
     idx = np.arange(n_step) % frames.shape[0]
     sample = np.ascontiguousarray(frames[idx])
     for _ in range(args.warmup):
@@ -145,7 +147,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(args), "frames_per_step": n_step, "detections_per_step": ndet // max(args.steps, 1)},
+            "config": {"workload": workload_name(args), "l2": "n/a (CPU arm)", "frames_per_step": n_step,
+                       "detections_per_step": ndet // max(args.steps, 1)},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_step} frames/step x {args.steps} steps, frame-parallel, one detector per thread"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -265,10 +268,13 @@ def main():
         host = torch.from_numpy(frames).pin_memory()
         host_batch = host.repeat((reps,) + (1,) * (host.dim() - 1))[:B].contiguous().pin_memory()
         hb = host_batch.numpy()
-        e2e_steps = max(2, min(args.steps, 5))
-        d2h = B * max_tags * capi.DET_DTYPE.itemsize + B * 4 + 4 * 24 * 4
+        e2e_steps = max(2, args.steps)
+        d2h = B * max_tags * capi.DET_DTYPE.itemsize + B * 4 + 4 * 4 * 32 * 4  # detections, counts, four sub-batches x four counter blocks
 
-        def measure_e2e(mode):
+        def measure_e2e(mode, pipelined):
+            """Every step copies every frame of the batch host->device and every result device->host inside the timed region.
+            pipelined: b200AprilTagsEnqueueBatchHost / CollectBatchHost with two batches in flight (step k+1's DMA and quad
+            detection overlap step k's decode / pose / D2H); otherwise one synchronous b200AprilTagsDetectBatchHost per step."""
             if mode is None:
                 os.environ.pop("B200AT_SPARSE_H2D", None)
             else:
@@ -277,8 +283,15 @@ def main():
                 det.detect_host(hb)
             barrier()
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                r = det.detect_host(hb)
+            if pipelined:
+                det.enqueue_host(hb)
+                for _ in range(e2e_steps - 1):
+                    det.enqueue_host(hb)
+                    r = det.collect_host()
+                r = det.collect_host()
+            else:
+                for _ in range(e2e_steps):
+                    r = det.detect_host(hb)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             te = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -290,14 +303,17 @@ def main():
             return {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(c["h2d_bytes"]),
                     "input_bytes_per_step": int(B * frame_bytes), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "staging": "sparse" if c["sparse_h2d"] else "full_copy", "detections_per_step": int(sum(len(x) for x in r)),
-                    "timer": "host wall clock around the synchronous C-ABI call"}
+                    "calls_in_flight": 2 if pipelined else 1,
+                    "h2d_gbs": world * c["h2d_bytes"] * e2e_steps / dt / 1e9,
+                    "timer": "host wall clock from the first enqueue to the last collect" if pipelined else "host wall clock around the synchronous C-ABI calls"}
 
-        e2e = measure_e2e(None)
-        e2e_modes[e2e["staging"]] = e2e
+        e2e = measure_e2e(None, True)
+        e2e_modes[e2e["staging"] + "_pipelined"] = e2e
+        e2e_modes[e2e["staging"] + "_synchronous"] = measure_e2e(None, False)
         other = "full_copy" if e2e["staging"] == "sparse" else "sparse"
-        alt = measure_e2e(other)
+        alt = measure_e2e(other, True)
         if alt["staging"] == other:
-            e2e_modes[other] = alt
+            e2e_modes[other + "_pipelined"] = alt
 
     if rank != 0:
         if world > 1:
@@ -316,10 +332,26 @@ def main():
     roofline = {"kernel": "k_threshold4", "bound": "hbm", "achieved": thr_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (thr_gbs / peak) if thr_gbs else None,
                 "traffic": load_ncu_traffic() if (args.config == "C2" and B == 256 and args.encoding == "bgr8") else None,
-                "traffic_source": "profiles/r01_final_ncu_full_dense_batch256.csv (ncu --set full, bytes per launch)",
+                "traffic_source": "profiles/" + NCU_TRAFFIC_FILE + " (ncu --set full of this command, bytes per launch; null if not captured)",
                 "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": 2 * Pd * B, "launch_ms": stage_ms.get("threshold")}
     dominant = max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else None
+    # SURVEY 8d end-to-end figure: (input bytes + 14 Pd) per frame at the measured frame rate against the HBM peak -- what the whole
+    # pipeline achieves of a dense, staged, HBM-bound pipeline; and the same for the slowest stage (quad fit: 4 B packed point in,
+    # 8 B sorted point out and in again = 20 B per boundary point kept; the other stages as in stages_gbs)
+    in_bytes = frame_bytes
+    per_frame = in_bytes + 14 * Pd
+    roofline_pipeline = {"bound": "hbm", "bytes_per_frame": int(per_frame), "achieved": per_frame * value / world / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": per_frame * value / world / 1e9 / peak,
+                         "note": "whole pipeline: (input bytes + 14 Pd) x frames/s per GPU (SURVEY 8d); the irregular stages are latency / issue bound, see DESIGN.md"}
+    alg_dom = dict(alg)
+    alg_dom["quadfit"] = 20 * counters["points"] / max(B, 1)
+    roofline_dominant = None
+    if dominant in alg_dom and stage_ms.get(dominant, 0) > 0:
+        gbs = alg_dom[dominant] * B / (stage_ms[dominant] / 1e3) / 1e9
+        roofline_dominant = {"stage": dominant, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             "algorithmic_bytes_per_frame": int(alg_dom[dominant]), "ms_per_step": stage_ms[dominant],
+                             "share_of_step": stage_ms[dominant] / max(sum(v for k, v in stage_ms.items() if k != "d2h"), 1e-9)}
 
     # ---- single-frame latency through the drop-in entry point (how the reference's README numbers were taken:
     # 720p, one frame in flight; /root/reference/README.md:69 quotes 2.0-2.9 ms for cuAprilTags on other hardware) ----
@@ -379,8 +411,9 @@ def main():
             "config": {"workload": workload_name(args), "l2": "inputs larger than L2 (batch %.0f MB)" % (B * frame_bytes / 1e6),
                        "detections_per_batch": n_det, "status": status, "points_per_batch": int(counters["points"]),
                        "clusters_per_batch": int(counters["clusters"]), "quads_per_batch": int(counters["quads"])},
-            "clocks": clocks, "e2e": e2e, "e2e_modes": {k: {kk: v[kk] for kk in ("value", "h2d_bytes_per_step")} for k, v in e2e_modes.items()},
-            "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e,
+            "e2e_modes": {k: {kk: v[kk] for kk in ("value", "h2d_bytes_per_step", "h2d_gbs", "calls_in_flight")} for k, v in e2e_modes.items()},
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_pipeline": roofline_pipeline, "roofline_dominant": roofline_dominant,
             "stages_ms_per_step": stage_ms, "stages_note": "stage times from extra steps with CUDA events between the stages (outside the timed region)", "stages_gbs": stage_gbs, "dominant_stage": dominant, "latency_720p": latency,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
