@@ -355,7 +355,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   g.pts_cap = (uint32_t)(ppf * B);
   g.clu_cap = (uint32_t)(cpf * B);
   g.quad_cap = (uint32_t)(qpf * B);
-  g.cand_cap = 256;
+  g.cand_cap = std::min<uint32_t>(1024u, std::max<uint32_t>(256u, 2 * opt.max_tags));  // decoded candidates per frame before reconcile (k_final.cu MAXC)
   g.max_tags = opt.max_tags;
   g.max_cluster_pts = (uint32_t)(2 * (2 * g.Wd + 2 * g.Hd));
 

@@ -1,4 +1,4 @@
-// k_final.cu -- a14 reconcile + ordering (one thread per frame; a frame has a handful of candidates) and a15
+// k_final.cu -- a14 reconcile + ordering (one warp per frame) and a15
 // pose (one thread per detection: homography initialisation, 50 orthogonal iterations, ambiguity resolution).
 // Restates AprilRobotics apriltag.c (reconcile block of apriltag_detector_detect), common/g2d.c
 // (g2d_polygon_overlaps_polygon) and apriltag_pose.c (estimate_tag_pose) -- SURVEY App. A.8-A.9 -- with the
@@ -9,7 +9,7 @@
 
 namespace b200at {
 
-constexpr int MAXC = 256;  // candidates per frame upper bound (Geo::cand_cap <= MAXC)
+constexpr int MAXC = 1024;  // candidates per frame upper bound (Geo::cand_cap <= MAXC)
 
 __device__ bool seg_intersect_dev(const double a0[2], const double a1[2], const double b0[2], const double b1[2]) {
   double ua[2] = {a1[0] - a0[0], a1[1] - a0[1]};
@@ -59,84 +59,127 @@ __device__ __forceinline__ int prefer_smaller_dev(int pref, double q0, double q1
   return 0;
 }
 
-__global__ void __launch_bounds__(32) k_reconcile(Geo g, const Cand *__restrict__ cands, const uint32_t *__restrict__ cand_count,
-                                                  b200AprilTagsDetection_t *__restrict__ out, uint32_t *__restrict__ out_count,
-                                                  uint32_t *__restrict__ counters, int nframes) {
-  const int fr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (fr >= nframes) return;
+// One WARP per frame.  The candidates' ordering keys are staged in shared memory; both orderings (processing order by
+// (cluster key, family), output order by (id, family, c.y, c.x)) are computed by rank counting across the lanes; the reconcile
+// loop keeps upstream's control flow (removal = swap with last, restart of the outer element when it loses) but finds the next
+// partner with the same (family, id) of the current element by a ballot over 32 positions at a time -- partners are rare, so an
+// outer element costs m / 32 steps instead of m, and the polygon test runs only on real partners.
+constexpr int RW = 2;  // frames (warps) per CTA
+__global__ void __launch_bounds__(32 * RW) k_reconcile(Geo g, const Cand *__restrict__ cands, const uint32_t *__restrict__ cand_count,
+                                                       b200AprilTagsDetection_t *__restrict__ out, uint32_t *__restrict__ out_count,
+                                                       uint32_t *__restrict__ counters, int nframes) {
+  __shared__ uint16_t s_idx_a[RW][MAXC];
+  __shared__ uint16_t s_ord_a[RW][MAXC];
+  __shared__ unsigned long long s_tag_a[RW][MAXC];  // family << 32 | id of the candidate at sorted position
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fr = blockIdx.x * RW + wid;
+  if (fr >= nframes) return;  // (whole warps leave; no block-wide barrier below)
+  uint16_t *idx = s_idx_a[wid], *ord = s_ord_a[wid];
+  unsigned long long *tag = s_tag_a[wid];
   const Cand *cf = cands + (size_t)fr * g.cand_cap;
   int n = (int)min(cand_count[fr], g.cand_cap);
   if (n > MAXC) n = MAXC;
-  uint16_t idx[MAXC];
-  for (int i = 0; i < n; i++) idx[i] = (uint16_t)i;
-  // canonical processing order: (cluster key, family index)
-  for (int i = 1; i < n; i++) {
-    uint16_t v = idx[i];
-    unsigned long long kv = cf[v].key;
-    int fv = cf[v].family;
-    int j = i - 1;
-    while (j >= 0 && (cf[idx[j]].key > kv || (cf[idx[j]].key == kv && cf[idx[j]].family > fv))) {
-      idx[j + 1] = idx[j];
-      j--;
+  // canonical processing order: (cluster key, family); ties cannot occur (one candidate per cluster and family)
+  for (int i = lane; i < n; i += 32) {
+    const unsigned long long kv = cf[i].key;
+    const int fv = cf[i].family;
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+      const unsigned long long kj = cf[j].key;
+      const int fj = cf[j].family;
+      rank += (kj < kv || (kj == kv && (fj < fv || (fj == fv && j < i)))) ? 1 : 0;
     }
-    idx[j + 1] = v;
+    idx[rank] = (uint16_t)i;
   }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const Cand &c = cf[idx[i]];
+    tag[i] = ((unsigned long long)(uint32_t)c.family << 32) | (uint32_t)c.id;
+  }
+  __syncwarp();
   // reconcile: same control flow as upstream, removal = swap with last
   int m = n;
   for (int i0 = 0; i0 < m; i0++) {
-    for (int i1 = i0 + 1; i1 < m; i1++) {
-      const Cand &d0 = cf[idx[i0]], &d1 = cf[idx[i1]];
-      if (d0.id != d1.id || d0.family != d1.family) continue;
-      if (polygon_overlaps_dev(d0.p, d1.p)) {
-        int pref = 0;
-        pref = prefer_smaller_dev(pref, d0.hamming, d1.hamming);
-        pref = prefer_smaller_dev(pref, -d0.decision_margin, -d1.decision_margin);
-        for (int i = 0; i < 4; i++) {
-          pref = prefer_smaller_dev(pref, d0.p[i][0], d1.p[i][0]);
-          pref = prefer_smaller_dev(pref, d0.p[i][1], d1.p[i][1]);
-        }
-        if (pref < 0) {
-          idx[i1] = idx[m - 1];
-          m--;
-          i1--;
-        } else {
-          idx[i0] = idx[m - 1];
-          m--;
-          i0--;
-          break;
+    int i1 = i0 + 1;
+    bool restart = false;
+    while (i1 < m) {
+      // first position >= i1 whose (family, id) equals that of i0
+      const unsigned long long t0 = tag[i0];
+      int found = -1;
+      for (int b0 = i1; b0 < m && found < 0; b0 += 32) {
+        const int j = b0 + lane;
+        const unsigned bal = __ballot_sync(0xffffffffu, j < m && tag[j] == t0);
+        if (bal) found = b0 + __ffs(bal) - 1;
+      }
+      if (found < 0) break;
+      i1 = found;
+      int pref = 0;
+      if (lane == 0) {
+        const Cand &d0 = cf[idx[i0]], &d1 = cf[idx[i1]];
+        if (polygon_overlaps_dev(d0.p, d1.p)) {
+          pref = prefer_smaller_dev(pref, d0.hamming, d1.hamming);
+          pref = prefer_smaller_dev(pref, -d0.decision_margin, -d1.decision_margin);
+          for (int i = 0; i < 4; i++) {
+            pref = prefer_smaller_dev(pref, d0.p[i][0], d1.p[i][0]);
+            pref = prefer_smaller_dev(pref, d0.p[i][1], d1.p[i][1]);
+          }
+          pref = pref < 0 ? 1 : 2;  // 1: d1 goes, 2: d0 goes
         }
       }
+      pref = __shfl_sync(0xffffffffu, pref, 0);
+      if (pref == 1) {
+        if (lane == 0) {
+          idx[i1] = idx[m - 1];
+          tag[i1] = tag[m - 1];
+        }
+        m--;
+        __syncwarp();
+        // (upstream: i1-- then i1++: the element swapped in is examined next)
+      } else if (pref == 2) {
+        if (lane == 0) {
+          idx[i0] = idx[m - 1];
+          tag[i0] = tag[m - 1];
+        }
+        m--;
+        __syncwarp();
+        restart = true;  // (upstream: i0--, break: the element swapped in is processed at the same position)
+        break;
+      } else {
+        i1++;
+      }
     }
+    if (restart) i0--;
   }
-  // output order: (id, family, c.y, c.x)
-  for (int i = 1; i < m; i++) {
-    uint16_t v = idx[i];
-    const Cand &cv = cf[v];
-    int j = i - 1;
-    while (j >= 0) {
+  __syncwarp();
+  // output order: (id, family, c.y, c.x), position as the last tie-break
+  for (int i = lane; i < m; i += 32) {
+    const Cand &cv = cf[idx[i]];
+    int rank = 0;
+    for (int j = 0; j < m; j++) {
       const Cand &cj = cf[idx[j]];
-      bool gt;
+      bool lt;
       if (cj.id != cv.id)
-        gt = cj.id > cv.id;
+        lt = cj.id < cv.id;
       else if (cj.family != cv.family)
-        gt = cj.family > cv.family;
+        lt = cj.family < cv.family;
       else if (cj.c[1] != cv.c[1])
-        gt = cj.c[1] > cv.c[1];
+        lt = cj.c[1] < cv.c[1];
+      else if (cj.c[0] != cv.c[0])
+        lt = cj.c[0] < cv.c[0];
       else
-        gt = cj.c[0] > cv.c[0];
-      if (!gt) break;
-      idx[j + 1] = idx[j];
-      j--;
+        lt = j < i;
+      rank += lt ? 1 : 0;
     }
-    idx[j + 1] = v;
+    ord[rank] = idx[i];
   }
+  __syncwarp();
   int no = m;
   if (no > (int)g.max_tags) {
     no = (int)g.max_tags;
-    atomicOr(&counters[CNT_STATUS], (uint32_t)ST_OUT_TRUNC);
+    if (lane == 0) atomicOr(&counters[CNT_STATUS], (uint32_t)ST_OUT_TRUNC);
   }
-  for (int i = 0; i < no; i++) {
-    const Cand &c = cf[idx[i]];
+  for (int i = lane; i < no; i += 32) {
+    const Cand &c = cf[ord[i]];
     b200AprilTagsDetection_t d;
     d.family = c.family;
     d.id = c.id;
@@ -154,8 +197,10 @@ __global__ void __launch_bounds__(32) k_reconcile(Geo g, const Cand *__restrict_
     d.pose_err = 0;
     out[(size_t)fr * g.max_tags + i] = d;
   }
-  out_count[fr] = (uint32_t)no;
-  atomicAdd(&counters[CNT_DETS], (uint32_t)no);
+  if (lane == 0) {
+    out_count[fr] = (uint32_t)no;
+    atomicAdd(&counters[CNT_DETS], (uint32_t)no);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -634,7 +679,7 @@ __global__ void __launch_bounds__(64) k_pose(Geo g, FitParams fp, b200AprilTagsD
 
 int launch_finalize(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
-  k_reconcile<<<(nframes + 31) / 32, 32, 0, s>>>(g, ws.cands, ws.cand_count, ws.out, ws.out_count, ws.counters, nframes);
+  k_reconcile<<<(nframes + RW - 1) / RW, 32 * RW, 0, s>>>(g, ws.cands, ws.cand_count, ws.out, ws.out_count, ws.counters, nframes);
   const int total = nframes * (int)g.max_tags;
   k_pose<<<(total + 63) / 64, 64, 0, s>>>(g, ws.fp, ws.out, ws.out_count, nframes);
   return 2;
