@@ -31,7 +31,9 @@ __device__ __forceinline__ uint32_t hash_key2(unsigned long long k) {
 // kernels are instruction-issue bound (ncu: 66 % of peak issue at 82 % warps active), this variant executes about half the
 // instructions per pixel than a thread-per-pixel pass.  The order of the points inside a cluster's segment is irrelevant (sorted
 // later).  (Measured and dropped, profiles/r03_variants.md: deferring the emit pass's stores by one round; recording (slot, point)
-// pairs in the count pass and scattering them instead of a second pass.)
+// pairs in the count pass and scattering them instead of a second pass; grouping the points of a whole row by key in a
+// shared-memory table so that one thread per distinct key touches the global table -- the three block barriers and the
+// serialised global round trips per CTA made both passes 2x slower: count 0.75 -> 1.58 ms, emit 1.39 -> 2.92 ms.)
 template <bool EMIT>
 __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
                                                        unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--host-only", action="store_true")
+    ap.add_argument("--device-only", action="store_true")
     ap.add_argument("--tag", default="")
     args = ap.parse_args()
     t_start = time.time()
@@ -132,6 +133,9 @@ def main():
         except Exception as e:
             emit(event="device_subbatched", sub=sub, error=repr(e))
     # ---- host path: staging mode x sub-batch size x knobs ----
+    if args.device_only:
+        emit(event="done", seconds=time.time() - t_start)
+        return
     host = torch.from_numpy(frames).pin_memory().repeat((reps, 1, 1, 1))[:B].contiguous().pin_memory().numpy()
     for tune, sparse_on, sub_i, streams_i, pipe_i, ramp_i, ncopy_i in HOST_CONFIGS:
         mode, sub, streams = str(sparse_on), str(sub_i), str(streams_i)
