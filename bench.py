@@ -112,6 +112,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank's threads to the CPUs next to its GPU's PCIe root BEFORE the pinned staging memory is allocated (first touch
+    then places it on that NUMA node): with 8 ranks on one box the host->device path is what bounds `e2e` (SCALE_r01: 0.59 at N=8
+    with every rank on the same CPUs).  Returns what was done, for the JSON line."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(base + "/numa_node").read().strip()
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        local = sorted(cpus & set(allowed))
+        if local and len(local) < len(allowed):
+            os.sched_setaffinity(0, local)
+            return {"numa_node": node, "cpus": f"{local[0]}-{local[-1]} ({len(local)})", "bound": True}
+        return {"numa_node": node, "cpus": f"{allowed[0]}-{allowed[-1]} ({len(allowed)})", "bound": False,
+                "why": "the GPU's local CPUs are all the CPUs this process may use"}
+    except Exception as e:  # no sysfs / nvidia-smi: run unbound
+        return {"bound": False, "why": repr(e)[:80]}
+
+
 def make_workload(config, distinct, encoding):
     from isaac_ros_apriltag_b200 import synth
     frames, truths, K, tagsize, fams = synth.make_config_frames(config, distinct)
@@ -191,6 +220,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the detector has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa(local_rank)
     if world > 1:
         # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -307,7 +337,30 @@ def main():
                     "h2d_gbs": world * c["h2d_bytes"] * e2e_steps / dt / 1e9,
                     "timer": "host wall clock from the first enqueue to the last collect" if pipelined else "host wall clock around the synchronous C-ABI calls"}
 
+        def h2d_ceiling():
+            """What the box gives: plain cudaMemcpyAsync of the pinned batch, all ranks at the same time (aggregate GB/s)."""
+            dst = torch.empty_like(dev_batch)
+            cs = torch.cuda.Stream()
+            with torch.cuda.stream(cs):
+                dst.copy_(host_batch, non_blocking=True)
+            cs.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(cs):
+                for _ in range(3):
+                    dst.copy_(host_batch, non_blocking=True)
+            cs.synchronize()
+            dt = time.perf_counter() - t0
+            te = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            del dst
+            return world * 3 * host_batch.numel() / float(te.item()) / 1e9
+
         e2e = measure_e2e(None, True)
+        e2e["h2d_ceiling_gbs"] = h2d_ceiling()
+        e2e["h2d_ceiling_note"] = "plain pinned cudaMemcpyAsync of the same batch, all ranks concurrently (aggregate)"
+        e2e["affinity"] = affinity
         e2e_modes[e2e["staging"] + "_pipelined"] = e2e
         e2e_modes[e2e["staging"] + "_synchronous"] = measure_e2e(None, False)
         other = "full_copy" if e2e["staging"] == "sparse" else "sparse"
