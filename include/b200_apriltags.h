@@ -114,7 +114,24 @@ enum {
 };
 
 /* family indices (bit i of family_mask); same order as the oracle */
-enum { B200AT_FAM_36H11 = 0, B200AT_FAM_25H9 = 1, B200AT_FAM_16H5 = 2, B200AT_FAM_36H10 = 3, B200AT_NUM_FAMILIES = 4 };
+enum { B200AT_FAM_36H11 = 0, B200AT_FAM_25H9 = 1, B200AT_FAM_16H5 = 2, B200AT_FAM_36H10 = 3, B200AT_NUM_FAMILIES = 4,
+       B200AT_FAM_CUSTOM0 = 4, B200AT_FAM_CUSTOM1 = 5, B200AT_MAX_FAMILIES = 6 /* slots 4, 5: b200AprilTagsRegisterFamily */ };
+
+/* A tag family supplied by the caller: the fields of AprilRobotics' apriltag_family_t (tagStandard41h12.c, tagCircle21h7.c, ...).
+ * This is how the families the reference's VPI path lists (apriltag_node.cpp:47-58) but whose code tables are not built in are
+ * used: copy the table from the upstream tag*.c file.  bit_x / bit_y are relative to the border's first cell and may be negative
+ * or >= width_at_border (data bits outside the border); reversed_border = the border is white on a black surround. */
+typedef struct {
+  uint32_t struct_size;      /* sizeof(b200AprilTagsFamilyDesc_t) */
+  uint32_t nbits;            /* <= 52 */
+  uint32_t ncodes;
+  uint32_t width_at_border;
+  uint32_t total_width;      /* <= 12 */
+  uint32_t reversed_border;
+  const int8_t *bit_x;       /* [nbits] */
+  const int8_t *bit_y;
+  const uint64_t *codes;     /* [ncodes] */
+} b200AprilTagsFamilyDesc_t;
 
 /* sensor_msgs encodings the reference's VPI path accepts (apriltag_node.cpp:76-82) */
 enum { B200AT_ENC_MONO8 = 0, B200AT_ENC_RGB8 = 1, B200AT_ENC_BGR8 = 2, B200AT_ENC_RGBA8 = 3, B200AT_ENC_BGRA8 = 4 };
@@ -163,6 +180,10 @@ typedef struct {
 } b200AprilTagsFrame_t;
 
 void b200AprilTagsDefaultOptions(b200AprilTagsOptions_t *opt);
+
+/* Registers (copies) a caller-supplied family in slot B200AT_FAM_CUSTOM0 / B200AT_FAM_CUSTOM1, process wide; handles created
+ * AFTERWARDS with that bit in family_mask decode it (existing handles keep the table they were created with). */
+int b200AprilTagsRegisterFamily(int32_t slot, const b200AprilTagsFamilyDesc_t *desc);
 
 int b200AprilTagsCreate(cuAprilTagsHandle *h, uint32_t img_width, uint32_t img_height,
                         const cuAprilTagsCameraIntrinsics_t *cam, float tag_dim, const b200AprilTagsOptions_t *opt);

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200apriltags.so")
 
-FAMILY_NAMES = ["tag36h11", "tag25h9", "tag16h5", "tag36h10"]
+FAMILY_NAMES = ["tag36h11", "tag25h9", "tag16h5", "tag36h10", "custom0", "custom1"]  # custom*: b200AprilTagsRegisterFamily slots
 ENCODINGS = {"mono8": 0, "rgb8": 1, "bgr8": 2, "rgba8": 3, "bgra8": 4}
 BPP = {"mono8": 1, "rgb8": 3, "bgr8": 3, "rgba8": 4, "bgra8": 4}
 ERRORS = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NOMEM", 5: "OVERFLOW", 6: "NO_DEVICE"}
@@ -24,7 +24,7 @@ STAGES = ["preprocess", "threshold", "ccl", "cluster", "quadfit", "decode", "fin
 # every symbol include/b200_apriltags.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED_SYMBOLS = [
     "nvCreateAprilTagsDetector", "cuAprilTagsDetect", "cuAprilTagsDestroy",
-    "b200AprilTagsDefaultOptions", "b200AprilTagsCreate", "b200AprilTagsSetInputEncoding", "b200AprilTagsDetectBatch",
+    "b200AprilTagsDefaultOptions", "b200AprilTagsRegisterFamily", "b200AprilTagsCreate", "b200AprilTagsSetInputEncoding", "b200AprilTagsDetectBatch",
     "b200AprilTagsDetectBatchHost", "b200AprilTagsEnqueueBatchHost", "b200AprilTagsCollectBatchHost", "b200AprilTagsEnqueueBatch", "b200AprilTagsCollectBatch", "b200AprilTagsLastStatus",
     "b200AprilTagsEnableStageTiming", "b200AprilTagsGetStageTimes", "b200AprilTagsGetCounters", "b200AprilTagsGetDims",
     "b200AprilTagsReadBuffer", "b200AprilTagsVersion",
@@ -69,6 +69,12 @@ class Detection(C.Structure):  # b200AprilTagsDetection_t
                 ("t", C.c_double * 3), ("pose_err", C.c_double)]
 
 
+class FamilyDesc(C.Structure):  # b200AprilTagsFamilyDesc_t
+    _fields_ = [("struct_size", C.c_uint32), ("nbits", C.c_uint32), ("ncodes", C.c_uint32), ("width_at_border", C.c_uint32),
+                ("total_width", C.c_uint32), ("reversed_border", C.c_uint32), ("bit_x", C.c_void_p), ("bit_y", C.c_void_p),
+                ("codes", C.c_void_p)]
+
+
 class Frame(C.Structure):  # b200AprilTagsFrame_t
     _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_size_t)]
 
@@ -108,6 +114,7 @@ def lib():
         L.cuAprilTagsDestroy.argtypes = [vp]
         L.b200AprilTagsDefaultOptions.argtypes = [C.POINTER(Options)]
         L.b200AprilTagsDefaultOptions.restype = None
+        L.b200AprilTagsRegisterFamily.argtypes = [C.c_int32, C.POINTER(FamilyDesc)]
         L.b200AprilTagsCreate.argtypes = [C.POINTER(vp), u32, u32, C.POINTER(Intrinsics), C.c_float, C.POINTER(Options)]
         L.b200AprilTagsSetInputEncoding.argtypes = [vp, C.c_int32]
         L.b200AprilTagsDetectBatch.argtypes = [vp, C.POINTER(Frame), u32, vp, vp, vp, vp]
@@ -125,6 +132,19 @@ def lib():
         L.b200AprilTagsVersion.restype = C.c_char_p
         _lib = L
     return _lib
+
+
+def register_family(slot, fam):
+    """b200AprilTagsRegisterFamily: fam = dict with nbits, width_at_border, total_width, reversed_border, bit_x, bit_y, codes;
+    slot = 4 ("custom0") or 5 ("custom1")."""
+    bx = np.asarray(fam["bit_x"], np.int8)
+    by = np.asarray(fam["bit_y"], np.int8)
+    codes = np.asarray(fam["codes"], np.uint64)
+    d = FamilyDesc(C.sizeof(FamilyDesc), int(fam["nbits"]), len(codes), int(fam["width_at_border"]), int(fam["total_width"]),
+                   int(bool(fam.get("reversed_border", False))), bx.ctypes.data, by.ctypes.data, codes.ctypes.data)
+    rc = lib().b200AprilTagsRegisterFamily(slot, C.byref(d))
+    if rc != 0:
+        raise B200ATError(rc, "b200AprilTagsRegisterFamily")
 
 
 def default_options(**kw):

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -25,9 +26,18 @@ namespace {
 
 struct HostFamily {
   int nbits, ncodes, width_at_border, total_width, reversed_border;
-  const unsigned char *bit_x, *bit_y;
+  const unsigned char *bit_x, *bit_y;  // (built-in tables: all coordinates inside the border)
   const unsigned long long *codes;
 };
+// caller-supplied families (b200AprilTagsRegisterFamily), process wide
+struct CustomFamily {
+  bool used = false;
+  int nbits = 0, ncodes = 0, width_at_border = 0, total_width = 0, reversed_border = 0;
+  std::vector<int8_t> bit_x, bit_y;
+  std::vector<unsigned long long> codes;
+};
+CustomFamily g_custom_families[B200AT_MAX_FAMILIES - B200AT_NUM_FAMILIES];
+std::mutex g_custom_mutex;
 const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
     {tag36h11_nbits, tag36h11_ncodes, tag36h11_width_at_border, tag36h11_total_width, 0, tag36h11_bit_x, tag36h11_bit_y, tag36h11_codes},
     {tag25h9_nbits, tag25h9_ncodes, tag25h9_width_at_border, tag25h9_total_width, 0, tag25h9_bit_x, tag25h9_bit_y, tag25h9_codes},
@@ -103,7 +113,7 @@ struct cuAprilTagsHandle_st {
   int device = 0;
   uint32_t max_batch = 1;
   std::vector<void *> dev_allocs;
-  unsigned long long *dev_codes[B200AT_NUM_FAMILIES] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long *dev_codes[B200AT_MAX_FAMILIES] = {};
   // pinned host mirrors
   FrameDesc *h_frames = nullptr;
   b200AprilTagsDetection_t *h_out = nullptr;
@@ -270,6 +280,27 @@ void b200AprilTagsDefaultOptions(b200AprilTagsOptions_t *o) {
   o->device = -1;
 }
 
+int b200AprilTagsRegisterFamily(int32_t slot, const b200AprilTagsFamilyDesc_t *d) {
+  if (slot < B200AT_NUM_FAMILIES || slot >= B200AT_MAX_FAMILIES || !d || d->struct_size != sizeof(*d)) return B200AT_ERR_INVALID_ARG;
+  if (d->nbits < 1 || d->nbits > (uint32_t)kMaxBits || d->ncodes < 1 || !d->bit_x || !d->bit_y || !d->codes) return B200AT_ERR_INVALID_ARG;
+  if (d->width_at_border < 1 || d->total_width < d->width_at_border || d->total_width > 12 || ((d->total_width - d->width_at_border) & 1)) return B200AT_ERR_INVALID_ARG;
+  const int lo = -(int)(d->total_width - d->width_at_border) / 2, hi = lo + (int)d->total_width - 1;
+  for (uint32_t k = 0; k < d->nbits; k++)
+    if (d->bit_x[k] < lo || d->bit_x[k] > hi || d->bit_y[k] < lo || d->bit_y[k] > hi) return B200AT_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(g_custom_mutex);
+  CustomFamily &cf = g_custom_families[slot - B200AT_NUM_FAMILIES];
+  cf.nbits = (int)d->nbits;
+  cf.ncodes = (int)d->ncodes;
+  cf.width_at_border = (int)d->width_at_border;
+  cf.total_width = (int)d->total_width;
+  cf.reversed_border = d->reversed_border ? 1 : 0;
+  cf.bit_x.assign(d->bit_x, d->bit_x + d->nbits);
+  cf.bit_y.assign(d->bit_y, d->bit_y + d->nbits);
+  cf.codes.assign(d->codes, d->codes + d->ncodes);
+  cf.used = true;
+  return B200AT_OK;
+}
+
 int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cuAprilTagsCameraIntrinsics_t *cam, float tag_dim,
                         const b200AprilTagsOptions_t *opt_in) {
   if (!out) return B200AT_ERR_INVALID_ARG;
@@ -282,7 +313,12 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   }
   if (W == 0 || H == 0 || W > 16382 || H > 16382) return B200AT_ERR_INVALID_ARG;
   if (opt.max_batch == 0 || opt.max_tags == 0 || opt.tile_size == 0) return B200AT_ERR_INVALID_ARG;
-  if (opt.family_mask == 0 || (opt.family_mask >> B200AT_NUM_FAMILIES) != 0) return B200AT_ERR_UNSUPPORTED;
+  if (opt.family_mask == 0 || (opt.family_mask >> B200AT_MAX_FAMILIES) != 0) return B200AT_ERR_UNSUPPORTED;
+  {
+    std::lock_guard<std::mutex> lk(g_custom_mutex);
+    for (int i = B200AT_NUM_FAMILIES; i < B200AT_MAX_FAMILIES; i++)
+      if ((opt.family_mask & (1u << i)) && !g_custom_families[i - B200AT_NUM_FAMILIES].used) return B200AT_ERR_UNSUPPORTED;
+  }
   if (bpp_of(opt.input_encoding) == 0) return B200AT_ERR_INVALID_ARG;
   // integer decimation factors, plus AprilRobotics' 3->2 "1.5" special case
   float qd = opt.quad_decimate;
@@ -363,27 +399,44 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   int min_tag_width = 1000000, nfam = 0;
   fp.normal_border = fp.reversed_border = 0;
   int rc = 0;
-  for (int i = 0; i < B200AT_NUM_FAMILIES && rc == 0; i++) {
+  for (int i = 0; i < B200AT_MAX_FAMILIES && rc == 0; i++) {
     if (!(opt.family_mask & (1u << i))) continue;
-    const HostFamily &hf = kHostFamilies[i];
     DevFamily &df = ws.fams[nfam++];
-    df.nbits = hf.nbits;
-    df.ncodes = hf.ncodes;
-    df.width_at_border = hf.width_at_border;
-    df.total_width = hf.total_width;
-    df.reversed_border = hf.reversed_border;
-    df.index = i;
-    for (int k = 0; k < hf.nbits; k++) {
-      df.bit_x[k] = hf.bit_x[k];
-      df.bit_y[k] = hf.bit_y[k];
+    const unsigned long long *host_codes = nullptr;
+    if (i < B200AT_NUM_FAMILIES) {
+      const HostFamily &hf = kHostFamilies[i];
+      df.nbits = hf.nbits;
+      df.ncodes = hf.ncodes;
+      df.width_at_border = hf.width_at_border;
+      df.total_width = hf.total_width;
+      df.reversed_border = hf.reversed_border;
+      for (int k = 0; k < hf.nbits; k++) {
+        df.bit_x[k] = (int8_t)hf.bit_x[k];
+        df.bit_y[k] = (int8_t)hf.bit_y[k];
+      }
+      host_codes = hf.codes;
+    } else {
+      std::lock_guard<std::mutex> lk(g_custom_mutex);
+      const CustomFamily &cf = g_custom_families[i - B200AT_NUM_FAMILIES];
+      df.nbits = cf.nbits;
+      df.ncodes = cf.ncodes;
+      df.width_at_border = cf.width_at_border;
+      df.total_width = cf.total_width;
+      df.reversed_border = cf.reversed_border;
+      for (int k = 0; k < cf.nbits; k++) {
+        df.bit_x[k] = cf.bit_x[k];
+        df.bit_y[k] = cf.bit_y[k];
+      }
+      host_codes = cf.codes.data();
     }
-    rc = dev_alloc(h, &h->dev_codes[i], (size_t)hf.ncodes);
-    if (rc == 0 && cudaMemcpy(h->dev_codes[i], hf.codes, sizeof(unsigned long long) * hf.ncodes, cudaMemcpyHostToDevice) != cudaSuccess)
+    df.index = i;
+    rc = dev_alloc(h, &h->dev_codes[i], (size_t)df.ncodes);
+    if (rc == 0 && cudaMemcpy(h->dev_codes[i], host_codes, sizeof(unsigned long long) * df.ncodes, cudaMemcpyHostToDevice) != cudaSuccess)
       rc = B200AT_ERR_CUDA;
     df.codes = h->dev_codes[i];
-    if (hf.width_at_border < min_tag_width) min_tag_width = hf.width_at_border;
-    fp.normal_border |= !hf.reversed_border;
-    fp.reversed_border |= hf.reversed_border;
+    if (df.width_at_border < min_tag_width) min_tag_width = df.width_at_border;
+    fp.normal_border |= !df.reversed_border;
+    fp.reversed_border |= df.reversed_border;
   }
   if (qd > 1) min_tag_width = (int)(min_tag_width / qd);
   if (min_tag_width < 3) min_tag_width = 3;

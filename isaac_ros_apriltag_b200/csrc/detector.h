@@ -21,13 +21,13 @@
 
 namespace b200at {
 
-constexpr int kMaxFamilies = B200AT_NUM_FAMILIES;
+constexpr int kMaxFamilies = B200AT_MAX_FAMILIES;
 constexpr int kMaxBits = 52;
 constexpr int kMaxNMaxima = 12;  // upper bound of the max_nmaxima option (pair tables live in shared memory)
 
 struct DevFamily {
   int nbits, ncodes, width_at_border, total_width, reversed_border, index;
-  uint8_t bit_x[kMaxBits], bit_y[kMaxBits];
+  int8_t bit_x[kMaxBits], bit_y[kMaxBits];  // relative to the border; negative / >= width_at_border = outside it
   const unsigned long long *codes;  // device pointer
 };
 

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
+#include <fstream>
 #include <map>
 #include <sstream>
 
@@ -47,6 +49,48 @@ int ToB200Family(FamilyId f) {
     default: return -1;
   }
 }
+// The five families the reference's VPI strategy lists but whose code tables this build cannot derive offline
+// (circle21h7, circle49h12, custom48h12, standard41h12, standard52h13) are read from $B200AT_FAMILY_PATH/<family>.txt when the file
+// exists -- the fields of upstream's tag<Family>.c as whitespace-separated text:
+//   nbits ncodes width_at_border total_width reversed_border   bit_x[nbits]   bit_y[nbits]   codes[ncodes] (hex)
+// -- and registered in slot B200AT_FAM_CUSTOM0.  Returns the family bit index, or -1.
+int LoadFamilyFile(const std::string &name) {
+  const char *dir = std::getenv("B200AT_FAMILY_PATH");
+  if (!dir) return -1;
+  std::ifstream f(std::string(dir) + "/" + name + ".txt");
+  if (!f) return -1;
+  long nbits = 0, ncodes = 0, wab = 0, tw = 0, rev = 0;
+  if (!(f >> nbits >> ncodes >> wab >> tw >> rev) || nbits < 1 || nbits > 64 || ncodes < 1 || ncodes > (1 << 20)) return -1;
+  std::vector<int8_t> bx(nbits), by(nbits);
+  std::vector<uint64_t> codes(ncodes);
+  for (long i = 0; i < nbits; i++) {
+    long v;
+    if (!(f >> v)) return -1;
+    bx[i] = (int8_t)v;
+  }
+  for (long i = 0; i < nbits; i++) {
+    long v;
+    if (!(f >> v)) return -1;
+    by[i] = (int8_t)v;
+  }
+  for (long i = 0; i < ncodes; i++) {
+    std::string tok;
+    if (!(f >> tok)) return -1;
+    codes[i] = std::strtoull(tok.c_str(), nullptr, 16);
+  }
+  b200AprilTagsFamilyDesc_t d;
+  d.struct_size = sizeof(d);
+  d.nbits = (uint32_t)nbits;
+  d.ncodes = (uint32_t)ncodes;
+  d.width_at_border = (uint32_t)wab;
+  d.total_width = (uint32_t)tw;
+  d.reversed_border = rev ? 1u : 0u;
+  d.bit_x = bx.data();
+  d.bit_y = by.data();
+  d.codes = codes.data();
+  return b200AprilTagsRegisterFamily(B200AT_FAM_CUSTOM0, &d) == 0 ? (int)B200AT_FAM_CUSTOM0 : -1;
+}
+
 // apriltag_node.cpp:76-82
 int ToB200Encoding(const std::string &enc) {
   if (enc == "rgb8") return B200AT_ENC_RGB8;
@@ -230,10 +274,12 @@ struct AprilTagNodeCore::VPIAprilTagImpl : AprilTagNodeCore::AprilTagImpl {
 
   void Initialize(const AprilTagNodeCore &node, const ImageView &image, const CameraInfo &camera_info) override {
     AprilTagImpl::Initialize(node, image, camera_info);
-    const int fam = ToB200Family(tag_family_);
+    int fam = ToB200Family(tag_family_);
+    if (fam < 0) fam = LoadFamilyFile(tag_family_str_);
     if (fam < 0) {
       initialized_ = false;
-      throw std::runtime_error("Failed to create AprilTag detector: no code table for family '" + tag_family_str_ + "' in this build");
+      throw std::runtime_error("Failed to create AprilTag detector: no code table for family '" + tag_family_str_ +
+                               "' in this build (supply one as $B200AT_FAMILY_PATH/" + tag_family_str_ + ".txt)");
     }
     const int enc = ToB200Encoding(image.encoding);
     if (enc < 0) {

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <thread>
 #include <unordered_map>
+#include <string>
 #include <vector>
 
 #include "tag_families_data.inc"
@@ -39,20 +40,34 @@ struct Family {
   const char *name;
   int nbits, h, ncodes, width_at_border, total_width;
   bool reversed_border;
-  const unsigned char *bit_x, *bit_y;
+  const signed char *bit_x, *bit_y;  // relative to the border's first cell: negative / >= width_at_border = outside the border
   const unsigned long long *codes;
 };
 
 const Family kFamilies[ATO_NUM_FAMILIES] = {
     {"tag36h11", tag36h11_nbits, tag36h11_h, tag36h11_ncodes, tag36h11_width_at_border, tag36h11_total_width, false,
-     tag36h11_bit_x, tag36h11_bit_y, tag36h11_codes},
+     (const signed char *)tag36h11_bit_x, (const signed char *)tag36h11_bit_y, tag36h11_codes},
     {"tag25h9", tag25h9_nbits, tag25h9_h, tag25h9_ncodes, tag25h9_width_at_border, tag25h9_total_width, false,
-     tag25h9_bit_x, tag25h9_bit_y, tag25h9_codes},
+     (const signed char *)tag25h9_bit_x, (const signed char *)tag25h9_bit_y, tag25h9_codes},
     {"tag16h5", tag16h5_nbits, tag16h5_h, tag16h5_ncodes, tag16h5_width_at_border, tag16h5_total_width, false,
-     tag16h5_bit_x, tag16h5_bit_y, tag16h5_codes},
+     (const signed char *)tag16h5_bit_x, (const signed char *)tag16h5_bit_y, tag16h5_codes},
     {"tag36h10", tag36h10_nbits, tag36h10_h, tag36h10_ncodes, tag36h10_width_at_border, tag36h10_total_width, false,
-     tag36h10_bit_x, tag36h10_bit_y, tag36h10_codes},
+     (const signed char *)tag36h10_bit_x, (const signed char *)tag36h10_bit_y, tag36h10_codes},
 };
+
+// Families registered at run time (ato_register_family): the same upstream tag family struct, filled by the caller -- how the
+// families without a built-in table (upstream tagStandard41h12.c, tagCircle21h7.c, ...: reversed border, bits outside the border) are
+// supplied, and what the parity tests use for a synthetic reversed-border family.
+struct CustomFamily {
+  Family f{};
+  std::string name;
+  std::vector<signed char> bx, by;
+  std::vector<unsigned long long> codes;
+  bool used = false;
+};
+CustomFamily g_custom[ATO_MAX_FAMILIES - ATO_NUM_FAMILIES];
+
+const Family &family_at(int f) { return f < ATO_NUM_FAMILIES ? kFamilies[f] : g_custom[f - ATO_NUM_FAMILIES].f; }
 
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -1705,9 +1720,9 @@ int detect(Detector &D, const uint8_t *im_orig, int width, int height, int strid
   bool normal_border = false, reversed_border = false;
   int min_tag_width = 1000000;
   for (int f : D.fams) {
-    if (kFamilies[f].width_at_border < min_tag_width) min_tag_width = kFamilies[f].width_at_border;
-    normal_border |= !kFamilies[f].reversed_border;
-    reversed_border |= kFamilies[f].reversed_border;
+    if (family_at(f).width_at_border < min_tag_width) min_tag_width = family_at(f).width_at_border;
+    normal_border |= !family_at(f).reversed_border;
+    reversed_border |= family_at(f).reversed_border;
   }
   if (D.prm.quad_decimate > 1) min_tag_width = (int)(min_tag_width / D.prm.quad_decimate);
   if (min_tag_width < 3) min_tag_width = 3;
@@ -1744,7 +1759,7 @@ int detect(Detector &D, const uint8_t *im_orig, int width, int height, int strid
     if (D.prm.refine_edges) refine_edges(D, im_orig, width, height, stride, &q);
     if (quad_update_homographies(&q) != 0) continue;
     for (int f : D.fams) {
-      const Family &family = kFamilies[f];
+      const Family &family = family_at(f);
       if (family.reversed_border != q.reversed_border) continue;
       DecodeEntry entry;
       float decision_margin = quad_decode(D, family, im_orig, width, height, stride, &q, &entry);
@@ -1839,8 +1854,8 @@ void ato_default_params(ato_params_t *p) {
 void *ato_create(const ato_params_t *p) {
   Detector *D = new Detector();
   D->prm = *p;
-  for (int f = 0; f < ATO_NUM_FAMILIES; f++)
-    if (p->family_mask & (1u << f)) D->fams.push_back(f);
+  for (int f = 0; f < ATO_MAX_FAMILIES; f++)
+    if ((p->family_mask & (1u << f)) && (f < ATO_NUM_FAMILIES || g_custom[f - ATO_NUM_FAMILIES].used)) D->fams.push_back(f);
   return D;
 }
 void ato_destroy(void *h) { delete (Detector *)h; }
@@ -1976,13 +1991,26 @@ int ato_detect_batch_enc(const ato_params_t *p, const uint8_t *frames, int enc, 
 
 uint64_t ato_rotate90(uint64_t w, int nbits) { return rotate90(w, nbits); }
 int ato_family_info(int fam, int *nbits, int *ncodes, int *width_at_border, int *total_width) {
-  if (fam < 0 || fam >= ATO_NUM_FAMILIES) return -1;
-  *nbits = kFamilies[fam].nbits;
-  *ncodes = kFamilies[fam].ncodes;
-  *width_at_border = kFamilies[fam].width_at_border;
-  *total_width = kFamilies[fam].total_width;
+  if (fam < 0 || fam >= ATO_MAX_FAMILIES || (fam >= ATO_NUM_FAMILIES && !g_custom[fam - ATO_NUM_FAMILIES].used)) return -1;
+  *nbits = family_at(fam).nbits;
+  *ncodes = family_at(fam).ncodes;
+  *width_at_border = family_at(fam).width_at_border;
+  *total_width = family_at(fam).total_width;
   return 0;
 }
-uint64_t ato_family_code(int fam, int idx) { return kFamilies[fam].codes[idx]; }
+uint64_t ato_family_code(int fam, int idx) { return family_at(fam).codes[idx]; }
+
+int ato_register_family(int slot, const char *name, int nbits, int ncodes, int width_at_border, int total_width, int reversed_border,
+                        const signed char *bit_x, const signed char *bit_y, const uint64_t *codes) {
+  if (slot < ATO_NUM_FAMILIES || slot >= ATO_MAX_FAMILIES || nbits < 1 || nbits > 64 || ncodes < 1 || !bit_x || !bit_y || !codes) return -1;
+  CustomFamily &c = g_custom[slot - ATO_NUM_FAMILIES];
+  c.name = name ? name : "custom";
+  c.bx.assign(bit_x, bit_x + nbits);
+  c.by.assign(bit_y, bit_y + nbits);
+  c.codes.assign(codes, codes + ncodes);
+  c.f = Family{c.name.c_str(), nbits, 0, ncodes, width_at_border, total_width, reversed_border != 0, c.bx.data(), c.by.data(), c.codes.data()};
+  c.used = true;
+  return 0;
+}
 
 }  // extern "C"

@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-enum { ATO_FAM_36H11 = 0, ATO_FAM_25H9 = 1, ATO_FAM_16H5 = 2, ATO_FAM_36H10 = 3, ATO_NUM_FAMILIES = 4 };
+enum { ATO_FAM_36H11 = 0, ATO_FAM_25H9 = 1, ATO_FAM_16H5 = 2, ATO_FAM_36H10 = 3, ATO_NUM_FAMILIES = 4,
+       ATO_FAM_CUSTOM0 = 4, ATO_FAM_CUSTOM1 = 5, ATO_MAX_FAMILIES = 6 /* slots 4, 5: ato_register_family */ };
 
 /* apriltag_detector_create() defaults (upstream apriltag.c) */
 typedef struct {
@@ -111,6 +112,10 @@ int ato_detect_batch_enc(const ato_params_t *p, const uint8_t *frames, int enc, 
 uint64_t ato_rotate90(uint64_t w, int nbits);
 int ato_family_info(int fam, int *nbits, int *ncodes, int *width_at_border, int *total_width);
 uint64_t ato_family_code(int fam, int idx);
+/* registers a family in slot ATO_FAM_CUSTOM0 / 1 (upstream apriltag_family_t fields; bit coordinates relative to the border's first
+ * cell, signed); detectors created afterwards with that family_mask bit use it.  0 on success. */
+int ato_register_family(int slot, const char *name, int nbits, int ncodes, int width_at_border, int total_width, int reversed_border,
+                        const signed char *bit_x, const signed char *bit_y, const uint64_t *codes);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libapriltag_oracle.so")
 
-FAMILY_NAMES = ["tag36h11", "tag25h9", "tag16h5", "tag36h10"]
+FAMILY_NAMES = ["tag36h11", "tag25h9", "tag16h5", "tag36h10", "custom0", "custom1"]
 ENCODINGS = {"mono8": 0, "rgb8": 1, "bgr8": 2, "rgba8": 3, "bgra8": 4}
 
 
@@ -89,8 +89,21 @@ def lib():
         L.ato_family_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4
         L.ato_family_code.argtypes = [C.c_int, C.c_int]
         L.ato_family_code.restype = C.c_uint64
+        L.ato_register_family.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def register_family(slot, fam):
+    """fam: dict with nbits, width_at_border, total_width, reversed_border, bit_x, bit_y, codes (isaac_ros_apriltag_b200.families layout);
+    slot 4 or 5 ("custom0" / "custom1")."""
+    bx = np.asarray(fam["bit_x"], np.int8)
+    by = np.asarray(fam["bit_y"], np.int8)
+    codes = np.asarray(fam["codes"], np.uint64)
+    rc = lib().ato_register_family(slot, FAMILY_NAMES[slot].encode(), int(fam["nbits"]), len(codes), int(fam["width_at_border"]),
+                                   int(fam["total_width"]), int(bool(fam.get("reversed_border", False))), bx.ctypes.data, by.ctypes.data,
+                                   codes.ctypes.data)
+    assert rc == 0, rc
 
 
 def default_params(families=("tag36h11",), **kw):

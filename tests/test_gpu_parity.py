@@ -249,6 +249,65 @@ def test_pol_golden_through_cuapriltags_abi(pu):
     n2.close()
 
 
+def test_registered_reversed_border_family(pu):
+    """b200AprilTagsRegisterFamily with a synthetic REVERSED-BORDER family (tag36h11's codes and bit layout, white border ring on a
+    black surround -- the polarity of upstream's tagStandard* / tagCircle* / tagCustom* families, whose tables are not built in):
+    exercises fit_quad's polarity gate, refine_edges' flipped normals, quad_decode's polarity check and, with a normal family
+    registered beside it, the per-family polarity filter (apriltag.c: `if (family->reversed_border != quad->reversed_border)`)."""
+    from isaac_ros_apriltag_b200 import capi, families as F, synth
+    from oracle import oracle as O
+    fam = dict(F.families()["tag36h11"])
+    fam["reversed_border"] = True
+    F.add_family("custom0", fam)
+    capi.register_family(4, fam)
+    O.register_family(4, fam)
+    rng = np.random.default_rng(9)
+    g, truth = synth.make_frame(rng, 960, 720, [("custom0", 5), ("custom0", 77), ("tag36h11", 5)], side_px=(100, 170), max_tilt_deg=25)
+    for fams, want in ((("custom0",), [(4, 5), (4, 77)]), (("tag36h11", "custom0"), [(0, 5), (4, 5), (4, 77)]), (("tag36h11",), [(0, 5)])):
+        rep = []
+        res, gd = pu.compare_stages(np.stack([g, g[::-1].copy()]), "mono8", fams, report=rep)
+        assert_exact(res, rep)
+        assert sorted((int(d["family"]), int(d["id"])) for d in gd[0] if d["hamming"] == 0) == want, fams
+    # argument validation of the registration entry point
+    with pytest.raises(capi.B200ATError):
+        capi.register_family(2, fam)          # built-in slots cannot be overwritten
+    bad = dict(fam)
+    bad["bit_x"] = [9] * fam["nbits"]          # outside the tag
+    with pytest.raises(capi.B200ATError):
+        capi.register_family(5, bad)
+    with pytest.raises(capi.B200ATError):
+        capi.Detector(640, 480, families=("custom1",))  # an unregistered slot is UNSUPPORTED at create
+
+
+def test_node_loads_a_family_table_file(pu, tmp_path, monkeypatch):
+    """The node's non-CUDA strategy accepts the nine family names of apriltag_node.cpp:47-58; for the five without a built-in table it
+    reads $B200AT_FAMILY_PATH/<family>.txt (the fields of upstream's tag<Family>.c).  Mechanism test with a synthetic reversed-border
+    table under the name custom48h12: detections are published with that family string and tf child frame."""
+    needs_real_gpu(pu)
+    import torch
+    from isaac_ros_apriltag_b200 import families as F, node, synth
+    fam = dict(F.families()["tag36h11"])
+    fam["reversed_border"] = True
+    F.add_family("custom0", fam)
+    with open(tmp_path / "custom48h12.txt", "w") as f:
+        f.write(f"{fam['nbits']} {len(fam['codes'])} {fam['width_at_border']} {fam['total_width']} 1\n")
+        f.write(" ".join(str(v) for v in fam["bit_x"]) + "\n" + " ".join(str(v) for v in fam["bit_y"]) + "\n")
+        f.write("\n".join(hex(c) for c in fam["codes"]) + "\n")
+    g, truth = synth.make_frame(np.random.default_rng(9), 960, 720, [("custom0", 5), ("custom0", 77)], side_px=(100, 170), max_tilt_deg=25)
+    t = torch.from_numpy(g).cuda()
+    K = synth.default_K(960, 720)
+    n = node.AprilTagNode(tag_family="custom48h12", backends="CPU")
+    with pytest.raises(RuntimeError, match="no code table for family"):
+        n.on_frame("mono8", 960, 720, 960, t.data_ptr(), K)   # no B200AT_FAMILY_PATH: the create error of the first frame
+    n.close()
+    monkeypatch.setenv("B200AT_FAMILY_PATH", str(tmp_path))
+    n = node.AprilTagNode(tag_family="custom48h12", backends="CPU")
+    dets = n.on_frame("mono8", 960, 720, 960, t.data_ptr(), K)
+    assert sorted(d["id"] for d in dets) == [5, 77] and all(d["family"] == "custom48h12" for d in dets)
+    assert sorted(d["child_frame_id"] for d in dets) == ["custom48h12:5", "custom48h12:77"]
+    n.close()
+
+
 def test_multi_tag_frame_through_cuapriltags_abi_and_node(pu):
     """Ten tags in one frame through cuAprilTagsDetect (array of cuAprilTagsID_t: 88-byte stride, CUDA's 8-byte aligned float2) and
     through both node strategies: every entry, not only the first, carries the id / corners / pose of the batch entry point."""
