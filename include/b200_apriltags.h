@@ -190,6 +190,27 @@ int b200AprilTagsCreate(cuAprilTagsHandle *h, uint32_t img_width, uint32_t img_h
 
 int b200AprilTagsSetInputEncoding(cuAprilTagsHandle h, int32_t encoding);
 
+/* Fused pre-stage (the reference's "AprilTag Graph" puts a rectify node and a resize node in front of the detector,
+ * README.md:16-29, launch/isaac_ros_apriltag_usb_cam.launch.py:43-63): with a rectification set, the frames handed to the
+ * DEVICE-pointer entry points (cuAprilTagsDetect, b200AprilTagsDetectBatch / EnqueueBatch) are RAW camera frames of
+ * src_width x src_height in the handle's input encoding; one kernel undistorts, rectifies, resizes and converts them to gray into
+ * an internal img_width x img_height image (the size the handle was created for), and detection runs on that.  The map is
+ * OpenCV's initUndistortRectifyMap: for every output pixel (u, v): [x y w] = R^T * P^-1 * [u v 1]; distortion
+ * (k1, k2, p1, p2, k3, k4, k5, k6: plumb_bob / rational_polynomial of sensor_msgs/CameraInfo) ; source = K * distorted point;
+ * bilinear interpolation of the gray values of the four source pixels, constant 0 outside the source.  A resize is a P with scaled
+ * focal lengths / principal point.  Detections (corners, centre, pose) are in the rectified output image, as in the reference's
+ * graph; pass P's intrinsics to the create call.  NULL disables.  The host-buffer entry points return B200AT_ERR_UNSUPPORTED
+ * while a rectification is set. */
+typedef struct {
+  uint32_t struct_size;   /* sizeof(b200AprilTagsRectify_t) */
+  uint32_t src_width, src_height;
+  double K[9];            /* raw camera matrix, row major */
+  double D[8];            /* k1 k2 p1 p2 k3 k4 k5 k6 (unused = 0) */
+  double R[9];            /* rectification rotation, row major (identity for a monocular camera) */
+  double P[9];            /* camera matrix of the rectified (and resized) output, row major (the 3x3 part of CameraInfo.p) */
+} b200AprilTagsRectify_t;
+int b200AprilTagsSetRectification(cuAprilTagsHandle h, const b200AprilTagsRectify_t *rect);
+
 /* Batch detect on DEVICE frames.  dets_out: HOST [n_frames][max_tags] (may be NULL), ids_out: HOST
  * [n_frames][max_tags] cuAprilTagsID_t (may be NULL), counts: HOST [n_frames].  Synchronous. */
 int b200AprilTagsDetectBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,
@@ -244,7 +265,8 @@ enum {
   B200AT_BUF_POINTS,        /* u64 sort keys per kept point (slope bits | y | x), cluster-contiguous, sorted */
   B200AT_BUF_QUADS,         /* records b200AprilTagsQuadRec_t, all frames */
   B200AT_BUF_QUADS_REFINED, /* same records after rescale + refine_edges */
-  B200AT_BUF_POINTS_RAW     /* u32 packed points as emitted: x | y<<14 | gx code<<28 | gy code<<30, cluster-contiguous */
+  B200AT_BUF_POINTS_RAW,    /* u32 packed points as emitted: x | y<<14 | gx code<<28 | gy code<<30, cluster-contiguous */
+  B200AT_BUF_RECTIFIED      /* u8  [H][W] gray output of the rectify / resize pre-stage (only with a rectification set) */
 };
 typedef struct {
   uint64_t key;

@@ -19,12 +19,12 @@ BPP = {"mono8": 1, "rgb8": 3, "bgr8": 3, "rgba8": 4, "bgra8": 4}
 ERRORS = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NOMEM", 5: "OVERFLOW", 6: "NO_DEVICE"}
 STAGES = ["preprocess", "threshold", "ccl", "cluster", "quadfit", "decode", "finalize", "d2h"]
 (BUF_DECIMATED, BUF_TILE_MIN, BUF_TILE_MAX, BUF_THRESHOLD, BUF_LABELS, BUF_SIZES, BUF_CLUSTERS, BUF_POINTS, BUF_QUADS,
- BUF_QUADS_REFINED, BUF_POINTS_RAW) = range(11)
+ BUF_QUADS_REFINED, BUF_POINTS_RAW, BUF_RECTIFIED) = range(12)
 
 # every symbol include/b200_apriltags.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED_SYMBOLS = [
     "nvCreateAprilTagsDetector", "cuAprilTagsDetect", "cuAprilTagsDestroy",
-    "b200AprilTagsDefaultOptions", "b200AprilTagsRegisterFamily", "b200AprilTagsCreate", "b200AprilTagsSetInputEncoding", "b200AprilTagsDetectBatch",
+    "b200AprilTagsDefaultOptions", "b200AprilTagsRegisterFamily", "b200AprilTagsCreate", "b200AprilTagsSetInputEncoding", "b200AprilTagsSetRectification", "b200AprilTagsDetectBatch",
     "b200AprilTagsDetectBatchHost", "b200AprilTagsEnqueueBatchHost", "b200AprilTagsCollectBatchHost", "b200AprilTagsEnqueueBatch", "b200AprilTagsCollectBatch", "b200AprilTagsLastStatus",
     "b200AprilTagsEnableStageTiming", "b200AprilTagsGetStageTimes", "b200AprilTagsGetCounters", "b200AprilTagsGetDims",
     "b200AprilTagsReadBuffer", "b200AprilTagsVersion",
@@ -75,6 +75,11 @@ class FamilyDesc(C.Structure):  # b200AprilTagsFamilyDesc_t
                 ("codes", C.c_void_p)]
 
 
+class Rectify(C.Structure):  # b200AprilTagsRectify_t
+    _fields_ = [("struct_size", C.c_uint32), ("src_width", C.c_uint32), ("src_height", C.c_uint32), ("K", C.c_double * 9),
+                ("D", C.c_double * 8), ("R", C.c_double * 9), ("P", C.c_double * 9)]
+
+
 class Frame(C.Structure):  # b200AprilTagsFrame_t
     _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_size_t)]
 
@@ -117,6 +122,7 @@ def lib():
         L.b200AprilTagsRegisterFamily.argtypes = [C.c_int32, C.POINTER(FamilyDesc)]
         L.b200AprilTagsCreate.argtypes = [C.POINTER(vp), u32, u32, C.POINTER(Intrinsics), C.c_float, C.POINTER(Options)]
         L.b200AprilTagsSetInputEncoding.argtypes = [vp, C.c_int32]
+        L.b200AprilTagsSetRectification.argtypes = [vp, C.POINTER(Rectify)]
         L.b200AprilTagsDetectBatch.argtypes = [vp, C.POINTER(Frame), u32, vp, vp, vp, vp]
         L.b200AprilTagsDetectBatchHost.argtypes = [vp, C.POINTER(Frame), u32, vp, vp, vp]
         L.b200AprilTagsEnqueueBatchHost.argtypes = [vp, C.POINTER(Frame), u32]
@@ -254,6 +260,23 @@ class Detector:
             raise B200ATError(rc, "b200AprilTagsCollectBatchHost")
         return [dets[i, :counts[i]].copy() for i in range(n)]
 
+    def set_rectification(self, src_width, src_height, K, D, R, P):
+        """Fused rectify / resize pre-stage for the device-pointer entry points (include/b200_apriltags.h); None for K disables."""
+        if K is None:
+            rc = lib().b200AprilTagsSetRectification(self.h, None)
+        else:
+            r = Rectify()
+            r.struct_size = C.sizeof(Rectify)
+            r.src_width, r.src_height = int(src_width), int(src_height)
+            r.K[:] = [float(v) for v in np.asarray(K).reshape(-1)]
+            d = list(np.asarray(D, float).reshape(-1)) + [0.0] * 8
+            r.D[:] = d[:8]
+            r.R[:] = [float(v) for v in np.asarray(R).reshape(-1)]
+            r.P[:] = [float(v) for v in np.asarray(P).reshape(-1)]
+            rc = lib().b200AprilTagsSetRectification(self.h, C.byref(r))
+        if rc != 0:
+            raise B200ATError(rc, "b200AprilTagsSetRectification")
+
     def status(self):
         s = C.c_uint32()
         lib().b200AprilTagsLastStatus(self.h, C.byref(s))
@@ -282,7 +305,9 @@ class Detector:
         wd, hd, tw, th = self.dims()
         n = C.c_size_t()
         lib().b200AprilTagsReadBuffer(self.h, which, frame, None, 0, C.byref(n))
-        if which in (BUF_DECIMATED, BUF_THRESHOLD):
+        if which == BUF_RECTIFIED:
+            out = np.empty((self.height, self.width), np.uint8)
+        elif which in (BUF_DECIMATED, BUF_THRESHOLD):
             out = np.empty((hd, wd), np.uint8)
         elif which in (BUF_TILE_MIN, BUF_TILE_MAX):
             out = np.empty((th, tw), np.uint8)

@@ -132,6 +132,7 @@ struct cuAprilTagsHandle_st {
               ev_tail[2] = {nullptr, nullptr}, ev_backdone[2] = {nullptr, nullptr};
   bool sparse_bufs = false;            // need1 / need2 / src_frames / quad_H allocated
   uint32_t sparse_skip = 0;            // calls left on the full copy after a sparse call that fetched nearly every row anyway
+  float2 *rect_map_buf = nullptr;      // rectify / resize pre-stage: the map's device buffer (ws.rect_map points at it while enabled)
   HostCall calls[2];                   // up to two host calls in flight
   HostPendingBack pending_back;        // BACK of the last sub-batch queued so far (queued after the next FRONT, or at collect)
   uint64_t host_k = 0, host_seq = 0;   // global sub-batch / call counters
@@ -624,6 +625,85 @@ int b200AprilTagsSetInputEncoding(cuAprilTagsHandle h, int32_t enc) {
   return B200AT_OK;
 }
 
+int b200AprilTagsSetRectification(cuAprilTagsHandle h, const b200AprilTagsRectify_t *r) {
+  if (!h || h->in_flight || h->calls[0].active || h->calls[1].active) return B200AT_ERR_INVALID_ARG;
+  if (r && (r->struct_size != sizeof(*r) || r->src_width == 0 || r->src_height == 0 || r->src_width > 16382 || r->src_height > 16382))
+    return B200AT_ERR_INVALID_ARG;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->graph_exec) {  // the cached graph was captured without / with another pre-stage
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  Workspace &ws = h->ws;
+  const Geo &g = ws.g;
+  int rc = B200AT_OK;
+  if (!r) {
+    ws.rect_map = nullptr;  // (buffers stay allocated for the next SetRectification)
+  } else {
+    const size_t npx = (size_t)g.W * g.H;
+    if (!h->rect_map_buf) {
+      ws.rect_pitch = (g.W + 15) & ~15;
+      rc = dev_alloc(h, &h->rect_map_buf, npx);
+      if (rc == 0) rc = dev_alloc(h, &ws.rect_img, (size_t)h->max_batch * g.H * ws.rect_pitch);
+      if (rc == 0) rc = dev_alloc(h, &ws.rect_frames, h->max_batch);
+      if (rc == 0) {
+        std::vector<FrameDesc> tab(h->max_batch);
+        for (uint32_t i = 0; i < h->max_batch; i++) {
+          tab[i].ptr = ws.rect_img + (size_t)i * g.H * ws.rect_pitch;
+          tab[i].pitch = (unsigned long long)ws.rect_pitch;
+        }
+        if (cudaMemcpy(ws.rect_frames, tab.data(), sizeof(FrameDesc) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      }
+    }
+    if (rc == 0) {
+      // OpenCV initUndistortRectifyMap in double, evaluated directly per pixel (oracle/rectify.py restates exactly this sequence)
+      double A[9], iR[9];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) A[i * 3 + j] = r->P[i * 3 + 0] * r->R[0 * 3 + j] + r->P[i * 3 + 1] * r->R[1 * 3 + j] + r->P[i * 3 + 2] * r->R[2 * 3 + j];
+      const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+      if (det == 0) rc = B200AT_ERR_INVALID_ARG;
+      const double id = 1.0 / det;
+      iR[0] = (A[4] * A[8] - A[5] * A[7]) * id;
+      iR[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+      iR[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+      iR[3] = (A[5] * A[6] - A[3] * A[8]) * id;
+      iR[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+      iR[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+      iR[6] = (A[3] * A[7] - A[4] * A[6]) * id;
+      iR[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+      iR[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+      const double fx = r->K[0], fy = r->K[4], u0 = r->K[2], v0 = r->K[5];
+      const double k1 = r->D[0], k2 = r->D[1], p1 = r->D[2], p2 = r->D[3], k3 = r->D[4], k4 = r->D[5], k5 = r->D[6], k6 = r->D[7];
+      std::vector<float2> map(rc == 0 ? npx : 0);
+      for (int v = 0; v < g.H && rc == 0; v++) {
+        for (int u = 0; u < g.W; u++) {
+          const double X = u * iR[0] + v * iR[1] + iR[2], Y = u * iR[3] + v * iR[4] + iR[5], Wq = u * iR[6] + v * iR[7] + iR[8];
+          const double w = 1.0 / Wq, x = X * w, y = Y * w;
+          const double x2 = x * x, y2 = y * y, r2 = x2 + y2, xy2 = 2 * x * y;
+          const double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2);
+          const double xd = x * kr + p1 * xy2 + p2 * (r2 + 2 * x2);
+          const double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * xy2;
+          float2 m;
+          m.x = (float)(fx * xd + u0);
+          m.y = (float)(fy * yd + v0);
+          map[(size_t)v * g.W + u] = m;
+        }
+      }
+      if (rc == 0 && cudaMemcpy(h->rect_map_buf, map.data(), sizeof(float2) * npx, cudaMemcpyHostToDevice) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      if (rc == 0) {
+        ws.rect_map = h->rect_map_buf;
+        ws.rect_src_w = (int)r->src_width;
+        ws.rect_src_h = (int)r->src_height;
+      }
+    }
+  }
+  if (prev != h->device) cudaSetDevice(prev);
+  return rc;
+}
+
 int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable) {
   if (!h) return B200AT_ERR_INVALID_ARG;
   h->timing = enable != 0;
@@ -636,7 +716,7 @@ int b200AprilTagsEnableStageTiming(cuAprilTagsHandle h, int enable) {
 static int fill_frame_table(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, FrameDesc *hf, int *fast_out) {
   const Geo &g = h->ws.g;
   int fast = 1;
-  const size_t min_pitch = (size_t)g.W * g.bpp;
+  const size_t min_pitch = (size_t)(h->ws.rect_map ? h->ws.rect_src_w : g.W) * g.bpp;  // (with a rectification set the frames are the raw ones)
   for (uint32_t i = 0; i < n; i++) {
     if (!frames[i].ptr || frames[i].pitch < min_pitch) return B200AT_ERR_INVALID_ARG;
     hf[i].ptr = (const uint8_t *)frames[i].ptr;
@@ -758,6 +838,27 @@ static int enqueue_core(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames,
 #define STAMP(i) \
   if (tm) cudaEventRecord(h->ev[i], stream)
   STAMP(0);
+  // rectify / resize pre-stage: raw frames -> internal gray frames; everything after it sees mono8 frames of the handle's size
+  struct RectScope {
+    Workspace &w;
+    FrameDesc *frames;
+    int enc, bpp, fast;
+    bool on;
+    ~RectScope() {
+      if (!on) return;
+      w.frames = frames;
+      w.g.enc = enc;
+      w.g.bpp = bpp;
+      w.g.fast_align = fast;
+    }
+  } rect_scope{ws, ws.frames, g.enc, g.bpp, g.fast_align, ws.rect_map != nullptr};
+  if (rect_scope.on) {
+    launches += launch_rectify(ws, (int)n, stream);
+    ws.frames = ws.rect_frames;
+    g.enc = B200AT_ENC_MONO8;
+    g.bpp = 1;
+    g.fast_align = 1;
+  }
   launches += launch_preprocess(ws, (int)n, stream);
   STAMP(1);
   launches += launch_threshold(ws, (int)n, stream);
@@ -1121,6 +1222,7 @@ int host_call_buffers(HostCall &c, uint32_t n, uint32_t nsub, uint32_t mt) {
 
 int host_enqueue(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n) {
   const Geo &g = h->ws.g;
+  if (h->ws.rect_map) return B200AT_ERR_UNSUPPORTED;  // the rectify pre-stage takes device frames (include/b200_apriltags.h)
   const uint32_t mt = g.max_tags;
   const size_t row = (size_t)g.W * g.bpp;
   // ---- everything that can fail on the arguments is checked before anything is queued ----
@@ -1420,7 +1522,8 @@ static cudaStream_t resolve_sync_stream(cuAprilTagsHandle h, cudaStream_t stream
 uint32_t cuAprilTagsDetect(cuAprilTagsHandle h, const cuAprilTagsImageInput_t *img, cuAprilTagsID_t *tags_out, uint32_t *num_tags,
                            const uint32_t max_tags, cudaStream_t stream) {
   if (!h || !img || !tags_out || !num_tags) return B200AT_ERR_INVALID_ARG;
-  if (img->width != h->ws.g.W || img->height != h->ws.g.H) return B200AT_ERR_INVALID_ARG;
+  if (h->ws.rect_map ? (img->width != h->ws.rect_src_w || img->height != h->ws.rect_src_h) : (img->width != h->ws.g.W || img->height != h->ws.g.H))
+    return B200AT_ERR_INVALID_ARG;
   if (h->ws.g.bpp != 3) return B200AT_ERR_INVALID_ARG;  // the uchar3 entry point carries rgb8/bgr8 only
   b200AprilTagsFrame_t fr;
   fr.ptr = img->dev_ptr;
@@ -1482,6 +1585,16 @@ int b200AprilTagsReadBuffer(cuAprilTagsHandle h, int which, uint32_t frame, void
     return ((unsigned long long)conv_label((uint32_t)(k >> 32)) << 32) | conv_label((uint32_t)(k & 0xffffffffu));
   };
   switch (which) {
+    case B200AT_BUF_RECTIFIED: {
+      if (!ws.rect_img) {
+        if (prev != h->device) cudaSetDevice(prev);
+        return B200AT_ERR_INVALID_ARG;
+      }
+      n = (size_t)g.W * g.H;
+      if (dst && cap >= n)
+        e = cudaMemcpy2D(dst, g.W, ws.rect_img + (size_t)frame * g.H * ws.rect_pitch, ws.rect_pitch, g.W, g.H, cudaMemcpyDeviceToHost);
+      break;
+    }
     case B200AT_BUF_DECIMATED:
     case B200AT_BUF_THRESHOLD: {
       const uint8_t *src = (which == B200AT_BUF_DECIMATED ? ws.dec : ws.thr) + (size_t)frame * Pp;

@@ -166,6 +166,11 @@ struct Workspace {
   int use_tma;
   cudaStream_t aux[kQuadAux];
   cudaEvent_t ev_fork, ev_join[kQuadAux];
+  // rectify / resize pre-stage: per-pixel source coordinates (shared by all frames: L2-resident), gray output, its frame table
+  const float2 *rect_map;   // [H][W] or nullptr
+  uint8_t *rect_img;        // [B][H][rect_pitch]
+  FrameDesc *rect_frames;   // [B] -> rect_img
+  int rect_pitch, rect_src_w, rect_src_h;
   uint8_t blur_k[32];
   int blur_ksz;
   int blur_sharpen;
@@ -175,6 +180,7 @@ __host__ __device__ inline int at_Wp(const Geo &g) { return (g.Wd + 15) & ~15; }
 __host__ __device__ inline int at_twp(const Geo &g) { return g.tw > 0 ? g.tw : 1; }    // tile-array pitch
 
 // ---- launchers (each returns the number of kernel launches it issued) ----
+int launch_rectify(const Workspace &ws, int nframes, cudaStream_t s);     // raw frames (ws.frames) -> ws.rect_img
 int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s);
 int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s);

@@ -436,6 +436,45 @@ int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s) {
   return launches;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Rectify / resize / colour->gray pre-stage (b200AprilTagsSetRectification): one thread per output pixel, source coordinates from
+// the precomputed map (initUndistortRectifyMap semantics, computed on the host in double, stored as float like OpenCV's
+// CV_32FC1 maps; 8 B / pixel shared by every frame of the batch, so it stays in L2), gray = the boundary's fixed-point luma at the
+// four taps, bilinear weights in float in the order the oracle (oracle/rectify.py) uses, border constant 0.
+// Algorithmic bytes per frame: 4 taps x bpp gathered (mostly the same sectors) + 1 B written per output pixel.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rectify(Geo g, const FrameDesc *__restrict__ frames, const float2 *__restrict__ map,
+                                                 uint8_t *__restrict__ out, int out_pitch, int src_w, int src_h) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int fr = blockIdx.z;
+  if (x >= g.W) return;
+  const FrameDesc fd = frames[fr];
+  const float2 m = map[(size_t)y * g.W + x];
+  const float fx0 = floorf(m.x), fy0 = floorf(m.y);
+  const float ax = m.x - fx0, ay = m.y - fy0;
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  auto tap = [&](int xx, int yy) -> float {
+    if (xx < 0 || yy < 0 || xx >= src_w || yy >= src_h) return 0.0f;
+    return (float)gray_generic(fd.ptr + (size_t)yy * fd.pitch, xx, g.enc, g.bpp);
+  };
+  float v = 0.0f;
+  if (m.x > -1.0f && m.y > -1.0f && m.x < (float)src_w && m.y < (float)src_h) {  // (also false for NaN)
+    const float g00 = tap(x0, y0), g01 = tap(x0 + 1, y0), g10 = tap(x0, y0 + 1), g11 = tap(x0 + 1, y0 + 1);
+    const float top = g00 * (1.0f - ax) + g01 * ax;
+    const float bot = g10 * (1.0f - ax) + g11 * ax;
+    v = top * (1.0f - ay) + bot * ay;
+  }
+  out[(size_t)fr * g.H * out_pitch + (size_t)y * out_pitch + x] = (uint8_t)(int)(v + 0.5f);
+}
+
+int launch_rectify(const Workspace &ws, int nframes, cudaStream_t s) {
+  const Geo &g = ws.g;
+  dim3 grd((g.W + 255) / 256, g.H, nframes);
+  k_rectify<<<grd, 256, 0, s>>>(g, ws.frames, ws.rect_map, ws.rect_img, ws.rect_pitch, ws.rect_src_w, ws.rect_src_h);
+  return 1;
+}
+
 int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
   const int Wp = at_Wp(g), twp = at_twp(g);
