@@ -6,8 +6,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
-#include <fstream>
 #include <map>
 #include <sstream>
 
@@ -57,26 +57,32 @@ int ToB200Family(FamilyId f) {
 int LoadFamilyFile(const std::string &name) {
   const char *dir = std::getenv("B200AT_FAMILY_PATH");
   if (!dir) return -1;
-  std::ifstream f(std::string(dir) + "/" + name + ".txt");
+  // (C stdio on purpose: this library is loaded into processes that carry other C++ runtimes -- e.g. Python extension modules --
+  // and iostream's locale facets do not survive two of them)
+  FILE *f = std::fopen((std::string(dir) + "/" + name + ".txt").c_str(), "r");
   if (!f) return -1;
+  struct Closer {
+    FILE *f;
+    ~Closer() { std::fclose(f); }
+  } closer{f};
   long nbits = 0, ncodes = 0, wab = 0, tw = 0, rev = 0;
-  if (!(f >> nbits >> ncodes >> wab >> tw >> rev) || nbits < 1 || nbits > 64 || ncodes < 1 || ncodes > (1 << 20)) return -1;
+  if (std::fscanf(f, "%ld %ld %ld %ld %ld", &nbits, &ncodes, &wab, &tw, &rev) != 5 || nbits < 1 || nbits > 64 || ncodes < 1 || ncodes > (1 << 20)) return -1;
   std::vector<int8_t> bx(nbits), by(nbits);
   std::vector<uint64_t> codes(ncodes);
   for (long i = 0; i < nbits; i++) {
     long v;
-    if (!(f >> v)) return -1;
+    if (std::fscanf(f, "%ld", &v) != 1) return -1;
     bx[i] = (int8_t)v;
   }
   for (long i = 0; i < nbits; i++) {
     long v;
-    if (!(f >> v)) return -1;
+    if (std::fscanf(f, "%ld", &v) != 1) return -1;
     by[i] = (int8_t)v;
   }
   for (long i = 0; i < ncodes; i++) {
-    std::string tok;
-    if (!(f >> tok)) return -1;
-    codes[i] = std::strtoull(tok.c_str(), nullptr, 16);
+    char tok[64];
+    if (std::fscanf(f, "%63s", tok) != 1) return -1;
+    codes[i] = std::strtoull(tok, nullptr, 16);
   }
   b200AprilTagsFamilyDesc_t d;
   d.struct_size = sizeof(d);
