@@ -212,7 +212,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from isaac_ros_apriltag_b200 import capi
+    from isaac_ros_apriltag_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -267,13 +267,12 @@ def main():
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = ev0.elapsed_time(ev1)
-    tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
+    # the sharding module's rule (tests/test_sharding_gloo.py runs the same two functions at world size 2 on gloo): the slowest
+    # rank's device time defines the step, `value` = frames all ranks processed / that time
+    ms_local = ev0.elapsed_time(ev1)
+    ms_total = sharding.max_over_ranks(ms_local, "cuda")
     ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1e3)
+    value = sharding.whole_job_throughput(B * args.steps, ms_local / 1e3, "cuda")
     counters = det.counters()
     # per-stage device times (CUDA events between the stages): measured on extra, UNPIPELINED steps outside the timed
     # region -- with stage timing on, the library runs the batch as one chunk so the stages do not overlap
@@ -323,11 +322,7 @@ def main():
                 for _ in range(e2e_steps):
                     r = det.detect_host(hb)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            te = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dt = float(te.item())
+            dt = sharding.max_over_ranks(time.perf_counter() - t0, "cuda")
             c = det.counters()
             os.environ.pop("B200AT_SPARSE_H2D", None)
             return {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(c["h2d_bytes"]),
@@ -350,12 +345,9 @@ def main():
                 for _ in range(3):
                     dst.copy_(host_batch, non_blocking=True)
             cs.synchronize()
-            dt = time.perf_counter() - t0
-            te = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dt = sharding.max_over_ranks(time.perf_counter() - t0, "cuda")
             del dst
-            return world * 3 * host_batch.numel() / float(te.item()) / 1e9
+            return world * 3 * host_batch.numel() / dt / 1e9
 
         e2e = measure_e2e(None, True)
         e2e["h2d_ceiling_gbs"] = h2d_ceiling()
