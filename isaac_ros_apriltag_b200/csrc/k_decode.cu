@@ -247,7 +247,6 @@ __device__ __forceinline__ void rescale_quad(const FitParams &fp, const QuadRec 
 // ---- a12: refine_edges (one warp; every lane ends with the same refined corners) ----
 __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
                                                   int o2, bool is_bgr, bool reversed, int lane, float p[4][2]) {
-  constexpr int NPOS = 33;  // probe positions held in registers: quad_decimate <= 2 (range <= 3: 25 steps + 8)
   double lines[4][4];
   const double range = (double)(fp.quad_decimate + 1.0f);
   const int nsteps = (int)floor(2.0 * range / 0.25) + 1;
@@ -274,36 +273,7 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
         double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
         double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
         double Mn = 0, Mcount = 0;
-        if (nsteps + 8 <= NPOS) {
-          // Step k compares the pixels at x0 + (n + 1) * normal and x0 + (n - 1) * normal, n = -range + k / 4: the two probe
-          // positions of all steps are the nsteps + 8 points t_j = -range - 1 + j / 4 (g2 of step k is j = k, g1 is j = k + 8; the
-          // products (n +- 1) * nx are the same doubles either way).  Every position is gathered ONCE (33 gathers instead of 50
-          // for quad_decimate 2), all of them independent loads, then the steps are consumed in order.
-          uint32_t gp[(NPOS + 3) / 4] = {};  // gray values packed four to a register
-          unsigned long long okm = 0;
-#pragma unroll
-          for (int j = 0; j < NPOS; j++) {
-            const double t = -range - 1.0 + 0.25 * j;
-            const int xx = (int)(x0 + t * nx);
-            const int yy = (int)(y0 + t * ny);
-            const bool ok = j < nsteps + 8 && !(xx < 0 || xx >= width || yy < 0 || yy >= height);
-            okm |= ok ? (1ull << j) : 0ull;
-            // unconditional loads from clamped (always valid) coordinates keep the gathers independent
-            gp[j >> 2] |= (uint32_t)gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, ok ? xx : 0, ok ? yy : 0) << (8 * (j & 3));
-          }
-#pragma unroll
-          for (int k = 0; k < NPOS - 8; k++) {
-            if (k >= nsteps || !((okm >> k) & 1ull) || !((okm >> (k + 8)) & 1ull)) continue;
-            const int g1 = (int)((gp[(k + 8) >> 2] >> (8 * ((k + 8) & 3))) & 0xffu), g2 = (int)((gp[k >> 2] >> (8 * (k & 3))) & 0xffu);
-            if (g1 < g2) continue;
-            const double n = -range + 0.25 * k;
-            const double weight = (double)((g2 - g1) * (g2 - g1));
-            Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
-            Mcount += weight;
-          }
-        } else
-        // (quad_decimate > 2: more positions than the register array holds) the pixel gathers of 8 steps are issued together
-        // (independent loads), then consumed in step order
+        // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
         for (int k0 = 0; k0 < nsteps; k0 += 8) {
           int g1[8], g2[8];
           bool okk[8];
@@ -318,6 +288,7 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
             const int y2 = (int)(y0 + (n - grange) * ny);
             okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
                      !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
+            // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
             g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
             g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
           }
@@ -378,6 +349,65 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
       p[i][1] = (float)(lines[i][1] + L0 * A10);
     }
   }
+}
+
+// ---- a12, opt-in variant (decode_pair=1): refine_edges with two short edges per pass ----
+// one sample point of an edge: search along the normal for the strongest step (returns 0 if no pixel pair qualified)
+__device__ __forceinline__ int refine_sample(const FrameDesc &fd, int width, int height, int bpp, int o1, int o2, bool is_bgr, float pax,
+                                             float pay, float pbx, float pby, double nx, double ny, int s, int nsamples, double range,
+                                             int nsteps, double *bestx, double *besty) {
+  double alpha = (1.0 + s) / (nsamples + 1);
+  double x0 = alpha * pax + (1 - alpha) * pbx;
+  double y0 = alpha * pay + (1 - alpha) * pby;
+  double Mn = 0, Mcount = 0;
+  // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
+  for (int k0 = 0; k0 < nsteps; k0 += 8) {
+    int g1[8], g2[8];
+    bool okk[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int k = k0 + u;
+      const double n = -range + 0.25 * k;
+      const double grange = 1;
+      const int x1 = (int)(x0 + (n + grange) * nx);
+      const int y1 = (int)(y0 + (n + grange) * ny);
+      const int x2 = (int)(x0 + (n - grange) * nx);
+      const int y2 = (int)(y0 + (n - grange) * ny);
+      okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) && !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
+      // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
+      g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
+      g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (!okk[u] || g1[u] < g2[u]) continue;
+      const double n = -range + 0.25 * (k0 + u);
+      const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
+      Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
+      Mcount += weight;
+    }
+  }
+  if (Mcount == 0) return 0;
+  double n0 = Mn / Mcount;
+  *bestx = x0 + n0 * nx;
+  *besty = y0 + n0 * ny;
+  return 1;
+}
+
+// line through the refined sample points of one edge: centroid + normal direction (float trigonometry as upstream)
+__device__ __forceinline__ void refine_line(double Mx, double My, double Mxx, double Mxy, double Myy, double N, double line[4]) {
+  double Ex = Mx / N, Ey = My / N;
+  double Cxx = Mxx / N - Ex * Ex;
+  double Cxy = Mxy / N - Ex * Ey;
+  double Cyy = Myy / N - Ey * Ey;
+  // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
+  float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
+  double normal_theta = .5 * th;
+  float nth = (float)normal_theta;
+  line[0] = Ex;
+  line[1] = Ey;
+  line[2] = (double)(float)cos((double)nth);
+  line[3] = (double)(float)sin((double)nth);
 }
 
 // ---- a13: homography of the (refined) corners; false = quad dropped (singular system / zero determinant) ----

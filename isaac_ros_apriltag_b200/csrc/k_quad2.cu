@@ -34,8 +34,6 @@ struct MaxRec {  // one local maximum of the smoothed window error, written by k
 };
 static_assert(sizeof(MaxRec) == 64, "MaxRec layout");
 
-enum { QS_MERGE = 0, QS_BITONIC = 1, QS_RADIX = 2 };  // k_qf_sort's sort
-
 // chunk c of nch of a cluster of n sorted points: [s, e)
 __device__ __forceinline__ void qf_chunk_bounds(int n, int nch, int c, int &s, int &e) {
   s = (int)((long long)c * n / nch);
@@ -105,13 +103,12 @@ __device__ __forceinline__ void qf_register_work(uint32_t ci, int sz, bool rever
 }
 
 // Clusters of at most THREADS * E points.
-// SORT = QS_BITONIC (one-warp clusters): the warp sorts its 32 * E keys in registers (warp_bitonic_sort) and never touches shared
-//   memory.  Measured (profiles/r03_variants.md): the network wins only at E = 4 (n <= 128); from E = 8 on its O(log^2) stages cost
-//   more instructions than the merge sort.
-// SORT = QS_MERGE: ITEMS keys sorted per thread, then merge-path passes in shared memory (sort_keys).
-// SORT = QS_RADIX (multi-warp clusters): four passes of an 8-bit LSD radix sort on (slope, y << 16 | x) pairs (radix_sort_pairs).
+// BIT: the warp sorts its 32 * E keys in registers (bitonic network, warp_bitonic_sort) -- one-warp clusters then never touch
+// shared memory.  Measured (profiles/r03_quadfit_sort.md): the network wins only at E = 4 (n <= 128); from E = 8 on its
+// O(log^2) stages cost more instructions than the shared-memory merge sort (ITEMS keys sorted per thread, then merge-path
+// passes), which is what the larger bins use.
 // WPC > 1 (one-warp clusters): WPC independent cluster workers per CTA, one warp each, no block-wide barrier anywhere.
-template <int THREADS, int E, int ITEMS, int MINB, int WPC, int SORT>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC, bool BIT>
 __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
               const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, const uint8_t *__restrict__ dec,
@@ -119,9 +116,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
               uint32_t *__restrict__ counters, int Wp) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
-  static_assert(SORT != QS_BITONIC || THREADS == 32, "the register network sorts one warp's keys");
-  static_assert(SORT != QS_RADIX || (THREADS > 32 && WPC == 1), "the radix sort is the multi-warp sort");
-  extern __shared__ unsigned long long dsm_sort[];  // [WPC][2 * NCAP] (QS_RADIX: the same bytes as four u32 arrays + the counters)
+  extern __shared__ unsigned long long dsm_sort[];  // [WPC][2 * NCAP] unless the sort stays in registers
   const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
   unsigned long long *skeys = dsm_sort + (size_t)grp * 2 * NCAP, *stmp = skeys + NCAP;
   __shared__ BBoxRed s_red[NW];
@@ -160,33 +155,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
       if (tid == 0) qinfo[ci] = 0u;
       continue;
     }
-    if (SORT == QS_RADIX) {
-      uint32_t *ka = reinterpret_cast<uint32_t *>(dsm_sort), *pa = ka + NCAP, *kb = pa + NCAP, *pb = kb + NCAP, *cnt = pb + NCAP;
-#pragma unroll
-      for (int k = 0; k < E; k++) {
-        const int i = wbase + k * 32 + lane;
-        if (i < sz) {
-          const unsigned long long key = slope_key(pr[k], cx, cy);
-          ka[i] = (uint32_t)(key >> 32);
-          pa[i] = (uint32_t)key;
-        }
-      }
-      __syncthreads();
-      radix_sort_pairs<THREADS>(ka, pa, kb, pb, cnt, sz, tid);
-      // sorted points out: y << 16 | x with the squared gradient magnitude of the decimated image at the point in the upper half
-      // (compute_lfps' weight is sqrt of it, + 1); four gathers in flight per thread
-      for (int i = tid; i < sz; i += 4 * THREADS) {
-        uint32_t yx[4];
-        int g2[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) yx[u] = (i + u * THREADS < sz) ? pa[i + u * THREADS] : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; u++) g2[u] = (i + u * THREADS < sz) ? grad2_at(im, Wp, g.Wd, g.Hd, (unsigned long long)yx[u]) : 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (unsigned long long)yx[u] | ((unsigned long long)(uint32_t)g2[u] << 32);
-      }
-    } else if (SORT == QS_BITONIC) {
+    if (BIT && NW == 1) {
       unsigned long long v[E];
 #pragma unroll
       for (int k = 0; k < E; k++) v[k] = (k * 32 + lane < sz) ? slope_key(pr[k], cx, cy) : ~0ull;
@@ -789,11 +758,11 @@ static int device_index() {
   return dev >= 0 && dev < 64 ? dev : 0;
 }
 
-template <int THREADS, int E, int ITEMS, int MINB, int WPC, int SORT>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC, bool BIT>
 static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t st) {
   const Geo &g = ws.g;
-  constexpr size_t smem = SORT == QS_BITONIC ? 0 : (size_t)2 * THREADS * E * 8 * WPC + (SORT == QS_RADIX ? (size_t)(THREADS / 32) * 256 * 4 : 0);
-  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC, SORT>;
+  constexpr size_t smem = (BIT && THREADS == 32) ? 0 : (size_t)2 * THREADS * E * 8 * WPC;
+  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC, BIT>;
   static int ctas_per_sm[64] = {};
   const int dev = device_index();
   if (!ctas_per_sm[dev]) {
@@ -821,21 +790,13 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
   k_qf_sort_global<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 7, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo, ws.qwbase, ws.qwork,
                                           ws.qwork_cap, ws.counters, at_Wp(g));                 // n > 8192 (4K-class frames)
-  if (getenv("B200AT_QF_RADIX") == nullptr || atoi(getenv("B200AT_QF_RADIX")) != 0) {  // (A/B switch while measuring)
-    launch_sort_bin<512, 16, 16, 1, 1, QS_RADIX>(ws, 6, sms, ws.aux[0]);  // n <= 8192
-    launch_sort_bin<256, 16, 16, 3, 1, QS_RADIX>(ws, 5, sms, ws.aux[1]);  // n <= 4096
-    launch_sort_bin<256, 8, 8, 4, 1, QS_RADIX>(ws, 4, sms, ws.aux[2]);    // n <= 2048
-    launch_sort_bin<128, 8, 8, 8, 1, QS_RADIX>(ws, 3, sms, ws.aux[3]);    // n <= 1024
-    launch_sort_bin<64, 8, 8, 16, 1, QS_RADIX>(ws, 2, sms, ws.aux[4]);    // n <= 512
-  } else {
-    launch_sort_bin<512, 16, 16, 1, 1, QS_MERGE>(ws, 6, sms, ws.aux[0]);
-    launch_sort_bin<256, 16, 16, 3, 1, QS_MERGE>(ws, 5, sms, ws.aux[1]);
-    launch_sort_bin<256, 8, 8, 4, 1, QS_MERGE>(ws, 4, sms, ws.aux[2]);
-    launch_sort_bin<128, 8, 8, 8, 1, QS_MERGE>(ws, 3, sms, ws.aux[3]);
-    launch_sort_bin<64, 8, 8, 16, 1, QS_MERGE>(ws, 2, sms, ws.aux[4]);
-  }
-  launch_sort_bin<32, 8, 8, 4, 8, QS_MERGE>(ws, 1, sms, ws.aux[5]);       // n <= 256: one warp per cluster, 8 workers per CTA
-  launch_sort_bin<32, 4, 4, 4, 8, QS_BITONIC>(ws, 0, sms, ws.aux[6]);     // n <= 128: registers only
+  launch_sort_bin<512, 16, 16, 1, 1, false>(ws, 6, sms, ws.aux[0]);  // n <= 8192
+  launch_sort_bin<256, 16, 16, 3, 1, false>(ws, 5, sms, ws.aux[1]);  // n <= 4096
+  launch_sort_bin<256, 8, 8, 4, 1, false>(ws, 4, sms, ws.aux[2]);    // n <= 2048
+  launch_sort_bin<128, 8, 8, 8, 1, false>(ws, 3, sms, ws.aux[3]);    // n <= 1024
+  launch_sort_bin<64, 8, 8, 16, 1, false>(ws, 2, sms, ws.aux[4]);    // n <= 512
+  launch_sort_bin<32, 8, 8, 4, 8, false>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
+  launch_sort_bin<32, 4, 4, 4, 8, true>(ws, 0, sms, ws.aux[6]);      // n <= 128: registers only
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);

@@ -396,133 +396,6 @@ __device__ __forceinline__ void merge_runs(unsigned long long *a, unsigned long 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Shared-memory LSD radix sort of (32-bit key, 32-bit payload) pairs, 8-bit digits, THREADS / 32 warps (k_quad2.cu, clusters of more
-// than 512 points).  The merge sort above makes log2(n / ITEMS) passes whose inner loops are chains of dependent shared-memory
-// loads with data-dependent branches (binary search, two-way merge); this makes FOUR passes of straight-line code.  Stability --
-// LSD needs it -- comes from the ranking: warp w owns the contiguous segment w of the array and walks it 32 elements at a time;
-// an element's destination is (keys with a smaller digit) + (same digit in earlier warps) + (same digit earlier in this warp's
-// walk: a running counter per warp and digit) + (same digit in lower lanes of this step: __match_any_sync).  Two sweeps per pass:
-// count, block scan over the 256 x NW counters (digit major, warp minor), scatter.
-// The sorted pairs end in (ka, pa).  cnt: [THREADS / 32][256].
-// ---------------------------------------------------------------------------------------------------------------------
-template <int THREADS>
-__device__ __forceinline__ void radix_sort_pairs(uint32_t *ka, uint32_t *pa, uint32_t *kb, uint32_t *pb, uint32_t *cnt, int n, int tid) {
-  constexpr int NW = THREADS / 32;
-  static_assert(THREADS >= 256 || 256 % THREADS == 0, "the scan assigns 256 / THREADS digits to a thread");
-  constexpr int DPT = THREADS >= 256 ? 1 : 256 / THREADS;  // digits per thread in the scan
-  __shared__ uint32_t s_wsum[NW];
-  const int lane = tid & 31, wid = tid >> 5;
-  const int seg = ((n + NW * 32 - 1) / (NW * 32)) * 32;  // elements per warp segment (a multiple of 32)
-  const int s0 = wid * seg, s1 = min(n, s0 + seg);
-  uint32_t *mycnt = cnt + wid * 256;
-  uint32_t *src_k = ka, *src_p = pa, *dst_k = kb, *dst_p = pb;
-#pragma unroll 1
-  for (int shift = 0; shift < 32; shift += 8) {
-    for (int d = lane; d < 256; d += 32) mycnt[d] = 0;
-    __syncwarp();
-    // ---- sweep 1: digit counts of my segment ----
-    for (int i0 = s0; i0 < s1; i0 += 32) {
-      const int i = i0 + lane;
-      const bool has = i < s1;
-      const unsigned act = __ballot_sync(0xffffffffu, has);
-      if (has) {
-        const uint32_t d = (src_k[i] >> shift) & 0xffu;
-        const unsigned peers = __match_any_sync(act, d);
-        if (lane == __ffs(peers) - 1) mycnt[d] += (uint32_t)__popc(peers);
-      }
-      __syncwarp();
-    }
-    __syncthreads();
-    // ---- scan: cnt[w][d] <- number of keys that precede the first key of (digit d, warp w) ----
-    {
-      uint32_t tot[DPT];
-      uint32_t mine = 0;
-#pragma unroll
-      for (int q = 0; q < DPT; q++) {
-        const int d = tid * DPT + q;
-        uint32_t t = 0;
-        if (d < 256) {
-#pragma unroll
-          for (int w = 0; w < NW; w++) {
-            const uint32_t c = cnt[w * 256 + d];
-            cnt[w * 256 + d] = t;  // exclusive over the warps, relative to the digit's base
-            t += c;
-          }
-        }
-        tot[q] = t;
-        mine += t;
-      }
-      // exclusive scan of `mine` over the threads that hold digits (tid < 256 / DPT)
-      uint32_t incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
-      }
-      if (lane == 31) s_wsum[wid] = incl;
-      __syncthreads();
-      uint32_t wbase = 0;
-#pragma unroll
-      for (int w = 0; w < NW; w++) wbase += w < wid ? s_wsum[w] : 0u;
-      uint32_t run = wbase + incl - mine;
-#pragma unroll
-      for (int q = 0; q < DPT; q++) {
-        const int d = tid * DPT + q;
-        if (d < 256) {
-#pragma unroll
-          for (int w = 0; w < NW; w++) cnt[w * 256 + d] += run;
-        }
-        run += tot[q];
-      }
-    }
-    __syncthreads();
-    // ---- sweep 2: scatter (running counters of my warp advance step by step) ----
-    for (int i0 = s0; i0 < s1; i0 += 32) {
-      const int i = i0 + lane;
-      const bool has = i < s1;
-      const unsigned act = __ballot_sync(0xffffffffu, has);
-      if (has) {
-        const uint32_t k = src_k[i], p = src_p[i];
-        const uint32_t d = (k >> shift) & 0xffu;
-        const unsigned peers = __match_any_sync(act, d);
-        const uint32_t pos = mycnt[d] + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        dst_k[pos] = k;
-        dst_p[pos] = p;
-        __syncwarp(act);
-        if (lane == __ffs(peers) - 1) mycnt[d] += (uint32_t)__popc(peers);
-      }
-      __syncwarp();
-    }
-    __syncthreads();
-    uint32_t *t = src_k;
-    src_k = dst_k;
-    dst_k = t;
-    t = src_p;
-    src_p = dst_p;
-    dst_p = t;
-  }
-  // four passes: the result is back in (ka, pa).  Keys that tie on all 32 bits are still in arrival order: order each run of equal
-  // keys by payload (the thread at the run's first element; runs are rare and short -- equal float slopes)
-  for (int i = tid; i < n; i += THREADS) {
-    const uint32_t k = ka[i];
-    if ((i == 0 || ka[i - 1] != k) && i + 1 < n && ka[i + 1] == k) {
-      int e = i + 1;
-      while (e < n && ka[e] == k) e++;
-      for (int a = i + 1; a < e; a++) {
-        const uint32_t v = pa[a];
-        int b = a - 1;
-        while (b >= i && pa[b] > v) {
-          pa[b + 1] = pa[b];
-          b--;
-        }
-        pa[b + 1] = v;
-      }
-    }
-  }
-  __syncthreads();
-}
-
 // squared gradient magnitude of the decimated image at the (half-resolution) point of a sorted key; 0 on the image
 // border, where the reference uses weight 1 = sqrt(0) + 1
 __device__ __forceinline__ int grad2_at(const uint8_t *__restrict__ im, int Wp, int Wd, int Hd, unsigned long long k) {
