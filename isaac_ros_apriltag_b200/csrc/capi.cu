@@ -60,6 +60,7 @@ Tune parse_tune() {
   Tune t;
   t.ccl_tma = 1;
   t.qf_exact = 0;
+  for (int i = 0; i < 8; i++) t.x[i] = 0;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -75,6 +76,7 @@ Tune parse_tune() {
     const int v = atoi(kv.c_str() + eq + 1);
     if (k == "ccl_tma") t.ccl_tma = v;
     else if (k == "qf_exact") t.qf_exact = v;
+    else if (k.size() == 2 && k[0] == 'x' && k[1] >= '0' && k[1] <= '7') t.x[k[1] - '0'] = v;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   return t;

@@ -124,6 +124,7 @@ struct Tune {
                   // and the pipeline is then TMA-free)
   int qf_exact;   // 1 = k_quad.cu (one CTA per cluster, serial prefix sums: float corners bit-identical to the CPU oracle);
                   // 0 (default) = k_quad2.cu (sort / windowed moments / tail: same formulas, prefix sums associated differently)
+  int x[8];       // x0..x7: A/B switches of the variant being measured (development only; 0 = default)
 };
 
 struct Workspace {

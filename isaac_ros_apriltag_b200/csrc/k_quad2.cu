@@ -103,23 +103,38 @@ __device__ __forceinline__ void qf_register_work(uint32_t ci, int sz, bool rever
 }
 
 // Clusters of at most THREADS * E points.
-// BIT: the warp sorts its 32 * E keys in registers (bitonic network, warp_bitonic_sort) -- one-warp clusters then never touch
-// shared memory.  Measured (profiles/r03_quadfit_sort.md): the network wins only at E = 4 (n <= 128); from E = 8 on its
-// O(log^2) stages cost more instructions than the shared-memory merge sort (ITEMS keys sorted per thread, then merge-path
-// passes), which is what the larger bins use.
+// MODE 2 (default): ANGULAR BUCKET SORT.  The sort key is an angle around the bounding-box centre, so a monotone map of the key
+// (key_bucket) spreads the cluster over NB >= n / 2 buckets of a few points each: one shared-memory histogram pass (the atomic's
+// return value is the point's arrival rank in its bucket), one scan of the NB counters, one scatter, and then every point finds
+// its final position by counting the smaller keys of its own bucket -- a loop of ~m independent loads and compares (median
+// largest bucket of a cluster on the bench frames: 7 points) instead of log2(n) merge passes of chained loads.  Points of
+// neighbouring positions sit in the same or adjacent buckets: the loop's loads are broadcasts.  Any monotone bucket map gives the
+// same final order (unique 64-bit keys); a degenerate outline (all points at one angle: a bucket of more than kBucketLimit
+// points) falls back to the merge sort in global memory.  Shared memory: 10 B per point instead of 16.
+// MODE 1: the warp sorts its 32 * E keys in registers (bitonic network, warp_bitonic_sort), no shared memory.
+// MODE 0: shared-memory merge sort (ITEMS keys sorted per thread, then merge-path passes).
 // WPC > 1 (one-warp clusters): WPC independent cluster workers per CTA, one warp each, no block-wide barrier anywhere.
-template <int THREADS, int E, int ITEMS, int MINB, int WPC, bool BIT>
+constexpr int kBucketLimit = 1024;
+template <int THREADS, int E, int MODE, int WPC>
+__host__ __device__ constexpr size_t qf_sort_smem() {
+  return MODE == 1 ? 0 : MODE == 0 ? (size_t)2 * THREADS * E * 8 * WPC : ((size_t)THREADS * E * 8 + (size_t)(THREADS * E / 2 + 2) * 4) * WPC;
+}
+
+template <int THREADS, int E, int ITEMS, int MINB, int WPC, int MODE>
 __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
-              const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, const uint8_t *__restrict__ dec,
-              uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work, uint32_t work_cap,
-              uint32_t *__restrict__ counters, int Wp) {
+              const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
+              const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work,
+              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
-  extern __shared__ unsigned long long dsm_sort[];  // [WPC][2 * NCAP] unless the sort stays in registers
+  static_assert(MODE != 1 || NW == 1, "register sort: one-warp clusters only");
+  extern __shared__ unsigned long long dsm_sort[];  // per worker: MODE 0 [2 * NCAP] keys; MODE 2 [NCAP] keys + [NCAP / 2 + 2] counters
   const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
-  unsigned long long *skeys = dsm_sort + (size_t)grp * 2 * NCAP, *stmp = skeys + NCAP;
+  unsigned long long *skeys = dsm_sort + (size_t)grp * (qf_sort_smem<THREADS, E, MODE == 1 ? 0 : MODE, 1>() / 8), *stmp = skeys + NCAP;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(stmp);  // MODE 2: bucket counters, then bucket start offsets
   __shared__ BBoxRed s_red[NW];
+  __shared__ uint32_t s_ws[WPC][NW], s_wm[WPC][NW];
   __shared__ int s_cluster_a[WPC];
   const int tid = WPC > 1 ? (int)(threadIdx.x % THREADS) : (int)threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t nbin = min(counters[CNT_BIN0 + bin], g.clu_cap);
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
       if (tid == 0) qinfo[ci] = 0u;
       continue;
     }
-    if (BIT && NW == 1) {
+    if (MODE == 1) {
       unsigned long long v[E];
 #pragma unroll
       for (int k = 0; k < E; k++) v[k] = (k * 32 + lane < sz) ? slope_key(pr[k], cx, cy) : ~0ull;
@@ -169,6 +184,89 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
 #pragma unroll
       for (int k = 0; k < E; k++)
         if (lane * E + k < sz) keys_g[lane * E + k] = (v[k] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[k] << 32);
+    } else if (MODE == 2) {
+      int NB = 32;
+      while (NB * 2 < sz) NB <<= 1;  // power of two, n / 2 <= NB <= NCAP / 2 (NCAP >= 64)
+      const float nbq = (float)(NB / 4);
+      for (int i = tid; i < NB; i += THREADS) cnt[i] = 0u;
+      unsigned long long v[E];
+#pragma unroll
+      for (int k = 0; k < E; k++) v[k] = slope_key(pr[k], cx, cy);
+      cta_sync<THREADS>();
+      // histogram: the atomic's return value is the point's arrival rank inside its bucket
+      uint32_t ba[E];
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        ba[k] = 0u;
+        if (wbase + k * 32 + lane < sz) {
+          const uint32_t b = (uint32_t)key_bucket(v[k], nbq, NB);
+          ba[k] = b | (atomicAdd(&cnt[b], 1u) << 16);
+        }
+      }
+      cta_sync<THREADS>();
+      // exclusive scan of the counters in place (thread t owns cpt consecutive counters) + the largest bucket
+      const int cpt = NB >= THREADS ? NB / THREADS : 1;
+      const int c0 = tid * cpt;
+      uint32_t sum = 0, mx = 0;
+      if (c0 < NB)
+        for (int j = 0; j < cpt; j++) {
+          const uint32_t c = cnt[c0 + j];
+          sum += c;
+          mx = max(mx, c);
+        }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+      uint32_t excl = incl - sum;
+      if (NW > 1) {
+        if (lane == 31) s_ws[grp][wid] = incl;
+        if (lane == 0) s_wm[grp][wid] = mx;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+          excl += w < wid ? s_ws[grp][w] : 0u;
+          mx = max(mx, s_wm[grp][w]);
+        }
+      }
+      if (mx > (uint32_t)kBucketLimit) {  // (uniform) degenerate outline: merge sort in global memory, scratch = the cluster's slice of errs
+#pragma unroll
+        for (int k = 0; k < E; k++)
+          if (wbase + k * 32 + lane < sz) keys_g[wbase + k * 32 + lane] = v[k];
+        cta_sync<THREADS>();
+        sort_keys<THREADS, ITEMS, false>(keys_g, reinterpret_cast<unsigned long long *>(errs_pool + (size_t)2 * o), sz, tid);
+        for (int i = tid; i < sz; i += THREADS) {
+          const unsigned long long k = keys_g[i];
+          keys_g[i] = (k & 0xffffffffull) | ((unsigned long long)(uint32_t)grad2_at(im, Wp, g.Wd, g.Hd, k) << 32);
+        }
+      } else {
+        if (c0 < NB)
+          for (int j = 0; j < cpt; j++) {
+            const uint32_t c = cnt[c0 + j];
+            cnt[c0 + j] = excl;
+            excl += c;
+          }
+        if (tid == 0) cnt[NB] = (uint32_t)sz;
+        cta_sync<THREADS>();
+#pragma unroll
+        for (int k = 0; k < E; k++)
+          if (wbase + k * 32 + lane < sz) skeys[cnt[ba[k] & 0xffffu] + (ba[k] >> 16)] = v[k];
+        cta_sync<THREADS>();
+        // final position = bucket start + number of smaller keys in the bucket; sorted points out with their squared gradient
+        for (int i = tid; i < sz; i += THREADS) {
+          const unsigned long long key = skeys[i];
+          const int b = key_bucket(key, nbq, NB);
+          const int s = (int)cnt[b], e = (int)cnt[b + 1];
+          int rank = 0;
+          for (int j = s; j < e; j++) rank += skeys[j] < key ? 1 : 0;
+          const int g2 = grad2_at(im, Wp, g.Wd, g.Hd, key);
+          keys_g[s + rank] = (key & 0xffffffffull) | ((unsigned long long)(uint32_t)g2 << 32);
+        }
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < E; k++) {
@@ -758,11 +856,11 @@ static int device_index() {
   return dev >= 0 && dev < 64 ? dev : 0;
 }
 
-template <int THREADS, int E, int ITEMS, int MINB, int WPC, bool BIT>
+template <int THREADS, int E, int ITEMS, int MINB, int WPC, int MODE>
 static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t st) {
   const Geo &g = ws.g;
-  constexpr size_t smem = (BIT && THREADS == 32) ? 0 : (size_t)2 * THREADS * E * 8 * WPC;
-  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC, BIT>;
+  constexpr size_t smem = qf_sort_smem<THREADS, E, MODE, WPC>();
+  auto kern = k_qf_sort<THREADS, E, ITEMS, MINB, WPC, MODE>;
   static int ctas_per_sm[64] = {};
   const int dev = device_index();
   if (!ctas_per_sm[dev]) {
@@ -771,8 +869,8 @@ static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS * WPC, smem);
     ctas_per_sm[dev] = std::max(1, n);
   }
-  kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.dec, ws.qinfo, ws.qwbase,
-                                                           ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
+  kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo,
+                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
 }
 
 int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
@@ -790,13 +888,23 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
   k_qf_sort_global<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 7, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo, ws.qwbase, ws.qwork,
                                           ws.qwork_cap, ws.counters, at_Wp(g));                 // n > 8192 (4K-class frames)
-  launch_sort_bin<512, 16, 16, 1, 1, false>(ws, 6, sms, ws.aux[0]);  // n <= 8192
-  launch_sort_bin<256, 16, 16, 3, 1, false>(ws, 5, sms, ws.aux[1]);  // n <= 4096
-  launch_sort_bin<256, 8, 8, 4, 1, false>(ws, 4, sms, ws.aux[2]);    // n <= 2048
-  launch_sort_bin<128, 8, 8, 8, 1, false>(ws, 3, sms, ws.aux[3]);    // n <= 1024
-  launch_sort_bin<64, 8, 8, 16, 1, false>(ws, 2, sms, ws.aux[4]);    // n <= 512
-  launch_sort_bin<32, 8, 8, 4, 8, false>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
-  launch_sort_bin<32, 4, 4, 4, 8, true>(ws, 0, sms, ws.aux[6]);      // n <= 128: registers only
+  if (ws.tune.x[0] == 0) {
+    launch_sort_bin<512, 16, 16, 2, 1, 2>(ws, 6, sms, ws.aux[0]);  // n <= 8192
+    launch_sort_bin<256, 16, 16, 4, 1, 2>(ws, 5, sms, ws.aux[1]);  // n <= 4096
+    launch_sort_bin<256, 8, 8, 4, 1, 2>(ws, 4, sms, ws.aux[2]);    // n <= 2048
+    launch_sort_bin<128, 8, 8, 8, 1, 2>(ws, 3, sms, ws.aux[3]);    // n <= 1024
+    launch_sort_bin<64, 8, 8, 16, 1, 2>(ws, 2, sms, ws.aux[4]);    // n <= 512
+    launch_sort_bin<32, 8, 8, 4, 8, 2>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
+    launch_sort_bin<32, 4, 4, 4, 8, 1>(ws, 0, sms, ws.aux[6]);     // n <= 128: register bitonic network (measured: 0.218 vs 0.226 ms)
+  } else {
+    launch_sort_bin<512, 16, 16, 1, 1, 0>(ws, 6, sms, ws.aux[0]);  // n <= 8192
+    launch_sort_bin<256, 16, 16, 3, 1, 0>(ws, 5, sms, ws.aux[1]);  // n <= 4096
+    launch_sort_bin<256, 8, 8, 4, 1, 0>(ws, 4, sms, ws.aux[2]);    // n <= 2048
+    launch_sort_bin<128, 8, 8, 8, 1, 0>(ws, 3, sms, ws.aux[3]);    // n <= 1024
+    launch_sort_bin<64, 8, 8, 16, 1, 0>(ws, 2, sms, ws.aux[4]);    // n <= 512
+    launch_sort_bin<32, 8, 8, 4, 8, 0>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
+    launch_sort_bin<32, 4, 4, 4, 8, 1>(ws, 0, sms, ws.aux[6]);     // n <= 128: registers only
+  }
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);

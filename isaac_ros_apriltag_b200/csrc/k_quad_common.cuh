@@ -289,6 +289,37 @@ __device__ __forceinline__ unsigned long long slope_key(uint32_t p, float cx, fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Angular bucket of a sort key (k_quad2.cu, bucket sort): a NON-DECREASING function of the key's float slope into [0, NB), so
+// that bucket order never contradicts key order -- the final order is decided by full 64-bit key comparisons inside a bucket
+// and is therefore the same total order every other sort produces.  The slope is quadrant base + tan-like ratio r >= 0; the
+// map r -> r / 2 (r <= 1), 1 - 1 / (2 r) (r > 1) is a cheap stand-in for atan that spreads a convex outline over the buckets
+// within a factor of ~2.  Every step (float subtract, correctly rounded divide, add, multiply by a positive constant,
+// truncation) is monotone, so rounding cannot reorder two keys.  nbq = NB / 4.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int key_bucket(unsigned long long key, float nbq, int NB) {
+  const uint32_t ob = (uint32_t)(key >> 32);
+  const float s = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7fffffffu) : ~ob);  // undo float_orderable
+  float qi, Q;
+  if (s < 0.0f) {
+    qi = 0.0f;
+    Q = -65536.0f;
+  } else if (s < 65536.0f) {
+    qi = 1.0f;
+    Q = 0.0f;
+  } else if (s < 131072.0f) {
+    qi = 2.0f;
+    Q = 65536.0f;
+  } else {
+    qi = 3.0f;
+    Q = 131072.0f;
+  }
+  const float r = s - Q;
+  const float t = r <= 1.0f ? 0.5f * r : 1.0f - 0.5f / r;
+  const int b = (int)((qi + t) * nbq);
+  return max(0, min(b, NB - 1));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Register bitonic sort of 32 * E 64-bit keys per warp (k_quad2.cu).  Element i of the warp's chunk lives in lane i / E, register
 // i % E, so the low log2(E) index bits are compare-exchanges between registers (one 64-bit compare = ISETP + ISETP.EX, four
 // SELs per pair) and the five lane bits are shuffles (two SHFLs, the compare, two SELs per key).  Ascending-only network: the
