@@ -502,6 +502,8 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.thr2, B * Pp);
   ALLOC(ws.lab, B * Pp);
   ALLOC(ws.csize, B * Pp);
+  ALLOC(ws.roots, B * Pp);
+  ALLOC(ws.nroots, B);
   ALLOC(ws.hkey, (size_t)B * g.hcap);
   ALLOC(ws.hcnt, (size_t)B * g.hcap);
   ALLOC(ws.hoff, (size_t)B * g.hcap);
@@ -744,6 +746,8 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
   v.tmax += (size_t)f0 * g.th * at_twp(g);
   v.lab += (size_t)f0 * Pp;
   v.csize += (size_t)f0 * Pp;
+  v.roots += (size_t)f0 * Pp;
+  v.nroots += f0;
   v.hkey += (size_t)f0 * g.hcap;
   v.hcnt += (size_t)f0 * g.hcap;
   v.hoff += (size_t)f0 * g.hcap;
@@ -1621,6 +1625,20 @@ int b200AprilTagsReadBuffer(cuAprilTagsHandle h, int which, uint32_t frame, void
         if (e == cudaSuccess && which == B200AT_BUF_LABELS && Wp != (size_t)g.Wd) {
           uint32_t *d = (uint32_t *)dst;
           for (size_t i = 0; i < n; i++) d[i] = conv_label(d[i]);
+        }
+        if (e == cudaSuccess && which == B200AT_BUF_SIZES) {
+          // the device image holds a count at component representatives only (everything else is never written): present it as
+          // "size at the representative, 1 at 127-pixels (AprilRobotics never connects them: singletons), 0 elsewhere"
+          std::vector<uint32_t> lab_h(n);
+          std::vector<uint8_t> thr_h(n);
+          e = cudaMemcpy2D(lab_h.data(), (size_t)g.Wd * 4, ws.lab + (size_t)frame * Pp, Wp * 4, (size_t)g.Wd * 4, g.Hd, cudaMemcpyDeviceToHost);
+          if (e == cudaSuccess) e = cudaMemcpy2D(thr_h.data(), g.Wd, ws.thr + (size_t)frame * Pp, Wp, g.Wd, g.Hd, cudaMemcpyDeviceToHost);
+          uint32_t *d = (uint32_t *)dst;
+          if (e == cudaSuccess)
+            for (size_t i = 0; i < n; i++) {
+              const size_t self = (i / g.Wd) * Wp + (i % g.Wd);
+              d[i] = thr_h[i] == 127 ? 1u : (lab_h[i] == (uint32_t)self ? d[i] : 0u);
+            }
         }
       }
       break;

@@ -120,8 +120,7 @@ struct FitParams {
 // Per-handle knobs, read once from the environment (B200AT_TUNE="key=value,key=value"; see capi.cu).  Every variant that did not
 // win its measurement was deleted (profiles/r03_variants.md); what is left are two real trade-offs.
 struct Tune {
-  int ccl_tma;    // 1 (default) = CCL tiles staged in shared memory by TMA; 0 = no staging (measured 0.16 ms per 256 frames faster,
-                  // and the pipeline is then TMA-free)
+  int ccl_tma;    // 1 (default) = CCL tiles staged in shared memory by TMA; 0 = staged by plain loads (the pipeline is then TMA-free)
   int qf_exact;   // 1 = k_quad.cu (one CTA per cluster, serial prefix sums: float corners bit-identical to the CPU oracle);
                   // 0 (default) = k_quad2.cu (sort / windowed moments / tail: same formulas, prefix sums associated differently)
   int x[8];       // x0..x7: A/B switches of the variant being measured (development only; 0 = default)
@@ -135,6 +134,7 @@ struct Workspace {
   FrameDesc *frames;
   uint8_t *dec, *dec_tmp, *tmin, *tmax, *thr, *thr2;
   uint32_t *lab, *csize;
+  uint32_t *roots, *nroots;  // [B][Hd][Wp] pixel indices of the CCL tile roots of a frame (a list: the first nroots[frame] entries), [B]
   unsigned long long *hkey;
   uint32_t *hcnt, *hoff, *hcur;
   ClusterRec *clusters;
@@ -157,7 +157,7 @@ struct Workspace {
   // windowed quad fit (k_quad2.cu)
   uint32_t *qinfo;             // [clu_cap] 0 = rejected before the sort, else point count | reversed_border << 31
   uint32_t *qwbase;            // [clu_cap] first work item of the cluster (its chunks are consecutive)
-  uint2 *qwork;                // [qwork_cap] (cluster, chunk)
+  uint4 *qwork;                // [qwork_cap] self-contained work items of k_qf_window: (point offset, point count, chunk, cluster)
   uint32_t qwork_cap;
   double *qwtot;               // [qwork_cap][6] moment totals of the chunk
   uint32_t *qwnmax;            // [qwork_cap] local maxima found in the chunk

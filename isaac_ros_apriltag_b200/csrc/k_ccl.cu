@@ -8,7 +8,8 @@
 //                         a run that touches the component above inherits its label, shared-memory unions only where a run
 //                         touches two labels; pixel counts per local root
 //   2. k_ccl_border     : only links that cross tile borders are merged in global memory
-//   3. k_ccl_roots      : the former tile roots (~5 % of the pixels) chase to their global root and hand over their count
+//   3. k_ccl_roots      : the former tile roots (the frame's root list, ~5 % of the pixels) chase to their global root and hand
+//                         over their count
 //   4. k_ccl_flatmark   : one gather per pixel lab[lab[p]], fused with the size gate thr2 (components < 25 px -> 127)
 // Algorithmic bytes per frame: read Pd (thr) + write 4*Pd (labels) = 5*Pd (SURVEY 8d contract figure).
 #include "detector.h"
@@ -115,7 +116,8 @@ constexpr int TSLOT = (TBYTES + 127) & ~127;           // 128-byte aligned slots
 
 template <bool USE_TMA>
 __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
-                                                                      uint32_t *__restrict__ csize, int Wp,
+                                                                      uint32_t *__restrict__ csize, uint32_t *__restrict__ roots,
+                                                                      uint32_t *__restrict__ nroots, int Wp, int variant,
                                                                       const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_t[SWEEP_TILES][TSLOT];
   __shared__ __align__(8) unsigned long long mbar;
@@ -194,169 +196,94 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
       if (n.UL && lane > 0) c2 = pl_l;
       if (n.UR && lane < TW - 1) c3 = pl_r;
     }
-    // segmented min over the run with FULL-mask shuffles: inclusive min-scan from the run's first lane, then the value of its
-    // last lane.  (redux.sync with one member mask per run makes the hardware execute the runs one after the other.)
-    uint32_t rl = min(c1, min(c2, c3));
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t2 = __shfl_up_sync(0xffffffffu, rl, d);
-      if ((int)lane - d >= rs) rl = min(rl, t2);
-    }
-    const int rlast = above ? (__ffs(above) - 2) : 31;  // last lane of my run
-    rl = __shfl_sync(0xffffffffu, rl, rlast);
     const int i = ly * TW + lane;
-    if (rl == NONE) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
-    L[i] = rl;
-    cnt[i] = 0;
-    __syncwarp();
-    // a run that touches several labels makes them equivalent
-    if (c1 != NONE && c1 != rl) unite_s(L, c1, rl);
-    if (c2 != NONE && c2 != rl) unite_s(L, c2, rl);
-    if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
+    uint32_t rl;
+    if (variant & 1) {
+      // segmented min over the run with FULL-mask shuffles: inclusive min-scan from the run's first lane, then the value of its
+      // last lane.  (redux.sync with one member mask per run makes the hardware execute the runs one after the other.)
+      rl = min(c1, min(c2, c3));
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t2 = __shfl_up_sync(0xffffffffu, rl, d);
+        if ((int)lane - d >= rs) rl = min(rl, t2);
+      }
+      const int rlast = above ? (__ffs(above) - 2) : 31;  // last lane of my run
+      rl = __shfl_sync(0xffffffffu, rl, rlast);
+      if (rl == NONE) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
+      L[i] = rl;
+      cnt[i] = 0;
+      __syncwarp();
+      // a run that touches several labels makes them equivalent
+      if (c1 != NONE && c1 != rl) unite_s(L, c1, rl);
+      if (c2 != NONE && c2 != rl) unite_s(L, c2, rl);
+      if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
+    } else {
+      // the run inherits the label of its LEFTMOST upward link (one ballot + one shuffle; any label of the component will do: the
+      // unions below make a run's labels equivalent and the root of a component is its smallest label = its first pixel)
+      const uint32_t mine = min(c1, min(c2, c3));
+      const unsigned linked = __ballot_sync(0xffffffffu, mine != NONE) & run_mask;
+      rl = __shfl_sync(0xffffffffu, mine, linked ? __ffs(linked) - 1 : lane);
+      if (!linked) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
+      L[i] = rl;
+      cnt[i] = 0;
+      __syncwarp();
+      // ONE union site, executed as often as the busiest lane needs it
+      bool n1 = c1 != NONE && c1 != rl, n2 = c2 != NONE && c2 != rl && c2 != c1, n3 = c3 != NONE && c3 != rl && c3 != c1 && c3 != c2;
+      while (__any_sync(0xffffffffu, n1 || n2 || n3)) {
+        if (n1 || n2 || n3) {
+          const uint32_t pick = n1 ? c1 : (n2 ? c2 : c3);
+          if (n1)
+            n1 = false;
+          else if (n2)
+            n2 = false;
+          else
+            n3 = false;
+          unite_s(L, pick, rl);
+        }
+      }
+    }
     if (lane == rs && x < g.Wd && vcur != 127) atomicAdd(&cnt[rl], (uint32_t)__popc(run_mask));
     plab = rl;
   }
   __syncwarp();
   uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
   uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
-  // flatten inside the tile; counts collected at merged labels move to their final local root
-  {
-    for (int ly = 0; ly < rows; ly++) {
-      const int i = ly * TW + lane;
-      const uint32_t r = find_s(L, i);
-      if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
-      const uint32_t c = cnt[i];  // non-zero only at labels; a non-root entry is touched by this lane alone
-      if (r != (uint32_t)i && c) {
-        atomicAdd(&cnt[r], c);
-        cnt[i] = 0;
-      }
-    }
-  }
-  __syncwarp();
-  for (int ly = 0; ly < rows; ly++) {
-    if (x >= g.Wd) break;
-    szf[(size_t)(y0 + ly) * Wp + x] = (t[(ly + 1) * TPITCH + lane + TOFF] == 127) ? 1u : cnt[ly * TW + lane];
-  }
-}
-
-// Occupancy variant of the row sweep (ccl_sweep=4, not measured yet).  The sweep is latency-bound at 20 warps per SM (ncu: 26 %
-// warps active, 50 % issue), and what limits the warps is shared memory: 10.4 KB per tile.  Here the tile is not staged at all
-// -- a lane reads its column's bytes straight from global memory, four rows ahead of their use, neighbours by shuffle, the two
-// halo columns by lanes 0 / 31 -- and the per-label pixel counts are 16-bit halves of shared words (a tile has 1024 pixels):
-// 6 KB per tile, 36 warps per SM.
-__global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep_direct(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
-                                                                             uint32_t *__restrict__ csize, int Wp) {
-  __shared__ uint32_t s_L[SWEEP_TILES][TH * TW];
-  __shared__ uint32_t s_cnt[SWEEP_TILES][TH * TW / 2];  // two 16-bit counts per word
-  const int fr = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int x0 = (blockIdx.x * SWEEP_TILES + wid) * TW, y0 = blockIdx.y * TH;
-  if (x0 >= g.Wd) return;  // (no block-wide barrier in this kernel)
-  const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
-  uint32_t *L = s_L[wid], *cnt = s_cnt[wid];
-  for (int i = lane; i < TH * TW / 2; i += 32) cnt[i] = 0;
-  const uint32_t NONE = 0xffffffffu;
-  const int x = x0 + lane;
-  const int rows = min(TH, g.Hd - y0);
-  // bytes of image row y in this lane's column and, on lanes 0 / 31, of the halo column; outside the image 127 (never links)
-  const int hx = lane == 0 ? x0 - 1 : x0 + TW;  // halo column of the edge lanes
-  const bool has_halo = (lane == 0 || lane == 31) && hx >= 0 && hx < g.Wd;
-  auto load_group = [&](int ly0) -> uint2 {  // rows ly0 .. ly0+3 of the tile, packed: .x centre bytes, .y halo bytes
-    uint32_t c = 0x7f7f7f7fu, hh = 0x7f7f7f7fu;
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int y = y0 + ly0 + u;
-      if (y >= 0 && y < g.Hd && ly0 + u < rows) {
-        if (x < g.Wd) c = (c & ~(0xffu << (8 * u))) | ((uint32_t)img[(size_t)y * Wp + x] << (8 * u));
-        if (has_halo) hh = (hh & ~(0xffu << (8 * u))) | ((uint32_t)img[(size_t)y * Wp + hx] << (8 * u));
-      }
-    }
-    return make_uint2(c, hh);
-  };
-  // the row above the tile
-  int uc = 127, uh = 127;
-  if (y0 > 0) {
-    if (x < g.Wd) uc = img[(size_t)(y0 - 1) * Wp + x];
-    if (has_halo) uh = img[(size_t)(y0 - 1) * Wp + hx];
-  }
-  uint2 cur = load_group(0);
-  uint32_t plab = NONE;  // label of the pixel above (row ly - 1) in this lane's column
-  __syncwarp();
-  for (int ly0 = 0; ly0 < rows; ly0 += 4) {
-    const uint2 nxt = load_group(ly0 + 4);  // in flight while this group is processed
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int ly = ly0 + u;
-      if (ly >= rows) break;
-      const int y = y0 + ly;
-      const int cc = (int)((cur.x >> (8 * u)) & 0xffu), ch = (int)((cur.y >> (8 * u)) & 0xffu);
-      // neighbours by shuffle; the edge lanes take the halo column
-      int cl = __shfl_up_sync(0xffffffffu, cc, 1), cr = __shfl_down_sync(0xffffffffu, cc, 1);
-      int ul = __shfl_up_sync(0xffffffffu, uc, 1), ur = __shfl_down_sync(0xffffffffu, uc, 1);
-      if (lane == 0) {
-        cl = ch;
-        ul = uh;
-      }
-      if (lane == 31) {
-        cr = ch;
-        ur = uh;
-      }
-      Nb n = {false, false, false, false};
-      if (x < g.Wd) n = ccl_links(cc, cl, uc, ul, ur, x, y, g.Wd);
-      const unsigned ml = __ballot_sync(0xffffffffu, n.L && lane > 0);  // bit x: x is linked to x-1 inside the tile
-      const unsigned upto = (2u << lane) - 1u;
-      const int rs = 31 - __clz(~ml & upto);
-      const unsigned above = ~ml & ~upto;
-      const unsigned run_mask = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << rs) - 1u);
-      const uint32_t pl_l = __shfl_up_sync(0xffffffffu, plab, 1), pl_r = __shfl_down_sync(0xffffffffu, plab, 1);
-      uint32_t c1 = NONE, c2 = NONE, c3 = NONE;
-      if (ly > 0) {
-        if (n.U) c1 = plab;
-        if (n.UL && lane > 0) c2 = pl_l;
-        if (n.UR && lane < TW - 1) c3 = pl_r;
-      }
-      uint32_t rl = min(c1, min(c2, c3));
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t2 = __shfl_up_sync(0xffffffffu, rl, d);
-        if (lane - d >= rs) rl = min(rl, t2);
-      }
-      const int rlast = above ? (__ffs(above) - 2) : 31;
-      rl = __shfl_sync(0xffffffffu, rl, rlast);
-      const int i = ly * TW + lane;
-      if (rl == NONE) rl = (uint32_t)(ly * TW + rs);
-      L[i] = rl;
-      __syncwarp();
-      if (c1 != NONE && c1 != rl) unite_s(L, c1, rl);
-      if (c2 != NONE && c2 != rl) unite_s(L, c2, rl);
-      if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
-      if (lane == rs && x < g.Wd && cc != 127) atomicAdd(&cnt[rl >> 1], (uint32_t)__popc(run_mask) << (16 * (rl & 1)));
-      plab = rl;
-      uc = cc;
-      uh = ch;
-    }
-    cur = nxt;
-  }
-  __syncwarp();
-  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
-  uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
+  // flatten inside the tile; counts collected at merged labels move to their final local root.  The rows in which this lane's
+  // column holds a local root are remembered as a bit mask (a root already owns the pixels of its first run: cnt != 0; the
+  // 127-pixels and the padding columns never get a count)
+  unsigned rootbits = 0u;
   for (int ly = 0; ly < rows; ly++) {
     const int i = ly * TW + lane;
     const uint32_t r = find_s(L, i);
     if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
-    const uint32_t c = (cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu;  // non-zero only at labels
+    const uint32_t c = cnt[i];  // non-zero only at labels; a non-root entry is touched by this lane alone
     if (r != (uint32_t)i && c) {
-      atomicAdd(&cnt[r >> 1], c << (16 * (r & 1)));
-      atomicSub(&cnt[i >> 1], c << (16 * (i & 1)));  // (the other half of the word may be in use: no plain store)
+      atomicAdd(&cnt[r], c);
+      cnt[i] = 0;
     }
+    rootbits |= (r == (uint32_t)i && c) ? (1u << ly) : 0u;
   }
   __syncwarp();
-  // 127 pixels are singletons; the pixel values are read once more (L2-resident)
-  for (int ly = 0; ly < rows; ly++) {
-    if (x >= g.Wd) break;
-    const int i = ly * TW + lane;
-    const uint8_t v = img[(size_t)(y0 + ly) * Wp + x];
-    szf[(size_t)(y0 + ly) * Wp + x] = (v == 127) ? 1u : ((cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+  // The tile's local roots (~5 % of the pixels) go to the frame's root list, their pixel counts to the size image: the later
+  // kernels never scan the size image (it is written at roots only).  One reservation per tile, one loop trip per root of the
+  // busiest column.
+  const int myroots = __popc(rootbits);
+  int incl = myroots;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += u;
+  }
+  uint32_t base = 0;
+  if (lane == 31 && incl > 0) base = atomicAdd(&nroots[fr], (uint32_t)incl);
+  base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - myroots);
+  uint32_t *rootf = roots + (size_t)fr * g.Hd * Wp;
+  while (rootbits) {
+    const int ly = __ffs(rootbits) - 1;
+    rootbits &= rootbits - 1u;
+    const size_t gi = (size_t)(y0 + ly) * Wp + x;
+    szf[gi] = cnt[ly * TW + lane];
+    rootf[base++] = (uint32_t)gi;
   }
 }
 
@@ -396,25 +323,19 @@ __global__ void __launch_bounds__(128) k_ccl_border(Geo g, const uint8_t *__rest
 }
 
 // Flatten + size gate in two phases.  After the tile and border kernels every pixel points at a (former) tile root, and only
-// those carry a count.  Phase A: the former tile roots (csize != 0; ~5 % of the pixels) chase to their global
-// root, point at it directly and hand over their count.  Phase B: every pixel needs exactly ONE gather, lab[lab[p]], and the
-// size gate (thr2 = thr with pixels of components < 25 px forced to 127: folds the size gates of gradient_clusters into one byte
-// image) is applied in the same pass: lab and thr are read once.  (Measured against a per-pixel chase + separate mark pass:
-// 1.34 -> 1.00 ms per 256 frames, profiles/r03_variants.md.)
-__global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__ lab, uint32_t *__restrict__ csize, int Wp) {
-  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y;
-  const int fr = blockIdx.z;
-  if (x4 >= g.Wd) return;
+// those carry a count.  Phase A (k_ccl_roots): the former tile roots -- the frame's root list written by the tile kernel, ~5 % of
+// the pixels -- chase to their global root, point at it directly and hand over their count.  Phase B (k_ccl_flatmark): every
+// pixel needs exactly ONE gather, lab[lab[p]], and the size gate (thr2 = thr with pixels of components < 25 px forced to 127:
+// folds the size gates of gradient_clusters into one byte image) is applied in the same pass: lab and thr are read once.
+constexpr int ROOT_CTAS = 48;  // per frame, grid-stride over the root list
+__global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__ lab, uint32_t *__restrict__ csize,
+                                                   const uint32_t *__restrict__ roots, const uint32_t *__restrict__ nroots, int Wp) {
+  const int fr = blockIdx.y;
   const size_t fo = (size_t)fr * g.Hd * Wp;
   uint32_t *L = lab + fo;
-  const uint32_t me0 = (uint32_t)(y * Wp + x4);
-  const uint4 cv = *reinterpret_cast<const uint4 *>(csize + fo + me0);
-  const uint32_t c[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (c[k] == 0 || x4 + k >= g.Wd) continue;
-    const uint32_t me = me0 + k;
+  const uint32_t n = nroots[fr];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t me = roots[fo + i];
     uint32_t a = me, p = __ldcg(&L[a]);
     while (p != a) {
       a = p;
@@ -422,7 +343,7 @@ __global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__
     }
     if (a != me) {
       __stcg(&L[me], a);
-      atomicAdd(&csize[fo + a], c[k]);
+      atomicAdd(&csize[fo + a], csize[fo + me]);  // (only global roots receive counts: csize[me] is final)
     }
   }
 }
@@ -462,19 +383,17 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   const int Wp = at_Wp(g);
   dim3 gt((g.Wd + TW - 1) / TW, (g.Hd + TH - 1) / TH, nframes);
   dim3 gs((gt.x + SWEEP_TILES - 1) / SWEEP_TILES, gt.y, gt.z);
-  // Tune::ccl_tma: 1 = tiles staged in shared memory by TMA (k_ccl_tile_sweep), 0 = no staging, lanes read their column straight from
-  // global memory (k_ccl_tile_sweep_direct: 6 KB instead of 10.4 KB of shared memory per tile)
+  cudaMemsetAsync(ws.nroots, 0, sizeof(uint32_t) * nframes, s);
+  // Tune::ccl_tma: 1 = tiles staged in shared memory by TMA, 0 = staged by plain loads (also the path without the driver entry point)
   if (ws.tune.ccl_tma && ws.use_tma)
-    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
-  else if (ws.tune.ccl_tma)
-    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp, ws.thr_tmap);
+    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.tune.x[1], ws.thr_tmap);
   else
-    k_ccl_tile_sweep_direct<<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, Wp);
+    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.tune.x[1], ws.thr_tmap);
   k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
+  k_ccl_roots<<<dim3(ROOT_CTAS, nframes), 256, 0, s>>>(g, ws.lab, ws.csize, ws.roots, ws.nroots, Wp);
   dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);
-  k_ccl_roots<<<gp, 256, 0, s>>>(g, ws.lab, ws.csize, Wp);
   k_ccl_flatmark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
-  return 4;
+  return 5;
 }
 
 }  // namespace b200at

@@ -26,21 +26,29 @@ __device__ __forceinline__ uint32_t hash_key2(unsigned long long k) {
 }
 
 // Four pixels per thread (x = 4t .. 4t+3 of row y): the byte image is read as aligned words (three per row instead of seven
-// byte loads per pixel), the labels as one uint4 + scalars per row, and the points of a warp are compacted with ONE exclusive
-// scan of per-thread counts per half instead of one ballot per (pixel, probe).  Same table protocol as k_cluster_pass; the
-// kernels are instruction-issue bound (ncu: 66 % of peak issue at 82 % warps active), this variant executes about half the
-// instructions per pixel than a thread-per-pixel pass.  The order of the points inside a cluster's segment is irrelevant (sorted
-// later).  (Measured and dropped, profiles/r03_variants.md: deferring the emit pass's stores by one round; recording (slot, point)
+// byte loads per pixel), the labels as one uint4 + scalars per row, and the points of a warp (up to 16 per thread) are compacted
+// into shared memory with one exclusive scan of the per-thread counts per half.  The order of the points inside a cluster's segment is
+// irrelevant (sorted later).
+// Count pass: issue bound (ncu: 79 % of peak issue): per chunk of 32 compacted points one __match_any_sync groups equal keys, the
+// group leaders insert / find the key and add the group size with a fire-and-forget atomic.
+// Emit pass: was latency bound -- per chunk a dependent chain key load -> compare -> atomicAdd with return -> store, 47 % of
+// its stall samples on exactly that chain (profiles/r03_ncu_full_irregular_batch32.csv).  Now the chain is software-pipelined
+// over kPipe chunks: every lane first loads the table entry of its own key's home slot for all chunks (no leader-only
+// divergence in front of the loads), then the leaders issue all cursor atomics, and only then the results are consumed.
+// The point word is assembled per pixel (the gradient-sign codes of the four probes are constants of the pixel's polarity).
+// (Measured and dropped, profiles/r03_variants.md: deferring the emit pass's stores by one round; recording (slot, point)
 // pairs in the count pass and scattering them instead of a second pass; grouping the points of a whole row by key in a
-// shared-memory table so that one thread per distinct key touches the global table -- the three block barriers and the
-// serialised global round trips per CTA made both passes 2x slower: count 0.75 -> 1.58 ms, emit 1.39 -> 2.92 ms.)
+// shared-memory table so that one thread per distinct key touches the global table.)
+constexpr int kPipe = 2;
 template <bool EMIT>
-__global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
-                                                       unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
-                                                       const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
-                                                       uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp) {
+__global__ void __launch_bounds__(256, EMIT ? 6 : 8) k_cluster_pass4(Geo g, const uint8_t *__restrict__ thr2, const uint32_t *__restrict__ lab,
+                                                                     unsigned long long *__restrict__ hkey, uint32_t *__restrict__ hcnt,
+                                                                     const uint32_t *__restrict__ hoff, uint32_t *__restrict__ hcur,
+                                                                     uint32_t *__restrict__ pts, uint32_t *__restrict__ counters, int Wp) {
+  // the four pixels of a thread are processed as two halves of two: 256 compacted points per warp at most, 24 KB of shared
+  // memory per CTA (measured: all four at once costs more in occupancy than the second scan costs in instructions)
   __shared__ unsigned long long s_key[8][256];
-  __shared__ uint32_t s_pt[8][256];
+  __shared__ uint32_t s_pt[EMIT ? 8 : 1][EMIT ? 256 : 1];
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y + 1;  // 1 .. Hd-2
   const int fr = blockIdx.z;
@@ -85,11 +93,10 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
   vb[5] = (int)(b2 & 0xffu);
   const uint32_t lrow0[5] = {la.x, la.y, la.z, la.w, la4};            // labels of row y,   columns x4 .. x4+4
   const uint32_t lrow1[6] = {lbm, lb.x, lb.y, lb.z, lb.w, lb4};       // labels of row y+1, columns x4-1 .. x4+4
-  const int dxs[4] = {1, 0, -1, 1};
-  const int dys[4] = {0, 1, 1, 1};
+  uint2 *skey2 = reinterpret_cast<uint2 *>(s_key[wid]);
 #pragma unroll
   for (int half = 0; half < 2; half++) {
-    // my points of pixels 2*half, 2*half+1: bit (2 * jj + k) of `mask` = probe k of pixel jj produced a point
+    // my points of pixels 2 * half, 2 * half + 1: bit (4 * jj + k) of `mask` = probe k of pixel jj produced a point
     unsigned mask = 0;
 #pragma unroll
     for (int jj = 0; jj < 2; jj++) {
@@ -112,43 +119,40 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
       if ((int)lane >= o) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int base0 = incl - cnt;
+    int pos = incl - cnt;
 #pragma unroll
     for (int jj = 0; jj < 2; jj++) {
       const int j = 2 * half + jj;
-      const int x = x4 + j;
-      const int v0 = va[1 + j];
       const uint32_t rep0 = lrow0[j];
       const uint32_t rep1[4] = {lrow0[j + 1], lrow1[j + 1], lrow1[j], lrow1[j + 2]};
+      // point word (2x+dx) | (2y+dy) << 14 | cx << 28 | cy << 30 with cx / cy = sign code (0: zero, 1: positive, 2: negative) of
+      // the gradient dx * (v1 - v0), dy * (v1 - v0); v1 - v0 = +255 when v0 == 0, -255 when v0 == 255 (v0 + v1 == 255)
+      const uint32_t A = va[1 + j] == 0 ? 1u : 2u, Bc = 3u - A;
+      const uint32_t low = (uint32_t)(2 * (x4 + j)) | ((uint32_t)(2 * y) << 14);
+      const uint32_t ptw[4] = {(low + 1u) | (A << 28), (low + (1u << 14)) | (A << 30), (low - 1u + (1u << 14)) | (Bc << 28) | (A << 30),
+                               (low + 1u + (1u << 14)) | (A << 28) | (A << 30)};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const int bit = 4 * jj + k;
-        if ((mask >> bit) & 1u) {
-          const int pos = base0 + __popc(mask & ((1u << bit) - 1u));
+        if ((mask >> (4 * jj + k)) & 1u) {
           const uint32_t q1 = rep1[k];
-          s_key[wid][pos] = rep0 < q1 ? (((unsigned long long)q1 << 32) | rep0) : (((unsigned long long)rep0 << 32) | q1);
-          if (EMIT) {
-            const int dx = dxs[k], dy = dys[k];
-            const int d = 255 - 2 * v0;  // v1 - v0 with v0 + v1 == 255
-            const int gx = dx * d, gy = dy * d;
-            const uint32_t cx = gx == 0 ? 0u : (gx > 0 ? 1u : 2u), cy = gy == 0 ? 0u : (gy > 0 ? 1u : 2u);
-            s_pt[wid][pos] = (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 14) | (cx << 28) | (cy << 30);
-          }
+          skey2[pos] = make_uint2(min(rep0, q1), max(rep0, q1));  // key = larger representative << 32 | smaller
+          if (EMIT) s_pt[wid][pos] = ptw[k];
+          pos++;
         }
       }
     }
     __syncwarp();
-    for (int c0 = 0; c0 < total; c0 += 32) {
-      const int j = c0 + (int)lane;
-      const bool has = j < total;
-      const unsigned act = __ballot_sync(0xffffffffu, has);
-      if (!has) continue;
-      const unsigned long long key = s_key[wid][j];
-      const unsigned peers = __match_any_sync(act, key);
-      const int leader = __ffs(peers) - 1;
-      const int n = __popc(peers);
-      uint32_t slot = hash_key2(key) & hmask;
-      if (!EMIT) {
+    if (!EMIT) {
+      for (int c0 = 0; c0 < total; c0 += 32) {
+        const int j = c0 + (int)lane;
+        const bool has = j < total;
+        const unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!has) continue;
+        const unsigned long long key = s_key[wid][j];
+        const unsigned peers = __match_any_sync(act, key);
+        const int leader = __ffs(peers) - 1;
+        const int n = __popc(peers);
+        uint32_t slot = hash_key2(key) & hmask;
         if ((int)lane == leader) {
           uint32_t found = 0xffffffffu;
           for (uint32_t probe = 0; probe < g.hcap; probe++) {
@@ -171,22 +175,51 @@ __global__ void __launch_bounds__(256) k_cluster_pass4(Geo g, const uint8_t *__r
           else
             atomicAdd(&hcnt[ho + found], (uint32_t)n);
         }
-      } else {
-        uint32_t base = 0xffffffffu;
-        if ((int)lane == leader) {
-          for (uint32_t probe = 0; probe < g.hcap; probe++) {
-            const unsigned long long cur = hk[slot];
-            const uint32_t off = hoff[ho + slot];  // issued together with the key load
-            if (cur == key) {
-              if (off != 0xffffffffu) base = off + atomicAdd(&hcur[ho + slot], (uint32_t)n);
-              break;
-            }
-            if (cur == 0ULL) break;
-            slot = (slot + 1) & hmask;
+      }
+    } else {
+      for (int c0 = 0; c0 < total; c0 += 32 * kPipe) {
+        unsigned long long key[kPipe], cur[kPipe];
+        uint32_t slot[kPipe], off[kPipe], base[kPipe];
+        unsigned peers[kPipe];
+        // (A) the table entry at the home slot of every lane's own key, all chunks in flight
+#pragma unroll
+        for (int u = 0; u < kPipe; u++) {
+          const int j = c0 + 32 * u + (int)lane;
+          key[u] = j < total ? s_key[wid][j] : 0ULL;
+          slot[u] = hash_key2(key[u]) & hmask;
+          cur[u] = 0ULL;
+          off[u] = 0xffffffffu;
+          if (j < total) {
+            cur[u] = hk[slot[u]];
+            off[u] = hoff[ho + slot[u]];
           }
         }
-        base = __shfl_sync(peers, base, leader);
-        if (base != 0xffffffffu) pts[base + __popc(peers & ((1u << lane) - 1))] = s_pt[wid][j];
+        // (B) collisions probe on (rare); equal keys are grouped and the group leader advances the cluster's cursor
+#pragma unroll
+        for (int u = 0; u < kPipe; u++) {
+          base[u] = 0xffffffffu;
+          peers[u] = 0u;
+          if (c0 + 32 * u >= total) continue;  // (uniform)
+          const bool has = c0 + 32 * u + (int)lane < total;
+          const unsigned act = __ballot_sync(0xffffffffu, has);
+          if (!has) continue;
+          for (uint32_t probe = 0; cur[u] != key[u] && cur[u] != 0ULL && probe < g.hcap; probe++) {
+            slot[u] = (slot[u] + 1) & hmask;
+            cur[u] = hk[slot[u]];
+            off[u] = hoff[ho + slot[u]];
+          }
+          peers[u] = __match_any_sync(act, key[u]);
+          const int leader = __ffs(peers[u]) - 1;
+          if ((int)lane == leader && cur[u] == key[u] && off[u] != 0xffffffffu)
+            base[u] = off[u] + atomicAdd(&hcur[ho + slot[u]], (uint32_t)__popc(peers[u]));
+        }
+        // (C) the points go to their cluster's segment
+#pragma unroll
+        for (int u = 0; u < kPipe; u++) {
+          if (peers[u] == 0u) continue;
+          const uint32_t bs = __shfl_sync(peers[u], base[u], __ffs(peers[u]) - 1);
+          if (bs != 0xffffffffu) pts[bs + __popc(peers[u] & ((1u << lane) - 1))] = s_pt[wid][c0 + 32 * u + (int)lane];
+        }
       }
     }
     __syncwarp();  // the buffer is reused by the second half

@@ -36,6 +36,7 @@ __device__ __forceinline__ int gray_at_bf(const uint8_t *base, size_t pitch, int
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 __device__ __forceinline__ void hproject(const double *H, double x, double y, double *ox, double *oy) {
   double xx = H[0] * x + H[1] * y + H[2];
@@ -308,19 +309,20 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
           has = 1;
         }
       }
-      const int cnt = min(32, nsamples - s0);
-      for (int k = 0; k < cnt; k++) {
-        const int h = __shfl_sync(0xffffffffu, has, k);
-        const double bx = shfl_d(bestx, k), by = shfl_d(besty, k);
-        if (h) {
-          Mx += bx;
-          My += by;
-          Mxx += bx * bx;
-          Mxy += bx * by;
-          Myy += by * by;
-          N++;
-        }
+      // moments of the 32 samples: butterfly sums (every lane ends with the same value).  The oracle adds the samples one
+      // after the other; the association differs in the last bits of sums whose line parameters are rounded to float below.
+      double m5[5] = {has ? bestx : 0.0, has ? besty : 0.0, has ? bestx * bestx : 0.0, has ? bestx * besty : 0.0, has ? besty * besty : 0.0};
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) m5[q] += shfl_xor_d(m5[q], of);
       }
+      Mx += m5[0];
+      My += m5[1];
+      Mxx += m5[2];
+      Mxy += m5[3];
+      Myy += m5[4];
+      N += (double)__popc(__ballot_sync(0xffffffffu, has != 0));
     }
     double Ex = Mx / N, Ey = My / N;
     double Cxx = Mxx / N - Ex * Ex;

@@ -88,12 +88,12 @@ __device__ __forceinline__ bool qf_pregate(const BBoxRed &r, const FitParams &fp
 }
 
 // the cluster's chunks become work items of k_qf_window (one thread)
-__device__ __forceinline__ void qf_register_work(uint32_t ci, int sz, bool reversed, uint32_t *qinfo, uint32_t *qwbase, uint2 *work,
-                                                 uint32_t work_cap, uint32_t *counters) {
+__device__ __forceinline__ void qf_register_work(uint32_t ci, uint32_t off, int sz, bool reversed, uint32_t *qinfo, uint32_t *qwbase,
+                                                 uint4 *work, uint32_t work_cap, uint32_t *counters) {
   const int nch = qf_nchunks(sz);
   const uint32_t wb = atomicAdd(&counters[CNT_QWORK], (uint32_t)nch);
   if (wb + (uint32_t)nch <= work_cap) {
-    for (int c = 0; c < nch; c++) work[wb + c] = make_uint2(ci, (uint32_t)c);
+    for (int c = 0; c < nch; c++) work[wb + c] = make_uint4(off, (uint32_t)sz, (uint32_t)c, ci);
     qwbase[ci] = wb;
     qinfo[ci] = (uint32_t)sz | (reversed ? 0x80000000u : 0u);
   } else {  // (cannot happen with the capacity capi.cu allocates: pts_cap / kQfChunkMax + clu_cap)
@@ -124,7 +124,7 @@ template <int THREADS, int E, int ITEMS, int MINB, int WPC, int MODE>
 __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
               const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
-              const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work,
+              const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint4 *__restrict__ work,
               uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
           if (i + u * THREADS < sz) keys_g[i + u * THREADS] = (k[u] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[u] << 32);
       }
     }
-    if (tid == 0) qf_register_work(ci, sz, reversed, qinfo, qwbase, work, work_cap, counters);
+    if (tid == 0) qf_register_work(ci, o, sz, reversed, qinfo, qwbase, work, work_cap, counters);
   }
 }
 
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
 __global__ void __launch_bounds__(256, 2)
     k_qf_sort_global(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
                      const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
-                     const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint2 *__restrict__ work,
+                     const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint4 *__restrict__ work,
                      uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
   constexpr int THREADS = 256;
   __shared__ BBoxRed s_red[THREADS / 32];
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256, 2)
       const unsigned long long k = keys_g[i];
       keys_g[i] = (k & 0xffffffffull) | ((unsigned long long)(uint32_t)grad2_at(im, Wp, g.Wd, g.Hd, k) << 32);
     }
-    if (tid == 0) qf_register_work(ci, sz, reversed, qinfo, qwbase, work, work_cap, counters);
+    if (tid == 0) qf_register_work(ci, o, sz, reversed, qinfo, qwbase, work, work_cap, counters);
   }
 }
 
@@ -341,10 +341,9 @@ constexpr int QW_WARPS = 4;
 constexpr int QW_SLOTS = 32 * kQfSlotsPerLane;
 
 __global__ void __launch_bounds__(32 * QW_WARPS)
-    k_qf_window(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ qinfo,
-                const uint2 *__restrict__ work, uint32_t work_cap, const unsigned long long *__restrict__ keys,
+    k_qf_window(Geo g, FitParams fp, const uint4 *__restrict__ work, uint32_t work_cap, const unsigned long long *__restrict__ keys,
                 LineFitPt *__restrict__ lfps_pool, double *__restrict__ wtot, uint32_t *__restrict__ wnmax,
-                uint32_t *__restrict__ counters) {
+                const uint32_t *__restrict__ counters) {
   constexpr int PPL = kQfSlotsPerLane, SLOTS = QW_SLOTS;
   extern __shared__ double dsm_win[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -354,30 +353,26 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
   const uint32_t nwork = min(counters[CNT_QWORK], work_cap);
   const double f0 = (double)fp.smooth[0], f1 = (double)fp.smooth[1], f2 = (double)fp.smooth[2], f3 = (double)fp.smooth[3],
                f4 = (double)fp.smooth[4], f5 = (double)fp.smooth[5], f6 = (double)fp.smooth[6];
-  // One work item ahead: while an item is being processed, the next one's queue ticket, metadata and keys are already in
-  // flight (the dependent chain atomic -> work[] -> cluster record -> keys is ~4 memory round trips; without the prefetch it
-  // was 35 % of the kernel's stall samples).
+  // Work items are self-contained records and statically strided over the warps (item sizes are bounded by the chunk size, and
+  // a warp sees hundreds of them: no queue needed).  Two items ahead the record is in flight, one item ahead the keys: the
+  // chain ticket -> work[] -> cluster record -> keys used to be 18 % of the kernel's stall samples even with one item prefetched.
+  const uint32_t stride = gridDim.x * QW_WARPS;
   struct Item {
     uint32_t w, off;
     int n, c, s, len, ksz;
-    bool valid;
   };
   unsigned long long kq[PPL];
-  auto fetch = [&](Item &it) {
-    uint32_t w = 0;
-    if (lane == 0) w = atomicAdd(&counters[CNT_Q2], 1u);
-    w = __shfl_sync(0xffffffffu, w, 0);
+  auto decode = [&](uint32_t w, const uint4 &rec, Item &it) {
     it.w = w;
-    it.valid = w < nwork;
-    if (!it.valid) return;
-    const uint2 wk = work[w];
-    it.off = clusters[wk.x].offset;
-    it.n = (int)(qinfo[wk.x] & 0x7fffffffu);
-    it.c = (int)wk.y;
+    it.off = rec.x;
+    it.n = (int)rec.y;
+    it.c = (int)rec.z;
     int e;
     qf_chunk_bounds(it.n, qf_nchunks(it.n), it.c, it.s, e);
     it.len = e - it.s;
     it.ksz = min(20, it.n / 12);
+  };
+  auto load_keys = [&](const Item &it) {
     const int HLn = it.ksz + 5, Ln = it.len + 2 * it.ksz + 9;
     const unsigned long long *kg = keys + it.off;
 #pragma unroll
@@ -389,12 +384,16 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
       kq[q] = j < Ln ? kg[gi] : 0ull;
     }
   };
+  uint32_t w = blockIdx.x * QW_WARPS + wid;
+  if (w >= nwork) return;
   Item cur;
-  fetch(cur);
-  while (cur.valid) {
-    const uint32_t w = cur.w, off = cur.off;
-    const int n = cur.n, c = cur.c, s = cur.s, len = cur.len, ksz = cur.ksz;
-    (void)n;
+  decode(w, work[w], cur);
+  load_keys(cur);
+  uint4 rec_next = make_uint4(0, 0, 0, 0);
+  if (w + stride < nwork) rec_next = work[w + stride];
+  for (;;) {
+    const uint32_t off = cur.off;
+    const int c = cur.c, s = cur.s, len = cur.len, ksz = cur.ksz;
     const int HL = ksz + 5;            // halo: ksz + 5 points before the chunk, ksz + 4 after (circular)
     const int L = len + 2 * ksz + 9;   // <= SLOTS by the choice of kQfChunkMax
     unsigned long long *Ek = reinterpret_cast<unsigned long long *>(E);
@@ -404,8 +403,14 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
       if (j < L) Ek[j] = kq[q];
     }
     __syncwarp();
-    Item nxt;
-    fetch(nxt);
+    const uint32_t w1 = w + stride;
+    const bool more = w1 < nwork;
+    Item nxt = cur;
+    if (more) {
+      decode(w1, rec_next, nxt);
+      load_keys(nxt);
+      if (w1 + stride < nwork) rec_next = work[w1 + stride];
+    }
     // line-fit terms and prefix moments: a lane owns PPL consecutive slots (serial chain), one warp scan joins the lanes
     double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -502,7 +507,9 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
     if (lane < 6) wtot[(size_t)w * 6 + lane] = P[lane * SLOTS + HL + len - 1] - P[lane * SLOTS + HL - 1];
     if (lane == 0) wnmax[w] = (uint32_t)run;
     __syncwarp();
+    if (!more) break;
     cur = nxt;
+    w = w1;
   }
 }
 
@@ -533,18 +540,36 @@ __global__ void __launch_bounds__(32 * QT_WARPS)
   double *s_val = s_val_a[wid];
   int *s_fm = s_fm_a[wid], *s_kp = s_kp_a[wid];
   const uint32_t ncl = min(counters[CNT_CLUSTERS], g.clu_cap);
+  // Dynamic queue (cluster costs differ by orders of magnitude), software-pipelined: the ticket of the cluster after the next is
+  // in flight while the next cluster's metadata loads and the current one is processed (the chain ticket -> qinfo -> record was
+  // exposed once per cluster: long-scoreboard stalls were 31 % of the kernel's samples).
+  auto take_raw = [&]() -> uint32_t { return lane == 0 ? atomicAdd(&counters[CNT_Q3], 1u) : 0u; };
+  uint32_t ci_next = __shfl_sync(0xffffffffu, take_raw(), 0);
+  uint32_t info_n = 0u, wb_n = 0u;
+  ClusterRec cr_n = {0ull, 0u, 0u, 0u, 0u};
+  if (ci_next < ncl) {
+    info_n = qinfo[ci_next];
+    cr_n = clusters[ci_next];
+    wb_n = qwbase[ci_next];
+  }
+  uint32_t t_raw = take_raw();
   for (;;) {
     __syncwarp();
-    uint32_t ci = 0;
-    if (lane == 0) ci = atomicAdd(&counters[CNT_Q3], 1u);
-    ci = __shfl_sync(0xffffffffu, ci, 0);
+    const uint32_t ci = ci_next;
     if (ci >= ncl) break;
-    const uint32_t info = qinfo[ci];
+    const uint32_t info = info_n;
+    const ClusterRec cr = cr_n;
+    const uint32_t wb = wb_n;
+    ci_next = __shfl_sync(0xffffffffu, t_raw, 0);  // (issued one cluster ago)
+    if (ci_next < ncl) {
+      info_n = qinfo[ci_next];
+      cr_n = clusters[ci_next];
+      wb_n = qwbase[ci_next];
+    }
+    t_raw = take_raw();
     if (info == 0u) continue;
     const int sz = (int)(info & 0x7fffffffu);
     const bool reversed = (info >> 31) != 0u;
-    const ClusterRec cr = clusters[ci];
-    const uint32_t wb = qwbase[ci];
     const int nch = qf_nchunks(sz);
     const MaxRec *mbase = reinterpret_cast<const MaxRec *>(lfps_pool + cr.offset);
     int m = 0;
@@ -919,8 +944,8 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_qf_window, 32 * QW_WARPS, smem);
       ctas_per_sm[di] = std::max(1, n);
     }
-    k_qf_window<<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(g, ws.fp, ws.clusters, ws.qinfo, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps,
-                                                                    ws.qwtot, ws.qwnmax, ws.counters);
+    k_qf_window<<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(g, ws.fp, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps, ws.qwtot, ws.qwnmax,
+                                                                    ws.counters);
   }
   {
     static int ctas_per_sm[64] = {};

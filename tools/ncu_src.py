@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Per-source-line view of one kernel from an ncu report captured with --import-source on:
-   ncu_src.py <report.ncu-rep> <kernel regex> [top N]   -> lines sorted by stall samples, with executed warp instructions."""
+   ncu_src.py <report.ncu-rep> <kernel regex> [top N] [substring the function name must contain]
+   -> lines sorted by stall samples, with their share of the executed warp instructions and the top stall reasons."""
 import csv
 import io
 import subprocess
@@ -9,48 +10,43 @@ from collections import defaultdict
 
 rep, kern = sys.argv[1:3]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+must = sys.argv[4] if len(sys.argv) > 4 else ""
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", "regex:" + kern],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-fname = ""
-agg = defaultdict(lambda: [0, 0, "", defaultdict(int)])
-hdr = None
-kname = None
+agg = {}
+hdr, fname, func, take, done = None, "", None, False, False
 for r in rows:
     if not r:
         continue
-    if r[0] == "Kernel Name":
-        if kname is not None and r[1] != kname:
-            break  # first matching kernel only
-        kname = r[1]
-        continue
-    if r[0] == "File Name":
+    if r[0] in ("File Path", "File Name"):
         fname = r[1].split("/")[-1]
+        continue
+    if r[0] in ("Function Name", "Kernel Name"):
+        if take and func is not None and r[1] != func:
+            done = True
+        if not done:
+            take = must.replace(" ", "") in r[1].replace(" ", "")
+            if take:
+                func = r[1]
         continue
     if r[0] == "Line No":
         hdr = r
         si, ii = hdr.index("# Samples"), hdr.index("Instructions Executed")
         stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
         continue
-    if hdr is None or len(r) < len(hdr):
+    if hdr is None or not take or done or len(r) < len(hdr) or not r[0].isdigit():
         continue
-    try:
-        ln = int(r[0])
-        s, n = int(r[si] or 0), int(r[ii] or 0)
-    except ValueError:
-        continue
-    a = agg[(fname, ln)]
-    a[0] += s
-    a[1] += n
-    a[2] = r[1].strip()
+    key = (fname, int(r[0]))
+    a = agg.setdefault(key, [0, 0, r[1].strip(), defaultdict(int)])
+    num = lambda t: int(t) if t.isdigit() else 0
+    a[0] += num(r[si])
+    a[1] += num(r[ii])
     for i, nm in stall_cols:
-        try:
-            a[3][nm] += int(r[i] or 0)
-        except ValueError:
-            pass
+        a[3][nm] += num(r[i])
 tot_s = sum(a[0] for a in agg.values()) or 1
 tot_i = sum(a[1] for a in agg.values()) or 1
-print(f"# {kname}\n# samples {tot_s}, warp instructions {tot_i}")
+print(f"# {func}\n# samples {tot_s}, warp instructions {tot_i}")
 mix = defaultdict(int)
 for a in agg.values():
     for k, v in a[3].items():
