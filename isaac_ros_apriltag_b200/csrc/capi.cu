@@ -469,6 +469,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     fp.cx = fp.cy = 0;
   }
   fp.tagsize = tag_dim;
+  fp.variant = 0;
   // blur taps (apriltag_detector_detect's quad_sigma block + image_u8_gaussian_blur)
   ws.blur_ksz = 0;
   ws.blur_sharpen = 0;
@@ -522,6 +523,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.counters, (size_t)kMaxChunks * CNT_N);
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   ws.tune = parse_tune();
+  ws.fp.variant = ws.tune.x[3];
   ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
   if (!ws.tune.qf_exact) {
     ws.qwork_cap = (uint32_t)std::min<size_t>((size_t)g.pts_cap / kQfChunkMax + g.clu_cap, 0xfffffff0ull);

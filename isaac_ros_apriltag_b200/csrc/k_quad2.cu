@@ -117,7 +117,7 @@ __device__ __forceinline__ void qf_register_work(uint32_t ci, uint32_t off, int 
 constexpr int kBucketLimit = 1024;
 template <int THREADS, int E, int MODE, int WPC>
 __host__ __device__ constexpr size_t qf_sort_smem() {
-  return MODE == 1 ? 0 : MODE == 0 ? (size_t)2 * THREADS * E * 8 * WPC : ((size_t)THREADS * E * 8 + (size_t)(THREADS * E / 2 + 2) * 4) * WPC;
+  return MODE == 1 ? 0 : MODE == 0 ? (size_t)2 * THREADS * E * 8 * WPC : ((size_t)THREADS * E * 8 + (size_t)(THREADS * E + 2) * 4) * WPC;
 }
 
 template <int THREADS, int E, int ITEMS, int MINB, int WPC, int MODE>
@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
               const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
               const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint4 *__restrict__ work,
-              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
+              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp, int nb_shift) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
   static_assert(MODE != 1 || NW == 1, "register sort: one-warp clusters only");
-  extern __shared__ unsigned long long dsm_sort[];  // per worker: MODE 0 [2 * NCAP] keys; MODE 2 [NCAP] keys + [NCAP / 2 + 2] counters
+  extern __shared__ unsigned long long dsm_sort[];  // per worker: MODE 0 [2 * NCAP] keys; MODE 2 [NCAP] keys + [NCAP + 2] counters
   const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
   unsigned long long *skeys = dsm_sort + (size_t)grp * (qf_sort_smem<THREADS, E, MODE == 1 ? 0 : MODE, 1>() / 8), *stmp = skeys + NCAP;
   uint32_t *cnt = reinterpret_cast<uint32_t *>(stmp);  // MODE 2: bucket counters, then bucket start offsets
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
         if (lane * E + k < sz) keys_g[lane * E + k] = (v[k] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[k] << 32);
     } else if (MODE == 2) {
       int NB = 32;
-      while (NB * 2 < sz) NB <<= 1;  // power of two, n / 2 <= NB <= NCAP / 2 (NCAP >= 64)
+      while ((NB << nb_shift) < sz) NB <<= 1;  // power of two, n / 2 <= NB <= NCAP / 2 (nb_shift = 1) or n <= NB <= NCAP (0)
       const float nbq = (float)(NB / 4);
       for (int i = tid; i < NB; i += THREADS) cnt[i] = 0u;
       unsigned long long v[E];
@@ -259,11 +259,11 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
         // final position = bucket start + number of smaller keys in the bucket; sorted points out with their squared gradient
         for (int i = tid; i < sz; i += THREADS) {
           const unsigned long long key = skeys[i];
+          const int g2 = grad2_at(im, Wp, g.Wd, g.Hd, key);  // (the four gathers are in flight during the rank loop)
           const int b = key_bucket(key, nbq, NB);
           const int s = (int)cnt[b], e = (int)cnt[b + 1];
           int rank = 0;
           for (int j = s; j < e; j++) rank += skeys[j] < key ? 1 : 0;
-          const int g2 = grad2_at(im, Wp, g.Wd, g.Hd, key);
           keys_g[s + rank] = (key & 0xffffffffull) | ((unsigned long long)(uint32_t)g2 << 32);
         }
       }
@@ -341,9 +341,10 @@ constexpr int QW_WARPS = 4;
 constexpr int QW_SLOTS = 32 * kQfSlotsPerLane;
 
 __global__ void __launch_bounds__(32 * QW_WARPS)
-    k_qf_window(Geo g, FitParams fp, const uint4 *__restrict__ work, uint32_t work_cap, const unsigned long long *__restrict__ keys,
+    k_qf_window(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ qinfo,
+                const uint4 *__restrict__ work, uint32_t work_cap, const unsigned long long *__restrict__ keys,
                 LineFitPt *__restrict__ lfps_pool, double *__restrict__ wtot, uint32_t *__restrict__ wnmax,
-                const uint32_t *__restrict__ counters) {
+                uint32_t *__restrict__ counters) {
   constexpr int PPL = kQfSlotsPerLane, SLOTS = QW_SLOTS;
   extern __shared__ double dsm_win[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -353,26 +354,30 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
   const uint32_t nwork = min(counters[CNT_QWORK], work_cap);
   const double f0 = (double)fp.smooth[0], f1 = (double)fp.smooth[1], f2 = (double)fp.smooth[2], f3 = (double)fp.smooth[3],
                f4 = (double)fp.smooth[4], f5 = (double)fp.smooth[5], f6 = (double)fp.smooth[6];
-  // Work items are self-contained records and statically strided over the warps (item sizes are bounded by the chunk size, and
-  // a warp sees hundreds of them: no queue needed).  Two items ahead the record is in flight, one item ahead the keys: the
-  // chain ticket -> work[] -> cluster record -> keys used to be 18 % of the kernel's stall samples even with one item prefetched.
-  const uint32_t stride = gridDim.x * QW_WARPS;
+  // One work item ahead: while an item is being processed, the next one's queue ticket, metadata and keys are already in
+  // flight (the dependent chain atomic -> work[] -> cluster record -> keys is ~4 memory round trips; without the prefetch it
+  // was 35 % of the kernel's stall samples).
   struct Item {
     uint32_t w, off;
     int n, c, s, len, ksz;
+    bool valid;
   };
   unsigned long long kq[PPL];
-  auto decode = [&](uint32_t w, const uint4 &rec, Item &it) {
+  auto fetch = [&](Item &it) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&counters[CNT_Q2], 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
     it.w = w;
-    it.off = rec.x;
-    it.n = (int)rec.y;
-    it.c = (int)rec.z;
+    it.valid = w < nwork;
+    if (!it.valid) return;
+    const uint4 wk = work[w];  // self-contained record: (point offset, point count, chunk, cluster)
+    it.off = wk.x;
+    it.n = (int)wk.y;
+    it.c = (int)wk.z;
     int e;
     qf_chunk_bounds(it.n, qf_nchunks(it.n), it.c, it.s, e);
     it.len = e - it.s;
     it.ksz = min(20, it.n / 12);
-  };
-  auto load_keys = [&](const Item &it) {
     const int HLn = it.ksz + 5, Ln = it.len + 2 * it.ksz + 9;
     const unsigned long long *kg = keys + it.off;
 #pragma unroll
@@ -384,16 +389,12 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
       kq[q] = j < Ln ? kg[gi] : 0ull;
     }
   };
-  uint32_t w = blockIdx.x * QW_WARPS + wid;
-  if (w >= nwork) return;
   Item cur;
-  decode(w, work[w], cur);
-  load_keys(cur);
-  uint4 rec_next = make_uint4(0, 0, 0, 0);
-  if (w + stride < nwork) rec_next = work[w + stride];
-  for (;;) {
-    const uint32_t off = cur.off;
-    const int c = cur.c, s = cur.s, len = cur.len, ksz = cur.ksz;
+  fetch(cur);
+  while (cur.valid) {
+    const uint32_t w = cur.w, off = cur.off;
+    const int n = cur.n, c = cur.c, s = cur.s, len = cur.len, ksz = cur.ksz;
+    (void)n;
     const int HL = ksz + 5;            // halo: ksz + 5 points before the chunk, ksz + 4 after (circular)
     const int L = len + 2 * ksz + 9;   // <= SLOTS by the choice of kQfChunkMax
     unsigned long long *Ek = reinterpret_cast<unsigned long long *>(E);
@@ -403,14 +404,8 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
       if (j < L) Ek[j] = kq[q];
     }
     __syncwarp();
-    const uint32_t w1 = w + stride;
-    const bool more = w1 < nwork;
-    Item nxt = cur;
-    if (more) {
-      decode(w1, rec_next, nxt);
-      load_keys(nxt);
-      if (w1 + stride < nwork) rec_next = work[w1 + stride];
-    }
+    Item nxt;
+    fetch(nxt);
     // line-fit terms and prefix moments: a lane owns PPL consecutive slots (serial chain), one warp scan joins the lanes
     double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -507,9 +502,7 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
     if (lane < 6) wtot[(size_t)w * 6 + lane] = P[lane * SLOTS + HL + len - 1] - P[lane * SLOTS + HL - 1];
     if (lane == 0) wnmax[w] = (uint32_t)run;
     __syncwarp();
-    if (!more) break;
     cur = nxt;
-    w = w1;
   }
 }
 
@@ -895,7 +888,7 @@ static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t 
     ctas_per_sm[dev] = std::max(1, n);
   }
   kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo,
-                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
+                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g), ws.tune.x[2] ? 0 : 1);
 }
 
 int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
@@ -944,8 +937,8 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_qf_window, 32 * QW_WARPS, smem);
       ctas_per_sm[di] = std::max(1, n);
     }
-    k_qf_window<<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(g, ws.fp, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps, ws.qwtot, ws.qwnmax,
-                                                                    ws.counters);
+    k_qf_window<<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(g, ws.fp, ws.clusters, ws.qinfo, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps,
+                                                                    ws.qwtot, ws.qwnmax, ws.counters);
   }
   {
     static int ctas_per_sm[64] = {};
