@@ -383,7 +383,7 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   const size_t Wp = (size_t)at_Wp(g), Pp = Wp * g.Hd, Pd = (size_t)g.Wd * g.Hd;
   // one slot per (black component, white component) pair with both >= 25 px: measured ~1 k per 1080p frame even on the
   // all-texture bench workload; Pd/8 slots leave room for ~40 k pairs (a 5x5-cell checkerboard) before ST_HASH_FULL
-  g.hcap = opt.hash_slots_per_frame ? next_pow2(opt.hash_slots_per_frame) : next_pow2((uint32_t)std::max<size_t>(Pd / 8, 4096));
+  g.hcap = opt.hash_slots_per_frame ? next_pow2(std::max<uint32_t>(opt.hash_slots_per_frame, 64u)) : next_pow2((uint32_t)std::max<size_t>(Pd / 8, 4096));
   const size_t ppf = opt.points_per_frame ? opt.points_per_frame : Pd;
   const size_t cpf = opt.clusters_per_frame ? opt.clusters_per_frame : std::max<size_t>(Pd / 64, 1024);
   const size_t qpf = opt.quads_per_frame ? opt.quads_per_frame : 1024;
@@ -469,7 +469,6 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
     fp.cx = fp.cy = 0;
   }
   fp.tagsize = tag_dim;
-  fp.variant = 0;
   // blur taps (apriltag_detector_detect's quad_sigma block + image_u8_gaussian_blur)
   ws.blur_ksz = 0;
   ws.blur_sharpen = 0;
@@ -523,7 +522,6 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.counters, (size_t)kMaxChunks * CNT_N);
   ALLOC(ws.bin_idx, (size_t)kQuadBins * g.clu_cap);
   ws.tune = parse_tune();
-  ws.fp.variant = ws.tune.x[3];
   ALLOC(ws.quad_H, (size_t)g.quad_cap * 10);
   if (!ws.tune.qf_exact) {
     ws.qwork_cap = (uint32_t)std::min<size_t>((size_t)g.pts_cap / kQfChunkMax + g.clu_cap, 0xfffffff0ull);

@@ -115,7 +115,6 @@ struct FitParams {
   int nfam;
   float fx, fy, cx, cy;
   float tagsize;
-  int variant;  // development A/B switch (Tune::x[3])
 };
 
 // Per-handle knobs, read once from the environment (B200AT_TUNE="key=value,key=value"; see capi.cu).  Every variant that did not

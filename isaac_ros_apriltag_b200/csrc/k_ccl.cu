@@ -117,7 +117,7 @@ constexpr int TSLOT = (TBYTES + 127) & ~127;           // 128-byte aligned slots
 template <bool USE_TMA>
 __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                                       uint32_t *__restrict__ csize, uint32_t *__restrict__ roots,
-                                                                      uint32_t *__restrict__ nroots, int Wp, int variant,
+                                                                      uint32_t *__restrict__ nroots, int Wp,
                                                                       const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_t[SWEEP_TILES][TSLOT];
   __shared__ __align__(8) unsigned long long mbar;
@@ -197,49 +197,27 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
       if (n.UR && lane < TW - 1) c3 = pl_r;
     }
     const int i = ly * TW + lane;
-    uint32_t rl;
-    if (variant & 1) {
-      // segmented min over the run with FULL-mask shuffles: inclusive min-scan from the run's first lane, then the value of its
-      // last lane.  (redux.sync with one member mask per run makes the hardware execute the runs one after the other.)
-      rl = min(c1, min(c2, c3));
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t2 = __shfl_up_sync(0xffffffffu, rl, d);
-        if ((int)lane - d >= rs) rl = min(rl, t2);
-      }
-      const int rlast = above ? (__ffs(above) - 2) : 31;  // last lane of my run
-      rl = __shfl_sync(0xffffffffu, rl, rlast);
-      if (rl == NONE) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
-      L[i] = rl;
-      cnt[i] = 0;
-      __syncwarp();
-      // a run that touches several labels makes them equivalent
-      if (c1 != NONE && c1 != rl) unite_s(L, c1, rl);
-      if (c2 != NONE && c2 != rl) unite_s(L, c2, rl);
-      if (c3 != NONE && c3 != rl) unite_s(L, c3, rl);
-    } else {
-      // the run inherits the label of its LEFTMOST upward link (one ballot + one shuffle; any label of the component will do: the
-      // unions below make a run's labels equivalent and the root of a component is its smallest label = its first pixel)
-      const uint32_t mine = min(c1, min(c2, c3));
-      const unsigned linked = __ballot_sync(0xffffffffu, mine != NONE) & run_mask;
-      rl = __shfl_sync(0xffffffffu, mine, linked ? __ffs(linked) - 1 : lane);
-      if (!linked) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
-      L[i] = rl;
-      cnt[i] = 0;
-      __syncwarp();
-      // ONE union site, executed as often as the busiest lane needs it
-      bool n1 = c1 != NONE && c1 != rl, n2 = c2 != NONE && c2 != rl && c2 != c1, n3 = c3 != NONE && c3 != rl && c3 != c1 && c3 != c2;
-      while (__any_sync(0xffffffffu, n1 || n2 || n3)) {
-        if (n1 || n2 || n3) {
-          const uint32_t pick = n1 ? c1 : (n2 ? c2 : c3);
-          if (n1)
-            n1 = false;
-          else if (n2)
-            n2 = false;
-          else
-            n3 = false;
-          unite_s(L, pick, rl);
-        }
+    // the run inherits the label of its LEFTMOST upward link (one ballot + one shuffle; any label of the component will do: the
+    // unions below make a run's labels equivalent and the root of a component is its smallest label = its first pixel)
+    const uint32_t mine = min(c1, min(c2, c3));
+    const unsigned linked = __ballot_sync(0xffffffffu, mine != NONE) & run_mask;
+    uint32_t rl = __shfl_sync(0xffffffffu, mine, linked ? __ffs(linked) - 1 : lane);
+    if (!linked) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
+    L[i] = rl;
+    cnt[i] = 0;
+    __syncwarp();
+    // ONE union site, executed as often as the busiest lane needs it
+    bool n1 = c1 != NONE && c1 != rl, n2 = c2 != NONE && c2 != rl && c2 != c1, n3 = c3 != NONE && c3 != rl && c3 != c1 && c3 != c2;
+    while (__any_sync(0xffffffffu, n1 || n2 || n3)) {
+      if (n1 || n2 || n3) {
+        const uint32_t pick = n1 ? c1 : (n2 ? c2 : c3);
+        if (n1)
+          n1 = false;
+        else if (n2)
+          n2 = false;
+        else
+          n3 = false;
+        unite_s(L, pick, rl);
       }
     }
     if (lane == rs && x < g.Wd && vcur != 127) atomicAdd(&cnt[rl], (uint32_t)__popc(run_mask));
@@ -386,9 +364,9 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.nroots, 0, sizeof(uint32_t) * nframes, s);
   // Tune::ccl_tma: 1 = tiles staged in shared memory by TMA, 0 = staged by plain loads (also the path without the driver entry point)
   if (ws.tune.ccl_tma && ws.use_tma)
-    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.tune.x[1], ws.thr_tmap);
+    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.thr_tmap);
   else
-    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.tune.x[1], ws.thr_tmap);
+    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.thr_tmap);
   k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
   k_ccl_roots<<<dim3(ROOT_CTAS, nframes), 256, 0, s>>>(g, ws.lab, ws.csize, ws.roots, ws.nroots, Wp);
   dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);

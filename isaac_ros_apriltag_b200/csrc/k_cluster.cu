@@ -210,15 +210,19 @@ __global__ void __launch_bounds__(256, EMIT ? 6 : 8) k_cluster_pass4(Geo g, cons
           }
           peers[u] = __match_any_sync(act, key[u]);
           const int leader = __ffs(peers[u]) - 1;
+          // (the atomic's return value is not touched before (C): the next chunk's work issues behind it)
           if ((int)lane == leader && cur[u] == key[u] && off[u] != 0xffffffffu)
-            base[u] = off[u] + atomicAdd(&hcur[ho + slot[u]], (uint32_t)__popc(peers[u]));
+            base[u] = atomicAdd(&hcur[ho + slot[u]], (uint32_t)__popc(peers[u]));
+          else
+            off[u] = 0xffffffffu;
         }
         // (C) the points go to their cluster's segment
 #pragma unroll
         for (int u = 0; u < kPipe; u++) {
           if (peers[u] == 0u) continue;
-          const uint32_t bs = __shfl_sync(peers[u], base[u], __ffs(peers[u]) - 1);
-          if (bs != 0xffffffffu) pts[bs + __popc(peers[u] & ((1u << lane) - 1))] = s_pt[wid][c0 + 32 * u + (int)lane];
+          const int leader = __ffs(peers[u]) - 1;
+          const uint32_t o = __shfl_sync(peers[u], off[u], leader), bs = __shfl_sync(peers[u], base[u], leader);
+          if (o != 0xffffffffu) pts[o + bs + __popc(peers[u] & ((1u << lane) - 1))] = s_pt[wid][c0 + 32 * u + (int)lane];
         }
       }
     }
@@ -226,123 +230,119 @@ __global__ void __launch_bounds__(256, EMIT ? 6 : 8) k_cluster_pass4(Geo g, cons
   }
 }
 
-// One CTA per (frame, table segment).  Pass 1 totals -> one reservation in the global cluster / point pools,
-// pass 2 ordered allocation inside the reservation (clusters of a segment appear in table-slot order).
+// One CTA per (frame, table segment of kSelSeg slots).  A thread owns kSelPT consecutive slots and keeps their counts in
+// registers: one block scan gives the segment's totals (-> one reservation in the global cluster / point pools) and every
+// slot's position inside the reservation (clusters of a segment appear in table-slot order).  The table is read once.
+constexpr int kSelPT = 16, kSelSeg = 1024 * kSelPT;
 __global__ void __launch_bounds__(1024) k_cluster_select(Geo g, const unsigned long long *__restrict__ hkey,
                                                          const uint32_t *__restrict__ hcnt, uint32_t *__restrict__ hoff,
                                                          uint32_t *__restrict__ hcur, ClusterRec *__restrict__ clusters,
                                                          uint32_t *__restrict__ counters, int segs) {
   const int fr = blockIdx.x / segs, seg = blockIdx.x % segs;
-  const uint32_t seg_len = g.hcap / (uint32_t)segs;
+  const uint32_t seg_len = g.hcap / (uint32_t)segs;  // <= kSelSeg; a multiple of 4 (hcap is a power of two >= 4 * segs)
   const size_t ho = (size_t)fr * g.hcap + (size_t)seg * seg_len;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   __shared__ uint32_t s_c[32], s_p[32];
-  __shared__ uint32_t s_base_c, s_base_p, s_run_c, s_run_p, s_ok;
-  // pass 1
+  __shared__ uint32_t s_base_c, s_base_p, s_ok;
+  const uint32_t i0 = (uint32_t)tid * kSelPT;
+  uint32_t c[kSelPT];
+#pragma unroll
+  for (int q = 0; q < kSelPT / 4; q++) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i0 + 4 * q < seg_len) v = *reinterpret_cast<const uint4 *>(hcnt + ho + i0 + 4 * q);
+    c[4 * q] = v.x;
+    c[4 * q + 1] = v.y;
+    c[4 * q + 2] = v.z;
+    c[4 * q + 3] = v.w;
+  }
   uint32_t nc = 0, np = 0;
-  for (uint32_t i = tid; i < seg_len; i += 1024) {
-    uint32_t c = hcnt[ho + i];
-    if (c >= 24u && c <= g.max_cluster_pts) {
-      nc++;
-      np += c;
+#pragma unroll
+  for (int k = 0; k < kSelPT; k++) {
+    const bool keep = c[k] >= 24u && c[k] <= g.max_cluster_pts;
+    nc += keep ? 1u : 0u;
+    np += keep ? c[k] : 0u;
+  }
+  // block scan of (clusters, points) per thread
+  uint32_t ic = nc, ip = np;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, o), tp = __shfl_up_sync(0xffffffffu, ip, o);
+    if (lane >= o) {
+      ic += tc;
+      ip += tp;
     }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    nc += __shfl_xor_sync(0xffffffffu, nc, o);
-    np += __shfl_xor_sync(0xffffffffu, np, o);
-  }
-  if (lane == 0) {
-    s_c[wid] = nc;
-    s_p[wid] = np;
+  if (lane == 31) {
+    s_c[wid] = ic;
+    s_p[wid] = ip;
   }
   __syncthreads();
-  if (tid == 0) {
-    uint32_t tc = 0, tp = 0;
-    for (int w = 0; w < 32; w++) {
-      tc += s_c[w];
-      tp += s_p[w];
+  if (wid == 0) {
+    const uint32_t vc = s_c[lane], vp = s_p[lane];
+    uint32_t jc = vc, jp = vp;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t tc = __shfl_up_sync(0xffffffffu, jc, o), tp = __shfl_up_sync(0xffffffffu, jp, o);
+      if (lane >= o) {
+        jc += tc;
+        jp += tp;
+      }
     }
-    uint32_t bc = atomicAdd(&counters[CNT_CLUSTERS], tc);
-    uint32_t bp = atomicAdd(&counters[CNT_POINTS], tp);
-    uint32_t ok = 1;
-    if (bc + tc > g.clu_cap) {
-      atomicOr(&counters[CNT_STATUS], (uint32_t)ST_CLUSTERS_FULL);
-      ok = 0;
+    s_c[lane] = jc - vc;  // exclusive warp offsets
+    s_p[lane] = jp - vp;
+    if (lane == 31) {  // totals of the segment: one reservation
+      const uint32_t tc = jc, tp = jp;
+      const uint32_t bc = atomicAdd(&counters[CNT_CLUSTERS], tc);
+      const uint32_t bp = atomicAdd(&counters[CNT_POINTS], tp);
+      uint32_t ok = 1;
+      if (bc + tc > g.clu_cap) {
+        atomicOr(&counters[CNT_STATUS], (uint32_t)ST_CLUSTERS_FULL);
+        ok = 0;
+      }
+      if (bp + tp > g.pts_cap) {
+        atomicOr(&counters[CNT_STATUS], (uint32_t)ST_POINTS_FULL);
+        ok = 0;
+      }
+      s_base_c = bc;
+      s_base_p = bp;
+      s_ok = ok;
     }
-    if (bp + tp > g.pts_cap) {
-      atomicOr(&counters[CNT_STATUS], (uint32_t)ST_POINTS_FULL);
-      ok = 0;
-    }
-    s_base_c = bc;
-    s_base_p = bp;
-    s_run_c = 0;
-    s_run_p = 0;
-    s_ok = ok;
   }
   __syncthreads();
   const bool ok = s_ok != 0;
-  // pass 2: chunked block scan in slot order
-  for (uint32_t i0 = 0; i0 < seg_len; i0 += 1024) {
-    const uint32_t i = i0 + tid;
-    uint32_t c = (i < seg_len) ? hcnt[ho + i] : 0;
-    const bool would_keep = c >= 24u && c <= g.max_cluster_pts;
-    const bool keep = ok && would_keep;
-    uint32_t fc = would_keep ? 1u : 0u, fp = would_keep ? c : 0u;  // (positions are those of the reservation, kept or not)
-    // inclusive warp scan
-    uint32_t ic = fc, ip = fp;
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t tc = __shfl_up_sync(0xffffffffu, ic, o), tp = __shfl_up_sync(0xffffffffu, ip, o);
-      if (lane >= o) {
-        ic += tc;
-        ip += tp;
-      }
-    }
-    if (lane == 31) {
-      s_c[wid] = ic;
-      s_p[wid] = ip;
-    }
-    __syncthreads();
-    if (wid == 0) {
-      uint32_t vc = s_c[lane], vp = s_p[lane];
-      uint32_t jc = vc, jp = vp;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t tc = __shfl_up_sync(0xffffffffu, jc, o), tp = __shfl_up_sync(0xffffffffu, jp, o);
-        if (lane >= o) {
-          jc += tc;
-          jp += tp;
-        }
-      }
-      s_c[lane] = jc - vc;  // exclusive warp offsets
-      s_p[lane] = jp - vp;
-    }
-    __syncthreads();
-    const uint32_t run_c = s_run_c, run_p = s_run_p;
-    const uint32_t ec = run_c + s_c[wid] + ic - fc;  // exclusive index of this slot's cluster
-    const uint32_t ep = run_p + s_p[wid] + ip - fp;
-    if (i < seg_len) {
-      if (keep) {
+  uint32_t ec = s_base_c + s_c[wid] + ic - nc;  // position of my first kept slot inside the pools
+  uint32_t ep = s_base_p + s_p[wid] + ip - np;
+  uint32_t off[kSelPT];
+#pragma unroll
+  for (int k = 0; k < kSelPT; k++) {
+    const bool would_keep = c[k] >= 24u && c[k] <= g.max_cluster_pts;
+    off[k] = 0xffffffffu;
+    if (would_keep) {
+      const uint32_t i = i0 + k;
+      if (ok) {
         ClusterRec r;
         r.key = hkey[ho + i];
-        r.offset = s_base_p + ep;
-        r.count = c;
+        r.offset = ep;
+        r.count = c[k];
         r.frame = (uint32_t)fr;
         r.pad = 0;
-        clusters[s_base_c + ec] = r;
-        hoff[ho + i] = s_base_p + ep;
-      } else {
+        clusters[ec] = r;
+        off[k] = ep;
+      } else if (ec < g.clu_cap) {
         // A reservation that did not fit keeps its range of the cluster list (the counter stays advanced): its records are
         // written EMPTY (count 0), so that a consumer that walks [0, min(CNT_CLUSTERS, clu_cap)) never reads a stale record.
-        if (!ok && would_keep && s_base_c + ec < g.clu_cap) clusters[s_base_c + ec] = ClusterRec{hkey[ho + i], 0u, 0u, (uint32_t)fr, 0u};
-        hoff[ho + i] = 0xffffffffu;
+        clusters[ec] = ClusterRec{hkey[ho + i], 0u, 0u, (uint32_t)fr, 0u};
       }
-      hcur[ho + i] = 0;
+      ec++;
+      ep += c[k];
     }
-    __syncthreads();
-    if (tid == 1023) {
-      s_run_c = ec + fc;
-      s_run_p = ep + fp;
+  }
+#pragma unroll
+  for (int q = 0; q < kSelPT / 4; q++) {
+    if (i0 + 4 * q < seg_len) {
+      *reinterpret_cast<uint4 *>(hoff + ho + i0 + 4 * q) = make_uint4(off[4 * q], off[4 * q + 1], off[4 * q + 2], off[4 * q + 3]);
+      *reinterpret_cast<uint4 *>(hcur + ho + i0 + 4 * q) = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
   }
 }
 
@@ -352,7 +352,7 @@ int launch_cluster(const Workspace &ws, int nframes, cudaStream_t s) {
   if (g.Wd < 3 || g.Hd < 3) return 0;
   cudaMemsetAsync(ws.hkey, 0, (size_t)nframes * g.hcap * sizeof(unsigned long long), s);
   cudaMemsetAsync(ws.hcnt, 0, (size_t)nframes * g.hcap * sizeof(uint32_t), s);
-  const int segs = g.hcap >= 65536 ? 4 : 1;  // hcap is a power of two
+  const int segs = g.hcap > (uint32_t)kSelSeg ? (int)(g.hcap / kSelSeg) : 1;  // hcap is a power of two
   dim3 g4(((g.Wd + 3) / 4 + 255) / 256, g.Hd - 2, nframes);
   k_cluster_pass4<false><<<g4, 256, 0, s>>>(g, ws.thr2, ws.lab, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.pts, ws.counters, Wp);
   k_cluster_select<<<nframes * segs, 1024, 0, s>>>(g, ws.hkey, ws.hcnt, ws.hoff, ws.hcur, ws.clusters, ws.counters, segs);

@@ -309,36 +309,20 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
           has = 1;
         }
       }
-      if (fp.variant) {
-        const int cnt = min(32, nsamples - s0);
-        for (int k = 0; k < cnt; k++) {
-          const int h = __shfl_sync(0xffffffffu, has, k);
-          const double bx = shfl_d(bestx, k), by = shfl_d(besty, k);
-          if (h) {
-            Mx += bx;
-            My += by;
-            Mxx += bx * bx;
-            Mxy += bx * by;
-            Myy += by * by;
-            N++;
-          }
-        }
-      } else {
-        // moments of the 32 samples: butterfly sums (every lane ends with the same value).  The oracle adds the samples one
-        // after the other; the association differs in the last bits of sums whose line parameters are rounded to float below.
-        double m5[5] = {has ? bestx : 0.0, has ? besty : 0.0, has ? bestx * bestx : 0.0, has ? bestx * besty : 0.0, has ? besty * besty : 0.0};
+      // moments of the 32 samples: butterfly sums (every lane ends with the same value).  The oracle adds the samples one
+      // after the other; the association differs in the last bits of sums whose line parameters are rounded to float below.
+      double m5[5] = {has ? bestx : 0.0, has ? besty : 0.0, has ? bestx * bestx : 0.0, has ? bestx * besty : 0.0, has ? besty * besty : 0.0};
 #pragma unroll
-        for (int of = 16; of > 0; of >>= 1) {
+      for (int of = 16; of > 0; of >>= 1) {
 #pragma unroll
-          for (int q = 0; q < 5; q++) m5[q] += shfl_xor_d(m5[q], of);
-        }
-        Mx += m5[0];
-        My += m5[1];
-        Mxx += m5[2];
-        Mxy += m5[3];
-        Myy += m5[4];
-        N += (double)__popc(__ballot_sync(0xffffffffu, has != 0));
+        for (int q = 0; q < 5; q++) m5[q] += shfl_xor_d(m5[q], of);
       }
+      Mx += m5[0];
+      My += m5[1];
+      Mxx += m5[2];
+      Mxy += m5[3];
+      Myy += m5[4];
+      N += (double)__popc(__ballot_sync(0xffffffffu, has != 0));
     }
     double Ex = Mx / N, Ey = My / N;
     double Cxx = Mxx / N - Ex * Ex;

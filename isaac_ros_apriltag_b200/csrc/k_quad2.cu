@@ -117,7 +117,7 @@ __device__ __forceinline__ void qf_register_work(uint32_t ci, uint32_t off, int 
 constexpr int kBucketLimit = 1024;
 template <int THREADS, int E, int MODE, int WPC>
 __host__ __device__ constexpr size_t qf_sort_smem() {
-  return MODE == 1 ? 0 : MODE == 0 ? (size_t)2 * THREADS * E * 8 * WPC : ((size_t)THREADS * E * 8 + (size_t)(THREADS * E + 2) * 4) * WPC;
+  return MODE == 1 ? 0 : MODE == 0 ? (size_t)2 * THREADS * E * 8 * WPC : ((size_t)THREADS * E * 8 + (size_t)(THREADS * E / 2 + 2) * 4) * WPC;
 }
 
 template <int THREADS, int E, int ITEMS, int MINB, int WPC, int MODE>
@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
               const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
               const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint4 *__restrict__ work,
-              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp, int nb_shift) {
+              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
   static_assert(MODE != 1 || NW == 1, "register sort: one-warp clusters only");
-  extern __shared__ unsigned long long dsm_sort[];  // per worker: MODE 0 [2 * NCAP] keys; MODE 2 [NCAP] keys + [NCAP + 2] counters
+  extern __shared__ unsigned long long dsm_sort[];  // per worker: MODE 0 [2 * NCAP] keys; MODE 2 [NCAP] keys + [NCAP / 2 + 2] counters
   const int grp = WPC > 1 ? (int)(threadIdx.x / THREADS) : 0;
   unsigned long long *skeys = dsm_sort + (size_t)grp * (qf_sort_smem<THREADS, E, MODE == 1 ? 0 : MODE, 1>() / 8), *stmp = skeys + NCAP;
   uint32_t *cnt = reinterpret_cast<uint32_t *>(stmp);  // MODE 2: bucket counters, then bucket start offsets
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
         if (lane * E + k < sz) keys_g[lane * E + k] = (v[k] & 0xffffffffull) | ((unsigned long long)(uint32_t)g2[k] << 32);
     } else if (MODE == 2) {
       int NB = 32;
-      while ((NB << nb_shift) < sz) NB <<= 1;  // power of two, n / 2 <= NB <= NCAP / 2 (nb_shift = 1) or n <= NB <= NCAP (0)
+      while (NB * 2 < sz) NB <<= 1;  // power of two, n / 2 <= NB <= NCAP / 2 (NCAP >= 64); measured: NB >= n is slower (4.01 vs 3.87 ms)
       const float nbq = (float)(NB / 4);
       for (int i = tid; i < NB; i += THREADS) cnt[i] = 0u;
       unsigned long long v[E];
@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(256, 2)
 // ---------------------------------------------------------------------------------------------------------------------
 // k_qf_window
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int QW_WARPS = 4;
 constexpr int QW_SLOTS = 32 * kQfSlotsPerLane;
 
+template <int QW_WARPS>
 __global__ void __launch_bounds__(32 * QW_WARPS)
     k_qf_window(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ qinfo,
                 const uint4 *__restrict__ work, uint32_t work_cap, const unsigned long long *__restrict__ keys,
@@ -888,7 +888,23 @@ static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t 
     ctas_per_sm[dev] = std::max(1, n);
   }
   kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo,
-                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g), ws.tune.x[2] ? 0 : 1);
+                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
+}
+
+// warps per CTA of k_qf_window: 14.3 KB of shared memory per warp; 3 per CTA -> 5 CTAs = 15 warps per SM (4 per CTA: 3 CTAs = 12 warps)
+template <int QW_WARPS>
+static void launch_window(const Workspace &ws, int sms, cudaStream_t s) {
+  constexpr size_t smem = (size_t)QW_WARPS * 8 * QW_SLOTS * sizeof(double);
+  static int ctas_per_sm[64] = {};
+  const int di = device_index();
+  if (!ctas_per_sm[di]) {
+    cudaFuncSetAttribute(k_qf_window<QW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_qf_window<QW_WARPS>, 32 * QW_WARPS, smem);
+    ctas_per_sm[di] = std::max(1, n);
+  }
+  k_qf_window<QW_WARPS><<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(ws.g, ws.fp, ws.clusters, ws.qinfo, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps,
+                                                                            ws.qwtot, ws.qwnmax, ws.counters);
 }
 
 int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
@@ -906,40 +922,21 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kQuadAux; i++) cudaStreamWaitEvent(ws.aux[i], ws.ev_fork, 0);
   k_qf_sort_global<<<sms * 2, 256, 0, s>>>(g, ws.fp, ws.clusters, ws.bin_idx, 7, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo, ws.qwbase, ws.qwork,
                                           ws.qwork_cap, ws.counters, at_Wp(g));                 // n > 8192 (4K-class frames)
-  if (ws.tune.x[0] == 0) {
-    launch_sort_bin<512, 16, 16, 2, 1, 2>(ws, 6, sms, ws.aux[0]);  // n <= 8192
-    launch_sort_bin<256, 16, 16, 4, 1, 2>(ws, 5, sms, ws.aux[1]);  // n <= 4096
-    launch_sort_bin<256, 8, 8, 4, 1, 2>(ws, 4, sms, ws.aux[2]);    // n <= 2048
-    launch_sort_bin<128, 8, 8, 8, 1, 2>(ws, 3, sms, ws.aux[3]);    // n <= 1024
-    launch_sort_bin<64, 8, 8, 16, 1, 2>(ws, 2, sms, ws.aux[4]);    // n <= 512
-    launch_sort_bin<32, 8, 8, 4, 8, 2>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
-    launch_sort_bin<32, 4, 4, 4, 8, 1>(ws, 0, sms, ws.aux[6]);     // n <= 128: register bitonic network (measured: 0.218 vs 0.226 ms)
-  } else {
-    launch_sort_bin<512, 16, 16, 1, 1, 0>(ws, 6, sms, ws.aux[0]);  // n <= 8192
-    launch_sort_bin<256, 16, 16, 3, 1, 0>(ws, 5, sms, ws.aux[1]);  // n <= 4096
-    launch_sort_bin<256, 8, 8, 4, 1, 0>(ws, 4, sms, ws.aux[2]);    // n <= 2048
-    launch_sort_bin<128, 8, 8, 8, 1, 0>(ws, 3, sms, ws.aux[3]);    // n <= 1024
-    launch_sort_bin<64, 8, 8, 16, 1, 0>(ws, 2, sms, ws.aux[4]);    // n <= 512
-    launch_sort_bin<32, 8, 8, 4, 8, 0>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
-    launch_sort_bin<32, 4, 4, 4, 8, 1>(ws, 0, sms, ws.aux[6]);     // n <= 128: registers only
-  }
+  launch_sort_bin<512, 16, 16, 2, 1, 2>(ws, 6, sms, ws.aux[0]);  // n <= 8192
+  launch_sort_bin<256, 16, 16, 4, 1, 2>(ws, 5, sms, ws.aux[1]);  // n <= 4096
+  launch_sort_bin<256, 8, 8, 4, 1, 2>(ws, 4, sms, ws.aux[2]);    // n <= 2048
+  launch_sort_bin<128, 8, 8, 8, 1, 2>(ws, 3, sms, ws.aux[3]);    // n <= 1024
+  launch_sort_bin<64, 8, 8, 16, 1, 2>(ws, 2, sms, ws.aux[4]);    // n <= 512
+  launch_sort_bin<32, 8, 8, 4, 8, 2>(ws, 1, sms, ws.aux[5]);     // n <= 256: one warp per cluster, 8 workers per CTA
+  launch_sort_bin<32, 4, 4, 4, 8, 1>(ws, 0, sms, ws.aux[6]);     // n <= 128: register bitonic network (measured: 0.218 vs 0.226 ms)
   for (int i = 0; i < kQuadAux; i++) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);
   }
-  {
-    constexpr size_t smem = (size_t)QW_WARPS * 8 * QW_SLOTS * sizeof(double);
-    static int ctas_per_sm[64] = {};
-    const int di = device_index();
-    if (!ctas_per_sm[di]) {
-      cudaFuncSetAttribute(k_qf_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      int n = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_qf_window, 32 * QW_WARPS, smem);
-      ctas_per_sm[di] = std::max(1, n);
-    }
-    k_qf_window<<<sms * ctas_per_sm[di], 32 * QW_WARPS, smem, s>>>(g, ws.fp, ws.clusters, ws.qinfo, ws.qwork, ws.qwork_cap, ws.keys, ws.lfps,
-                                                                    ws.qwtot, ws.qwnmax, ws.counters);
-  }
+  if (ws.tune.x[4])
+    launch_window<4>(ws, sms, s);
+  else
+    launch_window<3>(ws, sms, s);
   {
     static int ctas_per_sm[64] = {};
     const int di = device_index();
