@@ -501,8 +501,14 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.thr, B * Pp);
   ALLOC(ws.thr2, B * Pp);
   ALLOC(ws.lab, B * Pp);
+  ALLOC(ws.lab0, B * Pp);
   ALLOC(ws.csize, B * Pp);
   ALLOC(ws.roots, B * Pp);
+  {
+    const size_t ntl = (size_t)((g.Wd + 31) / 32) * ((g.Hd + 31) / 32);
+    ALLOC(ws.ccl_req, (size_t)B * ntl * 192);
+    ALLOC(ws.ccl_reqcnt, (size_t)B * ntl);
+  }
   ALLOC(ws.nroots, B);
   ALLOC(ws.hkey, (size_t)B * g.hcap);
   ALLOC(ws.hcnt, (size_t)B * g.hcap);
@@ -745,8 +751,14 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
   v.tmin += (size_t)f0 * g.th * at_twp(g);
   v.tmax += (size_t)f0 * g.th * at_twp(g);
   v.lab += (size_t)f0 * Pp;
+  v.lab0 += (size_t)f0 * Pp;
   v.csize += (size_t)f0 * Pp;
   v.roots += (size_t)f0 * Pp;
+  {
+    const size_t ntl = (size_t)((g.Wd + 31) / 32) * ((g.Hd + 31) / 32);
+    v.ccl_req += (size_t)f0 * ntl * 192;
+    v.ccl_reqcnt += (size_t)f0 * ntl;
+  }
   v.nroots += f0;
   v.hkey += (size_t)f0 * g.hcap;
   v.hcnt += (size_t)f0 * g.hcap;

@@ -133,7 +133,10 @@ struct Workspace {
   DevFamily fams[kMaxFamilies];
   FrameDesc *frames;
   uint8_t *dec, *dec_tmp, *tmin, *tmax, *thr, *thr2;
-  uint32_t *lab, *csize;
+  uint32_t *lab, *csize;     // final labels (global representative per pixel); pixel counts at representatives
+  uint32_t *lab0;            // CCL working labels: tile-local roots, then tile roots -> global roots (+ size flag in bit 31)
+  uint2 *ccl_req;            // [B][tiles][192] cross-tile links (pixel, neighbour) found by the CCL tile kernel
+  uint32_t *ccl_reqcnt;      // [B][tiles]
   uint32_t *roots, *nroots;  // [B][Hd][Wp] pixel indices of the CCL tile roots of a frame (a list: the first nroots[frame] entries), [B]
   unsigned long long *hkey;
   uint32_t *hcnt, *hoff, *hcur;

@@ -7,10 +7,11 @@
 //   1. k_ccl_tile_sweep : ONE WARP per 32x32 tile (staged incl. halo by a TMA bulk tensor copy), rows top to bottom: runs by ballot,
 //                         a run that touches the component above inherits its label, shared-memory unions only where a run
 //                         touches two labels; pixel counts per local root
-//   2. k_ccl_border     : only links that cross tile borders are merged in global memory
+//   2. k_ccl_border     : only links that cross tile borders are merged in global memory (lists written by the tile kernel)
 //   3. k_ccl_roots      : the former tile roots (the frame's root list, ~5 % of the pixels) chase to their global root and hand
 //                         over their count
-//   4. k_ccl_flatmark   : one gather per pixel lab[lab[p]], fused with the size gate thr2 (components < 25 px -> 127)
+//   4. k_ccl_rootflag   : the size gate (< 25 px) is decided per tile root and stored in bit 31 of its label
+//   5. k_ccl_flatmark   : one gather per pixel lab0[lab0[p]] -> final labels (lab) and thr2 (thr with small components -> 127)
 // Algorithmic bytes per frame: read Pd (thr) + write 4*Pd (labels) = 5*Pd (SURVEY 8d contract figure).
 #include "detector.h"
 
@@ -111,13 +112,15 @@ constexpr int TOFF = 16;    // column of pixel x0 (TMA needs the box start 16-by
 // CTA = 4 warps = 4 horizontally adjacent tiles; each tile is staged (with halo) by its own TMA box.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SWEEP_TILES = 4;
+constexpr int kReqCap = 192;  // cross-border links of a tile: <= 3 * 32 (row 0) + 32 + 31 + 31 (columns 0 / 31)
 constexpr int TBYTES = TPITCH * (TH + 1);              // one staged tile + halo row
 constexpr int TSLOT = (TBYTES + 127) & ~127;           // 128-byte aligned slots
 
 template <bool USE_TMA>
 __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
                                                                       uint32_t *__restrict__ csize, uint32_t *__restrict__ roots,
-                                                                      uint32_t *__restrict__ nroots, int Wp,
+                                                                      uint32_t *__restrict__ nroots, uint2 *__restrict__ reqs,
+                                                                      uint32_t *__restrict__ reqcnt, int Wp,
                                                                       const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_t[SWEEP_TILES][TSLOT];
   __shared__ __align__(8) unsigned long long mbar;
@@ -263,41 +266,54 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     szf[gi] = cnt[ly * TW + lane];
     rootf[base++] = (uint32_t)gi;
   }
+  // The tile's cross-border links (a few dozen, at most kReqCap) as a list of (pixel, neighbour) pairs: k_ccl_border no longer
+  // re-reads the threshold image around every border pixel, it only walks the lists.  The links of row 0 (lane <-> column) and of
+  // columns 0 / 31 (lane <-> row) are re-evaluated here from the staged tile: ~100 instructions per tile instead of ~10 per row.
+  {
+    const int tiles_x = (g.Wd + TW - 1) / TW, tile = blockIdx.y * tiles_x + blockIdx.x * SWEEP_TILES + wid;
+    const size_t tl = (size_t)fr * tiles_x * gridDim.y + tile;
+    uint2 *rq = reqs + tl * kReqCap;
+    uint32_t nreq = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    auto emit = [&](bool flag, uint32_t a, uint32_t b) {
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      if (flag) rq[nreq + __popc(bal & lt)] = make_uint2(a, b);
+      nreq += __popc(bal);
+    };
+    auto links_at = [&](int lx, int ly) -> Nb {
+      Nb n = {false, false, false, false};
+      const uint8_t *tr = t + (ly + 1) * TPITCH + lx + TOFF, *tu = tr - TPITCH;
+      if (ly < rows && x0 + lx < g.Wd) n = ccl_links(tr[0], tr[-1], tu[0], tu[-1], tu[1], x0 + lx, y0 + ly, g.Wd);
+      return n;
+    };
+    const Nb n0 = links_at(lane, 0);
+    const uint32_t me0 = (uint32_t)(y0 * Wp + x);
+    emit(n0.U, me0, me0 - Wp);
+    emit(n0.UL, me0, me0 - Wp - 1);
+    emit(n0.UR, me0, me0 - Wp + 1);
+    const Nb nl = links_at(0, lane), nr = links_at(TW - 1, lane);
+    const uint32_t meL = (uint32_t)((y0 + lane) * Wp + x0), meR = meL + TW - 1;
+    emit(nl.L, meL, meL - 1);
+    emit(nl.UL && lane > 0, meL, meL - Wp - 1);  // (row 0 is in the first list)
+    emit(nr.UR && lane > 0, meR, meR - Wp + 1);
+    if (lane == 0) reqcnt[tl] = nreq;
+  }
 }
 
-// one thread per tile-border pixel: top row (TW), left column rows 1..TH-1, right column rows 1..TH-1
-__global__ void __launch_bounds__(128) k_ccl_border(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab, int Wp) {
-  const int fr = blockIdx.z;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int b = threadIdx.x;
-  int lx, ly;
-  if (b < TW) {
-    lx = b;
-    ly = 0;
-  } else if (b < TW + TH - 1) {
-    lx = 0;
-    ly = b - TW + 1;
-  } else if (b < TW + 2 * (TH - 1)) {
-    lx = TW - 1;
-    ly = b - (TW + TH - 1) + 1;
-  } else {
-    return;
-  }
-  const int x = x0 + lx, y = y0 + ly;
-  if (x >= g.Wd || y >= g.Hd) return;
-  const uint8_t *img = thr + (size_t)fr * g.Hd * Wp;
+// Cross-tile merges in global memory: one warp per tile walks the tile's list of (pixel, neighbour) links written by the tile kernel.
+__global__ void __launch_bounds__(128) k_ccl_border(Geo g, uint32_t *__restrict__ lab, const uint2 *__restrict__ reqs,
+                                                    const uint32_t *__restrict__ reqcnt, int ntiles, int Wp) {
+  const int fr = blockIdx.y;
+  const int lane = threadIdx.x & 31, tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (tile >= ntiles) return;
+  const size_t tl = (size_t)fr * ntiles + tile;
+  const uint32_t n = min(reqcnt[tl], (uint32_t)kReqCap);
+  const uint2 *rq = reqs + tl * kReqCap;
   uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
-  auto T = [&](int xx, int yy) -> int {
-    if (xx < 0 || yy < 0 || xx >= g.Wd || yy >= g.Hd) return 127;
-    return img[(size_t)yy * Wp + xx];
-  };
-  int v = T(x, y);
-  Nb n = ccl_links(v, T(x - 1, y), T(x, y - 1), T(x - 1, y - 1), T(x + 1, y - 1), x, y, g.Wd);
-  const uint32_t me = (uint32_t)(y * Wp + x);
-  if (n.L && lx == 0) unite_g(labf, me, me - 1);
-  if (n.U && ly == 0) unite_g(labf, me, me - Wp);
-  if (n.UL && (ly == 0 || lx == 0)) unite_g(labf, me, me - Wp - 1);
-  if (n.UR && (ly == 0 || lx == TW - 1)) unite_g(labf, me, me - Wp + 1);
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint2 r = rq[i];
+    unite_g(labf, r.x, r.y);
+  }
 }
 
 // Flatten + size gate in two phases.  After the tile and border kernels every pixel points at a (former) tile root, and only
@@ -326,33 +342,48 @@ __global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_flatmark(Geo g, const uint8_t *__restrict__ thr, uint32_t *__restrict__ lab,
-                                                      const uint32_t *__restrict__ csize, uint8_t *__restrict__ thr2, int Wp) {
+// Phase A': the size gate is decided once per (former) tile root and travels in bit 31 of its label, so that phase B needs no
+// second gather into the size image.
+constexpr uint32_t kSmallFlag = 0x80000000u;
+__global__ void __launch_bounds__(256) k_ccl_rootflag(Geo g, uint32_t *__restrict__ lab, const uint32_t *__restrict__ csize,
+                                                      const uint32_t *__restrict__ roots, const uint32_t *__restrict__ nroots, int Wp) {
+  const int fr = blockIdx.y;
+  const size_t fo = (size_t)fr * g.Hd * Wp;
+  uint32_t *L = lab + fo;
+  const uint32_t n = nroots[fr];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t me = roots[fo + i];
+    const uint32_t a = L[me];  // the global root (k_ccl_roots); only this thread writes L[me]
+    if (csize[fo + a] < 25u) L[me] = a | kSmallFlag;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatmark(Geo g, const uint8_t *__restrict__ thr, const uint32_t *__restrict__ lab0,
+                                                      uint32_t *__restrict__ lab, uint8_t *__restrict__ thr2, int Wp) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   const int fr = blockIdx.z;
   if (x4 >= g.Wd) return;
   const size_t fo = (size_t)fr * g.Hd * Wp;
-  uint32_t *L = lab + fo;
+  const uint32_t *L = lab0 + fo;  // (read only here: the flags of the tile roots must survive until every pixel has seen them)
   const uint32_t me0 = (uint32_t)(y * Wp + x4);
   const uchar4 tv = *reinterpret_cast<const uchar4 *>(thr + fo + me0);
   const uint4 pv = *reinterpret_cast<const uint4 *>(L + me0);
   uint8_t v[4] = {tv.x, tv.y, tv.z, tv.w};
   const uint32_t p[4] = {pv.x, pv.y, pv.z, pv.w};
-  uint32_t r[4], c[4];
-  bool live[4];
+  uint32_t r[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     // AprilRobotics never connects 127 pixels (singletons); padding columns are ignored
-    live[k] = v[k] != 127 && x4 + k < g.Wd;
-    r[k] = live[k] ? __ldcg(&L[p[k]]) : me0 + k;
+    const bool live = v[k] != 127 && x4 + k < g.Wd;
+    r[k] = live ? L[p[k] & ~kSmallFlag] : me0 + k;
   }
 #pragma unroll
-  for (int k = 0; k < 4; k++) c[k] = live[k] ? __ldcg(&csize[fo + r[k]]) : 25u;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (c[k] < 25) v[k] = 127;
-  *reinterpret_cast<uint4 *>(L + me0) = make_uint4(r[0], r[1], r[2], r[3]);
+  for (int k = 0; k < 4; k++) {
+    if (r[k] & kSmallFlag) v[k] = 127;
+    r[k] &= ~kSmallFlag;
+  }
+  *reinterpret_cast<uint4 *>(lab + fo + me0) = make_uint4(r[0], r[1], r[2], r[3]);
   *reinterpret_cast<uchar4 *>(thr2 + fo + me0) = make_uchar4(v[0], v[1], v[2], v[3]);
 }
 
@@ -364,14 +395,16 @@ int launch_ccl(const Workspace &ws, int nframes, cudaStream_t s) {
   cudaMemsetAsync(ws.nroots, 0, sizeof(uint32_t) * nframes, s);
   // Tune::ccl_tma: 1 = tiles staged in shared memory by TMA, 0 = staged by plain loads (also the path without the driver entry point)
   if (ws.tune.ccl_tma && ws.use_tma)
-    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.thr_tmap);
+    k_ccl_tile_sweep<true><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab0, ws.csize, ws.roots, ws.nroots, ws.ccl_req, ws.ccl_reqcnt, Wp, ws.thr_tmap);
   else
-    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.roots, ws.nroots, Wp, ws.thr_tmap);
-  k_ccl_border<<<gt, 128, 0, s>>>(g, ws.thr, ws.lab, Wp);
-  k_ccl_roots<<<dim3(ROOT_CTAS, nframes), 256, 0, s>>>(g, ws.lab, ws.csize, ws.roots, ws.nroots, Wp);
+    k_ccl_tile_sweep<false><<<gs, 32 * SWEEP_TILES, 0, s>>>(g, ws.thr, ws.lab0, ws.csize, ws.roots, ws.nroots, ws.ccl_req, ws.ccl_reqcnt, Wp, ws.thr_tmap);
+  const int ntl = (int)(gt.x * gt.y);
+  k_ccl_border<<<dim3((ntl + 3) / 4, nframes), 128, 0, s>>>(g, ws.lab0, ws.ccl_req, ws.ccl_reqcnt, ntl, Wp);
+  k_ccl_roots<<<dim3(ROOT_CTAS, nframes), 256, 0, s>>>(g, ws.lab0, ws.csize, ws.roots, ws.nroots, Wp);
   dim3 gp(((g.Wd + 3) / 4 + 255) / 256, g.Hd, nframes);
-  k_ccl_flatmark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab, ws.csize, ws.thr2, Wp);
-  return 5;
+  k_ccl_rootflag<<<dim3(ROOT_CTAS, nframes), 256, 0, s>>>(g, ws.lab0, ws.csize, ws.roots, ws.nroots, Wp);
+  k_ccl_flatmark<<<gp, 256, 0, s>>>(g, ws.thr, ws.lab0, ws.lab, ws.thr2, Wp);
+  return 6;
 }
 
 }  // namespace b200at

@@ -810,8 +810,16 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
   // two kernels of 128 / 116 registers instead of one fused kernel that needs 167 and had to be capped at 128 (measured: 2.13 -> 1.69 ms)
   const int ctas = sm_count() * kDecodeCtasPerSm;
-  k_refine<false, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
-  k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+  if (ws.tune.x[5] == 1) {  // A/B: 6 CTAs per SM (85 registers)
+    k_refine<false, 6><<<sm_count() * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    k_decode_bits<6><<<sm_count() * 6, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+  } else if (ws.tune.x[5] == 2) {  // A/B: 5 CTAs per SM (102 registers)
+    k_refine<false, 5><<<sm_count() * 5, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    k_decode_bits<5><<<sm_count() * 5, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+  } else {
+    k_refine<false, 4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+    k_decode_bits<4><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
+  }
   return 3;
 }
 

@@ -891,7 +891,8 @@ static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t 
                                                            ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
 }
 
-// warps per CTA of k_qf_window: 14.3 KB of shared memory per warp; 3 per CTA -> 5 CTAs = 15 warps per SM (4 per CTA: 3 CTAs = 12 warps)
+// warps per CTA of k_qf_window: 14.3 KB of shared memory per warp.  Measured: 4 per CTA (3 CTAs = 12 warps per SM) 1.585 ms,
+// 3 per CTA (5 CTAs = 15 warps per SM) 1.629 ms -- the kernel is not occupancy bound.
 template <int QW_WARPS>
 static void launch_window(const Workspace &ws, int sms, cudaStream_t s) {
   constexpr size_t smem = (size_t)QW_WARPS * 8 * QW_SLOTS * sizeof(double);
@@ -933,10 +934,7 @@ int launch_quadfit_windowed(const Workspace &ws, int nframes, cudaStream_t s) {
     cudaEventRecord(ws.ev_join[i], ws.aux[i]);
     cudaStreamWaitEvent(s, ws.ev_join[i], 0);
   }
-  if (ws.tune.x[4])
-    launch_window<4>(ws, sms, s);
-  else
-    launch_window<3>(ws, sms, s);
+  launch_window<4>(ws, sms, s);
   {
     static int ctas_per_sm[64] = {};
     const int di = device_index();
