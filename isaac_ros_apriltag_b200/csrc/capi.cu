@@ -55,12 +55,12 @@ const HostFamily kHostFamilies[B200AT_NUM_FAMILIES] = {
     }                                                                                                         \
   } while (0)
 
-// B200AT_TUNE="ccl_tma=0,qf_exact=1": the per-handle knobs (detector.h, struct Tune).  Unknown keys are reported and ignored.
+// B200AT_TUNE="ccl_tma=0,qf_exact=1,qf_bucket_limit=4": the per-handle knobs (detector.h, struct Tune).  Unknown keys are reported and ignored.
 Tune parse_tune() {
   Tune t;
   t.ccl_tma = 1;
   t.qf_exact = 0;
-  for (int i = 0; i < 8; i++) t.x[i] = 0;
+  t.qf_bucket_limit = 1024;
   const char *e = getenv("B200AT_TUNE");
   if (!e) return t;
   std::string str(e);
@@ -76,7 +76,7 @@ Tune parse_tune() {
     const int v = atoi(kv.c_str() + eq + 1);
     if (k == "ccl_tma") t.ccl_tma = v;
     else if (k == "qf_exact") t.qf_exact = v;
-    else if (k.size() == 2 && k[0] == 'x' && k[1] >= '0' && k[1] <= '7') t.x[k[1] - '0'] = v;
+    else if (k == "qf_bucket_limit") t.qf_bucket_limit = v > 0 ? v : 1;
     else fprintf(stderr, "[b200apriltags] B200AT_TUNE: unknown key '%s'\n", k.c_str());
   }
   return t;
@@ -498,6 +498,8 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   ALLOC(ws.dec_tmp, ws.blur_ksz > 1 ? B * Pp : 16);
   ALLOC(ws.tmin, (size_t)B * g.th * at_twp(g));
   ALLOC(ws.tmax, (size_t)B * g.th * at_twp(g));
+  ALLOC(ws.tth, (size_t)B * ((g.Hd + 3) / 4) * (Wp / 4));
+  ALLOC(ws.tlow, (size_t)B * ((g.Hd + 3) / 4) * (Wp / 4));
   ALLOC(ws.thr, B * Pp);
   ALLOC(ws.thr2, B * Pp);
   ALLOC(ws.lab, B * Pp);
@@ -750,6 +752,8 @@ static Workspace make_view(cuAprilTagsHandle h, int f0, int c, int nch) {
   v.thr2 += (size_t)f0 * Pp;
   v.tmin += (size_t)f0 * g.th * at_twp(g);
   v.tmax += (size_t)f0 * g.th * at_twp(g);
+  v.tth += (size_t)f0 * ((g.Hd + 3) / 4) * (at_Wp(g) / 4);
+  v.tlow += (size_t)f0 * ((g.Hd + 3) / 4) * (at_Wp(g) / 4);
   v.lab += (size_t)f0 * Pp;
   v.lab0 += (size_t)f0 * Pp;
   v.csize += (size_t)f0 * Pp;

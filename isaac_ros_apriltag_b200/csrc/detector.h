@@ -123,7 +123,8 @@ struct Tune {
   int ccl_tma;    // 1 (default) = CCL tiles staged in shared memory by TMA; 0 = staged by plain loads (the pipeline is then TMA-free)
   int qf_exact;   // 1 = k_quad.cu (one CTA per cluster, serial prefix sums: float corners bit-identical to the CPU oracle);
                   // 0 (default) = k_quad2.cu (sort / windowed moments / tail: same formulas, prefix sums associated differently)
-  int x[8];       // x0..x7: A/B switches of the variant being measured (development only; 0 = default)
+  int qf_bucket_limit;  // bucket sort of the quad fit: a cluster with a bucket larger than this is sorted by the global-memory merge sort
+                        // instead (default 1024; small values route every cluster through the fallback: used by the tests)
 };
 
 struct Workspace {
@@ -133,6 +134,7 @@ struct Workspace {
   DevFamily fams[kMaxFamilies];
   FrameDesc *frames;
   uint8_t *dec, *dec_tmp, *tmin, *tmax, *thr, *thr2;
+  uint8_t *tth, *tlow;       // [B][ceil(Hd/4)][Wp/4] per-tile threshold value / low-contrast flag (tile size 4)
   uint32_t *lab, *csize;     // final labels (global representative per pixel); pixel counts at representatives
   uint32_t *lab0;            // CCL working labels: tile-local roots, then tile roots -> global roots (+ size flag in bit 31)
   uint2 *ccl_req;            // [B][tiles][192] cross-tile links (pixel, neighbour) found by the CCL tile kernel

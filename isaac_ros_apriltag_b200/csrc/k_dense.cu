@@ -226,120 +226,109 @@ __global__ void k_unsharp(Geo g, const uint8_t *__restrict__ orig, uint8_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// threshold (tile size 4): one thread per 4 horizontally adjacent tiles = 16 px x 4 rows; uint4 loads/stores.
+// threshold (tile size 4), two kernels:
+//   k_tile_thresh : per tile the 3x3 dilated min / max of the tile arrays -> threshold value + low-contrast flag (the tile
+//                   arrays are 1/16 of the image: ~3 % of the stage's bytes)
+//   k_threshold4  : one thread per 4 horizontally adjacent tiles = 16 px x 4 rows; uint4 loads / stores, one word of thresholds
+//                   and one word of flags per thread, byte compares as SIMD-in-word ops (__vcmpgtu4 = 5 instructions).  No shared
+//                   memory, no barrier: the kernel used to spend most of its 615 instructions per thread on staging the tile arrays and
+//                   on emulated byte min / max (sm_100a has no 8-bit SIMD min / max), and ran at 71 % issue utilisation and 0.74 of
+//                   the copy bandwidth.
 // Algorithmic bytes per frame: Pd read + Pd written (the metric's "threshold HBM GB/s": 2*Pd).
 // ------------------------------------------------------------------------------------------------
-// EARLY: the pixel loads are issued before the tile min/max staging and its barrier (they do not depend on it), so the two
-// memory latencies of a CTA overlap instead of adding up.
-template <int EARLY>  // 0 = off, 1 = on, 2 = on with the register budget of 6 CTAs per SM
-__global__ void __launch_bounds__(256, EARLY == 2 ? 6 : 0) k_threshold4(Geo g, const uint8_t *__restrict__ dec, const uint8_t *__restrict__ tmin,
-                                                    const uint8_t *__restrict__ tmax, uint8_t *__restrict__ thr, int Wp,
-                                                    int twp) {
-  // CTA = 32 x 8 threads = 128 tile columns x 8 tile rows.  The tile min/max of the region (+1 tile halo, neutral
-  // values outside the tile grid) are staged once in shared memory; the 3x3 dilate/erode of a thread's four tiles is
-  // then a handful of SIMD-in-word byte min/max ops instead of 72 byte loads.
-  __shared__ __align__(4) uint8_t s_mn[10][136], s_mx[10][136];  // column c <-> tile (tx0 - 4 + c): word aligned groups
-  const int tq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 tile columns
-  const int ty = blockIdx.y * blockDim.y + threadIdx.y;  // tile row (may be the partial one)
+// Tile (tx, ty) of the ceil-sized tile grid (pitch Wp / 4): partial tiles at the right / bottom edge take the values of the
+// nearest full tile and are never low-contrast (AprilRobotics' threshold(): the edge pixels use the clamped tile index).
+__global__ void __launch_bounds__(64) k_tile_thresh(Geo g, const uint8_t *__restrict__ tmin, const uint8_t *__restrict__ tmax,
+                                                     uint8_t *__restrict__ tth, uint8_t *__restrict__ tlow, int twp, int tp, int nty) {
+  const int tq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 tile columns (one word of the tile arrays)
+  const int ty = blockIdx.y;
   const int fr = blockIdx.z;
-  const int nty = (g.Hd + 3) >> 2;
+  if (tq * 4 >= tp) return;
   const uint8_t *mnb = tmin + (size_t)fr * g.th * twp;
   const uint8_t *mxb = tmax + (size_t)fr * g.th * twp;
-  const int tx0 = blockIdx.x * blockDim.x * 4, ty0 = blockIdx.y * blockDim.y;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const size_t base = (size_t)fr * g.Hd * Wp + (size_t)(ty * 4) * Wp + tq * 16;
-  uint4 v[4];
-  if (EARLY && tq * 16 < Wp && ty < nty) {
+  uint32_t thw = 0, loww = 0;
+  if ((twp & 3) == 0 && tq * 4 + 3 < g.tw && ty < g.th) {
+    // four full tiles: vertical min / max of the centre word (SIMD in word) and of the two side tiles (scalars), then the
+    // horizontal step on the shifted views [t-1 t0 t1 t2] and [t1 t2 t3 t4]
+    uint32_t cmn = 0xffffffffu, cmx = 0u, lmn = 0xffu, lmx = 0u, rmn = 0xffu, rmx = 0u;
+    const bool hasl = tq > 0, hasr = tq * 4 + 4 < g.tw;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-      if (ty * 4 + r < g.Hd) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
-  }
-  // staging: 10 rows x 34 words per array; a word = 4 consecutive tiles.  Whole-word loads when the tile pitch is a
-  // multiple of 4 and the word lies inside the tile grid, byte-wise with neutral fill otherwise.
-  const bool words_ok = (twp & 3) == 0;
-  for (int i = tid; i < 10 * 34; i += 256) {
-    const int r = i / 34, w = i - r * 34;
-    const int tyy = ty0 - 1 + r, txx = tx0 - 4 + 4 * w;
-    uint32_t a = 0xffffffffu, b = 0;  // neutral for min / max: tiles outside the grid do not take part
-    if (tyy >= 0 && tyy < g.th) {
-      if (words_ok && txx >= 0 && txx + 3 < g.tw) {
-        a = *reinterpret_cast<const uint32_t *>(mnb + (size_t)tyy * twp + txx);
-        b = *reinterpret_cast<const uint32_t *>(mxb + (size_t)tyy * twp + txx);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int tx = txx + k;
-          if (tx >= 0 && tx < g.tw) {
-            a = (a & ~(0xffu << (8 * k))) | ((uint32_t)mnb[(size_t)tyy * twp + tx] << (8 * k));
-            b |= (uint32_t)mxb[(size_t)tyy * twp + tx] << (8 * k);
-          }
-        }
+    for (int dy = -1; dy <= 1; dy++) {
+      const int yy = ty + dy;
+      if (yy < 0 || yy >= g.th) continue;
+      const size_t ro = (size_t)yy * twp + tq * 4;
+      cmn = __vminu4(cmn, *reinterpret_cast<const uint32_t *>(mnb + ro));
+      cmx = __vmaxu4(cmx, *reinterpret_cast<const uint32_t *>(mxb + ro));
+      if (hasl) {
+        lmn = min(lmn, (uint32_t)mnb[ro - 1]);
+        lmx = max(lmx, (uint32_t)mxb[ro - 1]);
+      }
+      if (hasr) {
+        rmn = min(rmn, (uint32_t)mnb[ro + 4]);
+        rmx = max(rmx, (uint32_t)mxb[ro + 4]);
       }
     }
-    *reinterpret_cast<uint32_t *>(&s_mn[r][4 * w]) = a;
-    *reinterpret_cast<uint32_t *>(&s_mx[r][4 * w]) = b;
-  }
-  __syncthreads();
-  if (tq * 16 >= Wp || ty >= nty) return;
-  uint32_t th4[4], low4[4];
-  const bool fast = (tq * 4 + 3 < g.tw) && (ty < g.th);
-  if (fast) {
-    // words of my 4 tiles in the three tile rows, plus the neighbouring words for the +-1 column shift
-    const int c = threadIdx.x * 4 + 4, r = threadIdx.y;
-    uint32_t mn = 0xffffffffu, mx = 0;
-#pragma unroll
-    for (int dr = 0; dr < 3; dr++) {
-      const uint32_t *wn = reinterpret_cast<const uint32_t *>(&s_mn[r + dr][c - 4]);
-      const uint32_t *wx = reinterpret_cast<const uint32_t *>(&s_mx[r + dr][c - 4]);
-      const uint32_t nl = wn[0], nc = wn[1], nr = wn[2];
-      const uint32_t xl = wx[0], xc = wx[1], xr = wx[2];
-      // left-shifted view [t-1,t0,t1,t2] and right-shifted view [t1,t2,t3,t4]
-      const uint32_t n_l = __byte_perm(nl, nc, 0x6543), n_r = __byte_perm(nc, nr, 0x4321);
-      const uint32_t x_l = __byte_perm(xl, xc, 0x6543), x_r = __byte_perm(xc, xr, 0x4321);
-      mn = __vminu4(mn, __vminu4(nc, __vminu4(n_l, n_r)));
-      mx = __vmaxu4(mx, __vmaxu4(xc, __vmaxu4(x_l, x_r)));
-    }
+    const uint32_t mn = __vminu4(cmn, __vminu4((cmn << 8) | lmn, (cmn >> 8) | (rmn << 24)));
+    const uint32_t mx = __vmaxu4(cmx, __vmaxu4((cmx << 8) | lmx, (cmx >> 8) | (rmx << 24)));
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const uint32_t a = (mn >> (8 * k)) & 0xff, b = (mx >> (8 * k)) & 0xff;
-      low4[k] = ((int)(b - a) < g.min_wb_diff) ? 1u : 0u;
-      th4[k] = (a + (b - a) / 2) * 0x01010101u;
+      const uint32_t a = (mn >> (8 * k)) & 0xffu, b = (mx >> (8 * k)) & 0xffu;
+      thw |= ((a + (b - a) / 2) & 0xffu) << (8 * k);
+      loww |= ((int)(b - a) < g.min_wb_diff ? 0xffu : 0u) << (8 * k);
     }
   } else {
     const int tyc = min(ty, g.th - 1);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      int tx = tq * 4 + k;
-      int txc = min(tx, g.tw - 1);
+      const int tx = tq * 4 + k;
+      const int txc = min(tx, g.tw - 1);
       uint32_t mn = 255, mx = 0;
       for (int dy = -1; dy <= 1; dy++) {
-        int yy = tyc + dy;
+        const int yy = tyc + dy;
         if (yy < 0 || yy >= g.th) continue;
         for (int dx = -1; dx <= 1; dx++) {
-          int xx = txc + dx;
+          const int xx = txc + dx;
           if (xx < 0 || xx >= g.tw) continue;
           mn = min(mn, (uint32_t)mnb[(size_t)yy * twp + xx]);
           mx = max(mx, (uint32_t)mxb[(size_t)yy * twp + xx]);
         }
       }
-      bool partial = (tx >= g.tw) || (ty >= g.th);
-      low4[k] = (!partial && (int)(mx - mn) < g.min_wb_diff) ? 1u : 0u;
-      th4[k] = (mn + (mx - mn) / 2) * 0x01010101u;
+      const bool partial = (tx >= g.tw) || (ty >= g.th);
+      thw |= ((mn + (mx - mn) / 2) & 0xffu) << (8 * k);
+      loww |= ((!partial && (int)(mx - mn) < g.min_wb_diff) ? 0xffu : 0u) << (8 * k);
     }
   }
-  if (!EARLY) {
+  const size_t o = ((size_t)fr * nty + ty) * tp + tq * 4;
+  *reinterpret_cast<uint32_t *>(tth + o) = thw;
+  *reinterpret_cast<uint32_t *>(tlow + o) = loww;
+}
+
+__global__ void __launch_bounds__(256) k_threshold4(Geo g, const uint8_t *__restrict__ dec, const uint8_t *__restrict__ tth,
+                                                    const uint8_t *__restrict__ tlow, uint8_t *__restrict__ thr, int Wp, int tp, int nty) {
+  const int tq = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 tile columns = 16 pixels
+  const int ty = blockIdx.y * blockDim.y + threadIdx.y;  // tile row (may be the partial one)
+  const int fr = blockIdx.z;
+  if (tq * 16 >= Wp || ty >= nty) return;
+  const size_t base = (size_t)fr * g.Hd * Wp + (size_t)(ty * 4) * Wp + tq * 16;
+  const int nr = min(4, g.Hd - ty * 4);
+  uint4 v[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-      if (ty * 4 + r < g.Hd) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
-  }
+  for (int r = 0; r < 4; r++)
+    if (r < nr) v[r] = *reinterpret_cast<const uint4 *>(dec + base + (size_t)r * Wp);
+  const size_t to = ((size_t)fr * nty + ty) * tp + tq * 4;
+  const uint32_t th = *reinterpret_cast<const uint32_t *>(tth + to), low = *reinterpret_cast<const uint32_t *>(tlow + to);
+  // byte k of th / low belongs to tile k of the group = word k of a row
+  const uint32_t t0 = __byte_perm(th, 0, 0x0000), t1 = __byte_perm(th, 0, 0x1111), t2 = __byte_perm(th, 0, 0x2222), t3 = __byte_perm(th, 0, 0x3333);
+  const uint32_t l0 = __byte_perm(low, 0, 0x0000), l1 = __byte_perm(low, 0, 0x1111), l2 = __byte_perm(low, 0, 0x2222), l3 = __byte_perm(low, 0, 0x3333);
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    if (ty * 4 + r >= g.Hd) break;
+    if (r >= nr) break;
     uint4 o;
-    o.x = low4[0] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].x, th4[0]);
-    o.y = low4[1] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].y, th4[1]);
-    o.z = low4[2] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].z, th4[2]);
-    o.w = low4[3] ? 0x7f7f7f7fu : __vcmpgtu4(v[r].w, th4[3]);
+    // low-contrast tile: 127 everywhere (l = 0xffffffff selects the constant), else 255 where the pixel exceeds the threshold
+    o.x = (__vcmpgtu4(v[r].x, t0) & ~l0) | (0x7f7f7f7fu & l0);
+    o.y = (__vcmpgtu4(v[r].y, t1) & ~l1) | (0x7f7f7f7fu & l1);
+    o.z = (__vcmpgtu4(v[r].z, t2) & ~l2) | (0x7f7f7f7fu & l2);
+    o.w = (__vcmpgtu4(v[r].w, t3) & ~l3) | (0x7f7f7f7fu & l3);
     *reinterpret_cast<uint4 *>(thr + base + (size_t)r * Wp) = o;
   }
 }
@@ -433,6 +422,11 @@ int launch_preprocess(const Workspace &ws, int nframes, cudaStream_t s) {
     k_tile_minmax<<<g3, b3, 0, s>>>(gg, ws.dec, ws.tmin, ws.tmax, Wp, twp);
     launches++;
   }
+  if (g.ts == 4) {  // per-tile threshold value / low-contrast flag for k_threshold4 (the tile arrays are 1/16 of the image)
+    const int tp = Wp / 4, nty = (g.Hd + 3) / 4;
+    k_tile_thresh<<<dim3((tp / 4 + 63) / 64, nty, nframes), 64, 0, s>>>(gg, ws.tmin, ws.tmax, ws.tth, ws.tlow, twp, tp, nty);
+    launches++;
+  }
   return launches;
 }
 
@@ -479,9 +473,10 @@ int launch_threshold(const Workspace &ws, int nframes, cudaStream_t s) {
   const Geo &g = ws.g;
   const int Wp = at_Wp(g), twp = at_twp(g);
   if (g.ts == 4) {
+    const int tp = Wp / 4, nty = (g.Hd + 3) / 4;  // (tth / tlow: k_tile_thresh at the end of the preprocess stage)
     dim3 blk(32, 8);
-    dim3 grd((Wp / 16 + 31) / 32, ((g.Hd + 3) / 4 + 7) / 8, nframes);
-    k_threshold4<0><<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);
+    dim3 grd((Wp / 16 + 31) / 32, (nty + 7) / 8, nframes);
+    k_threshold4<<<grd, blk, 0, s>>>(g, ws.dec, ws.tth, ws.tlow, ws.thr, Wp, tp, nty);
   } else {
     dim3 blk(256), grd((g.Wd + 255) / 256, g.Hd, nframes);
     k_threshold_generic<<<grd, blk, 0, s>>>(g, ws.dec, ws.tmin, ws.tmax, ws.thr, Wp, twp);

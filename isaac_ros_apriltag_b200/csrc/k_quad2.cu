@@ -109,12 +109,11 @@ __device__ __forceinline__ void qf_register_work(uint32_t ci, uint32_t off, int 
 // its final position by counting the smaller keys of its own bucket -- a loop of ~m independent loads and compares (median
 // largest bucket of a cluster on the bench frames: 7 points) instead of log2(n) merge passes of chained loads.  Points of
 // neighbouring positions sit in the same or adjacent buckets: the loop's loads are broadcasts.  Any monotone bucket map gives the
-// same final order (unique 64-bit keys); a degenerate outline (all points at one angle: a bucket of more than kBucketLimit
+// same final order (unique 64-bit keys); a degenerate outline (all points at one angle: a bucket of more than Tune::qf_bucket_limit
 // points) falls back to the merge sort in global memory.  Shared memory: 10 B per point instead of 16.
 // MODE 1: the warp sorts its 32 * E keys in registers (bitonic network, warp_bitonic_sort), no shared memory.
 // MODE 0: shared-memory merge sort (ITEMS keys sorted per thread, then merge-path passes).
 // WPC > 1 (one-warp clusters): WPC independent cluster workers per CTA, one warp each, no block-wide barrier anywhere.
-constexpr int kBucketLimit = 1024;
 template <int THREADS, int E, int MODE, int WPC>
 __host__ __device__ constexpr size_t qf_sort_smem() {
   return MODE == 1 ? 0 : MODE == 0 ? (size_t)2 * THREADS * E * 8 * WPC : ((size_t)THREADS * E * 8 + (size_t)(THREADS * E / 2 + 2) * 4) * WPC;
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
     k_qf_sort(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ bin_idx, int bin,
               const uint32_t *__restrict__ pts, unsigned long long *__restrict__ keys, double *__restrict__ errs_pool,
               const uint8_t *__restrict__ dec, uint32_t *__restrict__ qinfo, uint32_t *__restrict__ qwbase, uint4 *__restrict__ work,
-              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp) {
+              uint32_t work_cap, uint32_t *__restrict__ counters, int Wp, int bucket_limit) {
   constexpr int NW = THREADS / 32, NCAP = THREADS * E;
   static_assert(WPC == 1 || THREADS == 32, "several workers per CTA: one-warp clusters only");
   static_assert(MODE != 1 || NW == 1, "register sort: one-warp clusters only");
@@ -233,7 +232,7 @@ __global__ void __launch_bounds__(THREADS *WPC, MINB)
           mx = max(mx, s_wm[grp][w]);
         }
       }
-      if (mx > (uint32_t)kBucketLimit) {  // (uniform) degenerate outline: merge sort in global memory, scratch = the cluster's slice of errs
+      if (mx > (uint32_t)bucket_limit) {  // (uniform) degenerate outline: merge sort in global memory, scratch = the cluster's slice of errs
 #pragma unroll
         for (int k = 0; k < E; k++)
           if (wbase + k * 32 + lane < sz) keys_g[wbase + k * 32 + lane] = v[k];
@@ -888,7 +887,7 @@ static void launch_sort_bin(const Workspace &ws, int bin, int sms, cudaStream_t 
     ctas_per_sm[dev] = std::max(1, n);
   }
   kern<<<sms * ctas_per_sm[dev], THREADS * WPC, smem, st>>>(g, ws.fp, ws.clusters, ws.bin_idx, bin, ws.pts, ws.keys, ws.errs, ws.dec, ws.qinfo,
-                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g));
+                                                           ws.qwbase, ws.qwork, ws.qwork_cap, ws.counters, at_Wp(g), ws.tune.qf_bucket_limit);
 }
 
 // warps per CTA of k_qf_window: 14.3 KB of shared memory per warp.  Measured: 4 per CTA (3 CTAs = 12 warps per SM) 1.585 ms,

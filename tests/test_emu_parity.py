@@ -125,7 +125,7 @@ def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
     det.close()
 
 
-@pytest.mark.parametrize("tune", ["qf_exact=1", "ccl_tma=0", "ccl_tma=0,qf_exact=1"])
+@pytest.mark.parametrize("tune", ["qf_exact=1", "ccl_tma=0", "ccl_tma=0,qf_exact=1", "qf_bucket_limit=3"])
 def test_emulated_kernel_variants(pu, tune, monkeypatch):
     """The kernel variants behind B200AT_TUNE (csrc/detector.h, struct Tune) against the oracle (the GPU suite runs the same list:
     tests/test_gpu_parity.py::test_every_tune_variant_on_the_gpu)."""

@@ -97,10 +97,11 @@ def test_stage_parity_configs(pu, config, n, enc):
             assert len(set(got) & set(want)) >= 0.9 * len(want)
 
 
-@pytest.mark.parametrize("tune", ["qf_exact=1", "ccl_tma=0", "ccl_tma=0,qf_exact=1"])
+@pytest.mark.parametrize("tune", ["qf_exact=1", "ccl_tma=0", "ccl_tma=0,qf_exact=1", "qf_bucket_limit=3"])
 def test_every_tune_variant_on_the_gpu(pu, tune, monkeypatch):
-    """The kernel variants behind B200AT_TUNE (csrc/detector.h, struct Tune: the bit-exact quad fit, the CCL sweep without TMA staging)
-    run on the GPU against the oracle like the defaults do -- a variant that only ever ran under the emulator is inventory."""
+    """The kernel variants behind B200AT_TUNE (csrc/detector.h, struct Tune: the bit-exact quad fit, the CCL sweep without TMA staging,
+    the quad-fit sort's fallback for degenerate outlines -- qf_bucket_limit=3 sends nearly every cluster through it) run on the GPU
+    against the oracle like the defaults do -- a variant that only ever ran under the emulator is inventory."""
     from isaac_ros_apriltag_b200 import synth
     monkeypatch.setenv("B200AT_TUNE", tune)
     frames, truths, K, ts, fams = synth.make_config_frames("C2", 2)

@@ -20,7 +20,7 @@ from isaac_ros_apriltag_b200 import capi, synth  # noqa: E402
 ALL_OFF = "thr_early=0,ccl_sweep=0,cluster_eager=0,decode_split=0,qf_mc=0,qf_keys23=0"   # the round-1 kernels
 ALL_ON = ""                                                                               # library defaults
 # what the next GPU session should measure first (all bit-exact under the emulator, none measured yet except decode_pair)
-DEVICE_CONFIGS = ["qf_exact=1", "", "ccl_tma=0", ""]
+DEVICE_CONFIGS = ["qf_exact=1", "", "ccl_tma=0", "qf_bucket_limit=3", ""]
 if os.environ.get("B200AT_TUNE_CONFIGS"):
     DEVICE_CONFIGS = os.environ["B200AT_TUNE_CONFIGS"].split(";")
 # host entry point: (knobs, sparse staging (-1 = library default), sub-batch (0 = default), streams, pipelined fetch level, ramp, copy streams)

@@ -15,7 +15,7 @@ frames = np.stack([synth.make_frame(rng, 640, 480, [("tag36h11", 5), ("tag36h11"
 bgr = np.ascontiguousarray(np.repeat(frames[:, :, :, None], 3, axis=3))
 t = torch.from_numpy(bgr).cuda()
 fb = t[0].numel()
-for tune in ("", "qf_exact=1", "ccl_tma=0"):
+for tune in ("", "qf_exact=1", "ccl_tma=0", "qf_bucket_limit=3"):
     if tune:
         os.environ["B200AT_TUNE"] = tune
     else:
