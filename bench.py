@@ -30,7 +30,7 @@ METRIC = "frames_per_sec_1080p_tag36h11"
 UNIT = "frames/s"
 
 
-NCU_TRAFFIC_FILE = "r03_ncu_full_dense_batch256.csv"  # ncu --set full of the same command and batch (tools/gpu_final.sh)
+NCU_TRAFFIC_FILE = "r04_ncu_full_dense_batch256.csv"  # ncu --set full of the same command and batch (tools/gpu_final.sh)
 
 
 def load_ncu_traffic(kernel="k_threshold4"):

@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
   __shared__ __align__(128) uint8_t s_t[SWEEP_TILES][TSLOT];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ uint32_t s_L[SWEEP_TILES][TH * TW];
-  __shared__ uint32_t s_cnt[SWEEP_TILES][TH * TW];
   const int fr = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int x0 = (blockIdx.x * SWEEP_TILES + wid) * TW, y0 = blockIdx.y * TH;
@@ -176,11 +175,12 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
   }
   if (x0 >= g.Wd) return;  // (no block-wide barrier below this point)
   const uint8_t *t = s_t[wid];
-  uint32_t *L = s_L[wid], *cnt = s_cnt[wid];
+  uint32_t *L = s_L[wid];
   const uint32_t NONE = 0xffffffffu;
   const int x = x0 + lane;
   const int rows = min(TH, g.Hd - y0);
   uint32_t plab = NONE;  // label of the pixel above (row ly - 1) in this lane's column
+  unsigned dead = 0u;    // bit ly: my pixel of row ly is a 127-pixel (never connected, never counted) or a padding column
   for (int ly = 0; ly < rows; ly++) {
     const int y = y0 + ly;
     const uint8_t *tr = t + (ly + 1) * TPITCH + lane + TOFF, *tu = tr - TPITCH;
@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     uint32_t rl = __shfl_sync(0xffffffffu, mine, linked ? __ffs(linked) - 1 : lane);
     if (!linked) rl = (uint32_t)(ly * TW + rs);  // no link upwards anywhere in the run: new label = its first pixel
     L[i] = rl;
-    cnt[i] = 0;
     __syncwarp();
     // ONE union site, executed as often as the busiest lane needs it
     bool n1 = c1 != NONE && c1 != rl, n2 = c2 != NONE && c2 != rl && c2 != c1, n3 = c3 != NONE && c3 != rl && c3 != c1 && c3 != c2;
@@ -223,49 +222,10 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
         unite_s(L, pick, rl);
       }
     }
-    if (lane == rs && x < g.Wd && vcur != 127) atomicAdd(&cnt[rl], (uint32_t)__popc(run_mask));
+    dead |= (x >= g.Wd || vcur == 127) ? (1u << ly) : 0u;
     plab = rl;
   }
   __syncwarp();
-  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
-  uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
-  // flatten inside the tile; counts collected at merged labels move to their final local root.  The rows in which this lane's
-  // column holds a local root are remembered as a bit mask (a root already owns the pixels of its first run: cnt != 0; the
-  // 127-pixels and the padding columns never get a count)
-  unsigned rootbits = 0u;
-  for (int ly = 0; ly < rows; ly++) {
-    const int i = ly * TW + lane;
-    const uint32_t r = find_s(L, i);
-    if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
-    const uint32_t c = cnt[i];  // non-zero only at labels; a non-root entry is touched by this lane alone
-    if (r != (uint32_t)i && c) {
-      atomicAdd(&cnt[r], c);
-      cnt[i] = 0;
-    }
-    rootbits |= (r == (uint32_t)i && c) ? (1u << ly) : 0u;
-  }
-  __syncwarp();
-  // The tile's local roots (~5 % of the pixels) go to the frame's root list, their pixel counts to the size image: the later
-  // kernels never scan the size image (it is written at roots only).  One reservation per tile, one loop trip per root of the
-  // busiest column.
-  const int myroots = __popc(rootbits);
-  int incl = myroots;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += u;
-  }
-  uint32_t base = 0;
-  if (lane == 31 && incl > 0) base = atomicAdd(&nroots[fr], (uint32_t)incl);
-  base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - myroots);
-  uint32_t *rootf = roots + (size_t)fr * g.Hd * Wp;
-  while (rootbits) {
-    const int ly = __ffs(rootbits) - 1;
-    rootbits &= rootbits - 1u;
-    const size_t gi = (size_t)(y0 + ly) * Wp + x;
-    szf[gi] = cnt[ly * TW + lane];
-    rootf[base++] = (uint32_t)gi;
-  }
   // The tile's cross-border links (a few dozen, at most kReqCap) as a list of (pixel, neighbour) pairs: k_ccl_border no longer
   // re-reads the threshold image around every border pixel, it only walks the lists.  The links of row 0 (lane <-> column) and of
   // columns 0 / 31 (lane <-> row) are re-evaluated here from the staged tile: ~100 instructions per tile instead of ~10 per row.
@@ -297,6 +257,53 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     emit(nl.UL && lane > 0, meL, meL - Wp - 1);  // (row 0 is in the first list)
     emit(nr.UR && lane > 0, meR, meR - Wp + 1);
     if (lane == 0) reqcnt[tl] = nreq;
+  }
+  __syncwarp();
+  // The staged tile is dead from here on: its buffer becomes the pixel counters of the tile's labels (1024 x 16 bit; a tile has
+  // 1024 pixels), which keeps the kernel at 6.2 KB of shared memory per tile (36 warps per SM instead of 20).
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(s_t[wid]);
+  for (int k = lane; k < TH * TW / 2; k += 32) cnt[k] = 0u;
+  __syncwarp();
+  uint32_t *labf = lab + (size_t)fr * g.Hd * Wp;
+  uint32_t *szf = csize + (size_t)fr * g.Hd * Wp;
+  // flatten inside the tile and count the pixels of every local root (equal roots of a row are grouped by __match_any_sync:
+  // one shared-memory atomic per root and row).  The rows in which this lane's column holds a local root are remembered as a
+  // bit mask.
+  unsigned rootbits = 0u;
+  for (int ly = 0; ly < rows; ly++) {
+    const int i = ly * TW + lane;
+    const uint32_t r = find_s(L, i);
+    if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
+    const bool live = ((dead >> ly) & 1u) == 0u;
+    const unsigned act = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const unsigned peers = __match_any_sync(act, r);
+      if (lane == __ffs(peers) - 1) atomicAdd(&cnt[r >> 1], (uint32_t)__popc(peers) << (16 * (r & 1u)));
+      rootbits |= (r == (uint32_t)i) ? (1u << ly) : 0u;
+    }
+  }
+  __syncwarp();
+  // The tile's local roots (~5 % of the pixels) go to the frame's root list, their pixel counts to the size image: the later
+  // kernels never scan the size image (it is written at roots only).  One reservation per tile, one loop trip per root of the
+  // busiest column.
+  const int myroots = __popc(rootbits);
+  int incl = myroots;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += u;
+  }
+  uint32_t base = 0;
+  if (lane == 31 && incl > 0) base = atomicAdd(&nroots[fr], (uint32_t)incl);
+  base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - myroots);
+  uint32_t *rootf = roots + (size_t)fr * g.Hd * Wp;
+  while (rootbits) {
+    const int ly = __ffs(rootbits) - 1;
+    rootbits &= rootbits - 1u;
+    const size_t gi = (size_t)(y0 + ly) * Wp + x;
+    const int i = ly * TW + lane;
+    szf[gi] = (cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+    rootf[base++] = (uint32_t)gi;
   }
 }
 
