@@ -112,6 +112,7 @@ constexpr int TOFF = 16;    // column of pixel x0 (TMA needs the box start 16-by
 // CTA = 4 warps = 4 horizontally adjacent tiles; each tile is staged (with halo) by its own TMA box.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SWEEP_TILES = 4;
+constexpr uint32_t kSmallFlag = 0x80000000u;  // bit 31 of a tile root's working label: its component has fewer than 25 pixels
 constexpr int kReqCap = 192;  // cross-border links of a tile: <= 3 * 32 (row 0) + 32 + 31 + 31 (columns 0 / 31)
 constexpr int TBYTES = TPITCH * (TH + 1);              // one staged tile + halo row
 constexpr int TSLOT = (TBYTES + 127) & ~127;           // 128-byte aligned slots
@@ -276,13 +277,38 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     if (x < g.Wd) labf[(size_t)(y0 + ly) * Wp + x] = (uint32_t)((y0 + r / TW) * Wp + (x0 + r % TW));
     const bool live = ((dead >> ly) & 1u) == 0u;
     const unsigned act = __ballot_sync(0xffffffffu, live);
+    const unsigned bmask = (ly == 0 || ly == rows - 1) ? 0xffffffffu : 0x80000001u;  // lanes of this row on the tile border
     if (live) {
       const unsigned peers = __match_any_sync(act, r);
-      if (lane == __ffs(peers) - 1) atomicAdd(&cnt[r >> 1], (uint32_t)__popc(peers) << (16 * (r & 1u)));
+      if (lane == __ffs(peers) - 1) {
+        atomicAdd(&cnt[r >> 1], (uint32_t)__popc(peers) << (16 * (r & 1u)));
+        // bit 15 of a counter: the component touches the tile border (only those can merge with another tile)
+        if (peers & bmask) atomicOr(&cnt[r >> 1], 0x8000u << (16 * (r & 1u)));
+      }
       rootbits |= (r == (uint32_t)i) ? (1u << ly) : 0u;
     }
   }
   __syncwarp();
+  // Local roots whose component does not touch the tile border are FINAL: global root = themselves, size = their count; the size
+  // gate goes straight into bit 31 of their label (what k_ccl_rootflag does for the others).  Only border-touching roots go to the
+  // frame's root list (on thresholded noise most components are specks inside a tile: the list shrinks several times).
+  {
+    unsigned listbits = 0u, rb = rootbits;
+    while (rb) {
+      const int ly = __ffs(rb) - 1;
+      rb &= rb - 1u;
+      const int i = ly * TW + lane;
+      const uint32_t c16 = (cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+      if (c16 & 0x8000u) {
+        listbits |= 1u << ly;
+      } else {
+        const size_t gi = (size_t)(y0 + ly) * Wp + x;
+        szf[gi] = c16;
+        if (c16 < 25u) labf[gi] = (uint32_t)gi | kSmallFlag;
+      }
+    }
+    rootbits = listbits;
+  }
   // The tile's local roots (~5 % of the pixels) go to the frame's root list, their pixel counts to the size image: the later
   // kernels never scan the size image (it is written at roots only).  One reservation per tile, one loop trip per root of the
   // busiest column.
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(32 * SWEEP_TILES) k_ccl_tile_sweep(Geo g, cons
     rootbits &= rootbits - 1u;
     const size_t gi = (size_t)(y0 + ly) * Wp + x;
     const int i = ly * TW + lane;
-    szf[gi] = (cnt[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+    szf[gi] = (cnt[i >> 1] >> (16 * (i & 1))) & 0x7fffu;
     rootf[base++] = (uint32_t)gi;
   }
 }
@@ -351,7 +377,6 @@ __global__ void __launch_bounds__(256) k_ccl_roots(Geo g, uint32_t *__restrict__
 
 // Phase A': the size gate is decided once per (former) tile root and travels in bit 31 of its label, so that phase B needs no
 // second gather into the size image.
-constexpr uint32_t kSmallFlag = 0x80000000u;
 __global__ void __launch_bounds__(256) k_ccl_rootflag(Geo g, uint32_t *__restrict__ lab, const uint32_t *__restrict__ csize,
                                                       const uint32_t *__restrict__ roots, const uint32_t *__restrict__ nroots, int Wp) {
   const int fr = blockIdx.y;

@@ -509,9 +509,9 @@ __global__ void __launch_bounds__(32 * QW_WARPS)
 // k_qf_tail
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int QT_WARPS = 4;
-constexpr int QT_LIN = 512;  // maxima of a cluster held in shared memory for the top-k selection (more: the global scratch)
+constexpr int QT_LIN = 256;  // maxima of a cluster held in shared memory for the top-k selection (more: the global scratch)
 
-__global__ void __launch_bounds__(32 * QT_WARPS)
+__global__ void __launch_bounds__(32 * QT_WARPS, 8)
     k_qf_tail(Geo g, FitParams fp, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ qinfo,
               const uint32_t *__restrict__ qwbase, const unsigned long long *__restrict__ keys, const LineFitPt *__restrict__ lfps_pool,
               double *__restrict__ errs_pool, const double *__restrict__ wtot, const uint32_t *__restrict__ wnmax,
