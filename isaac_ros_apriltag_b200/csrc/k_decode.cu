@@ -245,98 +245,99 @@ __device__ __forceinline__ void rescale_quad(const FitParams &fp, const QuadRec 
   }
 }
 
-// ---- a12: refine_edges (one warp; every lane ends with the same refined corners) ----
-__device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
-                                                  int o2, bool is_bgr, bool reversed, int lane, float p[4][2]) {
-  double lines[4][4];
+// ---- a12: refine_edges ----
+// one edge (a warp; every lane ends with the same line): centroid + unit normal of the line through the refined sample points
+__device__ __forceinline__ void refine_edge_line(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1, int o2,
+                                                 bool is_bgr, bool reversed, int lane, const float p[4][2], int edge, double line[4]) {
   const double range = (double)(fp.quad_decimate + 1.0f);
   const int nsteps = (int)floor(2.0 * range / 0.25) + 1;
-#pragma unroll 1
-  for (int edge = 0; edge < 4; edge++) {
-    const int a = edge, b = (edge + 1) & 3;
-    double nx = (double)(p[b][1] - p[a][1]);
-    double ny = (double)(-p[b][0] + p[a][0]);
-    double mag = sqrt(nx * nx + ny * ny);
-    nx /= mag;
-    ny /= mag;
-    if (reversed) {
-      nx = -nx;
-      ny = -ny;
-    }
-    const int nsamples = max(16, (int)(mag / 8));
-    double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
-    for (int s0 = 0; s0 < nsamples; s0 += 32) {
-      const int s = s0 + lane;
-      double bestx = 0, besty = 0;
-      int has = 0;
-      if (s < nsamples) {
-        double alpha = (1.0 + s) / (nsamples + 1);
-        double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
-        double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
-        double Mn = 0, Mcount = 0;
-        // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
-        for (int k0 = 0; k0 < nsteps; k0 += 8) {
-          int g1[8], g2[8];
-          bool okk[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int k = k0 + u;
-            const double n = -range + 0.25 * k;
-            const double grange = 1;
-            const int x1 = (int)(x0 + (n + grange) * nx);
-            const int y1 = (int)(y0 + (n + grange) * ny);
-            const int x2 = (int)(x0 + (n - grange) * nx);
-            const int y2 = (int)(y0 + (n - grange) * ny);
-            okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
-                     !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
-            // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
-            g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
-            g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            if (!okk[u] || g1[u] < g2[u]) continue;
-            const double n = -range + 0.25 * (k0 + u);
-            const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
-            Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
-            Mcount += weight;
-          }
-        }
-        if (Mcount != 0) {
-          double n0 = Mn / Mcount;
-          bestx = x0 + n0 * nx;
-          besty = y0 + n0 * ny;
-          has = 1;
-        }
-      }
-      // moments of the 32 samples: butterfly sums (every lane ends with the same value).  The oracle adds the samples one
-      // after the other; the association differs in the last bits of sums whose line parameters are rounded to float below.
-      double m5[5] = {has ? bestx : 0.0, has ? besty : 0.0, has ? bestx * bestx : 0.0, has ? bestx * besty : 0.0, has ? besty * besty : 0.0};
-#pragma unroll
-      for (int of = 16; of > 0; of >>= 1) {
-#pragma unroll
-        for (int q = 0; q < 5; q++) m5[q] += shfl_xor_d(m5[q], of);
-      }
-      Mx += m5[0];
-      My += m5[1];
-      Mxx += m5[2];
-      Mxy += m5[3];
-      Myy += m5[4];
-      N += (double)__popc(__ballot_sync(0xffffffffu, has != 0));
-    }
-    double Ex = Mx / N, Ey = My / N;
-    double Cxx = Mxx / N - Ex * Ex;
-    double Cxy = Mxy / N - Ex * Ey;
-    double Cyy = Myy / N - Ey * Ey;
-    // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
-    float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
-    double normal_theta = .5 * th;
-    float nth = (float)normal_theta;
-    lines[edge][0] = Ex;
-    lines[edge][1] = Ey;
-    lines[edge][2] = (double)(float)cos((double)nth);
-    lines[edge][3] = (double)(float)sin((double)nth);
+  const int a = edge, b = (edge + 1) & 3;
+  double nx = (double)(p[b][1] - p[a][1]);
+  double ny = (double)(-p[b][0] + p[a][0]);
+  double mag = sqrt(nx * nx + ny * ny);
+  nx /= mag;
+  ny /= mag;
+  if (reversed) {
+    nx = -nx;
+    ny = -ny;
   }
+  const int nsamples = max(16, (int)(mag / 8));
+  double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+  for (int s0 = 0; s0 < nsamples; s0 += 32) {
+    const int s = s0 + lane;
+    double bestx = 0, besty = 0;
+    int has = 0;
+    if (s < nsamples) {
+      double alpha = (1.0 + s) / (nsamples + 1);
+      double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
+      double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
+      double Mn = 0, Mcount = 0;
+      // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
+      for (int k0 = 0; k0 < nsteps; k0 += 8) {
+        int g1[8], g2[8];
+        bool okk[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int k = k0 + u;
+          const double n = -range + 0.25 * k;
+          const double grange = 1;
+          const int x1 = (int)(x0 + (n + grange) * nx);
+          const int y1 = (int)(y0 + (n + grange) * ny);
+          const int x2 = (int)(x0 + (n - grange) * nx);
+          const int y2 = (int)(y0 + (n - grange) * ny);
+          okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) &&
+                   !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
+          // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
+          g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
+          g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (!okk[u] || g1[u] < g2[u]) continue;
+          const double n = -range + 0.25 * (k0 + u);
+          const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
+          Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
+          Mcount += weight;
+        }
+      }
+      if (Mcount != 0) {
+        double n0 = Mn / Mcount;
+        bestx = x0 + n0 * nx;
+        besty = y0 + n0 * ny;
+        has = 1;
+      }
+    }
+    // moments of the 32 samples: butterfly sums (every lane ends with the same value).  The oracle adds the samples one
+    // after the other; the association differs in the last bits of sums whose line parameters are rounded to float below.
+    double m5[5] = {has ? bestx : 0.0, has ? besty : 0.0, has ? bestx * bestx : 0.0, has ? bestx * besty : 0.0, has ? besty * besty : 0.0};
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 5; q++) m5[q] += shfl_xor_d(m5[q], of);
+    }
+    Mx += m5[0];
+    My += m5[1];
+    Mxx += m5[2];
+    Mxy += m5[3];
+    Myy += m5[4];
+    N += (double)__popc(__ballot_sync(0xffffffffu, has != 0));
+  }
+  double Ex = Mx / N, Ey = My / N;
+  double Cxx = Mxx / N - Ex * Ex;
+  double Cxy = Mxy / N - Ex * Ey;
+  double Cyy = Myy / N - Ey * Ey;
+  // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
+  float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
+  double normal_theta = .5 * th;
+  float nth = (float)normal_theta;
+  line[0] = Ex;
+  line[1] = Ey;
+  line[2] = (double)(float)cos((double)nth);
+  line[3] = (double)(float)sin((double)nth);
+}
+
+// the refined corners = intersections of adjacent lines (a corner whose lines are nearly parallel keeps its position)
+__device__ __forceinline__ void refine_corners(const double lines[4][4], float p[4][2]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
@@ -351,6 +352,15 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
       p[i][1] = (float)(lines[i][1] + L0 * A10);
     }
   }
+}
+
+// one warp per quad: the four edges one after the other; every lane ends with the same refined corners
+__device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const FrameDesc &fd, int width, int height, int bpp, int o1,
+                                                  int o2, bool is_bgr, bool reversed, int lane, float p[4][2]) {
+  double lines[4][4];
+#pragma unroll 1
+  for (int edge = 0; edge < 4; edge++) refine_edge_line(fp, fd, width, height, bpp, o1, o2, is_bgr, reversed, lane, p, edge, lines[edge]);
+  refine_corners(lines, p);
 }
 
 // ---- a12, opt-in variant (decode_pair=1): refine_edges with two short edges per pass ----
@@ -691,6 +701,44 @@ __global__ void __launch_bounds__(256) k_fetch_rows(Geo g, const FrameDesc *__re
   if (lane == 0 && copied) atomicAdd(&counters[CNT_FETCHED], copied);
 }
 
+// what follows refine_edges for one quad (one warp): refined corners out, homography, and on the sparse host path the rows of
+// every pixel the decoder will sample
+template <bool MARK>
+__device__ __forceinline__ void refine_finish(const Geo &g, const FitParams &fp, const DecodeFams &fams, const QuadRec &q0, uint32_t qi,
+                                              const float p[4][2], bool reversed, int lane, QuadRec *__restrict__ quads_refined,
+                                              double *__restrict__ quad_H, unsigned long long *__restrict__ need2) {
+  if (lane == 0) {
+    QuadRec qr = q0;
+    for (int j = 0; j < 4; j++) {
+      qr.p[j][0] = p[j][0];
+      qr.p[j][1] = p[j][1];
+    }
+    quads_refined[qi] = qr;
+  }
+  double H[9];
+  const bool ok = quad_homography_warp(p, H);
+  double *hq = quad_H + (size_t)qi * 10;
+  if (lane < 9) hq[lane] = H[lane];
+  if (lane == 9) hq[9] = ok ? 1.0 : 0.0;
+  if (MARK && ok) {
+    for (int fi = 0; fi < fp.nfam; fi++) {
+      const DevFamily &fam = fams.f[fi];
+      if ((fam.reversed_border != 0) != reversed) continue;
+      const int wab = fam.width_at_border;
+      for (int j = lane; j < 8 * wab; j += 32) {
+        const BorderSample b = border_sample(H, j, wab, g.W, g.H);
+        if (b.valid) mark_row(g, need2, q0.frame, b.iy, b.ix, b.ix);
+      }
+      for (int i = lane; i < fam.nbits; i += 32) {
+        const BitSample b = bit_sample(H, fam.bit_x[i], fam.bit_y[i], wab, g.W, g.H);
+        if (!b.valid) continue;
+        mark_row(g, need2, q0.frame, b.y1, b.x1, b.x2);
+        mark_row(g, need2, q0.frame, b.y2, b.x1, b.x2);
+      }
+    }
+  }
+}
+
 template <bool MARK, int MINB>
 __global__ void __launch_bounds__(DT, MINB) k_refine(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
                                                const QuadRec *__restrict__ quads, QuadRec *__restrict__ quads_refined,
@@ -709,36 +757,48 @@ __global__ void __launch_bounds__(DT, MINB) k_refine(Geo g, FitParams fp, Decode
     float p[4][2];
     rescale_quad(fp, q0, p);
     if (fp.refine_edges) refine_edges_warp(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p);
-    if (lane == 0) {
-      QuadRec qr = q0;
-      for (int j = 0; j < 4; j++) {
-        qr.p[j][0] = p[j][0];
-        qr.p[j][1] = p[j][1];
+    refine_finish<MARK>(g, fp, fams, q0, qi, p, reversed, lane, quads_refined, quad_H, need2);
+  }
+}
+
+// Latency form of k_refine for small batches (a single frame has a few dozen quads: the warp-per-quad kernel leaves the GPU
+// empty and walks the four edges one after the other): one CTA of four warps per quad, one edge per warp.
+template <bool MARK>
+__global__ void __launch_bounds__(128) k_refine_cta(Geo g, FitParams fp, DecodeFams fams, const FrameDesc *__restrict__ frames,
+                                                    const QuadRec *__restrict__ quads, QuadRec *__restrict__ quads_refined,
+                                                    double *__restrict__ quad_H, const uint32_t *__restrict__ counters,
+                                                    unsigned long long *__restrict__ need2) {
+  __shared__ double s_lines[4][4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t nq = min(counters[CNT_QUADS], g.quad_cap);
+  const int bpp = g.bpp;
+  const int o1 = bpp > 1 ? 1 : 0, o2 = bpp > 1 ? 2 : 0;
+  const bool is_bgr = (g.enc == B200AT_ENC_BGR8 || g.enc == B200AT_ENC_BGRA8);
+  for (uint32_t qi = blockIdx.x; qi < nq; qi += gridDim.x) {
+    const QuadRec q0 = quads[qi];
+    const FrameDesc fd = frames[q0.frame];
+    const bool reversed = q0.reversed_border != 0;
+    float p[4][2];
+    rescale_quad(fp, q0, p);
+    if (fp.refine_edges) {
+      double line[4];
+      refine_edge_line(fp, fd, g.W, g.H, bpp, o1, o2, is_bgr, reversed, lane, p, wid, line);
+      if (lane == 0) {
+        s_lines[wid][0] = line[0];
+        s_lines[wid][1] = line[1];
+        s_lines[wid][2] = line[2];
+        s_lines[wid][3] = line[3];
       }
-      quads_refined[qi] = qr;
+      __syncthreads();
+      double lines[4][4];
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) lines[e][k] = s_lines[e][k];
+      refine_corners(lines, p);
+      __syncthreads();  // (s_lines is rewritten for the next quad)
     }
-    double H[9];
-    const bool ok = quad_homography_warp(p, H);
-    double *hq = quad_H + (size_t)qi * 10;
-    if (lane < 9) hq[lane] = H[lane];
-    if (lane == 9) hq[9] = ok ? 1.0 : 0.0;
-    if (MARK && ok) {
-      for (int fi = 0; fi < fp.nfam; fi++) {
-        const DevFamily &fam = fams.f[fi];
-        if ((fam.reversed_border != 0) != reversed) continue;
-        const int wab = fam.width_at_border;
-        for (int j = lane; j < 8 * wab; j += 32) {
-          const BorderSample b = border_sample(H, j, wab, g.W, g.H);
-          if (b.valid) mark_row(g, need2, q0.frame, b.iy, b.ix, b.ix);
-        }
-        for (int i = lane; i < fam.nbits; i += 32) {
-          const BitSample b = bit_sample(H, fam.bit_x[i], fam.bit_y[i], wab, g.W, g.H);
-          if (!b.valid) continue;
-          mark_row(g, need2, q0.frame, b.y1, b.x1, b.x2);
-          mark_row(g, need2, q0.frame, b.y2, b.x1, b.x2);
-        }
-      }
-    }
+    if (wid == 0) refine_finish<MARK>(g, fp, fams, q0, qi, p, reversed, lane, quads_refined, quad_H, need2);
   }
 }
 
@@ -765,6 +825,7 @@ __global__ void __launch_bounds__(DT, MINB) k_decode_bits(Geo g, FitParams fp, D
   }
 }
 
+constexpr int kRefineCtaFrames = 4;  // batches of at most this many frames refine with one CTA per quad (k_refine_cta)
 constexpr int kDecodeCtasPerSm = 6;  // persistent CTAs per SM = register budget of k_refine / k_decode_bits (measured: 4 / 5 / 6 CTAs -> decode 1.70 / 1.69 / 1.66 ms)
 
 static int sm_count() {
@@ -795,7 +856,10 @@ int launch_sparse_back(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
   const int ctas = sm_count() * kDecodeCtasPerSm;
   const dim3 gf((g.H + 7) / 8, nframes);
-  k_refine<true, kDecodeCtasPerSm><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
+  if (nframes <= kRefineCtaFrames)
+    k_refine_cta<true><<<sm_count() * 4, 128, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
+  else
+    k_refine<true, kDecodeCtasPerSm><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, ws.need2);
   if (!nofetch) k_fetch_rows<<<gf, 256, 0, s>>>(g, ws.src_frames, ws.frames, ws.need2, ws.need1, ws.counters);
   k_decode_bits<kDecodeCtasPerSm><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
   return 4;
@@ -810,7 +874,10 @@ int launch_decode(const Workspace &ws, int nframes, cudaStream_t s) {
   for (int i = 0; i < kMaxFamilies; i++) df.f[i] = ws.fams[i];
   // two kernels instead of one fused kernel that needs 167 registers (measured: 2.13 -> 1.69 ms)
   const int ctas = sm_count() * kDecodeCtasPerSm;
-  k_refine<false, kDecodeCtasPerSm><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+  if (nframes <= kRefineCtaFrames)
+    k_refine_cta<false><<<sm_count() * 4, 128, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
+  else
+    k_refine<false, kDecodeCtasPerSm><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quads_refined, ws.quad_H, ws.counters, nullptr);
   k_decode_bits<kDecodeCtasPerSm><<<ctas, DT, 0, s>>>(g, ws.fp, df, ws.frames, ws.quads, ws.quad_H, ws.cands, ws.cand_count, ws.counters);
   return 3;
 }

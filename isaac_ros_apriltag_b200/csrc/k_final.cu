@@ -253,7 +253,10 @@ __device__ void polar_UVt_dev(const double *A, double *R) {
   mm33_dev(At, A, S);
   for (int sweep = 0; sweep < 30; sweep++) {
     double off = fabs(S[1]) + fabs(S[2]) + fabs(S[5]);
-    if (off <= 1e-32 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;  // converged far below double epsilon
+    // converged to double precision: a further rotation would change eigenvalues by off^2 / gap and the polar factor by less
+    // than one ulp.  (The oracle sweeps on to 1e-32 -- for the rank-2 matrices of orthogonal_iteration that is one more rotation
+    // with c == 1, s ~ 1e-17 per call: a third of k_pose's dependent instruction chain for a change of <= 1e-17 in R.)
+    if (off <= 2.5e-16 * (fabs(S[0]) + fabs(S[4]) + fabs(S[8]))) break;
     for (int pi = 0; pi < 3; pi++) {
       int p = pi == 2 ? 0 : pi, q = pi == 0 ? 1 : 2;
       double apq = S[p * 3 + q];
@@ -261,7 +264,7 @@ __device__ void polar_UVt_dev(const double *A, double *R) {
       double app = S[p * 3 + p], aqq = S[q * 3 + q];
       double theta = (aqq - app) / (2 * apq);
       double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-      double c = 1 / sqrt(t * t + 1), s = t * c;
+      double c = rsqrt(t * t + 1), s = t * c;  // (1 ulp from the oracle's 1 / sqrt: half the dependent chain)
       for (int k = 0; k < 3; k++) {
         double skp = S[k * 3 + p], skq = S[k * 3 + q];
         S[k * 3 + p] = c * skp - s * skq;
@@ -298,7 +301,8 @@ __device__ void polar_UVt_dev(const double *A, double *R) {
     if (s > 1e-12 * smax && s > 0) {
       double v[3] = {Vs[0 * 3 + c], Vs[1 * 3 + c], Vs[2 * 3 + c]}, u[3];
       mv33_dev(A, v, u);
-      for (int r = 0; r < 3; r++) U[r * 3 + c] = u[r] / s;
+      const double rs = 1.0 / s;  // one division per column instead of three (1 ulp from the oracle's u / s)
+      for (int r = 0; r < 3; r++) U[r * 3 + c] = u[r] * rs;
       rank = c + 1;
     } else {
       break;
@@ -316,6 +320,35 @@ __device__ void polar_UVt_dev(const double *A, double *R) {
   double Vt[9];
   tr33_dev(Vs, Vt);
   mm33_dev(U, Vt, R);
+}
+
+// Polar factor of a matrix whose third column is exactly zero (the object points of a tag are planar: M3 of orthogonal_iteration
+// always has this form), in closed form: the first two columns are Q = A (A'A)^(-1/2) with the 2 x 2 inverse square root
+// (S + delta I)^-1 * tau, delta = sqrt(det S), tau = sqrt(tr S + 2 delta); the third is their cross product (what the generic path
+// -- SVD, completion of the rank-2 factor, determinant fix -- ends with as well).  Three dependent long operations (sqrt, sqrt,
+// divide) instead of the Jacobi path's eight: the polar factor was two thirds of k_pose's dependent instruction chain.  Same
+// matrix up to rounding (~1e-15 for ordinary views); nearly rank-deficient input takes the generic path.
+__device__ void polar_planar_dev(const double *A, double *R) {
+  const double ax = A[0], ay = A[3], az = A[6], bx = A[1], by = A[4], bz = A[7];
+  const double p = ax * ax + ay * ay + az * az, q = ax * bx + ay * by + az * bz, r = bx * bx + by * by + bz * bz;
+  const double det = p * r - q * q, tr = p + r;
+  if (!(A[2] == 0 && A[5] == 0 && A[8] == 0) || !(det > 1e-10 * tr * tr)) {
+    polar_UVt_dev(A, R);
+    return;
+  }
+  const double delta = sqrt(det), tau = sqrt(tr + 2 * delta), inv = 1.0 / (delta * tau);
+  const double m00 = (r + delta) * inv, m01 = -q * inv, m11 = (p + delta) * inv;
+  const double q0x = ax * m00 + bx * m01, q0y = ay * m00 + by * m01, q0z = az * m00 + bz * m01;
+  const double q1x = ax * m01 + bx * m11, q1y = ay * m01 + by * m11, q1z = az * m01 + bz * m11;
+  R[0] = q0x;
+  R[3] = q0y;
+  R[6] = q0z;
+  R[1] = q1x;
+  R[4] = q1y;
+  R[7] = q1z;
+  R[2] = q0y * q1z - q0z * q1y;
+  R[5] = q0z * q1x - q0x * q1z;
+  R[8] = q0x * q1y - q0y * q1x;
 }
 
 __device__ void homography_to_pose_dev(const double *H, double fx, double fy, double cx, double cy, double R[9], double T[3]) {
@@ -403,7 +436,7 @@ __device__ double orthogonal_iteration_dev(const double v[4][3], const double p[
     for (int j = 0; j < n_points; j++)
       for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++) M3[a * 3 + b] += (q[j][a] - q_mean[a]) * p_res[j][b];
-    polar_UVt_dev(M3, R);
+    polar_planar_dev(M3, R);
     if (det33_dev(R) < 0) {
       R[2] *= -1;
       R[5] *= -1;
