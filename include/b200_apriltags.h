@@ -232,8 +232,12 @@ int b200AprilTagsEnqueueBatchHost(cuAprilTagsHandle h, const b200AprilTagsFrame_
 int b200AprilTagsCollectBatchHost(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out,
                                   uint32_t *counts);
 
-/* Asynchronous halves of DetectBatch for pipelined callers (bench, multi-stream): Enqueue launches the kernels
- * and the D2H copy on `stream`; Collect synchronises and unpacks into host arrays. */
+/* Asynchronous halves of DetectBatch for pipelined callers: Enqueue launches the kernels and the D2H copy of the results on
+ * `stream` and returns; Collect waits for the OLDEST batch in flight and unpacks it into host arrays.  Up to TWO batches may be
+ * in flight per handle, both on the same stream (the second one is queued behind the first: the host side of a call -- frame
+ * table, graph launch, unpacking -- then overlaps the previous batch's kernels instead of leaving the GPU idle between calls).
+ * B200AT_ERR_INVALID_ARG when two batches are already in flight, when the stream differs from the one in flight, or with stage
+ * timing enabled and a batch in flight.  b200AprilTagsReadBuffer shows the workspace of the batch queued LAST. */
 int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n_frames,
                               cudaStream_t stream);
 int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out,

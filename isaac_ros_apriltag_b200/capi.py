@@ -207,19 +207,30 @@ class Detector:
             arr[i].pitch = int(pitch[i] if hasattr(pitch, "__len__") else pitch)
         return arr
 
-    def enqueue(self, ptrs, pitch, stream=0):
-        fr = self._frames(ptrs, pitch)
-        rc = lib().b200AprilTagsEnqueueBatch(self.h, fr, len(ptrs), C.c_void_p(int(stream)))
+    def frame_table(self, ptrs, pitch):
+        """The ctypes frame array of a batch (device addresses + pitch); enqueue() accepts it in place of the address list, so a
+        caller that processes the same buffers again and again builds it once."""
+        return self._frames(ptrs, pitch)
+
+    def enqueue(self, ptrs, pitch=0, stream=0):
+        """Queues one batch on `stream` (b200AprilTagsEnqueueBatch; up to two may be in flight, same stream).  `ptrs`: device
+        addresses of the frames' first pixels, or a frame_table()."""
+        fr = ptrs if isinstance(ptrs, C.Array) else self._frames(ptrs, pitch)
+        rc = lib().b200AprilTagsEnqueueBatch(self.h, fr, len(fr), C.c_void_p(int(stream)))
         if rc != 0:
             raise B200ATError(rc, "b200AprilTagsEnqueueBatch")
-        self._n = len(ptrs)
+        self._dev_q = getattr(self, "_dev_q", []) + [(len(fr), fr)]
 
-    def collect(self, strict=True):
+    def collect(self, strict=True, copy=True):
+        """Waits for the oldest batch queued with enqueue() and returns its detections (list of DET_DTYPE arrays; copy=False:
+        views into a buffer that the next collect() overwrites)."""
+        n, _keep = self._dev_q.pop(0)
         rc = lib().b200AprilTagsCollectBatch(self.h, self._dets.ctypes.data, None, self._counts.ctypes.data)
         if rc != 0 and (strict or rc != 5):
             raise B200ATError(rc, "b200AprilTagsCollectBatch")
-        n = self._n
-        return [self._dets[i, :self._counts[i]].copy() for i in range(n)]
+        if copy:
+            return [self._dets[i, :self._counts[i]].copy() for i in range(n)]
+        return [self._dets[i, :self._counts[i]] for i in range(n)]
 
     def detect_device(self, ptrs, pitch, stream=0, strict=True):
         """ptrs: device addresses of the frames' first pixels.  Returns a list (per frame) of DET_DTYPE arrays."""

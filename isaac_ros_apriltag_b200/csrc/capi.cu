@@ -116,8 +116,25 @@ struct cuAprilTagsHandle_st {
   uint32_t max_batch = 1;
   std::vector<void *> dev_allocs;
   unsigned long long *dev_codes[B200AT_MAX_FAMILIES] = {};
-  // pinned host mirrors
-  FrameDesc *h_frames = nullptr;
+  // Device-pointer entry points: up to TWO batches may be queued (b200AprilTagsEnqueueBatch twice before the first
+  // b200AprilTagsCollectBatch, same stream), so that the host side of a call -- frame table, graph launch, copying the results
+  // out -- overlaps the previous batch's kernels instead of leaving the GPU idle between calls.  Each slot has its own pinned
+  // frame table / result buffers, its own cached CUDA graph (the graph bakes those host addresses in) and a completion event.
+  struct DevSlot {
+    FrameDesc *h_frames = nullptr;
+    b200AprilTagsDetection_t *h_out = nullptr;
+    uint32_t *h_out_count = nullptr;
+    uint32_t *h_counters = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_n = 0;
+    int graph_fast = -1, graph_enc = -1;
+    cudaStream_t graph_stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint32_t n = 0;
+    int launches = 0;
+  } dslot[2];
+  uint64_t dev_enq = 0, dev_col = 0;  // batches queued / collected (slot = counter & 1)
+  // results of the batch collected last (point into its slot): cuAprilTagsDetect and b200AprilTagsReadBuffer read them
   b200AprilTagsDetection_t *h_out = nullptr;
   uint32_t *h_out_count = nullptr;
   uint32_t *h_counters = nullptr;
@@ -157,10 +174,6 @@ struct cuAprilTagsHandle_st {
   cudaEvent_t ev_in = nullptr;  // orders the handle's own stream after the caller's legacy default stream (resolve_sync_stream)
   // CUDA graph of one whole batch (all stage launches, fork/join of the quad-fit streams, D2H): replayed when the same
   // (n, stream, alignment class, encoding) comes again, e.g. the one-frame-at-a-time node path
-  cudaGraphExec_t graph_exec = nullptr;
-  uint32_t graph_n = 0;
-  int graph_fast = -1, graph_enc = -1;
-  cudaStream_t graph_stream = nullptr;
   uint32_t plain_calls = 0;
   bool use_graph = true;
 };
@@ -187,7 +200,10 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->fetch_stream) cudaStreamSynchronize(h->fetch_stream);
   if (h->tail_stream) cudaStreamSynchronize(h->tail_stream);
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (auto &d : h->dslot) {
+    if (d.graph_exec) cudaGraphExecDestroy(d.graph_exec);
+    if (d.done) cudaEventDestroy(d.done);
+  }
   for (int i = 0; i < kQuadAux; i++) {
     if (h->lane_aux[i]) cudaStreamDestroy(h->lane_aux[i]);
     if (h->lane_join[i]) cudaEventDestroy(h->lane_join[i]);
@@ -195,10 +211,12 @@ void destroy_handle(cuAprilTagsHandle_st *h) {
   if (h->lane_fork) cudaEventDestroy(h->lane_fork);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   for (void *p : h->dev_allocs) cudaFree(p);
-  if (h->h_frames) cudaFreeHost(h->h_frames);
-  if (h->h_out) cudaFreeHost(h->h_out);
-  if (h->h_out_count) cudaFreeHost(h->h_out_count);
-  if (h->h_counters) cudaFreeHost(h->h_counters);
+  for (auto &d : h->dslot) {
+    if (d.h_frames) cudaFreeHost(d.h_frames);
+    if (d.h_out) cudaFreeHost(d.h_out);
+    if (d.h_out_count) cudaFreeHost(d.h_out_count);
+    if (d.h_counters) cudaFreeHost(d.h_counters);
+  }
   for (auto &c : h->calls) {
     if (c.frames_tab) cudaFreeHost(c.frames_tab);
     if (c.src_tab) cudaFreeHost(c.src_tab);
@@ -589,10 +607,17 @@ int b200AprilTagsCreate(cuAprilTagsHandle *out, uint32_t W, uint32_t H, const cu
   }
   if (rc == 0 && cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
 #undef ALLOC
-  if (rc == 0 && cudaMallocHost(&h->h_frames, sizeof(FrameDesc) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
-  if (rc == 0 && cudaMallocHost(&h->h_out, sizeof(b200AprilTagsDetection_t) * B * g.max_tags) != cudaSuccess) rc = B200AT_ERR_NOMEM;
-  if (rc == 0 && cudaMallocHost(&h->h_out_count, sizeof(uint32_t) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
-  if (rc == 0 && cudaMallocHost(&h->h_counters, sizeof(uint32_t) * CNT_N * kMaxChunks) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+  for (auto &d : h->dslot) {
+    if (rc == 0 && cudaMallocHost(&d.h_frames, sizeof(FrameDesc) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+    if (rc == 0 && cudaMallocHost(&d.h_out, sizeof(b200AprilTagsDetection_t) * B * g.max_tags) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+    if (rc == 0 && cudaMallocHost(&d.h_out_count, sizeof(uint32_t) * B) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+    if (rc == 0 && cudaMallocHost(&d.h_counters, sizeof(uint32_t) * CNT_N * kMaxChunks) != cudaSuccess) rc = B200AT_ERR_NOMEM;
+    if (rc == 0) memset(d.h_counters, 0, sizeof(uint32_t) * CNT_N * kMaxChunks);
+    if (rc == 0 && cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming) != cudaSuccess) rc = B200AT_ERR_CUDA;
+  }
+  h->h_out = h->dslot[0].h_out;
+  h->h_out_count = h->dslot[0].h_out_count;
+  h->h_counters = h->dslot[0].h_counters;
   if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
   for (int i = 0; i < kQuadAux && rc == 0; i++) {
     if (cudaStreamCreateWithFlags(&h->lane_aux[i], cudaStreamNonBlocking) != cudaSuccess) rc = B200AT_ERR_CUDA;
@@ -645,10 +670,11 @@ int b200AprilTagsSetRectification(cuAprilTagsHandle h, const b200AprilTagsRectif
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  if (h->graph_exec) {  // the cached graph was captured without / with another pre-stage
-    cudaGraphExecDestroy(h->graph_exec);
-    h->graph_exec = nullptr;
-  }
+  for (auto &d : h->dslot)
+    if (d.graph_exec) {  // the cached graphs were captured without / with another pre-stage
+      cudaGraphExecDestroy(d.graph_exec);
+      d.graph_exec = nullptr;
+    }
   Workspace &ws = h->ws;
   const Geo &g = ws.g;
   int rc = B200AT_OK;
@@ -998,69 +1024,79 @@ static int enqueue_view(cuAprilTagsHandle h, Workspace v, const b200AprilTagsFra
 
 int b200AprilTagsEnqueueBatch(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32_t n, cudaStream_t stream) {
   if (!h || !frames || n == 0 || n > h->max_batch) return B200AT_ERR_INVALID_ARG;
-  if (h->in_flight || h->calls[0].active || h->calls[1].active) return B200AT_ERR_INVALID_ARG;  // one workspace: collect what is in flight first
+  if (h->calls[0].active || h->calls[1].active) return B200AT_ERR_INVALID_ARG;  // one workspace: collect the host calls in flight first
+  // up to two device batches in flight, on ONE stream (stream order is what makes the reuse of the workspace safe); with stage
+  // timing on, one (the stage events are per handle)
+  const uint64_t queued = h->dev_enq - h->dev_col;
+  if (queued >= 2 || (queued == 1 && (h->timing || stream != h->cur_stream))) return B200AT_ERR_INVALID_ARG;
+  cuAprilTagsHandle_st::DevSlot &d = h->dslot[h->dev_enq & 1];
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
   int launches = h->launches;
   int fast = 1;
-  int rc = fill_frame_table(h, frames, n, h->h_frames, &fast);
+  int rc = fill_frame_table(h, frames, n, d.h_frames, &fast);
   if (rc == B200AT_OK) {
     h->ws.g.fast_align = fast;
     const bool graph_ok = h->use_graph && !h->timing && h->plain_calls >= 1;  // first call runs plain (lazy attribute setup)
-    if (graph_ok && h->graph_exec && h->graph_n == n && h->graph_fast == fast && h->graph_enc == h->ws.g.enc && h->graph_stream == stream) {
-      if (cudaGraphLaunch(h->graph_exec, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+    if (graph_ok && d.graph_exec && d.graph_n == n && d.graph_fast == fast && d.graph_enc == h->ws.g.enc && d.graph_stream == stream) {
+      if (cudaGraphLaunch(d.graph_exec, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+      launches = d.launches;
     } else if (graph_ok) {
-      if (h->graph_exec) {
-        cudaGraphExecDestroy(h->graph_exec);
-        h->graph_exec = nullptr;
+      if (d.graph_exec) {
+        cudaGraphExecDestroy(d.graph_exec);
+        d.graph_exec = nullptr;
       }
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
       if (e == cudaSuccess) {
-        rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, false, &launches, true);
+        rc = enqueue_core(h, frames, n, stream, d.h_frames, d.h_out, d.h_out_count, d.h_counters, false, &launches, true);
         e = cudaStreamEndCapture(stream, &graph);
-        if (rc == B200AT_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        if (rc == B200AT_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&d.graph_exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
-        if (rc == B200AT_OK && e == cudaSuccess && h->graph_exec) {
-          h->graph_n = n;
-          h->graph_fast = fast;
-          h->graph_enc = h->ws.g.enc;
-          h->graph_stream = stream;
-          if (cudaGraphLaunch(h->graph_exec, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
+        if (rc == B200AT_OK && e == cudaSuccess && d.graph_exec) {
+          d.graph_n = n;
+          d.graph_fast = fast;
+          d.graph_enc = h->ws.g.enc;
+          d.graph_stream = stream;
+          if (cudaGraphLaunch(d.graph_exec, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
         } else {
           // capture not possible in this context: fall back to plain launches from now on
           cudaGetLastError();
           h->use_graph = false;
-          h->graph_exec = nullptr;
-          rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches, true);
+          d.graph_exec = nullptr;
+          rc = enqueue_core(h, frames, n, stream, d.h_frames, d.h_out, d.h_out_count, d.h_counters, h->timing, &launches, true);
         }
       } else {
         cudaGetLastError();
         h->use_graph = false;
-        rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches, true);
+        rc = enqueue_core(h, frames, n, stream, d.h_frames, d.h_out, d.h_out_count, d.h_counters, h->timing, &launches, true);
       }
     } else {
-      rc = enqueue_core(h, frames, n, stream, h->h_frames, h->h_out, h->h_out_count, h->h_counters, h->timing, &launches, true);
+      rc = enqueue_core(h, frames, n, stream, d.h_frames, d.h_out, d.h_out_count, d.h_counters, h->timing, &launches, true);
       h->plain_calls++;
     }
   }
+  if (rc == B200AT_OK && cudaEventRecord(d.done, stream) != cudaSuccess) rc = B200AT_ERR_CUDA;
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != B200AT_OK) return rc;
-  h->launches = launches;
+  d.launches = launches;
+  d.n = n;
   h->cur_stream = stream;
-  h->cur_n = n;
+  h->dev_enq++;
   h->in_flight = true;
   return B200AT_OK;
 }
 
 int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *dets_out, cuAprilTagsID_t *ids_out, uint32_t *counts) {
-  if (!h || !h->in_flight) return B200AT_ERR_INVALID_ARG;
+  if (!h || h->dev_enq == h->dev_col) return B200AT_ERR_INVALID_ARG;
+  cuAprilTagsHandle_st::DevSlot &d = h->dslot[h->dev_col & 1];  // the oldest batch in flight
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
-  cudaError_t e = cudaStreamSynchronize(h->cur_stream);
-  h->in_flight = false;
+  cudaError_t e = cudaEventSynchronize(d.done);
+  h->dev_col++;
+  h->in_flight = h->dev_enq != h->dev_col;
   if (e == cudaSuccess && h->timing) {
     for (int i = 0; i < B200AT_NUM_STAGES; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
   }
@@ -1069,19 +1105,24 @@ int b200AprilTagsCollectBatch(cuAprilTagsHandle h, b200AprilTagsDetection_t *det
     fprintf(stderr, "[b200apriltags] batch failed: %s\n", cudaGetErrorString(e));
     return B200AT_ERR_CUDA;
   }
+  h->h_out = d.h_out;
+  h->h_out_count = d.h_out_count;
+  h->h_counters = d.h_counters;
+  h->launches = d.launches;
+  h->cur_n = d.n;
   const uint32_t mt = h->ws.g.max_tags;
-  for (uint32_t i = 0; i < h->cur_n; i++) {
-    uint32_t c = h->h_out_count[i];
+  for (uint32_t i = 0; i < d.n; i++) {
+    uint32_t c = d.h_out_count[i];
     if (c > mt) c = mt;
     if (counts) counts[i] = c;
-    if (dets_out) memcpy(dets_out + (size_t)i * mt, h->h_out + (size_t)i * mt, sizeof(b200AprilTagsDetection_t) * c);
+    if (dets_out) memcpy(dets_out + (size_t)i * mt, d.h_out + (size_t)i * mt, sizeof(b200AprilTagsDetection_t) * c);
     if (ids_out)
-      for (uint32_t k = 0; k < c; k++) to_id_struct(h->h_out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
+      for (uint32_t k = 0; k < c; k++) to_id_struct(d.h_out[(size_t)i * mt + k], ids_out + (size_t)i * mt + k);
   }
   uint32_t agg[CNT_N];
-  sum_counters(h->h_counters, agg);
+  sum_counters(d.h_counters, agg);
   h->last_status = agg[CNT_STATUS];
-  h->last_counters[0] = (uint64_t)h->launches;
+  h->last_counters[0] = (uint64_t)d.launches;
   h->last_counters[1] = agg[CNT_POINTS];
   h->last_counters[2] = agg[CNT_CLUSTERS];
   h->last_counters[3] = agg[CNT_QUADS];

@@ -86,6 +86,26 @@ def test_emulated_host_entry_point_matches_device_entry_point(pu):
     det.close()
 
 
+def test_emulated_two_device_batches_in_flight(pu):
+    """Two b200AprilTagsEnqueueBatch calls before the first CollectBatch: per-slot result buffers, oldest batch collected first."""
+    from isaac_ros_apriltag_b200 import capi
+    frames = np.stack([small_frame(40 + i, 322, 242, [("tag36h11", 20 + i)], side=(60, 110)) for i in range(6)])
+    det = capi.Detector(322, 242, encoding="mono8", max_batch=2, max_tags=16)
+    t, ptrs, pitch = pu.upload(frames)
+    want = [det.detect_device(ptrs[2 * k:2 * k + 2], pitch, 0) for k in range(3)]
+    det.enqueue(ptrs[0:2], pitch, 0)
+    det.enqueue(ptrs[2:4], pitch, 0)
+    with pytest.raises(capi.B200ATError):
+        det.enqueue(ptrs[4:6], pitch, 0)
+    got = [det.collect()]
+    det.enqueue(ptrs[4:6], pitch, 0)
+    got += [det.collect(), det.collect()]
+    for k in range(3):
+        for a, b in zip(got[k], want[k]):
+            assert a.tobytes() == b.tobytes() and len(a) == 1
+    det.close()
+
+
 @pytest.mark.parametrize("enc,dec", [("bgr8", 2.0), ("mono8", 2.0), ("rgba8", 3.0)])
 def test_emulated_sparse_host_path(pu, enc, dec, monkeypatch):
     """Sparse staging of the host entry point (only every f-th row by DMA, the rows around the quads fetched on demand): same

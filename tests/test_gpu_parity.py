@@ -432,6 +432,39 @@ def test_cuda_graph_replay_matches_plain_launches(pu):
     ref.close()
 
 
+def test_two_device_batches_in_flight(pu):
+    """b200AprilTagsEnqueueBatch twice before the first CollectBatch (same stream): the second batch queues behind the first on
+    the one workspace, each has its own pinned result buffers and cached graph; results equal the synchronous calls', in order.
+    A third batch, or another stream, is refused while two / one are in flight."""
+    needs_real_gpu(pu)
+    import torch
+    from isaac_ros_apriltag_b200 import capi, synth
+    frames, truths, K, ts, fams = synth.make_config_frames("C1", 6)
+    H, W = frames.shape[1:]
+    det = capi.Detector(W, H, families=fams, encoding="mono8", max_batch=2, max_tags=64)
+    t, ptrs, pitch = pu.upload(frames)
+    st, st2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    want = [det.detect_device(ptrs[2 * k:2 * k + 2], pitch, st.cuda_stream) for k in range(3)]
+    for rounds in range(3):  # plain launches, capture, replay -- per slot
+        got = []
+        det.enqueue(ptrs[0:2], pitch, st.cuda_stream)
+        det.enqueue(ptrs[2:4], pitch, st.cuda_stream)
+        with pytest.raises(capi.B200ATError):
+            det.enqueue(ptrs[4:6], pitch, st.cuda_stream)   # two already in flight
+        got.append(det.collect())
+        with pytest.raises(capi.B200ATError):
+            det.enqueue(ptrs[4:6], pitch, st2.cuda_stream)  # another stream while one is in flight
+        det.enqueue(ptrs[4:6], pitch, st.cuda_stream)
+        got.append(det.collect())
+        got.append(det.collect())
+        for k in range(3):
+            for a, b in zip(got[k], want[k]):
+                assert a.tobytes() == b.tobytes(), (rounds, k)
+    assert sum(len(x) for w in want for x in w) >= 6
+    det.close()
+
+
 def test_bench_workload_frames_match_oracle(pu):
     """The 32 distinct frames bench.py tiles into its 256-frame batch (C2, bgr8): tag IDs and Hamming distance exact,
     corners / centre within TOL_CORNER_PX, pose within tolerance, for every frame, through the batch entry point."""

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r04u_pytest_gpu.log 2>&1; tail -3 gpurun_out/r04u_pytest_gpu.log
-bash tools/gpu_latency.sh r04u | tail -32
-B200AT_TUNE_CONFIGS=";" timeout 600 python tools/gpu_tune.py --device-only > gpurun_out/r04u_tune.jsonl 2>/dev/null; python tools/tune_report.py gpurun_out/r04u_tune.jsonl | head -5
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r04x_pytest_gpu.log 2>&1; tail -3 gpurun_out/r04x_pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r04x_bench.json 2> gpurun_out/r04x_bench.err; tail -2 gpurun_out/r04x_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/r04x_bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['stages_ms_per_step'], d['latency_720p'], d['gpu_launches'])"
