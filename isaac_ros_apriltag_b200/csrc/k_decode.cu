@@ -363,65 +363,6 @@ __device__ __forceinline__ void refine_edges_warp(const FitParams &fp, const Fra
   refine_corners(lines, p);
 }
 
-// ---- a12, opt-in variant (decode_pair=1): refine_edges with two short edges per pass ----
-// one sample point of an edge: search along the normal for the strongest step (returns 0 if no pixel pair qualified)
-__device__ __forceinline__ int refine_sample(const FrameDesc &fd, int width, int height, int bpp, int o1, int o2, bool is_bgr, float pax,
-                                             float pay, float pbx, float pby, double nx, double ny, int s, int nsamples, double range,
-                                             int nsteps, double *bestx, double *besty) {
-  double alpha = (1.0 + s) / (nsamples + 1);
-  double x0 = alpha * pax + (1 - alpha) * pbx;
-  double y0 = alpha * pay + (1 - alpha) * pby;
-  double Mn = 0, Mcount = 0;
-  // the pixel gathers of 8 steps are issued together (independent loads), then consumed in step order
-  for (int k0 = 0; k0 < nsteps; k0 += 8) {
-    int g1[8], g2[8];
-    bool okk[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int k = k0 + u;
-      const double n = -range + 0.25 * k;
-      const double grange = 1;
-      const int x1 = (int)(x0 + (n + grange) * nx);
-      const int y1 = (int)(y0 + (n + grange) * ny);
-      const int x2 = (int)(x0 + (n - grange) * nx);
-      const int y2 = (int)(y0 + (n - grange) * ny);
-      okk[u] = k < nsteps && !(x1 < 0 || x1 >= width || y1 < 0 || y1 >= height) && !(x2 < 0 || x2 >= width || y2 < 0 || y2 >= height);
-      // unconditional loads from clamped (always valid) coordinates keep the 16 gathers independent
-      g1[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x1 : 0, okk[u] ? y1 : 0);
-      g2[u] = gray_at_bf(fd.ptr, fd.pitch, bpp, o1, o2, is_bgr, okk[u] ? x2 : 0, okk[u] ? y2 : 0);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      if (!okk[u] || g1[u] < g2[u]) continue;
-      const double n = -range + 0.25 * (k0 + u);
-      const double weight = (double)((g2[u] - g1[u]) * (g2[u] - g1[u]));
-      Mn += weight * n;  // integer-valued multiples of 0.25: exact, order independent
-      Mcount += weight;
-    }
-  }
-  if (Mcount == 0) return 0;
-  double n0 = Mn / Mcount;
-  *bestx = x0 + n0 * nx;
-  *besty = y0 + n0 * ny;
-  return 1;
-}
-
-// line through the refined sample points of one edge: centroid + normal direction (float trigonometry as upstream)
-__device__ __forceinline__ void refine_line(double Mx, double My, double Mxx, double Mxy, double Myy, double N, double line[4]) {
-  double Ex = Mx / N, Ey = My / N;
-  double Cxx = Mxx / N - Ex * Ex;
-  double Cxy = Mxy / N - Ex * Ey;
-  double Cyy = Myy / N - Ey * Ey;
-  // atan2f / cosf / sinf of the C library: evaluated in double and rounded once to float
-  float th = (float)atan2((double)(float)(-2 * Cxy), (double)(float)(Cyy - Cxx));
-  double normal_theta = .5 * th;
-  float nth = (float)normal_theta;
-  line[0] = Ex;
-  line[1] = Ey;
-  line[2] = (double)(float)cos((double)nth);
-  line[3] = (double)(float)sin((double)nth);
-}
-
 // ---- a13: homography of the (refined) corners; false = quad dropped (singular system / zero determinant) ----
 __device__ __forceinline__ bool quad_homography_warp(const float p[4][2], double H[9]) {
   if (!homography_compute2_warp(p, H)) return false;
