@@ -1421,14 +1421,25 @@ int host_enqueue(cuAprilTagsHandle h, const b200AprilTagsFrame_t *frames, uint32
     uint8_t *slot_base = h->d_stage + (size_t)slot * h->stage_sub * h->stage_pitch * g.H;
     cudaError_t e = cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0);  // staging slot free again (no-op before its first use)
     if (sparse && sparse_debug && e == cudaSuccess) e = cudaMemsetAsync(slot_base, 0xA5, (size_t)m * h->stage_pitch * g.H, h->copy_stream);
-    for (uint32_t q = 0; q < m && e == cudaSuccess; q++) {
+    for (uint32_t q = 0; q < m && e == cudaSuccess;) {
       uint8_t *dst = slot_base + (size_t)q * h->stage_pitch * g.H;
-      // rows 0, f, 2f, ... (all rows on the full-copy path)
-      e = cudaMemcpy2DAsync(dst, h->stage_pitch * row_step, frames[i0 + q].ptr, frames[i0 + q].pitch * row_step, row, rows_dma,
+      // rows 0, f, 2f, ... (all rows on the full-copy path).  Frames that follow each other in the caller's memory (one allocation
+      // for the batch) go out as ONE 2-D copy: with H a multiple of the row step the row pattern continues across the frame
+      // boundary on both sides.  (Measured: 256 copies of 540 rows 51.4 GB/s, 4 copies of 34,560 rows 55.2 GB/s = the rate of a
+      // contiguous copy on the same box.)
+      uint32_t cnt = 1;
+      if (g.H % row_step == 0)
+        while (q + cnt < m && frames[i0 + q + cnt].pitch == frames[i0 + q].pitch &&
+               (const uint8_t *)frames[i0 + q + cnt].ptr == (const uint8_t *)frames[i0 + q].ptr + (size_t)cnt * frames[i0 + q].pitch * g.H)
+          cnt++;
+      e = cudaMemcpy2DAsync(dst, h->stage_pitch * row_step, frames[i0 + q].ptr, frames[i0 + q].pitch * row_step, row, (size_t)rows_dma * cnt,
                             cudaMemcpyHostToDevice, h->copy_stream);
-      call.dma_bytes += (uint64_t)row * rows_dma;
-      dframes[q].ptr = dst;
-      dframes[q].pitch = h->stage_pitch;
+      call.dma_bytes += (uint64_t)row * rows_dma * cnt;
+      for (uint32_t u = 0; u < cnt; u++) {
+        dframes[q + u].ptr = slot_base + (size_t)(q + u) * h->stage_pitch * g.H;
+        dframes[q + u].pitch = h->stage_pitch;
+      }
+      q += cnt;
     }
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_copied[slot], h->copy_stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, h->ev_copied[slot], 0);
