@@ -239,10 +239,15 @@ class Detector:
 
     def detect_host(self, frames, strict=True):
         """frames: (n, H, W[, C]) uint8 numpy array in host memory (H2D copies happen inside the call)."""
-        frames = np.ascontiguousarray(frames, np.uint8)
-        n = frames.shape[0]
-        pitch = frames.strides[1]
-        fr = self._frames([frames[i].ctypes.data for i in range(n)], pitch)
+        if isinstance(frames, (list, tuple)):  # separately allocated frames (each C-contiguous), e.g. one buffer per camera
+            frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+            n = len(frames)
+            fr = self._frames([f.ctypes.data for f in frames], [f.strides[0] for f in frames])
+        else:
+            frames = np.ascontiguousarray(frames, np.uint8)
+            n = frames.shape[0]
+            pitch = frames.strides[1]
+            fr = self._frames([frames[i].ctypes.data for i in range(n)], pitch)
         dets = np.zeros((n, self.max_tags), DET_DTYPE)
         counts = np.zeros(n, np.uint32)
         rc = lib().b200AprilTagsDetectBatchHost(self.h, fr, n, dets.ctypes.data, None, counts.ctypes.data)

@@ -83,6 +83,16 @@ def test_emulated_host_entry_point_matches_device_entry_point(pu):
     got = det.detect_host(bgr)   # 5 frames through a 2-frame workspace: sub-batches + staging slots
     for a, b in zip(got, want):
         assert a.tobytes() == b.tobytes() and len(a) == 1
+    # separately allocated frames (not contiguous in the caller's memory: one DMA per frame instead of one per run of frames)
+    pad = [np.empty((242 * 322 * 3 + 64 * (i + 1),), np.uint8) for i in range(5)]
+    sep = []
+    for i in range(5):
+        v = pad[i][64 * (i + 1):].reshape(242, 322, 3)
+        v[...] = bgr[i]
+        sep.append(v)
+    got = det.detect_host(sep)
+    for a, b in zip(got, want):
+        assert a.tobytes() == b.tobytes() and len(a) == 1
     det.close()
 
 

@@ -657,6 +657,17 @@ def test_sparse_host_path_matches_full_copy(pu, config, enc, monkeypatch):
                 for i in range(n):
                     assert got4[i].tobytes() == want[i].tobytes(), (sub, mode, i)
     monkeypatch.delenv("B200AT_HOST_SUB")
+    # separately allocated (pinned) frames: not contiguous in the caller's memory, so every frame gets its own DMA instead of one
+    # 2-D copy per run of frames
+    if not pu.EMU:
+        import torch
+        keep = [torch.from_numpy(frames[i].copy()).pin_memory() for i in range(n)]
+        for mode in ("0", "1"):
+            monkeypatch.setenv("B200AT_SPARSE_H2D", mode)
+            got5 = det.detect_host([k.numpy() for k in keep])
+            assert det.counters()["sparse_h2d"] == int(mode)
+            for i in range(n):
+                assert got5[i].tobytes() == want[i].tobytes(), (mode, i)
     monkeypatch.setenv("B200AT_SPARSE_H2D", "1")
     # frames in pageable memory: the call falls back to the full copy by itself
     if not pu.EMU:
