@@ -38,6 +38,21 @@ for tune in ("", "qf_exact=1", "ccl_tma=0", "qf_bucket_limit=3"):
         os.environ.pop("B200AT_HOST_SUB")
     det.close()
 os.environ.pop("B200AT_TUNE", None)
+# six frames (more than kRefineCtaFrames: the warp-per-quad refine kernel), two device batches in flight on one stream
+frames6 = np.stack([synth.make_frame(rng, 640, 480, [("tag36h11", 20 + i)], side_px=(60, 140))[0] for i in range(6)])
+t6 = torch.from_numpy(np.ascontiguousarray(np.repeat(frames6[:, :, :, None], 3, axis=3))).cuda()
+fb6 = t6[0].numel()
+det = capi.Detector(640, 480, encoding="bgr8", max_batch=6, max_tags=64)
+st = torch.cuda.Stream()
+p6 = [t6.data_ptr() + i * fb6 for i in range(6)]
+sync = det.detect_device(p6, 640 * 3, st.cuda_stream)
+for _ in range(3):  # plain, capture, replay on both slots
+    det.enqueue(p6, 640 * 3, st.cuda_stream)
+    det.enqueue(p6[:3], 640 * 3, st.cuda_stream)
+    a, b = det.collect(), det.collect()
+print("six frames ids", [list(x["id"]) for x in sync], "two in flight ok",
+      all(x.tobytes() == y.tobytes() for x, y in zip(a, sync)) and all(x.tobytes() == y.tobytes() for x, y in zip(b, sync[:3])), "status", det.status())
+det.close()
 g, _ = synth.make_frame(rng, 751, 481, [("tag36h11", 17)], side_px=(60, 120))
 det = capi.Detector(751, 481, encoding="mono8", max_batch=1, max_tags=64, quad_sigma=0.8)
 t2 = torch.from_numpy(g).cuda()
