@@ -96,6 +96,20 @@ def test_emulated_host_entry_point_matches_device_entry_point(pu):
     det.close()
 
 
+def test_emulated_refine_kernels_agree(pu):
+    """Batches of at most four frames refine with k_refine_cta (one CTA per quad, one warp per edge), larger ones with the
+    warp-per-quad kernel: the same frames must give byte-identical detections either way."""
+    from isaac_ros_apriltag_b200 import capi
+    frames = np.stack([small_frame(70 + i, 322, 242, [("tag36h11", 40 + i)], side=(60, 110)) for i in range(6)])
+    det = capi.Detector(322, 242, encoding="mono8", max_batch=6, max_tags=16)
+    t, ptrs, pitch = pu.upload(frames)
+    big = det.detect_device(ptrs, pitch, 0)                                               # six frames: warp per quad
+    small = det.detect_device(ptrs[:3], pitch, 0) + det.detect_device(ptrs[3:], pitch, 0)  # three frames: CTA per quad
+    for a, b in zip(big, small):
+        assert a.tobytes() == b.tobytes() and len(a) == 1
+    det.close()
+
+
 def test_emulated_two_device_batches_in_flight(pu):
     """Two b200AprilTagsEnqueueBatch calls before the first CollectBatch: per-slot result buffers, oldest batch collected first."""
     from isaac_ros_apriltag_b200 import capi

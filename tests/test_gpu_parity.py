@@ -432,6 +432,22 @@ def test_cuda_graph_replay_matches_plain_launches(pu):
     ref.close()
 
 
+def test_refine_kernels_agree(pu):
+    """Batches of at most four frames refine with k_refine_cta (one CTA per quad, one warp per edge), larger ones with the
+    warp-per-quad kernel: the same frames must give byte-identical detections either way."""
+    from isaac_ros_apriltag_b200 import capi, synth
+    frames, truths, K, ts, fams = synth.make_config_frames("C1", 6)
+    H, W = frames.shape[1:]
+    det = capi.Detector(W, H, families=fams, encoding="mono8", max_batch=6, max_tags=64)
+    t, ptrs, pitch = pu.upload(frames)
+    big = det.detect_device(ptrs, pitch, pu.current_stream())
+    small = det.detect_device(ptrs[:3], pitch, pu.current_stream()) + det.detect_device(ptrs[3:], pitch, pu.current_stream())
+    for a, b in zip(big, small):
+        assert a.tobytes() == b.tobytes()
+    assert sum(len(x) for x in big) >= 6
+    det.close()
+
+
 def test_two_device_batches_in_flight(pu):
     """b200AprilTagsEnqueueBatch twice before the first CollectBatch (same stream): the second batch queues behind the first on
     the one workspace, each has its own pinned result buffers and cached graph; results equal the synchronous calls', in order.
